@@ -1,0 +1,15 @@
+"""hite_b200 -- Blackwell-native dynamic boundary adjustment for HiTE.
+
+Python host side of ``libhite_b200.so`` (hand-written sm_100a CUDA kernels behind a C-ABI,
+``include/hite_b200.h``).  Mirrors the reference's operator interface for this path:
+
+* ``hite_b200.boundary.flank_region_align_v5``        (reference module/Util.py:8032)
+* ``hite_b200.boundary.run_find_members_v8``          (reference module/Util.py:10439)
+* ``hite_b200.boundary.is_TE_from_align_file``        (reference module/Util.py:10407)
+* ``hite_b200.boundary.determine_repeat_boundary_v5`` (reference module/Util.py:4637)
+
+There is no CPU fallback: without the built extension and a CUDA device every entry point raises.
+"""
+__version__ = "0.1.0"
+
+from ._lib import HiteB200Error, Context, lib_path  # noqa: F401

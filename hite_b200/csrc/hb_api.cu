@@ -1,0 +1,140 @@
+// hite_b200 -- C-ABI entry points (include/hite_b200.h).  Host-side C++ only; the kernels live in
+// hb_vote.cu / hb_pack.cu / hb_index.cu / hb_extend.cu / hb_msa.cu.
+#include "hb_ctx.cuh"
+
+extern "C" size_t hb_vote_match_entry_size();
+extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
+                                      uint32_t* d_planes, void* d_matches, const uint8_t* d_cands,
+                                      uint8_t* d_cons, HbVoteCall* d_calls, cudaStream_t stream);
+
+static std::string g_last_global_error;
+
+extern "C" int hb_version(void) { return 100; }
+
+extern "C" int hb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* hb_last_error(hb_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_last_global_error.c_str();
+}
+
+extern "C" int hb_create(int device, hb_ctx** out) {
+    if (!out) return HB_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        g_last_global_error = "hite_b200: no CUDA device available (there is no CPU fallback)";
+        return HB_ENODEV;
+    }
+    if (device < 0 || device >= n) { g_last_global_error = "hite_b200: bad device ordinal"; return HB_EINVAL; }
+    hb_ctx* ctx = new hb_ctx();
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_last_global_error = cudaGetErrorString(e); delete ctx; return HB_ECUDA; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_last_global_error = cudaGetErrorString(e); delete ctx; return HB_ECUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        g_last_global_error = "hite_b200: kernels are built for sm_100a only; found compute capability " +
+                              std::to_string(prop.major) + "." + std::to_string(prop.minor);
+        delete ctx;
+        return HB_ENODEV;
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_last_global_error = cudaGetErrorString(e); delete ctx; return HB_ECUDA;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return HB_OK;
+}
+
+extern "C" void hb_destroy(hb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (HbDevBuf* b : {&ctx->v_tasks, &ctx->v_raw, &ctx->v_clean, &ctx->v_planes, &ctx->v_matches, &ctx->v_cands,
+                        &ctx->v_cons, &ctx->v_calls})
+        b->release();
+    ctx->h_stage.release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int hb_get_timing(hb_ctx* ctx, hb_timing* out) {
+    if (!ctx || !out) return HB_EINVAL;
+    *out = ctx->timing;
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_ascii, const uint64_t* mat_off,
+                                const int32_t* R, const int32_t* C, const uint8_t* cand_ascii,
+                                const uint64_t* cand_off, int te_type, int plant, int result_type,
+                                hb_call* calls, uint8_t* cons_out, uint64_t cons_cap) {
+    if (!ctx) return HB_EINVAL;
+    if (n == 0) return HB_OK;
+    if (!rows_ascii || !mat_off || !R || !C || !cand_ascii || !cand_off || !calls || !cons_out)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: null argument");
+    if (te_type != HB_TE_TIR) return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: only HB_TE_TIR is implemented");
+    static_assert(sizeof(hb_call) == sizeof(HbVoteCall), "hb_call layout");
+    cudaSetDevice(ctx->device);
+    std::vector<HbVoteTask> tasks(n);
+    uint64_t raw_total = 0, col_total = 0, match_total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (R[i] <= 0 || C[i] <= 0 || C[i] >= (1 << 26) || R[i] >= 65535)
+            return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: matrix " + std::to_string(i) + " has unsupported shape");
+        HbVoteTask& t = tasks[i];
+        memset(&t, 0, sizeof(t));
+        t.raw_off = mat_off[i];
+        t.clean_off = mat_off[i];
+        t.plane_off = col_total * 24;
+        t.cons_off = col_total;
+        t.match_off = match_total;
+        t.cand_off = cand_off[i];
+        t.cand_len = (int32_t)(cand_off[i + 1] - cand_off[i]);
+        t.R = R[i]; t.C = C[i];
+        t.te_type = te_type; t.plant = plant; t.result_type = result_type; t.raw_is_ascii = 1;
+        raw_total = mat_off[i] + (uint64_t)R[i] * C[i] > raw_total ? mat_off[i] + (uint64_t)R[i] * C[i] : raw_total;
+        col_total += (uint64_t)C[i];
+        match_total += 2ull * ((uint64_t)C[i] + 2);
+    }
+    if (cons_cap < col_total) return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: cons_cap < sum(C)");
+    const uint64_t cand_total = cand_off[n];
+    HB_CUDA_OK(ctx->v_tasks.ensure(sizeof(HbVoteTask) * n));
+    HB_CUDA_OK(ctx->v_raw.ensure(raw_total));
+    HB_CUDA_OK(ctx->v_clean.ensure(raw_total));
+    HB_CUDA_OK(ctx->v_planes.ensure(col_total * 24 * sizeof(uint32_t)));
+    HB_CUDA_OK(ctx->v_matches.ensure(match_total * hb_vote_match_entry_size()));
+    HB_CUDA_OK(ctx->v_cands.ensure(cand_total + 1));
+    HB_CUDA_OK(ctx->v_cons.ensure(col_total));
+    HB_CUDA_OK(ctx->v_calls.ensure(sizeof(HbVoteCall) * n));
+    cudaStream_t s = ctx->stream;
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->v_tasks.p, tasks.data(), sizeof(HbVoteTask) * n, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->v_raw.p, rows_ascii, raw_total, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->v_cands.p, cand_ascii, cand_total, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemsetAsync(ctx->v_calls.p, 0, sizeof(HbVoteCall) * n, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    HB_CUDA_OK(hb_vote_launch(ctx->v_tasks.as<HbVoteTask>(), (int)n, ctx->v_raw.as<uint8_t>(), ctx->v_clean.as<uint8_t>(),
+                              ctx->v_planes.as<uint32_t>(), ctx->v_matches.p, ctx->v_cands.as<uint8_t>(),
+                              ctx->v_cons.as<uint8_t>(), ctx->v_calls.as<HbVoteCall>(), s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    HB_CUDA_OK(cudaMemcpyAsync(calls, ctx->v_calls.p, sizeof(HbVoteCall) * n, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaMemcpyAsync(cons_out, ctx->v_cons.p, col_total, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    hb_timing& tm = ctx->timing;
+    memset(&tm, 0, sizeof(tm));
+    cudaEventElapsedTime(&tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&tm.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&tm.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    tm.h2d_bytes = sizeof(HbVoteTask) * n + raw_total + cand_total;
+    tm.d2h_bytes = sizeof(HbVoteCall) * n + col_total;
+    tm.launches = 2;
+    return HB_OK;
+}

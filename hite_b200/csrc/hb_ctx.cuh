@@ -1,0 +1,65 @@
+// hite_b200 -- context object behind the C-ABI (host side, C++).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hite_b200.h"
+#include "hb_common.cuh"
+
+struct HbDevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct HbHostBuf {  // pinned staging
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct hb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[12] = {};
+    std::string err;
+    hb_timing timing = {};
+    // vote path buffers
+    HbDevBuf v_tasks, v_raw, v_clean, v_planes, v_matches, v_cands, v_cons, v_calls;
+    HbHostBuf h_stage;
+};
+
+inline int hb_fail(hb_ctx* ctx, const char* what, cudaError_t e, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+    if (ctx) ctx->err = buf;
+    return e == cudaErrorMemoryAllocation ? HB_ENOMEM : HB_ECUDA;
+}
+inline int hb_fail_msg(hb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}

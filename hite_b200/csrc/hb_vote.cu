@@ -1,0 +1,735 @@
+// hite_b200 -- kernel (iii): flank-copy MSA column voting + homology-window boundary search.
+//
+// Replaces, bit-exactly on the same aligned matrix, the reference's pure-Python
+//   remove_sparse_col_in_align_file   (module/Util.py:10344-10405)   -> hb_clean_kernel
+//   judge_boundary_v5  (TIR)          (module/Util.py:9145-9480)     -> hb_judge_kernel
+//   search_boundary_homo_v3           (module/Util.py:8887-9143)
+//   calculate_window_homology         (module/Util.py:8827-8885)
+//   TSDsearch_v5                      (module/Util.py:2460-2492)
+//
+// Layout in HBM (per candidate): the R x C matrix row-major (1 B/cell) for the row-wise work
+// (anchor search, TSD strings) and, for the <=101 full-length rows the judge keeps, six column
+// bit-planes P[sym][word][col] (row r = bit r&31 of word r>>5) so that every column statistic
+// is a popc and every "rows valid in this window" set is a ballot.  One warp per candidate;
+// no tensor cores (integer/bit work), no CPU fallback.
+#include "hb_common.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int CLEAN_THREADS = 256;
+constexpr int MAX_KEPT = 101;   // "len(...) > 100: break"  Util.py:9201
+
+// ------------------------------------------------------------------------------------------
+// warp helpers
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(HB_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(HB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(HB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(HB_FULL, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(HB_FULL, x, o);
+        if (lane >= o) x += t;
+    }
+    *total = __shfl_sync(HB_FULL, x, 31);
+    return x - v;
+}
+__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// Python slice bounds s[a:b] for a sequence of length n
+__device__ __forceinline__ void py_slice(int n, long long a, long long b, int* lo, int* hi) {
+    if (a < 0) { a += n; if (a < 0) a = 0; } else if (a > n) a = n;
+    if (b < 0) { b += n; if (b < 0) b = 0; } else if (b > n) b = n;
+    if (b < a) b = a;
+    *lo = (int)a; *hi = (int)b;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel A: sparse-column removal (Util.py:10344-10405).  One CTA per candidate.
+// keeps column 0 and C-1 unconditionally (the elif order at :10384-10387), drops a column iff
+// gaps > row_num/2 (float compare == 2*gaps > R).  Output: symbol codes, row stride C.
+__global__ void __launch_bounds__(CLEAN_THREADS)
+hb_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint8_t* __restrict__ raw,
+                uint8_t* __restrict__ clean, HbVoteCall* __restrict__ calls) {
+    const HbVoteTask t = tasks[blockIdx.x];
+    const int R = t.R, C = t.C;
+    const uint8_t* in = raw + t.raw_off;
+    uint8_t* out = clean + t.clean_off;
+    __shared__ int s_warp[CLEAN_THREADS / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < C; c0 += CLEAN_THREADS) {
+        const int c = c0 + tid;
+        int keep = 0;
+        if (c < C) {
+            int gaps = 0;
+            for (int r = 0; r < R; ++r) {
+                uint8_t ch = in[(size_t)r * C + c];
+                gaps += t.raw_is_ascii ? (ch == '-') : (ch == HB_SYM_GAP);
+            }
+            keep = (c == 0) || (c == C - 1) || !(2 * gaps > R);
+        }
+        const uint32_t bal = __ballot_sync(HB_FULL, keep);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < CLEAN_THREADS / 32; ++w) {
+            int v = s_warp[w];
+            if (w < wid) before += v;
+            total += v;
+        }
+        const int base = s_base;
+        const int pos = base + before + __popc(bal & lanemask_lt(lane));
+        if (keep) {
+            for (int r = 0; r < R; ++r) {
+                uint8_t ch = in[(size_t)r * C + c];
+                out[(size_t)r * C + pos] = t.raw_is_ascii ? (uint8_t)hb_sym_of_ascii(ch) : ch;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_base = base + total;
+        __syncthreads();
+    }
+    if (tid == 0) calls[blockIdx.x].clean_cols = s_base;
+}
+
+// ------------------------------------------------------------------------------------------
+// anchor search: HB-fnm (see oracle/fnm.py; stand-in for fuzzysearch.find_near_matches with
+// max_l_dist = 2, Util.py:9173-9174).  Bit-parallel Sellers/Myers over 32 lane chunks.
+struct Pattern {
+    uint32_t peq[5];
+    unsigned long long p0;   // symbols 0..15, 4 bits each
+    uint32_t p1;             // symbols 16..19
+    int m;
+    __device__ __forceinline__ int sym(int j) const {
+        return j < 16 ? (int)((p0 >> (4 * j)) & 15ull) : (int)((p1 >> (4 * (j - 16))) & 15u);
+    }
+};
+__device__ __forceinline__ void pattern_init(Pattern& P, const uint8_t* ascii, int m) {
+    P.m = m; P.p0 = 0; P.p1 = 0;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) P.peq[s] = 0;
+    for (int j = 0; j < m; ++j) {
+        int s = hb_sym_of_ascii(ascii[j]);
+        if (s == HB_SYM_GAP) s = HB_SYM_N;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) if (q == s) P.peq[q] |= 1u << j;
+        if (j < 16) P.p0 |= (unsigned long long)s << (4 * j); else P.p1 |= (uint32_t)s << (4 * (j - 16));
+    }
+}
+struct Myers {
+    uint32_t pv, mv; int score;
+    __device__ __forceinline__ void init(int m) { pv = m >= 32 ? 0xffffffffu : ((1u << m) - 1u); mv = 0; score = m; }
+    __device__ __forceinline__ void step(uint32_t eq, uint32_t top) {
+        uint32_t xv = eq | mv;
+        uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
+        uint32_t ph = mv | ~(xh | pv);
+        uint32_t mh = pv & xh;
+        if (ph & top) ++score; else if (mh & top) --score;
+        ph <<= 1; mh <<= 1;
+        pv = mh | ~(xv | ph);
+        mv = ph & xv;
+    }
+};
+struct Hist {  // last 32 non-gap symbols, most recent first
+    unsigned long long h0, h1;
+    __device__ __forceinline__ void init() { h0 = 0; h1 = 0; }
+    __device__ __forceinline__ void push(int s) { h1 = (h1 << 4) | (h0 >> 60); h0 = (h0 << 4) | (unsigned long long)s; }
+    __device__ __forceinline__ int back(int k) const {  // k = 1: most recent
+        return k <= 16 ? (int)((h0 >> (4 * (k - 1))) & 15ull) : (int)((h1 >> (4 * (k - 17))) & 15ull);
+    }
+};
+// smallest a with lev(p, s[a:e]) == dist  (oracle/fnm.py::_longest_start)
+__device__ int longest_start(const Pattern& P, const Hist& H, int e, int dist) {
+    const int m = P.m;
+    int maxk = m + dist; if (maxk > e) maxk = e;
+    int row[24], nw[24];
+    for (int k = 0; k <= maxk; ++k) row[k] = k;
+    for (int j = 1; j <= m; ++j) {
+        const int pj = P.sym(m - j);
+        nw[0] = j;
+        for (int k = 1; k <= maxk; ++k) {
+            int v = row[k] + 1;
+            v = min(v, nw[k - 1] + 1);
+            v = min(v, row[k - 1] + (pj != H.back(k)));
+            nw[k] = v;
+        }
+        for (int k = 0; k <= maxk; ++k) row[k] = nw[k];
+    }
+    for (int k = maxk; k >= 0; --k) if (row[k] == dist) return e - k;
+    return e;  // unreachable
+}
+
+struct Match { int a, e, d; };
+
+// One row: run both patterns over the ungapped row, emit (start,end,dist) of every end with
+// dist <= 2 into mlist[0..cap) / mlist[cap..2cap).  Returns via cnt[0], cnt[1] (smem).
+__device__ void anchor_scan_row(const uint8_t* __restrict__ row, int Cc, const Pattern& P1, const Pattern& P2,
+                                Match* __restrict__ mlist, int cap, int* cnt, int lane,
+                                int* ub_out, int* n_out) {
+    const int chunk = (Cc + 31) >> 5;
+    const int lo = min(Cc, lane * chunk), hi = min(Cc, lo + chunk);
+    int c_ng = 0;
+    for (int c = lo; c < hi; ++c) c_ng += (row[c] != HB_SYM_GAP);
+    int n;
+    const int ub = warp_excl_scan(c_ng, lane, &n);
+    *ub_out = ub; *n_out = n;
+    if (lane < 2) cnt[lane] = 0;
+    __syncwarp();
+    Myers M1, M2; M1.init(P1.m); M2.init(P2.m);
+    const uint32_t top1 = 1u << (P1.m - 1), top2 = 1u << (P2.m - 1);
+    Hist H; H.init();
+    // warm-up: the previous 40 (= 2m) non-gap symbols fully determine the DP column
+    uint8_t warm[40];
+    int nwarm = 0;
+    for (int c = lo - 1; c >= 0 && nwarm < 40; --c) { uint8_t s = row[c]; if (s != HB_SYM_GAP) warm[nwarm++] = s; }
+    for (int i = nwarm - 1; i >= 0; --i) {
+        int s = warm[i];
+        M1.step(P1.peq[s], top1); M2.step(P2.peq[s], top2); H.push(s);
+    }
+    int e = ub;
+    for (int c = lo; c < hi; ++c) {
+        int s = row[c];
+        if (s == HB_SYM_GAP) continue;
+        M1.step(P1.peq[s], top1); M2.step(P2.peq[s], top2); H.push(s);
+        ++e;
+        if (M1.score <= 2) {
+            int i = atomicAdd(&cnt[0], 1);
+            if (i < cap) { Match mt; mt.e = e; mt.d = M1.score; mt.a = longest_start(P1, H, e, M1.score); mlist[i] = mt; }
+        }
+        if (M2.score <= 2) {
+            int i = atomicAdd(&cnt[1], 1);
+            if (i < cap) { Match mt; mt.e = e; mt.d = M2.score; mt.a = longest_start(P2, H, e, M2.score); mlist[cap + i] = mt; }
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ unsigned long long match_key(const Match& m) {
+    // min over (dist, -(len), start); end carried in the low bits
+    return ((unsigned long long)m.d << 58) | ((unsigned long long)(63 - (m.e - m.a)) << 52) |
+           ((unsigned long long)m.a << 26) | (unsigned long long)m.e;
+}
+
+// best match of the first overlap-group (by start) -> its start
+__device__ int first_group_best_start(const Match* l, int n, int lane) {
+    int gs = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) gs = min(gs, l[i].a);
+    gs = warp_min(gs);
+    int ge = gs + 1;
+    for (;;) {
+        int ne = ge;
+        for (int i = lane; i < n; i += 32) if (l[i].a < ge) ne = max(ne, l[i].e);
+        ne = warp_max(ne);
+        if (ne == ge) break;
+        ge = ne;
+    }
+    unsigned long long k = ~0ull;
+    for (int i = lane; i < n; i += 32) if (l[i].a < ge) { unsigned long long q = match_key(l[i]); k = q < k ? q : k; }
+    k = warp_min_u64(k);
+    return (int)((k >> 26) & 0x3ffffffull);
+}
+// best match of the last overlap-group -> its end
+__device__ int last_group_best_end(const Match* l, int n, int lane) {
+    int ge = -1;
+    for (int i = lane; i < n; i += 32) ge = max(ge, l[i].e);
+    ge = warp_max(ge);
+    int gs = ge - 1;
+    for (;;) {
+        int ns = gs;
+        for (int i = lane; i < n; i += 32) if (l[i].e > gs) ns = min(ns, l[i].a);
+        ns = warp_min(ns);
+        if (ns == gs) break;
+        gs = ns;
+    }
+    unsigned long long k = ~0ull;
+    for (int i = lane; i < n; i += 32) if (l[i].e > gs) { unsigned long long q = match_key(l[i]); k = q < k ? q : k; }
+    k = warp_min_u64(k);
+    return (int)(k & 0x3ffffffull);
+}
+// column of the idx-th non-gap symbol of the row (lanes own [lo,hi) with ungapped base ub)
+__device__ int column_of_ungapped(const uint8_t* row, int Cc, int idx, int ub, int lane) {
+    const int chunk = (Cc + 31) >> 5;
+    const int lo = min(Cc, lane * chunk), hi = min(Cc, lo + chunk);
+    int col = -1, k = ub;
+    for (int c = lo; c < hi; ++c) {
+        if (row[c] == HB_SYM_GAP) continue;
+        if (k == idx) { col = c; break; }
+        ++k;
+    }
+    return warp_max(col);
+}
+
+// ------------------------------------------------------------------------------------------
+// bit-plane view of the kept rows
+struct Planes {
+    const uint32_t* p;   // P[sym][word][col]
+    int stride;          // C
+    int nw;              // words in use
+    int row_num;
+    uint32_t rowmask[4];
+    __device__ __forceinline__ uint32_t w(int sym, int word, int col) const {
+        return p[(size_t)(sym * 4 + word) * stride + col];
+    }
+    __device__ __forceinline__ int count(int sym, int col) const {
+        int c = 0;
+        for (int k = 0; k < nw; ++k) c += __popc(w(sym, k, col));
+        return c;
+    }
+};
+
+// collect <= 100 valid columns (gaps <= valid_col_threshold) scanning from `start` in direction
+// dir while lo_bound <= col < hi_bound  (Util.py:8924-8947, 8976-8999, 9036-9060, 9096-9120)
+__device__ int collect_valid(const Planes& P, int vthr, int start, int dir, int lo_bound, int hi_bound,
+                             int* vc, int lane) {
+    int n = 0;
+    for (int c0 = start; n < 100; c0 += 32 * dir) {
+        const int c = c0 + dir * lane;
+        const bool in = (c >= lo_bound && c < hi_bound);
+        const bool ok = in && (P.count(HB_SYM_GAP, c) <= vthr);
+        const uint32_t bal = __ballot_sync(HB_FULL, ok);
+        const int pos = n + __popc(bal & lanemask_lt(lane));
+        if (ok && pos < 100) vc[pos] = c;
+        n = min(100, n + __popc(bal));
+        // stop once the leading lane has left the range (ranges are contiguous in scan order)
+        const int cfirst = c0, clast = c0 + dir * 31;
+        const bool any_in = (dir > 0) ? (cfirst < hi_bound) : (cfirst >= lo_bound);
+        const bool last_in = (dir > 0) ? (clast < hi_bound) : (clast >= lo_bound);
+        if (!any_in || !last_in) break;
+    }
+    __syncwarp();
+    return n;
+}
+__device__ void reverse_list(int* vc, int n, int lane) {
+    for (int i = lane; i < n / 2; i += 32) { int t = vc[i]; vc[i] = vc[n - 1 - i]; vc[n - 1 - i] = t; }
+    __syncwarp();
+}
+
+// calculate_window_homology (Util.py:8827-8885); window columns are first + step*k, k < ncols
+__device__ int window_homology(const Planes& P, int first, int ncols, int step, double thr, int lane) {
+    uint32_t valid[4] = {0, 0, 0, 0};
+    int nv = 0;
+    for (int wd = 0; wd < P.nw; ++wd) {
+        int cnt = 0;
+        for (int k = 0; k < ncols; ++k) cnt += (P.w(HB_SYM_GAP, wd, first + step * k) >> lane) & 1u;
+        valid[wd] = __ballot_sync(HB_FULL, 2 * cnt <= ncols) & P.rowmask[wd];      // :8846
+        nv += __popc(valid[wd]);
+    }
+    if (nv < 2) return -1;                                                          // :8850
+    const double thr2 = thr - 0.1;
+    double total = 0.0;
+    int first_cand = -1;
+    for (int k0 = 0; k0 < ncols; k0 += 32) {
+        const int k = k0 + lane;
+        double ratio = 0.0;
+        if (k < ncols) {
+            const int col = first + step * k;
+            int mx = 0;
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                int c = 0;
+                for (int wd = 0; wd < P.nw; ++wd) c += __popc(P.w(s, wd, col) & valid[wd]);
+                mx = max(mx, c);
+            }
+            ratio = mx > 0 ? (double)mx / (double)nv : 0.0;                         // :8865-8868
+        }
+        const uint32_t cb = __ballot_sync(HB_FULL, k < ncols && ratio >= thr2);     // :8871
+        if (first_cand == -1 && cb) first_cand = first + step * (k0 + __ffs(cb) - 1);
+        const int lim = min(32, ncols - k0);
+        for (int j = 0; j < lim; ++j) total += __shfl_sync(HB_FULL, ratio, j);      // ordered sum :8874
+    }
+    const double avg = total / (double)ncols;                                        // :8877
+    return avg >= thr ? first_cand : -1;
+}
+
+// slide windows of wsize over the valid-column list (Util.py:8958-8965, 9010-9017, 9072-9079, 9130-9137)
+__device__ int slide_windows(const Planes& P, const int* vc, int n, int wsize, int step, double thr, int lane) {
+    for (int i = 0; i + wsize <= n; ++i) {
+        const int first = vc[i], last = vc[i + wsize - 1];
+        // step>0: range(first, last+1) ; step<0: range(first, last+1, -1) = first .. last+2
+        const int ncols = step > 0 ? (last + 1 - first) : (first - last - 1);
+        int res = -1;
+        if (ncols > 0) res = window_homology(P, first, ncols, step, thr, lane);
+        else {
+            // empty window: len(valid_rows) == all rows (0 <= 0); total/0 raises in Python.
+            // cannot occur for wsize >= 10 (ncols >= wsize-2); treated as non-homologous.
+            res = -1;
+        }
+        if (res != -1) return res;
+    }
+    return -1;
+}
+
+// search_boundary_homo_v3 (Util.py:8887-9143)
+__device__ int search_boundary_v3(const Planes& P, int vthr, int pos, int Cc, bool is_start, double thr,
+                                  int int_win, int out_win, int* vc, int lane) {
+    int cur, n, w, nb;
+    if (is_start) {
+        n = collect_valid(P, vthr, pos, +1, 0, (Cc + 1) / 2, vc, lane);             // col < C/2  :8924
+        w = min(n, int_win);
+        cur = (w < 10) ? -1 : slide_windows(P, vc, n, w, +1, thr, lane);            // :8954-8969
+        n = (cur >= 0) ? collect_valid(P, vthr, cur, -1, 0, Cc, vc, lane) : 0;      // :8976
+        reverse_list(vc, n, lane);                                                   // :9003
+        w = min(n, out_win);
+        if (w < 10) cur = -1;                                                        // :9006-9008
+        else {
+            nb = slide_windows(P, vc, n, w, +1, thr, lane);
+            if (nb != -1) { if (nb < 10) cur = -1; else cur = nb; }                  // :9018-9027
+        }
+    } else {
+        n = collect_valid(P, vthr, pos, +1, 0, Cc, vc, lane);                        // :9036
+        reverse_list(vc, n, lane);                                                   // :9065
+        cur = pos;
+        w = min(n, out_win);
+        if (w < 10) cur = -1;                                                        // :9068-9070
+        else {
+            nb = slide_windows(P, vc, n, w, -1, thr, lane);
+            if (nb != -1) { if (Cc - nb < 10) cur = -1; else cur = nb; }             // :9080-9089
+        }
+        // col >= C/2  :9096
+        n = (cur >= 0) ? collect_valid(P, vthr, cur, -1, (Cc + 1) / 2, Cc, vc, lane) : 0;
+        w = min(n, int_win);
+        cur = (w < 10) ? -1 : slide_windows(P, vc, n, w, -1, thr, lane);             // :9126-9141
+    }
+    return cur;
+}
+
+// consensus vote of one column (Util.py:9314-9339); returns symbol or -1 (column emits nothing)
+__device__ __forceinline__ int vote_column(const Planes& P, int col, int half) {
+    int cnt[6], fs[6];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+        int c = 0, f = 1 << 20;
+        for (int wd = P.nw - 1; wd >= 0; --wd) {
+            uint32_t x = P.w(s, wd, col);
+            c += __popc(x);
+            if (x) f = wd * 32 + __ffs(x) - 1;
+        }
+        cnt[s] = c; fs[s] = f;   // first-seen row == dict insertion order (:9257-9266)
+    }
+    int mxc = 0, mxs = -1, mxf = 1 << 21;
+#pragma unroll
+    for (int s = 0; s < 6; ++s)
+        if (cnt[s] > mxc || (cnt[s] == mxc && cnt[s] > 0 && fs[s] < mxf)) { mxc = cnt[s]; mxs = s; mxf = fs[s]; }
+    if (mxc >= half) return mxs != HB_SYM_GAP ? mxs : -1;
+    mxc = 0; mxs = -1; mxf = 1 << 21;
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+        if (cnt[s] > mxc || (cnt[s] == mxc && cnt[s] > 0 && fs[s] < mxf)) { mxc = cnt[s]; mxs = s; mxf = fs[s]; }
+    return mxs;
+}
+
+// TSDsearch_v5 (Util.py:2460-2492) on one row: returns 1 iff a TSD is found
+__device__ int tsd_search_v5(const uint8_t* row, int Cc, int bs, int be, int plant) {
+    // ungapped neighbourhoods (get_boundary_ungap_str :2407-2429), 4 bits per symbol
+    unsigned long long L = 0, Rr = 0;   // L[i]: i-th non-gap going left from bs-1 ; Rr[i]: i-th going right from be+1
+    int nL = 0, nR = 0;
+    for (int c = bs - 1; c >= 0 && nL < 11; --c) { int s = row[c]; if (s != HB_SYM_GAP) { L |= (unsigned long long)s << (4 * nL); ++nL; } }
+    for (int c = be + 1; c < Cc && nR < 11; ++c) { int s = row[c]; if (s != HB_SYM_GAP) { Rr |= (unsigned long long)s << (4 * nR); ++nR; } }
+    uint32_t F = 0, E = 0;              // F[i]: i-th non-gap going right from bs ; E[i]: i-th going left from be
+    int nF = 0, nE = 0;
+    for (int c = bs; c < Cc && nF < 5; ++c) { int s = row[c]; if (s != HB_SYM_GAP) { F |= (uint32_t)s << (4 * nF); ++nF; } }
+    for (int c = be; c >= 0 && nE < 5; --c) { int s = row[c]; if (s != HB_SYM_GAP) { E |= (uint32_t)s << (4 * nE); ++nE; } }
+    // symbol codes: A0 C1 G2 T3
+    const bool f3_ccc = nF >= 3 && (F & 0xfff) == 0x111;
+    const bool l3_ggg = nE >= 3 && (E & 0xfff) == 0x222;
+    // first_5bp == 'CACTA' : F = C,A,C,T,A -> nibbles (low first) 1,0,1,3,0
+    const bool f5_cacta = nF >= 5 && F == 0x03101u;
+    const bool f5_cactg = nF >= 5 && F == 0x23101u;
+    // last_5bp == 'TAGTG' forward; E holds it reversed: G,T,G,A,T -> 2,3,2,0,3
+    const bool l5_tagtg = nE >= 5 && E == 0x30232u;
+    // 'CAGTG' reversed: G,T,G,A,C -> 2,3,2,0,1
+    const bool l5_cagtg = nE >= 5 && E == 0x10232u;
+    int found = 0;
+    const int lens[9] = {11, 10, 9, 8, 6, 5, 4, 3, 2};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const int k = lens[i];
+        if (nL < k || nR < k) continue;
+        // left_tsd[t] = L[k-1-t], right_tsd[t] = Rr[t]
+        int mm = 0;
+        for (int t = 0; t < k; ++t) mm += (((L >> (4 * (k - 1 - t))) & 15ull) != ((Rr >> (4 * t)) & 15ull));
+        if (mm == 0) {
+            bool ok;
+            if (k != 2 && k != 3 && k != 4) ok = true;
+            else if (k == 4) ok = ((Rr & 0xffffull) == 0x0033ull);                        // TTAA
+            else if (k == 2) ok = ((Rr & 0xffull) == 0x03ull) || (plant == 0 && f3_ccc && l3_ggg);   // TA
+            else ok = ((Rr & 0xfffull) == 0x003ull) || ((Rr & 0xfffull) == 0x033ull) ||  // TAA, TTA
+                      (plant == 1 && ((f5_cacta && l5_tagtg) || (f5_cactg && l5_cagtg)));
+            if (ok) found = 1;
+        } else if (k >= 8 && mm <= 1) found = 1;
+    }
+    return found;
+}
+
+__device__ int lev5(const char* a, int la, const char* b, int lb) {
+    int prev[8], cur[8];
+    for (int j = 0; j <= lb; ++j) prev[j] = j;
+    for (int i = 1; i <= la; ++i) {
+        cur[0] = i;
+        for (int j = 1; j <= lb; ++j) {
+            int v = min(prev[j] + 1, cur[j - 1] + 1);
+            cur[j] = min(v, prev[j - 1] + (a[i - 1] != b[j - 1]));
+        }
+        for (int j = 0; j <= lb; ++j) prev[j] = cur[j];
+    }
+    return prev[lb];
+}
+
+__device__ __forceinline__ bool starts_with(const char* s, int n, const char* p, int lp) {
+    if (n < lp) return false;
+    for (int i = 0; i < lp; ++i) if (s[i] != p[i]) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel B: judge_boundary_v5 (Util.py:9145-9480), one warp per candidate.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                uint32_t* __restrict__ planes, Match* __restrict__ matches, const uint8_t* __restrict__ cands,
+                uint8_t* __restrict__ cons_buf, HbVoteCall* __restrict__ calls) {
+    __shared__ int s_vc[WARPS_PER_CTA][128];
+    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    __shared__ int s_cnt[WARPS_PER_CTA][2];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    HbVoteCall call = calls[ti];          // clean_cols written by kernel A
+    const int R = t.R, C = t.C, Cc = call.clean_cols;
+    const uint8_t* m = clean + t.clean_off;
+    call.is_te = 0; call.info = 0; call.copy_num = 0; call.align_start = -1; call.align_end = -1;
+    call.homo_start = -1; call.homo_end = -1; call.cons_len = 0; call.trim_lead = 0; call.trim_trail = 0;
+    call.flags = 0; call.cons_off = (int64_t)t.cons_off;
+    int* vc = s_vc[wid];
+    unsigned short* rows = s_rows[wid];
+
+    // ---- 1. anchors (:9151-9181) ----------------------------------------------------------
+    int as = -1, ae = -1;
+    if (t.cand_len > 2 && Cc > 0) {
+        const uint8_t* cand = cands + t.cand_off;
+        const int alen = min(20, t.cand_len);
+        Pattern P1, P2;
+        pattern_init(P1, cand, alen);
+        pattern_init(P2, cand + (t.cand_len - alen), alen);
+        Match* ml = matches + t.match_off;
+        const int cap = C + 2;
+        for (int r = 0; r < R; ++r) {
+            const uint8_t* row = m + (size_t)r * C;
+            int ub, n;
+            anchor_scan_row(row, Cc, P1, P2, ml, cap, s_cnt[wid], lane, &ub, &n);
+            const int n1 = min(cap, s_cnt[wid][0]), n2 = min(cap, s_cnt[wid][1]);
+            __syncwarp();
+            if (n1 > 0 && n2 > 0) {
+                const int fs = first_group_best_start(ml, n1, lane);
+                const int le = last_group_best_end(ml + cap, n2, lane);
+                as = column_of_ungapped(row, Cc, fs, ub, lane);
+                ae = column_of_ungapped(row, Cc, le - 1, ub, lane);
+                break;
+            }
+        }
+    }
+    call.align_start = as; call.align_end = ae;
+    if (as < 0 || ae < 0) {                                                    // :9184-9187
+        call.info = 1;
+        if (lane == 0) calls[ti] = call;
+        return;
+    }
+    // ---- 2. full-length member filter (:9196-9217) -----------------------------------------
+    int row_num = 0;
+    {
+        const int s_lo = max(0, as - 10), s_hi = min(Cc, as + 10);
+        int e_lo, e_hi;
+        py_slice(Cc, (long long)ae - 10, (ae + 10 < Cc) ? ae + 10 : Cc, &e_lo, &e_hi);
+        for (int r0 = 0; r0 < R && row_num < MAX_KEPT; r0 += 32) {
+            const int r = r0 + lane;
+            bool ok = false;
+            if (r < R) {
+                const uint8_t* row = m + (size_t)r * C;
+                bool a1 = false, a2 = false;
+                for (int c = s_lo; c < s_hi; ++c) a1 |= (row[c] != HB_SYM_GAP);
+                for (int c = e_lo; c < e_hi; ++c) a2 |= (row[c] != HB_SYM_GAP);
+                ok = a1 && a2;
+            }
+            const uint32_t bal = __ballot_sync(HB_FULL, ok);
+            const int pos = row_num + __popc(bal & lanemask_lt(lane));
+            if (ok && pos < MAX_KEPT) rows[pos] = (unsigned short)r;
+            row_num = min(MAX_KEPT, row_num + __popc(bal));
+        }
+        __syncwarp();
+    }
+    if (row_num <= 1) {                                                        // :9222-9225
+        call.info = 2; call.copy_num = 1;
+        if (lane == 0) calls[ti] = call;
+        return;
+    }
+    call.copy_num = row_num;
+    // ---- 3. bit-planes of the kept rows -----------------------------------------------------
+    Planes P;
+    uint32_t* pw = planes + t.plane_off;
+    P.p = pw; P.stride = C; P.nw = (row_num + 31) >> 5; P.row_num = row_num;
+    for (int wd = 0; wd < 4; ++wd) {
+        int rem = row_num - wd * 32;
+        P.rowmask[wd] = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+    }
+    for (int col = lane; col < Cc; col += 32) {
+        for (int wd = 0; wd < P.nw; ++wd) {
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+            const int kend = min(32, row_num - wd * 32);
+            for (int kk = 0; kk < kend; ++kk) {
+                const int s = m[(size_t)rows[wd * 32 + kk] * C + col];
+                const uint32_t bit = 1u << kk;
+                a0 |= (s == 0) ? bit : 0u; a1 |= (s == 1) ? bit : 0u; a2 |= (s == 2) ? bit : 0u;
+                a3 |= (s == 3) ? bit : 0u; a4 |= (s == 4) ? bit : 0u; a5 |= (s == 5) ? bit : 0u;
+            }
+            pw[(size_t)(0 * 4 + wd) * C + col] = a0; pw[(size_t)(1 * 4 + wd) * C + col] = a1;
+            pw[(size_t)(2 * 4 + wd) * C + col] = a2; pw[(size_t)(3 * 4 + wd) * C + col] = a3;
+            pw[(size_t)(4 * 4 + wd) * C + col] = a4; pw[(size_t)(5 * 4 + wd) * C + col] = a5;
+        }
+    }
+    __syncwarp();
+    const int vthr = row_num / 2;                                              // int(row_num/2) :9238
+    const double thr = row_num <= 2 ? 0.95 : (row_num <= 5 ? 0.9 : 0.7);       // :9240-9245
+    // ---- 4. outermost valid columns (:9269-9294) --------------------------------------------
+    int vl = -1, vr = -1;
+    for (int c0 = 0; c0 < Cc; c0 += 32) {
+        const int c = c0 + lane;
+        const uint32_t bal = __ballot_sync(HB_FULL, c < Cc && 2 * P.count(HB_SYM_GAP, c) <= row_num);
+        if (bal) { vl = c0 + __ffs(bal) - 1; break; }
+    }
+    if (vl != -1) {
+        for (int c0 = Cc - 1; c0 >= 0; c0 -= 32) {
+            const int c = c0 - lane;
+            const uint32_t bal = __ballot_sync(HB_FULL, c >= 0 && 2 * P.count(HB_SYM_GAP, c) <= row_num);
+            if (bal) { vr = c0 - (__ffs(bal) - 1); break; }
+        }
+    }
+    if (!(vl != -1 && vr != -1 && vl < vr)) { vl = -1; vr = -1; }
+    // ---- 5. homology boundaries (:9297-9308) -------------------------------------------------
+    const int hs = search_boundary_v3(P, vthr, as, Cc, true, thr, 20, 10, vc, lane);
+    call.homo_start = hs;
+    if (hs == -1) { if (lane == 0) calls[ti] = call; return; }
+    const int he = search_boundary_v3(P, vthr, ae, Cc, false, thr, 20, 10, vc, lane);
+    call.homo_end = he;
+    if (he == -1) { if (lane == 0) calls[ti] = call; return; }
+    // ---- 6. consensus (:9312-9346) -----------------------------------------------------------
+    uint8_t* cons = cons_buf + t.cons_off;
+    int ml = 0;
+    for (int c0 = hs; c0 <= he; c0 += 32) {
+        const int c = c0 + lane;
+        int s = -1;
+        if (c <= he) {
+            if (t.result_type == 1) s = vote_column(P, c, row_num / 2);
+            else { int x = m[(size_t)rows[0] * C + c]; s = (x != HB_SYM_GAP) ? x : -1; }
+        }
+        const uint32_t bal = __ballot_sync(HB_FULL, s >= 0);
+        if (s >= 0) cons[ml + __popc(bal & lanemask_lt(lane))] = (uint8_t)hb_ascii_of_sym(s);
+        ml += __popc(bal);
+    }
+    __syncwarp();
+    // ---- 7. reject rule + TIR terminal trimming supported by TSDs (:9353-9413) ---------------
+    int final_lo = 0, final_hi = 0;
+    if (!(hs <= vl || he >= vr) && t.te_type == 0) {
+        char head[9], tail[9];
+        const int nh = min(9, ml), nt = min(9, ml);
+        for (int i = 0; i < nh; ++i) head[i] = (char)cons[i];
+        for (int i = 0; i < nt; ++i) tail[i] = (char)cons[ml - nt + i];
+        auto ends_with = [&](const char* p, int lp) {
+            if (ml < lp) return false;
+            for (int i = 0; i < lp; ++i) if (tail[nt - lp + i] != p[i]) return false;
+            return true;
+        };
+        int fo[5], nfo = 0, eo[5], neo = 0;
+        fo[nfo++] = 0; eo[neo++] = 0;
+        if (starts_with(head, nh, "A", 1)) fo[nfo++] = 1;
+        if (starts_with(head, nh, "AA", 2) || starts_with(head, nh, "TA", 2)) fo[nfo++] = 2;
+        if (starts_with(head, nh, "TAA", 3) || starts_with(head, nh, "TTA", 3)) fo[nfo++] = 3;
+        if (starts_with(head, nh, "TTAA", 4)) fo[nfo++] = 4;
+        if (ends_with("T", 1)) eo[neo++] = 1;
+        if (ends_with("TT", 2) || ends_with("TA", 2)) eo[neo++] = 2;
+        if (ends_with("TAA", 3) || ends_with("TTA", 3)) eo[neo++] = 3;
+        if (ends_with("TTAA", 4)) eo[neo++] = 4;
+        bool have = false;
+        int best_ed = 0, best_tsd = 0, best_f = 0, best_e = 0;
+        for (int a = 0; a < nfo; ++a) for (int b = 0; b < neo; ++b) {
+            const int bs = hs + fo[a], be = he - eo[b];
+            int tsd = 0;
+            if (bs >= 0 && bs < Cc && be >= 0 && be < Cc) {
+                for (int r = lane; r < R; r += 32) {                           // ALL rows :9391
+                    const uint8_t* row = m + (size_t)r * C;
+                    if (row[bs] == HB_SYM_GAP || row[be] == HB_SYM_GAP) continue;
+                    tsd += tsd_search_v5(row, Cc, bs, be, t.plant);
+                }
+                tsd = warp_sum(tsd);
+            }
+            if (tsd > 0) {
+                int lo, hi, lo2, hi2;
+                py_slice(ml, fo[a], fo[a] + 5, &lo, &hi);
+                if (eo[b] == 0) py_slice(ml, -5, ml, &lo2, &hi2);
+                else py_slice(ml, (long long)ml - 5 - eo[b], (long long)ml - eo[b], &lo2, &hi2);
+                char f[8], e[8];
+                const int nf = hi - lo, ne = hi2 - lo2;
+                for (int i = 0; i < nf; ++i) {                                 // getReverseSequence :1635
+                    char bch = (char)cons[lo + nf - 1 - i];
+                    f[i] = bch == 'A' ? 'T' : bch == 'T' ? 'A' : bch == 'C' ? 'G' : bch == 'G' ? 'C' : 'N';
+                }
+                for (int i = 0; i < ne; ++i) e[i] = (char)cons[lo2 + i];
+                const int ed = lev5(f, nf, e, ne);                             // :9403
+                if (!have || ed < best_ed || (ed == best_ed && tsd > best_tsd)) {   // stable sort :9405
+                    have = true; best_ed = ed; best_tsd = tsd; best_f = fo[a]; best_e = eo[b];
+                }
+            }
+        }
+        if (have) {                                                            // :9406-9413
+            if (best_e != 0) py_slice(ml, best_f, -(long long)best_e, &final_lo, &final_hi);
+            else py_slice(ml, best_f, ml, &final_lo, &final_hi);
+            call.trim_lead = best_f; call.trim_trail = best_e;
+        }
+    }
+    const int fl = max(0, final_hi - final_lo);
+    call.cons_len = fl;
+    call.cons_off = (int64_t)t.cons_off + final_lo;
+    call.is_te = fl > 0;                                                       // :9473-9476
+    if (lane == 0) calls[ti] = call;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host launchers (called from hb_api.cu)
+extern "C" size_t hb_vote_match_entry_size() { return sizeof(Match); }
+
+extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
+                                      uint32_t* d_planes, void* d_matches, const uint8_t* d_cands,
+                                      uint8_t* d_cons, HbVoteCall* d_calls, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    hb_clean_kernel<<<n, CLEAN_THREADS, 0, stream>>>(d_tasks, d_raw, d_clean, d_calls);
+    const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    hb_judge_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
+                                                             d_cands, d_cons, d_calls);
+    return cudaGetLastError();
+}

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Generate golden fixtures by running the UNMODIFIED reference functions (imported read-only from
+/root/reference/module/Util.py through oracle/ref_import.py) on seeded synthetic inputs.
+
+Run in the build container only:   python tests/golden/make_golden.py
+Outputs (committed):  tests/golden/judge_v5.json.gz
+"""
+import gzip
+import json
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import ref_import  # noqa: E402
+import msa_synth  # noqa: E402
+
+
+def run_reference_v5(U, case, tmpdir):
+    """remove_sparse_col_in_align_file (Util.py:10344) + judge_boundary_v5 (Util.py:9145)."""
+    path = os.path.join(tmpdir, "a.maf.fa")
+    with open(path, "w") as f:
+        for i, row in enumerate(case["rows"]):
+            f.write(">r%d\n%s\n" % (i, row))
+    clean = U.remove_sparse_col_in_align_file(path)
+    names, contigs = U.read_fasta(clean)
+    clean_rows = [contigs[n] for n in names]
+    trace = []
+    orig = U.search_boundary_homo_v3
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        trace.append(r)
+        return r
+
+    U.search_boundary_homo_v3 = spy
+    try:
+        is_te, info, cons, copy_num = U.judge_boundary_v5(case["cand"], clean, 0, "tir", case["plant"], "cons")
+    finally:
+        U.search_boundary_homo_v3 = orig
+    hs = trace[0] if len(trace) > 0 else -1
+    he = trace[1] if len(trace) > 1 else -1
+    return dict(clean_rows=clean_rows, is_te=bool(is_te), info=info, cons=cons, copy_num=copy_num,
+                homo_start=hs, homo_end=he)
+
+
+def main():
+    U = ref_import.load_util()
+    out = []
+    with tempfile.TemporaryDirectory() as td:
+        seeds = list(range(1, 161))
+        for seed in seeds:
+            case = msa_synth.synth_case(seed)
+            exp = run_reference_v5(U, case, td)
+            rec = dict(seed=seed, scenario=case["scenario"], cand=case["cand"], plant=case["plant"],
+                       rows=case["rows"], truth=case["truth"], expect=exp)
+            out.append(rec)
+    path = os.path.join(ROOT, "tests", "golden", "judge_v5.json.gz")
+    with gzip.GzipFile(path, "wb", mtime=0) as f:
+        f.write(json.dumps(out, separators=(",", ":")).encode())
+    n_te = sum(r["expect"]["is_te"] for r in out)
+    print("wrote", path, len(out), "cases;", n_te, "TE;", os.path.getsize(path), "bytes")
+    from collections import Counter
+    print(Counter((r["scenario"], r["expect"]["is_te"], r["expect"]["info"]) for r in out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+"""Seeded synthetic MSA generator for the judge parity tests (test infrastructure).
+
+Produces (candidate, rows) pairs shaped like what ``is_TE_from_align_file`` (reference
+Util.py:10407) hands to ``remove_sparse_col_in_align_file`` + ``judge_boundary_v5/v6/v9``:
+rows are *copies only* (flank + element + flank, aligned, '-' for gaps), candidate not included.
+Uses ``random.Random`` only, so a (scenario, seed) pair is reproducible anywhere.
+"""
+import random
+
+BASES = "ACGT"
+COMP = {"A": "T", "C": "G", "G": "C", "T": "A"}
+
+
+def revcomp(s):
+    return "".join(COMP.get(b, "N") for b in reversed(s))
+
+
+def rand_seq(rng, n):
+    return "".join(rng.choice(BASES) for _ in range(n))
+
+
+def make_tir_element(rng, length, tir_len, head=None):
+    tir = rand_seq(rng, tir_len)
+    if head:
+        tir = head + tir[len(head):]
+    body = rand_seq(rng, max(0, length - 2 * tir_len))
+    return tir + body + revcomp(tir)
+
+
+def make_tsd(rng, kind):
+    if kind == 2:
+        return "TA"
+    if kind == 3:
+        return rng.choice(["TAA", "TTA"])
+    if kind == 4:
+        return "TTAA"
+    return rand_seq(rng, kind)
+
+
+def mutate_row(rng, elem, sub, dele):
+    out = []
+    for b in elem:
+        r = rng.random()
+        if r < dele:
+            out.append("-")
+        elif r < dele + sub:
+            out.append(rng.choice([x for x in BASES if x != b]))
+        else:
+            out.append(b)
+    return "".join(out)
+
+
+def synth_case(seed, scenario=None):
+    """Returns dict(cand=str, rows=[str], plant=int, te_type='tir', scenario=str, truth=str)."""
+    rng = random.Random(seed)
+    scen = scenario or rng.choice(
+        ["clean", "clean", "clean", "shift_out", "shift_in", "fp_homolog_flank", "fragments",
+         "few_rows", "no_anchor", "many_rows", "ta_head", "n_bases", "short"])
+    flank = 50
+    nrows = rng.randint(6, 40)
+    length = rng.randint(90, 420)
+    sub = rng.choice([0.0, 0.02, 0.05, 0.1])
+    dele = rng.choice([0.0, 0.005, 0.02])
+    ins_cols = rng.randint(0, 6)
+    tsd_kind = rng.choice([2, 3, 4, 5, 8, 9, 10])
+    head = None
+    if scen == "few_rows":
+        nrows = rng.randint(1, 5)
+    elif scen == "many_rows":
+        nrows = rng.randint(101, 130)
+        length = rng.randint(90, 160)
+    elif scen == "ta_head":
+        head = rng.choice(["TTAA", "TAA", "TTA", "TA", "AA", "A"])
+    elif scen == "short":
+        length = rng.randint(40, 85)
+    tir_len = rng.randint(8, 20)
+    elem = make_tir_element(rng, length, tir_len, head)
+    if scen == "ta_head":
+        tail = rng.choice(["TTAA", "TAA", "TTA", "TA", "TT", "T"])
+        elem = elem[:-len(tail)] + tail
+    shared_l = rand_seq(rng, flank)
+    shared_r = rand_seq(rng, flank)
+    rows = []
+    for r in range(nrows):
+        tsd = make_tsd(rng, tsd_kind)
+        if rng.random() < 0.15:
+            tsd_r = make_tsd(rng, tsd_kind) if tsd_kind > 4 else tsd      # broken TSD
+        else:
+            tsd_r = tsd
+        lf = rand_seq(rng, flank - len(tsd)) + tsd
+        rf = tsd_r + rand_seq(rng, flank - len(tsd_r))
+        if scen == "fp_homolog_flank":
+            lf = mutate_row(rng, shared_l, 0.03, 0.0).replace("-", "A")
+            rf = mutate_row(rng, shared_r, 0.03, 0.0).replace("-", "A")
+        body = mutate_row(rng, elem, sub, dele)
+        if scen == "fragments" and r > 0 and rng.random() < 0.4:
+            cut = rng.randint(15, len(body) // 2)
+            if rng.random() < 0.5:
+                body = "-" * cut + body[cut:]
+                lf = "-" * flank
+            else:
+                body = body[:-cut] + "-" * cut
+                rf = "-" * flank
+        if scen == "n_bases" and rng.random() < 0.3:
+            p = rng.randrange(len(body))
+            body = body[:p] + "N" + body[p + 1:]
+        rows.append(lf + body + rf)
+    # insertion columns: a random row (or a few) carries a base, everyone else a gap
+    for _ in range(ins_cols):
+        p = rng.randint(1, len(rows[0]) - 1)
+        who = set(rng.sample(range(nrows), k=min(nrows, rng.choice([1, 1, 2, nrows // 2 + 1]))))
+        rows = [row[:p] + (rng.choice(BASES) if i in who else "-") + row[p:] for i, row in enumerate(rows)]
+    cand = elem
+    if scen == "shift_out":
+        # candidate carries a few bp of copy-0's own flank on each side (coarse boundary too wide)
+        a, b = rng.randint(0, 12), rng.randint(0, 12)
+        r0 = rows[0].replace("-", "")
+        s = r0.find(rows[0][flank:flank + 30].replace("-", "")[:12])
+        core_start = len(rows[0][:flank].replace("-", ""))
+        core_end = len(r0) - len(rows[0][-flank:].replace("-", ""))
+        cand = r0[max(0, core_start - a):core_end + b]
+    elif scen == "shift_in":
+        a, b = rng.randint(0, 15), rng.randint(0, 15)
+        cand = elem[a:len(elem) - b]
+    elif scen == "no_anchor":
+        cand = rand_seq(rng, length)
+    return dict(cand=cand, rows=rows, plant=rng.choice([0, 1]), te_type="tir", scenario=scen, truth=elem)
