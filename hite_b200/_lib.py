@@ -31,6 +31,19 @@ CALL_DTYPE = np.dtype([("is_te", "<i4"), ("info", "<i4"), ("copy_num", "<i4"), (
 assert CALL_DTYPE.itemsize == C.sizeof(HbCall)
 
 
+class HbParams(C.Structure):
+    _fields_ = [("occ_cap", C.c_int32), ("max_loci", C.c_int32), ("flank", C.c_int32), ("max_rows", C.c_int32),
+                ("te_type", C.c_int32), ("plant", C.c_int32), ("result_type", C.c_int32), ("pad", C.c_int32),
+                ("tb_budget_bytes", C.c_uint64)]
+
+
+COPY_DTYPE = np.dtype([("cand", "<u4"), ("rank", "<i4"), ("rel", "<i4"), ("nseeds", "<i4"), ("score", "<i4"),
+                       ("i_s", "<i4"), ("i_e", "<i4"), ("keep", "<i4"), ("row", "<i4"), ("contig", "<i4"),
+                       ("j0", "<i8"), ("j_s", "<i8"), ("j_e", "<i8"), ("start1", "<i8"), ("end1", "<i8"),
+                       ("ext_len", "<i4"), ("pad", "<i4")])
+assert COPY_DTYPE.itemsize == 88
+
+
 class HbTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("k_ms", C.c_float * 8), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
@@ -63,6 +76,14 @@ def load():
     lib.hb_get_timing.argtypes = [vp, C.POINTER(HbTiming)]
     lib.hb_vote_matrices.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp,
                                      C.c_uint64]
+    lib.hb_genome_load.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.hb_index_build.argtypes = [vp, C.c_int, C.c_int]
+    lib.hb_genome_info.argtypes = [vp, u64p, u64p, vp, C.c_uint32]
+    lib.hb_adjust.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(HbParams), vp, u64p]
+    lib.hb_last_cons.argtypes = [vp, vp, C.c_uint64]
+    lib.hb_last_copies.argtypes = [vp, vp, C.c_uint64, u64p]
+    lib.hb_debug_index.argtypes = [vp, vp, C.c_uint64]
+    lib.hb_last_msa.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
     _LIB = lib
     return lib
 
@@ -150,3 +171,80 @@ class Context:
                             homo_start=int(c["homo_start"]), homo_end=int(c["homo_end"]),
                             clean_cols=int(c["clean_cols"])))
         return out
+
+    # ------------------------------------------------------------------------------------
+    def load_genome(self, contig_seqs):
+        """Kernel (i) part 1.  ``contig_seqs``: list of bytes / uint8 arrays (ASCII, any case)."""
+        seqs = [np.frombuffer(x, dtype=np.uint8) if isinstance(x, (bytes, bytearray)) else
+                (np.frombuffer(x.encode("ascii"), dtype=np.uint8) if isinstance(x, str) else np.asarray(x, dtype=np.uint8))
+                for x in contig_seqs]
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in seqs])
+        flat = np.concatenate(seqs) if len(seqs) > 1 else np.ascontiguousarray(seqs[0])
+        self._check(self._lib.hb_genome_load(self._h, _ptr(flat), _ptr(off), len(seqs)), "hb_genome_load")
+        self.contig_lens = [len(x) for x in seqs]
+        return self.timing()
+
+    def build_index(self, k=15, w=10):
+        self._check(self._lib.hb_index_build(self._h, int(k), int(w)), "hb_index_build")
+        return self.timing()
+
+    def genome_info(self):
+        tot, nmm = C.c_uint64(0), C.c_uint64(0)
+        goff = np.zeros(max(1, len(getattr(self, "contig_lens", [0]))), dtype=np.uint64)
+        self._check(self._lib.hb_genome_info(self._h, C.byref(tot), C.byref(nmm), _ptr(goff), len(goff)), "hb_genome_info")
+        return dict(total_padded=tot.value, n_minimizers=nmm.value, contig_goff=goff)
+
+    def debug_index(self):
+        n = self.genome_info()["n_minimizers"]
+        keys = np.zeros(max(1, n), dtype=np.uint64)
+        self._check(self._lib.hb_debug_index(self._h, _ptr(keys), len(keys)), "hb_debug_index")
+        return keys[:n]
+
+    def adjust(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=128, flank=50,
+               max_rows=100, tb_budget_bytes=0):
+        """One ``flank_region_align_v5``-equivalent round (kernels ii + iii) over the candidates.
+        Returns a list of dicts mirroring ``is_TE_from_align_file``'s tuple per candidate."""
+        cb = [c if isinstance(c, (bytes, bytearray)) else c.encode("ascii") for c in cand_seqs]
+        n = len(cb)
+        if n == 0:
+            return []
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(c) for c in cb])
+        flat = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
+        prm = HbParams(occ_cap, max_loci, flank, max_rows, TE_TYPES[te_type], int(plant),
+                       1 if result_type == "cons" else 0, 0, int(tb_budget_bytes))
+        calls = np.zeros(n, dtype=CALL_DTYPE)
+        nbytes = C.c_uint64(0)
+        self._check(self._lib.hb_adjust(self._h, n, _ptr(flat), _ptr(off), C.byref(prm), _ptr(calls), C.byref(nbytes)),
+                    "hb_adjust")
+        cons = np.zeros(max(1, nbytes.value), dtype=np.uint8)
+        self._check(self._lib.hb_last_cons(self._h, _ptr(cons), len(cons)), "hb_last_cons")
+        cons_b = cons.tobytes()
+        self.last_calls = calls
+        out = []
+        for i in range(n):
+            c = calls[i]
+            o, ln = int(c["cons_off"]), int(c["cons_len"])
+            out.append(dict(is_te=bool(c["is_te"]), info=INFO[int(c["info"])], cons=cons_b[o:o + ln].decode("ascii"),
+                            copy_num=int(c["copy_num"]), align_start=int(c["align_start"]), align_end=int(c["align_end"]),
+                            homo_start=int(c["homo_start"]), homo_end=int(c["homo_end"]), clean_cols=int(c["clean_cols"]),
+                            no_copies=bool(int(c["flags"]) & 1)))
+        return out
+
+    def last_copies(self):
+        n = C.c_uint64(0)
+        self._check(self._lib.hb_last_copies(self._h, None, 0, C.byref(n)), "hb_last_copies")
+        arr = np.zeros(max(1, n.value), dtype=COPY_DTYPE)
+        self._check(self._lib.hb_last_copies(self._h, _ptr(arr), len(arr), C.byref(n)), "hb_last_copies")
+        return arr[:n.value]
+
+    def last_msa(self, cand):
+        R, Cn = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.hb_last_msa(self._h, cand, None, 0, C.byref(R), C.byref(Cn)), "hb_last_msa")
+        if R.value == 0:
+            return []
+        buf = np.zeros(R.value * Cn.value, dtype=np.uint8)
+        self._check(self._lib.hb_last_msa(self._h, cand, _ptr(buf), len(buf), C.byref(R), C.byref(Cn)), "hb_last_msa")
+        raw = buf.tobytes()
+        return [raw[r * Cn.value:(r + 1) * Cn.value].decode() for r in range(R.value)]

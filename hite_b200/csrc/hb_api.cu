@@ -59,6 +59,7 @@ extern "C" void hb_destroy(hb_ctx* ctx) {
     for (HbDevBuf* b : {&ctx->v_tasks, &ctx->v_raw, &ctx->v_clean, &ctx->v_planes, &ctx->v_matches, &ctx->v_cands,
                         &ctx->v_cons, &ctx->v_calls})
         b->release();
+    for (auto& kv : ctx->bufs) kv.second.release();
     ctx->h_stage.release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

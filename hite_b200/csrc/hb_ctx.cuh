@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,20 @@ struct hb_ctx {
     // vote path buffers
     HbDevBuf v_tasks, v_raw, v_clean, v_planes, v_matches, v_cands, v_cons, v_calls;
     HbHostBuf h_stage;
+    // named device buffers of the genome / index / adjust pipeline (hb_pipeline.cu)
+    std::map<std::string, HbDevBuf> bufs;
+    HbDevBuf& buf(const char* name) { return bufs[name]; }
+    // genome state (HB-align S1/S2)
+    bool have_genome = false, have_index = false;
+    uint64_t g_tot = 0, g_nmm = 0;
+    uint32_t g_ncontig = 0;
+    int k = 15, w = 10;
+    std::vector<uint64_t> g_goff, g_glen;
+    // results of the last hb_adjust kept for hb_last_* getters
+    std::vector<uint8_t> last_cons;
+    uint32_t last_ncand = 0, last_npairs = 0;
+    std::vector<uint64_t> last_mat_off;
+    std::vector<uint32_t> last_rows, last_cols;
 };
 
 inline int hb_fail(hb_ctx* ctx, const char* what, cudaError_t e, const char* file, int line) {

@@ -1,0 +1,196 @@
+// hite_b200 -- kernel (i): 2-bit packing and (k,w)-minimizer index build over the genome chunks.
+//
+// Replaces the `minimap2 -d ref.mmi` index build of get_full_length_copies_minimap2 (reference
+// module/Util.py:7938-7947) -- the reference shells out; the index here follows HB-align S1/S2
+//  and is bit-identical to oracle/hbo_align.c::hbo_minimizers + sort.
+//
+// HBM layout: sequences live in one padded global coordinate space (64 N between contigs):
+//   seq2[TOT/16]  uint32, base b of a word at bits 2*(b%16)         (2 bit/base)
+//   nmask[TOT/32] uint32, bit b%32 set = not ACGT                   (1 bit/base)
+//   index[M]      uint64  hash(30b)<<33 | pos(32b)<<1 | strand, sorted ascending
+//   bucket[2^22+1] uint32 first index entry of every 22-bit hash prefix
+#include "hb_common.cuh"
+#include "hb_index.cuh"
+
+namespace {
+
+// ---- S1: pack ---------------------------------------------------------------------------------
+// one thread per aligned 32-base group of the global coordinate space; the 64-base pads guarantee a
+// group intersects at most one contig.
+__global__ void pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ src_off,
+                            const uint64_t* __restrict__ goff, const uint64_t* __restrict__ glen, uint32_t n_contig,
+                            uint64_t tot, uint32_t* __restrict__ seq2, uint32_t* __restrict__ nmask) {
+    const uint64_t grp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t g0 = grp * 32;
+    if (g0 >= tot) return;
+    // last contig with goff <= g0 + 31
+    int lo = 0, hi = (int)n_contig;   // first contig with goff > g0+31
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (goff[mid] <= g0 + 31) lo = mid + 1; else hi = mid; }
+    const int c = lo - 1;
+    uint32_t w0 = 0, w1 = 0, nm = 0xffffffffu;
+    if (c >= 0) {
+        const uint64_t cs = goff[c], ce = cs + glen[c];
+        const uint8_t* src = ascii + src_off[c];
+#pragma unroll 4
+        for (int b = 0; b < 32; ++b) {
+            const uint64_t p = g0 + b;
+            if (p >= cs && p < ce) {
+                const int s = hb_sym_of_ascii(src[p - cs]);
+                if (s < 4) {
+                    nm &= ~(1u << b);
+                    if (b < 16) w0 |= (uint32_t)s << (2 * b); else w1 |= (uint32_t)s << (2 * (b - 16));
+                }
+            }
+        }
+    }
+    seq2[grp * 2] = w0; seq2[grp * 2 + 1] = w1; nmask[grp] = nm;
+}
+
+// ---- S2: minimizers -----------------------------------------------------------------------------
+constexpr int MM_THREADS = 256;
+constexpr int MM_PER_THREAD = 8;
+constexpr int MM_TILE = MM_THREADS * MM_PER_THREAD;     // positions owned by a CTA
+constexpr int MM_HALO = 16;                             // >= w-1 on both sides
+constexpr uint32_t INVALID_H = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t hash_kmer(uint64_t key, int k) {   // sketch.c hash64, masked
+    const uint64_t mask = (1ULL << (2 * k)) - 1;
+    key = (~key + (key << 21)) & mask;
+    key = key ^ key >> 24;
+    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = key ^ key >> 14;
+    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = key ^ key >> 28;
+    key = (key + (key << 31)) & mask;
+    return (uint32_t)key;
+}
+
+__device__ __forceinline__ int base_at(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask,
+                                       uint64_t tot, int64_t p) {
+    if (p < 0 || (uint64_t)p >= tot) return 4;
+    if ((nmask[p >> 5] >> (p & 31)) & 1u) return 4;
+    return (seq2[p >> 4] >> (2 * (p & 15))) & 3u;
+}
+
+// WRITE = false: count selected positions per CTA; WRITE = true: emit keys at cta_base[blockIdx]
+template <bool WRITE>
+__global__ void __launch_bounds__(MM_THREADS)
+minimizer_kernel(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask, uint64_t tot, int k, int w,
+                 uint32_t* __restrict__ cta_count, const uint32_t* __restrict__ cta_base, uint64_t* __restrict__ out) {
+    __shared__ uint32_t s_h[MM_TILE + 2 * MM_HALO];      // hash | strand in bit 31? no: hash < 2^30
+    __shared__ uint8_t s_st[MM_TILE + 2 * MM_HALO];
+    __shared__ uint8_t s_sel[MM_TILE + 2 * MM_HALO];
+    __shared__ uint32_t s_warp[8];
+    const int tid = threadIdx.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * MM_TILE;
+    const int64_t ext0 = tile0 - MM_HALO;
+    const int ext_n = MM_TILE + 2 * MM_HALO;
+    // hashes of the k-mers starting at ext0 + x
+    for (int x0 = tid * 9; x0 < ext_n; x0 += MM_THREADS * 9) {
+        // each thread rolls over 9 consecutive positions
+        uint64_t f = 0, r = 0;
+        int bad = 0;   // number of N among the current k bases (counted via last-N distance)
+        const int64_t p0 = ext0 + x0;
+        int last_n = -1000;
+        for (int t = 0; t < k - 1; ++t) {
+            const int c = base_at(seq2, nmask, tot, p0 + t);
+            if (c > 3) last_n = t;
+            f = (f << 2) | (uint64_t)(c & 3);
+            r = (r >> 2) | ((uint64_t)(3 - (c & 3)) << (2 * (k - 1)));
+        }
+        (void)bad;
+        const uint64_t mask = (1ULL << (2 * k)) - 1;
+        for (int j = 0; j < 9 && x0 + j < ext_n; ++j) {
+            const int t = k - 1 + j;
+            const int c = base_at(seq2, nmask, tot, p0 + t);
+            if (c > 3) last_n = t;
+            f = ((f << 2) | (uint64_t)(c & 3)) & mask;
+            r = (r >> 2) | ((uint64_t)(3 - (c & 3)) << (2 * (k - 1)));
+            const bool has_n = last_n >= j;              // an N inside positions j..j+k-1
+            uint32_t h = INVALID_H; uint8_t st = 0;
+            if (!has_n && f != r && p0 + j >= 0 && (uint64_t)(p0 + j) + (uint64_t)k <= tot) {
+                st = r < f;
+                h = hash_kmer(r < f ? r : f, k);
+            }
+            s_h[x0 + j] = h; s_st[x0 + j] = st; s_sel[x0 + j] = 0;
+        }
+    }
+    __syncthreads();
+    // every window start s in [tile0 - (w-1), tile0 + MM_TILE) marks its leftmost smallest k-mer
+    for (int x = tid; x < MM_TILE + (w - 1); x += MM_THREADS) {
+        const int xs = x + (MM_HALO - (w - 1));          // index of window start in s_h
+        const int64_t s = ext0 + xs;
+        if (s < 0 || (uint64_t)s + (uint64_t)w > tot) continue;
+        uint32_t best = INVALID_H; int bp = 0;
+        for (int t = 0; t < w; ++t) { const uint32_t h = s_h[xs + t]; if (h < best) { best = h; bp = xs + t; } }
+        if (best != INVALID_H) s_sel[bp] = 1;
+    }
+    __syncthreads();
+    // compaction over the owned positions (blocked per thread -> position order)
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < MM_PER_THREAD; ++j) {
+        const int x = MM_HALO + tid * MM_PER_THREAD + j;
+        const int64_t p = ext0 + x;
+        cnt += (p >= 0 && (uint64_t)p < tot && s_sel[x]) ? 1u : 0u;
+    }
+    // block exclusive scan
+    const int lane = tid & 31, wid = tid >> 5;
+    uint32_t xsum = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(HB_FULL, xsum, o); if (lane >= o) xsum += t; }
+    if (lane == 31) s_warp[wid] = xsum;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { uint32_t sv = s_warp[q]; if (q < wid) before += sv; total += sv; }
+    if (!WRITE) {
+        if (tid == 0) cta_count[blockIdx.x] = total;
+        return;
+    }
+    uint64_t o = (uint64_t)cta_base[blockIdx.x] + before + xsum - cnt;
+#pragma unroll
+    for (int j = 0; j < MM_PER_THREAD; ++j) {
+        const int x = MM_HALO + tid * MM_PER_THREAD + j;
+        const int64_t p = ext0 + x;
+        if (p >= 0 && (uint64_t)p < tot && s_sel[x])
+            out[o++] = ((uint64_t)s_h[x] << 33) | ((uint64_t)p << 1) | (uint64_t)s_st[x];
+    }
+}
+
+// ---- bucket table over the sorted index ----------------------------------------------------------
+__global__ void bucket_count_kernel(const uint64_t* __restrict__ idx, uint64_t n, int shift, uint32_t* __restrict__ cnt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(uint32_t)(idx[i] >> shift)], 1u);
+}
+
+}  // namespace
+
+cudaError_t hb_pack_launch(const uint8_t* d_ascii, const uint64_t* d_src_off, const uint64_t* d_goff,
+                           const uint64_t* d_glen, uint32_t n_contig, uint64_t tot, uint32_t* d_seq2,
+                           uint32_t* d_nmask, cudaStream_t s) {
+    const uint64_t groups = tot / 32;
+    pack_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, s>>>(d_ascii, d_src_off, d_goff, d_glen, n_contig, tot,
+                                                                  d_seq2, d_nmask);
+    return cudaGetLastError();
+}
+
+uint32_t hb_minimizer_ctas(uint64_t tot) { return (uint32_t)((tot + MM_TILE - 1) / MM_TILE); }
+
+cudaError_t hb_minimizer_count_launch(const uint32_t* d_seq2, const uint32_t* d_nmask, uint64_t tot, int k, int w,
+                                      uint32_t* d_cta_count, cudaStream_t s) {
+    minimizer_kernel<false><<<hb_minimizer_ctas(tot), MM_THREADS, 0, s>>>(d_seq2, d_nmask, tot, k, w, d_cta_count,
+                                                                          nullptr, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t hb_minimizer_write_launch(const uint32_t* d_seq2, const uint32_t* d_nmask, uint64_t tot, int k, int w,
+                                      const uint32_t* d_cta_base, uint64_t* d_out, cudaStream_t s) {
+    minimizer_kernel<true><<<hb_minimizer_ctas(tot), MM_THREADS, 0, s>>>(d_seq2, d_nmask, tot, k, w, nullptr,
+                                                                         d_cta_base, d_out);
+    return cudaGetLastError();
+}
+cudaError_t hb_bucket_count_launch(const uint64_t* d_idx, uint64_t n, int shift, uint32_t* d_cnt, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    bucket_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_idx, n, shift, d_cnt);
+    return cudaGetLastError();
+}

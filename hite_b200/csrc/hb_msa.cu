@@ -1,0 +1,239 @@
+// hite_b200 -- copy selection and candidate-anchored star-MSA assembly from the pairwise edit
+// scripts of kernel (ii); feeds the column-vote kernel (iii).
+//
+// Replaces (reference module/Util.py):
+//   get_copies_minimap2 coverage rules            :8003-8025   -> copy_filter_kernel
+//   copy extension / off-contig / <100 bp skips   :8095-8115   -> copy_filter_kernel
+//   "100 longest members" (ready_for_MSA.sh)      :10409-10412 -> copy_select_kernel
+//   mafft --preservecase                          :10416       -> ins_max / layout / msa_write kernels
+// Follows HB-align S8..S10; bit-identical to oracle/hbo_align.c::hbo_candidate_msa.
+#include "hb_common.cuh"
+#include "hb_msa.cuh"
+
+namespace {
+
+__device__ __forceinline__ int packed_base(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask,
+                                           uint64_t p) {
+    if ((nmask[p >> 5] >> (p & 31)) & 1u) return 4;
+    return (seq2[p >> 4] >> (2 * (p & 15))) & 3u;
+}
+__device__ __forceinline__ int target_base(const uint32_t* __restrict__ gseq2, const uint32_t* __restrict__ gnmask,
+                                           uint64_t tot, int rel, int64_t j) {
+    if (j < 0 || (uint64_t)j >= tot) return 4;
+    if (!rel) return packed_base(gseq2, gnmask, (uint64_t)j);
+    const int c = packed_base(gseq2, gnmask, tot - 1 - (uint64_t)j);
+    return c < 4 ? 3 - c : 4;
+}
+
+// S8: thread per pair
+__global__ void copy_filter_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const uint32_t* __restrict__ clen,
+                                   const uint64_t* __restrict__ goff, const uint64_t* __restrict__ glen, uint32_t n_contig,
+                                   uint64_t tot, int flank, HbAln* __restrict__ alns) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    HbAln a = alns[p];
+    a.keep = 0; a.contig = -1; a.row = -1;
+    if (a.score > 0) {
+        const int L = (int)clen[pairs[p].cand];
+        const int aligned = a.i_e - a.i_s + 1;
+        const long long tlen = a.j_e - a.j_s + 1;
+        const bool cov = ((double)aligned / (double)L >= 0.95) && ((double)aligned / (double)tlen >= 0.95);   // :8007-8022
+        if (cov) {
+            const int rel = (int)pairs[p].rel;
+            const int64_t fs = rel ? (int64_t)tot - 1 - a.j_e : a.j_s;
+            const int64_t fe = rel ? (int64_t)tot - 1 - a.j_s : a.j_e;
+            int lo = 0, hi = (int)n_contig;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if ((int64_t)goff[mid] <= fs) lo = mid + 1; else hi = mid; }
+            const int c = lo - 1;
+            if (c >= 0 && (uint64_t)fe < goff[c] + glen[c]) {
+                a.contig = c;
+                a.start1 = fs - (int64_t)goff[c] + 1;
+                a.end1 = fe - (int64_t)goff[c] + 1;
+                const bool off = (a.start1 - 1 - flank < 0) || (a.end1 + flank > (int64_t)glen[c]);            // :8103
+                a.ext_len = (int32_t)(a.end1 - a.start1 + 1 + 2 * flank);
+                if (!off && a.ext_len >= 100) a.keep = 1;                                                       // :8108
+            }
+        }
+    }
+    alns[p] = a;
+}
+
+// S8 dedup + S9 "max_rows longest": warp per candidate
+constexpr int SEL_MAX = 512;
+__global__ void __launch_bounds__(128)
+copy_select_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, uint32_t n_cand,
+                   int max_rows, HbAln* __restrict__ alns, uint32_t* __restrict__ n_rows) {
+    __shared__ uint8_t s_keep[4][SEL_MAX];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t c = blockIdx.x * 4 + wid;
+    if (c >= n_cand) return;
+    const uint32_t p0 = pair_off[c], p1 = pair_off[c + 1];
+    const int n = min((int)(p1 - p0), SEL_MAX);
+    uint8_t* keep = s_keep[wid];
+    for (int x = lane; x < n; x += 32) {
+        const HbAln a = alns[p0 + x];
+        int k = a.keep;
+        if (k) {
+            const uint32_t rel = pairs[p0 + x].rel;
+            for (int y = 0; y < x; ++y) {
+                const HbAln b = alns[p0 + y];
+                if (b.keep && pairs[p0 + y].rel == rel && b.j_s == a.j_s && b.j_e == a.j_e) { k = 0; break; }
+            }
+        }
+        keep[x] = (uint8_t)k;
+    }
+    __syncwarp();
+    int nk = 0;
+    for (int x = lane; x < n; x += 32) nk += keep[x];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nk += __shfl_xor_sync(HB_FULL, nk, o);
+    if (nk > max_rows) {
+        for (int x = lane; x < n; x += 32) {
+            if (!keep[x]) continue;
+            const int lx = alns[p0 + x].ext_len;
+            int longer = 0;
+            for (int y = 0; y < n; ++y) {
+                if (y == x || !keep[y]) continue;
+                const int ly = alns[p0 + y].ext_len;
+                longer += (ly > lx || (ly == lx && y < x)) ? 1 : 0;
+            }
+            if (longer >= max_rows) keep[x] = 2;
+        }
+        __syncwarp();
+        for (int x = lane; x < n; x += 32) if (keep[x] == 2) keep[x] = 0;
+        __syncwarp();
+    }
+    int rows = 0;
+    for (int x0 = 0; x0 < n; x0 += 32) {
+        const int x = x0 + lane;
+        const bool k = x < n && keep[x];
+        const uint32_t bal = __ballot_sync(HB_FULL, k);
+        if (x < n) {
+            alns[p0 + x].keep = k ? 1 : 0;
+            alns[p0 + x].row = k ? rows + __popc(bal & ((1u << lane) - 1u)) : -1;
+        }
+        rows += __popc(bal);
+    }
+    for (uint32_t x = p0 + n + lane; x < p1; x += 32) { alns[x].keep = 0; alns[x].row = -1; }
+    if (lane == 0) n_rows[c] = (uint32_t)rows;
+}
+
+// S10a: insertion-column widths, warp per kept pair
+__global__ void __launch_bounds__(256)
+ins_max_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAln* __restrict__ alns,
+               const uint32_t* __restrict__ qrec_unit_off, const uint32_t* __restrict__ qrec,
+               const uint64_t* __restrict__ coff, uint32_t* __restrict__ ins) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= n_pairs) return;
+    const HbAln a = alns[p];
+    if (!a.keep) return;
+    const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
+    uint32_t* dst = ins + coff[pairs[p].cand];
+    for (int q = a.i_s + lane; q <= a.i_e; q += 32) {
+        const uint32_t d = (qr[q] >> 16) & 255u;
+        if (d) atomicMax(&dst[q], d);
+    }
+}
+
+// S10b: per candidate exclusive prefix of the widths (in place) and total columns. Warp per candidate.
+__global__ void __launch_bounds__(128)
+layout_kernel(const uint64_t* __restrict__ coff, const uint32_t* __restrict__ clen, uint32_t n_cand, int flank,
+              uint32_t* __restrict__ ins, uint32_t* __restrict__ n_cols) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= n_cand) return;
+    uint32_t* a = ins + coff[c];
+    const int L = (int)clen[c];
+    uint32_t carry = 0;
+    for (int q0 = 0; q0 < L; q0 += 32) {
+        const int q = q0 + lane;
+        const uint32_t v = q < L ? a[q] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(HB_FULL, x, o); if (lane >= o) x += t; }
+        if (q < L) a[q] = carry + x - v;
+        carry += __shfl_sync(HB_FULL, x, 31);
+    }
+    if (lane == 0) n_cols[c] = (uint32_t)(L + 2 * flank) + carry;
+}
+
+// S10c: write one MSA row per kept pair (symbol codes; the matrix was pre-filled with HB_SYM_GAP)
+__global__ void __launch_bounds__(256)
+msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAln* __restrict__ alns,
+                 const uint32_t* __restrict__ qrec_unit_off, const uint32_t* __restrict__ qrec,
+                 const uint64_t* __restrict__ coff, const uint32_t* __restrict__ clen, const uint32_t* __restrict__ pre,
+                 const uint32_t* __restrict__ n_cols, const uint64_t* __restrict__ mat_off,
+                 const uint32_t* __restrict__ gseq2, const uint32_t* __restrict__ gnmask, uint64_t tot, int flank,
+                 uint8_t* __restrict__ mat) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= n_pairs) return;
+    const HbAln a = alns[p];
+    if (!a.keep) return;
+    const HbLocus pr = pairs[p];
+    const uint32_t c = pr.cand;
+    const int rel = (int)pr.rel;
+    const int L = (int)clen[c];
+    const uint32_t C = n_cols[c];
+    const uint32_t* pc = pre + coff[c];
+    const uint32_t total_ins = C - (uint32_t)(L + 2 * flank);
+    uint8_t* row = mat + mat_off[c] + (size_t)a.row * C;
+    const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
+    for (int q = a.i_s + lane; q <= a.i_e; q += 32) {
+        const uint32_t v = qr[q];
+        const int64_t j = pr.j0 + q + ((int64_t)(v & 0xFFFF) - 32768);
+        const uint32_t col = (uint32_t)(q + flank) + pc[q];
+        if (!((v >> 24) & 1u)) row[col] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j);
+        const int d = (int)((v >> 16) & 255u);
+        for (int t = 0; t < d; ++t) row[col + 1 + t] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j + 1 + t);
+    }
+    for (int t = lane + 1; t <= flank; t += 32) {
+        const int ql = a.i_s - t, qh = a.i_e + t;
+        const uint32_t cl = (uint32_t)(ql + flank) + (ql >= 0 ? pc[ql] : 0u);
+        const uint32_t ch = (uint32_t)(qh + flank) + (qh < L ? pc[qh] : total_ins);
+        row[cl] = (uint8_t)target_base(gseq2, gnmask, tot, rel, a.j_s - t);
+        row[ch] = (uint8_t)target_base(gseq2, gnmask, tot, rel, a.j_e + t);
+    }
+}
+
+}  // namespace
+
+cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const uint32_t* clen, const uint64_t* goff,
+                                  const uint64_t* glen, uint32_t n_contig, uint64_t tot, int flank, HbAln* alns,
+                                  cudaStream_t s) {
+    if (n_pairs == 0) return cudaSuccess;
+    copy_filter_kernel<<<(n_pairs + 255) / 256, 256, 0, s>>>(pairs, n_pairs, clen, goff, glen, n_contig, tot, flank, alns);
+    return cudaGetLastError();
+}
+cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, int max_rows,
+                                  HbAln* alns, uint32_t* n_rows, cudaStream_t s) {
+    if (n_cand == 0) return cudaSuccess;
+    copy_select_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, max_rows, alns, n_rows);
+    return cudaGetLastError();
+}
+cudaError_t hb_ins_max_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
+                              const uint32_t* qrec, const uint64_t* coff, uint32_t* ins, cudaStream_t s) {
+    if (n_pairs == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)n_pairs * 32;
+    ins_max_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(pairs, n_pairs, alns, qrec_unit_off, qrec, coff, ins);
+    return cudaGetLastError();
+}
+cudaError_t hb_layout_launch(const uint64_t* coff, const uint32_t* clen, uint32_t n_cand, int flank, uint32_t* ins,
+                             uint32_t* n_cols, cudaStream_t s) {
+    if (n_cand == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)n_cand * 32;
+    layout_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(coff, clen, n_cand, flank, ins, n_cols);
+    return cudaGetLastError();
+}
+cudaError_t hb_msa_write_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
+                                const uint32_t* qrec, const uint64_t* coff, const uint32_t* clen, const uint32_t* pre,
+                                const uint32_t* n_cols, const uint64_t* mat_off, const uint32_t* gseq2,
+                                const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* mat, cudaStream_t s) {
+    if (n_pairs == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)n_pairs * 32;
+    msa_write_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(pairs, n_pairs, alns, qrec_unit_off, qrec, coff,
+                                                                       clen, pre, n_cols, mat_off, gseq2, gnmask, tot,
+                                                                       flank, mat);
+    return cudaGetLastError();
+}

@@ -1,0 +1,232 @@
+// hite_b200 -- kernel (ii), first half: per-candidate seed lookup in the minimizer index, diagonal
+// clustering of the hits and ranking of the candidate loci.
+//
+// Replaces the seeding/chaining stage of `minimap2 -ax map-ont -N 300 -p 0.2` as driven by
+// get_full_length_copies_minimap2 (reference module/Util.py:7952-7961); follows HB-align S3..S6
+//  and is bit-identical to oracle/hbo_align.c::hbo_find_loci.
+#include "hb_common.cuh"
+#include "hb_seed.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t* __restrict__ a, uint64_t lo, uint64_t hi, uint64_t key) {
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// S3/S4 count: one thread per candidate minimizer.
+__global__ void seed_count_kernel(const uint64_t* __restrict__ cm, uint32_t n_cm, const uint64_t* __restrict__ cgoff,
+                                  uint32_t n_cand, const uint64_t* __restrict__ idx, uint64_t n_idx,
+                                  const uint32_t* __restrict__ bucket, int bucket_shift, int occ_cap,
+                                  uint32_t* __restrict__ m_cand, uint32_t* __restrict__ m_qidx,
+                                  uint32_t* __restrict__ m_lo, uint32_t* __restrict__ m_cnt) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_cm) return;
+    const uint64_t e = cm[m];
+    const uint64_t pos = (e >> 1) & 0xFFFFFFFFull;
+    const uint32_t h = (uint32_t)(e >> 33);
+    // candidate = last c with cgoff[c] <= pos
+    uint32_t lo = 0, hi = n_cand;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (cgoff[mid] <= pos) lo = mid + 1; else hi = mid; }
+    const uint32_t c = lo - 1;
+    // first minimizer of this candidate: lower_bound over positions of cgoff[c]
+    uint32_t a = 0, b = m;
+    const uint64_t cstart = cgoff[c];
+    while (a < b) { uint32_t mid = (a + b) >> 1; if (((cm[mid] >> 1) & 0xFFFFFFFFull) < cstart) a = mid + 1; else b = mid; }
+    const uint32_t qidx = m - a;
+    m_cand[m] = c; m_qidx[m] = qidx;
+    uint32_t cnt = 0, first = 0;
+    if (qidx < 8192 && n_idx > 0) {
+        const uint32_t bk = h >> (30 - HB_SEED_BUCKET_BITS);
+        (void)bucket_shift;
+        const uint64_t blo = bucket[bk], bhi = bucket[bk + 1];
+        const uint64_t l = lower_bound_u64(idx, blo, bhi, (uint64_t)h << 33);
+        const uint64_t r = lower_bound_u64(idx, l, bhi, ((uint64_t)h + 1) << 33);
+        first = (uint32_t)l;
+        cnt = (uint32_t)min((uint64_t)occ_cap, r - l);
+    }
+    m_lo[m] = first; m_cnt[m] = cnt;
+}
+
+// S4 fill: 8 lanes per candidate minimizer
+__global__ void seed_fill_kernel(const uint64_t* __restrict__ cm, uint32_t n_cm, const uint64_t* __restrict__ cgoff,
+                                 const uint64_t* __restrict__ idx, uint64_t tot, int k,
+                                 const uint32_t* __restrict__ m_cand, const uint32_t* __restrict__ m_qidx,
+                                 const uint32_t* __restrict__ m_lo, const uint32_t* __restrict__ m_cnt,
+                                 const uint32_t* __restrict__ m_off, uint64_t* __restrict__ hits) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t m = t >> 3, sub = t & 7;
+    if (m >= n_cm) return;
+    const uint32_t cnt = m_cnt[m];
+    if (cnt == 0) return;
+    const uint64_t e = cm[m];
+    const uint32_t c = m_cand[m];
+    const int64_t qpos = (int64_t)(((e >> 1) & 0xFFFFFFFFull) - cgoff[c]);
+    const uint32_t qs = (uint32_t)(e & 1);
+    const uint64_t base = m_off[m];
+    const uint64_t lo = m_lo[m];
+    for (uint32_t x = sub; x < cnt; x += 8) {
+        const uint64_t g = idx[lo + x];
+        const int64_t gpos = (int64_t)((g >> 1) & 0xFFFFFFFFull);
+        const uint32_t rel = qs ^ (uint32_t)(g & 1);
+        const int64_t d = rel ? ((int64_t)tot - gpos - k) - qpos + HB_DIAG_OFF : gpos - qpos + HB_DIAG_OFF;
+        hits[base + x] = ((uint64_t)c << 47) | ((uint64_t)rel << 46) | ((uint64_t)d << 13) | (uint64_t)m_qidx[m];
+    }
+}
+
+// S5: cluster starts
+__global__ void cluster_flag_kernel(const uint64_t* __restrict__ hits, uint64_t n, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t f = 1;
+    if (i > 0) {
+        const uint64_t a = hits[i - 1], b = hits[i];
+        if ((a >> 46) == (b >> 46)) {
+            const int64_t da = (int64_t)((a >> 13) & 0x1FFFFFFFFull), db = (int64_t)((b >> 13) & 0x1FFFFFFFFull);
+            if (db - da <= HB_DGAP) f = 0;
+        }
+    }
+    flag[i] = f;
+}
+__global__ void cluster_start_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ cid, uint64_t n,
+                                     uint32_t* __restrict__ cl_start) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) cl_start[cid[i]] = (uint32_t)i;
+}
+// per-candidate first cluster: clusters are ordered by candidate
+__global__ void cand_first_cluster_kernel(const uint64_t* __restrict__ hits, const uint32_t* __restrict__ cl_start,
+                                          uint32_t n_cl, uint32_t n_cand, uint32_t* __restrict__ cand_first) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_cl) return;
+    const uint32_t c = (uint32_t)(hits[cl_start[x]] >> 47);
+    const uint32_t pc = x > 0 ? (uint32_t)(hits[cl_start[x - 1]] >> 47) : 0xFFFFFFFFu;
+    if (x == 0 || pc != c) {
+        // candidates without clusters between pc and c get an empty range later (cand_first == END marker)
+        cand_first[c] = x;
+    }
+    (void)n_cand;
+}
+
+// S5/S6: rank the clusters of a candidate (n desc, rel asc, dmin asc), keep the best max_loci.
+// One warp per candidate.
+__global__ void __launch_bounds__(128)
+rank_select_kernel(const uint64_t* __restrict__ hits, uint64_t n_hits, const uint32_t* __restrict__ cl_start,
+                   uint32_t n_cl, const uint32_t* __restrict__ cand_first, uint32_t n_cand, int max_loci,
+                   HbLocus* __restrict__ loci, uint32_t* __restrict__ n_loci) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= n_cand) return;
+    const uint32_t first = cand_first[c];
+    uint32_t nvalid = 0;
+    if (first != 0xFFFFFFFFu) {
+        // end of this candidate's cluster range
+        uint32_t end = first;
+        {   // scan forward (warp-strided) for the first cluster belonging to another candidate
+            uint32_t lo = first, hi = n_cl;
+            while (lo < hi) {   // binary search on candidate id (monotone)
+                uint32_t mid = (lo + hi) >> 1;
+                if ((uint32_t)(hits[cl_start[mid]] >> 47) <= c) lo = mid + 1; else hi = mid;
+            }
+            end = lo;
+        }
+        auto cl_n = [&](uint32_t x) -> uint32_t {
+            const uint64_t e = (x + 1 < n_cl) ? cl_start[x + 1] : n_hits;
+            return (uint32_t)(e - cl_start[x]);
+        };
+        for (uint32_t x0 = first; x0 < end; x0 += 32) {
+            const uint32_t x = x0 + lane;
+            bool valid = false;
+            uint32_t nx = 0, relx = 0; int64_t dminx = 0;
+            if (x < end) {
+                nx = cl_n(x);
+                valid = nx >= HB_MIN_SEEDS;
+                const uint64_t k0 = hits[cl_start[x]];
+                relx = (uint32_t)((k0 >> 46) & 1); dminx = (int64_t)((k0 >> 13) & 0x1FFFFFFFFull);
+            }
+            uint32_t rank = 0;
+            if (valid) {
+                for (uint32_t y = first; y < end; ++y) {
+                    if (y == x) continue;
+                    const uint32_t ny = cl_n(y);
+                    if (ny < HB_MIN_SEEDS) continue;
+                    const uint64_t k1 = hits[cl_start[y]];
+                    const uint32_t rely = (uint32_t)((k1 >> 46) & 1); const int64_t dminy = (int64_t)((k1 >> 13) & 0x1FFFFFFFFull);
+                    const bool better = (ny != nx) ? (ny > nx) : ((rely != relx) ? (rely < relx) : (dminy < dminx));
+                    rank += better ? 1u : 0u;
+                }
+                if (rank < (uint32_t)max_loci) {
+                    const uint64_t e = (x + 1 < n_cl) ? cl_start[x + 1] : n_hits;
+                    const int64_t dmax = (int64_t)((hits[e - 1] >> 13) & 0x1FFFFFFFFull);
+                    HbLocus L;
+                    L.cand = c; L.rel = relx; L.nseeds = nx; L.rank = rank; L.dmin = dminx; L.dmax = dmax;
+                    L.j0 = ((dminx + dmax) >> 1) - HB_DIAG_OFF;
+                    loci[(size_t)c * max_loci + rank] = L;
+                }
+            }
+            nvalid += __popc(__ballot_sync(HB_FULL, valid));
+        }
+    }
+    if (lane == 0) n_loci[c] = min(nvalid, (uint32_t)max_loci);
+}
+
+// compact pair list: pair_off = exclusive scan of n_loci
+__global__ void pair_emit_kernel(const HbLocus* __restrict__ loci, const uint32_t* __restrict__ n_loci,
+                                 const uint32_t* __restrict__ pair_off, uint32_t n_cand, int max_loci,
+                                 HbLocus* __restrict__ pairs) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = t / (uint32_t)max_loci, r = t % (uint32_t)max_loci;
+    if (c >= n_cand || r >= n_loci[c]) return;
+    pairs[pair_off[c] + r] = loci[(size_t)c * max_loci + r];
+}
+
+}  // namespace
+
+cudaError_t hb_seed_count_launch(const uint64_t* cm, uint32_t n_cm, const uint64_t* cgoff, uint32_t n_cand,
+                                 const uint64_t* idx, uint64_t n_idx, const uint32_t* bucket, int occ_cap,
+                                 uint32_t* m_cand, uint32_t* m_qidx, uint32_t* m_lo, uint32_t* m_cnt, cudaStream_t s) {
+    if (n_cm == 0) return cudaSuccess;
+    seed_count_kernel<<<(n_cm + 255) / 256, 256, 0, s>>>(cm, n_cm, cgoff, n_cand, idx, n_idx, bucket, 0, occ_cap,
+                                                          m_cand, m_qidx, m_lo, m_cnt);
+    return cudaGetLastError();
+}
+cudaError_t hb_seed_fill_launch(const uint64_t* cm, uint32_t n_cm, const uint64_t* cgoff, const uint64_t* idx,
+                                uint64_t tot, int k, const uint32_t* m_cand, const uint32_t* m_qidx,
+                                const uint32_t* m_lo, const uint32_t* m_cnt, const uint32_t* m_off, uint64_t* hits,
+                                cudaStream_t s) {
+    if (n_cm == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)n_cm * 8;
+    seed_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(cm, n_cm, cgoff, idx, tot, k, m_cand, m_qidx,
+                                                                       m_lo, m_cnt, m_off, hits);
+    return cudaGetLastError();
+}
+cudaError_t hb_cluster_flag_launch(const uint64_t* hits, uint64_t n, uint32_t* flag, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    cluster_flag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hits, n, flag);
+    return cudaGetLastError();
+}
+cudaError_t hb_cluster_start_launch(const uint32_t* flag, const uint32_t* cid, uint64_t n, uint32_t* cl_start,
+                                    cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    cluster_start_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flag, cid, n, cl_start);
+    return cudaGetLastError();
+}
+cudaError_t hb_rank_select_launch(const uint64_t* hits, uint64_t n_hits, const uint32_t* cl_start, uint32_t n_cl,
+                                  uint32_t* cand_first, uint32_t n_cand, int max_loci, HbLocus* loci,
+                                  uint32_t* n_loci, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(cand_first, 0xFF, sizeof(uint32_t) * n_cand, s);
+    if (e != cudaSuccess) return e;
+    if (n_cl > 0)
+        cand_first_cluster_kernel<<<(n_cl + 255) / 256, 256, 0, s>>>(hits, cl_start, n_cl, n_cand, cand_first);
+    const uint64_t threads = (uint64_t)n_cand * 32;
+    rank_select_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(hits, n_hits, cl_start, n_cl, cand_first,
+                                                                          n_cand, max_loci, loci, n_loci);
+    return cudaGetLastError();
+}
+cudaError_t hb_pair_emit_launch(const HbLocus* loci, const uint32_t* n_loci, const uint32_t* pair_off,
+                                uint32_t n_cand, int max_loci, HbLocus* pairs, cudaStream_t s) {
+    const uint64_t threads = (uint64_t)n_cand * (uint64_t)max_loci;
+    if (threads == 0) return cudaSuccess;
+    pair_emit_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(loci, n_loci, pair_off, n_cand, max_loci, pairs);
+    return cudaGetLastError();
+}

@@ -88,6 +88,75 @@ int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_ascii, const u
                      const uint64_t* cand_off, int te_type, int plant, int result_type,
                      hb_call* calls, uint8_t* cons_out, uint64_t cons_cap);
 
+/* hb_call.flags */
+#define HB_FLAG_NO_COPIES 1 /* no full-length copy survived: the reference writes no member file for such a
+                               query (module/Util.py:8125-8137) and it silently drops out of the result */
+
+/*
+ * hb_genome_load -- kernel (i), part 1: upload the genome (the contigs of the `-r reference` FASTA,
+ * upper/lower case ASCII, read_fasta semantics module/Util.py:1650-1670) and pack it to 2 bit/base
+ * + N mask in one padded coordinate space.  contig_off has n_contig+1 entries into `ascii`.
+ * Replaces reading the reference into a Python dict (module/Util.py:8073) and feeds what
+ * `minimap2 -d` (module/Util.py:7941) indexes.
+ */
+int hb_genome_load(hb_ctx* ctx, const uint8_t* ascii, const uint64_t* contig_off, uint32_t n_contig);
+
+/*
+ * hb_index_build -- kernel (i), part 2: (k,w)-minimizer sketch of both strands, hand-written LSD
+ * radix sort with shared-memory binning, 22-bit bucket table.  Replaces `minimap2 -I 20G -d ref.mmi`
+ * (module/Util.py:7938-7947).  8 <= k <= 15, 1 <= w <= 16; HiTE-equivalent default k=15, w=10.
+ * Timing: k_ms[0] sketch, k_ms[1] sort, k_ms[2] bucket table.
+ */
+int hb_index_build(hb_ctx* ctx, int k, int w);
+int hb_genome_info(hb_ctx* ctx, uint64_t* total_padded, uint64_t* n_minimizers, uint64_t* contig_goff, uint32_t cap);
+
+typedef struct {
+    int32_t occ_cap;      /* occurrences used per minimizer (first occ_cap in position order); 512 */
+    int32_t max_loci;     /* loci aligned per candidate (minimap2 -N 300 analogue, module/Util.py:7955); 128 */
+    int32_t flank;        /* flanking_len, module/Util.py:8103-8105; 50 */
+    int32_t max_rows;     /* "100 longest" of ready_for_MSA.sh, module/Util.py:10409-10412; 100 */
+    int32_t te_type;      /* HB_TE_* */
+    int32_t plant;        /* --plant */
+    int32_t result_type;  /* 1 = 'cons' */
+    int32_t pad;
+    uint64_t tb_budget_bytes; /* HBM budget of the traceback stream, 0 = 16 GiB */
+} hb_params;
+
+/* One candidate x locus pair: what get_copies_minimap2 (module/Util.py:7977-8030) returns per SAM
+ * record -- (subject, start, end, aligned_len, strand) -- plus the alignment summary. */
+typedef struct {
+    uint32_t cand;
+    int32_t rank, rel, nseeds; /* rel: 0 '+', 1 '-' */
+    int32_t score, i_s, i_e;   /* query span of the local alignment, inclusive */
+    int32_t keep, row, contig; /* keep: passed the reference's copy rules; row: MSA row or -1 */
+    int64_t j0, j_s, j_e;      /* band origin / target span in oriented padded coordinates */
+    int64_t start1, end1;      /* 1-based inclusive contig coordinates (module/Util.py:8017-8018) */
+    int32_t ext_len, pad;
+} hb_copy;
+
+/*
+ * hb_adjust -- one `flank_region_align_v5`-equivalent round over n_cand candidates (module/Util.py:
+ * 8032-8299 up to the per-candidate verdict): seed lookup + diagonal clustering (replaces minimap2
+ * seeding/chaining, :7952-7961), banded affine Smith-Waterman per candidate x locus (replaces
+ * minimap2 base alignment), the copy rules of :8003-8025 and :8095-8115, the 100-longest subset of
+ * :10409-10412, a candidate-anchored star MSA (replaces mafft, :10416), then
+ * remove_sparse_col_in_align_file + judge_boundary_v5 (:10419-10428).
+ * calls[i] mirrors is_TE_from_align_file's tuple for candidate i; consensus bytes are fetched with
+ * hb_last_cons (calls[i].cons_off indexes that buffer); *cons_bytes = its size.
+ * Timing: k_ms[0] pack+sketch candidates, [1] seed/sort/cluster/rank, [2] extension+traceback,
+ * [3] copy rules + MSA, [4] clean + judge, [5] compaction, [6] #pairs, [7] million DP steps.
+ */
+int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii, const uint64_t* cand_off,
+              const hb_params* prm, hb_call* calls, uint64_t* cons_bytes);
+int hb_last_cons(hb_ctx* ctx, uint8_t* out, uint64_t cap);
+/* copies of the last hb_adjust, ordered by (candidate, rank); pass out=NULL to query the count */
+int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t* n);
+
+/* parity/debug getters: the sorted minimizer index (hash<<33 | pos<<1 | strand) and the raw
+ * (pre-clean) MSA of one candidate of the last hb_adjust as ASCII */
+int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap);
+int hb_last_msa(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii, uint64_t cap, int32_t* R, int32_t* C);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,33 @@ int hbo_find_anchor(const char *cand, int cand_len, const char *m, int R, int C,
 int hbo_judge_v5(const char *cand, int cand_len, const char *m, int R, int C, int plant,
                  int result_type_cons, hbo_call *out, char *cons);
 
+/* ---- HB-align restatement (hbo_align.c) ---- */
+#include <stdint.h>
+typedef struct hbo_genome hbo_genome;
+typedef struct { int32_t score, i_s, i_e, pad; int64_t j_s, j_e; } hbo_aln;   /* j: oriented coords */
+typedef struct { uint32_t cand, rel, nseeds, rank; int64_t dmin, dmax, j0; } hbo_locus;
+typedef struct {
+    int32_t rank, rel, score, i_s, i_e, contig;
+    int64_t j_s, j_e;        /* oriented global coords, inclusive */
+    int64_t start1, end1;    /* 1-based inclusive forward coords inside the contig (Util.py:8017-8018) */
+    int32_t keep, ext_len;
+} hbo_copy;
+
+hbo_genome *hbo_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_t n);
+void hbo_genome_free(hbo_genome *g);
+uint64_t hbo_genome_total(const hbo_genome *g);
+uint64_t hbo_genome_contig_off(const hbo_genome *g, uint32_t c);
+uint64_t hbo_minimizers_codes(const uint8_t *code, uint64_t tot, int k, int w, uint64_t *out, uint64_t cap);
+uint64_t hbo_minimizers(const hbo_genome *g, int k, int w, uint64_t *out, uint64_t cap);
+void hbo_sort_u64(uint64_t *keys, uint64_t n);
+int hbo_align_pair(const hbo_genome *g, const uint8_t *q, int L, int rel, int64_t j0, hbo_aln *out, uint32_t *qrec);
+uint64_t hbo_find_loci(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w,
+                       const uint8_t *cand_codes, const uint64_t *coff, uint32_t n_cand,
+                       int occ_cap, int max_loci, hbo_locus *out, uint64_t cap);
+int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w,
+                      const uint8_t *cand_ascii, int L, int occ_cap, int max_loci, int flank, int max_rows,
+                      hbo_copy *copies, int *n_copies, uint8_t *matrix, uint64_t matrix_cap, int *R_out, int *C_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,3 +72,81 @@ def find_near_matches_ends(p, s, d):
 
 def levenshtein(a, b):
     return lib().hbo_levenshtein(a.encode(), len(a), b.encode(), len(b))
+
+
+# ---------------------------------------------------------------------------------------------
+# HB-align restatement (oracle/hbo_align.c)
+class HboCopy(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("rel", C.c_int32), ("score", C.c_int32), ("i_s", C.c_int32),
+                ("i_e", C.c_int32), ("contig", C.c_int32), ("j_s", C.c_int64), ("j_e", C.c_int64),
+                ("start1", C.c_int64), ("end1", C.c_int64), ("keep", C.c_int32), ("ext_len", C.c_int32)]
+
+
+class HboLocus(C.Structure):
+    _fields_ = [("cand", C.c_uint32), ("rel", C.c_uint32), ("nseeds", C.c_uint32), ("rank", C.c_uint32),
+                ("dmin", C.c_int64), ("dmax", C.c_int64), ("j0", C.c_int64)]
+
+
+class Genome:
+    """CPU genome + minimizer index (restatement of S1/S2)."""
+
+    def __init__(self, contig_seqs, k=15, w=10):
+        import numpy as np
+        L = lib()
+        L.hbo_genome_create.restype = C.c_void_p
+        L.hbo_genome_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.hbo_genome_free.argtypes = [C.c_void_p]
+        L.hbo_genome_total.restype = C.c_uint64
+        L.hbo_genome_total.argtypes = [C.c_void_p]
+        L.hbo_minimizers.restype = C.c_uint64
+        L.hbo_minimizers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+        L.hbo_sort_u64.argtypes = [C.c_void_p, C.c_uint64]
+        seqs = [np.frombuffer(s, dtype=np.uint8) if isinstance(s, (bytes, bytearray)) else np.asarray(s, dtype=np.uint8)
+                for s in contig_seqs]
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(s) for s in seqs])
+        flat = np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)
+        self._L = L
+        self.k, self.w = k, w
+        self.g = L.hbo_genome_create(flat.ctypes.data, off.ctypes.data, len(seqs))
+        self.total = L.hbo_genome_total(self.g)
+        n = L.hbo_minimizers(self.g, k, w, None, 0)
+        self.mm_pos_order = np.zeros(n, dtype=np.uint64)
+        L.hbo_minimizers(self.g, k, w, self.mm_pos_order.ctypes.data, n)
+        self.index = self.mm_pos_order.copy()
+        L.hbo_sort_u64(self.index.ctypes.data, n)
+
+    def close(self):
+        if self.g:
+            self._L.hbo_genome_free(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def candidate_msa(self, cand, occ_cap=512, max_loci=128, flank=50, max_rows=100):
+        """-> (copies[list of dict], rows[list of str]) for one candidate (S3..S10)."""
+        import numpy as np
+        L = self._L
+        cb = cand if isinstance(cand, (bytes, bytearray)) else cand.encode()
+        n = len(cb)
+        copies = (HboCopy * (max_loci + 1))()
+        ncp = C.c_int(0)
+        cap = (max_rows + 1) * (n + 2 * flank) * 4 + 1024
+        mat = np.zeros(cap, dtype=np.uint8)
+        R, Cn = C.c_int(0), C.c_int(0)
+        L.hbo_candidate_msa.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_uint64, C.c_void_p, C.c_void_p]
+        rc = L.hbo_candidate_msa(self.g, self.index.ctypes.data, len(self.index), self.k, self.w, cb, n, occ_cap,
+                                 max_loci, flank, max_rows, copies, C.byref(ncp), mat.ctypes.data, cap,
+                                 C.byref(R), C.byref(Cn))
+        if rc != 0:
+            raise RuntimeError("hbo_candidate_msa: matrix capacity exceeded")
+        cps = [{f: getattr(copies[i], f) for f, _ in HboCopy._fields_} for i in range(ncp.value)]
+        raw = mat[:R.value * Cn.value].tobytes()
+        rows = [raw[r * Cn.value:(r + 1) * Cn.value].decode() for r in range(R.value)]
+        return cps, rows
