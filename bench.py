@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- HiTE dynamic boundary adjustment on B200: candidates boundary-adjusted per second.
+
+One "step" = one ``flank_region_align_v5``-equivalent round (reference module/Util.py:8032) over the
+workload's candidate batch: copy search (seed + banded SW), star MSA, sparse-column removal, column
+vote and boundary call.  Workload at N=1 = BASELINE.json configs[1] ("synthetic 100 Mbp genome, 10k
+planted TIR candidates, 1xB200"); at N>1 the genome and candidate set scale with N (weak scaling:
+N x 100 Mbp replicated on every GPU, 10k candidates per rank, one NCCL all-gather of the emitted
+consensus records per step -- the only collective on the path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--small]
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU implementation of the same path
+(the plain-C port under oracle/, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def workload_for(world, small=False):
+    from hite_b200 import synth
+    if small:
+        return synth.make_workload(genome_bp=4_000_000 * world, n_contigs=2, n_families=40 * world, cands_per_family=10,
+                                   copies=(10, 40), seed=1), "synthetic 4 Mbp x N, 400 TIR candidates per GPU (--small)"
+    wl = synth.make_workload(genome_bp=100_000_000 * world, n_contigs=10, n_families=1000 * world, cands_per_family=10,
+                             copies=(10, 40), length=(200, 2000), seed=1)
+    return wl, "synthetic %d Mbp genome, %d planted TIR candidates (10k per GPU), %dxB200" % (
+        100 * world, len(wl.cand_seqs), world)
+
+
+def algo_bytes_pair(L):
+    """Algorithmic bytes of one candidate x copy banded extension:
+    2-bit+N query and target window in, 4 B per query position of edit record out, 56 B result."""
+    return (2 * L + 64) * 3.0 / 8.0 + 4.0 * L + 56.0
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(wl, cand_idx, threads):
+    """The CPU implementation of the path (plain-C port, oracle/): per candidate copy search + star MSA
+    + sparse-column removal + judge.  Index build is outside the timed region (as for the GPU arm)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    G = oracle.Genome(wl.contig_seqs)
+
+    def one(i):
+        seq = wl.cand_seqs[i]
+        cps, rows = G.candidate_msa(seq)
+        if not rows:
+            return 0
+        r = oracle.judge_v5(seq.decode(), oracle.remove_sparse_cols(rows), 1)
+        return int(r["is_te"])
+
+    one(cand_idx[0])
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        n_te = sum(ex.map(one, cand_idx))
+    dt = time.perf_counter() - t0
+    return dt, n_te
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hite_b200")
+    ap.add_argument("--small", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        print(json.dumps({"error": "launch with torch.distributed.run for --gpus > 1"}))
+        return 2
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl, wname = workload_for(1, args.small)
+        per_step = min(len(wl.cand_seqs), max(64, 8 * cores))
+        times = []
+        for step in range(args.warmup + args.steps):
+            idx = [(step * per_step + i) % len(wl.cand_seqs) for i in range(per_step)]
+            dt, _ = cpu_reference_run(wl, idx, cores)
+            if step >= args.warmup:
+                times.append(dt)
+        dt = float(np.mean(times))
+        val = per_step / dt
+        line = {"impl": "reference", "metric": "candidate TEs boundary-adjusted/sec", "value": val, "unit": "candidates/s",
+                "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": wname, "sample": "%d candidates per step" % per_step},
+                "cpu_baseline": {"value": val, "unit": "candidates/s", "cores": cores, "kind": "port",
+                                 "sample": "%d candidates of the same workload per step, %d threads (plain-C port of the path, "
+                                           "oracle/; the reference's own aligners minimap2/mafft are not installed)" % (per_step, cores)},
+                "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------ GPU arm
+    import torch
+    import torch.distributed as dist
+    import hite_b200
+    if not torch.cuda.is_available():
+        raise hite_b200.HiteB200Error("bench.py needs a CUDA device: there is no CPU fallback on the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl, wname = workload_for(world, args.small)
+    my = list(range(rank, len(wl.cand_seqs), world))            # embarrassingly sharded candidates
+    my_cands = [wl.cand_seqs[i] for i in my]
+    ctx = hite_b200.Context(local)
+    t0 = time.perf_counter()
+    t_load = ctx.load_genome(wl.contig_seqs)
+    t_idx = ctx.build_index(15, 10)
+    setup_s = time.perf_counter() - t0
+    info = ctx.genome_info()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_results(res):
+        """The path's only exchange: all-gather of emitted (index, consensus) records before the
+        get_nonRedundant_lib merge (reference main.py:652-664 cat >>)."""
+        if world == 1:
+            return sum(r["is_te"] for r in res)
+        payload = b"".join(b"%d\t%s\n" % (my[i], r["cons"].encode()) for i, r in enumerate(res) if r["is_te"])
+        n = torch.tensor([len(payload)], device="cuda", dtype=torch.int64)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        mx = int(max(int(s.item()) for s in sizes))
+        buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+        if payload:
+            buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
+        out = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(out, buf)
+        return sum(bytes(o[:int(s.item())].cpu().numpy()).count(b"\n") for o, s in zip(out, sizes))
+
+    for _ in range(args.warmup):
+        res = ctx.adjust(my_cands, "tir", 1)
+        gather_results(res)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev_ms, ext_ms, stage = [], [], np.zeros(8)
+    h2d = d2h = launches = 0
+    n_te_total = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = ctx.adjust(my_cands, "tir", 1)
+        tm = ctx.timing()
+        n_te_total = gather_results(res)
+        dev_ms.append(tm["kernel_ms"]); ext_ms.append(tm["k_ms"][2]); stage += np.array(tm["k_ms"])
+        h2d, d2h, launches = tm["h2d_bytes"], tm["d2h_bytes"], tm["launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # max over ranks
+    stats = torch.tensor([wall, float(np.sum(dev_ms))], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    wall_max, dev_max = float(stats[0]), float(stats[1]) * 1e-3
+    n_total = len(wl.cand_seqs)
+    copies = ctx.last_copies()
+    lens = np.array([len(c) for c in my_cands])
+    pair_L = lens[copies["cand"]]
+    algo_bytes = float(np.sum(algo_bytes_pair(pair_L)))
+    ext_s = float(np.mean(ext_ms)) * 1e-3
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = algo_bytes / ext_s / 1e9 if ext_s > 0 else 0.0
+        dp_cells = float(stage[7] / args.steps) * 1e6 * 32
+        line = {
+            "metric": "candidate TEs boundary-adjusted/sec", "value": n_total * args.steps / dev_max, "unit": "candidates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_max / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": wname, "genome_bp": wl.genome_bp, "candidates": n_total, "k": 15, "w": 10,
+                       "max_loci": 128, "band": 64, "l2": "inputs larger than L2 (packed genome+index %.0f MB, traceback stream %.1f GB/step)"
+                       % ((info["total_padded"] * 0.375 + info["n_minimizers"] * 8) / 1e6, float(stage[7] / args.steps) * 1e6 * 16 / 1e9),
+                       "parallelism": "candidates sharded over %d GPU(s), genome+index replicated, 1 NCCL all-gather/step" % world},
+            "e2e": {"value": n_total * args.steps / wall_max, "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches) * args.steps,
+            "clocks": clocks,
+            "roofline": {"kernel": "extend_kernel (banded SW + traceback, hb_extend.cu)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "note": "integer-ALU-bound DP: %.2f GCUPS; algorithmic bytes/pair=(2L+64)*3/8+4L+56" % (dp_cells / ext_s / 1e9 if ext_s else 0),
+                         "kernel_ms": ext_s * 1e3, "pairs": int(len(copies))},
+            "stages_ms": {k: float(v / args.steps) for k, v in zip(
+                ("sketch_cands", "seed_sort_cluster", "extend", "copy_rules_msa", "clean_judge", "compact"), stage[:6])},
+            "setup": {"genome_load_ms": t_load["kernel_ms"] + t_load["h2d_ms"], "index_build_ms": t_idx["kernel_ms"],
+                      "index_Mbp_per_s": wl.genome_bp / 1e6 / max(1e-9, t_idx["kernel_ms"] * 1e-3), "setup_wall_s": setup_s,
+                      "n_minimizers": int(info["n_minimizers"])},
+            "calls": {"is_te": int(n_te_total)},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            per = min(len(wl.cand_seqs), max(64, 8 * cores))
+            dt, _ = cpu_reference_run(wl, list(range(per)), cores)
+            line["cpu_baseline"] = {"value": per / dt, "unit": "candidates/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d candidates of the same workload, %d threads, %.1f s (plain-C port of the "
+                                              "path under oracle/)" % (per, cores, dt)}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
