@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs brought back in gpurun_out/ into committed text under profiles/.
+
+  python tools/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/r1_launches.md "<command>"
+  python tools/ncu_summary.py full gpurun_out/prof_r1.ncu-rep profiles/r1_full.md "<command>"
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "smsp__inst_executed.sum",
+        "launch__grid_size", "launch__block_size", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct",
+        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
+        "smsp__warp_issue_stalled_barrier_per_warp_active.pct"]
+
+
+def launches(path, out, cmd):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        name = row["Kernel Name"].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        v = v / 1e6 if u in ("ns", "nsecond") else v / 1e3 if u in ("us", "usecond") else v * 1e3 if u in ("s", "second") else v
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v[1] for v in agg.values())
+    with open(out, "w") as f:
+        f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
+        f.write("command: `%s`\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n" % cmd)
+        for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write("| %s | %d | %.3f | %.1f%% |\n" % (k, v[0], v[1], 100 * v[1] / tot))
+        f.write("| **total** | %d | %.3f | 100%% |\n" % (sum(v[0] for v in agg.values()), tot))
+
+
+def full(path, out, cmd):
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        f.write("# ncu --set full --clock-control none (one capture per kernel; per launch)\n\ncommand: `%s`\n\n" % cmd)
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")].split("(")[0].replace("<unnamed>::", "")
+            f.write("## %s\n\n| metric | value | unit |\n|---|---:|---|\n" % name)
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write("| %s | %s | %s |\n" % (k, r[i], units[i]))
+            try:
+                rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", ""))
+                wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
+                f.write("| traffic (read+write) | %.3f | %s |\n" % (rd + wr, units[hdr.index("dram__bytes_read.sum")]))
+            except Exception:
+                pass
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
