@@ -33,6 +33,23 @@ __device__ __forceinline__ int target_base(const uint32_t* __restrict__ gseq2, c
     return c < 4 ? 3 - c : 4;
 }
 
+// One DP cell.  H >= 0; E and F are kept clamped at 0 (only positive gap states can ever be chosen
+// by H or walked by the traceback), which lets every recurrence be a single
+// 3-input max (VIMNMX3) and the left/up neighbour travel as one packed 32-bit shuffle.
+//   nib: bits0-1 source of H (0 stop, 1 diag, 2 E, 3 F), bit2 E extended, bit3 F extended
+#define HB_CELL(hl, el, hu, fu, hd, qb, tbse, H, E, F, NIB)                         \
+    {                                                                               \
+        const int t_e = (el) - 2, hm_e = (hl) - 6;                                  \
+        const int t_f = (fu) - 2, hm_f = (hu) - 6;                                  \
+        E = __vimax3_s32(t_e, hm_e, 0);                                             \
+        F = __vimax3_s32(t_f, hm_f, 0);                                             \
+        const int dg = (hd) + (((qb) == (tbse)) ? 2 : -4);                          \
+        H = __vimax3_s32_relu(dg, E, F);                                            \
+        const uint32_t src = (dg == H) ? 1u : ((E == H) ? 2u : 3u);                 \
+        const uint32_t fl = src | ((t_e > hm_e) ? 4u : 0u) | ((t_f > hm_f) ? 8u : 0u); \
+        NIB = (H > 0) ? fl : 0u;                                                    \
+    }
+
 __global__ void __launch_bounds__(EXT_WARPS * 32)
 extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi,
               const uint32_t* __restrict__ gseq2, const uint32_t* __restrict__ gnmask, uint64_t tot,
@@ -41,8 +58,10 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
               const uint32_t* __restrict__ tb_unit_off, uint32_t tb_unit_base, uint32_t* __restrict__ tbuf,
               const uint32_t* __restrict__ qrec_unit_off, uint32_t* __restrict__ qrec,
               HbAln* __restrict__ alns) {
-    __shared__ uint8_t s_rq[EXT_WARPS][128];
-    __shared__ uint8_t s_rt[EXT_WARPS][128];
+    // per-warp sequence windows for one super-step (64 anti-diagonals): positions
+    // [half0 - 16, half0 + 48) of the query (index = i - half0 + 16) and of the target (j' - half0 + 16)
+    __shared__ uint8_t s_rq[EXT_WARPS][64];
+    __shared__ uint8_t s_rt[EXT_WARPS][64];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t p = pair_lo + blockIdx.x * EXT_WARPS + wid;
     if (p >= pair_hi) return;
@@ -56,94 +75,76 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
     uint32_t* tb = tbuf + ((size_t)(tb_unit_off[p] - tb_unit_base) << 8);      // 256 words per unit
     const int n_super = (2 * L + 62 + 63) >> 6;
 
-    auto fill = [&](int x) {
-        rq[x & 127] = (uint8_t)((x >= 0 && x < L) ? packed_base(cseq2, cnmask, cstart + (uint64_t)x) : 4);
-        rt[x & 127] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j0 + x);
+    // query N = 4, target N = 5: never equal, so one compare scores a cell
+    auto qsym = [&](int x) -> uint8_t {
+        return (uint8_t)((x >= 0 && x < L) ? packed_base(cseq2, cnmask, cstart + (uint64_t)x) : 4);
     };
-    fill(-48 + lane);
-    fill(-16 + lane);
+    auto tsym = [&](int x) -> uint8_t {
+        const int c = target_base(gseq2, gnmask, tot, rel, j0 + x);
+        return (uint8_t)(c < 4 ? c : 5);
+    };
+    // window of the first super-step (half0 = -16): positions [-32, 32)
+    rq[lane] = qsym(-32 + lane); rt[lane] = tsym(-32 + lane);
+    rq[32 + lane] = qsym(lane); rt[32 + lane] = tsym(lane);
+    __syncwarp();
 
-    int H1 = 0, E1 = NEG6, F1 = NEG6, H2 = 0;
-    int best_h = 0, best_r = -1;
+    int H1 = 0, E1 = 0, F1 = 0, H2 = 0;
+    uint32_t best = 0;                                   // (h << 16) | (65535 - r): max = best score, earliest r
     uint32_t tbword = 0;
+    const uint32_t m_up = lane == 0 ? 0u : 0xffffffffu;  // band edge: neighbour outside = (H 0, E/F 0)
+    const uint32_t m_dn = lane == 31 ? 0u : 0xffffffffu;
+    const uint8_t* pq = rq + (32 - lane);                // query index of pair-step u:  u - lane + 32
+    const uint8_t* pt = rt + lane;                       // target index: u + lane (even), u + lane + 1 (odd)
     for (int sup = 0; sup < n_super; ++sup) {
-        const int half0 = -16 + 32 * sup;          // s0 / 2
-        fill(half0 + 16 + lane);
-        __syncwarp();
+        if (sup > 0) {
+            const int half0 = -16 + 32 * sup;
+            const uint8_t a = rq[32 + lane], b = rt[32 + lane];
+            const uint8_t nq = qsym(half0 + 16 + lane), nt = tsym(half0 + 16 + lane);
+            __syncwarp();
+            rq[lane] = a; rt[lane] = b; rq[32 + lane] = nq; rt[32 + lane] = nt;
+            __syncwarp();
+        }
+        const uint32_t rbase = 65535u - (uint32_t)(64 * sup);
+        int tnext = pt[0];
 #pragma unroll 4
         for (int u = 0; u < 32; ++u) {
-            const int half = half0 + u;            // s/2 for the even step
-            const int i = half - lane + 16;
-            const int jp = half + lane - 16;
-            const int r = 64 * sup + 2 * u;        // s + 32
-            const bool row_ok = (i >= 0 && i < L);
-            const int qb = rq[i & 127];
-            // ---------------- even step: cell (i, jp) ----------------
+            const int qb = pq[u];
+            const int te = tnext;
+            const int to = pt[u + 1];
+            tnext = to;
+            int h, e, f; uint32_t nib;
+            // even step (r = 64 sup + 2u): left from lane-1, up/diag own
             {
-                const int tbse = rt[jp & 127];
-                uint32_t v = ((uint32_t)H1 << 16) | (uint32_t)(E1 + 8);
-                uint32_t rv = __shfl_up_sync(HB_FULL, v, 1);
-                if (lane == 0) rv = 2u;                                   // H = 0, E = -6
-                const int hl = (int)(rv >> 16), el = (int)(rv & 0xFFFF) - 8;
-                const int hu = H1, fu = F1, hd = H2;
-                const int eo = hl - 4, fo = hu - 4;
-                const bool eext = el > eo, fext = fu > fo;
-                int e = (eext ? el : eo) - 2;
-                int f = (fext ? fu : fo) - 2;
-                const int sc = (qb < 4 && qb == tbse) ? 2 : -4;
-                const int dg = hd + sc;
-                int h = 0, src = 0;
-                if (dg > h) { h = dg; src = 1; }
-                if (e > h) { h = e; src = 2; }
-                if (f > h) { h = f; src = 3; }
-                const int64_t j = j0 + jp;
-                const bool act = row_ok && j >= 0 && (uint64_t)j < tot;
-                uint32_t nib = (uint32_t)src | (eext ? 4u : 0u) | (fext ? 8u : 0u);
-                if (!act) { h = 0; e = NEG6; f = NEG6; nib = 0; }
-                if (h > best_h) { best_h = h; best_r = r; }
-                tbword |= nib << (4 * (r & 7));
+                uint32_t rv = __shfl_up_sync(HB_FULL, __byte_perm((uint32_t)E1, (uint32_t)H1, 0x5410), 1) & m_up;
+                const int hl = (int)(rv >> 16), el = (int)(rv & 0xFFFFu);
+                HB_CELL(hl, el, H1, F1, H2, qb, te, h, e, f, nib);
+                best = max(best, ((uint32_t)h << 16) | (rbase - (uint32_t)(2 * u)));
+                tbword |= nib << (4 * ((2 * u) & 7));
                 H2 = H1; H1 = h; E1 = e; F1 = f;
             }
-            // ---------------- odd step: cell (i, jp + 1) ----------------
+            // odd step (r + 1): up from lane+1, left/diag own
             {
-                const int tbse = rt[(jp + 1) & 127];
-                uint32_t v = ((uint32_t)H1 << 16) | (uint32_t)(F1 + 8);
-                uint32_t rv = __shfl_down_sync(HB_FULL, v, 1);
-                if (lane == 31) rv = 2u;
-                const int hu = (int)(rv >> 16), fu = (int)(rv & 0xFFFF) - 8;
-                const int hl = H1, el = E1, hd = H2;
-                const int eo = hl - 4, fo = hu - 4;
-                const bool eext = el > eo, fext = fu > fo;
-                int e = (eext ? el : eo) - 2;
-                int f = (fext ? fu : fo) - 2;
-                const int sc = (qb < 4 && qb == tbse) ? 2 : -4;
-                const int dg = hd + sc;
-                int h = 0, src = 0;
-                if (dg > h) { h = dg; src = 1; }
-                if (e > h) { h = e; src = 2; }
-                if (f > h) { h = f; src = 3; }
-                const int64_t j = j0 + jp + 1;
-                const bool act = row_ok && j >= 0 && (uint64_t)j < tot;
-                uint32_t nib = (uint32_t)src | (eext ? 4u : 0u) | (fext ? 8u : 0u);
-                if (!act) { h = 0; e = NEG6; f = NEG6; nib = 0; }
-                if (h > best_h) { best_h = h; best_r = r + 1; }
-                tbword |= nib << (4 * ((r + 1) & 7));
+                uint32_t rv = __shfl_down_sync(HB_FULL, __byte_perm((uint32_t)F1, (uint32_t)H1, 0x5410), 1) & m_dn;
+                const int hu = (int)(rv >> 16), fu = (int)(rv & 0xFFFFu);
+                HB_CELL(H1, E1, hu, fu, H2, qb, to, h, e, f, nib);
+                best = max(best, ((uint32_t)h << 16) | (rbase - (uint32_t)(2 * u + 1)));
+                tbword |= nib << (4 * ((2 * u + 1) & 7));
                 H2 = H1; H1 = h; E1 = e; F1 = f;
             }
             if ((u & 3) == 3) {
-                tb[(size_t)(r >> 3) * 32 + lane] = tbword;               // 128 B per warp, coalesced
+                tb[(size_t)(8 * sup + (u >> 2)) * 32 + lane] = tbword;      // 128 B per warp, coalesced
                 tbword = 0;
             }
         }
-        __syncwarp();
     }
     // ---- best cell: max score, then smallest i, then smallest j ------------------------------
     unsigned long long key = 0;
-    if (best_r >= 0) {
-        const int s = best_r - 32;
+    if ((best >> 16) != 0) {
+        const int r = 65535 - (int)(best & 0xFFFFu);
+        const int s = r - 32;
         const int o = 2 * lane - 32 + (s & 1);
         const int i = (s - o) >> 1;
-        key = ((unsigned long long)(uint32_t)best_h << 32) | ((unsigned long long)(0xFFFF - i) << 16) |
+        key = ((unsigned long long)(best >> 16) << 32) | ((unsigned long long)(0xFFFF - i) << 16) |
               (unsigned long long)(63 - (o + 32));
     }
 #pragma unroll
@@ -161,50 +162,64 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
     }
     const int bi = 0xFFFF - (int)((key >> 16) & 0xFFFF);
     const int bo = (63 - (int)(key & 0xFFFF)) - 32;
-    // ---- traceback (warp-uniform walk; 128 B line of 8 steps held across the lanes) ------------
-    __syncwarp();
+    // the walk back is done by traceback_kernel (one thread per pair); leave the end cell here
+    out.i_s = bi; out.i_e = bi; out.j_s = j0 + bi + bo; out.j_e = j0 + bi + bo;
+    if (lane == 0) alns[p] = out;
+}
+
+// Traceback: ONE THREAD per pair (the walk is inherently serial; 32 independent walks per warp keep
+// the issue slots full where a warp-per-pair walk leaves 31 lanes idle).  A 32-bit word holds the
+// nibbles of 8 consecutive anti-diagonals of one lane, so a run of diagonal moves re-uses it 4 times.
+__global__ void __launch_bounds__(128)
+traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi,
+                 const uint32_t* __restrict__ tb_unit_off, uint32_t tb_unit_base, const uint32_t* __restrict__ tbuf,
+                 const uint32_t* __restrict__ qrec_unit_off, uint32_t* __restrict__ qrec, HbAln* __restrict__ alns) {
+    const uint32_t p = pair_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pair_hi) return;
+    HbAln a = alns[p];
+    if (a.score <= 0) return;
+    const int64_t j0 = pairs[p].j0;
+    const uint32_t* tb = tbuf + ((size_t)(tb_unit_off[p] - tb_unit_base) << 8);
     uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
-    int i = bi, o = bo, st = 0, pending_d = 0;
-    int i_s = bi; int64_t j_s = j0 + bi + bo;
-    int g_cur = -1;
-    uint32_t w_cur = 0, w_next = 0;
-    uint32_t qv = 0;
-    for (;;) {
-        if (i < 0 || o < -32 || o > 31) break;
-        const int r = 2 * i + o + 32;
-        const int g = r >> 3;
-        if (g != g_cur) {
-            if (g == g_cur - 1) w_cur = w_next; else w_cur = tb[(size_t)g * 32 + lane];
-            g_cur = g;
-            if (g > 0) w_next = tb[(size_t)(g - 1) * 32 + lane];
-        }
-        const uint32_t nib = (__shfl_sync(HB_FULL, w_cur, (o + 32) >> 1) >> (4 * (r & 7))) & 15u;
-        if (st == 0) {
-            const int src = (int)(nib & 3u);
-            if (src == 0) break;
-            if (src == 1) {
-                if (lane == (i & 31)) qv = (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 25);
-                pending_d = 0; i_s = i; j_s = j0 + i + o;
-                if ((i & 31) == 0) { qr[(size_t)(i >> 5) * 32 + lane] = qv; qv = 0; }
-                --i;
-            } else if (src == 2) st = 1;
-            else st = 2;
-        } else if (st == 1) {
-            ++pending_d;
-            st = ((nib >> 2) & 1u) ? 1 : 0;
-            --o;
-        } else {
-            if (lane == (i & 31)) qv = (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 24) | (1u << 25);
-            pending_d = 0; i_s = i;
-            if ((i & 31) == 0) { qr[(size_t)(i >> 5) * 32 + lane] = qv; qv = 0; }
-            st = ((nib >> 3) & 1u) ? 2 : 0;
-            --i; ++o;
+    int i = a.i_e, o = (int)(a.j_e - j0) - a.i_e, pending_d = 0;
+    int i_s = i, o_s = o;
+    int w_idx = -1;
+    uint32_t w = 0;
+    auto fetch = [&](int ii, int oo) -> uint32_t {
+        const int r = 2 * ii + oo + 32;
+        const int idx = (r >> 3) * 32 + ((oo + 32) >> 1);
+        if (idx != w_idx) { w = tb[idx]; w_idx = idx; }
+        return (w >> (4 * (r & 7))) & 15u;
+    };
+    while (i >= 0) {
+        uint32_t nib = fetch(i, o);
+        const uint32_t src = nib & 3u;
+        if (src == 0) break;
+        if (src == 1) {
+            qr[i] = (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 25);
+            pending_d = 0; i_s = i; o_s = o;
+            --i;
+        } else if (src == 2) {                            // run of target-only bases
+            for (;;) {
+                ++pending_d;
+                const bool ext = (nib >> 2) & 1u;
+                --o;
+                if (!ext) break;
+                nib = fetch(i, o);
+            }
+        } else {                                          // run of query-only bases
+            for (;;) {
+                qr[i] = (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 24) | (1u << 25);
+                pending_d = 0; i_s = i; o_s = o;
+                const bool ext = (nib >> 3) & 1u;
+                --i; ++o;
+                if (!ext || i < 0) break;
+                nib = fetch(i, o);
+            }
         }
     }
-    if (i >= 0 && (i & 31) != 31) qr[(size_t)(i >> 5) * 32 + lane] = qv;   // partial block holding i_s
-    else if (i < 0) { /* i_s == 0 was flushed at (i & 31) == 0 */ }
-    out.i_s = i_s; out.i_e = bi; out.j_s = j_s; out.j_e = j0 + bi + bo;
-    if (lane == 0) alns[p] = out;
+    a.i_s = i_s; a.j_s = j0 + i_s + o_s;
+    alns[p] = a;
 }
 
 // sizes: tb units (1 KB = 64 steps x 32 lanes x 4 bit) and qrec units (32 words) per pair
@@ -236,5 +251,7 @@ cudaError_t hb_extend_launch(const HbLocus* pairs, uint32_t pair_lo, uint32_t pa
     extend_kernel<<<(n + EXT_WARPS - 1) / EXT_WARPS, EXT_WARPS * 32, 0, s>>>(
         pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf,
         qrec_unit_off, qrec, alns);
+    traceback_kernel<<<(n + 127) / 128, 128, 0, s>>>(pairs, pair_lo, pair_hi, tb_unit_off, tb_unit_base, tbuf,
+                                                      qrec_unit_off, qrec, alns);
     return cudaGetLastError();
 }

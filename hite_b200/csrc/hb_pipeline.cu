@@ -374,7 +374,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
                                         ctx->buf("c.nmask").as<uint32_t>(), d_cgoff, d_clen, ctx->buf("p.tb_off").as<uint32_t>(),
                                         (uint32_t)base, ctx->buf("p.tbuf").as<uint32_t>(), ctx->buf("p.qr_off").as<uint32_t>(),
                                         ctx->buf("p.qrec").as<uint32_t>(), ctx->buf("p.alns").as<HbAln>(), s));
-            ++launches;
+            launches += 2;
             lo = hi;
         }
         ext_steps = tb_units_total * 64;
