@@ -92,6 +92,20 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _calls_to_dicts(calls, cons_b):
+    """hb_call records -> list of dicts (field columns converted once; structured scalar access is slow)."""
+    cols = {k: calls[k].tolist() for k in CALL_DTYPE.names}
+    text = cons_b.decode("ascii")
+    out = []
+    for i in range(len(calls)):
+        o = cols["cons_off"][i]
+        out.append(dict(is_te=bool(cols["is_te"][i]), info=INFO[cols["info"][i]], cons=text[o:o + cols["cons_len"][i]],
+                        copy_num=cols["copy_num"][i], align_start=cols["align_start"][i], align_end=cols["align_end"][i],
+                        homo_start=cols["homo_start"][i], homo_end=cols["homo_end"][i], clean_cols=cols["clean_cols"][i],
+                        no_copies=bool(cols["flags"][i] & 1)))
+    return out
+
+
 class Context:
     """One context per process per GPU (include/hite_b200.h).  Not thread-safe."""
 
@@ -161,16 +175,7 @@ class Context:
                                         _ptr(cand_off), TE_TYPES[te_type], int(plant),
                                         1 if result_type == "cons" else 0, _ptr(calls), _ptr(cons), cons_cap)
         self._check(rc, "hb_vote_matrices")
-        out = []
-        cons_b = cons.tobytes()
-        for i in range(n):
-            c = calls[i]
-            seq = cons_b[int(c["cons_off"]):int(c["cons_off"]) + int(c["cons_len"])].decode("ascii")
-            out.append(dict(is_te=bool(c["is_te"]), info=INFO[int(c["info"])], cons=seq, copy_num=int(c["copy_num"]),
-                            align_start=int(c["align_start"]), align_end=int(c["align_end"]),
-                            homo_start=int(c["homo_start"]), homo_end=int(c["homo_end"]),
-                            clean_cols=int(c["clean_cols"])))
-        return out
+        return _calls_to_dicts(calls, cons.tobytes())
 
     # ------------------------------------------------------------------------------------
     def load_genome(self, contig_seqs):
@@ -220,17 +225,8 @@ class Context:
                     "hb_adjust")
         cons = np.zeros(max(1, nbytes.value), dtype=np.uint8)
         self._check(self._lib.hb_last_cons(self._h, _ptr(cons), len(cons)), "hb_last_cons")
-        cons_b = cons.tobytes()
         self.last_calls = calls
-        out = []
-        for i in range(n):
-            c = calls[i]
-            o, ln = int(c["cons_off"]), int(c["cons_len"])
-            out.append(dict(is_te=bool(c["is_te"]), info=INFO[int(c["info"])], cons=cons_b[o:o + ln].decode("ascii"),
-                            copy_num=int(c["copy_num"]), align_start=int(c["align_start"]), align_end=int(c["align_end"]),
-                            homo_start=int(c["homo_start"]), homo_end=int(c["homo_end"]), clean_cols=int(c["clean_cols"]),
-                            no_copies=bool(int(c["flags"]) & 1)))
-        return out
+        return _calls_to_dicts(calls, cons.tobytes())
 
     def last_copies(self):
         n = C.c_uint64(0)

@@ -1,0 +1,160 @@
+"""Host-side mirror of the reference's operator interface for the dynamic boundary-adjustment path.
+
+Same names, argument order and meaning, and the same FASTA-in / FASTA-out contract as
+
+* ``flank_region_align_v5``   reference module/Util.py:8032-8299
+* ``run_find_members_v8``     reference module/Util.py:10439-10449
+* ``is_TE_from_align_file``   reference module/Util.py:10407-10437
+
+but the copy search (minimap2), the MSA (mafft) and the pure-Python column voting are replaced by
+one ``hb_adjust`` call into libhite_b200.so (sm_100a kernels).  There is no CPU fallback: without
+the built extension or without a GPU these functions raise ``HiteB200Error``.
+
+What is NOT reproduced (out of scope; documented in DESIGN.md): the low-copy
+rescue of module/Util.py:8197-8281 needs ``trf``, the closed ELF ``itrsearch`` and ``blastx`` -- low-copy
+elements are all appended to ``all_low_copy`` exactly as the reference does for the ones it cannot
+rescue (module/Util.py:8284-8287).
+"""
+import os
+import re
+import time
+
+from . import _lib
+from .fasta import read_fasta, store_fasta
+
+_CTX = {}          # device -> Context
+_GENOME = {}       # device -> (path, mtime, size)
+
+
+def _device():
+    env = os.environ.get("HITE_GPU_DEVICES")
+    if env:
+        devs = [int(x) for x in env.split(",") if x.strip() != ""]
+        rank = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+        return devs[rank % len(devs)]
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def get_context(device=None):
+    d = _device() if device is None else device
+    if d not in _CTX:
+        _CTX[d] = _lib.Context(d)
+    return _CTX[d]
+
+
+def ensure_genome(ctx, reference, k=15, w=10):
+    """Load + index the reference once per process (the analogue of the ``ref.mmi`` existence check,
+    module/Util.py:7938-7947)."""
+    st = os.stat(reference)
+    key = (os.path.abspath(reference), st.st_mtime_ns, st.st_size, k, w)
+    if _GENOME.get(ctx.device) != key:
+        names, contigs = read_fasta(reference)
+        ctx.contig_names = names
+        ctx.load_genome([contigs[n].encode("ascii") for n in names])
+        ctx.build_index(k, w)
+        _GENOME[ctx.device] = key
+    return ctx
+
+
+def _post_filter(names, seqs, results, TE_type):
+    """module/Util.py:8159-8193: drop 'TG...CA', split by copy-count threshold."""
+    true_tes, low_copy = {}, {}
+    for name, r in zip(names, results):
+        if not r["is_te"]:
+            continue
+        cons = r["cons"]
+        if TE_type in ("tir", "helitron", "non_ltr"):
+            if cons.startswith("TG") and cons.endswith("CA"):                     # :8175
+                continue
+            threshold = 5 if TE_type in ("tir", "non_ltr") else 2                  # :8179-8183
+            if r["copy_num"] <= threshold:
+                low_copy[name] = cons
+            else:
+                true_tes[name] = cons
+        else:
+            true_tes[name] = cons
+    return true_tes, low_copy
+
+
+def flank_region_align_v5(candidate_sequence_path, real_TEs, flanking_len, reference, split_ref_dir, TE_type,
+                          tmp_output_dir, threads, ref_index, log, subset_script_path, plant, debug, iter_num,
+                          all_low_copy, result_type="cons"):
+    if log is not None:
+        log.logger.info("------Determination of homology in regions outside the boundaries of " + TE_type + " copies")
+    starttime = time.time()
+    names, contigs = read_fasta(candidate_sequence_path)
+    ctx = ensure_genome(get_context(), reference)
+    seqs = [contigs[n] for n in names]
+    # HB-align limits: a candidate must be 3..32000 bp (max_repeat_len defaults to 30000, main.py:25)
+    ok = [i for i, s in enumerate(seqs) if 3 <= len(s) <= 32000]
+    results = [dict(is_te=False, info="", cons="", copy_num=0)] * len(seqs)
+    if ok:
+        res = []
+        for b in range(0, len(ok), 65536):
+            chunk = ok[b:b + 65536]
+            res.extend(ctx.adjust([seqs[i] for i in chunk], TE_type, int(plant), result_type, flank=int(flanking_len)))
+        results = list(results)
+        for i, r in zip(ok, res):
+            results[i] = r
+    true_tes, low_copy = _post_filter(names, seqs, results, TE_type)
+    store_fasta(true_tes, real_TEs)                                                # :8282
+    with open(all_low_copy, "a") as f_save:                                        # :8284-8287
+        for te_name, seq in low_copy.items():
+            f_save.write(">" + te_name + "\n" + seq + "\n")
+    if debug:
+        nb = sum(1 for r in results if r["info"] == "nb")
+        fl1 = sum(1 for r in results if r["info"] == "fl1")
+        print("not found boundary num: " + str(nb) + ", full length 1: " + str(fl1))
+    if log is not None:
+        log.logger.info("Running time of determination of homology in regions outside the boundaries of  " + TE_type +
+                        " copies: %.8s s" % (time.time() - starttime))
+    return results
+
+
+def _is_aligned(member_contigs):
+    lens = {len(s) for s in member_contigs.values()}
+    return len(lens) == 1 and any("-" in s for s in member_contigs.values())
+
+
+def is_TE_from_align_file(cur_align_file, query_name, cur_seq, temp_dir, subset_script_path, plant, TE_type, debug,
+                          result_type):
+    """Mirror of module/Util.py:10407-10437.  An aligned member file (equal-length rows with '-') is judged
+    directly (kernel iii); an unaligned one is aligned by kernels (i)+(ii) with the members as the target set."""
+    member_names, member_contigs = read_fasta(cur_align_file)
+    if not member_names:
+        return (None, None, "", 0, cur_align_file)
+    ctx = get_context()
+    if _is_aligned(member_contigs):
+        rows = [member_contigs[n] for n in member_names]
+        r = ctx.vote_matrices([cur_seq], [rows], TE_type, int(plant), result_type)[0]
+    else:
+        if len(member_names) > 100:                                              # :10409-10412, 100 longest
+            order = sorted(range(len(member_names)), key=lambda i: (-len(member_contigs[member_names[i]]), i))[:100]
+            member_names = [member_names[i] for i in sorted(order)]
+        _GENOME.pop(ctx.device, None)
+        ctx.load_genome([member_contigs[n].encode("ascii") for n in member_names])
+        ctx.build_index(15, 10)
+        r = ctx.adjust([cur_seq], TE_type, int(plant), result_type, flank=50)[0]
+    if r["is_te"]:
+        return (query_name, r["cons"], r["info"], r["copy_num"], cur_align_file)
+    return (None, None, r["info"], 0, cur_align_file)
+
+
+def run_find_members_v8(batch_member_file, temp_dir, subset_script_path, plant, TE_type, debug, result_type):
+    """Mirror of module/Util.py:10439-10449 (truncated-member gate first, then the full members)."""
+    (query_name, cur_seq, trunc_member_file, extend_member_file) = batch_member_file
+    if trunc_member_file is not None:
+        query_name, cons_seq, info, copy_num, trunc_member_file = is_TE_from_align_file(
+            trunc_member_file, query_name, cur_seq, temp_dir, subset_script_path, plant, TE_type, debug, result_type)
+        if query_name is not None:
+            return is_TE_from_align_file(extend_member_file, query_name, cur_seq, temp_dir, subset_script_path, plant,
+                                         TE_type, debug, result_type)
+        return query_name, cons_seq, info, copy_num, trunc_member_file
+    return is_TE_from_align_file(extend_member_file, query_name, cur_seq, temp_dir, subset_script_path, plant, TE_type,
+                                 debug, result_type)
+
+
+def member_file_name(temp_dir, query_name, trunc=False):
+    """module/Util.py:8127-8133 file naming of the per-candidate member files."""
+    valid = re.sub(r'[<>:"/\\|?*]', "-", query_name)
+    return temp_dir + "/" + valid + (".trunc.blast.bed.fa" if trunc else ".blast.bed.fa")

@@ -3,6 +3,8 @@
 // hb_seed.cu, hb_extend.cu, hb_msa.cu and hb_vote.cu; this file only sizes buffers, launches and
 // copies.  One stream per context; stage times are CUDA events on that stream.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "hb_ctx.cuh"
 #include "hb_extend.cuh"
@@ -232,6 +234,14 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     const uint64_t tot = ctx->g_tot;
     uint32_t launches = 0;
 
+    const bool dbg = getenv("HB_DEBUG_TIMING") != nullptr;
+    auto t_host0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!dbg) return;
+        cudaStreamSynchronize(s);
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[hb_adjust] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_host0).count());
+    };
     // ---- S3: pack + sketch the candidates ----------------------------------------------------
     HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
     Layout CL = make_layout(cand_off, n_cand);
@@ -244,6 +254,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     ++launches;
     tm.h2d_bytes += cand_off[n_cand] + sizeof(uint64_t) * (3 * (uint64_t)n_cand + 1);
     HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    mark("sketch");
     const uint64_t* d_cgoff = ctx->buf("c.goff").as<uint64_t>();
     const uint64_t* d_coff = ctx->buf("c.src_off").as<uint64_t>();
     const uint32_t* d_clen = ctx->buf("c.clen").as<uint32_t>();
@@ -344,6 +355,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         launches += 8;
     }
     HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    mark("seed/sort/cluster/pairs");
 
     // ---- S7: banded extension, chunked by the traceback budget -----------------------------------
     uint64_t budget_units = (prm->tb_budget_bytes ? prm->tb_budget_bytes : (16ull << 30)) >> 10;
@@ -380,6 +392,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         ext_steps = tb_units_total * 64;
     }
     HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+    mark("extend");
 
     // ---- S8..S10: copy rules, star MSA -------------------------------------------------------------
     ENSURE("m.n_rows", sizeof(uint32_t) * (n_cand + 1)); ENSURE("m.n_cols", sizeof(uint32_t) * (n_cand + 1));
@@ -434,6 +447,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
                                    ctx->buf("g.nmask").as<uint32_t>(), tot, flank, ctx->buf("m.mat").as<uint8_t>(), s));
     ++launches;
     HB_CUDA_OK(cudaEventRecord(ctx->ev[4], s));
+    mark("copy rules + msa");
 
     // ---- kernel (iii): clean + judge ---------------------------------------------------------------
     std::vector<HbVoteCall> h_calls(n_tasks);
@@ -480,6 +494,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         HB_CUDA_OK(cudaEventRecord(ctx->ev[7], s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
     }
+    mark("vote + d2h");
     // scatter results back to candidate order; candidates without copies: nothing found
     for (uint32_t c = 0; c < n_cand; ++c) {
         hb_call& o = calls[c];
@@ -503,6 +518,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     tm.launches = launches;
     tm.k_ms[6] = (float)n_pairs;                                  // diagnostics: pairs extended
     tm.k_ms[7] = (float)((double)ext_steps * 1e-6);               // diagnostics: million DP steps
+    mark("done");
     return HB_OK;
 }
 

@@ -8,7 +8,7 @@
 #define HB_DGAP 16
 #define HB_MIN_SEEDS 3
 
-struct HbLocus {          // == hbo_locus (oracle/hbo.h)
+struct HbLocus {          // one ranked locus of a candidate (HB-align S6)
     uint32_t cand, rel, nseeds, rank;
     int64_t dmin, dmax, j0;
 };

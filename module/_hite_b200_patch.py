@@ -1,0 +1,52 @@
+"""Shared launcher of the drop-in stage scripts in this directory.
+
+HiTE's ``main.py`` runs its stages by script name found on ``$PATH`` (reference main.py:441-725,
+configure.py:48).  Putting this directory *ahead* of HiTE's own ``module/`` on ``$PATH`` makes
+``main.py`` call these scripts unchanged; each one executes the reference's own stage script (same
+argparse flags, same file names, same logs) after replacing exactly the hot-path functions in the
+reference's ``Util`` namespace with the B200 implementations:
+
+    Util.flank_region_align_v5   -> hite_b200.boundary.flank_region_align_v5
+    Util.run_find_members_v8     -> hite_b200.boundary.run_find_members_v8
+    Util.is_TE_from_align_file   -> hite_b200.boundary.is_TE_from_align_file
+
+Everything else on the stage (TSD pre-filter, cd-hit-est, renaming, prev_TE bookkeeping) stays the
+reference's code.  ``HITE_HOME`` must point at the HiTE checkout.  There is no CPU fallback: if the
+extension or the GPU is missing the stage fails loudly (main.py ignores exit codes but checks that
+the output file exists, reference main.py:541-562).
+"""
+import os
+import runpy
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def hite_home():
+    home = os.environ.get("HITE_HOME")
+    if not home:
+        for cand in (os.path.join(ROOT, "..", "HiTE"), "/root/reference"):
+            if os.path.exists(os.path.join(cand, "module", "Util.py")):
+                home = cand
+                break
+    if not home or not os.path.exists(os.path.join(home, "module", "Util.py")):
+        sys.stderr.write("hite_b200: set HITE_HOME to the HiTE checkout (module/Util.py not found)\n")
+        sys.exit(2)
+    return os.path.abspath(home)
+
+
+def run_stage(script_name, patch_names=("flank_region_align_v5", "run_find_members_v8", "is_TE_from_align_file")):
+    home = hite_home()
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    moddir = os.path.join(home, "module")
+    sys.path.insert(0, moddir)
+    sys.path.insert(0, home)
+    import hite_b200.boundary as hb
+    import Util  # the reference's own module, unmodified
+    for name in patch_names:
+        setattr(Util, name, getattr(hb, name))
+    target = os.path.join(moddir, script_name)
+    sys.argv[0] = target
+    runpy.run_path(target, run_name="__main__")

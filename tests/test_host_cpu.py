@@ -1,0 +1,124 @@
+"""CPU: host logic, C-ABI surface, FASTA contract, no-CPU-fallback behaviour, gloo sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "hite_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(hb_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from hite_b200 import _lib
+    lib = ctypes.CDLL(_lib.lib_path())
+    syms = _declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert lib.hb_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    import hite_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(hite_b200.HiteB200Error):
+        hite_b200.Context(0)
+    from hite_b200 import boundary
+    with pytest.raises(hite_b200.HiteB200Error):
+        boundary.get_context(0)
+
+
+def test_product_never_imports_oracle():
+    for dp, _, fs in os.walk(os.path.join(ROOT, "hite_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+                assert not re.search(r'#include\s+"[^"]*oracle', src) and "hbo.h" not in src, f
+
+
+def test_fasta_contract(tmp_path):
+    from hite_b200 import fasta
+    p = tmp_path / "a.fa"
+    p.write_text(">chr1 some desc\nacgt\nNNac\n>chr2\tx\nGG\n>empty\n>chr3\nTT\n")
+    names, contigs = fasta.read_fasta(str(p))
+    assert names == ["chr1", "chr2", "chr3"]
+    assert contigs == {"chr1": "ACGTNNAC", "chr2": "GG", "chr3": "TT"}
+    q = tmp_path / "b.fa"
+    fasta.store_fasta(contigs, str(q))
+    assert q.read_text() == ">chr1\nACGTNNAC\n>chr2\nGG\n>chr3\nTT\n"
+    assert fasta.file_exist(str(q)) and not fasta.file_exist(str(tmp_path / "nope.fa"))
+    ref = "/root/reference/module/Util.py"
+    if os.path.exists(ref):
+        from oracle import ref_import
+        U = ref_import.load_util()
+        assert U.read_fasta(str(p)) == (names, contigs)
+        r = tmp_path / "c.fa"
+        U.store_fasta(contigs, str(r))
+        assert r.read_bytes() == q.read_bytes()
+
+
+def test_post_filter_rules():
+    from hite_b200 import boundary
+    names = ["a", "b", "c", "d"]
+    res = [dict(is_te=True, cons="TGAAAACA", copy_num=30, info=""), dict(is_te=True, cons="ACGT", copy_num=5, info=""),
+           dict(is_te=True, cons="ACGTT", copy_num=6, info=""), dict(is_te=False, cons="", copy_num=0, info="nb")]
+    true_tes, low = boundary._post_filter(names, None, res, "tir")
+    assert true_tes == {"c": "ACGTT"} and low == {"b": "ACGT"}          # Util.py:8175, 8179-8188
+    true_tes, low = boundary._post_filter(names, None, res, "helitron")
+    assert set(true_tes) == {"b", "c"} and low == {}
+
+
+def test_shard_indices_deterministic_partition():
+    from hite_b200 import dist as hd
+    lens = [5, 9, 1, 7, 7, 3, 8]
+    parts = [hd.shard_indices(len(lens), r, 3, lens) for r in range(3)]
+    assert sorted(sum(parts, [])) == list(range(len(lens)))
+    assert parts == [hd.shard_indices(len(lens), r, 3, lens) for r in range(3)]
+    assert hd.shard_indices(5, 1, 2) == [1, 3]
+
+
+GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from hite_b200 import dist as hd
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+names = ["te%%d" %% i for i in range(11)]
+seqs = ["ACGT" * (i + 1) for i in range(11)]
+mine = hd.shard_indices(len(seqs), rank, world, [len(s) for s in seqs])
+recs = [(names[i], seqs[i]) for i in mine if i %% 3 != 0]          # "accepted" subset
+merged = hd.allgather_records(recs)
+exp = []
+for r in range(world):
+    exp += [(names[i], seqs[i]) for i in hd.shard_indices(len(seqs), r, world, [len(s) for s in seqs]) if i %% 3 != 0]
+assert merged == exp, (merged, exp)
+empty = hd.allgather_records([] if rank == 0 else [("x", "A")])
+assert empty == [("x", "A")] * (world - 1)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_allgather_records_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
