@@ -58,6 +58,11 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
                       const uint8_t *cand_ascii, int L, int occ_cap, int max_loci, int flank, int max_rows,
                       hbo_copy *copies, int *n_copies, uint8_t *matrix, uint64_t matrix_cap, int *R_out, int *C_out);
 
+typedef struct { int32_t is_te, info, copy_num, cons_len; } hbo_result;
+int hbo_run_batch(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w, const uint8_t *cand_ascii,
+                  const uint64_t *coff, uint32_t n_cand, int occ_cap, int max_loci, int flank, int max_rows, int plant,
+                  int threads, hbo_result *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,7 +145,11 @@ typedef struct { int32_t h, e, f; uint8_t tb; } cell_t;   /* tb: bits0-1 hsrc (0
 int hbo_align_pair(const hbo_genome *g, const uint8_t *q /*codes*/, int L, int rel, int64_t j0,
                    hbo_aln *out, uint32_t *qrec /* L entries or NULL */) {
     const int W = BAND_HI - BAND_LO + 1;
-    cell_t *rows = (cell_t *)malloc(sizeof(cell_t) * (size_t)L * W);
+    /* per-thread scratch, grown on demand (avoids an mmap/munmap + page-fault storm per pair) */
+    static _Thread_local cell_t *tl_rows = NULL;
+    static _Thread_local size_t tl_cap = 0;
+    if ((size_t)L * W > tl_cap) { free(tl_rows); tl_cap = (size_t)L * W * 2; tl_rows = (cell_t *)malloc(sizeof(cell_t) * tl_cap); }
+    cell_t *rows = tl_rows;
     int32_t best = 0; int bi = -1, bo = 0;
     for (int i = 0; i < L; ++i) {
         for (int oi = 0; oi < W; ++oi) {
@@ -180,7 +184,7 @@ int hbo_align_pair(const hbo_genome *g, const uint8_t *q /*codes*/, int L, int r
     memset(out, 0, sizeof(*out));
     out->score = best;
     if (qrec) for (int i = 0; i < L; ++i) qrec[i] = 0;
-    if (best <= 0) { free(rows); out->i_s = out->i_e = -1; return 0; }
+    if (best <= 0) { out->i_s = out->i_e = -1; return 0; }
     /* traceback */
     int i = bi, oi = bo, state = 0; /* 0 H, 1 E, 2 F */
     int64_t je = j0 + bi + (BAND_LO + bo);
@@ -216,7 +220,6 @@ int hbo_align_pair(const hbo_genome *g, const uint8_t *q /*codes*/, int L, int r
         }
     }
     out->i_s = i_s; out->i_e = bi; out->j_s = j_s; out->j_e = je;
-    free(rows);
     return 1;
 }
 

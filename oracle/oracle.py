@@ -150,3 +150,19 @@ class Genome:
         raw = mat[:R.value * Cn.value].tobytes()
         rows = [raw[r * Cn.value:(r + 1) * Cn.value].decode() for r in range(R.value)]
         return cps, rows
+
+    def run_batch(self, cand_seqs, threads, occ_cap=512, max_loci=128, flank=50, max_rows=100, plant=1):
+        """Whole per-candidate path (copy search + MSA + clean + judge) on ``threads`` host threads.
+        -> int32 array [n, 4] = (is_te, info, copy_num, cons_len)."""
+        import numpy as np
+        cb = [c if isinstance(c, (bytes, bytearray)) else c.encode() for c in cand_seqs]
+        off = np.zeros(len(cb) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(c) for c in cb])
+        flat = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
+        out = np.zeros((len(cb), 4), dtype=np.int32)
+        L = self._L
+        L.hbo_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.hbo_run_batch(self.g, self.index.ctypes.data, len(self.index), self.k, self.w, flat.ctypes.data,
+                        off.ctypes.data, len(cb), occ_cap, max_loci, flank, max_rows, plant, threads, out.ctypes.data)
+        return out
