@@ -91,6 +91,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Host cores this process may actually use: min(cpu_count, affinity, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, per = open(path).read().split()
+            if q != "max":
+                n = min(n, max(1, int(int(q) / int(per))))
+        except Exception:
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            n = min(n, max(1, q // per))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_run(wl, cand_idx, threads, G=None):
     """The CPU implementation of the path (plain-C port, oracle/): per candidate copy search + star MSA
     + sparse-column removal + judge on ``threads`` host threads (pthreads inside the port, no Python in
@@ -121,7 +145,7 @@ def main():
     if world == 1 and args.gpus > 1:
         print(json.dumps({"error": "launch with torch.distributed.run for --gpus > 1"}))
         return 2
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
 
     # ------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -174,12 +198,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    my_arr = np.asarray(my, dtype=np.int64)
+
     def gather_results(res):
-        """The path's only exchange: all-gather of emitted (index, consensus) records before the
-        get_nonRedundant_lib merge (reference main.py:652-664 cat >>)."""
+        """The path's only exchange: all-gather of the emitted records (candidate index, consensus length,
+        consensus bytes) before the get_nonRedundant_lib merge (reference main.py:652-664 cat >>)."""
+        calls, cons = res
+        te = calls["is_te"] != 0
         if world == 1:
-            return sum(r["is_te"] for r in res)
-        payload = b"".join(b"%d\t%s\n" % (my[i], r["cons"].encode()) for i, r in enumerate(res) if r["is_te"])
+            return int(te.sum())
+        head = np.stack([my_arr[te], calls["cons_len"][te].astype(np.int64)], axis=1).tobytes()
+        payload = np.int64(int(te.sum())).tobytes() + head + cons       # accepted consensi are the dense buffer
         n = torch.tensor([len(payload)], device="cuda", dtype=torch.int64)
         sizes = [torch.zeros_like(n) for _ in range(world)]
         dist.all_gather(sizes, n)
@@ -189,10 +218,17 @@ def main():
             buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
         out = [torch.empty_like(buf) for _ in range(world)]
         dist.all_gather(out, buf)
-        return sum(bytes(o[:int(s.item())].cpu().numpy()).count(b"\n") for o, s in zip(out, sizes))
+        total = 0
+        for o in out:
+            total += int(np.frombuffer(bytes(o[:8].cpu().numpy()), dtype=np.int64)[0])
+        return total
 
+    flat = np.frombuffer(b"".join(my_cands) + b"\0", dtype=np.uint8)
+    offs = np.zeros(len(my_cands) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(c) for c in my_cands])
+    host_cands = (flat, offs)                                   # the step's input, in host memory
     for _ in range(args.warmup):
-        res = ctx.adjust(my_cands, "tir", 1)
+        res = ctx.adjust_raw(host_cands, "tir", 1)
         gather_results(res)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -203,7 +239,7 @@ def main():
     n_te_total = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = ctx.adjust(my_cands, "tir", 1)
+        res = ctx.adjust_raw(host_cands, "tir", 1)
         tm = ctx.timing()
         n_te_total = gather_results(res)
         dev_ms.append(tm["kernel_ms"]); ext_ms.append(tm["k_ms"][2]); stage += np.array(tm["k_ms"])

@@ -206,27 +206,38 @@ class Context:
         self._check(self._lib.hb_debug_index(self._h, _ptr(keys), len(keys)), "hb_debug_index")
         return keys[:n]
 
-    def adjust(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=128, flank=50,
-               max_rows=100, tb_budget_bytes=0):
+    def adjust_raw(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=128, flank=50,
+                   max_rows=100, tb_budget_bytes=0):
         """One ``flank_region_align_v5``-equivalent round (kernels ii + iii) over the candidates.
-        Returns a list of dicts mirroring ``is_TE_from_align_file``'s tuple per candidate."""
-        cb = [c if isinstance(c, (bytes, bytearray)) else c.encode("ascii") for c in cand_seqs]
-        n = len(cb)
+        Returns ``(calls, cons)``: a structured array (CALL_DTYPE, one record per candidate) and the
+        consensus bytes; candidate i's consensus is ``cons[calls['cons_off'][i] : +calls['cons_len'][i]]``."""
+        if isinstance(cand_seqs, tuple):                      # pre-flattened (uint8 array, uint64 offsets)
+            flat, off = cand_seqs
+            n = len(off) - 1
+        else:
+            cb = [c if isinstance(c, (bytes, bytearray)) else c.encode("ascii") for c in cand_seqs]
+            n = len(cb)
+            off = np.zeros(n + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([len(c) for c in cb])
+            flat = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
+        calls = np.zeros(n, dtype=CALL_DTYPE)
         if n == 0:
-            return []
-        off = np.zeros(n + 1, dtype=np.uint64)
-        off[1:] = np.cumsum([len(c) for c in cb])
-        flat = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
+            return calls, b""
         prm = HbParams(occ_cap, max_loci, flank, max_rows, TE_TYPES[te_type], int(plant),
                        1 if result_type == "cons" else 0, 0, int(tb_budget_bytes))
-        calls = np.zeros(n, dtype=CALL_DTYPE)
         nbytes = C.c_uint64(0)
         self._check(self._lib.hb_adjust(self._h, n, _ptr(flat), _ptr(off), C.byref(prm), _ptr(calls), C.byref(nbytes)),
                     "hb_adjust")
         cons = np.zeros(max(1, nbytes.value), dtype=np.uint8)
         self._check(self._lib.hb_last_cons(self._h, _ptr(cons), len(cons)), "hb_last_cons")
         self.last_calls = calls
-        return _calls_to_dicts(calls, cons.tobytes())
+        return calls, cons[:nbytes.value].tobytes()
+
+    def adjust(self, cand_seqs, *a, **kw):
+        """Same as ``adjust_raw`` but returns a list of dicts mirroring ``is_TE_from_align_file``'s tuple
+        (reference module/Util.py:10434-10437) per candidate."""
+        calls, cons = self.adjust_raw(cand_seqs, *a, **kw)
+        return _calls_to_dicts(calls, cons)
 
     def last_copies(self):
         n = C.c_uint64(0)
