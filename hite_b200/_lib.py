@@ -169,7 +169,7 @@ class Context:
         cand_off[1:] = np.cumsum([len(c) for c in cb])
         cand = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
         calls = np.zeros(n, dtype=CALL_DTYPE)
-        cons_cap = int(Cc.astype(np.int64).sum())
+        cons_cap = int(Cc.astype(np.int64).sum()) + 2 * n
         cons = np.zeros(max(1, cons_cap), dtype=np.uint8)
         rc = self._lib.hb_vote_matrices(self._h, n, _ptr(rows), _ptr(mat_off), _ptr(R), _ptr(Cc), _ptr(cand),
                                         _ptr(cand_off), TE_TYPES[te_type], int(plant),

@@ -4,8 +4,8 @@
 
 extern "C" size_t hb_vote_match_entry_size();
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
-                                      uint32_t* d_planes, void* d_matches, const uint8_t* d_cands,
-                                      uint8_t* d_cons, HbVoteCall* d_calls, cudaStream_t stream);
+                                      uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
+                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, cudaStream_t stream);
 
 static std::string g_last_global_error;
 
@@ -81,11 +81,12 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
     if (n == 0) return HB_OK;
     if (!rows_ascii || !mat_off || !R || !C || !cand_ascii || !cand_off || !calls || !cons_out)
         return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: null argument");
-    if (te_type != HB_TE_TIR) return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: only HB_TE_TIR is implemented");
+    if (te_type != HB_TE_TIR && te_type != HB_TE_HELITRON)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: te_type must be HB_TE_TIR or HB_TE_HELITRON (non-LTR: not implemented)");
     static_assert(sizeof(hb_call) == sizeof(HbVoteCall), "hb_call layout");
     cudaSetDevice(ctx->device);
     std::vector<HbVoteTask> tasks(n);
-    uint64_t raw_total = 0, col_total = 0, match_total = 0;
+    uint64_t raw_total = 0, col_total = 0, match_total = 0, row_total = 0;
     for (uint32_t i = 0; i < n; ++i) {
         if (R[i] <= 0 || C[i] <= 0 || C[i] >= (1 << 26) || R[i] >= 65535)
             return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: matrix " + std::to_string(i) + " has unsupported shape");
@@ -94,8 +95,9 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
         t.raw_off = mat_off[i];
         t.clean_off = mat_off[i];
         t.plane_off = col_total * 24;
-        t.cons_off = col_total;
+        t.cons_off = col_total + 2ull * i;          // capacity C + 2 (Helitron +-1 bp extension)
         t.match_off = match_total;
+        t.anchor_off = 2 * row_total;
         t.cand_off = cand_off[i];
         t.cand_len = (int32_t)(cand_off[i + 1] - cand_off[i]);
         t.R = R[i]; t.C = C[i];
@@ -103,8 +105,10 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
         raw_total = mat_off[i] + (uint64_t)R[i] * C[i] > raw_total ? mat_off[i] + (uint64_t)R[i] * C[i] : raw_total;
         col_total += (uint64_t)C[i];
         match_total += 2ull * ((uint64_t)C[i] + 2);
+        row_total += (uint64_t)R[i];
     }
-    if (cons_cap < col_total) return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: cons_cap < sum(C)");
+    const uint64_t cons_total = col_total + 2ull * n;
+    if (cons_cap < cons_total) return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: cons_cap < sum(C) + 2n");
     const uint64_t cand_total = cand_off[n];
     HB_CUDA_OK(ctx->v_tasks.ensure(sizeof(HbVoteTask) * n));
     HB_CUDA_OK(ctx->v_raw.ensure(raw_total));
@@ -112,7 +116,8 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
     HB_CUDA_OK(ctx->v_planes.ensure(col_total * 24 * sizeof(uint32_t)));
     HB_CUDA_OK(ctx->v_matches.ensure(match_total * hb_vote_match_entry_size()));
     HB_CUDA_OK(ctx->v_cands.ensure(cand_total + 1));
-    HB_CUDA_OK(ctx->v_cons.ensure(col_total));
+    HB_CUDA_OK(ctx->v_cons.ensure(cons_total));
+    HB_CUDA_OK(ctx->buf("v.anchors").ensure(sizeof(int) * (2 * row_total + 2)));
     HB_CUDA_OK(ctx->v_calls.ensure(sizeof(HbVoteCall) * n));
     cudaStream_t s = ctx->stream;
     HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
@@ -122,11 +127,12 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
     HB_CUDA_OK(cudaMemsetAsync(ctx->v_calls.p, 0, sizeof(HbVoteCall) * n, s));
     HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
     HB_CUDA_OK(hb_vote_launch(ctx->v_tasks.as<HbVoteTask>(), (int)n, ctx->v_raw.as<uint8_t>(), ctx->v_clean.as<uint8_t>(),
-                              ctx->v_planes.as<uint32_t>(), ctx->v_matches.p, ctx->v_cands.as<uint8_t>(),
-                              ctx->v_cons.as<uint8_t>(), ctx->v_calls.as<HbVoteCall>(), s));
+                              ctx->v_planes.as<uint32_t>(), ctx->v_matches.p, ctx->buf("v.anchors").as<int>(),
+                              ctx->v_cands.as<uint8_t>(), ctx->v_cons.as<uint8_t>(), ctx->v_calls.as<HbVoteCall>(),
+                              te_type, s));
     HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
     HB_CUDA_OK(cudaMemcpyAsync(calls, ctx->v_calls.p, sizeof(HbVoteCall) * n, cudaMemcpyDeviceToHost, s));
-    HB_CUDA_OK(cudaMemcpyAsync(cons_out, ctx->v_cons.p, col_total, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaMemcpyAsync(cons_out, ctx->v_cons.p, cons_total, cudaMemcpyDeviceToHost, s));
     HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
     HB_CUDA_OK(cudaStreamSynchronize(s));
     hb_timing& tm = ctx->timing;
@@ -135,7 +141,7 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
     cudaEventElapsedTime(&tm.kernel_ms, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&tm.d2h_ms, ctx->ev[2], ctx->ev[3]);
     tm.h2d_bytes = sizeof(HbVoteTask) * n + raw_total + cand_total;
-    tm.d2h_bytes = sizeof(HbVoteCall) * n + col_total;
+    tm.d2h_bytes = sizeof(HbVoteCall) * n + cons_total;
     tm.launches = 2;
     return HB_OK;
 }

@@ -31,6 +31,7 @@ struct HbVoteTask {
     uint64_t cons_off;   // byte offset of the consensus output (capacity C)
     uint64_t match_off;  // entry offset of the anchor match scratch (capacity 2*(C+2))
     uint64_t cand_off;   // byte offset of the candidate sequence (ASCII)
+    uint64_t anchor_off; // int offset of the per-row anchor scratch (capacity 2*R), Helitron only
     int32_t cand_len;
     int32_t R, C;
     int32_t te_type;     // 0 tir, 1 helitron, 2 non_ltr

@@ -15,8 +15,8 @@
 
 extern "C" size_t hb_vote_match_entry_size();
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
-                                      uint32_t* d_planes, void* d_matches, const uint8_t* d_cands,
-                                      uint8_t* d_cons, HbVoteCall* d_calls, cudaStream_t stream);
+                                      uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
+                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, cudaStream_t stream);
 
 namespace {
 
@@ -218,7 +218,8 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     if (!ctx->have_index) return hb_fail_msg(ctx, HB_ESTATE, "hb_adjust: call hb_genome_load + hb_index_build first");
     if (n_cand == 0) { if (cons_bytes) *cons_bytes = 0; return HB_OK; }
     if (n_cand > (1u << 17)) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: at most 131072 candidates per call");
-    if (prm->te_type != HB_TE_TIR) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: only HB_TE_TIR is implemented");
+    if (prm->te_type != HB_TE_TIR && prm->te_type != HB_TE_HELITRON)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: te_type must be HB_TE_TIR or HB_TE_HELITRON (non-LTR: not implemented)");
     if (prm->max_loci < 1 || prm->max_loci > 512 || prm->max_rows < 2 || prm->max_rows > 100 || prm->occ_cap < 1 ||
         prm->flank < 0 || prm->flank > 200)
         return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: parameter out of range");
@@ -418,14 +419,15 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     std::vector<HbVoteTask> tasks;
     std::vector<uint32_t> task_cand;
     tasks.reserve(n_cand); task_cand.reserve(n_cand);
-    uint64_t mat_total = 0, col_total = 0, match_total = 0;
+    uint64_t mat_total = 0, col_total = 0, match_total = 0, row_total = 0;
     for (uint32_t c = 0; c < n_cand; ++c) {
         h_mat_off[c] = mat_total;
         if (h_rows[c] == 0) continue;
         HbVoteTask t;
         memset(&t, 0, sizeof(t));
         t.raw_off = mat_total; t.clean_off = mat_total;
-        t.plane_off = col_total * 24; t.cons_off = col_total; t.match_off = match_total;
+        t.plane_off = col_total * 24; t.cons_off = col_total + 2ull * tasks.size(); t.match_off = match_total;
+        t.anchor_off = 2 * row_total;
         t.cand_off = cand_off[c]; t.cand_len = (int32_t)(cand_off[c + 1] - cand_off[c]);
         t.R = (int32_t)h_rows[c]; t.C = (int32_t)h_cols[c];
         t.te_type = prm->te_type; t.plant = prm->plant; t.result_type = prm->result_type; t.raw_is_ascii = 0;
@@ -433,6 +435,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         mat_total += (uint64_t)h_rows[c] * h_cols[c];
         col_total += h_cols[c];
         match_total += 2ull * ((uint64_t)h_cols[c] + 2);
+        row_total += h_rows[c];
     }
     h_mat_off[n_cand] = mat_total;
     const uint32_t n_tasks = (uint32_t)tasks.size();
@@ -458,18 +461,19 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         ENSURE("v.clean", mat_total + 1);
         ENSURE("v.planes", col_total * 24 * sizeof(uint32_t));
         ENSURE("v.matches", match_total * hb_vote_match_entry_size());
-        ENSURE("v.cons", col_total + 1);
+        ENSURE("v.cons", col_total + 2ull * n_tasks + 1);
+        ENSURE("v.anchors", sizeof(int) * (2 * row_total + 2));
         ENSURE("v.calls", sizeof(HbVoteCall) * n_tasks);
         ENSURE("v.len", sizeof(uint32_t) * (n_tasks + 1)); ENSURE("v.off", sizeof(uint32_t) * (n_tasks + 1));
-        ENSURE("v.dense", col_total + 1);
+        ENSURE("v.dense", col_total + 2ull * n_tasks + 1);
         ENSURE("v.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(n_tasks + 1));
         ENSURE("v.total", sizeof(uint64_t));
         HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("v.tasks").p, tasks.data(), sizeof(HbVoteTask) * n_tasks, cudaMemcpyHostToDevice, s));
         HB_CUDA_OK(cudaMemsetAsync(ctx->buf("v.calls").p, 0, sizeof(HbVoteCall) * n_tasks, s));
         HB_CUDA_OK(hb_vote_launch(ctx->buf("v.tasks").as<HbVoteTask>(), (int)n_tasks, ctx->buf("m.mat").as<uint8_t>(),
                                   ctx->buf("v.clean").as<uint8_t>(), ctx->buf("v.planes").as<uint32_t>(), ctx->buf("v.matches").p,
-                                  ctx->buf("c.ascii").as<uint8_t>(), ctx->buf("v.cons").as<uint8_t>(),
-                                  ctx->buf("v.calls").as<HbVoteCall>(), s));
+                                  ctx->buf("v.anchors").as<int>(), ctx->buf("c.ascii").as<uint8_t>(),
+                                  ctx->buf("v.cons").as<uint8_t>(), ctx->buf("v.calls").as<HbVoteCall>(), prm->te_type, s));
         HB_CUDA_OK(cudaEventRecord(ctx->ev[5], s));
         u32_field_kernel<<<(n_tasks + 255) / 256, 256, 0, s>>>(ctx->buf("v.calls").as<HbVoteCall>(), n_tasks, ctx->buf("v.len").as<uint32_t>());
         HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("v.len").as<uint32_t>(), ctx->buf("v.off").as<uint32_t>(), n_tasks,

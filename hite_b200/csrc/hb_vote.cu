@@ -506,6 +506,147 @@ __device__ __forceinline__ bool starts_with(const char* s, int n, const char* p,
     return true;
 }
 
+// anchors of one row (Util.py:9158-9181): true iff both 20-mers hit; columns in *as, *ae
+__device__ bool row_anchor(const uint8_t* __restrict__ row, int Cc, int cap, const Pattern& P1, const Pattern& P2,
+                           Match* __restrict__ ml, int* cnt, int lane, int* as, int* ae) {
+    int ub, n;
+    anchor_scan_row(row, Cc, P1, P2, ml, cap, cnt, lane, &ub, &n);
+    const int n1 = min(cap, cnt[0]), n2 = min(cap, cnt[1]);
+    __syncwarp();
+    if (n1 <= 0 || n2 <= 0) return false;
+    const int fs = first_group_best_start(ml, n1, lane);
+    const int le = last_group_best_end(ml + cap, n2, lane);
+    *as = column_of_ungapped(row, Cc, fs, ub, lane);
+    *ae = column_of_ungapped(row, Cc, le - 1, ub, lane);
+    return true;
+}
+
+// six bit-planes of the listed rows (row k of the list = bit k&31 of word k>>5)
+__device__ void build_planes(Planes& P, uint32_t* __restrict__ pw, const uint8_t* __restrict__ m, int C, int Cc,
+                             const unsigned short* rows, int row_num, int lane) {
+    P.p = pw; P.stride = C; P.nw = (row_num + 31) >> 5; P.row_num = row_num;
+    for (int wd = 0; wd < 4; ++wd) {
+        int rem = row_num - wd * 32;
+        P.rowmask[wd] = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+    }
+    __syncwarp();
+    for (int col = lane; col < Cc; col += 32) {
+        for (int wd = 0; wd < P.nw; ++wd) {
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+            const int kend = min(32, row_num - wd * 32);
+            for (int kk = 0; kk < kend; ++kk) {
+                const int s = m[(size_t)rows[wd * 32 + kk] * C + col];
+                const uint32_t bit = 1u << kk;
+                a0 |= (s == 0) ? bit : 0u; a1 |= (s == 1) ? bit : 0u; a2 |= (s == 2) ? bit : 0u;
+                a3 |= (s == 3) ? bit : 0u; a4 |= (s == 4) ? bit : 0u; a5 |= (s == 5) ? bit : 0u;
+            }
+            pw[(size_t)(0 * 4 + wd) * C + col] = a0; pw[(size_t)(1 * 4 + wd) * C + col] = a1;
+            pw[(size_t)(2 * 4 + wd) * C + col] = a2; pw[(size_t)(3 * 4 + wd) * C + col] = a3;
+            pw[(size_t)(4 * 4 + wd) * C + col] = a4; pw[(size_t)(5 * 4 + wd) * C + col] = a5;
+        }
+    }
+    __syncwarp();
+}
+
+// rows (in order) that have a non-gap symbol in [lo1,hi1) and in [lo2,hi2); at most MAX_KEPT
+// ("len(...) > 100: break", Util.py:9201 / :10017)
+__device__ int select_rows(const uint8_t* __restrict__ m, int R, int C, int lo1, int hi1, int lo2, int hi2,
+                           unsigned short* rows, int lane) {
+    int row_num = 0;
+    for (int r0 = 0; r0 < R && row_num < MAX_KEPT; r0 += 32) {
+        const int r = r0 + lane;
+        bool ok = false;
+        if (r < R) {
+            const uint8_t* row = m + (size_t)r * C;
+            bool a1 = false, a2 = false;
+            for (int c = lo1; c < hi1; ++c) a1 |= (row[c] != HB_SYM_GAP);
+            for (int c = lo2; c < hi2; ++c) a2 |= (row[c] != HB_SYM_GAP);
+            ok = a1 && a2;
+        }
+        const uint32_t bal = __ballot_sync(HB_FULL, ok);
+        const int pos = row_num + __popc(bal & lanemask_lt(lane));
+        if (ok && pos < MAX_KEPT) rows[pos] = (unsigned short)r;
+        row_num = min(MAX_KEPT, row_num + __popc(bal));
+    }
+    __syncwarp();
+    return row_num;
+}
+
+// ---- Helitron helpers: search_boundary_homo_v4 (Util.py:8556-8824) ---------------------------
+__device__ double ordered_ratio_avg(const Planes& P, const int* vc, int w, int lane) {
+    // mean of the stored per-column max_homo_ratio (denominator row_num, :8607) in list order
+    double total = 0.0;
+    for (int k0 = 0; k0 < w; k0 += 32) {
+        const int k = k0 + lane;
+        double ratio = 0.0;
+        if (k < w) {
+            const int col = vc[k];
+            int mx = 0;
+#pragma unroll
+            for (int s = 0; s < 5; ++s) mx = max(mx, P.count(s, col));
+            ratio = mx > 0 ? (double)mx / (double)P.row_num : 0.0;
+        }
+        const int lim = min(32, w - k0);
+        for (int j = 0; j < lim; ++j) total += __shfl_sync(HB_FULL, ratio, j);
+    }
+    return total / (double)w;
+}
+
+__device__ bool search_boundary_v4(const Planes& P, int vthr, int pos, int Cc, bool is_start, double thr,
+                                   double int_thr, double out_thr, int int_win, int out_win, int* vc, int lane,
+                                   int* boundary) {
+    int n, w, nb, cur;
+    if (is_start) {
+        n = collect_valid(P, vthr, pos, +1, 0, (Cc + 1) / 2, vc, lane);                  // :8592
+        cur = pos;
+        w = min(n, int_win);
+        if (w < 10) cur = -1;                                                            // :8622-8624
+        else { nb = slide_windows(P, vc, n, w, +1, thr, lane); if (nb != cur && nb != -1) cur = nb; }   // :8634-8637
+        n = (cur - 1 >= 0) ? collect_valid(P, vthr, cur - 1, -1, 0, Cc, vc, lane) : 0;   // :8639-8669
+        reverse_list(vc, n, lane);
+        w = min(n, out_win);
+        if (w < 10) cur = -1;                                                            // :8676-8678
+        else {
+            nb = slide_windows(P, vc, n, w, +1, thr, lane);
+            if (nb != -1) { if (nb < 10) cur = -1; else cur = nb; }                      // :8689-8697
+        }
+        *boundary = cur;
+        return true;                                                                     // :8699
+    }
+    *boundary = -1;
+    n = collect_valid(P, vthr, pos + 1, +1, 0, Cc, vc, lane);                            // :8704-8732
+    w = min(n, out_win);
+    if (w < 10) return false;                                                            // :8739-8741
+    if (ordered_ratio_avg(P, vc, w, lane) >= out_thr) return false;                      // :8754-8767
+    __syncwarp();
+    n = collect_valid(P, vthr, pos, -1, (Cc + 1) / 2, Cc, vc, lane);                     // :8769-8798
+    w = min(n, int_win);
+    if (w < 10) return false;                                                            // :8804-8806
+    if (ordered_ratio_avg(P, vc, w, lane) < int_thr) {
+        const int ne = vc[w - 1];
+        if (ne != pos && ne != -1) return false;                                         // :8817-8823
+    }
+    *boundary = pos;
+    return true;                                                                         // :8824
+}
+
+// first key (dict insertion order) with the largest count (Util.py:10082-10088): symbol + count
+__device__ __forceinline__ int max_key(const Planes& P, int col, int* count) {
+    int mxc = 0, mxs = -1, mxf = 1 << 21;
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+        int c = 0, f = 1 << 20;
+        for (int wd = P.nw - 1; wd >= 0; --wd) {
+            uint32_t x = P.w(s, wd, col);
+            c += __popc(x);
+            if (x) f = wd * 32 + __ffs(x) - 1;
+        }
+        if (c > mxc || (c == mxc && c > 0 && f < mxf)) { mxc = c; mxs = s; mxf = f; }
+    }
+    *count = mxc;
+    return mxs;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel B: judge_boundary_v5 (Util.py:9145-9480), one warp per candidate.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
@@ -717,6 +858,195 @@ hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t
     if (lane == 0) calls[ti] = call;
 }
 
+// ------------------------------------------------------------------------------------------
+// kernel B': judge_boundary_v6 (Helitron, Util.py:9821-10159), one warp per candidate.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_v6_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                   uint32_t* __restrict__ planes, Match* __restrict__ matches, int* __restrict__ anchors,
+                   const uint8_t* __restrict__ cands, uint8_t* __restrict__ cons_buf, HbVoteCall* __restrict__ calls) {
+    __shared__ int s_vc[WARPS_PER_CTA][128];
+    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    __shared__ unsigned short s_rows2[WARPS_PER_CTA][104];
+    __shared__ int s_cnt[WARPS_PER_CTA][2];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    HbVoteCall call = calls[ti];
+    const int R = t.R, C = t.C, Cc = call.clean_cols;
+    const uint8_t* m = clean + t.clean_off;
+    call.is_te = 0; call.info = 0; call.copy_num = 0; call.align_start = -1; call.align_end = -1;
+    call.homo_start = -1; call.homo_end = -1; call.cons_len = 0; call.trim_lead = 0; call.trim_trail = 0;
+    call.flags = 0; call.cons_off = (int64_t)t.cons_off;
+    int* vc = s_vc[wid];
+    unsigned short* rows = s_rows[wid];
+    unsigned short* rows2 = s_rows2[wid];
+    // ---- 1. anchors of ALL rows, then the mode (:9837-9866) ------------------------------------
+    int as = -1, ae = -1;
+    if (t.cand_len > 2 && Cc > 0) {
+        const uint8_t* cand = cands + t.cand_off;
+        const int alen = min(20, t.cand_len);
+        Pattern P1, P2;
+        pattern_init(P1, cand, alen);
+        pattern_init(P2, cand + (t.cand_len - alen), alen);
+        Match* ml = matches + t.match_off;
+        int* an = anchors + t.anchor_off;          // [0..R) starts, [R..2R) ends
+        int na = 0;
+        for (int r = 0; r < R; ++r) {
+            int a = -1, b = -1;
+            if (row_anchor(m + (size_t)r * C, Cc, C + 2, P1, P2, ml, s_cnt[wid], lane, &a, &b)) {
+                if (lane == 0) { an[na] = a; an[R + na] = b; }
+                ++na;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        // most_common_element (:9722-9730): highest count, ties -> first inserted
+        for (int which = 0; which < 2; ++which) {
+            const int* arr = an + which * R;
+            unsigned long long best = 0;
+            for (int i = lane; i < na; i += 32) {
+                const int v = arr[i];
+                int cnt = 0, first = i;
+                for (int j = 0; j < na; ++j) { if (arr[j] == v) { ++cnt; if (j < first) first = j; } }
+                const unsigned long long key = ((unsigned long long)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)first);
+                best = key > best ? key : best;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(HB_FULL, best, o); best = x > best ? x : best; }
+            const int val = na > 0 ? arr[0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull)] : -1;
+            if (which == 0) as = val; else ae = val;
+        }
+    }
+    call.align_start = as; call.align_end = ae;
+    if (as < 0 || ae < 0) { call.info = 1; if (lane == 0) calls[ti] = call; return; }     // :9870-9873
+    // ---- 2. start / end member sets (:9884-9936): the loop stops for both once either exceeds 100
+    int ns = 0, ne = 0;
+    {
+        const int s_lo = max(0, as - 1), s_hi = min(Cc, as + 1);
+        int e_lo, e_hi;
+        py_slice(Cc, (long long)ae - 1, (ae + 1 < Cc) ? ae + 1 : Cc, &e_lo, &e_hi);
+        for (int r0 = 0; r0 < R && ns <= 100 && ne <= 100; r0 += 32) {
+            const int r = r0 + lane;
+            bool fs = false, fe = false;
+            if (r < R) {
+                const uint8_t* row = m + (size_t)r * C;
+                for (int c = s_lo; c < s_hi; ++c) fs |= (row[c] != HB_SYM_GAP);
+                for (int c = e_lo; c < e_hi; ++c) fe |= (row[c] != HB_SYM_GAP);
+            }
+            const uint32_t bs = __ballot_sync(HB_FULL, fs), be = __ballot_sync(HB_FULL, fe);
+            const int ps = ns + __popc(bs & lanemask_lt(lane)), pe = ne + __popc(be & lanemask_lt(lane));
+            const bool processed = r < R && ps <= 100 && pe <= 100;        // loop-top checks :9885-9888
+            const uint32_t bsp = __ballot_sync(HB_FULL, fs && processed), bep = __ballot_sync(HB_FULL, fe && processed);
+            if (fs && processed) rows[ps] = (unsigned short)r;
+            if (fe && processed) rows2[pe] = (unsigned short)r;
+            ns += __popc(bsp); ne += __popc(bep);
+            if (__ballot_sync(HB_FULL, r < R && !processed)) break;
+        }
+        __syncwarp();
+    }
+    if (ne <= 0) { if (lane == 0) calls[ti] = call; return; }                              // :9940-9941
+    Planes P;
+    uint32_t* pw = planes + t.plane_off;
+    int he = -1, hs = -1;
+    {   // end first (:9972-9979)
+        build_planes(P, pw, m, C, Cc, rows2, ne, lane);
+        const double thr = ne <= 2 ? 0.95 : (ne <= 5 ? 0.9 : 0.7);
+        const double ithr = ne <= 2 ? 0.9 : (ne <= 5 ? 0.85 : 0.65);
+        const double othr = ne <= 2 ? 0.95 : (ne <= 5 ? 0.9 : 0.7);
+        const bool ok = search_boundary_v4(P, ne / 2, ae, Cc, false, thr, ithr, othr, 20, 10, vc, lane, &he);
+        if (!ok) { if (lane == 0) calls[ti] = call; return; }
+        call.homo_end = he;
+    }
+    {   // then start (:9991-10008)
+        build_planes(P, pw, m, C, Cc, rows, ns, lane);
+        const double thr = ns <= 2 ? 0.95 : (ns <= 5 ? 0.9 : 0.7);
+        const double ithr = ns <= 2 ? 0.9 : (ns <= 5 ? 0.85 : 0.65);
+        const double othr = ns <= 2 ? 0.95 : (ns <= 5 ? 0.9 : 0.7);
+        search_boundary_v4(P, ns / 2, as, Cc, true, thr, ithr, othr, 20, 10, vc, lane, &hs);
+        call.homo_start = hs;
+    }
+    // ---- 3. full-length members (+-1 around the homology boundaries, :10012-10038) -------------
+    int row_num;
+    {
+        int s_lo, s_hi, e_lo, e_hi;
+        py_slice(Cc, hs - 1 >= 0 ? hs - 1 : 0, (long long)hs + 1, &s_lo, &s_hi);
+        py_slice(Cc, (long long)he - 1, (he + 1 < Cc) ? he + 1 : Cc, &e_lo, &e_hi);
+        row_num = select_rows(m, R, C, s_lo, s_hi, e_lo, e_hi, rows, lane);
+    }
+    if (row_num <= 0) { if (lane == 0) calls[ti] = call; return; }
+    call.copy_num = row_num;
+    build_planes(P, pw, m, C, Cc, rows, row_num, lane);
+    // ---- 4. consensus with 'N' for weak columns (:10078-10095) and +-1 bp extension (:10097-10130)
+    uint8_t* cons = cons_buf + t.cons_off;
+    const int half = row_num / 2;
+    int lext = -1, rext = -1;
+    for (int c0 = hs - 1; c0 >= 0 && lext < 0; c0 -= 32) {
+        const int c = c0 - lane;
+        int cnt = 0, sy = -1;
+        if (c >= 0) sy = max_key(P, c, &cnt);
+        const uint32_t bal = __ballot_sync(HB_FULL, c >= 0 && cnt >= half && sy != HB_SYM_GAP);
+        if (bal) lext = __shfl_sync(HB_FULL, sy, __ffs(bal) - 1);
+    }
+    for (int c0 = he + 1; c0 < Cc && rext < 0; c0 += 32) {
+        const int c = c0 + lane;
+        int cnt = 0, sy = -1;
+        if (c < Cc) sy = max_key(P, c, &cnt);
+        const uint32_t bal = __ballot_sync(HB_FULL, c < Cc && cnt >= half && sy != HB_SYM_GAP);
+        if (bal) rext = __shfl_sync(HB_FULL, sy, __ffs(bal) - 1);
+    }
+    int ml = 0;
+    if (lext >= 0) { if (lane == 0) cons[0] = (uint8_t)hb_ascii_of_sym(lext); ml = 1; }
+    for (int c0 = hs; c0 <= he; c0 += 32) {
+        const int c = c0 + lane;
+        int out = -1;                                    // -1 nothing, else ASCII
+        if (c <= he) {
+            int cnt; const int sy = max_key(P, c, &cnt);
+            if (cnt >= half) out = (sy != HB_SYM_GAP) ? hb_ascii_of_sym(sy) : -1;
+            else out = 'N';
+        }
+        const uint32_t bal = __ballot_sync(HB_FULL, out >= 0);
+        if (out >= 0) cons[ml + __popc(bal & lanemask_lt(lane))] = (uint8_t)out;
+        ml += __popc(bal);
+    }
+    if (rext >= 0) { if (lane == 0) cons[ml] = (uint8_t)hb_ascii_of_sym(rext); ++ml; }
+    __syncwarp();
+    // ---- 5. ATC ... CTRRT motif (:10135-10150) ---------------------------------------------------
+    int final_lo = 0, final_hi = 0;
+    {
+        int f_lo, f_hi, l_lo, l_hi;
+        py_slice(ml, 0, 10, &f_lo, &f_hi);
+        py_slice(ml, -10, ml, &l_lo, &l_hi);
+        char head[10], tail[10];
+        for (int i = 0; i < f_hi - f_lo; ++i) head[i] = (char)cons[f_lo + i];
+        for (int i = 0; i < l_hi - l_lo; ++i) tail[i] = (char)cons[l_lo + i];
+        const char motifs[4][5] = {{'C', 'T', 'A', 'G', 'T'}, {'C', 'T', 'A', 'A', 'T'}, {'C', 'T', 'G', 'G', 'T'}, {'C', 'T', 'G', 'A', 'T'}};
+        for (int q = 0; q < 4; ++q) {
+            int end_index = -1;
+            for (int k = (l_hi - l_lo) - 5; k >= 0; --k) {
+                bool eq = true;
+                for (int z = 0; z < 5; ++z) eq &= (tail[k + z] == motifs[q][z]);
+                if (eq) { end_index = k; break; }
+            }
+            if (end_index == -1) continue;
+            int start_index = -1;
+            for (int k = 0; k + 3 <= f_hi - f_lo; ++k)
+                if (head[k] == 'A' && head[k + 1] == 'T' && head[k + 2] == 'C') { start_index = k; break; }
+            if (start_index != -1) {
+                const int cut = 10 - (end_index + 3) - 1;
+                if (cut == 0) py_slice(ml, start_index + 1, ml, &final_lo, &final_hi);
+                else py_slice(ml, start_index + 1, -(long long)cut, &final_lo, &final_hi);
+                break;
+            }
+        }
+    }
+    const int fl = max(0, final_hi - final_lo);
+    call.cons_len = fl;
+    call.cons_off = (int64_t)t.cons_off + final_lo;
+    call.is_te = fl > 0;
+    if (lane == 0) calls[ti] = call;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -724,12 +1054,18 @@ hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t
 extern "C" size_t hb_vote_match_entry_size() { return sizeof(Match); }
 
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
-                                      uint32_t* d_planes, void* d_matches, const uint8_t* d_cands,
-                                      uint8_t* d_cons, HbVoteCall* d_calls, cudaStream_t stream) {
+                                      uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
+                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     hb_clean_kernel<<<n, CLEAN_THREADS, 0, stream>>>(d_tasks, d_raw, d_clean, d_calls);
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    hb_judge_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
-                                                             d_cands, d_cons, d_calls);
+    if (te_type == 0)
+        hb_judge_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
+                                                                 d_cands, d_cons, d_calls);
+    else if (te_type == 1)
+        hb_judge_v6_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
+                                                                    d_anchors, d_cands, d_cons, d_calls);
+    else
+        return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

@@ -73,14 +73,15 @@ int hb_get_timing(hb_ctx* ctx, hb_timing* out);
 /*
  * hb_vote_matrices -- judge n pre-aligned matrices (the parity entry; kernel (iii)).
  * Replaces, per candidate, remove_sparse_col_in_align_file (module/Util.py:10344-10405) followed
- * by judge_boundary_v5 (module/Util.py:9145-9480; te_type HB_TE_TIR), i.e. the body of
+ * by judge_boundary_v5 (module/Util.py:9145-9480; te_type HB_TE_TIR) or judge_boundary_v6
+ * (module/Util.py:9821-10159; HB_TE_HELITRON, plant/result_type ignored), i.e. the body of
  * is_TE_from_align_file after mafft (module/Util.py:10419-10432).
  *
  *   rows_ascii : concatenated R_i x C_i row-major ASCII matrices ('-' = gap), matrix i at mat_off[i]
  *   cand_ascii : concatenated candidate sequences, candidate i at cand_off[i] .. cand_off[i+1]
  *   result_type: 1 = 'cons' (column vote), 0 = first full-length row
  *   calls      : n results
- *   cons_out   : receives consensus bytes; capacity cons_cap >= sum(C_i); candidate i's consensus
+ *   cons_out   : receives consensus bytes; capacity cons_cap >= sum(C_i) + 2n; candidate i's consensus
  *                is cons_out[calls[i].cons_off .. +cons_len)
  */
 int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_ascii, const uint64_t* mat_off,

@@ -31,6 +31,11 @@ int hbo_find_anchor(const char *cand, int cand_len, const char *m, int R, int C,
 int hbo_judge_v5(const char *cand, int cand_len, const char *m, int R, int C, int plant,
                  int result_type_cons, hbo_call *out, char *cons);
 
+int hbo_search_boundary_homo_v4(int vthr, int pos, const char *const *rows, int R, int C, int is_start,
+                                double thr, double int_thr, double out_thr, int int_win, int out_win,
+                                const void *colmaps, int *boundary);
+int hbo_judge_v6(const char *cand, int cand_len, const char *m, int R, int C, hbo_call *out, char *cons);
+
 /* ---- HB-align restatement (hbo_align.c) ---- */
 #include <stdint.h>
 typedef struct hbo_genome hbo_genome;

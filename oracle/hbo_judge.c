@@ -525,3 +525,218 @@ int hbo_judge_v5(const char *cand, int cand_len, const char *m, int R, int C, in
     free(model); free(cm); free(rows);
     return 0;
 }
+
+/* ========================================================================================== */
+/* Helitron: judge_boundary_v6 (Util.py:9821-10159) + search_boundary_homo_v4 (Util.py:8556-8824) */
+
+static int collect_valid_cols(const colmap *cm, int vthr, int start, int dir, int lo, int hi, int *vc) {
+    int n = 0;
+    for (int c = start; n < 100 && c >= lo && c < hi; c += dir)
+        if (cm[c].cnt[5] <= vthr) vc[n++] = c;
+    return n;
+}
+
+static double col_max_ratio(const colmap *x, int row_num) {      /* stored max_homo_ratio :8607-8613 */
+    int mx = 0;
+    for (int s = 0; s < 5; ++s) if (x->cnt[s] > mx) mx = x->cnt[s];
+    return mx > 0 ? (double)mx / (double)row_num : 0.0;
+}
+
+/* returns valid flag; *boundary gets the second tuple element */
+int hbo_search_boundary_homo_v4(int vthr, int pos, const char *const *rows, int R, int C, int is_start,
+                                double thr, double int_thr, double out_thr, int int_win, int out_win,
+                                const void *cmv, int *boundary) {
+    const colmap *cm = (const colmap *)cmv;
+    int *vc = (int *)malloc(sizeof(int) * (size_t)(C + 1));
+    int n, w, nb, cur;
+    if (is_start) {
+        n = (pos >= 0) ? collect_valid_cols(cm, vthr, pos, +1, 0, (C + 1) / 2, vc) : 0;      /* :8592 */
+        cur = pos;
+        w = n < int_win ? n : int_win;
+        if (w < 10) cur = -1;                                                                  /* :8622-8624 */
+        else {
+            nb = slide_windows(rows, R, vc, n, w, +1, thr);
+            if (nb != cur && nb != -1) cur = nb;                                               /* :8634-8637 */
+        }
+        n = (cur - 1 >= 0) ? collect_valid_cols(cm, vthr, cur - 1, -1, 0, C, vc) : 0;          /* :8639-8669 */
+        for (int a = 0, b = n - 1; a < b; ++a, --b) { int t = vc[a]; vc[a] = vc[b]; vc[b] = t; }
+        w = n < out_win ? n : out_win;
+        if (w < 10) cur = -1;                                                                  /* :8676-8678 */
+        else {
+            nb = slide_windows(rows, R, vc, n, w, +1, thr);
+            if (nb != -1) { if (nb < 10) cur = -1; else if (nb != cur) cur = nb; }             /* :8689-8697 */
+        }
+        *boundary = cur;
+        free(vc);
+        return 1;                                                                              /* :8699 */
+    }
+    n = collect_valid_cols(cm, vthr, pos + 1, +1, 0, C, vc);                                   /* :8704-8732 */
+    w = n < out_win ? n : out_win;
+    *boundary = -1;
+    if (w < 10) { free(vc); return 0; }                                                        /* :8739-8741 */
+    {
+        double avg = 0.0;                                                                      /* window i == 0 only */
+        for (int k = 0; k < w; ++k) avg += col_max_ratio(&cm[vc[k]], R);
+        avg = avg / (double)w;
+        if (avg >= out_thr) { free(vc); return 0; }       /* new_boundary_end != -1 -> both branches return False (:8758-8767) */
+    }
+    n = collect_valid_cols(cm, vthr, pos, -1, (C + 1) / 2, C, vc);                             /* :8769-8798 */
+    w = n < int_win ? n : int_win;
+    if (w < 10) { free(vc); return 0; }                                                        /* :8804-8806 */
+    {
+        double avg = 0.0;
+        for (int k = 0; k < w; ++k) avg += col_max_ratio(&cm[vc[k]], R);
+        avg = avg / (double)w;
+        if (avg < int_thr) {
+            int ne = vc[w - 1];
+            if (ne != pos && ne != -1) { free(vc); return 0; }                                 /* :8817-8823 */
+        }
+    }
+    *boundary = pos;
+    free(vc);
+    return 1;                                                                                  /* :8824 */
+}
+
+static int most_common(const int *arr, int n) {          /* most_common_element :9722-9730 */
+    if (n <= 0) return -1;
+    int best = arr[0], bc = 0;
+    for (int i = 0; i < n; ++i) {
+        int seen = 0;
+        for (int j = 0; j < i; ++j) if (arr[j] == arr[i]) { seen = 1; break; }
+        if (seen) continue;
+        int c = 0;
+        for (int j = i; j < n; ++j) c += (arr[j] == arr[i]);
+        if (c > bc) { bc = c; best = arr[i]; }            /* ties: first inserted wins */
+    }
+    return best;
+}
+
+static int max_key(const colmap *x, int *count) {         /* first key with the largest count (:10082-10088) */
+    int mxc = 0, mxs = -1;
+    for (int k = 0; k < x->nkeys; ++k) { int s = x->order[k]; if (x->cnt[s] > mxc) { mxc = x->cnt[s]; mxs = s; } }
+    *count = mxc;
+    return mxs;
+}
+
+int hbo_judge_v6(const char *cand, int cand_len, const char *m, int R, int C, hbo_call *out, char *cons) {
+    memset(out, 0, sizeof(*out));
+    out->homo_start = out->homo_end = -1; out->align_start = out->align_end = -1;
+    cons[0] = 0;
+    int alen = cand_len < 20 ? cand_len : 20;
+    const char *first = cand, *last = cand + (cand_len - alen);
+    char *u = (char *)malloc((size_t)C + 1);
+    int *pos = (int *)malloc(sizeof(int) * (size_t)(C + 1));
+    int *as_l = (int *)malloc(sizeof(int) * (size_t)(R + 1)), *ae_l = (int *)malloc(sizeof(int) * (size_t)(R + 1));
+    int na = 0;
+    for (int r = 0; r < R; ++r) {                                                       /* :9837-9863, all rows */
+        const char *row = m + (size_t)r * C;
+        int n = 0;
+        for (int c = 0; c < C; ++c) if (row[c] != '-') { u[n] = row[c]; pos[n] = c; ++n; }
+        int fs, fe, ls, le;
+        if (hbo_find_near_matches(first, alen, u, n, 2, &fs, &fe, NULL, NULL) <= 0) continue;
+        if (hbo_find_near_matches(last, alen, u, n, 2, NULL, NULL, &ls, &le) <= 0) continue;
+        as_l[na] = pos[fs]; ae_l[na] = pos[le - 1]; ++na;
+    }
+    int as = most_common(as_l, na), ae = most_common(ae_l, na);                         /* :9865-9866 */
+    free(u); free(pos); free(as_l); free(ae_l);
+    out->align_start = as; out->align_end = ae;
+    if (as == -1 || ae == -1) { out->info = HBO_INFO_NB; return 0; }                    /* :9870-9873 */
+    /* start / end member sets :9884-9936 */
+    const char **srows = (const char **)malloc(sizeof(char *) * (size_t)(R + 1));
+    const char **erows = (const char **)malloc(sizeof(char *) * (size_t)(R + 1));
+    int ns = 0, ne = 0;
+    for (int r = 0; r < R; ++r) {
+        if (ns > 100) break;
+        if (ne > 100) break;
+        const char *row = m + (size_t)r * C;
+        int lo, hi, any = 0;
+        py_slice(C, as - 1 >= 0 ? as - 1 : 0, (long)as + 1, &lo, &hi);
+        for (int c = lo; c < hi; ++c) if (row[c] != '-') { any = 1; break; }
+        if (any) srows[ns++] = row;
+        any = 0;
+        py_slice(C, (long)ae - 1, ae + 1 < C ? ae + 1 : C, &lo, &hi);
+        for (int c = lo; c < hi; ++c) if (row[c] != '-') { any = 1; break; }
+        if (any) erows[ne++] = row;
+    }
+    if (ne <= 0) { free(srows); free(erows); return 0; }                                /* :9940-9941 */
+    colmap *cm = (colmap *)malloc(sizeof(colmap) * (size_t)C);
+    {
+        double thr = ne <= 2 ? 0.95 : (ne <= 5 ? 0.9 : 0.7);
+        double ithr = ne <= 2 ? 0.9 : (ne <= 5 ? 0.85 : 0.65);
+        double othr = ne <= 2 ? 0.95 : (ne <= 5 ? 0.9 : 0.7);
+        build_colmap(erows, ne, C, cm);
+        int he;
+        int ok = hbo_search_boundary_homo_v4(ne / 2, ae, erows, ne, C, 0, thr, ithr, othr, 20, 10, cm, &he);
+        if (!ok) { free(cm); free(srows); free(erows); return 0; }                      /* :9976-9979 */
+        out->homo_end = he;
+    }
+    int hs;
+    {
+        double thr = ns <= 2 ? 0.95 : (ns <= 5 ? 0.9 : 0.7);
+        double ithr = ns <= 2 ? 0.9 : (ns <= 5 ? 0.85 : 0.65);
+        double othr = ns <= 2 ? 0.95 : (ns <= 5 ? 0.9 : 0.7);
+        build_colmap(srows, ns, C, cm);
+        hbo_search_boundary_homo_v4(ns / 2, as, srows, ns, C, 1, thr, ithr, othr, 20, 10, cm, &hs);
+        out->homo_start = hs;
+    }
+    const int he = out->homo_end;
+    /* full-length members :10012-10038 (rows reuse srows storage) */
+    int nr = 0;
+    for (int r = 0; r < R; ++r) {
+        if (nr > 100) break;
+        const char *row = m + (size_t)r * C;
+        int lo, hi, a1 = 0, a2 = 0;
+        py_slice(C, hs - 1 >= 0 ? hs - 1 : 0, (long)hs + 1, &lo, &hi);
+        for (int c = lo; c < hi; ++c) if (row[c] != '-') { a1 = 1; break; }
+        py_slice(C, (long)he - 1, he + 1 < C ? he + 1 : C, &lo, &hi);
+        for (int c = lo; c < hi; ++c) if (row[c] != '-') { a2 = 1; break; }
+        if (a1 && a2) srows[nr++] = row;
+    }
+    if (nr <= 0) { free(cm); free(srows); free(erows); return 0; }
+    const int row_num = nr;
+    out->copy_num = row_num;
+    build_colmap(srows, row_num, C, cm);
+    /* consensus with 'N' for weak columns :10078-10095, +-1 bp extension :10097-10130 */
+    char *model = (char *)malloc((size_t)C + 8);
+    int ml = 0;
+    {
+        int col = hs - 1, cnt;                                                          /* left extension first in the result */
+        char lext = 0;
+        while (col >= 0) { int s = max_key(&cm[col], &cnt); if (cnt >= row_num / 2 && s != 5) { lext = SYM_CHR[s]; break; } --col; }
+        if (lext) model[ml++] = lext;
+        for (int c = hs; c <= he; ++c) {
+            int s = max_key(&cm[c], &cnt);
+            if (cnt >= row_num / 2) { if (s != 5) model[ml++] = SYM_CHR[s]; }
+            else model[ml++] = 'N';
+        }
+        col = he + 1;
+        while (col < C) { int s = max_key(&cm[col], &cnt); if (cnt >= row_num / 2 && s != 5) { model[ml++] = SYM_CHR[s]; break; } ++col; }
+    }
+    model[ml] = 0;
+    /* motif search :10135-10150 */
+    static const char *tails[4] = {"CTAGT", "CTAAT", "CTGGT", "CTGAT"};
+    int f_lo, f_hi, l_lo, l_hi;
+    py_slice(ml, 0, 10, &f_lo, &f_hi);
+    py_slice(ml, -10, ml, &l_lo, &l_hi);
+    int final_lo = 0, final_hi = 0;
+    for (int t = 0; t < 4; ++t) {
+        int end_index = -1;
+        for (int k = l_hi - l_lo - 5; k >= 0; --k) if (memcmp(model + l_lo + k, tails[t], 5) == 0) { end_index = k; break; }
+        if (end_index == -1) continue;
+        int start_index = -1;
+        for (int k = 0; k + 3 <= f_hi - f_lo; ++k) if (memcmp(model + f_lo + k, "ATC", 3) == 0) { start_index = k; break; }
+        if (start_index != -1) {
+            int cut = 10 - (end_index + 3) - 1;
+            if (cut == 0) py_slice(ml, start_index + 1, ml, &final_lo, &final_hi);
+            else py_slice(ml, start_index + 1, -(long)cut, &final_lo, &final_hi);
+            break;
+        }
+    }
+    int fl = final_hi - final_lo;
+    if (fl > 0) memcpy(cons, model + final_lo, (size_t)fl);
+    cons[fl > 0 ? fl : 0] = 0;
+    out->cons_len = fl > 0 ? fl : 0;
+    out->is_te = fl > 0;
+    free(model); free(cm); free(srows); free(erows);
+    return 0;
+}

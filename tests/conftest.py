@@ -26,3 +26,11 @@ def golden_v5():
     import json
     with gzip.open(os.path.join(ROOT, "tests", "golden", "judge_v5.json.gz")) as f:
         return json.loads(f.read())
+
+
+@pytest.fixture(scope="session")
+def golden_v6():
+    import gzip
+    import json
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "judge_v6.json.gz")) as f:
+        return json.loads(f.read())

@@ -47,8 +47,49 @@ def run_reference_v5(U, case, tmpdir):
                 homo_start=hs, homo_end=he)
 
 
+def run_reference_v6(U, case, tmpdir):
+    """remove_sparse_col_in_align_file (Util.py:10344) + judge_boundary_v6 (Util.py:9821)."""
+    path = os.path.join(tmpdir, "h.maf.fa")
+    with open(path, "w") as f:
+        for i, row in enumerate(case["rows"]):
+            f.write(">r%d\n%s\n" % (i, row))
+    clean = U.remove_sparse_col_in_align_file(path)
+    names, contigs = U.read_fasta(clean)
+    trace = []
+    orig = U.search_boundary_homo_v4
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        trace.append(r)
+        return r
+
+    U.search_boundary_homo_v4 = spy
+    try:
+        is_te, info, cons, copy_num = U.judge_boundary_v6(case["cand"], clean, 0, "helitron", case["plant"], "cons")
+    finally:
+        U.search_boundary_homo_v4 = orig
+    return dict(clean_rows=[contigs[n] for n in names], is_te=bool(is_te), info=info, cons=cons, copy_num=copy_num,
+                v4=[[bool(a), int(b)] for a, b in trace])
+
+
+def write(path, out):
+    with gzip.GzipFile(path, "wb", mtime=0) as f:
+        f.write(json.dumps(out, separators=(",", ":")).encode())
+    print("wrote", path, len(out), "cases;", sum(r["expect"]["is_te"] for r in out), "TE;", os.path.getsize(path), "bytes")
+    from collections import Counter
+    print(Counter((r["scenario"], r["expect"]["is_te"], r["expect"]["info"]) for r in out))
+
+
 def main():
     U = ref_import.load_util()
+    with tempfile.TemporaryDirectory() as td:
+        out = []
+        for seed in range(1, 121):
+            case = msa_synth.synth_case_helitron(seed)
+            exp = run_reference_v6(U, case, td)
+            out.append(dict(seed=seed, scenario=case["scenario"], cand=case["cand"], plant=case["plant"],
+                            rows=case["rows"], truth=case["truth"], expect=exp))
+        write(os.path.join(ROOT, "tests", "golden", "judge_v6.json.gz"), out)
     out = []
     with tempfile.TemporaryDirectory() as td:
         seeds = list(range(1, 161))

@@ -125,3 +125,56 @@ def synth_case(seed, scenario=None):
     elif scen == "no_anchor":
         cand = rand_seq(rng, length)
     return dict(cand=cand, rows=rows, plant=rng.choice([0, 1]), te_type="tir", scenario=scen, truth=elem)
+
+
+def synth_case_helitron(seed, scenario=None):
+    """Helitron-shaped cases for judge_boundary_v6 (reference Util.py:9821): element 5'-TC ... CTRR-3',
+    inserted between an A and a T of the host (so the row reads ...A|TC......CTRR|T...)."""
+    rng = random.Random(seed)
+    scen = scenario or rng.choice(["clean", "clean", "clean", "shift_out", "shift_in", "fp_homolog_flank",
+                                   "fragments", "few_rows", "no_anchor", "no_motif", "many_rows"])
+    flank = 50
+    nrows = rng.randint(3, 30)
+    if scen == "few_rows":
+        nrows = rng.randint(1, 5)
+    elif scen == "many_rows":
+        nrows = rng.randint(101, 120)
+    length = rng.randint(100, 380)
+    sub = rng.choice([0.0, 0.02, 0.05])
+    dele = rng.choice([0.0, 0.005, 0.02])
+    tail = rng.choice(["CTAG", "CTAA", "CTGG", "CTGA"]) if scen != "no_motif" else rand_seq(rng, 4)
+    head = "TC" if scen != "no_motif" or rng.random() < 0.5 else rand_seq(rng, 2)
+    elem = head + rand_seq(rng, length - 6) + tail
+    shared_l, shared_r = rand_seq(rng, flank), rand_seq(rng, flank)
+    rows = []
+    for r in range(nrows):
+        lf = rand_seq(rng, flank - 1) + "A"
+        rf = "T" + rand_seq(rng, flank - 1)
+        if scen == "fp_homolog_flank":
+            lf = mutate_row(rng, shared_l, 0.03, 0.0).replace("-", "A")
+            rf = mutate_row(rng, shared_r, 0.03, 0.0).replace("-", "A")
+        body = mutate_row(rng, elem, sub, dele)
+        if scen == "fragments" and r > 0 and rng.random() < 0.4:
+            cut = rng.randint(10, len(body) // 2)
+            if rng.random() < 0.5:
+                body = "-" * cut + body[cut:]
+                lf = "-" * flank
+            else:
+                body = body[:-cut] + "-" * cut
+                rf = "-" * flank
+        rows.append(lf + body + rf)
+    for _ in range(rng.randint(0, 4)):
+        p = rng.randint(1, len(rows[0]) - 1)
+        who = set(rng.sample(range(nrows), k=min(nrows, rng.choice([1, 1, 2, nrows // 2 + 1]))))
+        rows = [row[:p] + (rng.choice(BASES) if i in who else "-") + row[p:] for i, row in enumerate(rows)]
+    cand = elem
+    if scen == "shift_out":
+        r0 = rows[0].replace("-", "")
+        core_start = len(rows[0][:flank].replace("-", ""))
+        core_end = len(r0) - len(rows[0][-flank:].replace("-", ""))
+        cand = r0[max(0, core_start - rng.randint(0, 10)):core_end + rng.randint(0, 10)]
+    elif scen == "shift_in":
+        cand = elem[rng.randint(0, 12):len(elem) - rng.randint(0, 12)]
+    elif scen == "no_anchor":
+        cand = rand_seq(rng, length)
+    return dict(cand=cand, rows=rows, plant=1, te_type="helitron", scenario=scen, truth=elem)

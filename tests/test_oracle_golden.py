@@ -63,3 +63,14 @@ def test_levenshtein():
     assert oracle.levenshtein("ACGTA", "TCGTT") == 2
     assert oracle.levenshtein("", "ACG") == 3
     assert fnm.levenshtein("kitten", "sitting") == 3 == oracle.levenshtein("kitten", "sitting")
+
+
+def test_oracle_judge_v6_matches_reference_goldens(golden_v6):
+    assert len(golden_v6) >= 100
+    for rec in golden_v6:
+        exp = rec["expect"]
+        clean = oracle.remove_sparse_cols(rec["rows"])
+        assert clean == exp["clean_rows"], rec["seed"]
+        r = oracle.judge_v6(rec["cand"], clean)
+        for k in ("is_te", "info", "cons", "copy_num"):
+            assert r[k] == exp[k], (rec["seed"], rec["scenario"], k)

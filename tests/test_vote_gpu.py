@@ -61,3 +61,21 @@ def test_vote_large_matrix_property(ctx):
     assert r2["cons"] == r1["cons"] and r2["homo_start"] == r1["homo_start"]
     exp = oracle.judge_v5(elem, clean, 1)
     _check(r1, exp, "large")
+
+
+def test_helitron_vote_matches_reference_goldens(ctx, golden_v6):
+    res = ctx.vote_matrices([r["cand"] for r in golden_v6], [r["rows"] for r in golden_v6], "helitron", 1)
+    for r, rec in zip(res, golden_v6):
+        exp = rec["expect"]
+        for k in KEYS:
+            assert r[k] == exp[k], (rec["seed"], rec["scenario"], k, r[k], exp[k])
+
+
+def test_helitron_vote_matches_oracle_on_fresh_seeds(ctx):
+    cases = [msa_synth.synth_case_helitron(s) for s in range(7000, 7500)]
+    res = ctx.vote_matrices([c["cand"] for c in cases], [c["rows"] for c in cases], "helitron", 1)
+    for r, c in zip(res, cases):
+        exp = oracle.judge_v6(c["cand"], oracle.remove_sparse_cols(c["rows"]))
+        assert (r["align_start"], r["align_end"]) == (exp["align_start"], exp["align_end"]), c["scenario"]
+        for k in KEYS + ("homo_start", "homo_end"):
+            assert r[k] == exp[k], (c["scenario"], k, r[k], exp[k])
