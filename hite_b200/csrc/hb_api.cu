@@ -81,8 +81,8 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
     if (n == 0) return HB_OK;
     if (!rows_ascii || !mat_off || !R || !C || !cand_ascii || !cand_off || !calls || !cons_out)
         return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: null argument");
-    if (te_type != HB_TE_TIR && te_type != HB_TE_HELITRON)
-        return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: te_type must be HB_TE_TIR or HB_TE_HELITRON (non-LTR: not implemented)");
+    if (te_type < HB_TE_TIR || te_type > HB_TE_NON_LTR)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_vote_matrices: te_type must be HB_TE_TIR, HB_TE_HELITRON or HB_TE_NON_LTR");
     static_assert(sizeof(hb_call) == sizeof(HbVoteCall), "hb_call layout");
     cudaSetDevice(ctx->device);
     std::vector<HbVoteTask> tasks(n);

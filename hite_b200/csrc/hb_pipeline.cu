@@ -218,8 +218,8 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     if (!ctx->have_index) return hb_fail_msg(ctx, HB_ESTATE, "hb_adjust: call hb_genome_load + hb_index_build first");
     if (n_cand == 0) { if (cons_bytes) *cons_bytes = 0; return HB_OK; }
     if (n_cand > (1u << 17)) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: at most 131072 candidates per call");
-    if (prm->te_type != HB_TE_TIR && prm->te_type != HB_TE_HELITRON)
-        return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: te_type must be HB_TE_TIR or HB_TE_HELITRON (non-LTR: not implemented)");
+    if (prm->te_type < HB_TE_TIR || prm->te_type > HB_TE_NON_LTR)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: te_type must be HB_TE_TIR, HB_TE_HELITRON or HB_TE_NON_LTR");
     if (prm->max_loci < 1 || prm->max_loci > 512 || prm->max_rows < 2 || prm->max_rows > 100 || prm->occ_cap < 1 ||
         prm->flank < 0 || prm->flank > 200)
         return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: parameter out of range");

@@ -648,27 +648,23 @@ __device__ __forceinline__ int max_key(const Planes& P, int col, int* count) {
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel B: judge_boundary_v5 (Util.py:9145-9480), one warp per candidate.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
-                uint32_t* __restrict__ planes, Match* __restrict__ matches, const uint8_t* __restrict__ cands,
-                uint8_t* __restrict__ cons_buf, HbVoteCall* __restrict__ calls) {
-    __shared__ int s_vc[WARPS_PER_CTA][128];
-    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
-    __shared__ int s_cnt[WARPS_PER_CTA][2];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
-    if (ti >= n_tasks) return;
-    const HbVoteTask t = tasks[ti];
-    HbVoteCall call = calls[ti];          // clean_cols written by kernel A
+// Shared front of judge_boundary_v5 (Util.py:9151-9308) and judge_boundary_v9 (Util.py:9490-9597):
+// anchors from the first row where both 20-mers hit, full-length member filter, bit-planes,
+// outermost valid columns, search_boundary_homo_v3 for both ends.  Returns true when the caller
+// should go on to the consensus; otherwise `call` already holds the verdict.
+struct Front {
+    Planes P;
+    int row_num, hs, he, vl, vr, Cc;
+};
+__device__ bool judge_front_v3(const HbVoteTask& t, HbVoteCall& call, const uint8_t* __restrict__ m,
+                               uint32_t* __restrict__ planes, Match* __restrict__ matches,
+                               const uint8_t* __restrict__ cands, double thr_many, int fl1_copy_num_is_rows,
+                               int* vc, unsigned short* rows, int* cnt, int lane, Front& F) {
     const int R = t.R, C = t.C, Cc = call.clean_cols;
-    const uint8_t* m = clean + t.clean_off;
+    F.Cc = Cc;
     call.is_te = 0; call.info = 0; call.copy_num = 0; call.align_start = -1; call.align_end = -1;
     call.homo_start = -1; call.homo_end = -1; call.cons_len = 0; call.trim_lead = 0; call.trim_trail = 0;
     call.flags = 0; call.cons_off = (int64_t)t.cons_off;
-    int* vc = s_vc[wid];
-    unsigned short* rows = s_rows[wid];
-
     // ---- 1. anchors (:9151-9181) ----------------------------------------------------------
     int as = -1, ae = -1;
     if (t.cand_len > 2 && Cc > 0) {
@@ -678,83 +674,26 @@ hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t
         pattern_init(P1, cand, alen);
         pattern_init(P2, cand + (t.cand_len - alen), alen);
         Match* ml = matches + t.match_off;
-        const int cap = C + 2;
-        for (int r = 0; r < R; ++r) {
-            const uint8_t* row = m + (size_t)r * C;
-            int ub, n;
-            anchor_scan_row(row, Cc, P1, P2, ml, cap, s_cnt[wid], lane, &ub, &n);
-            const int n1 = min(cap, s_cnt[wid][0]), n2 = min(cap, s_cnt[wid][1]);
-            __syncwarp();
-            if (n1 > 0 && n2 > 0) {
-                const int fs = first_group_best_start(ml, n1, lane);
-                const int le = last_group_best_end(ml + cap, n2, lane);
-                as = column_of_ungapped(row, Cc, fs, ub, lane);
-                ae = column_of_ungapped(row, Cc, le - 1, ub, lane);
-                break;
-            }
-        }
+        for (int r = 0; r < R; ++r)
+            if (row_anchor(m + (size_t)r * C, Cc, C + 2, P1, P2, ml, cnt, lane, &as, &ae)) break;
     }
     call.align_start = as; call.align_end = ae;
-    if (as < 0 || ae < 0) {                                                    // :9184-9187
-        call.info = 1;
-        if (lane == 0) calls[ti] = call;
-        return;
-    }
+    if (as < 0 || ae < 0) { call.info = 1; return false; }                     // :9184-9187
     // ---- 2. full-length member filter (:9196-9217) -----------------------------------------
-    int row_num = 0;
-    {
-        const int s_lo = max(0, as - 10), s_hi = min(Cc, as + 10);
-        int e_lo, e_hi;
-        py_slice(Cc, (long long)ae - 10, (ae + 10 < Cc) ? ae + 10 : Cc, &e_lo, &e_hi);
-        for (int r0 = 0; r0 < R && row_num < MAX_KEPT; r0 += 32) {
-            const int r = r0 + lane;
-            bool ok = false;
-            if (r < R) {
-                const uint8_t* row = m + (size_t)r * C;
-                bool a1 = false, a2 = false;
-                for (int c = s_lo; c < s_hi; ++c) a1 |= (row[c] != HB_SYM_GAP);
-                for (int c = e_lo; c < e_hi; ++c) a2 |= (row[c] != HB_SYM_GAP);
-                ok = a1 && a2;
-            }
-            const uint32_t bal = __ballot_sync(HB_FULL, ok);
-            const int pos = row_num + __popc(bal & lanemask_lt(lane));
-            if (ok && pos < MAX_KEPT) rows[pos] = (unsigned short)r;
-            row_num = min(MAX_KEPT, row_num + __popc(bal));
-        }
-        __syncwarp();
-    }
-    if (row_num <= 1) {                                                        // :9222-9225
-        call.info = 2; call.copy_num = 1;
-        if (lane == 0) calls[ti] = call;
-        return;
+    int e_lo, e_hi;
+    py_slice(Cc, (long long)ae - 10, (ae + 10 < Cc) ? ae + 10 : Cc, &e_lo, &e_hi);
+    const int row_num = select_rows(m, R, C, max(0, as - 10), min(Cc, as + 10), e_lo, e_hi, rows, lane);
+    F.row_num = row_num;
+    if (row_num <= 1) {                                                        // :9222-9225 / :9561-9564
+        call.info = 2; call.copy_num = fl1_copy_num_is_rows ? row_num : 1;
+        return false;
     }
     call.copy_num = row_num;
     // ---- 3. bit-planes of the kept rows -----------------------------------------------------
-    Planes P;
-    uint32_t* pw = planes + t.plane_off;
-    P.p = pw; P.stride = C; P.nw = (row_num + 31) >> 5; P.row_num = row_num;
-    for (int wd = 0; wd < 4; ++wd) {
-        int rem = row_num - wd * 32;
-        P.rowmask[wd] = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
-    }
-    for (int col = lane; col < Cc; col += 32) {
-        for (int wd = 0; wd < P.nw; ++wd) {
-            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-            const int kend = min(32, row_num - wd * 32);
-            for (int kk = 0; kk < kend; ++kk) {
-                const int s = m[(size_t)rows[wd * 32 + kk] * C + col];
-                const uint32_t bit = 1u << kk;
-                a0 |= (s == 0) ? bit : 0u; a1 |= (s == 1) ? bit : 0u; a2 |= (s == 2) ? bit : 0u;
-                a3 |= (s == 3) ? bit : 0u; a4 |= (s == 4) ? bit : 0u; a5 |= (s == 5) ? bit : 0u;
-            }
-            pw[(size_t)(0 * 4 + wd) * C + col] = a0; pw[(size_t)(1 * 4 + wd) * C + col] = a1;
-            pw[(size_t)(2 * 4 + wd) * C + col] = a2; pw[(size_t)(3 * 4 + wd) * C + col] = a3;
-            pw[(size_t)(4 * 4 + wd) * C + col] = a4; pw[(size_t)(5 * 4 + wd) * C + col] = a5;
-        }
-    }
-    __syncwarp();
+    build_planes(F.P, planes + t.plane_off, m, C, Cc, rows, row_num, lane);
+    const Planes& P = F.P;
     const int vthr = row_num / 2;                                              // int(row_num/2) :9238
-    const double thr = row_num <= 2 ? 0.95 : (row_num <= 5 ? 0.9 : 0.7);       // :9240-9245
+    const double thr = row_num <= 2 ? 0.95 : (row_num <= 5 ? 0.9 : thr_many);  // :9240-9245 / :9579-9584
     // ---- 4. outermost valid columns (:9269-9294) --------------------------------------------
     int vl = -1, vr = -1;
     for (int c0 = 0; c0 < Cc; c0 += 32) {
@@ -770,21 +709,26 @@ hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t
         }
     }
     if (!(vl != -1 && vr != -1 && vl < vr)) { vl = -1; vr = -1; }
+    F.vl = vl; F.vr = vr;
     // ---- 5. homology boundaries (:9297-9308) -------------------------------------------------
-    const int hs = search_boundary_v3(P, vthr, as, Cc, true, thr, 20, 10, vc, lane);
-    call.homo_start = hs;
-    if (hs == -1) { if (lane == 0) calls[ti] = call; return; }
-    const int he = search_boundary_v3(P, vthr, ae, Cc, false, thr, 20, 10, vc, lane);
-    call.homo_end = he;
-    if (he == -1) { if (lane == 0) calls[ti] = call; return; }
-    // ---- 6. consensus (:9312-9346) -----------------------------------------------------------
-    uint8_t* cons = cons_buf + t.cons_off;
+    F.hs = search_boundary_v3(P, vthr, as, Cc, true, thr, 20, 10, vc, lane);
+    call.homo_start = F.hs;
+    if (F.hs == -1) return false;
+    F.he = search_boundary_v3(P, vthr, ae, Cc, false, thr, 20, 10, vc, lane);
+    call.homo_end = F.he;
+    if (F.he == -1) return false;
+    return true;
+}
+
+// column-vote consensus of columns [hs, he] written to cons (Util.py:9312-9346); returns its length
+__device__ int vote_consensus(const Planes& P, const uint8_t* __restrict__ m, int C, const unsigned short* rows,
+                              int hs, int he, int result_type, uint8_t* __restrict__ cons, int lane) {
     int ml = 0;
     for (int c0 = hs; c0 <= he; c0 += 32) {
         const int c = c0 + lane;
         int s = -1;
         if (c <= he) {
-            if (t.result_type == 1) s = vote_column(P, c, row_num / 2);
+            if (result_type == 1) s = vote_column(P, c, P.row_num / 2);
             else { int x = m[(size_t)rows[0] * C + c]; s = (x != HB_SYM_GAP) ? x : -1; }
         }
         const uint32_t bal = __ballot_sync(HB_FULL, s >= 0);
@@ -792,6 +736,37 @@ hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t
         ml += __popc(bal);
     }
     __syncwarp();
+    return ml;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel B: judge_boundary_v5 (TIR, Util.py:9145-9480), one warp per candidate.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                uint32_t* __restrict__ planes, Match* __restrict__ matches, const uint8_t* __restrict__ cands,
+                uint8_t* __restrict__ cons_buf, HbVoteCall* __restrict__ calls) {
+    __shared__ int s_vc[WARPS_PER_CTA][128];
+    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    __shared__ int s_cnt[WARPS_PER_CTA][2];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    HbVoteCall call = calls[ti];          // clean_cols written by kernel A
+    const int R = t.R, C = t.C;
+    const uint8_t* m = clean + t.clean_off;
+    unsigned short* rows = s_rows[wid];
+    Front F;
+    if (!judge_front_v3(t, call, m, planes, matches, cands, 0.7, 0, s_vc[wid], rows, s_cnt[wid], lane, F)) {
+        if (lane == 0) calls[ti] = call;
+        return;
+    }
+    const Planes& P = F.P;
+    const int Cc = F.Cc, row_num = F.row_num, hs = F.hs, he = F.he, vl = F.vl, vr = F.vr;
+    (void)row_num;
+    // ---- 6. consensus (:9312-9346) -----------------------------------------------------------
+    uint8_t* cons = cons_buf + t.cons_off;
+    const int ml = vote_consensus(P, m, C, rows, hs, he, t.result_type, cons, lane);
     // ---- 7. reject rule + TIR terminal trimming supported by TSDs (:9353-9413) ---------------
     int final_lo = 0, final_hi = 0;
     if (!(hs <= vl || he >= vr) && t.te_type == 0) {
@@ -1047,6 +1022,157 @@ hb_judge_v6_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint
     if (lane == 0) calls[ti] = call;
 }
 
+// ------------------------------------------------------------------------------------------
+// non-LTR helpers (Util.py:9604-9664, find_tail_polyA :10832, find_longest_tandem_repeat_tail :9732)
+
+// fuzzysearch.find_near_matches(TSD, kmer, max_l_dist=1) non-empty for |TSD| == |kmer| == k:
+// Hamming <= 1, or TSD minus one symbol equals kmer[1:] / kmer[:-1]
+__device__ bool near1(const uint8_t* ring, int tsd0, const uint8_t* sub, int k0, int k) {
+    int mm = 0;
+    for (int t = 0; t < k; ++t) mm += (ring[(tsd0 + t) & 63] != sub[k0 + t]);
+    if (mm <= 1) return true;
+    for (int which = 0; which < 2; ++which) {
+        const int s0 = k0 + (which == 0 ? 1 : 0);
+        int a = 0;
+        while (a < k - 1 && ring[(tsd0 + a) & 63] == sub[s0 + a]) ++a;
+        bool ok = true;
+        for (int t = a; t < k - 1; ++t) if (ring[(tsd0 + t + 1) & 63] != sub[s0 + t]) { ok = false; break; }
+        if (ok) return true;
+    }
+    return false;
+}
+
+// one row of the per-copy 3'-end / TSD search.  hs0/he: homology boundary columns.
+// returns found; *end5 (new 5' end) and *end3 in ungapped coordinates of the row
+__device__ bool nonltr_row(const uint8_t* __restrict__ row, int Cc, int hs0, int he, int* end5_out, int* end3_out) {
+    uint8_t ring[64];      // last 64 non-gap symbols, index = ungapped position & 63
+    uint8_t sub[50];       // the <= 50 symbols before column hs0 (align_seq[left_pos:end_5]), oldest first
+    int n = 0, end_5 = -1, h3 = -1, sl = 0;
+    int run = 0, pa_end = -1;
+    bool done = false;
+    for (int c = 0; c < Cc && !done; ++c) {
+        if (c == hs0) {
+            end_5 = n;
+            sl = min(50, n);
+            for (int t = 0; t < sl; ++t) sub[t] = ring[(n - sl + t) & 63];
+        }
+        if (c == he) h3 = n;
+        const uint8_t s = row[c];
+        if (s == HB_SYM_GAP) continue;
+        ring[n & 63] = s;
+        ++n;
+        // cur_seq = align_seq[0 : h3 + 10]: A-runs only count while inside it
+        if (h3 < 0 || n <= h3 + 10) {
+            run = (s == 0) ? run + 1 : 0;
+            if (run >= 6) pa_end = n;
+        }
+        if (h3 >= 0 && n >= h3 + 30) done = true;
+    }
+    if (h3 < 0) h3 = n;            // he beyond the last column never happens (he < Cc); keeps the maths defined
+    if (end_5 < 0) end_5 = n;
+    const int cl = min(n, h3 + 10);
+    int end_3 = pa_end;                                                    // find_tail_polyA
+    if (end_3 < 0) {                                                       // find_longest_tandem_repeat_tail
+        const int tl = min(30, cl), t0 = cl - tl;
+        int max_len = 0;
+        for (int ul = 2; ul <= 6; ++ul) {
+            for (int start = tl - ul * 4; start >= 0; --start) {
+                int count = 1;
+                for (int i = 1; i < (tl - start) / ul; ++i) {
+                    bool eq = true;
+                    for (int z = 0; z < ul; ++z) eq &= (ring[(t0 + start + i * ul + z) & 63] == ring[(t0 + start + z) & 63]);
+                    if (!eq) break;
+                    ++count;
+                }
+                if (count >= 4 && ul * count > max_len) { max_len = ul * count; end_3 = t0 + start + ul * count; }
+            }
+        }
+    }
+    *end3_out = end_3;
+    *end5_out = end_5;
+    if (abs(end_3 - h3) > 10) return false;                                // :9632
+    if (end_3 == -1 || end_5 == -1) return false;
+    const int left_pos = max(0, end_5 - 50);
+    for (int k = 20; k >= 8; --k) {
+        if (min(k, max(0, n - end_3)) != k) {
+            // the scan stops 30 symbols past h3, so n >= end_3 + 20 unless the row really ends here
+            continue;
+        }
+        for (int i = 0; i + k <= sl; ++i) {
+            if (near1(ring, end_3, sub, i, k)) { *end5_out = left_pos + i + k; return true; }
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel B'': judge_boundary_v9 (non-LTR, Util.py:9483-9720), one warp per candidate.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_v9_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                   uint32_t* __restrict__ planes, Match* __restrict__ matches, const uint8_t* __restrict__ cands,
+                   uint8_t* __restrict__ cons_buf, HbVoteCall* __restrict__ calls) {
+    __shared__ int s_vc[WARPS_PER_CTA][128];
+    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    __shared__ int s_cnt[WARPS_PER_CTA][2];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    HbVoteCall call = calls[ti];
+    const int R = t.R, C = t.C;
+    const uint8_t* m = clean + t.clean_off;
+    unsigned short* rows = s_rows[wid];
+    Front F;
+    if (!judge_front_v3(t, call, m, planes, matches, cands, 0.8, 1, s_vc[wid], rows, s_cnt[wid], lane, F)) {
+        if (lane == 0) calls[ti] = call;
+        return;
+    }
+    const int Cc = F.Cc, row_num = F.row_num, he = F.he;
+    int hs = F.hs;
+    // ---- per-copy 3' end + TSD (:9604-9664), all R rows, one row per lane -----------------------
+    int tsd_count = 0;
+    int first_nonempty = 0x7fffffff, last_found = -1;    // row indices
+    for (int r0 = 0; r0 < R; r0 += 32) {
+        const int r = r0 + lane;
+        bool found = false, nonempty = false;
+        if (r < R) {
+            int e5, e3;
+            found = nonltr_row(m + (size_t)r * C, Cc, F.hs, he, &e5, &e3);
+            nonempty = found && (max(e5, e3) > min(e5, e3));
+        }
+        const uint32_t bf = __ballot_sync(HB_FULL, found), bn = __ballot_sync(HB_FULL, nonempty);
+        tsd_count += __popc(bf);
+        if (bf) last_found = r0 + (31 - __clz(bf));
+        if (bn && first_nonempty == 0x7fffffff) first_nonempty = r0 + __ffs(bn) - 1;
+    }
+    // homo_boundary_start follows every TSD-bearing row until the first with a non-empty element (:9660-9664)
+    const int src_row = (first_nonempty != 0x7fffffff) ? first_nonempty : last_found;
+    if (src_row >= 0) {
+        const uint8_t* row = m + (size_t)src_row * C;
+        int e5 = 0, e3 = 0;
+        if (lane == 0) nonltr_row(row, Cc, F.hs, he, &e5, &e3);
+        e5 = __shfl_sync(HB_FULL, e5, 0); e3 = __shfl_sync(HB_FULL, e3, 0);
+        const int fbs = min(e5, e3);
+        // column of ungapped index fbs
+        const int chunk = (Cc + 31) >> 5;
+        const int lo = min(Cc, lane * chunk), hi = min(Cc, lo + chunk);
+        int c_ng = 0;
+        for (int c = lo; c < hi; ++c) c_ng += (row[c] != HB_SYM_GAP);
+        int ntot;
+        const int ub = warp_excl_scan(c_ng, lane, &ntot);
+        if (fbs >= 0 && fbs < ntot) hs = column_of_ungapped(row, Cc, fbs, ub, lane);
+    }
+    call.homo_start = hs;
+    call.trim_lead = tsd_count;
+    int ml = 0;
+    uint8_t* cons = cons_buf + t.cons_off;
+    if (tsd_count >= 5 || 2 * tsd_count > row_num)                               // :9668
+        ml = vote_consensus(F.P, m, C, rows, hs, he, 1, cons, lane);
+    call.cons_len = ml;
+    call.is_te = !(ml == 0 || ml < 80);                                          // :9713-9716
+    if (lane == 0) calls[ti] = call;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1065,6 +1191,9 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
     else if (te_type == 1)
         hb_judge_v6_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
                                                                     d_anchors, d_cands, d_cons, d_calls);
+    else if (te_type == 2)
+        hb_judge_v9_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
+                                                                    d_cands, d_cons, d_calls);
     else
         return cudaErrorInvalidValue;
     return cudaGetLastError();

@@ -36,6 +36,8 @@ int hbo_search_boundary_homo_v4(int vthr, int pos, const char *const *rows, int 
                                 const void *colmaps, int *boundary);
 int hbo_judge_v6(const char *cand, int cand_len, const char *m, int R, int C, hbo_call *out, char *cons);
 
+int hbo_judge_v9(const char *cand, int cand_len, const char *m, int R, int C, hbo_call *out, char *cons);
+
 /* ---- HB-align restatement (hbo_align.c) ---- */
 #include <stdint.h>
 typedef struct hbo_genome hbo_genome;

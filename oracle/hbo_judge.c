@@ -740,3 +740,145 @@ int hbo_judge_v6(const char *cand, int cand_len, const char *m, int R, int C, hb
     free(model); free(cm); free(srows); free(erows);
     return 0;
 }
+
+/* ========================================================================================== */
+/* non-LTR: judge_boundary_v9 (Util.py:9483-9720), find_tail_polyA (:10832),                    */
+/* find_longest_tandem_repeat_tail (:9732-9770)                                                 */
+
+static int tail_polyA_end(const char *s, int n) {                 /* find_tail_polyA, min_length 6 */
+    for (int i = n - 5 - 1 + 0; i >= 0; --i) {                    /* range(len-(6-1), -1, -1): i = n-5 .. 0 */
+        (void)0;
+    }
+    for (int i = n - 5; i >= 0; --i) {
+        if (i + 6 <= n && memcmp(s + i, "AAAAAA", 6) == 0) return i + 6;
+    }
+    return -1;
+}
+
+static int tandem_tail_end(const char *seq, int n) {              /* find_longest_tandem_repeat_tail */
+    const int tail_length = 30, min_repeats = 4;
+    const char *tail = n >= tail_length ? seq + (n - tail_length) : seq;
+    int tl = n >= tail_length ? tail_length : n;
+    int longest_end = -1, max_len = 0;
+    for (int ul = 2; ul <= 6; ++ul) {
+        for (int start = tl - ul * min_repeats; start >= 0; --start) {
+            int count = 1;
+            for (int i = 1; i < (tl - start) / ul; ++i) {
+                if (memcmp(tail + start + i * ul, tail + start, (size_t)ul) != 0) break;
+                ++count;
+            }
+            if (count >= min_repeats) {
+                int total = ul * count;
+                if (total > max_len) { max_len = total; longest_end = n - tl + start + total; }
+            }
+        }
+    }
+    return longest_end;
+}
+
+/* fuzzysearch.find_near_matches(TSD, kmer, max_l_dist=1) non-empty, |TSD| == |kmer| == k (Util.py:9650) */
+static int near1(const char *tsd, const char *kmer, int k) {
+    int mm = 0;
+    for (int t = 0; t < k; ++t) mm += (tsd[t] != kmer[t]);
+    if (mm <= 1) return 1;
+    /* one deletion from TSD equals kmer[1:] or kmer[:-1] */
+    for (int which = 0; which < 2; ++which) {
+        const char *s = kmer + (which == 0 ? 1 : 0);          /* length k-1 */
+        int a = 0;
+        while (a < k - 1 && tsd[a] == s[a]) ++a;
+        int ok = 1;
+        for (int t = a; t < k - 1; ++t) if (tsd[t + 1] != s[t]) { ok = 0; break; }
+        if (ok) return 1;
+    }
+    return 0;
+}
+
+int hbo_judge_v9(const char *cand, int cand_len, const char *m, int R, int C, hbo_call *out, char *cons) {
+    memset(out, 0, sizeof(*out));
+    out->homo_start = out->homo_end = -1;
+    cons[0] = 0;
+    int as, ae;
+    if (!hbo_find_anchor(cand, cand_len, m, R, C, &as, &ae)) {                  /* :9522-9525 */
+        out->info = HBO_INFO_NB; out->align_start = as; out->align_end = ae;
+        return 0;
+    }
+    out->align_start = as; out->align_end = ae;
+    const char **rows = (const char **)malloc(sizeof(char *) * (size_t)(R + 1));
+    int nr = 0;
+    for (int r = 0; r < R; ++r) {                                                /* :9535-9556 */
+        if (nr > 100) break;
+        const char *row = m + (size_t)r * C;
+        int lo, hi, any1 = 0, any2 = 0;
+        py_slice(C, as - 10 >= 0 ? as - 10 : 0, (long)as + 10, &lo, &hi);
+        for (int c = lo; c < hi; ++c) if (row[c] != '-') { any1 = 1; break; }
+        py_slice(C, (long)ae - 10, ae + 10 < C ? ae + 10 : C, &lo, &hi);
+        for (int c = lo; c < hi; ++c) if (row[c] != '-') { any2 = 1; break; }
+        if (any1 && any2) rows[nr++] = row;
+    }
+    int row_num = nr;
+    if (row_num <= 1) { out->info = HBO_INFO_FL1; out->copy_num = row_num; free(rows); return 0; }   /* :9561-9564 */
+    double thr = row_num <= 2 ? 0.95 : (row_num <= 5 ? 0.9 : 0.8);              /* :9579-9584 */
+    colmap *cm = (colmap *)malloc(sizeof(colmap) * (size_t)C);
+    build_colmap(rows, row_num, C, cm);
+    out->copy_num = row_num;
+    int hs = hbo_search_boundary_homo_v3(row_num / 2, as, rows, row_num, C, 1, thr, 20, 10, cm);
+    out->homo_start = hs;
+    if (hs == -1) { free(cm); free(rows); return 0; }
+    int he = hbo_search_boundary_homo_v3(row_num / 2, ae, rows, row_num, C, 0, thr, 20, 10, cm);
+    out->homo_end = he;
+    if (he == -1) { free(cm); free(rows); return 0; }
+    /* per-row polyA / tandem 3' end + TSD search over ALL rows :9604-9664 */
+    int tsd_count = 0, have_first = 0;
+    const int cur_boundary_start = hs;
+    char *u = (char *)malloc((size_t)C + 1);
+    int *n2g = (int *)malloc(sizeof(int) * (size_t)(C + 1));
+    for (int r = 0; r < R; ++r) {
+        const char *row = m + (size_t)r * C;
+        int n = 0, end_5 = 0, h3 = 0;
+        for (int c = 0; c < C; ++c) {
+            if (c == cur_boundary_start) end_5 = n;
+            if (c == he) h3 = n;
+            if (row[c] != '-') { u[n] = row[c]; n2g[n] = c; ++n; }
+        }
+        int cl = h3 + 10; if (cl > n) cl = n;                                     /* cur_seq = align_seq[0:h3+10] */
+        int end_3 = tail_polyA_end(u, cl);
+        if (end_3 == -1) end_3 = tandem_tail_end(u, cl);
+        int diff = end_3 - h3; if (diff < 0) diff = -diff;
+        if (diff > 10) continue;                                                  /* :9632 */
+        int found = 0;
+        if (end_3 != -1 && end_5 != -1) {
+            int left_pos = end_5 - 50; if (left_pos < 0) left_pos = 0;
+            int sl = end_5 - left_pos;                                            /* len(subsequence) */
+            for (int k = 20; k >= 8 && !found; --k) {
+                int tl = n - end_3; if (tl > k) tl = k; if (tl < 0) tl = 0;      /* len(align_seq[end_3:end_3+k]) */
+                if (tl != k) continue;
+                for (int i = 0; i + k <= sl; ++i) {
+                    if (near1(u + end_3, u + left_pos + i, k)) { end_5 = left_pos + i + k; found = 1; break; }
+                }
+            }
+        }
+        if (found) {
+            ++tsd_count;
+            if (!have_first) {
+                int fbs = end_5 < end_3 ? end_5 : end_3, fbe = end_5 < end_3 ? end_3 : end_5;
+                if (fbe > fbs) have_first = 1;                                    /* first_non_ltr_seq != '' */
+                if (fbs < n) hs = n2g[fbs];                                       /* :9664 (KeyError if fbs == n) */
+            }
+        }
+    }
+    free(u); free(n2g);
+    out->homo_start = hs;
+    out->trim_lead = tsd_count;
+    int ml = 0;
+    if (tsd_count >= 5 || 2 * tsd_count > row_num) {                              /* :9668 */
+        for (int c = hs; c <= he; ++c) {
+            int s = vote_col(&cm[c], row_num / 2);
+            if (s >= 0) cons[ml++] = SYM_CHR[s];
+        }
+    }
+    cons[ml] = 0;
+    out->cons_len = ml;
+    out->is_te = !(ml == 0 || ml < 80);                                           /* :9713-9716 */
+    free(cm); free(rows);
+    return 0;
+}

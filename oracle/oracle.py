@@ -75,6 +75,19 @@ def judge_v6(cand, rows):
                 homo_start=call.homo_start, homo_end=call.homo_end)
 
 
+def judge_v9(cand, rows):
+    """-> dict mirroring judge_boundary_v9's (is_TE, info, cons_seq, copy_num) (non-LTR); ``cons`` is the
+    model sequence the reference returns even when is_TE is False."""
+    m, R, Cn = _mat(rows)
+    call = HboCall()
+    cons = C.create_string_buffer(Cn + 8)
+    cb = cand.encode()
+    lib().hbo_judge_v9(cb, len(cb), m, R, Cn, C.byref(call), cons)
+    return dict(is_te=bool(call.is_te), info=INFO[call.info], cons=cons.value.decode(),
+                copy_num=call.copy_num, align_start=call.align_start, align_end=call.align_end,
+                homo_start=call.homo_start, homo_end=call.homo_end, tsd_count=call.trim_lead)
+
+
 def find_near_matches_ends(p, s, d):
     fs, fe, ls, le = C.c_int(-1), C.c_int(-1), C.c_int(-1), C.c_int(-1)
     n = lib().hbo_find_near_matches(p.encode(), len(p), s.encode(), len(s), d,

@@ -34,3 +34,11 @@ def golden_v6():
     import json
     with gzip.open(os.path.join(ROOT, "tests", "golden", "judge_v6.json.gz")) as f:
         return json.loads(f.read())
+
+
+@pytest.fixture(scope="session")
+def golden_v9():
+    import gzip
+    import json
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "judge_v9.json.gz")) as f:
+        return json.loads(f.read())

@@ -72,6 +72,18 @@ def run_reference_v6(U, case, tmpdir):
                 v4=[[bool(a), int(b)] for a, b in trace])
 
 
+def run_reference_v9(U, case, tmpdir):
+    """remove_sparse_col_in_align_file (Util.py:10344) + judge_boundary_v9 (Util.py:9483)."""
+    path = os.path.join(tmpdir, "n.maf.fa")
+    with open(path, "w") as f:
+        for i, row in enumerate(case["rows"]):
+            f.write(">r%d\n%s\n" % (i, row))
+    clean = U.remove_sparse_col_in_align_file(path)
+    names, contigs = U.read_fasta(clean)
+    is_te, info, cons, copy_num = U.judge_boundary_v9(case["cand"], clean, 0, "non_ltr", case["plant"], "cons")
+    return dict(clean_rows=[contigs[n] for n in names], is_te=bool(is_te), info=info, cons=cons, copy_num=copy_num)
+
+
 def write(path, out):
     with gzip.GzipFile(path, "wb", mtime=0) as f:
         f.write(json.dumps(out, separators=(",", ":")).encode())
@@ -90,6 +102,13 @@ def main():
             out.append(dict(seed=seed, scenario=case["scenario"], cand=case["cand"], plant=case["plant"],
                             rows=case["rows"], truth=case["truth"], expect=exp))
         write(os.path.join(ROOT, "tests", "golden", "judge_v6.json.gz"), out)
+        out = []
+        for seed in range(1, 121):
+            case = msa_synth.synth_case_nonltr(seed)
+            exp = run_reference_v9(U, case, td)
+            out.append(dict(seed=seed, scenario=case["scenario"], cand=case["cand"], plant=case["plant"],
+                            rows=case["rows"], truth=case["truth"], expect=exp))
+        write(os.path.join(ROOT, "tests", "golden", "judge_v9.json.gz"), out)
     out = []
     with tempfile.TemporaryDirectory() as td:
         seeds = list(range(1, 161))

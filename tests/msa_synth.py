@@ -178,3 +178,59 @@ def synth_case_helitron(seed, scenario=None):
     elif scen == "no_anchor":
         cand = rand_seq(rng, length)
     return dict(cand=cand, rows=rows, plant=1, te_type="helitron", scenario=scen, truth=elem)
+
+
+def synth_case_nonltr(seed, scenario=None):
+    """non-LTR-shaped cases for judge_boundary_v9 (reference Util.py:9483): element with a polyA (or
+    short tandem) 3' tail, flanked by 8-20 bp target-site duplications; some copies 5'-truncated."""
+    rng = random.Random(seed)
+    scen = scenario or rng.choice(["clean", "clean", "clean", "tandem_tail", "trunc5", "no_tsd", "few_rows",
+                                   "no_anchor", "fp_homolog_flank", "shift_out", "short"])
+    flank = 50
+    nrows = rng.randint(4, 30)
+    if scen == "few_rows":
+        nrows = rng.randint(1, 6)
+    length = rng.randint(120, 400) if scen != "short" else rng.randint(60, 95)
+    sub = rng.choice([0.0, 0.02, 0.05])
+    dele = rng.choice([0.0, 0.005, 0.01])
+    if scen == "tandem_tail":
+        unit = rand_seq(rng, rng.randint(2, 5))
+        tail = unit * rng.randint(4, 7)
+    else:
+        tail = "A" * rng.randint(7, 20)
+    body = rand_seq(rng, length - len(tail))
+    elem = body + tail
+    shared_l, shared_r = rand_seq(rng, flank), rand_seq(rng, flank)
+    rows = []
+    for r in range(nrows):
+        k = rng.randint(8, 18)
+        tsd = rand_seq(rng, k)
+        tsd_r = tsd if scen != "no_tsd" else rand_seq(rng, k)
+        if scen != "no_tsd" and rng.random() < 0.25:
+            p = rng.randrange(k)
+            tsd_r = tsd[:p] + rng.choice([x for x in BASES if x != tsd[p]]) + tsd[p + 1:]
+        lf = rand_seq(rng, flank - k) + tsd
+        rf = tsd_r + rand_seq(rng, flank - k)
+        if scen == "fp_homolog_flank":
+            lf = mutate_row(rng, shared_l, 0.03, 0.0).replace("-", "A")
+            rf = mutate_row(rng, shared_r, 0.03, 0.0).replace("-", "A")
+        # keep the tail intact (polyA detection is exact), mutate the body
+        b = mutate_row(rng, body, sub, dele) + tail
+        if scen == "trunc5" and r > 0 and rng.random() < 0.5:
+            cut = rng.randint(10, len(body) // 2)
+            b = "-" * cut + b[cut:]
+            lf = "-" * (flank - k) + tsd if rng.random() < 0.5 else "-" * flank
+        rows.append(lf + b + rf)
+    for _ in range(rng.randint(0, 4)):
+        p = rng.randint(1, len(rows[0]) - 1)
+        who = set(rng.sample(range(nrows), k=min(nrows, rng.choice([1, 1, 2, nrows // 2 + 1]))))
+        rows = [row[:p] + (rng.choice(BASES) if i in who else "-") + row[p:] for i, row in enumerate(rows)]
+    cand = elem
+    if scen == "shift_out":
+        r0 = rows[0].replace("-", "")
+        core_start = len(rows[0][:flank].replace("-", ""))
+        core_end = len(r0) - len(rows[0][-flank:].replace("-", ""))
+        cand = r0[max(0, core_start - rng.randint(0, 10)):core_end + rng.randint(0, 8)]
+    elif scen == "no_anchor":
+        cand = rand_seq(rng, length)
+    return dict(cand=cand, rows=rows, plant=1, te_type="non_ltr", scenario=scen, truth=elem)

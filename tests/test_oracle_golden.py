@@ -74,3 +74,14 @@ def test_oracle_judge_v6_matches_reference_goldens(golden_v6):
         r = oracle.judge_v6(rec["cand"], clean)
         for k in ("is_te", "info", "cons", "copy_num"):
             assert r[k] == exp[k], (rec["seed"], rec["scenario"], k)
+
+
+def test_oracle_judge_v9_matches_reference_goldens(golden_v9):
+    assert len(golden_v9) >= 100
+    for rec in golden_v9:
+        exp = rec["expect"]
+        clean = oracle.remove_sparse_cols(rec["rows"])
+        assert clean == exp["clean_rows"], rec["seed"]
+        r = oracle.judge_v9(rec["cand"], clean)
+        for k in ("is_te", "info", "cons", "copy_num"):
+            assert r[k] == exp[k], (rec["seed"], rec["scenario"], k)

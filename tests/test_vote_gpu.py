@@ -79,3 +79,20 @@ def test_helitron_vote_matches_oracle_on_fresh_seeds(ctx):
         assert (r["align_start"], r["align_end"]) == (exp["align_start"], exp["align_end"]), c["scenario"]
         for k in KEYS + ("homo_start", "homo_end"):
             assert r[k] == exp[k], (c["scenario"], k, r[k], exp[k])
+
+
+def test_nonltr_vote_matches_reference_goldens(ctx, golden_v9):
+    res = ctx.vote_matrices([r["cand"] for r in golden_v9], [r["rows"] for r in golden_v9], "non_ltr", 1)
+    for r, rec in zip(res, golden_v9):
+        exp = rec["expect"]
+        for k in KEYS:
+            assert r[k] == exp[k], (rec["seed"], rec["scenario"], k, r[k], exp[k])
+
+
+def test_nonltr_vote_matches_oracle_on_fresh_seeds(ctx):
+    cases = [msa_synth.synth_case_nonltr(s) for s in range(9000, 9500)]
+    res = ctx.vote_matrices([c["cand"] for c in cases], [c["rows"] for c in cases], "non_ltr", 1)
+    for r, c in zip(res, cases):
+        exp = oracle.judge_v9(c["cand"], oracle.remove_sparse_cols(c["rows"]))
+        for k in KEYS + ("homo_start", "homo_end", "align_start", "align_end"):
+            assert r[k] == exp[k], (c["scenario"], k, r[k], exp[k])
