@@ -33,14 +33,14 @@ assert CALL_DTYPE.itemsize == C.sizeof(HbCall)
 
 class HbParams(C.Structure):
     _fields_ = [("occ_cap", C.c_int32), ("max_loci", C.c_int32), ("flank", C.c_int32), ("max_rows", C.c_int32),
-                ("te_type", C.c_int32), ("plant", C.c_int32), ("result_type", C.c_int32), ("pad", C.c_int32),
+                ("te_type", C.c_int32), ("plant", C.c_int32), ("result_type", C.c_int32), ("trunc_gate", C.c_int32),
                 ("tb_budget_bytes", C.c_uint64)]
 
 
 COPY_DTYPE = np.dtype([("cand", "<u4"), ("rank", "<i4"), ("rel", "<i4"), ("nseeds", "<i4"), ("score", "<i4"),
                        ("i_s", "<i4"), ("i_e", "<i4"), ("keep", "<i4"), ("row", "<i4"), ("contig", "<i4"),
                        ("j0", "<i8"), ("j_s", "<i8"), ("j_e", "<i8"), ("start1", "<i8"), ("end1", "<i8"),
-                       ("ext_len", "<i4"), ("pad", "<i4")])
+                       ("ext_len", "<i4"), ("trow", "<i4")])
 assert COPY_DTYPE.itemsize == 88
 
 
@@ -102,7 +102,7 @@ def _calls_to_dicts(calls, cons_b):
         out.append(dict(is_te=bool(cols["is_te"][i]), info=INFO[cols["info"][i]], cons=text[o:o + cols["cons_len"][i]],
                         copy_num=cols["copy_num"][i], align_start=cols["align_start"][i], align_end=cols["align_end"][i],
                         homo_start=cols["homo_start"][i], homo_end=cols["homo_end"][i], clean_cols=cols["clean_cols"][i],
-                        no_copies=bool(cols["flags"][i] & 1)))
+                        no_copies=bool(cols["flags"][i] & 1), trunc_reject=bool(cols["flags"][i] & 2)))
     return out
 
 
@@ -207,7 +207,7 @@ class Context:
         return keys[:n]
 
     def adjust_raw(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=128, flank=50,
-                   max_rows=100, tb_budget_bytes=0):
+                   max_rows=100, tb_budget_bytes=0, trunc_gate=True):
         """One ``flank_region_align_v5``-equivalent round (kernels ii + iii) over the candidates.
         Returns ``(calls, cons)``: a structured array (CALL_DTYPE, one record per candidate) and the
         consensus bytes; candidate i's consensus is ``cons[calls['cons_off'][i] : +calls['cons_len'][i]]``."""
@@ -224,7 +224,7 @@ class Context:
         if n == 0:
             return calls, b""
         prm = HbParams(occ_cap, max_loci, flank, max_rows, TE_TYPES[te_type], int(plant),
-                       1 if result_type == "cons" else 0, 0, int(tb_budget_bytes))
+                       1 if result_type == "cons" else 0, 1 if trunc_gate else 0, int(tb_budget_bytes))
         nbytes = C.c_uint64(0)
         self._check(self._lib.hb_adjust(self._h, n, _ptr(flat), _ptr(off), C.byref(prm), _ptr(calls), C.byref(nbytes)),
                     "hb_adjust")

@@ -134,7 +134,8 @@ def is_TE_from_align_file(cur_align_file, query_name, cur_seq, temp_dir, subset_
         _GENOME.pop(ctx.device, None)
         ctx.load_genome([member_contigs[n].encode("ascii") for n in member_names])
         ctx.build_index(15, 10)
-        r = ctx.adjust([cur_seq], TE_type, int(plant), result_type, flank=50)[0]
+        # the truncated-member gate is run_find_members_v8's job (it owns the two files), not this call's
+        r = ctx.adjust([cur_seq], TE_type, int(plant), result_type, flank=50, trunc_gate=False)[0]
     if r["is_te"]:
         return (query_name, r["cons"], r["info"], r["copy_num"], cur_align_file)
     return (None, None, r["info"], 0, cur_align_file)

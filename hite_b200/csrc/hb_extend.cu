@@ -154,7 +154,7 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
     }
     HbAln out;
     out.score = (int32_t)(key >> 32);
-    out.keep = 0; out.contig = -1; out.ext_len = 0; out.start1 = 0; out.end1 = 0; out.row = -1; out.pad = 0;
+    out.keep = 0; out.contig = -1; out.ext_len = 0; out.start1 = 0; out.end1 = 0; out.row = -1; out.trow = -1;
     if (out.score <= 0) {
         out.score = 0; out.i_s = -1; out.i_e = -1; out.j_s = 0; out.j_e = 0;
         if (lane == 0) alns[p] = out;

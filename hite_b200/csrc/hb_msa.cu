@@ -32,7 +32,7 @@ __global__ void copy_filter_kernel(const HbLocus* __restrict__ pairs, uint32_t n
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     HbAln a = alns[p];
-    a.keep = 0; a.contig = -1; a.row = -1;
+    a.keep = 0; a.contig = -1; a.row = -1; a.trow = -1;
     if (a.score > 0) {
         const int L = (int)clen[pairs[p].cand];
         const int aligned = a.i_e - a.i_s + 1;
@@ -62,7 +62,8 @@ __global__ void copy_filter_kernel(const HbLocus* __restrict__ pairs, uint32_t n
 constexpr int SEL_MAX = 512;
 __global__ void __launch_bounds__(128)
 copy_select_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, uint32_t n_cand,
-                   int max_rows, HbAln* __restrict__ alns, uint32_t* __restrict__ n_rows) {
+                   int max_rows, int trunc_gate, HbAln* __restrict__ alns, uint32_t* __restrict__ n_rows,
+                   uint32_t* __restrict__ n_trows) {
     __shared__ uint8_t s_keep[4][SEL_MAX];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = blockIdx.x * 4 + wid;
@@ -103,18 +104,24 @@ copy_select_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict
         for (int x = lane; x < n; x += 32) if (keep[x] == 2) keep[x] = 0;
         __syncwarp();
     }
-    int rows = 0;
+    // rows of the full MSA, and of the truncated-member pass (Util.py:8116-8124, :10442-10446): the kept
+    // copies whose extended length exceeds 1000 bp, reduced to their first 500 + last 500 bases
+    int rows = 0, trows = 0;
     for (int x0 = 0; x0 < n; x0 += 32) {
         const int x = x0 + lane;
         const bool k = x < n && keep[x];
-        const uint32_t bal = __ballot_sync(HB_FULL, k);
+        const bool lg = trunc_gate && k && alns[p0 + x].ext_len > 1000;
+        const uint32_t bal = __ballot_sync(HB_FULL, k), balt = __ballot_sync(HB_FULL, lg);
         if (x < n) {
             alns[p0 + x].keep = k ? 1 : 0;
             alns[p0 + x].row = k ? rows + __popc(bal & ((1u << lane) - 1u)) : -1;
+            alns[p0 + x].trow = lg ? trows + __popc(balt & ((1u << lane) - 1u)) : -1;
         }
         rows += __popc(bal);
+        trows += __popc(balt);
     }
-    for (uint32_t x = p0 + n + lane; x < p1; x += 32) { alns[x].keep = 0; alns[x].row = -1; }
+    if (lane == 0) n_trows[c] = (uint32_t)trows;
+    for (uint32_t x = p0 + n + lane; x < p1; x += 32) { alns[x].keep = 0; alns[x].row = -1; alns[x].trow = -1; }
     if (lane == 0) n_rows[c] = (uint32_t)rows;
 }
 
@@ -165,12 +172,16 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
                  const uint64_t* __restrict__ coff, const uint32_t* __restrict__ clen, const uint32_t* __restrict__ pre,
                  const uint32_t* __restrict__ n_cols, const uint64_t* __restrict__ mat_off,
                  const uint32_t* __restrict__ gseq2, const uint32_t* __restrict__ gnmask, uint64_t tot, int flank,
-                 uint8_t* __restrict__ mat) {
+                 int trunc, uint8_t* __restrict__ mat) {
     const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p >= n_pairs) return;
     const HbAln a = alns[p];
-    if (!a.keep) return;
+    const int my_row = trunc ? a.trow : a.row;
+    if (my_row < 0) return;
+    // truncated pass keeps only the first 500 and last 500 bases of the extended copy
+    const int64_t ext_lo = a.j_s - flank, ext_hi = a.j_e + flank;
+    auto kept = [&](int64_t j) -> bool { return !trunc || (j - ext_lo) < 500 || (ext_hi - j) < 500; };
     const HbLocus pr = pairs[p];
     const uint32_t c = pr.cand;
     const int rel = (int)pr.rel;
@@ -178,22 +189,23 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
     const uint32_t C = n_cols[c];
     const uint32_t* pc = pre + coff[c];
     const uint32_t total_ins = C - (uint32_t)(L + 2 * flank);
-    uint8_t* row = mat + mat_off[c] + (size_t)a.row * C;
+    uint8_t* row = mat + mat_off[c] + (size_t)my_row * C;
     const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
     for (int q = a.i_s + lane; q <= a.i_e; q += 32) {
         const uint32_t v = qr[q];
         const int64_t j = pr.j0 + q + ((int64_t)(v & 0xFFFF) - 32768);
         const uint32_t col = (uint32_t)(q + flank) + pc[q];
-        if (!((v >> 24) & 1u)) row[col] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j);
+        if (!((v >> 24) & 1u) && kept(j)) row[col] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j);
         const int d = (int)((v >> 16) & 255u);
-        for (int t = 0; t < d; ++t) row[col + 1 + t] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j + 1 + t);
+        for (int t = 0; t < d; ++t)
+            if (kept(j + 1 + t)) row[col + 1 + t] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j + 1 + t);
     }
     for (int t = lane + 1; t <= flank; t += 32) {
         const int ql = a.i_s - t, qh = a.i_e + t;
         const uint32_t cl = (uint32_t)(ql + flank) + (ql >= 0 ? pc[ql] : 0u);
         const uint32_t ch = (uint32_t)(qh + flank) + (qh < L ? pc[qh] : total_ins);
-        row[cl] = (uint8_t)target_base(gseq2, gnmask, tot, rel, a.j_s - t);
-        row[ch] = (uint8_t)target_base(gseq2, gnmask, tot, rel, a.j_e + t);
+        if (kept(a.j_s - t)) row[cl] = (uint8_t)target_base(gseq2, gnmask, tot, rel, a.j_s - t);
+        if (kept(a.j_e + t)) row[ch] = (uint8_t)target_base(gseq2, gnmask, tot, rel, a.j_e + t);
     }
 }
 
@@ -207,9 +219,10 @@ cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const 
     return cudaGetLastError();
 }
 cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, int max_rows,
-                                  HbAln* alns, uint32_t* n_rows, cudaStream_t s) {
+                                  int trunc_gate, HbAln* alns, uint32_t* n_rows, uint32_t* n_trows, cudaStream_t s) {
     if (n_cand == 0) return cudaSuccess;
-    copy_select_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, max_rows, alns, n_rows);
+    copy_select_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, max_rows, trunc_gate, alns, n_rows,
+                                                        n_trows);
     return cudaGetLastError();
 }
 cudaError_t hb_ins_max_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
@@ -229,11 +242,12 @@ cudaError_t hb_layout_launch(const uint64_t* coff, const uint32_t* clen, uint32_
 cudaError_t hb_msa_write_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
                                 const uint32_t* qrec, const uint64_t* coff, const uint32_t* clen, const uint32_t* pre,
                                 const uint32_t* n_cols, const uint64_t* mat_off, const uint32_t* gseq2,
-                                const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* mat, cudaStream_t s) {
+                                const uint32_t* gnmask, uint64_t tot, int flank, int trunc, uint8_t* mat,
+                                cudaStream_t s) {
     if (n_pairs == 0) return cudaSuccess;
     const uint64_t threads = (uint64_t)n_pairs * 32;
     msa_write_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(pairs, n_pairs, alns, qrec_unit_off, qrec, coff,
                                                                        clen, pre, n_cols, mat_off, gseq2, gnmask, tot,
-                                                                       flank, mat);
+                                                                       flank, trunc, mat);
     return cudaGetLastError();
 }

@@ -6,7 +6,7 @@ cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const 
                                   const uint64_t* glen, uint32_t n_contig, uint64_t tot, int flank, HbAln* alns,
                                   cudaStream_t s);
 cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, int max_rows,
-                                  HbAln* alns, uint32_t* n_rows, cudaStream_t s);
+                                  int trunc_gate, HbAln* alns, uint32_t* n_rows, uint32_t* n_trows, cudaStream_t s);
 cudaError_t hb_ins_max_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
                               const uint32_t* qrec, const uint64_t* coff, uint32_t* ins, cudaStream_t s);
 cudaError_t hb_layout_launch(const uint64_t* coff, const uint32_t* clen, uint32_t n_cand, int flank, uint32_t* ins,
@@ -14,4 +14,5 @@ cudaError_t hb_layout_launch(const uint64_t* coff, const uint32_t* clen, uint32_
 cudaError_t hb_msa_write_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
                                 const uint32_t* qrec, const uint64_t* coff, const uint32_t* clen, const uint32_t* pre,
                                 const uint32_t* n_cols, const uint64_t* mat_off, const uint32_t* gseq2,
-                                const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* mat, cudaStream_t s);
+                                const uint32_t* gnmask, uint64_t tot, int flank, int trunc, uint8_t* mat,
+                                cudaStream_t s);

@@ -397,58 +397,80 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
 
     // ---- S8..S10: copy rules, star MSA -------------------------------------------------------------
     ENSURE("m.n_rows", sizeof(uint32_t) * (n_cand + 1)); ENSURE("m.n_cols", sizeof(uint32_t) * (n_cand + 1));
+    ENSURE("m.n_trows", sizeof(uint32_t) * (n_cand + 1));
+    HB_CUDA_OK(cudaMemsetAsync(ctx->buf("m.n_trows").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
+    const int trunc_gate = prm->trunc_gate ? 1 : 0;
     ENSURE("m.ins", sizeof(uint32_t) * (cand_off[n_cand] + 1));
     HB_CUDA_OK(cudaMemsetAsync(ctx->buf("m.ins").p, 0, sizeof(uint32_t) * (cand_off[n_cand] + 1), s));
     HB_CUDA_OK(cudaMemsetAsync(ctx->buf("m.n_rows").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
     HB_CUDA_OK(hb_copy_filter_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, d_clen, ctx->buf("g.goff").as<uint64_t>(),
                                      ctx->buf("g.glen").as<uint64_t>(), ctx->g_ncontig, tot, flank, ctx->buf("p.alns").as<HbAln>(), s));
     HB_CUDA_OK(hb_copy_select_launch(ctx->buf("p.pairs").as<HbLocus>(), ctx->buf("s.pair_off").as<uint32_t>(), n_cand,
-                                     prm->max_rows, ctx->buf("p.alns").as<HbAln>(), ctx->buf("m.n_rows").as<uint32_t>(), s));
+                                     prm->max_rows, trunc_gate, ctx->buf("p.alns").as<HbAln>(),
+                                     ctx->buf("m.n_rows").as<uint32_t>(), ctx->buf("m.n_trows").as<uint32_t>(), s));
     HB_CUDA_OK(hb_ins_max_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, ctx->buf("p.alns").as<HbAln>(),
                                  ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(), d_coff,
                                  ctx->buf("m.ins").as<uint32_t>(), s));
     HB_CUDA_OK(hb_layout_launch(d_coff, d_clen, n_cand, flank, ctx->buf("m.ins").as<uint32_t>(), ctx->buf("m.n_cols").as<uint32_t>(), s));
     launches += 4;
-    std::vector<uint32_t> h_rows(n_cand), h_cols(n_cand);
+    std::vector<uint32_t> h_rows(n_cand), h_cols(n_cand), h_trows(n_cand);
+    HB_CUDA_OK(cudaMemcpyAsync(h_trows.data(), ctx->buf("m.n_trows").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
     HB_CUDA_OK(cudaMemcpyAsync(h_rows.data(), ctx->buf("m.n_rows").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
     HB_CUDA_OK(cudaMemcpyAsync(h_cols.data(), ctx->buf("m.n_cols").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
     HB_CUDA_OK(cudaStreamSynchronize(s));
     // candidates with >= 1 row become judge tasks (0 rows: no member file in the reference either,
     // flank_region_align_v5 only submits queries present in extend_all_copies, Util.py:8125-8137)
-    std::vector<uint64_t> h_mat_off(n_cand + 1, 0);
+    std::vector<uint64_t> h_mat_off(n_cand + 1, 0), h_tmat_off(n_cand + 1, 0);
     std::vector<HbVoteTask> tasks;
-    std::vector<uint32_t> task_cand;
-    tasks.reserve(n_cand); task_cand.reserve(n_cand);
+    std::vector<uint32_t> task_cand;          // candidate of each task; trunc tasks follow the full ones
+    tasks.reserve(2 * (size_t)n_cand); task_cand.reserve(2 * (size_t)n_cand);
     uint64_t mat_total = 0, col_total = 0, match_total = 0, row_total = 0;
-    for (uint32_t c = 0; c < n_cand; ++c) {
-        h_mat_off[c] = mat_total;
-        if (h_rows[c] == 0) continue;
+    auto add_task = [&](uint32_t c, uint32_t rows, uint64_t off) {
         HbVoteTask t;
         memset(&t, 0, sizeof(t));
-        t.raw_off = mat_total; t.clean_off = mat_total;
+        t.raw_off = off; t.clean_off = off;
         t.plane_off = col_total * 24; t.cons_off = col_total + 2ull * tasks.size(); t.match_off = match_total;
         t.anchor_off = 2 * row_total;
         t.cand_off = cand_off[c]; t.cand_len = (int32_t)(cand_off[c + 1] - cand_off[c]);
-        t.R = (int32_t)h_rows[c]; t.C = (int32_t)h_cols[c];
+        t.R = (int32_t)rows; t.C = (int32_t)h_cols[c];
         t.te_type = prm->te_type; t.plant = prm->plant; t.result_type = prm->result_type; t.raw_is_ascii = 0;
         tasks.push_back(t); task_cand.push_back(c);
-        mat_total += (uint64_t)h_rows[c] * h_cols[c];
         col_total += h_cols[c];
         match_total += 2ull * ((uint64_t)h_cols[c] + 2);
-        row_total += h_rows[c];
+        row_total += rows;
+    };
+    for (uint32_t c = 0; c < n_cand; ++c) {
+        h_mat_off[c] = mat_total;
+        if (h_rows[c] == 0) continue;
+        add_task(c, h_rows[c], mat_total);
+        mat_total += (uint64_t)h_rows[c] * h_cols[c];
     }
     h_mat_off[n_cand] = mat_total;
+    const uint32_t n_full = (uint32_t)tasks.size();
+    const uint64_t tmat_base = mat_total;      // truncated matrices live after the full ones in the same buffer
+    for (uint32_t c = 0; c < n_cand; ++c) {
+        h_tmat_off[c] = mat_total;
+        if (h_rows[c] == 0 || h_trows[c] == 0) continue;
+        add_task(c, h_trows[c], mat_total);
+        mat_total += (uint64_t)h_trows[c] * h_cols[c];
+    }
+    h_tmat_off[n_cand] = mat_total;
+    (void)tmat_base;
     const uint32_t n_tasks = (uint32_t)tasks.size();
     ENSURE("m.mat_off", sizeof(uint64_t) * (n_cand + 1));
+    ENSURE("m.tmat_off", sizeof(uint64_t) * (n_cand + 1));
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("m.mat_off").p, h_mat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("m.tmat_off").p, h_tmat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
     ENSURE("m.mat", mat_total + 1);
     HB_CUDA_OK(cudaMemsetAsync(ctx->buf("m.mat").p, HB_SYM_GAP, mat_total + 1, s));
-    HB_CUDA_OK(hb_msa_write_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, ctx->buf("p.alns").as<HbAln>(),
-                                   ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(), d_coff, d_clen,
-                                   ctx->buf("m.ins").as<uint32_t>(), ctx->buf("m.n_cols").as<uint32_t>(),
-                                   ctx->buf("m.mat_off").as<uint64_t>(), ctx->buf("g.seq2").as<uint32_t>(),
-                                   ctx->buf("g.nmask").as<uint32_t>(), tot, flank, ctx->buf("m.mat").as<uint8_t>(), s));
-    ++launches;
+    for (int trunc = 0; trunc <= (n_tasks > n_full ? 1 : 0); ++trunc) {
+        HB_CUDA_OK(hb_msa_write_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, ctx->buf("p.alns").as<HbAln>(),
+                                       ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(), d_coff, d_clen,
+                                       ctx->buf("m.ins").as<uint32_t>(), ctx->buf("m.n_cols").as<uint32_t>(),
+                                       ctx->buf(trunc ? "m.tmat_off" : "m.mat_off").as<uint64_t>(), ctx->buf("g.seq2").as<uint32_t>(),
+                                       ctx->buf("g.nmask").as<uint32_t>(), tot, flank, trunc, ctx->buf("m.mat").as<uint8_t>(), s));
+        ++launches;
+    }
     HB_CUDA_OK(cudaEventRecord(ctx->ev[4], s));
     mark("copy rules + msa");
 
@@ -506,7 +528,15 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         o.align_start = o.align_end = o.homo_start = o.homo_end = -1;
         o.flags = HB_FLAG_NO_COPIES;
     }
-    for (uint32_t t = 0; t < n_tasks; ++t) memcpy(&calls[task_cand[t]], &h_calls[t], sizeof(hb_call));
+    for (uint32_t t = 0; t < n_full; ++t) memcpy(&calls[task_cand[t]], &h_calls[t], sizeof(hb_call));
+    // truncated-member gate (Util.py:10442-10446): a candidate whose truncated members fail is rejected
+    // with the truncated pass's verdict; otherwise the full pass decides
+    for (uint32_t t = n_full; t < n_tasks; ++t) {
+        if (h_calls[t].is_te) continue;
+        hb_call& o = calls[task_cand[t]];
+        memcpy(&o, &h_calls[t], sizeof(hb_call));
+        o.flags |= HB_FLAG_TRUNC_REJECT;
+    }
     if (cons_bytes) *cons_bytes = dense_total;
     ctx->last_ncand = n_cand; ctx->last_npairs = n_pairs;
     ctx->last_mat_off = h_mat_off; ctx->last_rows = h_rows; ctx->last_cols = h_cols;
@@ -550,7 +580,7 @@ extern "C" int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t*
         o.cand = pr[i].cand; o.rank = (int32_t)pr[i].rank; o.rel = (int32_t)pr[i].rel; o.nseeds = (int32_t)pr[i].nseeds;
         o.score = al[i].score; o.i_s = al[i].i_s; o.i_e = al[i].i_e; o.keep = al[i].keep; o.row = al[i].row;
         o.contig = al[i].contig; o.j0 = pr[i].j0; o.j_s = al[i].j_s; o.j_e = al[i].j_e;
-        o.start1 = al[i].start1; o.end1 = al[i].end1; o.ext_len = al[i].ext_len; o.pad = 0;
+        o.start1 = al[i].start1; o.end1 = al[i].end1; o.ext_len = al[i].ext_len; o.trow = al[i].trow;
     }
     return HB_OK;
 }

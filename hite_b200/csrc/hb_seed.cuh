@@ -18,7 +18,8 @@ struct HbAln {            // per candidate x locus pair, result of the banded al
     int64_t j_s, j_e;     // oriented global coordinates, inclusive
     int32_t contig, ext_len;
     int64_t start1, end1; // 1-based inclusive forward coordinates inside the contig
-    int32_t row, pad;
+    int32_t row;          // row in the full MSA or -1
+    int32_t trow;         // row in the truncated (first 500 + last 500) MSA or -1  (Util.py:8116-8124)
 };
 
 cudaError_t hb_seed_count_launch(const uint64_t* cm, uint32_t n_cm, const uint64_t* cgoff, uint32_t n_cand,

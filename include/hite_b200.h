@@ -93,6 +93,8 @@ int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_ascii, const u
 #define HB_FLAG_NO_COPIES 1 /* no full-length copy survived: the reference writes no member file for such a
                                query (module/Util.py:8125-8137) and it silently drops out of the result */
 
+#define HB_FLAG_TRUNC_REJECT 2 /* verdict comes from the truncated-member pass (module/Util.py:10442-10446) */
+
 /*
  * hb_genome_load -- kernel (i), part 1: upload the genome (the contigs of the `-r reference` FASTA,
  * upper/lower case ASCII, read_fasta semantics module/Util.py:1650-1670) and pack it to 2 bit/base
@@ -119,7 +121,7 @@ typedef struct {
     int32_t te_type;      /* HB_TE_* */
     int32_t plant;        /* --plant */
     int32_t result_type;  /* 1 = 'cons' */
-    int32_t pad;
+    int32_t trunc_gate;   /* 1 = truncated-member pass first (module/Util.py:8116-8124, :10442-10446); 1 */
     uint64_t tb_budget_bytes; /* HBM budget of the traceback stream, 0 = 16 GiB */
 } hb_params;
 
@@ -132,7 +134,7 @@ typedef struct {
     int32_t keep, row, contig; /* keep: passed the reference's copy rules; row: MSA row or -1 */
     int64_t j0, j_s, j_e;      /* band origin / target span in oriented padded coordinates */
     int64_t start1, end1;      /* 1-based inclusive contig coordinates (module/Util.py:8017-8018) */
-    int32_t ext_len, pad;
+    int32_t ext_len, trow;     /* trow: row in the truncated-member MSA or -1 */
 } hb_copy;
 
 /*

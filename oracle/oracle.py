@@ -88,6 +88,31 @@ def judge_v9(cand, rows):
                 homo_start=call.homo_start, homo_end=call.homo_end, tsd_count=call.trim_lead)
 
 
+def truncated_rows(copies, rows):
+    """Truncated-member matrix of the reference's first pass (Util.py:8116-8124): the kept copies whose
+    extended length exceeds 1000 bp, each reduced to its first 500 + last 500 bases (same columns)."""
+    kept = [c for c in copies if c["keep"]]
+    out = []
+    for c, row in zip(kept, rows):
+        if c["ext_len"] <= 1000:
+            continue
+        idx = [i for i, ch in enumerate(row) if ch != "-"]
+        keep = set(idx[:500]) | set(idx[-500:])
+        out.append("".join(ch if i in keep else "-" for i, ch in enumerate(row)))
+    return out
+
+
+def judge_with_trunc_gate(cand, copies, rows, judge=None, plant=1):
+    """run_find_members_v8 (Util.py:10439-10449): truncated members first, then the full members."""
+    judge = judge or (lambda c, r: judge_v5(c, r, plant))
+    t = truncated_rows(copies, rows)
+    if t:
+        rt = judge(cand, remove_sparse_cols(t))
+        if not rt["is_te"]:
+            return rt
+    return judge(cand, remove_sparse_cols(rows))
+
+
 def find_near_matches_ends(p, s, d):
     fs, fe, ls, le = C.c_int(-1), C.c_int(-1), C.c_int(-1), C.c_int(-1)
     n = lib().hbo_find_near_matches(p.encode(), len(p), s.encode(), len(s), d,

@@ -35,7 +35,7 @@ def test_flank_region_align_v5_fasta_contract(tmp_path):
     G = oracle.Genome(wl.contig_seqs)
     for name, seq, r in zip(wl.cand_names, wl.cand_seqs, res):
         cps, rows = G.candidate_msa(seq)
-        exp = oracle.judge_v5(seq.decode(), oracle.remove_sparse_cols(rows), 1) if rows else dict(is_te=False, cons="", copy_num=0)
+        exp = oracle.judge_with_trunc_gate(seq.decode(), cps, rows) if rows else dict(is_te=False, cons="", copy_num=0)
         assert (r["is_te"], r["cons"]) == (exp["is_te"], exp["cons"])
         keep = exp["is_te"] and not (exp["cons"].startswith("TG") and exp["cons"].endswith("CA")) and exp["copy_num"] > 5
         assert (name in contigs) == keep
@@ -69,7 +69,7 @@ def test_run_find_members_v8_on_member_files(tmp_path):
     fasta.store_fasta(members, mf)
     name, cons, info, copy_num, f = boundary.run_find_members_v8((wl.cand_names[0], seq.decode(), None, mf), str(tmp_path),
                                                                  None, 1, "tir", 0, "cons")
-    exp = oracle.judge_v5(seq.decode(), oracle.remove_sparse_cols(rows), 1)
+    exp = oracle.judge_v5(seq.decode(), oracle.remove_sparse_cols(rows), 1)      # no trunc file -> full pass only
     assert name == wl.cand_names[0] and cons == exp["cons"] and copy_num == exp["copy_num"]
     # an already aligned file is judged directly
     af = str(tmp_path / "aligned.fa")

@@ -45,7 +45,7 @@ def test_copies_msa_and_calls_bit_exact(ctx, small):
         got_rows = ctx.last_msa(ci)
         assert got_rows == rows, ci
         if rows:
-            exp = oracle.judge_v5(seq.decode(), oracle.remove_sparse_cols(rows), 1)
+            exp = oracle.judge_with_trunc_gate(seq.decode(), cps, rows)
             r = res[ci]
             for k in ("is_te", "info", "cons", "copy_num", "homo_start", "homo_end"):
                 assert r[k] == exp[k], (ci, k)
@@ -67,7 +67,7 @@ def test_edge_cases(ctx, small):
         cps, rows = G.candidate_msa(seq.upper())
         assert ctx.last_msa(ci) == rows, ci
         if rows:
-            exp = oracle.judge_v5(seq.decode().upper(), oracle.remove_sparse_cols(rows), 1)
+            exp = oracle.judge_with_trunc_gate(seq.decode().upper(), cps, rows)
             for k in ("is_te", "info", "cons", "copy_num"):
                 assert res[ci][k] == exp[k], (ci, k)
 
