@@ -18,7 +18,7 @@
 namespace {
 
 constexpr int EXT_WARPS = 8;
-constexpr int NEG6 = -6;
+constexpr int HB_NARROW_SPREAD = 8;      // HB-align S7
 
 __device__ __forceinline__ int packed_base(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask,
                                            uint64_t p) {
@@ -50,61 +50,79 @@ __device__ __forceinline__ int target_base(const uint32_t* __restrict__ gseq2, c
         NIB = (H > 0) ? fl : 0u;                                                    \
     }
 
+// HB = half band = lanes per pair: 32 (o in [-32,31], one pair per warp) or 16 (o in [-16,15], two
+// pairs per warp) -- HB-align S7: the narrow band is used when the seed cluster's diagonal spread is
+// <= HB_NARROW_SPREAD.  Traceback stream: word (r>>3)*HB + sublane, nibble r&7, 128-word units.
+template <int HB>
 __global__ void __launch_bounds__(EXT_WARPS * 32)
 extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi,
               const uint32_t* __restrict__ gseq2, const uint32_t* __restrict__ gnmask, uint64_t tot,
               const uint32_t* __restrict__ cseq2, const uint32_t* __restrict__ cnmask,
               const uint64_t* __restrict__ cgoff, const uint32_t* __restrict__ clen,
               const uint32_t* __restrict__ tb_unit_off, uint32_t tb_unit_base, uint32_t* __restrict__ tbuf,
-              const uint32_t* __restrict__ qrec_unit_off, uint32_t* __restrict__ qrec,
               HbAln* __restrict__ alns) {
-    // per-warp sequence windows for one super-step (64 anti-diagonals): positions
-    // [half0 - 16, half0 + 48) of the query (index = i - half0 + 16) and of the target (j' - half0 + 16)
-    __shared__ uint8_t s_rq[EXT_WARPS][64];
-    __shared__ uint8_t s_rt[EXT_WARPS][64];
+    constexpr int PPW = 32 / HB;                 // pairs per warp
+    constexpr int WIN = HB + 32;                 // sequence window of one super-step (64 anti-diagonals)
+    __shared__ uint8_t s_rq[EXT_WARPS * PPW][WIN];
+    __shared__ uint8_t s_rt[EXT_WARPS * PPW][WIN];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t p = pair_lo + blockIdx.x * EXT_WARPS + wid;
-    if (p >= pair_hi) return;
-    const HbLocus pr = pairs[p];
-    const int L = (int)clen[pr.cand];
-    const uint64_t cstart = cgoff[pr.cand];
+    const int sub = lane / HB, sl = lane % HB;   // which pair of the warp, lane inside the pair
+    const uint32_t p = pair_lo + (blockIdx.x * EXT_WARPS + wid) * PPW + sub;
+    bool active = p < pair_hi;
+    HbLocus pr;
+    pr.cand = 0; pr.rel = 0; pr.j0 = 0; pr.dmin = 0; pr.dmax = 0; pr.nseeds = 0; pr.rank = 0;
+    if (active) {
+        pr = pairs[p];
+        const bool narrow = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD;
+        active = (HB == 16) ? narrow : !narrow;
+    }
+    if (!__ballot_sync(HB_FULL, active)) return;
+    const int L = active ? (int)clen[pr.cand] : 0;
+    const uint64_t cstart = active ? cgoff[pr.cand] : 0;
     const int rel = (int)pr.rel;
     const int64_t j0 = pr.j0;
-    uint8_t* rq = s_rq[wid];
-    uint8_t* rt = s_rt[wid];
-    uint32_t* tb = tbuf + ((size_t)(tb_unit_off[p] - tb_unit_base) << 8);      // 256 words per unit
-    const int n_super = (2 * L + 62 + 63) >> 6;
+    uint8_t* rq = s_rq[wid * PPW + sub];
+    uint8_t* rt = s_rt[wid * PPW + sub];
+    uint32_t* tb = tbuf + (active ? ((size_t)(tb_unit_off[p] - tb_unit_base) << 7) : 0);   // 128 words per unit
+    const int my_super = active ? ((2 * L + 2 * HB - 2 + 63) >> 6) : 0;
+    int n_super = my_super;
+    if (PPW == 2) n_super = max(__shfl_sync(HB_FULL, my_super, 0), __shfl_sync(HB_FULL, my_super, 16));
 
     // query N = 4, target N = 5: never equal, so one compare scores a cell
     auto qsym = [&](int x) -> uint8_t {
-        return (uint8_t)((x >= 0 && x < L) ? packed_base(cseq2, cnmask, cstart + (uint64_t)x) : 4);
+        return (uint8_t)((active && x >= 0 && x < L) ? packed_base(cseq2, cnmask, cstart + (uint64_t)x) : 4);
     };
     auto tsym = [&](int x) -> uint8_t {
+        if (!active) return 5;
         const int c = target_base(gseq2, gnmask, tot, rel, j0 + x);
         return (uint8_t)(c < 4 ? c : 5);
     };
-    // window of the first super-step (half0 = -16): positions [-32, 32)
-    rq[lane] = qsym(-32 + lane); rt[lane] = tsym(-32 + lane);
-    rq[32 + lane] = qsym(lane); rt[32 + lane] = tsym(lane);
+    // window of the first super-step (half0 = -HB/2): positions [-HB, 32)
+    for (int t = sl; t < WIN; t += HB) { rq[t] = qsym(-HB + t); rt[t] = tsym(-HB + t); }
     __syncwarp();
 
     int H1 = 0, E1 = 0, F1 = 0, H2 = 0;
     uint32_t best = 0;                                   // (h << 16) | (65535 - r): max = best score, earliest r
     uint32_t tbword = 0;
-    const uint32_t m_up = lane == 0 ? 0u : 0xffffffffu;  // band edge: neighbour outside = (H 0, E/F 0)
-    const uint32_t m_dn = lane == 31 ? 0u : 0xffffffffu;
-    const uint8_t* pq = rq + (32 - lane);                // query index of pair-step u:  u - lane + 32
-    const uint8_t* pt = rt + lane;                       // target index: u + lane (even), u + lane + 1 (odd)
+    const uint32_t m_up = sl == 0 ? 0u : 0xffffffffu;    // band edge: neighbour outside = (H 0, E/F 0)
+    const uint32_t m_dn = sl == HB - 1 ? 0u : 0xffffffffu;
+    const uint8_t* pq = rq + (HB - sl);                  // query index of pair-step u:  u - sl + HB
+    const uint8_t* pt = rt + sl;                         // target index: u + sl (even), u + sl + 1 (odd)
     for (int sup = 0; sup < n_super; ++sup) {
         if (sup > 0) {
-            const int half0 = -16 + 32 * sup;
-            const uint8_t a = rq[32 + lane], b = rt[32 + lane];
-            const uint8_t nq = qsym(half0 + 16 + lane), nt = tsym(half0 + 16 + lane);
+            const int half0 = -HB / 2 + 32 * sup;
+            const uint8_t a = rq[32 + sl], b = rt[32 + sl];
+            uint8_t nq[32 / HB], nt[32 / HB];
+#pragma unroll
+            for (int z = 0; z < 32 / HB; ++z) { nq[z] = qsym(half0 + HB / 2 + sl + z * HB); nt[z] = tsym(half0 + HB / 2 + sl + z * HB); }
             __syncwarp();
-            rq[lane] = a; rt[lane] = b; rq[32 + lane] = nq; rt[32 + lane] = nt;
+            rq[sl] = a; rt[sl] = b;
+#pragma unroll
+            for (int z = 0; z < 32 / HB; ++z) { rq[HB + sl + z * HB] = nq[z]; rt[HB + sl + z * HB] = nt[z]; }
             __syncwarp();
         }
         const uint32_t rbase = 65535u - (uint32_t)(64 * sup);
+        const bool store = sup < my_super;
         int tnext = pt[0];
 #pragma unroll 4
         for (int u = 0; u < 32; ++u) {
@@ -115,7 +133,7 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
             int h, e, f; uint32_t nib;
             // even step (r = 64 sup + 2u): left from lane-1, up/diag own
             {
-                uint32_t rv = __shfl_up_sync(HB_FULL, __byte_perm((uint32_t)E1, (uint32_t)H1, 0x5410), 1) & m_up;
+                uint32_t rv = __shfl_up_sync(HB_FULL, __byte_perm((uint32_t)E1, (uint32_t)H1, 0x5410), 1, HB) & m_up;
                 const int hl = (int)(rv >> 16), el = (int)(rv & 0xFFFFu);
                 HB_CELL(hl, el, H1, F1, H2, qb, te, h, e, f, nib);
                 best = max(best, ((uint32_t)h << 16) | (rbase - (uint32_t)(2 * u)));
@@ -124,7 +142,7 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
             }
             // odd step (r + 1): up from lane+1, left/diag own
             {
-                uint32_t rv = __shfl_down_sync(HB_FULL, __byte_perm((uint32_t)F1, (uint32_t)H1, 0x5410), 1) & m_dn;
+                uint32_t rv = __shfl_down_sync(HB_FULL, __byte_perm((uint32_t)F1, (uint32_t)H1, 0x5410), 1, HB) & m_dn;
                 const int hu = (int)(rv >> 16), fu = (int)(rv & 0xFFFFu);
                 HB_CELL(H1, E1, hu, fu, H2, qb, to, h, e, f, nib);
                 best = max(best, ((uint32_t)h << 16) | (rbase - (uint32_t)(2 * u + 1)));
@@ -132,39 +150,41 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
                 H2 = H1; H1 = h; E1 = e; F1 = f;
             }
             if ((u & 3) == 3) {
-                tb[(size_t)(8 * sup + (u >> 2)) * 32 + lane] = tbword;      // 128 B per warp, coalesced
+                if (store) tb[(size_t)(8 * sup + (u >> 2)) * HB + sl] = tbword;      // 4*HB B per pair, coalesced
                 tbword = 0;
             }
         }
     }
     // ---- best cell: max score, then smallest i, then smallest j ------------------------------
     unsigned long long key = 0;
-    if ((best >> 16) != 0) {
+    if (active && (best >> 16) != 0) {
         const int r = 65535 - (int)(best & 0xFFFFu);
-        const int s = r - 32;
-        const int o = 2 * lane - 32 + (s & 1);
+        const int s = r - HB;
+        const int o = 2 * sl - HB + (s & 1);
         const int i = (s - o) >> 1;
-        key = ((unsigned long long)(best >> 16) << 32) | ((unsigned long long)(0xFFFF - i) << 16) |
-              (unsigned long long)(63 - (o + 32));
+        if (i >= 0 && i < L)      // rows below the query are never better than the row above them
+            key = ((unsigned long long)(best >> 16) << 32) | ((unsigned long long)(0xFFFF - i) << 16) |
+                  (unsigned long long)(127 - (o + HB));
     }
 #pragma unroll
-    for (int off = 16; off; off >>= 1) {
+    for (int off = HB / 2; off; off >>= 1) {
         unsigned long long t = __shfl_xor_sync(HB_FULL, key, off);
         key = t > key ? t : key;
     }
+    if (!active) return;
     HbAln out;
     out.score = (int32_t)(key >> 32);
     out.keep = 0; out.contig = -1; out.ext_len = 0; out.start1 = 0; out.end1 = 0; out.row = -1; out.trow = -1;
     if (out.score <= 0) {
         out.score = 0; out.i_s = -1; out.i_e = -1; out.j_s = 0; out.j_e = 0;
-        if (lane == 0) alns[p] = out;
+        if (sl == 0) alns[p] = out;
         return;
     }
     const int bi = 0xFFFF - (int)((key >> 16) & 0xFFFF);
-    const int bo = (63 - (int)(key & 0xFFFF)) - 32;
+    const int bo = (127 - (int)(key & 0xFFFF)) - HB;
     // the walk back is done by traceback_kernel (one thread per pair); leave the end cell here
     out.i_s = bi; out.i_e = bi; out.j_s = j0 + bi + bo; out.j_e = j0 + bi + bo;
-    if (lane == 0) alns[p] = out;
+    if (sl == 0) alns[p] = out;
 }
 
 // Traceback: ONE THREAD per pair (the walk is inherently serial; 32 independent walks per warp keep
@@ -178,16 +198,18 @@ traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t p
     if (p >= pair_hi) return;
     HbAln a = alns[p];
     if (a.score <= 0) return;
-    const int64_t j0 = pairs[p].j0;
-    const uint32_t* tb = tbuf + ((size_t)(tb_unit_off[p] - tb_unit_base) << 8);
+    const HbLocus pr = pairs[p];
+    const int64_t j0 = pr.j0;
+    const int HB = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD ? 16 : 32;
+    const uint32_t* tb = tbuf + ((size_t)(tb_unit_off[p] - tb_unit_base) << 7);
     uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
     int i = a.i_e, o = (int)(a.j_e - j0) - a.i_e, pending_d = 0;
     int i_s = i, o_s = o;
     int w_idx = -1;
     uint32_t w = 0;
     auto fetch = [&](int ii, int oo) -> uint32_t {
-        const int r = 2 * ii + oo + 32;
-        const int idx = (r >> 3) * 32 + ((oo + 32) >> 1);
+        const int r = 2 * ii + oo + HB;
+        const int idx = (r >> 3) * HB + ((oo + HB) >> 1);
         if (idx != w_idx) { w = tb[idx]; w_idx = idx; }
         return (w >> (4 * (r & 7))) & 15u;
     };
@@ -222,13 +244,15 @@ traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t p
     alns[p] = a;
 }
 
-// sizes: tb units (1 KB = 64 steps x 32 lanes x 4 bit) and qrec units (32 words) per pair
+// sizes: tb units (512 B = 64 steps x 16 lanes x 4 bit) and qrec units (32 words) per pair
 __global__ void pair_sizes_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const uint32_t* __restrict__ clen,
                                   uint32_t* __restrict__ tb_units, uint32_t* __restrict__ qrec_units) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
-    const uint32_t L = clen[pairs[p].cand];
-    tb_units[p] = (2 * L + 62 + 63) >> 6;
+    const HbLocus pr = pairs[p];
+    const uint32_t L = clen[pr.cand];
+    const uint32_t hb = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD ? 16u : 32u;
+    tb_units[p] = ((2 * L + 2 * hb - 2 + 63) >> 6) * (hb / 16);      // 128-word units
     qrec_units[p] = (L + 31) >> 5;
 }
 
@@ -248,9 +272,11 @@ cudaError_t hb_extend_launch(const HbLocus* pairs, uint32_t pair_lo, uint32_t pa
                              HbAln* alns, cudaStream_t s) {
     if (pair_hi <= pair_lo) return cudaSuccess;
     const uint32_t n = pair_hi - pair_lo;
-    extend_kernel<<<(n + EXT_WARPS - 1) / EXT_WARPS, EXT_WARPS * 32, 0, s>>>(
-        pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf,
-        qrec_unit_off, qrec, alns);
+    // wide band: one pair per warp; narrow band: two pairs per warp.  Each kernel skips the other class.
+    extend_kernel<32><<<(n + EXT_WARPS - 1) / EXT_WARPS, EXT_WARPS * 32, 0, s>>>(
+        pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
+    extend_kernel<16><<<(n + 2 * EXT_WARPS - 1) / (2 * EXT_WARPS), EXT_WARPS * 32, 0, s>>>(
+        pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
     traceback_kernel<<<(n + 127) / 128, 128, 0, s>>>(pairs, pair_lo, pair_hi, tb_unit_off, tb_unit_base, tbuf,
                                                       qrec_unit_off, qrec, alns);
     return cudaGetLastError();

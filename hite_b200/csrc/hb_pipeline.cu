@@ -359,12 +359,12 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     mark("seed/sort/cluster/pairs");
 
     // ---- S7: banded extension, chunked by the traceback budget -----------------------------------
-    uint64_t budget_units = (prm->tb_budget_bytes ? prm->tb_budget_bytes : (16ull << 30)) >> 10;
+    uint64_t budget_units = (prm->tb_budget_bytes ? prm->tb_budget_bytes : (16ull << 30)) >> 9;      // 512 B units
     if (budget_units < 64) budget_units = 64;
     uint64_t ext_steps = 0;
     if (n_pairs > 0) {
         const uint64_t alloc_units = std::min<uint64_t>(tb_units_total, budget_units);
-        ENSURE("p.tbuf", (alloc_units + 1) << 10);
+        ENSURE("p.tbuf", (alloc_units + 1) << 9);
         ENSURE("p.qrec", ((qr_units_total + 1) << 5) * sizeof(uint32_t));
         uint32_t lo = 0;
         while (lo < n_pairs) {
@@ -387,10 +387,10 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
                                         ctx->buf("c.nmask").as<uint32_t>(), d_cgoff, d_clen, ctx->buf("p.tb_off").as<uint32_t>(),
                                         (uint32_t)base, ctx->buf("p.tbuf").as<uint32_t>(), ctx->buf("p.qr_off").as<uint32_t>(),
                                         ctx->buf("p.qrec").as<uint32_t>(), ctx->buf("p.alns").as<HbAln>(), s));
-            launches += 2;
+            launches += 3;
             lo = hi;
         }
-        ext_steps = tb_units_total * 64;
+        ext_steps = tb_units_total * 32;                 // one 512 B unit = 64 anti-diagonals of 16 lanes
     }
     HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
     mark("extend");

@@ -57,7 +57,7 @@ uint64_t hbo_genome_contig_off(const hbo_genome *g, uint32_t c);
 uint64_t hbo_minimizers_codes(const uint8_t *code, uint64_t tot, int k, int w, uint64_t *out, uint64_t cap);
 uint64_t hbo_minimizers(const hbo_genome *g, int k, int w, uint64_t *out, uint64_t cap);
 void hbo_sort_u64(uint64_t *keys, uint64_t n);
-int hbo_align_pair(const hbo_genome *g, const uint8_t *q, int L, int rel, int64_t j0, hbo_aln *out, uint32_t *qrec);
+int hbo_align_pair(const hbo_genome *g, const uint8_t *q, int L, int rel, int64_t j0, int half_band, hbo_aln *out, uint32_t *qrec);
 uint64_t hbo_find_loci(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w,
                        const uint8_t *cand_codes, const uint64_t *coff, uint32_t n_cand,
                        int occ_cap, int max_loci, hbo_locus *out, uint64_t cap);

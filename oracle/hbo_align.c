@@ -132,8 +132,9 @@ void hbo_sort_u64(uint64_t *keys, uint64_t n) { qsort(keys, n, sizeof(uint64_t),
 /* banded affine local alignment (HB-align S7).  Query rows i in [0,L), oriented target j = j0+j',
    band o = j' - i in [-32, 31].  Scores: match +2, mismatch/N -4, gap open 4, gap extend 2.
    Outside the band / outside the genome: H = 0, E = F = -6.                                       */
-#define BAND_LO (-32)
-#define BAND_HI 31
+/* band half-width: 16 when the seed cluster's diagonal spread is <= HB_NARROW_SPREAD (o in [-16,15]),
+   else 32 (o in [-32,31])  -- HB-align S7 */
+#define HB_NARROW_SPREAD 8
 #define SC_MATCH 2
 #define SC_MIS (-4)
 #define SC_GAPO 4
@@ -142,8 +143,9 @@ void hbo_sort_u64(uint64_t *keys, uint64_t n) { qsort(keys, n, sizeof(uint64_t),
 
 typedef struct { int32_t h, e, f; uint8_t tb; } cell_t;   /* tb: bits0-1 hsrc (0 stop,1 diag,2 E,3 F), bit2 eext, bit3 fext */
 
-int hbo_align_pair(const hbo_genome *g, const uint8_t *q /*codes*/, int L, int rel, int64_t j0,
+int hbo_align_pair(const hbo_genome *g, const uint8_t *q /*codes*/, int L, int rel, int64_t j0, int half_band,
                    hbo_aln *out, uint32_t *qrec /* L entries or NULL */) {
+    const int BAND_LO = -half_band, BAND_HI = half_band - 1;
     const int W = BAND_HI - BAND_LO + 1;
     /* per-thread scratch, grown on demand (avoids an mmap/munmap + page-fault storm per pair) */
     static _Thread_local cell_t *tl_rows = NULL;
@@ -352,7 +354,8 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
         hbo_copy *cp = &copies[x];
         memset(cp, 0, sizeof(*cp));
         cp->rank = x; cp->rel = (int32_t)loci[x].rel; cp->contig = -1;
-        hbo_align_pair(g, q, L, (int)loci[x].rel, loci[x].j0, &a, qrecs + (size_t)x * L);
+        hbo_align_pair(g, q, L, (int)loci[x].rel, loci[x].j0,
+                       (loci[x].dmax - loci[x].dmin <= HB_NARROW_SPREAD) ? 16 : 32, &a, qrecs + (size_t)x * L);
         cp->score = a.score; cp->i_s = a.i_s; cp->i_e = a.i_e; cp->j_s = a.j_s; cp->j_e = a.j_e;
         if (a.score <= 0) continue;
         const int aligned = a.i_e - a.i_s + 1;                         /* query_alignment_length (M+I) */
