@@ -163,25 +163,34 @@ struct Hist {  // last 32 non-gap symbols, most recent first
         return k <= 16 ? (int)((h0 >> (4 * (k - 1))) & 15ull) : (int)((h1 >> (4 * (k - 17))) & 15ull);
     }
 };
-// smallest a with lev(p, s[a:e]) == dist  (oracle/fnm.py::_longest_start)
+// smallest a with lev(p, s[a:e]) == dist  (oracle/fnm.py::_longest_start).  Bit-parallel: the
+// reversed pattern is aligned globally-at-the-start against the text read backwards from e, so after
+// k symbols the running score is lev(p, s[e-k:e]); the largest k that reaches `dist` wins.
 __device__ int longest_start(const Pattern& P, const Hist& H, int e, int dist) {
     const int m = P.m;
     int maxk = m + dist; if (maxk > e) maxk = e;
-    int row[24], nw[24];
-    for (int k = 0; k <= maxk; ++k) row[k] = k;
-    for (int j = 1; j <= m; ++j) {
-        const int pj = P.sym(m - j);
-        nw[0] = j;
-        for (int k = 1; k <= maxk; ++k) {
-            int v = row[k] + 1;
-            v = min(v, nw[k - 1] + 1);
-            v = min(v, row[k - 1] + (pj != H.back(k)));
-            nw[k] = v;
-        }
-        for (int k = 0; k <= maxk; ++k) row[k] = nw[k];
+    uint32_t peq_r[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) peq_r[s] = __brev(P.peq[s]) >> (32 - m);
+    const uint32_t top = 1u << (m - 1);
+    uint32_t pv = m >= 32 ? 0xffffffffu : ((1u << m) - 1u), mv = 0;
+    int score = m, best_k = 0;          // k = 0: lev(p, '') = m, only equal to dist when m <= dist
+    for (int k = 1; k <= maxk; ++k) {
+        const int c = H.back(k);
+        uint32_t eq = 0;
+#pragma unroll
+        for (int s = 0; s < 5; ++s) eq = (c == s) ? peq_r[s] : eq;
+        const uint32_t xv = eq | mv;
+        const uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
+        uint32_t ph = mv | ~(xh | pv);
+        uint32_t mh = pv & xh;
+        if (ph & top) ++score; else if (mh & top) --score;
+        ph = (ph << 1) | 1u; mh <<= 1;
+        pv = mh | ~(xv | ph);
+        mv = ph & xv;
+        if (score == dist) best_k = k;
     }
-    for (int k = maxk; k >= 0; --k) if (row[k] == dist) return e - k;
-    return e;  // unreachable
+    return e - best_k;
 }
 
 struct Match { int a, e, d; };
