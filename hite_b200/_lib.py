@@ -95,7 +95,7 @@ def _ptr(a):
 def _calls_to_dicts(calls, cons_b):
     """hb_call records -> list of dicts (field columns converted once; structured scalar access is slow)."""
     cols = {k: calls[k].tolist() for k in CALL_DTYPE.names}
-    text = cons_b.decode("ascii")
+    text = cons_b.decode("latin-1")       # 1:1 bytes -> str; slices are pure ASCII
     out = []
     for i in range(len(calls)):
         o = cols["cons_off"][i]

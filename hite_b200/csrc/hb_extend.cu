@@ -205,12 +205,23 @@ traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t p
     uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
     int i = a.i_e, o = (int)(a.j_e - j0) - a.i_e, pending_d = 0;
     int i_s = i, o_s = o;
-    int w_idx = -1;
-    uint32_t w = 0;
+    // four consecutive 8-step groups of the current lane column are fetched together (independent
+    // loads in flight): a diagonal run walks down the groups of one column
+    int c_lane = -1, g_hi = -1;                 // buffered: column c_lane, groups g_hi .. g_hi-3
+    uint32_t wb0 = 0, wb1 = 0, wb2 = 0, wb3 = 0;
     auto fetch = [&](int ii, int oo) -> uint32_t {
         const int r = 2 * ii + oo + HB;
-        const int idx = (r >> 3) * HB + ((oo + HB) >> 1);
-        if (idx != w_idx) { w = tb[idx]; w_idx = idx; }
+        const int g = r >> 3, lc = (oo + HB) >> 1;
+        if (lc != c_lane || g > g_hi || g < g_hi - 3) {
+            c_lane = lc; g_hi = g;
+            const uint32_t* base = tb + (size_t)g * HB + lc;
+            wb0 = base[0];
+            wb1 = g >= 1 ? base[-(ptrdiff_t)HB] : 0u;
+            wb2 = g >= 2 ? base[-(ptrdiff_t)(2 * HB)] : 0u;
+            wb3 = g >= 3 ? base[-(ptrdiff_t)(3 * HB)] : 0u;
+        }
+        const int d = g_hi - g;
+        const uint32_t w = d == 0 ? wb0 : d == 1 ? wb1 : d == 2 ? wb2 : wb3;
         return (w >> (4 * (r & 7))) & 15u;
     };
     while (i >= 0) {

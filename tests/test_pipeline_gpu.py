@@ -77,3 +77,39 @@ def test_traceback_budget_chunking_is_invariant(ctx, small):
     a = ctx.adjust(wl.cand_seqs[:12], "tir", 1)
     b = ctx.adjust(wl.cand_seqs[:12], "tir", 1, tb_budget_bytes=4 << 20)
     assert a == b
+
+
+def test_stress_shapes_bit_exact(ctx):
+    """High-copy families (> max_loci clusters, > 100 surviving copies), long elements (wide band,
+    multi-super-step traceback), N runs and lower-case input: GPU == C port on every record."""
+    wl = synth.make_workload(genome_bp=3_000_000, n_contigs=3, n_families=3, cands_per_family=2, copies=(150, 220),
+                             length=(300, 700), seed=21, indel=0.002)
+    wl2 = synth.make_workload(genome_bp=1_500_000, n_contigs=1, n_families=4, cands_per_family=2, copies=(6, 12),
+                              length=(4000, 9000), seed=22, indel=0.004, sub=(0.0, 0.05))
+    contigs = [c.copy() for c in wl.contig_seqs] + [c.copy() for c in wl2.contig_seqs]
+    contigs[0][1000:1400] = ord("N")
+    contigs[1][5000:5003] = ord("n")
+    contigs[2] = np.frombuffer(contigs[2].tobytes().lower(), dtype=np.uint8).copy()
+    cands = list(wl.cand_seqs) + list(wl2.cand_seqs)
+    G = oracle.Genome(contigs)
+    ctx.load_genome(contigs)
+    ctx.build_index(15, 10)
+    assert np.array_equal(ctx.debug_index(), G.index)
+    res = ctx.adjust(cands, "tir", 1)
+    copies = ctx.last_copies()
+    n_big = 0
+    for ci, seq in enumerate(cands):
+        cps, rows = G.candidate_msa(seq)
+        mine = copies[copies["cand"] == ci]
+        assert len(mine) == len(cps), ci
+        for a, b in zip(mine, cps):
+            for k in ("rank", "rel", "score", "i_s", "i_e", "j_s", "j_e", "keep"):
+                assert int(a[k]) == int(b[k]), (ci, k, int(a[k]), int(b[k]))
+        assert ctx.last_msa(ci) == rows, ci
+        n_big += len(rows) == 100
+        if rows:
+            exp = oracle.judge_with_trunc_gate(seq.decode(), cps, rows)
+            for k in ("is_te", "info", "cons", "copy_num"):
+                assert res[ci][k] == exp[k], (ci, k)
+    assert n_big >= 1                       # the 100-longest rule was exercised
+    assert sum(r["is_te"] for r in res[len(wl.cand_seqs):]) >= 1      # long elements come through
