@@ -202,26 +202,32 @@ def main():
 
     def gather_results(res):
         """The path's only exchange: all-gather of the emitted records (candidate index, consensus length,
-        consensus bytes) before the get_nonRedundant_lib merge (reference main.py:652-664 cat >>)."""
+        consensus bytes) before the get_nonRedundant_lib merge (reference main.py:652-664 cat >>).  The
+        consensus bytes are gathered straight from the library's device buffer over NVLink; rank 0 (the
+        CPU merge's host) then reads the merged payload back."""
         calls, cons = res
         te = calls["is_te"] != 0
         if world == 1:
             return int(te.sum())
-        head = np.stack([my_arr[te], calls["cons_len"][te].astype(np.int64)], axis=1).tobytes()
-        payload = np.int64(int(te.sum())).tobytes() + head + cons       # accepted consensi are the dense buffer
-        n = torch.tensor([len(payload)], device="cuda", dtype=torch.int64)
+        head = torch.from_numpy(np.stack([my_arr[te], calls["cons_len"][te].astype(np.int64)], axis=1).reshape(-1)).cuda()
+        dev = ctx.last_cons_device()
+        body = torch.as_tensor(dev, device="cuda") if dev is not None else torch.zeros(0, dtype=torch.uint8, device="cuda")
+        n = torch.tensor([head.numel(), body.numel()], device="cuda", dtype=torch.int64)
         sizes = [torch.zeros_like(n) for _ in range(world)]
         dist.all_gather(sizes, n)
-        mx = int(max(int(s.item()) for s in sizes))
-        buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
-        if payload:
-            buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
-        out = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(out, buf)
-        total = 0
-        for o in out:
-            total += int(np.frombuffer(bytes(o[:8].cpu().numpy()), dtype=np.int64)[0])
-        return total
+        sz = torch.stack(sizes).cpu().numpy()
+        hmax, bmax = int(sz[:, 0].max()), int(sz[:, 1].max())
+        hbuf = torch.zeros(hmax, dtype=torch.int64, device="cuda"); hbuf[:head.numel()] = head
+        bbuf = torch.zeros(bmax, dtype=torch.uint8, device="cuda"); bbuf[:body.numel()] = body
+        hout = [torch.empty_like(hbuf) for _ in range(world)]
+        bout = [torch.empty_like(bbuf) for _ in range(world)]
+        dist.all_gather(hout, hbuf)
+        dist.all_gather(bout, bbuf)
+        if rank == 0:                                   # the merge consumer is a CPU stage
+            merged_head = torch.cat([h[:int(k)] for h, k in zip(hout, sz[:, 0])]).cpu()
+            merged_body = torch.cat([b[:int(k)] for b, k in zip(bout, sz[:, 1])]).cpu()
+            assert int(merged_head[1::2].sum()) == merged_body.numel()
+        return int(sz[:, 0].sum() // 2)
 
     flat = np.frombuffer(b"".join(my_cands) + b"\0", dtype=np.uint8)
     offs = np.zeros(len(my_cands) + 1, dtype=np.uint64)

@@ -81,6 +81,7 @@ def load():
     lib.hb_genome_info.argtypes = [vp, u64p, u64p, vp, C.c_uint32]
     lib.hb_adjust.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(HbParams), vp, u64p]
     lib.hb_last_cons.argtypes = [vp, vp, C.c_uint64]
+    lib.hb_last_cons_device.argtypes = [vp, C.POINTER(vp), u64p]
     lib.hb_last_copies.argtypes = [vp, vp, C.c_uint64, u64p]
     lib.hb_debug_index.argtypes = [vp, vp, C.c_uint64]
     lib.hb_last_msa.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
@@ -222,22 +223,35 @@ class Context:
             flat = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
         calls = np.zeros(n, dtype=CALL_DTYPE)
         if n == 0:
-            return calls, b""
+            return calls, np.zeros(0, dtype=np.uint8)
         prm = HbParams(occ_cap, max_loci, flank, max_rows, TE_TYPES[te_type], int(plant),
                        1 if result_type == "cons" else 0, 1 if trunc_gate else 0, int(tb_budget_bytes))
         nbytes = C.c_uint64(0)
         self._check(self._lib.hb_adjust(self._h, n, _ptr(flat), _ptr(off), C.byref(prm), _ptr(calls), C.byref(nbytes)),
                     "hb_adjust")
-        cons = np.zeros(max(1, nbytes.value), dtype=np.uint8)
+        cons = np.empty(max(1, nbytes.value), dtype=np.uint8)
         self._check(self._lib.hb_last_cons(self._h, _ptr(cons), len(cons)), "hb_last_cons")
         self.last_calls = calls
-        return calls, cons[:nbytes.value].tobytes()
+        return calls, cons[:nbytes.value]
 
     def adjust(self, cand_seqs, *a, **kw):
         """Same as ``adjust_raw`` but returns a list of dicts mirroring ``is_TE_from_align_file``'s tuple
         (reference module/Util.py:10434-10437) per candidate."""
         calls, cons = self.adjust_raw(cand_seqs, *a, **kw)
-        return _calls_to_dicts(calls, cons)
+        return _calls_to_dicts(calls, cons.tobytes())
+
+    def last_cons_device(self):
+        """The consensus bytes of the last adjust, still on the GPU, as an object torch can wrap without a
+        copy (``torch.as_tensor(ctx.last_cons_device(), device='cuda')``); None when empty."""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        self._check(self._lib.hb_last_cons_device(self._h, C.byref(p), C.byref(n)), "hb_last_cons_device")
+        if not n.value:
+            return None
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "|u1", "data": (int(p.value), False),
+                                        "version": 2}
+        return _Dev()
 
     def last_copies(self):
         n = C.c_uint64(0)

@@ -61,6 +61,7 @@ extern "C" void hb_destroy(hb_ctx* ctx) {
         b->release();
     for (auto& kv : ctx->bufs) kv.second.release();
     ctx->h_stage.release();
+    ctx->h_cons.release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

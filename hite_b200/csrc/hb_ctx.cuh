@@ -62,7 +62,8 @@ struct hb_ctx {
     int k = 15, w = 10;
     std::vector<uint64_t> g_goff, g_glen;
     // results of the last hb_adjust kept for hb_last_* getters
-    std::vector<uint8_t> last_cons;
+    HbHostBuf h_cons;              // pinned copy of the dense consensus bytes of the last hb_adjust
+    uint64_t last_cons_bytes = 0;
     uint32_t last_ncand = 0, last_npairs = 0;
     std::vector<uint64_t> last_mat_off;
     std::vector<uint32_t> last_rows, last_cols;

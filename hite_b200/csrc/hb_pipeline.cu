@@ -37,6 +37,20 @@ __global__ void cons_compact_kernel(HbVoteCall* __restrict__ calls, uint32_t n, 
     __syncwarp();
     if (lane == 0) calls[c].cons_off = (int64_t)off[c];
 }
+// truncated-member gate (Util.py:10442-10446), resolved on the device before the consensus bytes are
+// compacted: a failed truncated pass overrides the full pass's verdict; truncated consensi are dropped
+__global__ void gate_resolve_kernel(HbVoteCall* __restrict__ calls, uint32_t n_full, uint32_t n_tasks,
+                                    const uint32_t* __restrict__ trunc_to_full) {
+    const uint32_t t = n_full + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    HbVoteCall c = calls[t];
+    if (!c.is_te) {
+        c.flags |= HB_FLAG_TRUNC_REJECT;
+        c.cons_len = 0;
+        calls[trunc_to_full[t - n_full]] = c;
+    }
+    calls[t].cons_len = 0;
+}
 __global__ void clen_kernel(const uint64_t* __restrict__ coff, uint32_t n, uint32_t* __restrict__ clen) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) clen[i] = (uint32_t)(coff[i + 1] - coff[i]);
@@ -423,6 +437,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     std::vector<uint64_t> h_mat_off(n_cand + 1, 0), h_tmat_off(n_cand + 1, 0);
     std::vector<HbVoteTask> tasks;
     std::vector<uint32_t> task_cand;          // candidate of each task; trunc tasks follow the full ones
+    std::vector<uint32_t> trunc_to_full, full_of_cand(n_cand, 0);
     tasks.reserve(2 * (size_t)n_cand); task_cand.reserve(2 * (size_t)n_cand);
     uint64_t mat_total = 0, col_total = 0, match_total = 0, row_total = 0;
     auto add_task = [&](uint32_t c, uint32_t rows, uint64_t off) {
@@ -442,6 +457,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     for (uint32_t c = 0; c < n_cand; ++c) {
         h_mat_off[c] = mat_total;
         if (h_rows[c] == 0) continue;
+        full_of_cand[c] = (uint32_t)tasks.size();
         add_task(c, h_rows[c], mat_total);
         mat_total += (uint64_t)h_rows[c] * h_cols[c];
     }
@@ -451,6 +467,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     for (uint32_t c = 0; c < n_cand; ++c) {
         h_tmat_off[c] = mat_total;
         if (h_rows[c] == 0 || h_trows[c] == 0) continue;
+        trunc_to_full.push_back(full_of_cand[c]);
         add_task(c, h_trows[c], mat_total);
         mat_total += (uint64_t)h_trows[c] * h_cols[c];
     }
@@ -477,7 +494,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     // ---- kernel (iii): clean + judge ---------------------------------------------------------------
     std::vector<HbVoteCall> h_calls(n_tasks);
     uint64_t dense_total = 0;
-    ctx->last_cons.clear();
+    ctx->last_cons_bytes = 0;
     if (n_tasks > 0) {
         ENSURE("v.tasks", sizeof(HbVoteTask) * n_tasks);
         ENSURE("v.clean", mat_total + 1);
@@ -497,6 +514,13 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
                                   ctx->buf("v.anchors").as<int>(), ctx->buf("c.ascii").as<uint8_t>(),
                                   ctx->buf("v.cons").as<uint8_t>(), ctx->buf("v.calls").as<HbVoteCall>(), prm->te_type, s));
         HB_CUDA_OK(cudaEventRecord(ctx->ev[5], s));
+        if (n_tasks > n_full) {
+            ENSURE("v.t2f", sizeof(uint32_t) * trunc_to_full.size());
+            HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("v.t2f").p, trunc_to_full.data(), sizeof(uint32_t) * trunc_to_full.size(), cudaMemcpyHostToDevice, s));
+            gate_resolve_kernel<<<(n_tasks - n_full + 255) / 256, 256, 0, s>>>(ctx->buf("v.calls").as<HbVoteCall>(), n_full, n_tasks,
+                                                                              ctx->buf("v.t2f").as<uint32_t>());
+            ++launches;
+        }
         u32_field_kernel<<<(n_tasks + 255) / 256, 256, 0, s>>>(ctx->buf("v.calls").as<HbVoteCall>(), n_tasks, ctx->buf("v.len").as<uint32_t>());
         HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("v.len").as<uint32_t>(), ctx->buf("v.off").as<uint32_t>(), n_tasks,
                                          ctx->buf("v.scan_tmp").as<uint32_t>(), ctx->buf("v.total").as<uint64_t>(), s));
@@ -506,14 +530,15 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         launches += 7;
         HB_CUDA_OK(cudaEventRecord(ctx->ev[6], s));
         HB_CUDA_OK(cudaMemcpyAsync(&dense_total, ctx->buf("v.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        HB_CUDA_OK(cudaMemcpyAsync(h_calls.data(), ctx->buf("v.calls").p, sizeof(HbVoteCall) * n_tasks, cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaMemcpyAsync(h_calls.data(), ctx->buf("v.calls").p, sizeof(HbVoteCall) * n_full, cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
-        ctx->last_cons.resize(dense_total);
+        HB_CUDA_OK(ctx->h_cons.ensure(dense_total + 1));
+        ctx->last_cons_bytes = dense_total;
         if (dense_total)
-            HB_CUDA_OK(cudaMemcpyAsync(ctx->last_cons.data(), ctx->buf("v.dense").p, dense_total, cudaMemcpyDeviceToHost, s));
+            HB_CUDA_OK(cudaMemcpyAsync(ctx->h_cons.p, ctx->buf("v.dense").p, dense_total, cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaEventRecord(ctx->ev[7], s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
-        tm.d2h_bytes += dense_total + sizeof(HbVoteCall) * n_tasks;
+        tm.d2h_bytes += dense_total + sizeof(HbVoteCall) * n_full;
     } else {
         HB_CUDA_OK(cudaEventRecord(ctx->ev[5], s));
         HB_CUDA_OK(cudaEventRecord(ctx->ev[6], s));
@@ -529,14 +554,6 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         o.flags = HB_FLAG_NO_COPIES;
     }
     for (uint32_t t = 0; t < n_full; ++t) memcpy(&calls[task_cand[t]], &h_calls[t], sizeof(hb_call));
-    // truncated-member gate (Util.py:10442-10446): a candidate whose truncated members fail is rejected
-    // with the truncated pass's verdict; otherwise the full pass decides
-    for (uint32_t t = n_full; t < n_tasks; ++t) {
-        if (h_calls[t].is_te) continue;
-        hb_call& o = calls[task_cand[t]];
-        memcpy(&o, &h_calls[t], sizeof(hb_call));
-        o.flags |= HB_FLAG_TRUNC_REJECT;
-    }
     if (cons_bytes) *cons_bytes = dense_total;
     ctx->last_ncand = n_cand; ctx->last_npairs = n_pairs;
     ctx->last_mat_off = h_mat_off; ctx->last_rows = h_rows; ctx->last_cols = h_cols;
@@ -558,8 +575,15 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
 
 extern "C" int hb_last_cons(hb_ctx* ctx, uint8_t* out, uint64_t cap) {
     if (!ctx || !out) return HB_EINVAL;
-    if (cap < ctx->last_cons.size()) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_cons: buffer too small");
-    if (!ctx->last_cons.empty()) memcpy(out, ctx->last_cons.data(), ctx->last_cons.size());
+    if (cap < ctx->last_cons_bytes) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_cons: buffer too small");
+    if (ctx->last_cons_bytes) memcpy(out, ctx->h_cons.p, ctx->last_cons_bytes);
+    return HB_OK;
+}
+
+extern "C" int hb_last_cons_device(hb_ctx* ctx, const void** dptr, uint64_t* nbytes) {
+    if (!ctx || !dptr || !nbytes) return HB_EINVAL;
+    *nbytes = ctx->last_cons_bytes;
+    *dptr = ctx->last_cons_bytes ? ctx->buf("v.dense").p : nullptr;
     return HB_OK;
 }
 

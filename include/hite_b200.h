@@ -152,6 +152,9 @@ typedef struct {
 int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii, const uint64_t* cand_off,
               const hb_params* prm, hb_call* calls, uint64_t* cons_bytes);
 int hb_last_cons(hb_ctx* ctx, uint8_t* out, uint64_t cap);
+/* device-resident copy of the same bytes (valid until the next hb_adjust on this context): lets the
+ * multi-GPU merge all-gather the records over NVLink without a host round trip */
+int hb_last_cons_device(hb_ctx* ctx, const void** dptr, uint64_t* nbytes);
 /* copies of the last hb_adjust, ordered by (candidate, rank); pass out=NULL to query the count */
 int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t* n);
 
