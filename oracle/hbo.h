@@ -65,6 +65,13 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
                       const uint8_t *cand_ascii, int L, int occ_cap, int max_loci, int flank, int max_rows,
                       hbo_copy *copies, int *n_copies, uint8_t *matrix, uint64_t matrix_cap, int *R_out, int *C_out);
 
+/* ---- FMEA restatement (hbo_fmea.c) ---- */
+typedef struct { int32_t subj, qs, qe, ss, se; } hbo_hsp;            /* 1-based inclusive, s_start > s_end = reverse */
+typedef struct { int32_t chr, pad; int64_t start, end; } hbo_interval; /* 'chr:start-end', 0-based half open */
+int hbo_fmea(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_subj,
+             const int32_t *subj_chr, const int64_t *subj_seg_start, int n_subj,
+             int skip_gap, int max_len, hbo_interval *out, int cap);
+
 typedef struct { int32_t is_te, info, copy_num, cons_len; } hbo_result;
 int hbo_run_batch(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w, const uint8_t *cand_ascii,
                   const uint64_t *coff, uint32_t n_cand, int occ_cap, int max_loci, int flank, int max_rows, int plant,

@@ -1,0 +1,198 @@
+/*
+ * TEST INFRASTRUCTURE (oracle) -- NOT part of the product path.
+ *
+ * Plain C restatement of the reference's FMEA interval chaining for the coarse-boundary stage:
+ *   get_longest_repeats_v4   module/Util.py:4122-4400
+ *   get_overlap_len          module/Util.py:4402-4405
+ *   get_integer_pos          module/Util.py:4566-4569
+ *   process_all_seqs / process_seq_group   module/Util.py:4529-4563
+ * for ONE query segment (one `.final.out` file of process_blast_alignments, module/Util.py:4763-4770).
+ * Pinned against tests/golden/fmea.json.gz, produced by the imported, unmodified reference function.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hbo.h"
+
+typedef struct { int32_t qs, qe, ss, se; int order; } frag_t;
+
+static int cmp_fwd(const void *a, const void *b) {          /* key (s_start, s_end), stable */
+    const frag_t *x = (const frag_t *)a, *y = (const frag_t *)b;
+    if (x->ss != y->ss) return x->ss < y->ss ? -1 : 1;
+    if (x->se != y->se) return x->se < y->se ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int cmp_rev(const void *a, const void *b) {          /* key (-s_start, -s_end), stable */
+    const frag_t *x = (const frag_t *)a, *y = (const frag_t *)b;
+    if (x->ss != y->ss) return x->ss > y->ss ? -1 : 1;
+    if (x->se != y->se) return x->se > y->se ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int cmp_q(const void *a, const void *b) {            /* key (q_start, q_end), stable */
+    const frag_t *x = (const frag_t *)a, *y = (const frag_t *)b;
+    if (x->qs != y->qs) return x->qs < y->qs ? -1 : 1;
+    if (x->qe != y->qe) return x->qe < y->qe ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int same_frag(const frag_t *a, const frag_t *b) {
+    return a->qs == b->qs && a->qe == b->qe && a->ss == b->ss && a->se == b->se;
+}
+
+typedef struct { int32_t qs, qe, ss, se, subj; } longest_t;
+
+/* chain one cluster (:4229-4319), append to lq */
+static void chain_cluster(frag_t *c, int n, int skip_gap, int subj, longest_t **lq, int *nlq, int *caplq) {
+    for (int i = 0; i < n; ++i) c[i].order = i;
+    qsort(c, (size_t)n, sizeof(frag_t), cmp_q);                                  /* :4231 */
+    uint8_t *visited = (uint8_t *)calloc((size_t)n + 1, 1);
+    for (int i = 0; i < n; ++i) {
+        if (visited[i]) continue;
+        int32_t pqs = c[i].qs, pqe = c[i].qe, pss = c[i].ss, pse = c[i].se;
+        for (int t = 0; t < n; ++t) if (same_frag(&c[t], &c[i])) visited[t] = 1;   /* dict keyed by the tuple */
+        for (int j = i + 1; j < n; ++j) {
+            if (visited[j]) continue;
+            const int32_t cqs = c[j].qs, cqe = c[j].qe, css = c[j].ss, cse = c[j].se;
+            if (cqe > pqe) {                                                      /* :4278 */
+                if (pss < pse && css < cse) {
+                    if (cse > pse) {
+                        if (cqs - pqe < skip_gap && cqe > pqe && css - pse < skip_gap) {
+                            pqe = cqe; pss = pss < css ? pss : css; pse = cse;
+                            for (int t = 0; t < n; ++t) if (same_frag(&c[t], &c[j])) visited[t] = 1;
+                        } else if (cqs - pqe >= skip_gap) break;
+                    }
+                } else if (pss > pse && css > cse) {
+                    if (cse < pse) {
+                        if (cqs - pqe < skip_gap && cqe > pqe && pse - css < skip_gap) {
+                            pqe = cqe; pss = pss > css ? pss : css; pse = cse;
+                            for (int t = 0; t < n; ++t) if (same_frag(&c[t], &c[j])) visited[t] = 1;
+                        } else if (cqs - pqe >= skip_gap) break;
+                    }
+                }
+            }
+        }
+        if (*nlq == *caplq) { *caplq = *caplq * 2 + 16; *lq = (longest_t *)realloc(*lq, sizeof(longest_t) * (size_t)*caplq); }
+        longest_t *o = &(*lq)[(*nlq)++];
+        o->qs = pqs; o->qe = pqe; o->ss = pss; o->se = pse; o->subj = subj;
+    }
+    free(visited);
+}
+
+/* tiny open-addressing set of (chr, start, end) */
+typedef struct { int32_t chr; int64_t a, b; int used; } key_t;
+typedef struct { key_t *t; size_t cap, n; } set_t;
+static size_t key_hash(int32_t chr, int64_t a, int64_t b) {
+    uint64_t h = (uint64_t)chr * 0x9E3779B97F4A7C15ull ^ (uint64_t)a * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)b * 0x165667B19E3779F9ull;
+    h ^= h >> 29; return (size_t)h;
+}
+static int set_has(const set_t *s, int32_t chr, int64_t a, int64_t b) {
+    size_t i = key_hash(chr, a, b) & (s->cap - 1);
+    while (s->t[i].used) { if (s->t[i].chr == chr && s->t[i].a == a && s->t[i].b == b) return 1; i = (i + 1) & (s->cap - 1); }
+    return 0;
+}
+static void set_add(set_t *s, int32_t chr, int64_t a, int64_t b) {
+    if ((s->n + 1) * 2 > s->cap) {
+        set_t ns; ns.cap = s->cap * 2; ns.n = 0; ns.t = (key_t *)calloc(ns.cap, sizeof(key_t));
+        for (size_t i = 0; i < s->cap; ++i) if (s->t[i].used) set_add(&ns, s->t[i].chr, s->t[i].a, s->t[i].b);
+        free(s->t); *s = ns;
+    }
+    size_t i = key_hash(chr, a, b) & (s->cap - 1);
+    while (s->t[i].used) { if (s->t[i].chr == chr && s->t[i].a == a && s->t[i].b == b) return; i = (i + 1) & (s->cap - 1); }
+    s->t[i].chr = chr; s->t[i].a = a; s->t[i].b = b; s->t[i].used = 1; s->n++;
+}
+
+typedef struct { int64_t a, b; int order; } iv_t;
+static int cmp_len_desc(const void *x, const void *y) {      /* sort by length desc, stable */
+    const iv_t *p = (const iv_t *)x, *q = (const iv_t *)y;
+    int64_t lp = p->b - p->a, lq = q->b - q->a;
+    if (lp != lq) return lp > lq ? -1 : 1;
+    return (p->order > q->order) - (p->order < q->order);
+}
+
+int hbo_fmea(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_subj,
+             const int32_t *subj_chr, const int64_t *subj_seg_start, int n_subj,
+             int skip_gap, int max_len, hbo_interval *out, int cap) {
+    /* subjects in first-appearance order (:4140-4147) */
+    int *order = (int *)malloc(sizeof(int) * (size_t)(n_subj + 1));
+    int *seen = (int *)calloc((size_t)n_subj + 1, sizeof(int));
+    int n_order = 0;
+    for (int i = 0; i < n; ++i) {
+        if (h[i].subj == self_subj && h[i].qs == h[i].ss && h[i].qe == h[i].se) continue;   /* :4138 */
+        if (!seen[h[i].subj]) { seen[h[i].subj] = 1; order[n_order++] = h[i].subj; }
+    }
+    longest_t *lq = NULL; int nlq = 0, caplq = 0;
+    frag_t *fw = (frag_t *)malloc(sizeof(frag_t) * (size_t)(n + 1)), *rv = (frag_t *)malloc(sizeof(frag_t) * (size_t)(n + 1));
+    frag_t *cl = (frag_t *)malloc(sizeof(frag_t) * (size_t)(n + 1));
+    for (int oi = 0; oi < n_order; ++oi) {
+        const int s = order[oi];
+        int nf = 0, nr = 0;
+        for (int i = 0; i < n; ++i) {
+            if (h[i].subj != s) continue;
+            if (s == self_subj && h[i].qs == h[i].ss && h[i].qe == h[i].se) continue;
+            frag_t f = {h[i].qs, h[i].qe, h[i].ss, h[i].se, 0};
+            if (f.ss > f.se) { f.order = nr; rv[nr++] = f; } else { f.order = nf; fw[nf++] = f; }      /* :4168-4172 */
+        }
+        qsort(fw, (size_t)nf, sizeof(frag_t), cmp_fwd);
+        qsort(rv, (size_t)nr, sizeof(frag_t), cmp_rev);
+        for (int pass = 0; pass < 2; ++pass) {                       /* forward clusters, then reverse (:4178-4227) */
+            frag_t *p = pass ? rv : fw; const int np = pass ? nr : nf;
+            int nc = 0;
+            for (int k = 0; k < np; ++k) {
+                int closed = 0;
+                if (k > 0) {
+                    for (int e = nc - 1; e >= 0; --e) {
+                        const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
+                        if (gap < skip_gap && p[k].qe > cl[e].qe) { closed = 1; break; }
+                    }
+                }
+                if (k == 0 || closed) cl[nc++] = p[k];
+                else { chain_cluster(cl, nc, skip_gap, s, &lq, &nlq, &caplq); nc = 0; cl[nc++] = p[k]; }
+            }
+            if (nc > 0) chain_cluster(cl, nc, skip_gap, s, &lq, &nlq, &caplq);
+        }
+    }
+    /* position de-duplication (:4330-4390) */
+    set_t set; set.cap = 1024; set.n = 0; set.t = (key_t *)calloc(set.cap, sizeof(key_t));
+    iv_t *names = (iv_t *)malloc(sizeof(iv_t) * (size_t)(nlq + 1));
+    int nn = 0;
+    for (int r = 0; r < nlq; ++r) {
+        const int32_t schr = subj_chr[lq[r].subj];
+        const int64_t sa = subj_seg_start[lq[r].subj] + (lq[r].ss - 1), sb = subj_seg_start[lq[r].subj] + lq[r].se;
+        const int64_t qa = q_seg_start + (lq[r].qs - 1), qb = q_seg_start + lq[r].qe;
+        const int64_t sa1 = (sa / 10) * 10, sa2 = sa1 + 10, sb1 = (sb / 10) * 10, sb2 = sb1 + 10;
+        const int64_t qa1 = (qa / 10) * 10, qa2 = qa1 + 10, qb1 = (qb / 10) * 10, qb2 = qb1 + 10;
+        const int64_t qlen = lq[r].qe - (lq[r].qs - 1) >= 0 ? lq[r].qe - (lq[r].qs - 1) : -(lq[r].qe - (lq[r].qs - 1));
+        const int hit = set_has(&set, schr, sa1, sb1) || set_has(&set, schr, sa1, sb2) || set_has(&set, schr, sa2, sb1) ||
+                        set_has(&set, schr, sa2, sb2) || set_has(&set, q_chr, qa1, qb1) || set_has(&set, q_chr, qa1, qb2) ||
+                        set_has(&set, q_chr, qa2, qb1) || set_has(&set, q_chr, qa2, qb2);
+        if (!hit && qlen >= 80 && qlen < max_len) { names[nn].a = qa; names[nn].b = qb; names[nn].order = nn; ++nn; }
+        set_add(&set, schr, sa1, sb1); set_add(&set, schr, sa1, sb2); set_add(&set, schr, sa2, sb1); set_add(&set, schr, sa2, sb2);
+        set_add(&set, q_chr, qa1, qb1); set_add(&set, q_chr, qa1, qb2); set_add(&set, q_chr, qa2, qb1); set_add(&set, q_chr, qa2, qb2);
+    }
+    /* process_all_seqs on one chromosome (all names carry the query's chromosome) (:4529-4563) */
+    qsort(names, (size_t)nn, sizeof(iv_t), cmp_len_desc);
+    uint8_t *keep = (uint8_t *)malloc((size_t)nn + 1);
+    memset(keep, 1, (size_t)nn + 1);
+    for (int i = 0; i < nn; ++i) {
+        if (!keep[i]) continue;
+        for (int j = i + 1; j < nn; ++j) {
+            if (!keep[j]) continue;
+            int64_t lo = names[i].a > names[j].a ? names[i].a : names[j].a;
+            int64_t hi = names[i].b < names[j].b ? names[i].b : names[j].b;
+            int64_t ov = hi - lo > 0 ? hi - lo : 0;
+            if ((double)ov / (double)(names[j].b - names[j].a) >= 0.95) keep[j] = 0;
+        }
+    }
+    int no = 0;
+    for (int i = 0; i < nn; ++i) {
+        if (!keep[i]) continue;
+        /* longest_repeats is a dict keyed by the name: a repeated name keeps its first position */
+        int dup = 0;
+        for (int t = 0; t < no; ++t) if (out[t].start == names[i].a && out[t].end == names[i].b) { dup = 1; break; }
+        if (dup) continue;
+        if (no < cap) { out[no].chr = q_chr; out[no].start = names[i].a; out[no].end = names[i].b; }
+        ++no;
+    }
+    free(keep); free(names); free(set.t); free(lq); free(fw); free(rv); free(cl); free(order); free(seen);
+    return no;
+}

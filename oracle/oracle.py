@@ -113,6 +113,32 @@ def judge_with_trunc_gate(cand, copies, rows, judge=None, plant=1):
     return judge(cand, remove_sparse_cols(rows))
 
 
+class HboHsp(C.Structure):
+    _fields_ = [("subj", C.c_int32), ("qs", C.c_int32), ("qe", C.c_int32), ("ss", C.c_int32), ("se", C.c_int32)]
+
+
+class HboInterval(C.Structure):
+    _fields_ = [("chr", C.c_int32), ("pad", C.c_int32), ("start", C.c_int64), ("end", C.c_int64)]
+
+
+def fmea(query, subjects, self_subj, hsps, skip_gap, max_len):
+    """get_longest_repeats_v4 for one query segment -> ['chr:start-end', ...] in the reference's order."""
+    chr_ids = {}
+    for name in [query[0]] + [s[0] for s in subjects]:
+        chr_ids.setdefault(name, len(chr_ids))
+    n = len(hsps)
+    arr = (HboHsp * max(1, n))(*[HboHsp(*h) for h in hsps])
+    sc = (C.c_int32 * max(1, len(subjects)))(*[chr_ids[s[0]] for s in subjects])
+    so = (C.c_int64 * max(1, len(subjects)))(*[s[1] for s in subjects])
+    cap = n + 8
+    out = (HboInterval * cap)()
+    L = lib()
+    L.hbo_fmea.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                           C.c_int, C.c_void_p, C.c_int]
+    k = L.hbo_fmea(arr, n, chr_ids[query[0]], query[1], self_subj, sc, so, len(subjects), skip_gap, max_len, out, cap)
+    return ["%s:%d-%d" % (query[0], out[i].start, out[i].end) for i in range(k)]
+
+
 def find_near_matches_ends(p, s, d):
     fs, fe, ls, le = C.c_int(-1), C.c_int(-1), C.c_int(-1), C.c_int(-1)
     n = lib().hbo_find_near_matches(p.encode(), len(p), s.encode(), len(s), d,

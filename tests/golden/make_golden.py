@@ -84,6 +84,19 @@ def run_reference_v9(U, case, tmpdir):
     return dict(clean_rows=[contigs[n] for n in names], is_te=bool(is_te), info=info, cons=cons, copy_num=copy_num)
 
 
+def run_reference_fmea(U, case, tmpdir):
+    """get_longest_repeats_v4 (Util.py:4122) on a synthetic outfmt-6 file of one query segment."""
+    path = os.path.join(tmpdir, "q.final.out")
+    qn = "%s$%d" % case["query"]
+    with open(path, "w") as f:
+        for (si, qs, qe, ss, se) in case["hsps"]:
+            sn = "%s$%d" % tuple(case["subjects"][si])
+            f.write("\t".join([qn, sn, "95.0", str(abs(qe - qs) + 1), "0", "0", str(qs), str(qe), str(ss), str(se), "1e-50", "200"]) + "\n")
+    out = U.get_longest_repeats_v4(path, case["skip_gap"], case["max_len"], 0)
+    d = U.load_from_file(out)
+    return list(d.keys())
+
+
 def write(path, out):
     with gzip.GzipFile(path, "wb", mtime=0) as f:
         f.write(json.dumps(out, separators=(",", ":")).encode())
@@ -109,6 +122,17 @@ def main():
             out.append(dict(seed=seed, scenario=case["scenario"], cand=case["cand"], plant=case["plant"],
                             rows=case["rows"], truth=case["truth"], expect=exp))
         write(os.path.join(ROOT, "tests", "golden", "judge_v9.json.gz"), out)
+    with tempfile.TemporaryDirectory() as td:
+        recs = []
+        for seed in range(1, 201):
+            case = msa_synth.synth_hsps(seed)
+            case["expect"] = run_reference_fmea(U, case, td)
+            case["seed"] = seed
+            recs.append(case)
+        path = os.path.join(ROOT, "tests", "golden", "fmea.json.gz")
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(json.dumps(recs, separators=(",", ":")).encode())
+        print("wrote", path, len(recs), "cases;", sum(len(r["expect"]) for r in recs), "intervals;", os.path.getsize(path), "bytes")
     out = []
     with tempfile.TemporaryDirectory() as td:
         seeds = list(range(1, 161))

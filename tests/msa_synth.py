@@ -234,3 +234,62 @@ def synth_case_nonltr(seed, scenario=None):
     elif scen == "no_anchor":
         cand = rand_seq(rng, length)
     return dict(cand=cand, rows=rows, plant=1, te_type="non_ltr", scenario=scen, truth=elem)
+
+
+def synth_hsps(seed):
+    """Synthetic BLAST-outfmt-6 style HSP list of ONE query segment against several subject segments for the
+    FMEA chaining tests (reference get_longest_repeats_v4, module/Util.py:4122).  Returns dict(query=(chr,off),
+    subjects=[(chr,off)], self_subj=index|-1, hsps=[(subj,qs,qe,ss,se)], skip_gap, max_len)."""
+    rng = random.Random(seed)
+    chrs = ["chr1", "chr2", "chr3"]
+    query = (rng.choice(chrs), rng.choice([0, 1_000_000, 2_000_000]))
+    subjects = []
+    while len(subjects) < rng.randint(2, 5):
+        s = (rng.choice(chrs), rng.choice([0, 1_000_000, 2_000_000, 3_000_000]))
+        if s not in subjects:
+            subjects.append(s)
+    self_subj = -1
+    if rng.random() < 0.7:
+        if query in subjects:
+            self_subj = subjects.index(query)
+        else:
+            subjects.append(query)
+            self_subj = len(subjects) - 1
+    skip_gap = rng.choice([200, 2000, 4000])
+    hsps = []
+    for fam in range(rng.randint(2, 7)):
+        flen = rng.randint(100, 6000)
+        qcopies = [rng.randint(1, 990_000 - flen) for _ in range(rng.randint(1, 3))]
+        for si in range(len(subjects)):
+            for _ in range(rng.randint(0, 3)):
+                spos = rng.randint(1, 990_000 - flen)
+                strand = rng.random() < 0.4
+                for qpos in qcopies:
+                    # one alignment, possibly broken into pieces separated by small/large gaps
+                    pieces = rng.randint(1, 4)
+                    cuts = sorted(rng.sample(range(20, flen - 20), pieces - 1)) if pieces > 1 and flen > 60 else []
+                    bounds = [0] + cuts + [flen]
+                    qshift = sshift = 0
+                    for a, b in zip(bounds[:-1], bounds[1:]):
+                        if b - a < 12:
+                            continue
+                        g1 = rng.choice([0, 0, 5, 50, 300, skip_gap + 10])
+                        g2 = rng.choice([0, 0, 5, 50, 300, skip_gap + 10])
+                        qshift += g1; sshift += g2
+                        qs, qe = qpos + a + qshift, qpos + b - 1 + qshift
+                        if not strand:
+                            ss, se = spos + a + sshift, spos + b - 1 + sshift
+                        else:
+                            ss, se = spos + flen - a + 6000 - sshift, spos + flen - b + 1 + 6000 - sshift
+                        if qe > 1_000_000 or max(ss, se) > 1_000_000 or min(ss, se) < 1:
+                            continue
+                        hsps.append((si, qs, qe, ss, se))
+                        if rng.random() < 0.1:
+                            hsps.append((si, qs, qe, ss, se))            # exact duplicate line
+    if self_subj >= 0:
+        for _ in range(rng.randint(1, 3)):                               # self hits that must be skipped
+            a = rng.randint(1, 900_000); b = a + rng.randint(100, 5000)
+            hsps.append((self_subj, a, b, a, b))
+    rng.shuffle(hsps)
+    return dict(query=query, subjects=subjects, self_subj=self_subj, hsps=hsps, skip_gap=skip_gap,
+                max_len=rng.choice([30000, 3000]))

@@ -85,3 +85,14 @@ def test_oracle_judge_v9_matches_reference_goldens(golden_v9):
         r = oracle.judge_v9(rec["cand"], clean)
         for k in ("is_te", "info", "cons", "copy_num"):
             assert r[k] == exp[k], (rec["seed"], rec["scenario"], k)
+
+
+def test_oracle_fmea_matches_reference_goldens():
+    import gzip, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    recs = json.loads(gzip.open(os.path.join(root, "tests", "golden", "fmea.json.gz")).read())
+    assert len(recs) >= 150
+    for rec in recs:
+        r = oracle.fmea(tuple(rec["query"]), [tuple(s) for s in rec["subjects"]], rec["self_subj"],
+                        [tuple(h) for h in rec["hsps"]], rec["skip_gap"], rec["max_len"])
+        assert r == rec["expect"], rec["seed"]
