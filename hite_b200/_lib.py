@@ -44,6 +44,31 @@ COPY_DTYPE = np.dtype([("cand", "<u4"), ("rank", "<i4"), ("rel", "<i4"), ("nseed
 assert COPY_DTYPE.itemsize == 88
 
 
+HSP_DTYPE = np.dtype([("subj", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("ss", "<i4"), ("se", "<i4")])
+SEG_DTYPE = np.dtype([("chr", "<i4"), ("pad", "<i4"), ("start", "<i8")])
+INTERVAL_DTYPE = np.dtype([("chr", "<i4"), ("qseg", "<i4"), ("start", "<i8"), ("end", "<i8")])
+
+
+def fmea_chain(hsps, q_off, segs, skip_gap, max_len, threads=1):
+    """FMEA interval chaining (reference get_longest_repeats_v4 + process_all_seqs) on HSP arrays:
+    ``hsps`` HSP_DTYPE grouped by query segment, ``q_off`` uint64 [n_seg+1], ``segs`` SEG_DTYPE."""
+    lib = load()
+    hsps = np.ascontiguousarray(hsps, dtype=HSP_DTYPE)
+    q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+    segs = np.ascontiguousarray(segs, dtype=SEG_DTYPE)
+    n = C.c_uint64(0)
+    rc = lib.hb_fmea_chain(_ptr(hsps), _ptr(q_off), len(segs), _ptr(segs), int(skip_gap), int(max_len), int(threads), None, 0,
+                           C.byref(n))
+    if rc != 0:
+        raise HiteB200Error("hb_fmea_chain failed (%d)" % rc)
+    out = np.zeros(max(1, n.value), dtype=INTERVAL_DTYPE)
+    rc = lib.hb_fmea_chain(_ptr(hsps), _ptr(q_off), len(segs), _ptr(segs), int(skip_gap), int(max_len), int(threads), _ptr(out),
+                           len(out), C.byref(n))
+    if rc != 0:
+        raise HiteB200Error("hb_fmea_chain failed (%d)" % rc)
+    return out[:n.value]
+
+
 class HbTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("k_ms", C.c_float * 8), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
@@ -85,6 +110,9 @@ def load():
     lib.hb_last_copies.argtypes = [vp, vp, C.c_uint64, u64p]
     lib.hb_debug_index.argtypes = [vp, vp, C.c_uint64]
     lib.hb_last_msa.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
+    lib.hb_fmea_chain.argtypes = [vp, vp, C.c_uint32, vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
+    lib.hb_coarse_boundary.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
+    lib.hb_last_hsps.argtypes = [vp, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     _LIB = lib
     return lib
 
@@ -269,3 +297,24 @@ class Context:
         self._check(self._lib.hb_last_msa(self._h, cand, _ptr(buf), len(buf), C.byref(R), C.byref(Cn)), "hb_last_msa")
         raw = buf.tobytes()
         return [raw[r * Cn.value:(r + 1) * Cn.value].decode() for r in range(R.value)]
+
+    # ------------------------------------------------------------------------------------
+    def coarse_boundary(self, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=8):
+        """The all-vs-all + FMEA step of ``determine_repeat_boundary_v5`` (reference module/Util.py:4657-4663) on
+        the loaded genome -> INTERVAL_DTYPE array ('chr:start-end', 0-based half open)."""
+        n = C.c_uint64(0)
+        self._check(self._lib.hb_coarse_boundary(self._h, int(seg_len), int(skip_gap), int(max_len), int(occ_cap), int(threads),
+                                                 None, 0, C.byref(n)), "hb_coarse_boundary")
+        # the first call already ran the GPU stage; fetch by re-running the cheap host stage on the cached HSPs
+        hsps, q_off, segs = self.last_hsps()
+        return fmea_chain(hsps, q_off, segs, skip_gap, max_len, threads)
+
+    def last_hsps(self):
+        n, ns = C.c_uint64(0), C.c_uint32(0)
+        self._check(self._lib.hb_last_hsps(self._h, None, 0, C.byref(n), None, None, 0, C.byref(ns)), "hb_last_hsps")
+        hsps = np.zeros(max(1, n.value), dtype=HSP_DTYPE)
+        q_off = np.zeros(ns.value + 1, dtype=np.uint64)
+        segs = np.zeros(max(1, ns.value), dtype=SEG_DTYPE)
+        self._check(self._lib.hb_last_hsps(self._h, _ptr(hsps), len(hsps), C.byref(n), _ptr(q_off), _ptr(segs), len(segs),
+                                           C.byref(ns)), "hb_last_hsps")
+        return hsps[:n.value], q_off, segs[:ns.value]

@@ -1,0 +1,22 @@
+// hite_b200 -- coarse-boundary HSP generation launchers (hb_coarse.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HB_COARSE_BUCKET_BITS 22
+
+struct HbHspRec { int32_t qseg, subj, qs, qe, ss, se, pad; };
+
+cudaError_t hb_pair_count_launch(const uint64_t* mm, uint32_t n_mm, const uint64_t* idx, const uint32_t* bucket,
+                                 int occ_cap, uint32_t* lo, uint32_t* cnt, cudaStream_t s);
+cudaError_t hb_pair_fill_launch(const uint64_t* mm, uint32_t n_mm, const uint64_t* idx, uint64_t n_idx, uint64_t tot, int k, int occ_cap,
+                                const uint32_t* lo, const uint32_t* cnt, const uint32_t* off, uint64_t* keys,
+                                cudaStream_t s);
+cudaError_t hb_hsp_flag_launch(const uint64_t* keys, uint64_t n, const uint64_t* mm, uint64_t tot, int k,
+                               const uint64_t* seg_goff, int n_seg, uint32_t* flag, cudaStream_t s);
+cudaError_t hb_hsp_start_launch(const uint32_t* flag, const uint32_t* rid, uint64_t n, uint32_t* run_start, cudaStream_t s);
+cudaError_t hb_hsp_emit_launch(const uint64_t* keys, uint64_t n, const uint32_t* run_start, uint32_t n_runs,
+                               const uint64_t* mm, uint64_t tot, int k, const uint64_t* seg_goff, int n_seg,
+                               HbHspRec* recs, uint32_t* keep, cudaStream_t s);
+cudaError_t hb_hsp_compact_launch(const HbHspRec* recs, const uint32_t* keep, const uint32_t* pos, uint32_t n_runs,
+                                  HbHspRec* out, cudaStream_t s);

@@ -66,6 +66,9 @@ struct hb_ctx {
     uint64_t last_cons_bytes = 0;
     uint32_t last_ncand = 0, last_npairs = 0;
     std::vector<uint64_t> last_mat_off;
+    std::vector<hb_hsp> last_hsps;            // last hb_coarse_boundary: HSPs grouped by query segment
+    std::vector<uint64_t> last_hsp_off;
+    std::vector<hb_segment> last_segs;
     std::vector<uint32_t> last_rows, last_cols;
 };
 

@@ -1,0 +1,171 @@
+// hite_b200 -- FMEA interval chaining of the coarse-boundary stage (host C++, inside the C-ABI library).
+//
+// Replaces get_longest_repeats_v4 (reference module/Util.py:4122-4400) with process_all_seqs
+// (module/Util.py:4529-4563): per query segment, HSPs are grouped by subject and strand, clustered
+// along the subject, greedily chained along the query within `fixed_extend_base_threshold`, the
+// resulting query intervals are de-duplicated on 10-bp-rounded positions and on >= 95 % overlap.
+// Why host code: the chaining is a data-dependent greedy walk over tiny sorted lists whose
+// de-duplication is order-dependent (a Python dict filled in visiting order); there is no data
+// parallelism inside a query segment, so query segments are the parallel grain (std::thread pool here,
+// ProcessPoolExecutor in the reference, module/Util.py:4773).  The HSPs themselves come from the GPU
+// (hb_coarse.cu).  Results are bit-identical to the reference on the same HSP list (tests/golden/fmea.json.gz).
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <thread>
+#include <unordered_set>
+#include <vector>
+
+#include "hb_fmea.cuh"
+
+namespace {
+
+struct Frag { int32_t qs, qe, ss, se; };
+
+struct Chain { int32_t qs, qe, ss, se, subj; };
+
+// greedy extension inside one subject cluster (module/Util.py:4229-4319)
+void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Chain>& out) {
+    std::stable_sort(c.begin(), c.end(), [](const Frag& a, const Frag& b) {
+        return a.qs != b.qs ? a.qs < b.qs : a.qe < b.qe;
+    });
+    const size_t n = c.size();
+    std::vector<char> used(n, 0);
+    auto mark = [&](size_t i) {       // visited_frag is keyed by the HSP tuple: identical lines fall together
+        for (size_t t = 0; t < n; ++t)
+            if (c[t].qs == c[i].qs && c[t].qe == c[i].qe && c[t].ss == c[i].ss && c[t].se == c[i].se) used[t] = 1;
+    };
+    for (size_t i = 0; i < n; ++i) {
+        if (used[i]) continue;
+        Chain ch{c[i].qs, c[i].qe, c[i].ss, c[i].se, subj};
+        mark(i);
+        for (size_t j = i + 1; j < n; ++j) {
+            if (used[j]) continue;
+            const Frag& f = c[j];
+            if (f.qe <= ch.qe) continue;
+            const bool fwd = ch.ss < ch.se && f.ss < f.se, rev = ch.ss > ch.se && f.ss > f.se;
+            if (fwd && f.se > ch.se) {
+                if (f.qs - ch.qe < skip_gap && f.ss - ch.se < skip_gap) {
+                    ch.qe = f.qe; ch.ss = std::min(ch.ss, f.ss); ch.se = f.se;
+                    mark(j);
+                } else if (f.qs - ch.qe >= skip_gap) break;
+            } else if (rev && f.se < ch.se) {
+                if (f.qs - ch.qe < skip_gap && ch.se - f.ss < skip_gap) {
+                    ch.qe = f.qe; ch.ss = std::max(ch.ss, f.ss); ch.se = f.se;
+                    mark(j);
+                } else if (f.qs - ch.qe >= skip_gap) break;
+            }
+        }
+        out.push_back(ch);
+    }
+}
+
+struct Key { int32_t chr; int64_t a, b; bool operator==(const Key& o) const { return chr == o.chr && a == o.a && b == o.b; } };
+struct KeyHash {
+    size_t operator()(const Key& k) const {
+        uint64_t h = (uint64_t)k.chr * 0x9E3779B97F4A7C15ull;
+        h ^= (uint64_t)k.a + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= (uint64_t)k.b + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        return (size_t)h;
+    }
+};
+
+// one query segment
+void fmea_query(const hb_hsp* h, size_t n, const hb_segment& q, int32_t q_index, const hb_segment* segs,
+                int skip_gap, int max_len, std::vector<hb_interval>& out) {
+    // subjects in order of first appearance (Python dict order, module/Util.py:4140-4147)
+    std::vector<int32_t> order;
+    std::vector<std::vector<Frag>> per;      // parallel to `order`
+    std::vector<int32_t> slot;               // subject id -> index in order (grown lazily)
+    for (size_t i = 0; i < n; ++i) {
+        const hb_hsp& x = h[i];
+        if (x.subj == q_index && x.qs == x.ss && x.qe == x.se) continue;            // :4138
+        if ((size_t)x.subj >= slot.size()) slot.resize((size_t)x.subj + 1, -1);
+        if (slot[x.subj] < 0) { slot[x.subj] = (int32_t)order.size(); order.push_back(x.subj); per.emplace_back(); }
+        per[slot[x.subj]].push_back(Frag{x.qs, x.qe, x.ss, x.se});
+    }
+    std::vector<Chain> chains;
+    std::vector<Frag> cl;
+    for (size_t oi = 0; oi < order.size(); ++oi) {
+        std::vector<Frag> fw, rv;
+        for (const Frag& f : per[oi]) (f.ss > f.se ? rv : fw).push_back(f);           // :4168-4172
+        std::stable_sort(fw.begin(), fw.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : a.se < b.se; });
+        std::stable_sort(rv.begin(), rv.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : a.se > b.se; });
+        for (int pass = 0; pass < 2; ++pass) {                                        // :4178-4227
+            const std::vector<Frag>& p = pass ? rv : fw;
+            cl.clear();
+            for (size_t k = 0; k < p.size(); ++k) {
+                bool closed = false;
+                if (k > 0)
+                    for (size_t e = cl.size(); e-- > 0;) {
+                        const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
+                        if (gap < skip_gap && p[k].qe > cl[e].qe) { closed = true; break; }
+                    }
+                if (k > 0 && !closed) { chain_cluster(cl, skip_gap, order[oi], chains); cl.clear(); }
+                cl.push_back(p[k]);
+            }
+            if (!cl.empty()) chain_cluster(cl, skip_gap, order[oi], chains);
+        }
+    }
+    // 10-bp-rounded position de-duplication in visiting order (module/Util.py:4330-4390)
+    std::unordered_set<Key, KeyHash> seen;
+    struct Iv { int64_t a, b; };
+    std::vector<Iv> names;
+    auto round10 = [](int64_t x, int64_t& lo, int64_t& hi) { lo = (x / 10) * 10; hi = lo + 10; };
+    for (const Chain& ch : chains) {
+        const hb_segment& s = segs[ch.subj];
+        const int64_t sa = s.start + (ch.ss - 1), sb = s.start + ch.se;
+        const int64_t qa = q.start + (ch.qs - 1), qb = q.start + ch.qe;
+        int64_t sa1, sa2, sb1, sb2, qa1, qa2, qb1, qb2;
+        round10(sa, sa1, sa2); round10(sb, sb1, sb2); round10(qa, qa1, qa2); round10(qb, qb1, qb2);
+        const Key ks[8] = {{s.chr, sa1, sb1}, {s.chr, sa1, sb2}, {s.chr, sa2, sb1}, {s.chr, sa2, sb2},
+                           {q.chr, qa1, qb1}, {q.chr, qa1, qb2}, {q.chr, qa2, qb1}, {q.chr, qa2, qb2}};
+        bool hit = false;
+        for (const Key& k : ks) hit = hit || seen.count(k);
+        const int64_t qlen = std::llabs((long long)ch.qe - (ch.qs - 1));
+        if (!hit && qlen >= 80 && qlen < max_len) names.push_back(Iv{qa, qb});
+        for (const Key& k : ks) seen.insert(k);
+    }
+    // >= 95 % overlap merge, longest first (module/Util.py:4529-4549)
+    std::stable_sort(names.begin(), names.end(), [](const Iv& x, const Iv& y) { return (x.b - x.a) > (y.b - y.a); });
+    std::vector<char> keep(names.size(), 1);
+    for (size_t i = 0; i < names.size(); ++i) {
+        if (!keep[i]) continue;
+        for (size_t j = i + 1; j < names.size(); ++j) {
+            if (!keep[j]) continue;
+            const int64_t ov = std::max<int64_t>(0, std::min(names[i].b, names[j].b) - std::max(names[i].a, names[j].a));
+            if ((double)ov / (double)(names[j].b - names[j].a) >= 0.95) keep[j] = 0;
+        }
+    }
+    for (size_t i = 0; i < names.size(); ++i) {
+        if (!keep[i]) continue;
+        bool dup = false;
+        for (const hb_interval& o : out) if (o.start == names[i].a && o.end == names[i].b) { dup = true; break; }
+        if (!dup) out.push_back(hb_interval{q.chr, q_index, names[i].a, names[i].b});
+    }
+}
+
+}  // namespace
+
+// HSPs must be grouped by query segment: query segment g owns hsp[q_off[g] .. q_off[g+1]).
+int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
+                int max_len, int threads, std::vector<hb_interval>& result) {
+    std::vector<std::vector<hb_interval>> per(n_seg);
+    std::atomic<uint32_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t g = next.fetch_add(1);
+            if (g >= n_seg) break;
+            const uint64_t a = q_off[g], b = q_off[g + 1];
+            if (b > a) fmea_query(hsp + a, (size_t)(b - a), segs[g], (int32_t)g, segs, skip_gap, max_len, per[g]);
+        }
+    };
+    const int nt = std::max(1, std::min<int>(threads, (int)n_seg));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    result.clear();
+    for (uint32_t g = 0; g < n_seg; ++g) result.insert(result.end(), per[g].begin(), per[g].end());
+    return 0;
+}

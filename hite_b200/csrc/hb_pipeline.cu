@@ -6,8 +6,11 @@
 #include <chrono>
 #include <cstdlib>
 
+#include <chrono>
+#include "hb_coarse.cuh"
 #include "hb_ctx.cuh"
 #include "hb_extend.cuh"
+#include "hb_fmea.cuh"
 #include "hb_index.cuh"
 #include "hb_msa.cuh"
 #include "hb_prims.cuh"
@@ -178,6 +181,9 @@ extern "C" int hb_index_build(hb_ctx* ctx, int k, int w) {
     ENSURE("g.sort_tmp", sizeof(uint32_t) * hb_sort_tmp_words(n_mm));
     HB_CUDA_OK(hb_minimizer_write_launch(ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(), tot, k, w,
                                          ctx->buf("g.mm_base").as<uint32_t>(), ctx->buf("g.idx_a").as<uint64_t>(), s));
+    // the position-ordered list is kept for the coarse-boundary self-join (hb_coarse.cu)
+    ENSURE("g.mm_pos", sizeof(uint64_t) * (n_mm + 1));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("g.mm_pos").p, ctx->buf("g.idx_a").p, sizeof(uint64_t) * n_mm, cudaMemcpyDeviceToDevice, s));
     HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
     // stable sort on the 2k-bit hash (keys are emitted in position order, so (hash,pos) ends sorted)
     uint64_t* sorted = nullptr;
@@ -620,5 +626,141 @@ extern "C" int hb_last_msa(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii, uint6
     HB_CUDA_OK(cudaMemcpyAsync(out_ascii, ctx->buf("m.mat").as<uint8_t>() + ctx->last_mat_off[cand], bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     for (uint64_t i = 0; i < bytes; ++i) out_ascii[i] = (uint8_t)hb_ascii_of_sym(out_ascii[i]);
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int hb_fmea_chain(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
+                             int max_len, int threads, hb_interval* out, uint64_t cap, uint64_t* n_out) {
+    if (!q_off || !segs || !n_out || (n_seg && q_off[n_seg] && !hsp)) return HB_EINVAL;
+    std::vector<hb_interval> res;
+    hb_fmea_run(hsp, q_off, n_seg, segs, skip_gap, max_len, threads, res);
+    *n_out = res.size();
+    if (!out) return HB_OK;
+    if (cap < res.size()) return HB_EINVAL;
+    if (!res.empty()) memcpy(out, res.data(), sizeof(hb_interval) * res.size());
+    return HB_OK;
+}
+
+extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
+                                  hb_interval* out, uint64_t cap, uint64_t* n_out) {
+    if (!ctx || !n_out) return HB_EINVAL;
+    if (!ctx->have_index) return hb_fail_msg(ctx, HB_ESTATE, "hb_coarse_boundary: call hb_genome_load + hb_index_build first");
+    if (seg_len < 1000 || occ_cap < 1 || occ_cap > 4096) return hb_fail_msg(ctx, HB_EINVAL, "hb_coarse_boundary: parameter out of range");
+    if (ctx->g_nmm >= (1ull << 29)) return hb_fail_msg(ctx, HB_EINVAL, "hb_coarse_boundary: more than 2^29 minimizers");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    hb_timing& tm = ctx->timing;
+    uint32_t launches = 0;
+    // segments: seg_len pieces of every contig (split_genome_chunks.py:44-52)
+    std::vector<hb_segment> segs;
+    std::vector<uint64_t> seg_goff;
+    for (uint32_t c = 0; c < ctx->g_ncontig; ++c)
+        for (uint64_t o = 0; o < ctx->g_glen[c]; o += (uint64_t)seg_len) {
+            segs.push_back(hb_segment{(int32_t)c, 0, (int64_t)o});
+            seg_goff.push_back(ctx->g_goff[c] + o);
+        }
+    const int n_seg = (int)segs.size();
+    const uint32_t n_mm = (uint32_t)ctx->g_nmm;
+    ENSURE("h.seg_goff", sizeof(uint64_t) * (n_seg + 1));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("h.seg_goff").p, seg_goff.data(), sizeof(uint64_t) * n_seg, cudaMemcpyHostToDevice, s));
+    ENSURE("h.lo", sizeof(uint32_t) * (n_mm + 1)); ENSURE("h.cnt", sizeof(uint32_t) * (n_mm + 1)); ENSURE("h.off", sizeof(uint32_t) * (n_mm + 1));
+    ENSURE("h.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(n_mm + 1));
+    ENSURE("h.total", sizeof(uint64_t));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    HB_CUDA_OK(hb_pair_count_launch(ctx->buf("g.mm_pos").as<uint64_t>(), n_mm, ctx->buf("g.idx_a").as<uint64_t>(),
+                                    ctx->buf("g.bucket").as<uint32_t>(), occ_cap, ctx->buf("h.lo").as<uint32_t>(),
+                                    ctx->buf("h.cnt").as<uint32_t>(), s));
+    HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("h.cnt").as<uint32_t>(), ctx->buf("h.off").as<uint32_t>(), n_mm,
+                                     ctx->buf("h.scan_tmp").as<uint32_t>(), ctx->buf("h.total").as<uint64_t>(), s));
+    uint64_t n_pairs = 0;
+    HB_CUDA_OK(cudaMemcpyAsync(&n_pairs, ctx->buf("h.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    launches += 4;
+    if (n_pairs >= (1ull << 32)) return hb_fail_msg(ctx, HB_ENOMEM, "hb_coarse_boundary: more than 2^32 seed pairs; lower occ_cap");
+    std::vector<HbHspRec> h_recs;
+    if (n_pairs > 0) {
+        ENSURE("h.keys_a", sizeof(uint64_t) * n_pairs); ENSURE("h.keys_b", sizeof(uint64_t) * n_pairs);
+        ENSURE("h.sort_tmp", sizeof(uint32_t) * hb_sort_tmp_words(n_pairs));
+        HB_CUDA_OK(hb_pair_fill_launch(ctx->buf("g.mm_pos").as<uint64_t>(), n_mm, ctx->buf("g.idx_a").as<uint64_t>(), ctx->g_nmm,
+                                       ctx->g_tot, ctx->k, occ_cap, ctx->buf("h.lo").as<uint32_t>(), ctx->buf("h.cnt").as<uint32_t>(),
+                                       ctx->buf("h.off").as<uint32_t>(), ctx->buf("h.keys_a").as<uint64_t>(), s));
+        HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+        uint64_t* keys = nullptr;
+        HB_CUDA_OK(hb_radix_sort_u64(ctx->buf("h.keys_a").as<uint64_t>(), ctx->buf("h.keys_b").as<uint64_t>(), n_pairs, 0, 64,
+                                     ctx->buf("h.sort_tmp").as<uint32_t>(), &keys, &launches, s));
+        HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+        ENSURE("h.flag", sizeof(uint32_t) * n_pairs); ENSURE("h.rid", sizeof(uint32_t) * n_pairs);
+        ENSURE("h.scan_tmp2", sizeof(uint32_t) * hb_scan_tmp_words(n_pairs));
+        HB_CUDA_OK(hb_hsp_flag_launch(keys, n_pairs, ctx->buf("g.mm_pos").as<uint64_t>(), ctx->g_tot, ctx->k,
+                                      ctx->buf("h.seg_goff").as<uint64_t>(), n_seg, ctx->buf("h.flag").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("h.flag").as<uint32_t>(), ctx->buf("h.rid").as<uint32_t>(), n_pairs,
+                                         ctx->buf("h.scan_tmp2").as<uint32_t>(), ctx->buf("h.total").as<uint64_t>(), s));
+        uint64_t n_runs64 = 0;
+        HB_CUDA_OK(cudaMemcpyAsync(&n_runs64, ctx->buf("h.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaStreamSynchronize(s));
+        const uint32_t n_runs = (uint32_t)n_runs64;
+        ENSURE("h.run_start", sizeof(uint32_t) * (n_runs + 1)); ENSURE("h.keep", sizeof(uint32_t) * (n_runs + 1));
+        ENSURE("h.pos", sizeof(uint32_t) * (n_runs + 1)); ENSURE("h.recs", sizeof(HbHspRec) * ((size_t)n_runs + 1));
+        ENSURE("h.scan_tmp3", sizeof(uint32_t) * hb_scan_tmp_words(n_runs + 1));
+        HB_CUDA_OK(hb_hsp_start_launch(ctx->buf("h.flag").as<uint32_t>(), ctx->buf("h.rid").as<uint32_t>(), n_pairs,
+                                       ctx->buf("h.run_start").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_hsp_emit_launch(keys, n_pairs, ctx->buf("h.run_start").as<uint32_t>(), n_runs,
+                                      ctx->buf("g.mm_pos").as<uint64_t>(), ctx->g_tot, ctx->k, ctx->buf("h.seg_goff").as<uint64_t>(),
+                                      n_seg, ctx->buf("h.recs").as<HbHspRec>(), ctx->buf("h.keep").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("h.keep").as<uint32_t>(), ctx->buf("h.pos").as<uint32_t>(), n_runs,
+                                         ctx->buf("h.scan_tmp3").as<uint32_t>(), ctx->buf("h.total").as<uint64_t>(), s));
+        uint64_t n_hsp = 0;
+        HB_CUDA_OK(cudaMemcpyAsync(&n_hsp, ctx->buf("h.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaStreamSynchronize(s));
+        ENSURE("h.out", sizeof(HbHspRec) * (n_hsp + 1));
+        HB_CUDA_OK(hb_hsp_compact_launch(ctx->buf("h.recs").as<HbHspRec>(), ctx->buf("h.keep").as<uint32_t>(),
+                                         ctx->buf("h.pos").as<uint32_t>(), n_runs, ctx->buf("h.out").as<HbHspRec>(), s));
+        HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+        h_recs.resize(n_hsp);
+        if (n_hsp) HB_CUDA_OK(cudaMemcpyAsync(h_recs.data(), ctx->buf("h.out").p, sizeof(HbHspRec) * n_hsp, cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaStreamSynchronize(s));
+        launches += 12;
+        tm.d2h_bytes = sizeof(HbHspRec) * n_hsp;
+        cudaEventElapsedTime(&tm.k_ms[0], ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&tm.k_ms[1], ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&tm.k_ms[2], ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&tm.kernel_ms, ctx->ev[0], ctx->ev[3]);
+    }
+    // group by query segment, stable (the "file order" of each query is the sorted-key order)
+    ctx->last_hsp_off.assign((size_t)n_seg + 1, 0);
+    for (const HbHspRec& r : h_recs) ctx->last_hsp_off[(size_t)r.qseg + 1]++;
+    for (int g = 0; g < n_seg; ++g) ctx->last_hsp_off[g + 1] += ctx->last_hsp_off[g];
+    ctx->last_hsps.resize(h_recs.size());
+    {
+        std::vector<uint64_t> cur(ctx->last_hsp_off.begin(), ctx->last_hsp_off.end() - 1);
+        for (const HbHspRec& r : h_recs) ctx->last_hsps[cur[r.qseg]++] = hb_hsp{r.subj, r.qs, r.qe, r.ss, r.se};
+    }
+    ctx->last_segs = segs;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<hb_interval> res;
+    hb_fmea_run(ctx->last_hsps.data(), ctx->last_hsp_off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, res);
+    tm.k_ms[3] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    tm.k_ms[6] = (float)h_recs.size();
+    tm.k_ms[7] = (float)((double)n_pairs * 1e-6);
+    tm.launches = launches;
+    *n_out = res.size();
+    if (!out) return HB_OK;
+    if (cap < res.size()) return hb_fail_msg(ctx, HB_EINVAL, "hb_coarse_boundary: output buffer too small");
+    if (!res.empty()) memcpy(out, res.data(), sizeof(hb_interval) * res.size());
+    return HB_OK;
+}
+
+extern "C" int hb_last_hsps(hb_ctx* ctx, hb_hsp* out, uint64_t cap, uint64_t* n, uint64_t* q_off, hb_segment* segs,
+                            uint32_t seg_cap, uint32_t* n_seg) {
+    if (!ctx || !n || !n_seg) return HB_EINVAL;
+    *n = ctx->last_hsps.size();
+    *n_seg = (uint32_t)ctx->last_segs.size();
+    if (!out) return HB_OK;
+    if (cap < ctx->last_hsps.size() || seg_cap < ctx->last_segs.size()) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_hsps: buffer too small");
+    if (!ctx->last_hsps.empty()) memcpy(out, ctx->last_hsps.data(), sizeof(hb_hsp) * ctx->last_hsps.size());
+    if (q_off) memcpy(q_off, ctx->last_hsp_off.data(), sizeof(uint64_t) * ctx->last_hsp_off.size());
+    if (segs) memcpy(segs, ctx->last_segs.data(), sizeof(hb_segment) * ctx->last_segs.size());
     return HB_OK;
 }

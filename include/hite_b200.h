@@ -158,6 +158,35 @@ int hb_last_cons_device(hb_ctx* ctx, const void** dptr, uint64_t* nbytes);
 /* copies of the last hb_adjust, ordered by (candidate, rank); pass out=NULL to query the count */
 int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t* n);
 
+/* ---- coarse boundary (module/coarse_boundary.py -> determine_repeat_boundary_v5, module/Util.py:4637) ---- */
+typedef struct { int32_t subj, qs, qe, ss, se; } hb_hsp;      /* one HSP of a query segment against segment `subj`;
+                                                                  1-based inclusive, ss > se = minus strand: the fields
+                                                                  get_longest_repeats_v4 reads from outfmt 6 (module/Util.py:4130-4137) */
+typedef struct { int32_t chr, pad; int64_t start; } hb_segment; /* segment `chr$start` of split_genome_chunks.py:47-52 */
+typedef struct { int32_t chr, qseg; int64_t start, end; } hb_interval; /* 'chr:start-end' (0-based, end exclusive; module/Util.py:4354-4363) */
+
+/*
+ * hb_fmea_chain -- FMEA interval chaining: get_longest_repeats_v4 + process_all_seqs (module/Util.py:
+ * 4122-4400, 4529-4563) for n_seg query segments; query segment g owns hsp[q_off[g] .. q_off[g+1]) in
+ * "file order".  Bit-identical to the reference on the same HSP list.  Two-call: out == NULL returns the
+ * count in *n_out.  Host code (see hb_fmea.cu for why); `threads` host threads over query segments.
+ */
+int hb_fmea_chain(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
+                  int max_len, int threads, hb_interval* out, uint64_t cap, uint64_t* n_out);
+
+/*
+ * hb_coarse_boundary -- the all-vs-all step of process_blast_alignments (module/Util.py:4724-4780: n^2 blastn
+ * runs of 1 Mbp segments) as one self-join of the minimizer index on the GPU (seed pairs -> radix sort ->
+ * exact-diagonal runs = HSPs), followed by hb_fmea_chain.  Uses the genome + index of the context; segments
+ * are seg_len-long pieces of each contig (chrom_seg_length, main.py:41).  Two-call like hb_fmea_chain.
+ * Timing: k_ms[0] pair count+fill, [1] sort, [2] HSP extraction, [3] host FMEA (wall), [6] #HSPs, [7] million seed pairs.
+ */
+int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
+                       hb_interval* out, uint64_t cap, uint64_t* n_out);
+/* the HSPs of the last hb_coarse_boundary, grouped by query segment (q_off has n_seg+1 entries) */
+int hb_last_hsps(hb_ctx* ctx, hb_hsp* out, uint64_t cap, uint64_t* n, uint64_t* q_off, hb_segment* segs,
+                 uint32_t seg_cap, uint32_t* n_seg);
+
 /* parity/debug getters: the sorted minimizer index (hash<<33 | pos<<1 | strand) and the raw
  * (pre-clean) MSA of one candidate of the last hb_adjust as ASCII */
 int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap);

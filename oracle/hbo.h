@@ -72,6 +72,11 @@ int hbo_fmea(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_s
              const int32_t *subj_chr, const int64_t *subj_seg_start, int n_subj,
              int skip_gap, int max_len, hbo_interval *out, int cap);
 
+/* ---- HB-hsp restatement (hbo_hsp.c) ---- */
+typedef struct { int32_t qseg, subj, qs, qe, ss, se; } hbo_hsp_rec;
+uint64_t hbo_self_hsps(const uint64_t *mm_pos, const uint64_t *idx, uint64_t n, uint64_t tot, int k,
+                       const uint64_t *seg_goff, int n_seg, int occ_cap, hbo_hsp_rec *out, uint64_t cap);
+
 typedef struct { int32_t is_te, info, copy_num, cons_len; } hbo_result;
 int hbo_run_batch(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w, const uint8_t *cand_ascii,
                   const uint64_t *coff, uint32_t n_cand, int occ_cap, int max_loci, int flank, int max_rows, int plant,

@@ -242,3 +242,36 @@ class Genome:
         L.hbo_run_batch(self.g, self.index.ctypes.data, len(self.index), self.k, self.w, flat.ctypes.data,
                         off.ctypes.data, len(cb), occ_cap, max_loci, flank, max_rows, plant, threads, out.ctypes.data)
         return out
+
+    def coarse_boundary(self, contig_lens, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64):
+        """HB-hsp self-join (hbo_hsp.c) + FMEA (hbo_fmea.c) -> (hsps [n,6] int32 in sorted-key order,
+        segments [(contig, start)], intervals [(contig, start, end)] in query-segment order)."""
+        import numpy as np
+        L = self._L
+        segs, goff = [], []
+        p = 64
+        for c, ln in enumerate(contig_lens):
+            for o in range(0, ln, seg_len):
+                segs.append((c, o)); goff.append(p + o)
+            p += ln + 64
+        goff = np.asarray(goff, dtype=np.uint64)
+        L.hbo_self_hsps.restype = C.c_uint64
+        L.hbo_self_hsps.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_uint64]
+        n = L.hbo_self_hsps(self.mm_pos_order.ctypes.data, self.index.ctypes.data, len(self.index), self.total, self.k,
+                            goff.ctypes.data, len(segs), occ_cap, None, 0)
+        recs = np.zeros((max(1, n), 6), dtype=np.int32)
+        L.hbo_self_hsps(self.mm_pos_order.ctypes.data, self.index.ctypes.data, len(self.index), self.total, self.k,
+                        goff.ctypes.data, len(segs), occ_cap, recs.ctypes.data, n)
+        recs = recs[:n]
+        intervals = []
+        for g, (qc, qo) in enumerate(segs):
+            mine = recs[recs[:, 0] == g]
+            if len(mine) == 0:
+                continue
+            hs = [(int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5])) for r in mine]
+            names = fmea(("c%d" % qc, qo), [("c%d" % c, o) for c, o in segs], g, hs, skip_gap, max_len)
+            for nm in names:
+                a, b = nm.split(":")[1].split("-")
+                intervals.append((qc, int(a), int(b)))
+        return recs, segs, intervals

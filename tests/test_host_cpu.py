@@ -122,3 +122,37 @@ def test_allgather_records_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_product_fmea_matches_reference_goldens():
+    """hb_fmea_chain (host C++ inside libhite_b200.so) vs goldens from the imported reference
+    get_longest_repeats_v4 (tests/golden/make_golden.py): bit-identical interval lists, same order."""
+    import gzip
+    import json
+    import numpy as np
+    from hite_b200 import _lib
+    recs = json.loads(gzip.open(os.path.join(ROOT, "tests", "golden", "fmea.json.gz")).read())
+    for rec in recs:
+        chr_ids = {}
+        for name in [rec["query"][0]] + [s[0] for s in rec["subjects"]]:
+            chr_ids.setdefault(name, len(chr_ids))
+        subjects = [tuple(s) for s in rec["subjects"]]
+        q = tuple(rec["query"])
+        # the query must be one of the segments: index self_subj if present, else appended
+        segs = list(subjects)
+        qi = rec["self_subj"]
+        if qi < 0:
+            segs.append(q)
+            qi = len(segs) - 1
+        seg_arr = np.zeros(len(segs), dtype=_lib.SEG_DTYPE)
+        for i, (c, o) in enumerate(segs):
+            seg_arr[i] = (chr_ids[c], 0, o)
+        hs = np.zeros(len(rec["hsps"]), dtype=_lib.HSP_DTYPE)
+        for i, h in enumerate(rec["hsps"]):
+            hs[i] = tuple(h)
+        q_off = np.zeros(len(segs) + 1, dtype=np.uint64)
+        q_off[qi + 1:] = len(hs)
+        out = _lib.fmea_chain(hs, q_off, seg_arr, rec["skip_gap"], rec["max_len"], threads=2)
+        names = ["%s:%d-%d" % (q[0], int(o["start"]), int(o["end"])) for o in out]
+        assert names == rec["expect"], rec["seed"]
+        assert all(int(o["qseg"]) == qi for o in out)
