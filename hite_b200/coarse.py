@@ -1,0 +1,82 @@
+"""Host-side mirror of the coarse-boundary stage (reference module/coarse_boundary.py).
+
+* ``determine_repeat_boundary_v5``  reference module/Util.py:4637-4669 -- same signature.  The all-vs-all
+  ``blastn`` of 1 Mbp segments (process_blast_alignments, :4724-4780) becomes one self-join of the minimizer
+  index on the GPU (``hb_coarse_boundary``); FMEA chaining (get_longest_repeats_v4, :4122) runs in the C-ABI
+  library; ``generate_final_result`` (:4783-4796) slices the intervals out of the reference genome.
+  NOT reproduced (out of scope; external ``trf`` / ``minimap2``): the tandem-repeat and
+  known-TE masking of :4651-4654 -- the chunk is taken as given (mask it beforehand if needed).
+* ``flanking_seq``  reference module/Util.py:4614-4634 -- same signature and clamping rules.
+"""
+import os
+
+import numpy as np
+
+from .boundary import _GENOME, get_context
+from .fasta import read_fasta, store_fasta
+
+
+def _chunk_to_chromosomes(repeats_path):
+    """genome.cut{i}.fa holds records ``chr$start`` (split_genome_chunks.py:47-52).  Rebuild per-chromosome
+    arrays (pieces missing from this chunk stay 'N') so segments sit at their real coordinates."""
+    names, contigs = read_fasta(repeats_path)
+    pieces = {}
+    order = []
+    for n in names:
+        if "$" in n:
+            c, off = n.rsplit("$", 1)
+            off = int(off)
+        else:
+            c, off = n, 0
+        if c not in pieces:
+            pieces[c] = []
+            order.append(c)
+        pieces[c].append((off, contigs[n]))
+    chroms = []
+    for c in order:
+        end = max(o + len(s) for o, s in pieces[c])
+        arr = np.full(end, ord("N"), dtype=np.uint8)
+        for o, s in pieces[c]:
+            arr[o:o + len(s)] = np.frombuffer(s.encode("ascii"), dtype=np.uint8)
+        chroms.append(arr)
+    return order, chroms
+
+
+def determine_repeat_boundary_v5(repeats_path, longest_repeats_path, prev_TE, fixed_extend_base_threshold,
+                                 max_single_repeat_len, tmp_output_dir, threads, ref_index, reference, debug,
+                                 chrom_seg_length=1_000_000, occ_cap=64):
+    if not os.path.exists(tmp_output_dir):
+        os.makedirs(tmp_output_dir)
+    chr_names, chroms = _chunk_to_chromosomes(repeats_path)
+    ctx = get_context()
+    _GENOME.pop(ctx.device, None)                 # this context now holds the chunk, not the reference
+    ctx.load_genome(chroms)
+    ctx.build_index(15, 10)
+    iv = ctx.coarse_boundary(seg_len=int(chrom_seg_length), skip_gap=int(fixed_extend_base_threshold),
+                             max_len=int(max_single_repeat_len), occ_cap=int(occ_cap), threads=max(1, int(threads)))
+    ref_names, ref_contigs = read_fasta(reference)
+    final = {}
+    for o in iv:                                  # generate_final_result (module/Util.py:4783-4796)
+        c = chr_names[int(o["chr"])]
+        a, b = int(o["start"]), int(o["end"])
+        final["%s:%d-%d" % (c, a, b)] = ref_contigs[c][a:b]
+    store_fasta(final, longest_repeats_path)
+    return longest_repeats_path
+
+
+def flanking_seq(longest_repeats_path, longest_repeats_flanked_path, reference, flanking_len):
+    seq_names, _ = read_fasta(longest_repeats_path)
+    _, ref_contigs = read_fasta(reference)
+    flanked = {}
+    for name in seq_names:
+        ref_name, pos = name.split(":")[0], name.split(":")[1]
+        a, b = pos.split("-")
+        start1, end1 = int(a) + 1, int(b)                      # 1-based inclusive
+        seq = ref_contigs[ref_name]
+        if start1 - 1 - flanking_len < 0:                      # clamp so a full flank exists (:4625-4628)
+            start1 = flanking_len + 1
+        if end1 + flanking_len > len(seq):
+            end1 = len(seq) - flanking_len
+        flanked["%s:%d-%d" % (ref_name, start1 - flanking_len, end1 + flanking_len)] = \
+            seq[start1 - 1 - flanking_len:end1 + flanking_len]
+    store_fasta(flanked, longest_repeats_flanked_path)

@@ -9,6 +9,7 @@ reference's ``Util`` namespace with the B200 implementations:
     Util.flank_region_align_v5   -> hite_b200.boundary.flank_region_align_v5
     Util.run_find_members_v8     -> hite_b200.boundary.run_find_members_v8
     Util.is_TE_from_align_file   -> hite_b200.boundary.is_TE_from_align_file
+    Util.determine_repeat_boundary_v5 -> hite_b200.coarse.determine_repeat_boundary_v5   (coarse_boundary.py)
 
 Everything else on the stage (TSD pre-filter, cd-hit-est, renaming, prev_TE bookkeeping) stays the
 reference's code.  ``HITE_HOME`` must point at the HiTE checkout.  There is no CPU fallback: if the
@@ -36,14 +37,16 @@ def hite_home():
     return os.path.abspath(home)
 
 
-def run_stage(script_name, patch_names=("flank_region_align_v5", "run_find_members_v8", "is_TE_from_align_file")):
+def run_stage(script_name, patch_names=("flank_region_align_v5", "run_find_members_v8", "is_TE_from_align_file"),
+              source="hite_b200.boundary"):
     home = hite_home()
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     moddir = os.path.join(home, "module")
     sys.path.insert(0, moddir)
     sys.path.insert(0, home)
-    import hite_b200.boundary as hb
+    import importlib
+    hb = importlib.import_module(source)
     import Util  # the reference's own module, unmodified
     for name in patch_names:
         setattr(Util, name, getattr(hb, name))

@@ -156,3 +156,23 @@ def test_product_fmea_matches_reference_goldens():
         names = ["%s:%d-%d" % (q[0], int(o["start"]), int(o["end"])) for o in out]
         assert names == rec["expect"], rec["seed"]
         assert all(int(o["qseg"]) == qi for o in out)
+
+
+def test_flanking_seq_matches_reference(tmp_path):
+    ref_util = "/root/reference/module/Util.py"
+    from hite_b200 import coarse
+    ref = tmp_path / "g.fa"
+    ref.write_text(">c1\n" + "ACGT" * 100 + "\n>c2\n" + "TTGCA" * 50 + "\n")
+    lr = tmp_path / "lr.fa"
+    lr.write_text(">c1:10-120\nA\n>c1:0-90\nA\n>c1:300-399\nA\n>c2:100-250\nA\n")
+    out = tmp_path / "b.fa"
+    coarse.flanking_seq(str(lr), str(out), str(ref), 50)
+    text = out.read_text()
+    assert text.startswith(">c1:")            # names: chr:(s+1-50)-(e+50), clamped (Util.py:4620-4633)
+    assert ">c1:1-170\n" in text and ">c1:251-400\n" in text
+    if os.path.exists(ref_util):
+        from oracle import ref_import
+        U = ref_import.load_util()
+        exp = tmp_path / "a.fa"
+        U.flanking_seq(str(lr), str(exp), str(ref), 50)
+        assert exp.read_text() == text
