@@ -191,6 +191,18 @@ def main():
     t_idx = ctx.build_index(15, 10)
     setup_s = time.perf_counter() - t0
     info = ctx.genome_info()
+    # coarse-boundary stage on the same genome (module/coarse_boundary.py): all-vs-all self-join + FMEA
+    coarse = None
+    if rank == 0:
+        tc = time.perf_counter()
+        iv = ctx.coarse_boundary(seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=max(1, cores))
+        tmc = ctx.timing()
+        tcw = time.perf_counter() - tc
+        # ctx.coarse_boundary runs the host FMEA twice (count + fetch); time one GPU pass + one FMEA pass
+        one = (tmc["kernel_ms"] + tmc["k_ms"][3]) * 1e-3
+        coarse = {"intervals": int(len(iv)), "hsps": int(tmc["k_ms"][6]), "seed_pairs_M": float(tmc["k_ms"][7]),
+                  "gpu_ms": tmc["kernel_ms"], "fmea_host_ms": tmc["k_ms"][3], "wall_s": tcw,
+                  "Mbp_per_s": wl.genome_bp / 1e6 / max(1e-9, one)}
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,6 +308,8 @@ def main():
                       "index_Mbp_per_s": wl.genome_bp / 1e6 / max(1e-9, t_idx["kernel_ms"] * 1e-3), "setup_wall_s": setup_s,
                       "n_minimizers": int(info["n_minimizers"])},
             "calls": {"is_te": int(n_te_total)},
+            "coarse_boundary": coarse,
+            "mbp_per_s": coarse["Mbp_per_s"] if coarse else None,
         }
         if not args.no_cpu_baseline and world == 1:
             per = min(len(wl.cand_seqs), max(256, 48 * cores))

@@ -6,7 +6,8 @@ Python host side of ``libhite_b200.so`` (hand-written sm_100a CUDA kernels behin
 * ``hite_b200.boundary.flank_region_align_v5``        (reference module/Util.py:8032)
 * ``hite_b200.boundary.run_find_members_v8``          (reference module/Util.py:10439)
 * ``hite_b200.boundary.is_TE_from_align_file``        (reference module/Util.py:10407)
-* ``hite_b200.boundary.determine_repeat_boundary_v5`` (reference module/Util.py:4637)
+* ``hite_b200.coarse.determine_repeat_boundary_v5``   (reference module/Util.py:4637)
+* ``hite_b200.coarse.flanking_seq``                   (reference module/Util.py:4614)
 
 There is no CPU fallback: without the built extension and a CUDA device every entry point raises.
 """

@@ -302,12 +302,19 @@ class Context:
     def coarse_boundary(self, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=8):
         """The all-vs-all + FMEA step of ``determine_repeat_boundary_v5`` (reference module/Util.py:4657-4663) on
         the loaded genome -> INTERVAL_DTYPE array ('chr:start-end', 0-based half open)."""
-        n = C.c_uint64(0)
-        self._check(self._lib.hb_coarse_boundary(self._h, int(seg_len), int(skip_gap), int(max_len), int(occ_cap), int(threads),
-                                                 None, 0, C.byref(n)), "hb_coarse_boundary")
-        # the first call already ran the GPU stage; fetch by re-running the cheap host stage on the cached HSPs
-        hsps, q_off, segs = self.last_hsps()
-        return fmea_chain(hsps, q_off, segs, skip_gap, max_len, threads)
+        # generous one-shot buffer: an interval needs at least one HSP, so #HSPs bounds the count; retry if short
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=INTERVAL_DTYPE)
+            n = C.c_uint64(0)
+            rc = self._lib.hb_coarse_boundary(self._h, int(seg_len), int(skip_gap), int(max_len), int(occ_cap), int(threads),
+                                              _ptr(out), cap, C.byref(n))
+            if rc == 0:
+                return out[:n.value]
+            if n.value > cap:
+                cap = int(n.value)
+                continue
+            self._check(rc, "hb_coarse_boundary")
 
     def last_hsps(self):
         n, ns = C.c_uint64(0), C.c_uint32(0)

@@ -142,8 +142,9 @@ typedef struct {
  * 8032-8299 up to the per-candidate verdict): seed lookup + diagonal clustering (replaces minimap2
  * seeding/chaining, :7952-7961), banded affine Smith-Waterman per candidate x locus (replaces
  * minimap2 base alignment), the copy rules of :8003-8025 and :8095-8115, the 100-longest subset of
- * :10409-10412, a candidate-anchored star MSA (replaces mafft, :10416), then
- * remove_sparse_col_in_align_file + judge_boundary_v5 (:10419-10428).
+ * :10409-10412, a candidate-anchored star MSA (replaces mafft, :10416), the truncated-member gate of
+ * run_find_members_v8 (:10439-10449), then remove_sparse_col_in_align_file + judge_boundary_v5 / v6 / v9
+ * by te_type (:10419-10432).
  * calls[i] mirrors is_TE_from_align_file's tuple for candidate i; consensus bytes are fetched with
  * hb_last_cons (calls[i].cons_off indexes that buffer); *cons_bytes = its size.
  * Timing: k_ms[0] pack+sketch candidates, [1] seed/sort/cluster/rank, [2] extension+traceback,
