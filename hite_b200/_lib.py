@@ -69,6 +69,25 @@ def fmea_chain(hsps, q_off, segs, skip_gap, max_len, threads=1):
     return out[:n.value]
 
 
+QCOPY_DTYPE = np.dtype([("subj", "<i4"), ("start", "<i4"), ("end", "<i4"), ("qlen", "<i4"), ("strand", "<i4")])
+
+
+def query_copies(hsps, idents, query_len, subj_lens, query_coverage=0.95, subject_coverage=0.0, qthr=200, sthr=200,
+                 max_copy_num=100):
+    """get_query_copies (reference module/Util.py:6828) for one query: ``hsps`` HSP_DTYPE, ``idents`` float64."""
+    lib = load()
+    hsps = np.ascontiguousarray(hsps, dtype=HSP_DTYPE)
+    idents = np.ascontiguousarray(idents, dtype=np.float64)
+    sl = np.ascontiguousarray(subj_lens, dtype=np.int32)
+    out = np.zeros(len(hsps) + 8, dtype=QCOPY_DTYPE)
+    n = C.c_uint32(0)
+    rc = lib.hb_query_copies(_ptr(hsps), _ptr(idents), len(hsps), int(query_len), _ptr(sl), float(query_coverage),
+                             float(subject_coverage), int(qthr), int(sthr), int(max_copy_num), _ptr(out), len(out), C.byref(n))
+    if rc != 0:
+        raise HiteB200Error("hb_query_copies failed (%d)" % rc)
+    return out[:n.value]
+
+
 class HbTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("k_ms", C.c_float * 8), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
@@ -111,6 +130,8 @@ def load():
     lib.hb_debug_index.argtypes = [vp, vp, C.c_uint64]
     lib.hb_last_msa.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
     lib.hb_fmea_chain.argtypes = [vp, vp, C.c_uint32, vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
+    lib.hb_query_copies.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, vp,
+                                    C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_coarse_boundary.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
     lib.hb_last_hsps.argtypes = [vp, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     _LIB = lib

@@ -159,3 +159,30 @@ def member_file_name(temp_dir, query_name, trunc=False):
     """module/Util.py:8127-8133 file naming of the per-candidate member files."""
     valid = re.sub(r'[<>:"/\\|?*]', "-", query_name)
     return temp_dir + "/" + valid + (".trunc.blast.bed.fa" if trunc else ".blast.bed.fa")
+
+
+def get_query_copies(cur_segments, query_contigs, subject_path, query_coverage, subject_coverage,
+                     query_fixed_extend_base_threshold=200, subject_fixed_extend_base_threshold=200, max_copy_num=100):
+    """Mirror of module/Util.py:6828-7030 (same signature and return value): ``cur_segments`` is a list of
+    ``(query_name, {subject_name: [(q_start, q_end, s_start, s_end, identity), ...]})``; returns
+    ``{query_name: [(subject_name, start, end, length, '+'|'-'), ...]}``.  The chaining runs in the C-ABI
+    library (``hb_query_copies``); HSPs come from BLAST as in the reference, or from ``Context.last_hsps``."""
+    import numpy as np
+    subject_lens = {}
+    if subject_coverage > 0:
+        names, contigs = read_fasta(subject_path)
+        subject_lens = {n: len(contigs[n]) for n in names}
+    all_copies = {}
+    for query_name, subject_dict in cur_segments:
+        subj_names = list(subject_dict.keys())
+        rows, idents = [], []
+        for si, sn in enumerate(subj_names):
+            for (qs, qe, ss, se, idn) in subject_dict[sn]:
+                rows.append((si, qs, qe, ss, se)); idents.append(float(idn))
+        hs = np.array(rows, dtype=_lib.HSP_DTYPE) if rows else np.zeros(0, dtype=_lib.HSP_DTYPE)
+        sl = [subject_lens.get(sn, 1) for sn in subj_names] or [1]
+        out = _lib.query_copies(hs, idents, len(query_contigs[query_name]), sl, query_coverage, subject_coverage,
+                                query_fixed_extend_base_threshold, subject_fixed_extend_base_threshold, max_copy_num)
+        all_copies[query_name] = [(subj_names[int(o["subj"])], int(o["start"]), int(o["end"]), int(o["qlen"]),
+                                   "-" if int(o["strand"]) else "+") for o in out]
+    return all_copies

@@ -169,3 +169,95 @@ int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const 
     for (uint32_t g = 0; g < n_seg; ++g) result.insert(result.end(), per[g].begin(), per[g].end());
     return 0;
 }
+
+// ================================================================================================
+// get_query_copies (reference module/Util.py:6828-7030): chain the BLAST HSPs of ONE query per subject into
+// full-length copies, keep per subject cluster the longest chain, order by length, apply the coverage rules.
+namespace {
+
+struct CFrag { int32_t qs, qe, ss, se; double ident; };
+struct CBest { int32_t qs = -1, qe = -1, len = -1, ss = -1, se = -1, slen = -1, subj = -1; };
+
+void copies_cluster(std::vector<CFrag>& c, int qthr, int sthr, int subj, std::vector<CBest>& out) {
+    std::stable_sort(c.begin(), c.end(), [](const CFrag& a, const CFrag& b) { return a.qs != b.qs ? a.qs < b.qs : a.qe < b.qe; });
+    const size_t n = c.size();
+    std::vector<char> used(n, 0);
+    auto mark = [&](size_t i) {
+        for (size_t t = 0; t < n; ++t)
+            if (c[t].qs == c[i].qs && c[t].qe == c[i].qe && c[t].ss == c[i].ss && c[t].se == c[i].se && c[t].ident == c[i].ident) used[t] = 1;
+    };
+    CBest best;
+    for (size_t i = 0; i < n; ++i) {
+        if (used[i]) continue;
+        int32_t qs = c[i].qs, qe = c[i].qe, ss = c[i].ss, se = c[i].se;
+        int32_t len = qe - qs + 1;                                   // :6919
+        mark(i);
+        for (size_t j = i + 1; j < n; ++j) {
+            if (used[j]) continue;
+            const CFrag& f = c[j];
+            if (f.qe <= qe) continue;
+            const bool fwd = ss < se && f.ss < f.se, rev = ss > se && f.ss > f.se;
+            if (fwd && f.se > se) {
+                if (f.qs - qe < qthr && f.ss - se < sthr) { qe = f.qe; ss = std::min(ss, f.ss); se = f.se; len = qe - qs; mark(j); }
+                else if (f.qs - qe >= qthr) break;
+            } else if (rev && f.se < se) {
+                if (f.qs - qe < qthr && se - f.ss < sthr) { qe = f.qe; ss = std::max(ss, f.ss); se = f.se; len = qe - qs; mark(j); }
+                else if (f.qs - qe >= qthr) break;
+            }
+        }
+        if (len > best.len) { best.qs = qs; best.qe = qe; best.len = len; best.ss = ss; best.se = se; best.slen = std::abs(se - ss) + 1; best.subj = subj; }
+    }
+    if (best.len != -1) out.push_back(best);
+}
+
+}  // namespace
+
+int hb_query_copies_run(const hb_hsp* h, const double* ident, size_t n, int query_len, const int32_t* subj_len,
+                        double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
+                        std::vector<hb_query_copy>& result) {
+    std::vector<int32_t> order, slot;
+    std::vector<std::vector<CFrag>> per;
+    for (size_t i = 0; i < n; ++i) {
+        const hb_hsp& x = h[i];
+        if ((size_t)x.subj >= slot.size()) slot.resize((size_t)x.subj + 1, -1);
+        if (slot[x.subj] < 0) { slot[x.subj] = (int32_t)order.size(); order.push_back(x.subj); per.emplace_back(); }
+        per[slot[x.subj]].push_back(CFrag{x.qs, x.qe, x.ss, x.se, ident[i]});
+    }
+    std::vector<CBest> longest;
+    std::vector<CFrag> cl;
+    for (size_t oi = 0; oi < order.size(); ++oi) {
+        std::vector<CFrag> fw, rv;
+        for (const CFrag& f : per[oi]) (f.ss > f.se ? rv : fw).push_back(f);
+        std::stable_sort(fw.begin(), fw.end(), [](const CFrag& a, const CFrag& b) { return a.ss != b.ss ? a.ss < b.ss : a.se < b.se; });
+        std::stable_sort(rv.begin(), rv.end(), [](const CFrag& a, const CFrag& b) { return a.ss != b.ss ? a.ss > b.ss : a.se > b.se; });
+        for (int pass = 0; pass < 2; ++pass) {
+            const std::vector<CFrag>& p = pass ? rv : fw;
+            cl.clear();
+            for (size_t k = 0; k < p.size(); ++k) {
+                bool closed = false;
+                if (k > 0)
+                    for (size_t e = cl.size(); e-- > 0;) {
+                        const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
+                        if (gap < sthr && p[k].qe > cl[e].qe) { closed = true; break; }
+                    }
+                if (k > 0 && !closed) { copies_cluster(cl, qthr, sthr, order[oi], longest); cl.clear(); }
+                cl.push_back(p[k]);
+            }
+            if (!cl.empty()) copies_cluster(cl, qthr, sthr, order[oi], longest);
+        }
+    }
+    std::stable_sort(longest.begin(), longest.end(), [](const CBest& a, const CBest& b) { return a.len > b.len; });   // :6997
+    result.clear();
+    for (const CBest& q : longest) {
+        if ((int)result.size() > max_copy_num) break;                                                               // :7002
+        int32_t a = q.ss, b = q.se, strand = 0;
+        if (a > b) { std::swap(a, b); strand = 1; }
+        bool ok = (double)q.len / (double)query_len >= query_coverage;
+        if (subject_coverage > 0) ok = ok && ((double)q.slen / (double)subj_len[q.subj] >= subject_coverage);
+        if (!ok) continue;
+        bool dup = false;
+        for (const hb_query_copy& o : result) if (o.subj == q.subj && o.start == a && o.end == b) { dup = true; break; }
+        if (!dup) result.push_back(hb_query_copy{q.subj, a, b, q.len, strand});
+    }
+    return 0;
+}

@@ -642,6 +642,19 @@ extern "C" int hb_fmea_chain(const hb_hsp* hsp, const uint64_t* q_off, uint32_t 
     return HB_OK;
 }
 
+extern "C" int hb_query_copies(const hb_hsp* hsp, const double* ident, uint32_t n, int query_len, const int32_t* subj_len,
+                               double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
+                               hb_query_copy* out, uint32_t cap, uint32_t* n_out) {
+    if (!n_out || (n && (!hsp || !ident)) || query_len <= 0) return HB_EINVAL;
+    std::vector<hb_query_copy> res;
+    hb_query_copies_run(hsp, ident, n, query_len, subj_len, query_coverage, subject_coverage, qthr, sthr, max_copy_num, res);
+    *n_out = (uint32_t)res.size();
+    if (!out) return HB_OK;
+    if (cap < res.size()) return HB_EINVAL;
+    if (!res.empty()) memcpy(out, res.data(), sizeof(hb_query_copy) * res.size());
+    return HB_OK;
+}
+
 extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
                                   hb_interval* out, uint64_t cap, uint64_t* n_out) {
     if (!ctx || !n_out) return HB_EINVAL;

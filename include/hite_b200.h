@@ -176,6 +176,18 @@ int hb_fmea_chain(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, cons
                   int max_len, int threads, hb_interval* out, uint64_t cap, uint64_t* n_out);
 
 /*
+ * hb_query_copies -- get_query_copies (module/Util.py:6828-7030; used by judge_Other_transposons.py:45 through
+ * Util.py:8382 and by pan_recover_low_copy_TEs): chain the HSPs of ONE query per subject into full-length
+ * copies (gap thresholds qthr/sthr, 200 in the reference), keep the longest chain per subject cluster, sort by
+ * length, apply query/subject coverage and max_copy_num.  ident[i] is the HSP's percent identity (part of the
+ * reference's visited-key).  Bit-identical to the reference on the same HSP list.  Host code (hb_fmea.cu).
+ */
+typedef struct { int32_t subj, start, end, qlen, strand; } hb_query_copy; /* (subject, start, end, len, 0 '+' / 1 '-') :7015 */
+int hb_query_copies(const hb_hsp* hsp, const double* ident, uint32_t n, int query_len, const int32_t* subj_len,
+                    double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
+                    hb_query_copy* out, uint32_t cap, uint32_t* n_out);
+
+/*
  * hb_coarse_boundary -- the all-vs-all step of process_blast_alignments (module/Util.py:4724-4780: n^2 blastn
  * runs of 1 Mbp segments) as one self-join of the minimizer index on the GPU (seed pairs -> radix sort ->
  * exact-diagonal runs = HSPs), followed by hb_fmea_chain.  Uses the genome + index of the context; segments

@@ -77,6 +77,11 @@ typedef struct { int32_t qseg, subj, qs, qe, ss, se; } hbo_hsp_rec;
 uint64_t hbo_self_hsps(const uint64_t *mm_pos, const uint64_t *idx, uint64_t n, uint64_t tot, int k,
                        const uint64_t *seg_goff, int n_seg, int occ_cap, hbo_hsp_rec *out, uint64_t cap);
 
+typedef struct { int32_t subj, start, end, qlen, strand; } hbo_copy_out;   /* (subject, start, end, len, '+'/'-') :7015 */
+int hbo_query_copies(const hbo_hsp *h, const double *ident, int n, int query_len, const int32_t *subj_len, int n_subj,
+                     double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
+                     hbo_copy_out *out, int cap);
+
 typedef struct { int32_t is_te, info, copy_num, cons_len; } hbo_result;
 int hbo_run_batch(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w, const uint8_t *cand_ascii,
                   const uint64_t *coff, uint32_t n_cand, int occ_cap, int max_loci, int flank, int max_rows, int plant,

@@ -196,3 +196,135 @@ int hbo_fmea(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_s
     free(keep); free(names); free(set.t); free(lq); free(fw); free(rv); free(cl); free(order); free(seen);
     return no;
 }
+
+/* ========================================================================================== */
+/* get_query_copies  module/Util.py:6828-7030 -- BLAST-HSP copy chaining of ONE query           */
+typedef struct { int32_t qs, qe, ss, se; double ident; int order; } cfrag_t;
+
+static int ccmp_fwd(const void *a, const void *b) {
+    const cfrag_t *x = (const cfrag_t *)a, *y = (const cfrag_t *)b;
+    if (x->ss != y->ss) return x->ss < y->ss ? -1 : 1;
+    if (x->se != y->se) return x->se < y->se ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int ccmp_rev(const void *a, const void *b) {
+    const cfrag_t *x = (const cfrag_t *)a, *y = (const cfrag_t *)b;
+    if (x->ss != y->ss) return x->ss > y->ss ? -1 : 1;
+    if (x->se != y->se) return x->se > y->se ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int ccmp_q(const void *a, const void *b) {
+    const cfrag_t *x = (const cfrag_t *)a, *y = (const cfrag_t *)b;
+    if (x->qs != y->qs) return x->qs < y->qs ? -1 : 1;
+    if (x->qe != y->qe) return x->qe < y->qe ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int csame(const cfrag_t *a, const cfrag_t *b) {
+    return a->qs == b->qs && a->qe == b->qe && a->ss == b->ss && a->se == b->se && a->ident == b->ident;
+}
+typedef struct { int32_t qs, qe, qlen, ss, se, slen, subj; int order; } clong_t;
+static int ccmp_len(const void *a, const void *b) {            /* sort(key=-len), stable */
+    const clong_t *x = (const clong_t *)a, *y = (const clong_t *)b;
+    if (x->qlen != y->qlen) return x->qlen > y->qlen ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+
+static void copies_cluster(cfrag_t *c, int n, int qthr, int sthr, int subj, clong_t **lq, int *nlq, int *cap) {
+    for (int i = 0; i < n; ++i) c[i].order = i;
+    qsort(c, (size_t)n, sizeof(cfrag_t), ccmp_q);                                   /* :6899 */
+    uint8_t *vis = (uint8_t *)calloc((size_t)n + 1, 1);
+    int32_t bqs = -1, bqe = -1, bql = -1, bss = -1, bse = -1, bsl = -1;
+    for (int i = 0; i < n; ++i) {
+        if (vis[i]) continue;
+        int32_t lqs = c[i].qs, lqe = c[i].qe, lss = c[i].ss, lse = c[i].se;
+        int32_t cur_len = c[i].qe - c[i].qs + 1;                                     /* :6919 */
+        for (int t = 0; t < n; ++t) if (csame(&c[t], &c[i])) vis[t] = 1;
+        for (int j = i + 1; j < n; ++j) {
+            if (vis[j]) continue;
+            const cfrag_t *e = &c[j];
+            if (e->qe > lqe) {
+                if (lss < lse && e->ss < e->se) {
+                    if (e->se > lse) {
+                        if (e->qs - lqe < qthr && e->ss - lse < sthr) {
+                            lqe = e->qe; lss = lss < e->ss ? lss : e->ss; lse = e->se;
+                            cur_len = lqe - lqs;                                    /* :6951 (no +1) */
+                            for (int t = 0; t < n; ++t) if (csame(&c[t], e)) vis[t] = 1;
+                        } else if (e->qs - lqe >= qthr) break;
+                    }
+                } else if (lss > lse && e->ss > e->se) {
+                    if (e->se < lse) {
+                        if (e->qs - lqe < qthr && lse - e->ss < sthr) {
+                            lqe = e->qe; lss = lss > e->ss ? lss : e->ss; lse = e->se;
+                            cur_len = lqe - lqs;
+                            for (int t = 0; t < n; ++t) if (csame(&c[t], e)) vis[t] = 1;
+                        } else if (e->qs - lqe >= qthr) break;
+                    }
+                }
+            }
+        }
+        if (cur_len > bql) {                                                        /* :6979-6989 */
+            bqs = lqs; bqe = lqe; bql = cur_len; bss = lss; bse = lse;
+            bsl = (lse > lss ? lse - lss : lss - lse) + 1;
+        }
+    }
+    free(vis);
+    if (bql != -1) {
+        if (*nlq == *cap) { *cap = *cap * 2 + 16; *lq = (clong_t *)realloc(*lq, sizeof(clong_t) * (size_t)*cap); }
+        clong_t *o = &(*lq)[*nlq];
+        o->qs = bqs; o->qe = bqe; o->qlen = bql; o->ss = bss; o->se = bse; o->slen = bsl; o->subj = subj; o->order = *nlq;
+        ++*nlq;
+    }
+}
+
+int hbo_query_copies(const hbo_hsp *h, const double *ident, int n, int query_len, const int32_t *subj_len, int n_subj,
+                     double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
+                     hbo_copy_out *out, int cap) {
+    int *order = (int *)malloc(sizeof(int) * (size_t)(n_subj + 1));
+    int *seen = (int *)calloc((size_t)n_subj + 1, sizeof(int));
+    int n_order = 0;
+    for (int i = 0; i < n; ++i) if (!seen[h[i].subj]) { seen[h[i].subj] = 1; order[n_order++] = h[i].subj; }
+    clong_t *lq = NULL; int nlq = 0, caplq = 0;
+    cfrag_t *fw = (cfrag_t *)malloc(sizeof(cfrag_t) * (size_t)(n + 1)), *rv = (cfrag_t *)malloc(sizeof(cfrag_t) * (size_t)(n + 1));
+    cfrag_t *cl = (cfrag_t *)malloc(sizeof(cfrag_t) * (size_t)(n + 1));
+    for (int oi = 0; oi < n_order; ++oi) {
+        const int s = order[oi];
+        int nf = 0, nr = 0;
+        for (int i = 0; i < n; ++i) {
+            if (h[i].subj != s) continue;
+            cfrag_t f = {h[i].qs, h[i].qe, h[i].ss, h[i].se, ident[i], 0};
+            if (f.ss > f.se) { f.order = nr; rv[nr++] = f; } else { f.order = nf; fw[nf++] = f; }
+        }
+        qsort(fw, (size_t)nf, sizeof(cfrag_t), ccmp_fwd);
+        qsort(rv, (size_t)nr, sizeof(cfrag_t), ccmp_rev);
+        for (int pass = 0; pass < 2; ++pass) {
+            cfrag_t *p = pass ? rv : fw; const int np = pass ? nr : nf;
+            int nc = 0;
+            for (int k = 0; k < np; ++k) {
+                int closed = 0;
+                if (k > 0)
+                    for (int e = nc - 1; e >= 0; --e) {
+                        const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
+                        if (gap < sthr && p[k].qe > cl[e].qe) { closed = 1; break; }
+                    }
+                if (k == 0 || closed) cl[nc++] = p[k];
+                else { copies_cluster(cl, nc, qthr, sthr, s, &lq, &nlq, &caplq); nc = 0; cl[nc++] = p[k]; }
+            }
+            if (nc > 0) copies_cluster(cl, nc, qthr, sthr, s, &lq, &nlq, &caplq);
+        }
+    }
+    qsort(lq, (size_t)nlq, sizeof(clong_t), ccmp_len);                              /* :6997 */
+    int no = 0;
+    for (int r = 0; r < nlq; ++r) {
+        if (no > max_copy_num) break;                                               /* :7002 */
+        int32_t a = lq[r].ss, b = lq[r].se, strand = 0;
+        if (a > b) { int32_t t = a; a = b; b = t; strand = 1; }
+        int ok = ((double)lq[r].qlen / (double)query_len >= query_coverage);
+        if (subject_coverage > 0) ok = ok && ((double)lq[r].slen / (double)subj_len[lq[r].subj] >= subject_coverage);
+        if (ok) for (int t = 0; t < no && t < cap; ++t) if (out[t].subj == lq[r].subj && out[t].start == a && out[t].end == b) { ok = 0; break; }
+        if (!ok) continue;
+        if (no < cap) { out[no].subj = lq[r].subj; out[no].start = a; out[no].end = b; out[no].qlen = lq[r].qlen; out[no].strand = strand; }
+        ++no;
+    }
+    free(lq); free(fw); free(rv); free(cl); free(order); free(seen);
+    return no;
+}

@@ -139,6 +139,27 @@ def fmea(query, subjects, self_subj, hsps, skip_gap, max_len):
     return ["%s:%d-%d" % (query[0], out[i].start, out[i].end) for i in range(k)]
 
 
+class HboCopyOut(C.Structure):
+    _fields_ = [("subj", C.c_int32), ("start", C.c_int32), ("end", C.c_int32), ("qlen", C.c_int32), ("strand", C.c_int32)]
+
+
+def query_copies(hsps, idents, query_len, subj_lens, query_coverage=0.95, subject_coverage=0.0, qthr=200, sthr=200,
+                 max_copy_num=100):
+    """get_query_copies (Util.py:6828) for one query -> [(subj, start, end, len, '+'|'-')]."""
+    n = len(hsps)
+    arr = (HboHsp * max(1, n))(*[HboHsp(*h) for h in hsps])
+    idn = (C.c_double * max(1, n))(*idents)
+    sl = (C.c_int32 * max(1, len(subj_lens)))(*subj_lens)
+    cap = n + 8
+    out = (HboCopyOut * cap)()
+    L = lib()
+    L.hbo_query_copies.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    k = L.hbo_query_copies(arr, idn, n, query_len, sl, len(subj_lens), query_coverage, subject_coverage, qthr, sthr,
+                           max_copy_num, out, cap)
+    return [(out[i].subj, out[i].start, out[i].end, out[i].qlen, "-" if out[i].strand else "+") for i in range(k)]
+
+
 def find_near_matches_ends(p, s, d):
     fs, fe, ls, le = C.c_int(-1), C.c_int(-1), C.c_int(-1), C.c_int(-1)
     n = lib().hbo_find_near_matches(p.encode(), len(p), s.encode(), len(s), d,

@@ -97,6 +97,20 @@ def run_reference_fmea(U, case, tmpdir):
     return list(d.keys())
 
 
+def run_reference_copies(U, case, tmpdir):
+    """get_query_copies (Util.py:6828) for one query named 'q' against subjects s0..sk."""
+    subject_dict = {}
+    for (si, qs, qe, ss, se), idn in zip(case["hsps"], case["idents"]):
+        subject_dict.setdefault("s%d" % si, []).append((qs, qe, ss, se, idn))
+    subj_path = os.path.join(tmpdir, "subj.fa")
+    with open(subj_path, "w") as f:
+        for i, ln in enumerate(case["subj_lens"]):
+            f.write(">s%d\n%s\n" % (i, "A" * ln))
+    res = U.get_query_copies([("q", subject_dict)], {"q": "A" * case["qlen"]}, subj_path, case["query_coverage"],
+                             case["subject_coverage"], max_copy_num=case["max_copy_num"])
+    return [[int(c[0][1:]), int(c[1]), int(c[2]), int(c[3]), c[4]] for c in res["q"]]
+
+
 def write(path, out):
     with gzip.GzipFile(path, "wb", mtime=0) as f:
         f.write(json.dumps(out, separators=(",", ":")).encode())
@@ -133,6 +147,17 @@ def main():
         with gzip.GzipFile(path, "wb", mtime=0) as f:
             f.write(json.dumps(recs, separators=(",", ":")).encode())
         print("wrote", path, len(recs), "cases;", sum(len(r["expect"]) for r in recs), "intervals;", os.path.getsize(path), "bytes")
+    with tempfile.TemporaryDirectory() as td:
+        recs = []
+        for seed in range(1, 201):
+            case = msa_synth.synth_copy_hsps(seed)
+            case["expect"] = run_reference_copies(U, case, td)
+            case["seed"] = seed
+            recs.append(case)
+        path = os.path.join(ROOT, "tests", "golden", "query_copies.json.gz")
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(json.dumps(recs, separators=(",", ":")).encode())
+        print("wrote", path, len(recs), "cases;", sum(len(r["expect"]) for r in recs), "copies;", os.path.getsize(path), "bytes")
     out = []
     with tempfile.TemporaryDirectory() as td:
         seeds = list(range(1, 161))

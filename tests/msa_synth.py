@@ -293,3 +293,42 @@ def synth_hsps(seed):
     rng.shuffle(hsps)
     return dict(query=query, subjects=subjects, self_subj=self_subj, hsps=hsps, skip_gap=skip_gap,
                 max_len=rng.choice([30000, 3000]))
+
+
+def synth_copy_hsps(seed):
+    """HSPs of ONE query (a TE of length qlen) against several subject sequences for get_query_copies
+    (reference module/Util.py:6828): full-length hits broken into pieces, partial hits, duplicates."""
+    rng = random.Random(seed)
+    qlen = rng.randint(300, 4000)
+    n_subj = rng.randint(1, 4)
+    subj_lens = [rng.randint(20_000, 200_000) for _ in range(n_subj)]
+    hsps, idents = [], []
+    for si in range(n_subj):
+        for _ in range(rng.randint(1, 8)):
+            spos = rng.randint(1, subj_lens[si] - qlen - 600)
+            strand = rng.random() < 0.4
+            lo = 1 if rng.random() < 0.7 else rng.randint(2, qlen // 3)
+            hi = qlen if rng.random() < 0.7 else rng.randint(2 * qlen // 3, qlen - 1)
+            pieces = rng.randint(1, 4)
+            cuts = sorted(rng.sample(range(lo + 10, hi - 10), pieces - 1)) if pieces > 1 and hi - lo > 60 else []
+            bounds = [lo] + cuts + [hi + 1]
+            qshift = sshift = 0
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                if b - a < 12:
+                    continue
+                qshift += rng.choice([0, 0, 3, 40, 150, 260]); sshift += rng.choice([0, 0, 3, 40, 150, 260])
+                qs, qe = a + qshift, b - 1 + qshift
+                if not strand:
+                    ss, se = spos + a + sshift, spos + b - 1 + sshift
+                else:
+                    ss, se = spos + qlen + 600 - a - sshift, spos + qlen + 600 - b + 1 - sshift
+                if min(ss, se) < 1 or max(ss, se) > subj_lens[si]:
+                    continue
+                hsps.append((si, qs, qe, ss, se)); idents.append(round(rng.uniform(80, 100), 3))
+                if rng.random() < 0.08:
+                    hsps.append((si, qs, qe, ss, se)); idents.append(idents[-1])
+    order = list(range(len(hsps)))
+    rng.shuffle(order)
+    return dict(qlen=qlen, subj_lens=subj_lens, hsps=[hsps[i] for i in order], idents=[idents[i] for i in order],
+                query_coverage=rng.choice([0.95, 0.8]), subject_coverage=rng.choice([0, 0, 0.001]),
+                max_copy_num=rng.choice([100, 3]))

@@ -176,3 +176,22 @@ def test_flanking_seq_matches_reference(tmp_path):
         exp = tmp_path / "a.fa"
         U.flanking_seq(str(lr), str(exp), str(ref), 50)
         assert exp.read_text() == text
+
+
+def test_product_query_copies_matches_reference_goldens(tmp_path):
+    """hb_query_copies / boundary.get_query_copies vs goldens from the imported reference get_query_copies."""
+    import gzip
+    import json
+    from hite_b200 import boundary
+    recs = json.loads(gzip.open(os.path.join(ROOT, "tests", "golden", "query_copies.json.gz")).read())
+    assert len(recs) >= 150
+    for rec in recs:
+        subject_dict = {}
+        for (si, qs, qe, ss, se), idn in zip(rec["hsps"], rec["idents"]):
+            subject_dict.setdefault("s%d" % si, []).append((qs, qe, ss, se, idn))
+        subj = tmp_path / "s.fa"
+        subj.write_text("".join(">s%d\n%s\n" % (i, "A" * ln) for i, ln in enumerate(rec["subj_lens"])))
+        res = boundary.get_query_copies([("q", subject_dict)], {"q": "A" * rec["qlen"]}, str(subj), rec["query_coverage"],
+                                        rec["subject_coverage"], max_copy_num=rec["max_copy_num"])
+        got = [[int(c[0][1:]), c[1], c[2], c[3], c[4]] for c in res["q"]]
+        assert got == rec["expect"], rec["seed"]

@@ -96,3 +96,13 @@ def test_oracle_fmea_matches_reference_goldens():
         r = oracle.fmea(tuple(rec["query"]), [tuple(s) for s in rec["subjects"]], rec["self_subj"],
                         [tuple(h) for h in rec["hsps"]], rec["skip_gap"], rec["max_len"])
         assert r == rec["expect"], rec["seed"]
+
+
+def test_oracle_query_copies_matches_reference_goldens():
+    import gzip, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    recs = json.loads(gzip.open(os.path.join(root, "tests", "golden", "query_copies.json.gz")).read())
+    for rec in recs:
+        r = oracle.query_copies([tuple(h) for h in rec["hsps"]], rec["idents"], rec["qlen"], rec["subj_lens"],
+                                rec["query_coverage"], rec["subject_coverage"], max_copy_num=rec["max_copy_num"])
+        assert r == [tuple(x) for x in rec["expect"]], rec["seed"]
