@@ -52,7 +52,7 @@ __device__ __forceinline__ int target_base(const uint32_t* __restrict__ gseq2, c
 
 // HB = half band = lanes per pair: 32 (o in [-32,31], one pair per warp) or 16 (o in [-16,15], two
 // pairs per warp) -- HB-align S7: the narrow band is used when the seed cluster's diagonal spread is
-// <= HB_NARROW_SPREAD.  Traceback stream: word (r>>3)*HB + sublane, nibble r&7, 128-word units.
+// <= HB_NARROW_SPREAD.  Traceback stream: word ((r>>6)*HB + sublane)*8 + ((r>>3)&7), nibble r&7, 128-word units.
 template <int HB>
 __global__ void __launch_bounds__(EXT_WARPS * 32)
 extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi,
@@ -123,6 +123,7 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
         }
         const uint32_t rbase = 65535u - (uint32_t)(64 * sup);
         const bool store = sup < my_super;
+        uint32_t tw[8];                                   // the 8 traceback words of this super-step
         int tnext = pt[0];
 #pragma unroll 4
         for (int u = 0; u < 32; ++u) {
@@ -149,10 +150,14 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
                 tbword |= nib << (4 * ((2 * u + 1) & 7));
                 H2 = H1; H1 = h; E1 = e; F1 = f;
             }
-            if ((u & 3) == 3) {
-                if (store) tb[(size_t)(8 * sup + (u >> 2)) * HB + sl] = tbword;      // 4*HB B per pair, coalesced
-                tbword = 0;
-            }
+            if ((u & 3) == 3) { tw[u >> 2] = tbword; tbword = 0; }
+        }
+        // lane-major layout: the 8 words (64 anti-diagonals) of one band column are one 32 B sector, so
+        // the traceback thread that walks down a diagonal reads one sector per 32 steps
+        if (store) {
+            uint4* dst = reinterpret_cast<uint4*>(tb + ((size_t)sup * HB + sl) * 8);
+            dst[0] = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+            dst[1] = make_uint4(tw[4], tw[5], tw[6], tw[7]);
         }
     }
     // ---- best cell: max score, then smallest i, then smallest j ------------------------------
@@ -205,31 +210,41 @@ traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t p
     uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
     int i = a.i_e, o = (int)(a.j_e - j0) - a.i_e, pending_d = 0;
     int i_s = i, o_s = o;
-    // four consecutive 8-step groups of the current lane column are fetched together (independent
-    // loads in flight): a diagonal run walks down the groups of one column
-    int c_lane = -1, g_hi = -1;                 // buffered: column c_lane, groups g_hi .. g_hi-3
-    uint32_t wb0 = 0, wb1 = 0, wb2 = 0, wb3 = 0;
+    // one 32 B sector = the 8 words (64 anti-diagonals) of one band column of one super-step
+    int c_sec = -1;
+    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
     auto fetch = [&](int ii, int oo) -> uint32_t {
         const int r = 2 * ii + oo + HB;
-        const int g = r >> 3, lc = (oo + HB) >> 1;
-        if (lc != c_lane || g > g_hi || g < g_hi - 3) {
-            c_lane = lc; g_hi = g;
-            const uint32_t* base = tb + (size_t)g * HB + lc;
-            wb0 = base[0];
-            wb1 = g >= 1 ? base[-(ptrdiff_t)HB] : 0u;
-            wb2 = g >= 2 ? base[-(ptrdiff_t)(2 * HB)] : 0u;
-            wb3 = g >= 3 ? base[-(ptrdiff_t)(3 * HB)] : 0u;
+        const int sec = (r >> 6) * HB + ((oo + HB) >> 1);
+        if (sec != c_sec) {
+            c_sec = sec;
+            const uint4* src = reinterpret_cast<const uint4*>(tb + (size_t)sec * 8);
+            s0 = src[0]; s1 = src[1];
         }
-        const int d = g_hi - g;
-        const uint32_t w = d == 0 ? wb0 : d == 1 ? wb1 : d == 2 ? wb2 : wb3;
+        const int g8 = (r >> 3) & 7;
+        const uint32_t w = g8 == 0 ? s0.x : g8 == 1 ? s0.y : g8 == 2 ? s0.z : g8 == 3 ? s0.w :
+                           g8 == 4 ? s1.x : g8 == 5 ? s1.y : g8 == 6 ? s1.z : s1.w;
         return (w >> (4 * (r & 7))) & 15u;
+    };
+    // edit records are staged 8 query positions (one 32 B sector) at a time instead of one scattered
+    // 4 B store per step
+    uint32_t blk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto record = [&](int ii, uint32_t v) {
+        blk[ii & 7] = v;
+        if ((ii & 7) == 0) {
+            uint4* dst = reinterpret_cast<uint4*>(qr + ii);
+            dst[0] = make_uint4(blk[0], blk[1], blk[2], blk[3]);
+            dst[1] = make_uint4(blk[4], blk[5], blk[6], blk[7]);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) blk[z] = 0;
+        }
     };
     while (i >= 0) {
         uint32_t nib = fetch(i, o);
         const uint32_t src = nib & 3u;
         if (src == 0) break;
         if (src == 1) {
-            qr[i] = (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 25);
+            record(i, (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 25));
             pending_d = 0; i_s = i; o_s = o;
             --i;
         } else if (src == 2) {                            // run of target-only bases
@@ -242,7 +257,7 @@ traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t p
             }
         } else {                                          // run of query-only bases
             for (;;) {
-                qr[i] = (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 24) | (1u << 25);
+                record(i, (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 24) | (1u << 25));
                 pending_d = 0; i_s = i; o_s = o;
                 const bool ext = (nib >> 3) & 1u;
                 --i; ++o;
@@ -250,6 +265,11 @@ traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t p
                 nib = fetch(i, o);
             }
         }
+    }
+    if (i >= 0 && (i & 7) != 7) {                         // partial sector holding i_s
+        uint4* dst = reinterpret_cast<uint4*>(qr + (i & ~7));
+        dst[0] = make_uint4(blk[0], blk[1], blk[2], blk[3]);
+        dst[1] = make_uint4(blk[4], blk[5], blk[6], blk[7]);
     }
     a.i_s = i_s; a.j_s = j0 + i_s + o_s;
     alns[p] = a;
