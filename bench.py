@@ -283,6 +283,13 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None                    # dram read+write bytes of the dominant kernel, one `ncu --set full` capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if not args.small and world == 1:
+                traffic = tj["extend_kernel<16>"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         achieved = algo_bytes / ext_s / 1e9 if ext_s > 0 else 0.0
         dp_cells = float(stage[7] / args.steps) * 1e6 * 32
         line = {
@@ -299,7 +306,7 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "extend_kernel (banded SW + traceback, hb_extend.cu)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "note": "integer-ALU-bound DP: %.2f GCUPS; algorithmic bytes/pair=(2L+64)*3/8+4L+56" % (dp_cells / ext_s / 1e9 if ext_s else 0),
                          "kernel_ms": ext_s * 1e3, "pairs": int(len(copies))},
             "stages_ms": {k: float(v / args.steps) for k, v in zip(

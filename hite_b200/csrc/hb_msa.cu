@@ -137,6 +137,7 @@ ins_max_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAln*
     if (!a.keep) return;
     const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
     uint32_t* dst = ins + coff[pairs[p].cand];
+#pragma unroll 4
     for (int q = a.i_s + lane; q <= a.i_e; q += 32) {
         const uint32_t d = (qr[q] >> 16) & 255u;
         if (d) atomicMax(&dst[q], d);
@@ -191,6 +192,7 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
     const uint32_t total_ins = C - (uint32_t)(L + 2 * flank);
     uint8_t* row = mat + mat_off[c] + (size_t)my_row * C;
     const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
+#pragma unroll 4
     for (int q = a.i_s + lane; q <= a.i_e; q += 32) {
         const uint32_t v = qr[q];
         const int64_t j = pr.j0 + q + ((int64_t)(v & 0xFFFF) - 32768);

@@ -543,6 +543,7 @@ __device__ void build_planes(Planes& P, uint32_t* __restrict__ pw, const uint8_t
         for (int wd = 0; wd < P.nw; ++wd) {
             uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
             const int kend = min(32, row_num - wd * 32);
+#pragma unroll 8
             for (int kk = 0; kk < kend; ++kk) {
                 const int s = m[(size_t)rows[wd * 32 + kk] * C + col];
                 const uint32_t bit = 1u << kk;

@@ -54,9 +54,11 @@ def full(path, out, cmd):
                     i = hdr.index(k)
                     f.write("| %s | %s | %s |\n" % (k, r[i], units[i]))
             try:
-                rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", ""))
-                wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
-                f.write("| traffic (read+write) | %.3f | %s |\n" % (rd + wr, units[hdr.index("dram__bytes_read.sum")]))
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+                ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+                rd = float(r[ir].replace(",", "")) * mult[units[ir]]
+                wr = float(r[iw].replace(",", "")) * mult[units[iw]]
+                f.write("| traffic (dram read+write) | %.0f | byte |\n" % (rd + wr))
             except Exception:
                 pass
             f.write("\n")
