@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <functional>
 #include <thread>
 #include <unordered_set>
 #include <vector>
@@ -70,43 +71,52 @@ struct KeyHash {
     }
 };
 
-// one query segment
-void fmea_query(const hb_hsp* h, size_t n, const hb_segment& q, int32_t q_index, const hb_segment* segs,
-                int skip_gap, int max_len, std::vector<hb_interval>& out) {
-    // subjects in order of first appearance (Python dict order, module/Util.py:4140-4147)
-    std::vector<int32_t> order;
-    std::vector<std::vector<Frag>> per;      // parallel to `order`
-    std::vector<int32_t> slot;               // subject id -> index in order (grown lazily)
+// chains of one (query, subject) pair: forward clusters, then reverse clusters (module/Util.py:4162-4319)
+void chain_subject(std::vector<Frag>& frags, int skip_gap, int subj, std::vector<Chain>& chains) {
+    std::vector<Frag> fw, rv, cl;
+    for (const Frag& f : frags) (f.ss > f.se ? rv : fw).push_back(f);                 // :4168-4172
+    std::stable_sort(fw.begin(), fw.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : a.se < b.se; });
+    std::stable_sort(rv.begin(), rv.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : a.se > b.se; });
+    for (int pass = 0; pass < 2; ++pass) {                                            // :4178-4227
+        const std::vector<Frag>& p = pass ? rv : fw;
+        cl.clear();
+        for (size_t k = 0; k < p.size(); ++k) {
+            bool closed = false;
+            if (k > 0)
+                for (size_t e = cl.size(); e-- > 0;) {
+                    const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
+                    if (gap < skip_gap && p[k].qe > cl[e].qe) { closed = true; break; }
+                }
+            if (k > 0 && !closed) { chain_cluster(cl, skip_gap, subj, chains); cl.clear(); }
+            cl.push_back(p[k]);
+        }
+        if (!cl.empty()) chain_cluster(cl, skip_gap, subj, chains);
+    }
+}
+
+// per query segment: subjects in order of first appearance (Python dict order, module/Util.py:4140-4147)
+struct QueryWork {
+    std::vector<int32_t> order;                  // subject ids in first-appearance order
+    std::vector<std::vector<Frag>> per;          // HSPs of each subject, file order
+    std::vector<std::vector<Chain>> chains;      // filled by the (query, subject) work items
+};
+
+void group_query(const hb_hsp* h, size_t n, int32_t q_index, QueryWork& w) {
+    std::vector<int32_t> slot;
     for (size_t i = 0; i < n; ++i) {
         const hb_hsp& x = h[i];
         if (x.subj == q_index && x.qs == x.ss && x.qe == x.se) continue;            // :4138
         if ((size_t)x.subj >= slot.size()) slot.resize((size_t)x.subj + 1, -1);
-        if (slot[x.subj] < 0) { slot[x.subj] = (int32_t)order.size(); order.push_back(x.subj); per.emplace_back(); }
-        per[slot[x.subj]].push_back(Frag{x.qs, x.qe, x.ss, x.se});
+        if (slot[x.subj] < 0) { slot[x.subj] = (int32_t)w.order.size(); w.order.push_back(x.subj); w.per.emplace_back(); }
+        w.per[slot[x.subj]].push_back(Frag{x.qs, x.qe, x.ss, x.se});
     }
+    w.chains.resize(w.order.size());
+}
+
+void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const hb_segment* segs, int max_len,
+                 std::vector<hb_interval>& out) {
     std::vector<Chain> chains;
-    std::vector<Frag> cl;
-    for (size_t oi = 0; oi < order.size(); ++oi) {
-        std::vector<Frag> fw, rv;
-        for (const Frag& f : per[oi]) (f.ss > f.se ? rv : fw).push_back(f);           // :4168-4172
-        std::stable_sort(fw.begin(), fw.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : a.se < b.se; });
-        std::stable_sort(rv.begin(), rv.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : a.se > b.se; });
-        for (int pass = 0; pass < 2; ++pass) {                                        // :4178-4227
-            const std::vector<Frag>& p = pass ? rv : fw;
-            cl.clear();
-            for (size_t k = 0; k < p.size(); ++k) {
-                bool closed = false;
-                if (k > 0)
-                    for (size_t e = cl.size(); e-- > 0;) {
-                        const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
-                        if (gap < skip_gap && p[k].qe > cl[e].qe) { closed = true; break; }
-                    }
-                if (k > 0 && !closed) { chain_cluster(cl, skip_gap, order[oi], chains); cl.clear(); }
-                cl.push_back(p[k]);
-            }
-            if (!cl.empty()) chain_cluster(cl, skip_gap, order[oi], chains);
-        }
-    }
+    for (const auto& c : w.chains) chains.insert(chains.end(), c.begin(), c.end());
     // 10-bp-rounded position de-duplication in visiting order (module/Util.py:4330-4390)
     std::unordered_set<Key, KeyHash> seen;
     struct Iv { int64_t a, b; };
@@ -148,23 +158,36 @@ void fmea_query(const hb_hsp* h, size_t n, const hb_segment& q, int32_t q_index,
 }  // namespace
 
 // HSPs must be grouped by query segment: query segment g owns hsp[q_off[g] .. q_off[g+1]).
+// Three phases over a thread pool: group per query, chain per (query, subject) pair (the bulk of the work,
+// 10^4 independent items for a 100-segment chunk), order-dependent de-duplication per query.
 int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
                 int max_len, int threads, std::vector<hb_interval>& result) {
+    std::vector<QueryWork> work(n_seg);
     std::vector<std::vector<hb_interval>> per(n_seg);
-    std::atomic<uint32_t> next{0};
-    auto work = [&]() {
-        for (;;) {
-            const uint32_t g = next.fetch_add(1);
-            if (g >= n_seg) break;
-            const uint64_t a = q_off[g], b = q_off[g + 1];
-            if (b > a) fmea_query(hsp + a, (size_t)(b - a), segs[g], (int32_t)g, segs, skip_gap, max_len, per[g]);
-        }
+    const int nt = std::max(1, threads);
+    auto run_pool = [&](size_t n_items, const std::function<void(size_t)>& fn) {
+        std::atomic<size_t> next{0};
+        auto loop = [&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n_items) break; fn(i); } };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < std::min<size_t>(nt, n_items); ++t) pool.emplace_back(loop);
+        loop();
+        for (auto& th : pool) th.join();
     };
-    const int nt = std::max(1, std::min<int>(threads, (int)n_seg));
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
+    run_pool(n_seg, [&](size_t g) {
+        const uint64_t a = q_off[g], b = q_off[g + 1];
+        if (b > a) group_query(hsp + a, (size_t)(b - a), (int32_t)g, work[g]);
+    });
+    std::vector<std::pair<uint32_t, uint32_t>> items;          // (query, subject slot)
+    for (uint32_t g = 0; g < n_seg; ++g)
+        for (uint32_t k = 0; k < work[g].order.size(); ++k) items.emplace_back(g, k);
+    run_pool(items.size(), [&](size_t i) {
+        QueryWork& w = work[items[i].first];
+        const uint32_t k = items[i].second;
+        chain_subject(w.per[k], skip_gap, w.order[k], w.chains[k]);
+    });
+    run_pool(n_seg, [&](size_t g) {
+        if (!work[g].order.empty()) dedup_query(work[g], segs[g], (int32_t)g, segs, max_len, per[g]);
+    });
     result.clear();
     for (uint32_t g = 0; g < n_seg; ++g) result.insert(result.end(), per[g].begin(), per[g].end());
     return 0;

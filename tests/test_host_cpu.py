@@ -195,3 +195,35 @@ def test_product_query_copies_matches_reference_goldens(tmp_path):
                                         rec["subject_coverage"], max_copy_num=rec["max_copy_num"])
         got = [[int(c[0][1:]), c[1], c[2], c[3], c[4]] for c in res["q"]]
         assert got == rec["expect"], rec["seed"]
+
+
+def test_drop_in_stage_scripts_patch_the_reference_namespace(monkeypatch, tmp_path):
+    """module/_hite_b200_patch.run_stage rebinds exactly the hot-path names in the reference's Util and then
+    runs the reference's own stage script (runpy), so main.py's call is unchanged."""
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "module", "Util.py")):
+        pytest.skip("reference checkout not mounted")
+    from oracle import ref_import
+    U = ref_import.load_util()                         # Util with the missing third-party imports stubbed
+    sys.path.insert(0, os.path.join(ROOT, "module"))
+    import _hite_b200_patch as patch
+    import runpy
+    ran = {}
+    monkeypatch.setenv("HITE_HOME", ref)
+    monkeypatch.setattr(runpy, "run_path", lambda path, run_name=None: ran.setdefault("path", path))
+    saved = {n: getattr(U, n) for n in ("flank_region_align_v5", "run_find_members_v8", "is_TE_from_align_file",
+                                        "determine_repeat_boundary_v5")}
+    try:
+        patch.run_stage("judge_TIR_transposons.py")
+        import hite_b200.boundary as hb
+        assert U.flank_region_align_v5 is hb.flank_region_align_v5
+        assert U.run_find_members_v8 is hb.run_find_members_v8
+        assert ran["path"].endswith("module/judge_TIR_transposons.py") and ran["path"].startswith(ref)
+        patch.run_stage("coarse_boundary.py", patch_names=("determine_repeat_boundary_v5",), source="hite_b200.coarse")
+        import hite_b200.coarse as hc
+        assert U.determine_repeat_boundary_v5 is hc.determine_repeat_boundary_v5
+    finally:
+        for n, f in saved.items():
+            setattr(U, n, f)
+    for s in ("coarse_boundary.py", "judge_TIR_transposons.py", "judge_Helitron_transposons.py", "judge_Non_LTR_transposons.py"):
+        assert os.access(os.path.join(ROOT, "module", s), os.X_OK)
