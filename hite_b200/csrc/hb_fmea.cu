@@ -11,7 +11,10 @@
 // (hb_coarse.cu).  Results are bit-identical to the reference on the same HSP list (tests/golden/fmea.json.gz).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <thread>
 #include <unordered_set>
@@ -21,17 +24,28 @@
 
 namespace {
 
-struct Frag { int32_t qs, qe, ss, se; };
+struct Frag { int32_t qs, qe, ss, se; int32_t ord; };      // ord: position before the current sort (stable order)
 
 struct Chain { int32_t qs, qe, ss, se, subj; };
 
 // greedy extension inside one subject cluster (module/Util.py:4229-4319)
-void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Chain>& out) {
-    std::stable_sort(c.begin(), c.end(), [](const Frag& a, const Frag& b) {
-        return a.qs != b.qs ? a.qs < b.qs : a.qe < b.qe;
+struct Key { int32_t chr; int64_t a, b; bool operator==(const Key& o) const { return chr == o.chr && a == o.a && b == o.b; } };
+// Per-worker scratch, reused across work items: repeated large malloc/free from many threads serialises on
+// the kernel's address-space lock (mmap/munmap), which made the pool anti-scale.
+struct Scratch {
+    std::vector<Frag> fw, rv, cl;
+    std::vector<char> used;
+    std::vector<Chain> chains;
+    std::vector<Key> table;
+};
+
+void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Chain>& out, std::vector<char>& used) {
+    for (size_t i = 0; i < c.size(); ++i) c[i].ord = (int32_t)i;
+    std::sort(c.begin(), c.end(), [](const Frag& a, const Frag& b) {          // == stable sort on (qs, qe)
+        return a.qs != b.qs ? a.qs < b.qs : (a.qe != b.qe ? a.qe < b.qe : a.ord < b.ord);
     });
     const size_t n = c.size();
-    std::vector<char> used(n, 0);
+    used.assign(n, 0);
     auto mark = [&](size_t i) {       // visited_frag is keyed by the HSP tuple: identical lines fall together
         for (size_t t = 0; t < n; ++t)
             if (c[t].qs == c[i].qs && c[t].qe == c[i].qe && c[t].ss == c[i].ss && c[t].se == c[i].se) used[t] = 1;
@@ -61,7 +75,6 @@ void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Cha
     }
 }
 
-struct Key { int32_t chr; int64_t a, b; bool operator==(const Key& o) const { return chr == o.chr && a == o.a && b == o.b; } };
 struct KeyHash {
     size_t operator()(const Key& k) const {
         uint64_t h = (uint64_t)k.chr * 0x9E3779B97F4A7C15ull;
@@ -72,11 +85,12 @@ struct KeyHash {
 };
 
 // chains of one (query, subject) pair: forward clusters, then reverse clusters (module/Util.py:4162-4319)
-void chain_subject(std::vector<Frag>& frags, int skip_gap, int subj, std::vector<Chain>& chains) {
-    std::vector<Frag> fw, rv, cl;
-    for (const Frag& f : frags) (f.ss > f.se ? rv : fw).push_back(f);                 // :4168-4172
-    std::stable_sort(fw.begin(), fw.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : a.se < b.se; });
-    std::stable_sort(rv.begin(), rv.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : a.se > b.se; });
+void chain_subject(const std::vector<Frag>& frags, int skip_gap, int subj, std::vector<Chain>& chains, Scratch& S) {
+    std::vector<Frag>&fw = S.fw, &rv = S.rv, &cl = S.cl;
+    fw.clear(); rv.clear();
+    for (const Frag& f : frags) { Frag g = f; std::vector<Frag>& dst = (f.ss > f.se ? rv : fw); g.ord = (int32_t)dst.size(); dst.push_back(g); }   // :4168-4172
+    std::sort(fw.begin(), fw.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : (a.se != b.se ? a.se < b.se : a.ord < b.ord); });
+    std::sort(rv.begin(), rv.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : (a.se != b.se ? a.se > b.se : a.ord < b.ord); });
     for (int pass = 0; pass < 2; ++pass) {                                            // :4178-4227
         const std::vector<Frag>& p = pass ? rv : fw;
         cl.clear();
@@ -87,10 +101,10 @@ void chain_subject(std::vector<Frag>& frags, int skip_gap, int subj, std::vector
                     const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
                     if (gap < skip_gap && p[k].qe > cl[e].qe) { closed = true; break; }
                 }
-            if (k > 0 && !closed) { chain_cluster(cl, skip_gap, subj, chains); cl.clear(); }
+            if (k > 0 && !closed) { chain_cluster(cl, skip_gap, subj, chains, S.used); cl.clear(); }
             cl.push_back(p[k]);
         }
-        if (!cl.empty()) chain_cluster(cl, skip_gap, subj, chains);
+        if (!cl.empty()) chain_cluster(cl, skip_gap, subj, chains, S.used);
     }
 }
 
@@ -108,17 +122,32 @@ void group_query(const hb_hsp* h, size_t n, int32_t q_index, QueryWork& w) {
         if (x.subj == q_index && x.qs == x.ss && x.qe == x.se) continue;            // :4138
         if ((size_t)x.subj >= slot.size()) slot.resize((size_t)x.subj + 1, -1);
         if (slot[x.subj] < 0) { slot[x.subj] = (int32_t)w.order.size(); w.order.push_back(x.subj); w.per.emplace_back(); }
-        w.per[slot[x.subj]].push_back(Frag{x.qs, x.qe, x.ss, x.se});
+        w.per[slot[x.subj]].push_back(Frag{x.qs, x.qe, x.ss, x.se, 0});
     }
     w.chains.resize(w.order.size());
 }
 
 void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const hb_segment* segs, int max_len,
-                 std::vector<hb_interval>& out) {
-    std::vector<Chain> chains;
+                 std::vector<hb_interval>& out, Scratch& S) {
+    std::vector<Chain>& chains = S.chains;
+    chains.clear();
     for (const auto& c : w.chains) chains.insert(chains.end(), c.begin(), c.end());
-    // 10-bp-rounded position de-duplication in visiting order (module/Util.py:4330-4390)
-    std::unordered_set<Key, KeyHash> seen;
+    // 10-bp-rounded position de-duplication in visiting order (module/Util.py:4330-4390); the set is a flat
+    // open-addressing table (8 keys per chain, no per-node allocation)
+    size_t cap = 64;
+    while (cap < chains.size() * 16 + 16) cap <<= 1;
+    std::vector<Key>& table = S.table;
+    table.assign(cap, Key{-1, 0, 0});
+    KeyHash hasher;
+    auto probe = [&](const Key& k, bool insert) -> bool {       // returns whether k was present
+        size_t i = hasher(k) & (cap - 1);
+        while (table[i].chr != -1) {
+            if (table[i] == k) return true;
+            i = (i + 1) & (cap - 1);
+        }
+        if (insert) table[i] = k;
+        return false;
+    };
     struct Iv { int64_t a, b; };
     std::vector<Iv> names;
     auto round10 = [](int64_t x, int64_t& lo, int64_t& hi) { lo = (x / 10) * 10; hi = lo + 10; };
@@ -131,10 +160,10 @@ void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const
         const Key ks[8] = {{s.chr, sa1, sb1}, {s.chr, sa1, sb2}, {s.chr, sa2, sb1}, {s.chr, sa2, sb2},
                            {q.chr, qa1, qb1}, {q.chr, qa1, qb2}, {q.chr, qa2, qb1}, {q.chr, qa2, qb2}};
         bool hit = false;
-        for (const Key& k : ks) hit = hit || seen.count(k);
+        for (const Key& k : ks) hit = hit || probe(k, false);
         const int64_t qlen = std::llabs((long long)ch.qe - (ch.qs - 1));
         if (!hit && qlen >= 80 && qlen < max_len) names.push_back(Iv{qa, qb});
-        for (const Key& k : ks) seen.insert(k);
+        for (const Key& k : ks) probe(k, true);
     }
     // >= 95 % overlap merge, longest first (module/Util.py:4529-4549)
     std::stable_sort(names.begin(), names.end(), [](const Iv& x, const Iv& y) { return (x.b - x.a) > (y.b - y.a); });
@@ -165,29 +194,44 @@ int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const 
     std::vector<QueryWork> work(n_seg);
     std::vector<std::vector<hb_interval>> per(n_seg);
     const int nt = std::max(1, threads);
-    auto run_pool = [&](size_t n_items, const std::function<void(size_t)>& fn) {
+    std::vector<Scratch> scratch((size_t)nt);
+    auto run_pool = [&](size_t n_items, const std::function<void(size_t, Scratch&)>& fn) {
         std::atomic<size_t> next{0};
-        auto loop = [&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n_items) break; fn(i); } };
+        std::atomic<int> workers{0};
+        std::atomic<long> busy_us{0};
+        auto loop = [&](int tid) { int did = 0; auto b0 = std::chrono::steady_clock::now(); for (;;) { const size_t i = next.fetch_add(1); if (i >= n_items) break; fn(i, scratch[(size_t)tid]); ++did; } if (did) workers++; busy_us += (long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - b0).count(); };
         std::vector<std::thread> pool;
-        for (int t = 1; t < std::min<size_t>(nt, n_items); ++t) pool.emplace_back(loop);
-        loop();
+        for (int t = 1; t < (int)std::min<size_t>((size_t)nt, n_items); ++t) pool.emplace_back(loop, t);
+        loop(0);
         for (auto& th : pool) th.join();
+        if (getenv("HB_DEBUG_TIMING")) fprintf(stderr, "[hb_fmea] pool: %zu items, nt=%d, spawned=%zu, workers that got items=%d, sum busy %.1f ms\n", n_items, nt, pool.size(), workers.load(), busy_us.load() * 1e-3);
     };
-    run_pool(n_seg, [&](size_t g) {
+    const bool dbg = getenv("HB_DEBUG_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[hb_fmea] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t0).count());
+        t0 = t;
+    };
+    run_pool(n_seg, [&](size_t g, Scratch&) {
         const uint64_t a = q_off[g], b = q_off[g + 1];
         if (b > a) group_query(hsp + a, (size_t)(b - a), (int32_t)g, work[g]);
     });
+    lap("group");
     std::vector<std::pair<uint32_t, uint32_t>> items;          // (query, subject slot)
     for (uint32_t g = 0; g < n_seg; ++g)
         for (uint32_t k = 0; k < work[g].order.size(); ++k) items.emplace_back(g, k);
-    run_pool(items.size(), [&](size_t i) {
+    run_pool(items.size(), [&](size_t i, Scratch& S) {
         QueryWork& w = work[items[i].first];
         const uint32_t k = items[i].second;
-        chain_subject(w.per[k], skip_gap, w.order[k], w.chains[k]);
+        chain_subject(w.per[k], skip_gap, w.order[k], w.chains[k], S);
     });
-    run_pool(n_seg, [&](size_t g) {
-        if (!work[g].order.empty()) dedup_query(work[g], segs[g], (int32_t)g, segs, max_len, per[g]);
+    lap("chain");
+    run_pool(n_seg, [&](size_t g, Scratch& S) {
+        if (!work[g].order.empty()) dedup_query(work[g], segs[g], (int32_t)g, segs, max_len, per[g], S);
     });
+    lap("dedup");
     result.clear();
     for (uint32_t g = 0; g < n_seg; ++g) result.insert(result.end(), per[g].begin(), per[g].end());
     return 0;
