@@ -62,8 +62,10 @@ def _mutate(rng, cons, sub, indel):
 
 def make_workload(genome_bp=2_000_000, n_contigs=2, n_families=20, cands_per_family=5, copies=(8, 40),
                   length=(200, 2000), sub=(0.0, 0.08), indel=0.004, tsd_choices=(2, 3, 4, 8, 9), seed=1,
-                  inexact_frac=0.4, rc_frac=0.5):
-    """Returns a Workload.  ``n_families * cands_per_family`` candidates."""
+                  inexact_frac=0.4, rc_frac=0.5, kind="tir"):
+    """Returns a Workload.  ``n_families * cands_per_family`` candidates.  ``kind``: 'tir' (terminal inverted
+    repeats + TSD), 'helitron' (5'-TC ... CTRR-3' inserted between A and T, no TSD, forward strand only so the
+    candidate carries the motif) or 'non_ltr' (polyA tail, 8-15 bp TSD, forward strand only)."""
     rng = np.random.default_rng(seed)
     clen = genome_bp // n_contigs
     contigs = [_ASCII[rng.integers(0, 4, size=clen, dtype=np.uint8)] for _ in range(n_contigs)]
@@ -80,6 +82,13 @@ def make_workload(genome_bp=2_000_000, n_contigs=2, n_families=20, cands_per_fam
         # avoid terminal TA/TTAA-like ambiguity about where the element starts being the common case
         body = _ASCII[rng.integers(0, 4, size=max(0, L - 2 * tir_len))]
         cons = np.concatenate([tir, body, revcomp_arr(tir)])
+        if kind == "helitron":
+            cons = _ASCII[rng.integers(0, 4, size=L)]
+            cons[:2] = np.frombuffer(b"TC", dtype=np.uint8)
+            cons[-4:] = np.frombuffer([b"CTAG", b"CTAA", b"CTGG", b"CTGA"][int(rng.integers(0, 4))], dtype=np.uint8)
+        elif kind == "non_ltr":
+            cons = _ASCII[rng.integers(0, 4, size=L)]
+            cons[-int(rng.integers(8, 20)):] = ord("A")
         n_copies = int(rng.integers(copies[0], copies[1] + 1))
         fam_sub = float(rng.uniform(sub[0], sub[1]))
         tsd_len = int(rng.choice(tsd_choices))
@@ -90,11 +99,27 @@ def make_workload(genome_bp=2_000_000, n_contigs=2, n_families=20, cands_per_fam
             c, s = slots[order[next_slot]]
             next_slot += 1
             cp = _mutate(rng, cons, fam_sub, indel)
-            strand = "-" if rng.random() < rc_frac else "+"
+            strand = "-" if (kind == "tir" and rng.random() < rc_frac) else "+"
             if strand == "-":
                 cp = revcomp_arr(cp)
             pos = s + int(rng.integers(60, 200))
             g = contigs[c]
+            if kind == "helitron":
+                # keep the termini exact (the motif search is exact), insertion site A | T, no TSD
+                cp[:2] = cons[:2]; cp[-4:] = cons[-4:]
+                g[pos - 1] = ord("A")
+                g[pos:pos + len(cp)] = cp
+                g[pos + len(cp)] = ord("T")
+                loci.append((c, pos, pos + len(cp), strand))
+                continue
+            if kind == "non_ltr":
+                k = int(rng.integers(8, 16))
+                ntail = int((cons[::-1] == ord("A")).argmin())
+                cp[-ntail:] = ord("A")                   # the polyA test is exact
+                g[pos:pos + len(cp)] = cp
+                g[pos + len(cp):pos + len(cp) + k] = g[pos - k:pos]
+                loci.append((c, pos, pos + len(cp), strand))
+                continue
             if tsd_len == 2:
                 g[pos - 2:pos] = np.frombuffer(b"TA", dtype=np.uint8)
             elif tsd_len == 3:
