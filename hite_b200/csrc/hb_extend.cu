@@ -12,13 +12,21 @@
 //   odd  s: left neighbour from the same lane, up neighbour from lane l+1,
 //   diagonal neighbour: same lane two steps earlier.
 // Integer DP (no tensor cores).  Scores: match +2, mismatch/N -4, gap open 4, gap extend 2.
+//
+// Two implementations of the same recurrence live here:
+//   * extend16_kernel (body in hb_extend16.cuh): two pairs per lane as s16x2 halves on the DPX
+//     instructions -- every candidate of at most HB16_MAX_L bases, i.e. practically all of them;
+//   * extend_kernel (below): one pair per lane in 32-bit registers, for longer candidates.
+// Pairs are routed by class through the order lists built by hb_extend_order_launch.
 #include "hb_common.cuh"
 #include "hb_extend.cuh"
+#include "hb_extend16.cuh"
+#include "hb_prims.cuh"
 
 namespace {
 
 constexpr int EXT_WARPS = 8;
-constexpr int HB_NARROW_SPREAD = 8;      // HB-align S7
+constexpr int HB_NARROW_SPREAD = hb16::NARROW_SPREAD;      // HB-align S7
 
 __device__ __forceinline__ int packed_base(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask,
                                            uint64_t p) {
@@ -74,7 +82,7 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
     if (active) {
         pr = pairs[p];
         const bool narrow = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD;
-        active = (HB == 16) ? narrow : !narrow;
+        active = ((HB == 16) ? narrow : !narrow) && (int)clen[pr.cand] > hb16::HB16_MAX_L;
     }
     if (!__ballot_sync(HB_FULL, active)) return;
     const int L = active ? (int)clen[pr.cand] : 0;
@@ -192,87 +200,67 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
     if (sl == 0) alns[p] = out;
 }
 
+// ---- two pairs per lane (hb_extend16.cuh) -----------------------------------------------------------
+struct DevWarp {
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ uint32_t shfl_up(uint32_t v, int d, int width) const { return __shfl_up_sync(HB_FULL, v, d, width); }
+    __device__ __forceinline__ uint32_t shfl_down(uint32_t v, int d, int width) const { return __shfl_down_sync(HB_FULL, v, d, width); }
+    __device__ __forceinline__ unsigned long long shfl_xor64(unsigned long long v, int off) const { return __shfl_xor_sync(HB_FULL, v, off); }
+    __device__ __forceinline__ int max_all(int v) const { return __reduce_max_sync(HB_FULL, v); }
+};
+
+template <int HB>
+__global__ void __launch_bounds__(EXT_WARPS * 32)
+extend16_kernel(const uint32_t* __restrict__ order, const uint64_t* __restrict__ n_order_p,
+                const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ gseq2,
+                const uint32_t* __restrict__ gnmask, uint64_t tot, const uint32_t* __restrict__ cseq2,
+                const uint32_t* __restrict__ cnmask, const uint64_t* __restrict__ cgoff,
+                const uint32_t* __restrict__ clen, const uint32_t* __restrict__ tb_unit_off, uint32_t tb_unit_base,
+                uint32_t* __restrict__ tbuf, HbAln* __restrict__ alns) {
+    constexpr int PPW = 32 / HB, WIN = HB + 32;
+    __shared__ uint32_t s_rq[EXT_WARPS * PPW * WIN];
+    __shared__ uint32_t s_rt[EXT_WARPS * PPW * WIN];
+    const uint32_t n_order = (uint32_t)*n_order_p;
+    const int wid = threadIdx.x >> 5;
+    const uint32_t group0 = (blockIdx.x * EXT_WARPS + wid) * PPW;
+    if (2ull * group0 >= n_order) return;                 // the grid is sized for the worst case
+    DevWarp w;
+    hb16::extend16_warp<HB>(w, group0, order, n_order, pairs, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen,
+                            tb_unit_off, tb_unit_base, tbuf, alns, s_rq + wid * PPW * WIN, s_rt + wid * PPW * WIN);
+}
+
+// class of every pair of [pair_lo, pair_hi): flag arrays for the two order lists
+__global__ void order_flag_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi,
+                                  const uint32_t* __restrict__ clen, uint32_t* __restrict__ flag_n,
+                                  uint32_t* __restrict__ flag_w) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair_lo + t >= pair_hi) return;
+    const HbLocus pr = pairs[pair_lo + t];
+    const bool fits = (int)clen[pr.cand] <= hb16::HB16_MAX_L;
+    const bool narrow = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD;
+    flag_n[t] = (fits && narrow) ? 1u : 0u;
+    flag_w[t] = (fits && !narrow) ? 1u : 0u;
+}
+__global__ void order_scatter_kernel(uint32_t pair_lo, uint32_t n, const uint32_t* __restrict__ flag_n,
+                                     const uint32_t* __restrict__ flag_w, const uint32_t* __restrict__ off_n,
+                                     const uint32_t* __restrict__ off_w, uint32_t* __restrict__ order_n,
+                                     uint32_t* __restrict__ order_w) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (flag_n[t]) order_n[off_n[t]] = pair_lo + t;
+    if (flag_w[t]) order_w[off_w[t]] = pair_lo + t;
+}
+
 // Traceback: ONE THREAD per pair (the walk is inherently serial; 32 independent walks per warp keep
-// the issue slots full where a warp-per-pair walk leaves 31 lanes idle).  A 32-bit word holds the
-// nibbles of 8 consecutive anti-diagonals of one lane, so a run of diagonal moves re-uses it 4 times.
+// the issue slots full where a warp-per-pair walk leaves 31 lanes idle).
 __global__ void __launch_bounds__(128)
 traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi,
                  const uint32_t* __restrict__ tb_unit_off, uint32_t tb_unit_base, const uint32_t* __restrict__ tbuf,
                  const uint32_t* __restrict__ qrec_unit_off, uint32_t* __restrict__ qrec, HbAln* __restrict__ alns) {
     const uint32_t p = pair_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= pair_hi) return;
-    HbAln a = alns[p];
-    if (a.score <= 0) return;
-    const HbLocus pr = pairs[p];
-    const int64_t j0 = pr.j0;
-    const int HB = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD ? 16 : 32;
-    const uint32_t* tb = tbuf + ((size_t)(tb_unit_off[p] - tb_unit_base) << 7);
-    uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
-    int i = a.i_e, o = (int)(a.j_e - j0) - a.i_e, pending_d = 0;
-    int i_s = i, o_s = o;
-    // one 32 B sector = the 8 words (64 anti-diagonals) of one band column of one super-step
-    int c_sec = -1;
-    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
-    auto fetch = [&](int ii, int oo) -> uint32_t {
-        const int r = 2 * ii + oo + HB;
-        const int sec = (r >> 6) * HB + ((oo + HB) >> 1);
-        if (sec != c_sec) {
-            c_sec = sec;
-            const uint4* src = reinterpret_cast<const uint4*>(tb + (size_t)sec * 8);
-            s0 = src[0]; s1 = src[1];
-        }
-        const int g8 = (r >> 3) & 7;
-        const uint32_t w = g8 == 0 ? s0.x : g8 == 1 ? s0.y : g8 == 2 ? s0.z : g8 == 3 ? s0.w :
-                           g8 == 4 ? s1.x : g8 == 5 ? s1.y : g8 == 6 ? s1.z : s1.w;
-        return (w >> (4 * (r & 7))) & 15u;
-    };
-    // edit records are staged 8 query positions (one 32 B sector) at a time instead of one scattered
-    // 4 B store per step
-    uint32_t blk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    auto record = [&](int ii, uint32_t v) {
-        blk[ii & 7] = v;
-        if ((ii & 7) == 0) {
-            uint4* dst = reinterpret_cast<uint4*>(qr + ii);
-            dst[0] = make_uint4(blk[0], blk[1], blk[2], blk[3]);
-            dst[1] = make_uint4(blk[4], blk[5], blk[6], blk[7]);
-#pragma unroll
-            for (int z = 0; z < 8; ++z) blk[z] = 0;
-        }
-    };
-    while (i >= 0) {
-        uint32_t nib = fetch(i, o);
-        const uint32_t src = nib & 3u;
-        if (src == 0) break;
-        if (src == 1) {
-            record(i, (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 25));
-            pending_d = 0; i_s = i; o_s = o;
-            --i;
-        } else if (src == 2) {                            // run of target-only bases
-            for (;;) {
-                ++pending_d;
-                const bool ext = (nib >> 2) & 1u;
-                --o;
-                if (!ext) break;
-                nib = fetch(i, o);
-            }
-        } else {                                          // run of query-only bases
-            for (;;) {
-                record(i, (uint32_t)(o + 32768) | ((uint32_t)min(pending_d, 255) << 16) | (1u << 24) | (1u << 25));
-                pending_d = 0; i_s = i; o_s = o;
-                const bool ext = (nib >> 3) & 1u;
-                --i; ++o;
-                if (!ext || i < 0) break;
-                nib = fetch(i, o);
-            }
-        }
-    }
-    if (i >= 0 && (i & 7) != 7) {                         // partial sector holding i_s
-        uint4* dst = reinterpret_cast<uint4*>(qr + (i & ~7));
-        dst[0] = make_uint4(blk[0], blk[1], blk[2], blk[3]);
-        dst[1] = make_uint4(blk[4], blk[5], blk[6], blk[7]);
-    }
-    a.i_s = i_s; a.j_s = j0 + i_s + o_s;
-    alns[p] = a;
+    hb16::traceback_pair(p, pairs, tb_unit_off, tb_unit_base, tbuf, qrec_unit_off, qrec, alns);
 }
 
 // sizes: tb units (512 B = 64 steps x 16 lanes x 4 bit) and qrec units (32 words) per pair
@@ -296,19 +284,47 @@ cudaError_t hb_pair_sizes_launch(const HbLocus* pairs, uint32_t n_pairs, const u
     return cudaGetLastError();
 }
 
+size_t hb_extend_order_words(uint32_t n_pairs) {
+    // flag_n, flag_w, off_n, off_w, order_n, order_w (n each), two totals (4 words), scan scratch
+    return 6 * ((size_t)n_pairs + 2) + 4 + hb_scan_tmp_words((size_t)n_pairs + 1);
+}
+
 cudaError_t hb_extend_launch(const HbLocus* pairs, uint32_t pair_lo, uint32_t pair_hi, const uint32_t* gseq2,
                              const uint32_t* gnmask, uint64_t tot, const uint32_t* cseq2, const uint32_t* cnmask,
                              const uint64_t* cgoff, const uint32_t* clen, const uint32_t* tb_unit_off,
                              uint32_t tb_unit_base, uint32_t* tbuf, const uint32_t* qrec_unit_off, uint32_t* qrec,
-                             HbAln* alns, cudaStream_t s) {
+                             HbAln* alns, uint32_t* order_ws, int any_long, uint32_t* launches, cudaStream_t s) {
     if (pair_hi <= pair_lo) return cudaSuccess;
     const uint32_t n = pair_hi - pair_lo;
-    // wide band: one pair per warp; narrow band: two pairs per warp.  Each kernel skips the other class.
-    extend_kernel<32><<<(n + EXT_WARPS - 1) / EXT_WARPS, EXT_WARPS * 32, 0, s>>>(
-        pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
-    extend_kernel<16><<<(n + 2 * EXT_WARPS - 1) / (2 * EXT_WARPS), EXT_WARPS * 32, 0, s>>>(
-        pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
+    const size_t st = (size_t)n + 2;
+    uint32_t *flag_n = order_ws, *flag_w = flag_n + st, *off_n = flag_w + st, *off_w = off_n + st,
+             *order_n = off_w + st, *order_w = order_n + st;
+    uint64_t* totals = reinterpret_cast<uint64_t*>(order_w + st);        // 6 * st words: 8 B aligned
+    uint32_t* scan_tmp = reinterpret_cast<uint32_t*>(totals + 2);
+    // ---- order lists: narrow / wide pairs whose candidate fits the 16-bit kernel ------------------
+    order_flag_kernel<<<(n + 255) / 256, 256, 0, s>>>(pairs, pair_lo, pair_hi, clen, flag_n, flag_w);
+    cudaError_t e = hb_exclusive_scan_u32(flag_n, off_n, n, scan_tmp, totals, s);
+    if (e != cudaSuccess) return e;
+    e = hb_exclusive_scan_u32(flag_w, off_w, n, scan_tmp, totals + 1, s);
+    if (e != cudaSuccess) return e;
+    order_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pair_lo, n, flag_n, flag_w, off_n, off_w, order_n, order_w);
+    // ---- 16-bit kernels: grids sized for "all pairs in this class", surplus blocks exit at once ----
+    extend16_kernel<32><<<(n + 2 * EXT_WARPS - 1) / (2 * EXT_WARPS), EXT_WARPS * 32, 0, s>>>(
+        order_w, totals + 1, pairs, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
+    extend16_kernel<16><<<(n + 4 * EXT_WARPS - 1) / (4 * EXT_WARPS), EXT_WARPS * 32, 0, s>>>(
+        order_n, totals, pairs, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
+    *launches += 10;
+    if (any_long) {
+        // 32-bit kernels: one pair per warp (wide band) / two pairs per warp (narrow); each skips the
+        // pairs of the other class and those the 16-bit kernels took
+        extend_kernel<32><<<(n + EXT_WARPS - 1) / EXT_WARPS, EXT_WARPS * 32, 0, s>>>(
+            pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
+        extend_kernel<16><<<(n + 2 * EXT_WARPS - 1) / (2 * EXT_WARPS), EXT_WARPS * 32, 0, s>>>(
+            pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
+        *launches += 2;
+    }
     traceback_kernel<<<(n + 127) / 128, 128, 0, s>>>(pairs, pair_lo, pair_hi, tb_unit_off, tb_unit_base, tbuf,
                                                       qrec_unit_off, qrec, alns);
+    *launches += 1;
     return cudaGetLastError();
 }

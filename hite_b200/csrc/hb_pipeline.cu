@@ -243,9 +243,11 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     if (prm->max_loci < 1 || prm->max_loci > 512 || prm->max_rows < 2 || prm->max_rows > 100 || prm->occ_cap < 1 ||
         prm->flank < 0 || prm->flank > 200)
         return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: parameter out of range");
+    int any_long = 0;                 // candidates beyond the 16-bit extension kernel (hb_extend16.cuh)
     for (uint32_t c = 0; c < n_cand; ++c) {
         const uint64_t L = cand_off[c + 1] - cand_off[c];
         if (L < 3 || L > 32000) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: candidate " + std::to_string(c) + " length must be in [3, 32000]");
+        if (L > HB_EXTEND16_MAX_L) any_long = 1;
     }
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
@@ -386,6 +388,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         const uint64_t alloc_units = std::min<uint64_t>(tb_units_total, budget_units);
         ENSURE("p.tbuf", (alloc_units + 1) << 9);
         ENSURE("p.qrec", ((qr_units_total + 1) << 5) * sizeof(uint32_t));
+        ENSURE("p.order", hb_extend_order_words(n_pairs) * sizeof(uint32_t));
         uint32_t lo = 0;
         while (lo < n_pairs) {
             uint32_t hi = lo + 1;
@@ -406,8 +409,8 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
                                         ctx->buf("g.nmask").as<uint32_t>(), tot, ctx->buf("c.seq2").as<uint32_t>(),
                                         ctx->buf("c.nmask").as<uint32_t>(), d_cgoff, d_clen, ctx->buf("p.tb_off").as<uint32_t>(),
                                         (uint32_t)base, ctx->buf("p.tbuf").as<uint32_t>(), ctx->buf("p.qr_off").as<uint32_t>(),
-                                        ctx->buf("p.qrec").as<uint32_t>(), ctx->buf("p.alns").as<HbAln>(), s));
-            launches += 3;
+                                        ctx->buf("p.qrec").as<uint32_t>(), ctx->buf("p.alns").as<HbAln>(),
+                                        ctx->buf("p.order").as<uint32_t>(), any_long, &launches, s));
             lo = hi;
         }
         ext_steps = tb_units_total * 32;                 // one 512 B unit = 64 anti-diagonals of 16 lanes
