@@ -133,10 +133,14 @@ HB_HD void cell2(uint32_t hl, uint32_t el, uint32_t hu, uint32_t fu, uint32_t hd
     const uint32_t s6 = minu2(qb & tb, K_6);              // 6 on a match, 0 otherwise
     const uint32_t dg = add2(hd4, s6);                    // H_diag - 4 + {6, 0}
     const uint32_t h = max3_relu(dg, e, f);
-    const uint32_t fa = minu2(e ^ hmz_e, K_1);
-    const uint32_t fb = minu2(f ^ hmz_f, K_1);
-    const uint32_t fc = minu2(dg ^ h, K_1);               // H != diag
-    const uint32_t fd = minu2(e ^ h, K_1);                // H != E
+    // e >= hmz_e, f >= hmz_f and h >= e hold per half (all >= 0), so plain 32-bit subtraction never borrows
+    // across the halves and can issue on the FMA pipe (IMAD.IADD); the kernel is ALU-pipe bound.  (At a
+    // band-edge lane the masked e / f may be below hmz: both halves sit on the edge there and the flag of
+    // such a cell is never read, see above.)
+    const uint32_t fa = minu2(e - hmz_e, K_1);
+    const uint32_t fb = minu2(f - hmz_f, K_1);
+    const uint32_t fc = minu2(dg ^ h, K_1);               // H != diag  (dg may be negative: xor, not minus)
+    const uint32_t fd = minu2(h - e, K_1);                // H != E
     const uint32_t fp = minu2(h, K_1);                    // H > 0
     const uint32_t s0 = fp & (~fc | fd);
     const uint32_t s1 = fp & fc;

@@ -166,12 +166,37 @@ layout_kernel(const uint64_t* __restrict__ coff, const uint32_t* __restrict__ cl
     if (lane == 0) n_cols[c] = (uint32_t)(L + 2 * flank) + carry;
 }
 
-// S10c: write one MSA row per kept pair (symbol codes; the matrix was pre-filled with HB_SYM_GAP)
+// S10c: column map of every candidate's MSA: entry of column x = ((q + flank) << 8) | slot, where q in
+// [-flank, L + flank) is the candidate position the column belongs to, slot 0 its base column and
+// slot t >= 1 the t-th insertion column after it.  Warp per candidate; shared by all rows of the candidate.
+__global__ void __launch_bounds__(128)
+colmap_kernel(const uint64_t* __restrict__ coff, const uint32_t* __restrict__ clen, uint32_t n_cand, int flank,
+              const uint32_t* __restrict__ pre, const uint32_t* __restrict__ n_cols,
+              const uint32_t* __restrict__ col_off, uint32_t* __restrict__ colq) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= n_cand) return;
+    const int L = (int)clen[c];
+    const uint32_t* pc = pre + coff[c];
+    const uint32_t total_ins = n_cols[c] - (uint32_t)(L + 2 * flank);
+    uint32_t* dst = colq + col_off[c];
+    for (int q = -flank + lane; q < L + flank; q += 32) {
+        const uint32_t p0 = q < 0 ? 0u : (q < L ? pc[q] : total_ins);
+        const uint32_t p1 = (q < 0 || q >= L) ? p0 : (q + 1 < L ? pc[q + 1] : total_ins);
+        const uint32_t base = (uint32_t)(q + flank) + p0;
+        for (uint32_t t = 0; t <= p1 - p0; ++t) dst[base + t] = ((uint32_t)(q + flank) << 8) | t;
+    }
+}
+
+// S10d: one MSA row per kept pair, column-centric: a warp walks the row's columns in address-aligned
+// groups of 4 per lane, derives every symbol (base, insertion base, flank base or gap) from the column
+// map and the pair's edit records, and writes whole 32-bit words -- gaps included, so the matrix needs
+// no pre-fill and each byte of it is written exactly once (HBM: R x C bytes out).
 __global__ void __launch_bounds__(256)
 msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAln* __restrict__ alns,
                  const uint32_t* __restrict__ qrec_unit_off, const uint32_t* __restrict__ qrec,
-                 const uint64_t* __restrict__ coff, const uint32_t* __restrict__ clen, const uint32_t* __restrict__ pre,
-                 const uint32_t* __restrict__ n_cols, const uint64_t* __restrict__ mat_off,
+                 const uint32_t* __restrict__ n_cols, const uint32_t* __restrict__ col_off,
+                 const uint32_t* __restrict__ colq, const uint64_t* __restrict__ mat_off,
                  const uint32_t* __restrict__ gseq2, const uint32_t* __restrict__ gnmask, uint64_t tot, int flank,
                  int trunc, uint8_t* __restrict__ mat) {
     const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -182,32 +207,40 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
     if (my_row < 0) return;
     // truncated pass keeps only the first 500 and last 500 bases of the extended copy
     const int64_t ext_lo = a.j_s - flank, ext_hi = a.j_e + flank;
-    auto kept = [&](int64_t j) -> bool { return !trunc || (j - ext_lo) < 500 || (ext_hi - j) < 500; };
     const HbLocus pr = pairs[p];
     const uint32_t c = pr.cand;
     const int rel = (int)pr.rel;
-    const int L = (int)clen[c];
-    const uint32_t C = n_cols[c];
-    const uint32_t* pc = pre + coff[c];
-    const uint32_t total_ins = C - (uint32_t)(L + 2 * flank);
+    const int C = (int)n_cols[c];
+    const uint32_t* cq = colq + col_off[c];
     uint8_t* row = mat + mat_off[c] + (size_t)my_row * C;
     const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
-#pragma unroll 4
-    for (int q = a.i_s + lane; q <= a.i_e; q += 32) {
-        const uint32_t v = qr[q];
-        const int64_t j = pr.j0 + q + ((int64_t)(v & 0xFFFF) - 32768);
-        const uint32_t col = (uint32_t)(q + flank) + pc[q];
-        if (!((v >> 24) & 1u) && kept(j)) row[col] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j);
-        const int d = (int)((v >> 16) & 255u);
-        for (int t = 0; t < d; ++t)
-            if (kept(j + 1 + t)) row[col + 1 + t] = (uint8_t)target_base(gseq2, gnmask, tot, rel, j + 1 + t);
-    }
-    for (int t = lane + 1; t <= flank; t += 32) {
-        const int ql = a.i_s - t, qh = a.i_e + t;
-        const uint32_t cl = (uint32_t)(ql + flank) + (ql >= 0 ? pc[ql] : 0u);
-        const uint32_t ch = (uint32_t)(qh + flank) + (qh < L ? pc[qh] : total_ins);
-        if (kept(a.j_s - t)) row[cl] = (uint8_t)target_base(gseq2, gnmask, tot, rel, a.j_s - t);
-        if (kept(a.j_e + t)) row[ch] = (uint8_t)target_base(gseq2, gnmask, tot, rel, a.j_e + t);
+    auto sym_at = [&](int col) -> uint32_t {
+        const uint32_t e = cq[col];
+        const int q = (int)(e >> 8) - flank, slot = (int)(e & 255u);
+        int64_t j;
+        if (q >= a.i_s && q <= a.i_e) {
+            const uint32_t v = qr[q];
+            j = pr.j0 + q + ((int64_t)(v & 0xFFFF) - 32768) + slot;
+            if (slot == 0 ? ((v >> 24) & 1u) != 0 : slot > (int)((v >> 16) & 255u)) return HB_SYM_GAP;
+        } else {
+            if (slot != 0) return HB_SYM_GAP;
+            if (q < a.i_s) { if (q < a.i_s - flank) return HB_SYM_GAP; j = a.j_s - (a.i_s - q); }
+            else { if (q > a.i_e + flank) return HB_SYM_GAP; j = a.j_e + (q - a.i_e); }
+        }
+        if (trunc && (j - ext_lo) >= 500 && (ext_hi - j) >= 500) return HB_SYM_GAP;
+        return (uint32_t)target_base(gseq2, gnmask, tot, rel, j);
+    };
+    const int a0 = (int)(reinterpret_cast<uintptr_t>(row) & 3u);        // virtual column x = col + a0 is word aligned
+    for (int x = 4 * lane; x < C + a0; x += 128) {
+        const int col = x - a0;
+        if (col >= 0 && col + 3 < C) {
+            const uint32_t w = sym_at(col) | (sym_at(col + 1) << 8) | (sym_at(col + 2) << 16) | (sym_at(col + 3) << 24);
+            *reinterpret_cast<uint32_t*>(row + col) = w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (col + t >= 0 && col + t < C) row[col + t] = (uint8_t)sym_at(col + t);
+        }
     }
 }
 
@@ -241,15 +274,22 @@ cudaError_t hb_layout_launch(const uint64_t* coff, const uint32_t* clen, uint32_
     layout_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(coff, clen, n_cand, flank, ins, n_cols);
     return cudaGetLastError();
 }
+cudaError_t hb_colmap_launch(const uint64_t* coff, const uint32_t* clen, uint32_t n_cand, int flank, const uint32_t* pre,
+                             const uint32_t* n_cols, const uint32_t* col_off, uint32_t* colq, cudaStream_t s) {
+    if (n_cand == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)n_cand * 32;
+    colmap_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(coff, clen, n_cand, flank, pre, n_cols, col_off, colq);
+    return cudaGetLastError();
+}
 cudaError_t hb_msa_write_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
-                                const uint32_t* qrec, const uint64_t* coff, const uint32_t* clen, const uint32_t* pre,
-                                const uint32_t* n_cols, const uint64_t* mat_off, const uint32_t* gseq2,
+                                const uint32_t* qrec, const uint32_t* n_cols, const uint32_t* col_off,
+                                const uint32_t* colq, const uint64_t* mat_off, const uint32_t* gseq2,
                                 const uint32_t* gnmask, uint64_t tot, int flank, int trunc, uint8_t* mat,
                                 cudaStream_t s) {
     if (n_pairs == 0) return cudaSuccess;
     const uint64_t threads = (uint64_t)n_pairs * 32;
-    msa_write_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(pairs, n_pairs, alns, qrec_unit_off, qrec, coff,
-                                                                       clen, pre, n_cols, mat_off, gseq2, gnmask, tot,
-                                                                       flank, trunc, mat);
+    msa_write_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(pairs, n_pairs, alns, qrec_unit_off, qrec, n_cols,
+                                                                       col_off, colq, mat_off, gseq2, gnmask, tot, flank,
+                                                                       trunc, mat);
     return cudaGetLastError();
 }

@@ -11,8 +11,11 @@ cudaError_t hb_ins_max_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAl
                               const uint32_t* qrec, const uint64_t* coff, uint32_t* ins, cudaStream_t s);
 cudaError_t hb_layout_launch(const uint64_t* coff, const uint32_t* clen, uint32_t n_cand, int flank, uint32_t* ins,
                              uint32_t* n_cols, cudaStream_t s);
+// column map ((q + flank) << 8 | slot per MSA column) of every candidate, at colq + col_off[c]
+cudaError_t hb_colmap_launch(const uint64_t* coff, const uint32_t* clen, uint32_t n_cand, int flank, const uint32_t* pre,
+                             const uint32_t* n_cols, const uint32_t* col_off, uint32_t* colq, cudaStream_t s);
 cudaError_t hb_msa_write_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
-                                const uint32_t* qrec, const uint64_t* coff, const uint32_t* clen, const uint32_t* pre,
-                                const uint32_t* n_cols, const uint64_t* mat_off, const uint32_t* gseq2,
+                                const uint32_t* qrec, const uint32_t* n_cols, const uint32_t* col_off,
+                                const uint32_t* colq, const uint64_t* mat_off, const uint32_t* gseq2,
                                 const uint32_t* gnmask, uint64_t tot, int flank, int trunc, uint8_t* mat,
                                 cudaStream_t s);

@@ -435,7 +435,12 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
                                  ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(), d_coff,
                                  ctx->buf("m.ins").as<uint32_t>(), s));
     HB_CUDA_OK(hb_layout_launch(d_coff, d_clen, n_cand, flank, ctx->buf("m.ins").as<uint32_t>(), ctx->buf("m.n_cols").as<uint32_t>(), s));
-    launches += 4;
+    // column offsets of the per-candidate column maps (device scan: no host round trip)
+    ENSURE("m.col_off", sizeof(uint32_t) * (n_cand + 1));
+    ENSURE("m.col_total", sizeof(uint64_t));
+    HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("m.n_cols").as<uint32_t>(), ctx->buf("m.col_off").as<uint32_t>(), n_cand,
+                                     ctx->buf("s.scan_tmp").as<uint32_t>(), ctx->buf("m.col_total").as<uint64_t>(), s));
+    launches += 7;
     std::vector<uint32_t> h_rows(n_cand), h_cols(n_cand), h_trows(n_cand);
     HB_CUDA_OK(cudaMemcpyAsync(h_trows.data(), ctx->buf("m.n_trows").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
     HB_CUDA_OK(cudaMemcpyAsync(h_rows.data(), ctx->buf("m.n_rows").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
@@ -487,12 +492,22 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     ENSURE("m.tmat_off", sizeof(uint64_t) * (n_cand + 1));
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("m.mat_off").p, h_mat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("m.tmat_off").p, h_tmat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
-    ENSURE("m.mat", mat_total + 1);
-    HB_CUDA_OK(cudaMemsetAsync(ctx->buf("m.mat").p, HB_SYM_GAP, mat_total + 1, s));
+    ENSURE("m.mat", mat_total + 4);
+    // every byte of every row is written by msa_write_kernel (gaps included): no pre-fill
+    {
+        uint64_t all_cols = 0;
+        for (uint32_t c = 0; c < n_cand; ++c) all_cols += h_cols[c];
+        if (all_cols >= (1ull << 32)) return hb_fail_msg(ctx, HB_ENOMEM, "hb_adjust: too many MSA columns in one call; pass fewer candidates");
+        ENSURE("m.colq", sizeof(uint32_t) * (all_cols + 1));
+        HB_CUDA_OK(hb_colmap_launch(d_coff, d_clen, n_cand, flank, ctx->buf("m.ins").as<uint32_t>(), ctx->buf("m.n_cols").as<uint32_t>(),
+                                    ctx->buf("m.col_off").as<uint32_t>(), ctx->buf("m.colq").as<uint32_t>(), s));
+        ++launches;
+    }
     for (int trunc = 0; trunc <= (n_tasks > n_full ? 1 : 0); ++trunc) {
         HB_CUDA_OK(hb_msa_write_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, ctx->buf("p.alns").as<HbAln>(),
-                                       ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(), d_coff, d_clen,
-                                       ctx->buf("m.ins").as<uint32_t>(), ctx->buf("m.n_cols").as<uint32_t>(),
+                                       ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(),
+                                       ctx->buf("m.n_cols").as<uint32_t>(), ctx->buf("m.col_off").as<uint32_t>(),
+                                       ctx->buf("m.colq").as<uint32_t>(),
                                        ctx->buf(trunc ? "m.tmat_off" : "m.mat_off").as<uint64_t>(), ctx->buf("g.seq2").as<uint32_t>(),
                                        ctx->buf("g.nmask").as<uint32_t>(), tot, flank, trunc, ctx->buf("m.mat").as<uint8_t>(), s));
         ++launches;
