@@ -17,6 +17,7 @@
 #include "hb_seed.cuh"
 
 extern "C" size_t hb_vote_match_entry_size();
+extern "C" size_t hb_vote_state_entries();
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
                                       uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
                                       uint8_t* d_cons, HbVoteCall* d_calls, int te_type, cudaStream_t stream);
@@ -465,7 +466,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         t.te_type = prm->te_type; t.plant = prm->plant; t.result_type = prm->result_type; t.raw_is_ascii = 0;
         tasks.push_back(t); task_cand.push_back(c);
         col_total += h_cols[c];
-        match_total += 2ull * ((uint64_t)h_cols[c] + 2);
+        match_total += 2ull * ((uint64_t)h_cols[c] + 2) + hb_vote_state_entries();
         row_total += rows;
     };
     for (uint32_t c = 0; c < n_cand; ++c) {

@@ -166,7 +166,7 @@ struct Hist {  // last 32 non-gap symbols, most recent first
 // smallest a with lev(p, s[a:e]) == dist  (oracle/fnm.py::_longest_start).  Bit-parallel: the
 // reversed pattern is aligned globally-at-the-start against the text read backwards from e, so after
 // k symbols the running score is lev(p, s[e-k:e]); the largest k that reaches `dist` wins.
-__device__ int longest_start(const Pattern& P, const Hist& H, int e, int dist) {
+__device__ __noinline__ int longest_start(const Pattern& P, const Hist& H, int e, int dist) {
     const int m = P.m;
     int maxk = m + dist; if (maxk > e) maxk = e;
     uint32_t peq_r[5];
@@ -197,7 +197,7 @@ struct Match { int a, e, d; };
 
 // One row: run both patterns over the ungapped row, emit (start,end,dist) of every end with
 // dist <= 2 into mlist[0..cap) / mlist[cap..2cap).  Returns via cnt[0], cnt[1] (smem).
-__device__ void anchor_scan_row(const uint8_t* __restrict__ row, int Cc, const Pattern& P1, const Pattern& P2,
+__device__ __noinline__ void anchor_scan_row(const uint8_t* __restrict__ row, int Cc, const Pattern& P1, const Pattern& P2,
                                 Match* __restrict__ mlist, int cap, int* cnt, int lane,
                                 int* ub_out, int* n_out) {
     const int chunk = (Cc + 31) >> 5;
@@ -245,7 +245,7 @@ __device__ __forceinline__ unsigned long long match_key(const Match& m) {
 }
 
 // best match of the first overlap-group (by start) -> its start
-__device__ int first_group_best_start(const Match* l, int n, int lane) {
+__device__ __noinline__ int first_group_best_start(const Match* l, int n, int lane) {
     int gs = 0x7fffffff;
     for (int i = lane; i < n; i += 32) gs = min(gs, l[i].a);
     gs = warp_min(gs);
@@ -263,7 +263,7 @@ __device__ int first_group_best_start(const Match* l, int n, int lane) {
     return (int)((k >> 26) & 0x3ffffffull);
 }
 // best match of the last overlap-group -> its end
-__device__ int last_group_best_end(const Match* l, int n, int lane) {
+__device__ __noinline__ int last_group_best_end(const Match* l, int n, int lane) {
     int ge = -1;
     for (int i = lane; i < n; i += 32) ge = max(ge, l[i].e);
     ge = warp_max(ge);
@@ -281,7 +281,7 @@ __device__ int last_group_best_end(const Match* l, int n, int lane) {
     return (int)(k & 0x3ffffffull);
 }
 // column of the idx-th non-gap symbol of the row (lanes own [lo,hi) with ungapped base ub)
-__device__ int column_of_ungapped(const uint8_t* row, int Cc, int idx, int ub, int lane) {
+__device__ __noinline__ int column_of_ungapped(const uint8_t* row, int Cc, int idx, int ub, int lane) {
     const int chunk = (Cc + 31) >> 5;
     const int lo = min(Cc, lane * chunk), hi = min(Cc, lo + chunk);
     int col = -1, k = ub;
@@ -313,7 +313,7 @@ struct Planes {
 
 // collect <= 100 valid columns (gaps <= valid_col_threshold) scanning from `start` in direction
 // dir while lo_bound <= col < hi_bound  (Util.py:8924-8947, 8976-8999, 9036-9060, 9096-9120)
-__device__ int collect_valid(const Planes& P, int vthr, int start, int dir, int lo_bound, int hi_bound,
+__device__ __noinline__ int collect_valid(const Planes& P, int vthr, int start, int dir, int lo_bound, int hi_bound,
                              int* vc, int lane) {
     int n = 0;
     for (int c0 = start; n < 100; c0 += 32 * dir) {
@@ -339,7 +339,7 @@ __device__ void reverse_list(int* vc, int n, int lane) {
 }
 
 // calculate_window_homology (Util.py:8827-8885); window columns are first + step*k, k < ncols
-__device__ int window_homology(const Planes& P, int first, int ncols, int step, double thr, int lane) {
+__device__ __noinline__ int window_homology(const Planes& P, int first, int ncols, int step, double thr, int lane) {
     uint32_t valid[4] = {0, 0, 0, 0};
     int nv = 0;
     for (int wd = 0; wd < P.nw; ++wd) {
@@ -376,7 +376,7 @@ __device__ int window_homology(const Planes& P, int first, int ncols, int step, 
 }
 
 // slide windows of wsize over the valid-column list (Util.py:8958-8965, 9010-9017, 9072-9079, 9130-9137)
-__device__ int slide_windows(const Planes& P, const int* vc, int n, int wsize, int step, double thr, int lane) {
+__device__ __noinline__ int slide_windows(const Planes& P, const int* vc, int n, int wsize, int step, double thr, int lane) {
     for (int i = 0; i + wsize <= n; ++i) {
         const int first = vc[i], last = vc[i + wsize - 1];
         // step>0: range(first, last+1) ; step<0: range(first, last+1, -1) = first .. last+2
@@ -394,7 +394,7 @@ __device__ int slide_windows(const Planes& P, const int* vc, int n, int wsize, i
 }
 
 // search_boundary_homo_v3 (Util.py:8887-9143)
-__device__ int search_boundary_v3(const Planes& P, int vthr, int pos, int Cc, bool is_start, double thr,
+__device__ __noinline__ int search_boundary_v3(const Planes& P, int vthr, int pos, int Cc, bool is_start, double thr,
                                   int int_win, int out_win, int* vc, int lane) {
     int cur, n, w, nb;
     if (is_start) {
@@ -453,7 +453,7 @@ __device__ __forceinline__ int vote_column(const Planes& P, int col, int half) {
 }
 
 // TSDsearch_v5 (Util.py:2460-2492) on one row: returns 1 iff a TSD is found
-__device__ int tsd_search_v5(const uint8_t* row, int Cc, int bs, int be, int plant) {
+__device__ __noinline__ int tsd_search_v5(const uint8_t* row, int Cc, int bs, int be, int plant) {
     // ungapped neighbourhoods (get_boundary_ungap_str :2407-2429), 4 bits per symbol
     unsigned long long L = 0, Rr = 0;   // L[i]: i-th non-gap going left from bs-1 ; Rr[i]: i-th going right from be+1
     int nL = 0, nR = 0;
@@ -495,7 +495,7 @@ __device__ int tsd_search_v5(const uint8_t* row, int Cc, int bs, int be, int pla
     return found;
 }
 
-__device__ int lev5(const char* a, int la, const char* b, int lb) {
+__device__ __noinline__ int lev5(const char* a, int la, const char* b, int lb) {
     int prev[8], cur[8];
     for (int j = 0; j <= lb; ++j) prev[j] = j;
     for (int i = 1; i <= la; ++i) {
@@ -516,7 +516,7 @@ __device__ __forceinline__ bool starts_with(const char* s, int n, const char* p,
 }
 
 // anchors of one row (Util.py:9158-9181): true iff both 20-mers hit; columns in *as, *ae
-__device__ bool row_anchor(const uint8_t* __restrict__ row, int Cc, int cap, const Pattern& P1, const Pattern& P2,
+__device__ __noinline__ bool row_anchor(const uint8_t* __restrict__ row, int Cc, int cap, const Pattern& P1, const Pattern& P2,
                            Match* __restrict__ ml, int* cnt, int lane, int* as, int* ae) {
     int ub, n;
     anchor_scan_row(row, Cc, P1, P2, ml, cap, cnt, lane, &ub, &n);
@@ -531,7 +531,7 @@ __device__ bool row_anchor(const uint8_t* __restrict__ row, int Cc, int cap, con
 }
 
 // six bit-planes of the listed rows (row k of the list = bit k&31 of word k>>5)
-__device__ void build_planes(Planes& P, uint32_t* __restrict__ pw, const uint8_t* __restrict__ m, int C, int Cc,
+__device__ __noinline__ void build_planes(Planes& P, uint32_t* __restrict__ pw, const uint8_t* __restrict__ m, int C, int Cc,
                              const unsigned short* rows, int row_num, int lane) {
     P.p = pw; P.stride = C; P.nw = (row_num + 31) >> 5; P.row_num = row_num;
     for (int wd = 0; wd < 4; ++wd) {
@@ -560,7 +560,7 @@ __device__ void build_planes(Planes& P, uint32_t* __restrict__ pw, const uint8_t
 
 // rows (in order) that have a non-gap symbol in [lo1,hi1) and in [lo2,hi2); at most MAX_KEPT
 // ("len(...) > 100: break", Util.py:9201 / :10017)
-__device__ int select_rows(const uint8_t* __restrict__ m, int R, int C, int lo1, int hi1, int lo2, int hi2,
+__device__ __noinline__ int select_rows(const uint8_t* __restrict__ m, int R, int C, int lo1, int hi1, int lo2, int hi2,
                            unsigned short* rows, int lane) {
     int row_num = 0;
     for (int r0 = 0; r0 < R && row_num < MAX_KEPT; r0 += 32) {
@@ -583,7 +583,7 @@ __device__ int select_rows(const uint8_t* __restrict__ m, int R, int C, int lo1,
 }
 
 // ---- Helitron helpers: search_boundary_homo_v4 (Util.py:8556-8824) ---------------------------
-__device__ double ordered_ratio_avg(const Planes& P, const int* vc, int w, int lane) {
+__device__ __noinline__ double ordered_ratio_avg(const Planes& P, const int* vc, int w, int lane) {
     // mean of the stored per-column max_homo_ratio (denominator row_num, :8607) in list order
     double total = 0.0;
     for (int k0 = 0; k0 < w; k0 += 32) {
@@ -602,7 +602,7 @@ __device__ double ordered_ratio_avg(const Planes& P, const int* vc, int w, int l
     return total / (double)w;
 }
 
-__device__ bool search_boundary_v4(const Planes& P, int vthr, int pos, int Cc, bool is_start, double thr,
+__device__ __noinline__ bool search_boundary_v4(const Planes& P, int vthr, int pos, int Cc, bool is_start, double thr,
                                    double int_thr, double out_thr, int int_win, int out_win, int* vc, int lane,
                                    int* boundary) {
     int n, w, nb, cur;
@@ -666,10 +666,10 @@ struct Front {
     Planes P;
     int row_num, hs, he, vl, vr, Cc;
 };
-__device__ bool judge_front_v3(const HbVoteTask& t, HbVoteCall& call, const uint8_t* __restrict__ m,
-                               uint32_t* __restrict__ planes, Match* __restrict__ matches,
-                               const uint8_t* __restrict__ cands, double thr_many, int fl1_copy_num_is_rows,
-                               int* vc, unsigned short* rows, int* cnt, int lane, Front& F) {
+// phase a: call defaults + anchors (:9151-9187).  false: `call` holds the verdict ('nb').
+__device__ __noinline__ bool front_anchors(const HbVoteTask& t, HbVoteCall& call, const uint8_t* __restrict__ m,
+                                           Match* __restrict__ matches, const uint8_t* __restrict__ cands, int* cnt,
+                                           int lane, Front& F, int* as_out, int* ae_out) {
     const int R = t.R, C = t.C, Cc = call.clean_cols;
     F.Cc = Cc;
     call.is_te = 0; call.info = 0; call.copy_num = 0; call.align_start = -1; call.align_end = -1;
@@ -688,8 +688,15 @@ __device__ bool judge_front_v3(const HbVoteTask& t, HbVoteCall& call, const uint
             if (row_anchor(m + (size_t)r * C, Cc, C + 2, P1, P2, ml, cnt, lane, &as, &ae)) break;
     }
     call.align_start = as; call.align_end = ae;
+    *as_out = as; *ae_out = ae;
     if (as < 0 || ae < 0) { call.info = 1; return false; }                     // :9184-9187
-    // ---- 2. full-length member filter (:9196-9217) -----------------------------------------
+    return true;
+}
+// phase b: full-length member filter (:9196-9225) + bit-planes of the kept rows.  false: verdict 'fl1'.
+__device__ __noinline__ bool front_members(const HbVoteTask& t, HbVoteCall& call, const uint8_t* __restrict__ m,
+                                           uint32_t* __restrict__ planes, int as, int ae, int fl1_copy_num_is_rows,
+                                           unsigned short* rows, int lane, Front& F) {
+    const int R = t.R, C = t.C, Cc = F.Cc;
     int e_lo, e_hi;
     py_slice(Cc, (long long)ae - 10, (ae + 10 < Cc) ? ae + 10 : Cc, &e_lo, &e_hi);
     const int row_num = select_rows(m, R, C, max(0, as - 10), min(Cc, as + 10), e_lo, e_hi, rows, lane);
@@ -699,12 +706,16 @@ __device__ bool judge_front_v3(const HbVoteTask& t, HbVoteCall& call, const uint
         return false;
     }
     call.copy_num = row_num;
-    // ---- 3. bit-planes of the kept rows -----------------------------------------------------
     build_planes(F.P, planes + t.plane_off, m, C, Cc, rows, row_num, lane);
+    return true;
+}
+// phase c: outermost valid columns (:9269-9294) + homology boundaries (:9297-9308).
+__device__ __noinline__ bool front_boundaries(HbVoteCall& call, int as, int ae, double thr_many, int* vc, int lane,
+                                              Front& F) {
     const Planes& P = F.P;
+    const int Cc = F.Cc, row_num = F.row_num;
     const int vthr = row_num / 2;                                              // int(row_num/2) :9238
     const double thr = row_num <= 2 ? 0.95 : (row_num <= 5 ? 0.9 : thr_many);  // :9240-9245 / :9579-9584
-    // ---- 4. outermost valid columns (:9269-9294) --------------------------------------------
     int vl = -1, vr = -1;
     for (int c0 = 0; c0 < Cc; c0 += 32) {
         const int c = c0 + lane;
@@ -720,7 +731,6 @@ __device__ bool judge_front_v3(const HbVoteTask& t, HbVoteCall& call, const uint
     }
     if (!(vl != -1 && vr != -1 && vl < vr)) { vl = -1; vr = -1; }
     F.vl = vl; F.vr = vr;
-    // ---- 5. homology boundaries (:9297-9308) -------------------------------------------------
     F.hs = search_boundary_v3(P, vthr, as, Cc, true, thr, 20, 10, vc, lane);
     call.homo_start = F.hs;
     if (F.hs == -1) return false;
@@ -729,9 +739,18 @@ __device__ bool judge_front_v3(const HbVoteTask& t, HbVoteCall& call, const uint
     if (F.he == -1) return false;
     return true;
 }
+__device__ bool judge_front_v3(const HbVoteTask& t, HbVoteCall& call, const uint8_t* __restrict__ m,
+                               uint32_t* __restrict__ planes, Match* __restrict__ matches,
+                               const uint8_t* __restrict__ cands, double thr_many, int fl1_copy_num_is_rows,
+                               int* vc, unsigned short* rows, int* cnt, int lane, Front& F) {
+    int as, ae;
+    if (!front_anchors(t, call, m, matches, cands, cnt, lane, F, &as, &ae)) return false;
+    if (!front_members(t, call, m, planes, as, ae, fl1_copy_num_is_rows, rows, lane, F)) return false;
+    return front_boundaries(call, as, ae, thr_many, vc, lane, F);
+}
 
 // column-vote consensus of columns [hs, he] written to cons (Util.py:9312-9346); returns its length
-__device__ int vote_consensus(const Planes& P, const uint8_t* __restrict__ m, int C, const unsigned short* rows,
+__device__ __noinline__ int vote_consensus(const Planes& P, const uint8_t* __restrict__ m, int C, const unsigned short* rows,
                               int hs, int he, int result_type, uint8_t* __restrict__ cons, int lane) {
     int ml = 0;
     for (int c0 = hs; c0 <= he; c0 += 32) {
@@ -750,30 +769,115 @@ __device__ int vote_consensus(const Planes& P, const uint8_t* __restrict__ m, in
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel B: judge_boundary_v5 (TIR, Util.py:9145-9480), one warp per candidate.
+// kernel B: judge_boundary_v5 (TIR, Util.py:9145-9480), one warp per candidate, run as FOUR phase
+// kernels (anchors | member filter + bit-planes | boundaries | consensus + TSD trimming).  As a single
+// kernel the judge is ~40 k instructions and warps of one SM sit in different phases, so the warps
+// starve on instruction fetch (ncu: stall_no_instruction dominant, profiles/); per phase the code is
+// a few thousand instructions, registers drop and rejected candidates leave early.  The per-task
+// state between phases lives behind the task's match scratch (hb_vote_state_entries()).
+struct JState {
+    int go, as, ae, row_num, hs, he, vl, vr, Cc, nw;
+    uint32_t rowmask[4];
+    unsigned short rows[MAX_KEPT + 3];
+};
+__device__ __forceinline__ JState* jstate_of(Match* matches, const HbVoteTask& t) {
+    return reinterpret_cast<JState*>(matches + t.match_off + 2 * ((size_t)t.C + 2));
+}
+__device__ __forceinline__ void front_load(Front& F, const JState* st, uint32_t* planes, const HbVoteTask& t) {
+    F.Cc = st->Cc; F.row_num = st->row_num; F.hs = st->hs; F.he = st->he; F.vl = st->vl; F.vr = st->vr;
+    F.P.p = planes + t.plane_off; F.P.stride = t.C; F.P.nw = st->nw; F.P.row_num = st->row_num;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) F.P.rowmask[k] = st->rowmask[k];
+}
+
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
-                uint32_t* __restrict__ planes, Match* __restrict__ matches, const uint8_t* __restrict__ cands,
-                uint8_t* __restrict__ cons_buf, HbVoteCall* __restrict__ calls) {
-    __shared__ int s_vc[WARPS_PER_CTA][128];
-    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+hb_judge_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                  Match* __restrict__ matches, const uint8_t* __restrict__ cands, HbVoteCall* __restrict__ calls) {
     __shared__ int s_cnt[WARPS_PER_CTA][2];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * WARPS_PER_CTA + wid;
     if (ti >= n_tasks) return;
     const HbVoteTask t = tasks[ti];
     HbVoteCall call = calls[ti];          // clean_cols written by kernel A
+    Front F;
+    int as, ae;
+    const bool go = front_anchors(t, call, clean + t.clean_off, matches, cands, s_cnt[wid], lane, F, &as, &ae);
+    __syncwarp();                          // the match scratch is dead from here on; the state sits behind it
+    if (lane == 0) {
+        JState* st = jstate_of(matches, t);
+        st->go = go ? 1 : 0; st->as = as; st->ae = ae; st->Cc = F.Cc;
+        calls[ti] = call;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                  uint32_t* __restrict__ planes, Match* __restrict__ matches, HbVoteCall* __restrict__ calls) {
+    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    JState* st = jstate_of(matches, t);
+    if (!st->go) return;
+    HbVoteCall call = calls[ti];
+    unsigned short* rows = s_rows[wid];
+    Front F;
+    F.Cc = st->Cc;
+    const bool go = front_members(t, call, clean + t.clean_off, planes, st->as, st->ae, 0, rows, lane, F);
+    for (int k = lane; k < F.row_num; k += 32) st->rows[k] = rows[k];
+    if (lane == 0) {
+        st->go = go ? 1 : 0; st->row_num = F.row_num;
+        if (go) {
+            st->nw = F.P.nw;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st->rowmask[k] = F.P.rowmask[k];
+        }
+        calls[ti] = call;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_c_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, uint32_t* __restrict__ planes,
+                  Match* __restrict__ matches, HbVoteCall* __restrict__ calls) {
+    __shared__ int s_vc[WARPS_PER_CTA][128];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    JState* st = jstate_of(matches, t);
+    if (!st->go) return;
+    HbVoteCall call = calls[ti];
+    Front F;
+    front_load(F, st, planes, t);
+    const bool go = front_boundaries(call, st->as, st->ae, 0.7, s_vc[wid], lane, F);
+    if (lane == 0) {
+        st->go = go ? 1 : 0; st->hs = F.hs; st->he = F.he; st->vl = F.vl; st->vr = F.vr;
+        calls[ti] = call;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_d_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                  uint32_t* __restrict__ planes, Match* __restrict__ matches, uint8_t* __restrict__ cons_buf,
+                  HbVoteCall* __restrict__ calls) {
+    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    const JState* st = jstate_of(matches, t);
+    if (!st->go) return;
+    HbVoteCall call = calls[ti];
     const int R = t.R, C = t.C;
     const uint8_t* m = clean + t.clean_off;
     unsigned short* rows = s_rows[wid];
     Front F;
-    if (!judge_front_v3(t, call, m, planes, matches, cands, 0.7, 0, s_vc[wid], rows, s_cnt[wid], lane, F)) {
-        if (lane == 0) calls[ti] = call;
-        return;
-    }
+    front_load(F, st, planes, t);
+    for (int k = lane; k < F.row_num; k += 32) rows[k] = st->rows[k];
+    __syncwarp();
     const Planes& P = F.P;
-    const int Cc = F.Cc, row_num = F.row_num, hs = F.hs, he = F.he, vl = F.vl, vr = F.vr;
-    (void)row_num;
+    const int Cc = F.Cc, hs = F.hs, he = F.he, vl = F.vl, vr = F.vr;
     // ---- 6. consensus (:9312-9346) -----------------------------------------------------------
     uint8_t* cons = cons_buf + t.cons_off;
     const int ml = vote_consensus(P, m, C, rows, hs, he, t.result_type, cons, lane);
@@ -801,7 +905,10 @@ hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t
         if (ends_with("TTAA", 4)) eo[neo++] = 4;
         bool have = false;
         int best_ed = 0, best_tsd = 0, best_f = 0, best_e = 0;
-        for (int a = 0; a < nfo; ++a) for (int b = 0; b < neo; ++b) {
+#pragma unroll 1
+        for (int a = 0; a < nfo; ++a)
+#pragma unroll 1
+        for (int b = 0; b < neo; ++b) {
             const int bs = hs + fo[a], be = he - eo[b];
             int tsd = 0;
             if (bs >= 0 && bs < Cc && be >= 0 && be < Cc) {
@@ -819,10 +926,12 @@ hb_judge_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t
                 else py_slice(ml, (long long)ml - 5 - eo[b], (long long)ml - eo[b], &lo2, &hi2);
                 char f[8], e[8];
                 const int nf = hi - lo, ne = hi2 - lo2;
+#pragma unroll 1
                 for (int i = 0; i < nf; ++i) {                                 // getReverseSequence :1635
                     char bch = (char)cons[lo + nf - 1 - i];
                     f[i] = bch == 'A' ? 'T' : bch == 'T' ? 'A' : bch == 'C' ? 'G' : bch == 'G' ? 'C' : 'N';
                 }
+#pragma unroll 1
                 for (int i = 0; i < ne; ++i) e[i] = (char)cons[lo2 + i];
                 const int ed = lev5(f, nf, e, ne);                             // :9403
                 if (!have || ed < best_ed || (ed == best_ed && tsd > best_tsd)) {   // stable sort :9405
@@ -1054,7 +1163,7 @@ __device__ bool near1(const uint8_t* ring, int tsd0, const uint8_t* sub, int k0,
 
 // one row of the per-copy 3'-end / TSD search.  hs0/he: homology boundary columns.
 // returns found; *end5 (new 5' end) and *end3 in ungapped coordinates of the row
-__device__ bool nonltr_row(const uint8_t* __restrict__ row, int Cc, int hs0, int he, int* end5_out, int* end3_out) {
+__device__ __noinline__ bool nonltr_row(const uint8_t* __restrict__ row, int Cc, int hs0, int he, int* end5_out, int* end3_out) {
     uint8_t ring[64];      // last 64 non-gap symbols, index = ungapped position & 63
     uint8_t sub[50];       // the <= 50 symbols before column hs0 (align_seq[left_pos:end_5]), oldest first
     int n = 0, end_5 = -1, h3 = -1, sl = 0;
@@ -1188,6 +1297,8 @@ hb_judge_v9_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint
 // ------------------------------------------------------------------------------------------
 // host launchers (called from hb_api.cu)
 extern "C" size_t hb_vote_match_entry_size() { return sizeof(Match); }
+// extra Match entries per task (after its 2 * (C + 2) match slots) that hold the judge's phase state
+extern "C" size_t hb_vote_state_entries() { return (sizeof(JState) + sizeof(Match) - 1) / sizeof(Match); }
 
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
                                       uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
@@ -1195,10 +1306,13 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
     if (n <= 0) return cudaSuccess;
     hb_clean_kernel<<<n, CLEAN_THREADS, 0, stream>>>(d_tasks, d_raw, d_clean, d_calls);
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    if (te_type == 0)
-        hb_judge_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
-                                                                 d_cands, d_cons, d_calls);
-    else if (te_type == 1)
+    if (te_type == 0) {
+        hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);
+        hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls);
+        hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls);
+        hb_judge_d_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
+                                                                   d_calls);
+    } else if (te_type == 1)
         hb_judge_v6_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
                                                                     d_anchors, d_cands, d_cons, d_calls);
     else if (te_type == 2)
