@@ -34,7 +34,7 @@ assert CALL_DTYPE.itemsize == C.sizeof(HbCall)
 class HbParams(C.Structure):
     _fields_ = [("occ_cap", C.c_int32), ("max_loci", C.c_int32), ("flank", C.c_int32), ("max_rows", C.c_int32),
                 ("te_type", C.c_int32), ("plant", C.c_int32), ("result_type", C.c_int32), ("trunc_gate", C.c_int32),
-                ("tb_budget_bytes", C.c_uint64)]
+                ("tb_budget_bytes", C.c_uint64), ("overlap", C.c_int32), ("reserved", C.c_int32)]
 
 
 COPY_DTYPE = np.dtype([("cand", "<u4"), ("rank", "<i4"), ("rel", "<i4"), ("nseeds", "<i4"), ("score", "<i4"),
@@ -257,10 +257,12 @@ class Context:
         return keys[:n]
 
     def adjust_raw(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=128, flank=50,
-                   max_rows=100, tb_budget_bytes=0, trunc_gate=True):
+                   max_rows=100, tb_budget_bytes=0, trunc_gate=True, overlap=None):
         """One ``flank_region_align_v5``-equivalent round (kernels ii + iii) over the candidates.
         Returns ``(calls, cons)``: a structured array (CALL_DTYPE, one record per candidate) and the
-        consensus bytes; candidate i's consensus is ``cons[calls['cons_off'][i] : +calls['cons_len'][i]]``."""
+        consensus bytes; candidate i's consensus is ``cons[calls['cons_off'][i] : +calls['cons_len'][i]]``.
+        ``overlap``: number of candidate sub-batches software-pipelined over two CUDA streams (same results;
+        default 4 from 2048 candidates up, else one serial batch -- which ``last_copies`` / ``last_msa`` need)."""
         if isinstance(cand_seqs, tuple):                      # pre-flattened (uint8 array, uint64 offsets)
             flat, off = cand_seqs
             n = len(off) - 1
@@ -274,7 +276,8 @@ class Context:
         if n == 0:
             return calls, np.zeros(0, dtype=np.uint8)
         prm = HbParams(occ_cap, max_loci, flank, max_rows, TE_TYPES[te_type], int(plant),
-                       1 if result_type == "cons" else 0, 1 if trunc_gate else 0, int(tb_budget_bytes))
+                       1 if result_type == "cons" else 0, 1 if trunc_gate else 0, int(tb_budget_bytes),
+                       int(overlap) if overlap is not None else (4 if n >= 2048 else 0), 0)
         nbytes = C.c_uint64(0)
         self._check(self._lib.hb_adjust(self._h, n, _ptr(flat), _ptr(off), C.byref(prm), _ptr(calls), C.byref(nbytes)),
                     "hb_adjust")

@@ -49,6 +49,15 @@ extern "C" int hb_create(int device, hb_ctx** out) {
         g_last_global_error = cudaGetErrorString(e); delete ctx; return HB_ECUDA;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    // lane 0 = the serial lane on the context's stream; lanes 1, 2 = overlapped sub-batches
+    ctx->lane[0].stream = ctx->stream;
+    for (int l = 1; l < 3; ++l) {
+        ctx->lane[l].prefix = l == 1 ? "L1:" : "L2:";
+        if ((e = cudaStreamCreateWithFlags(&ctx->lane[l].stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            g_last_global_error = cudaGetErrorString(e); delete ctx; return HB_ECUDA;
+        }
+    }
+    for (auto& ln : ctx->lane) for (auto& ev : ln.ev) cudaEventCreate(&ev);
     *out = ctx;
     return HB_OK;
 }
@@ -63,6 +72,13 @@ extern "C" void hb_destroy(hb_ctx* ctx) {
     for (auto& kv : ctx->bufs) kv.second.release();
     ctx->h_stage.release();
     ctx->h_cons.release();
+    for (auto& pc : ctx->part_cons) pc.release();
+    for (auto& ln : ctx->lane) {
+        cudaStreamSynchronize(ln.stream);
+        ln.h_cons.release();
+        for (auto& ev : ln.ev) if (ev) cudaEventDestroy(ev);
+    }
+    for (int l = 1; l < 3; ++l) if (ctx->lane[l].stream) cudaStreamDestroy(ctx->lane[l].stream);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

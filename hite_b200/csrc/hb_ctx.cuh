@@ -6,7 +6,9 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/hite_b200.h"
@@ -42,6 +44,22 @@ struct HbHostBuf {  // pinned staging
     template <class T> T* as() const { return (T*)p; }
 };
 
+// One in-flight sub-batch of hb_adjust: its own stream, events, staging and result bookkeeping.
+// Lane 0 is the serial lane (the context's stream, un-prefixed buffers); lanes 1 and 2 run the
+// overlapped sub-batches of hb_params.overlap >= 2 on their own streams and "L1:" / "L2:" buffers.
+struct HbLane {
+    std::string prefix;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    hb_timing timing = {};
+    HbHostBuf h_cons;              // pinned copy of the dense consensus bytes of this lane's last batch
+    uint64_t cons_bytes = 0;
+    uint32_t n_pairs = 0;
+    uint64_t ext_steps = 0;
+    std::vector<uint64_t> mat_off;
+    std::vector<uint32_t> rows, cols;
+};
+
 struct hb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -54,7 +72,13 @@ struct hb_ctx {
     HbHostBuf h_stage;
     // named device buffers of the genome / index / adjust pipeline (hb_pipeline.cu)
     std::map<std::string, HbDevBuf> bufs;
-    HbDevBuf& buf(const char* name) { return bufs[name]; }
+    std::mutex mu;                 // guards `bufs` (node insertion) and `err` when two lanes run
+    HbDevBuf& buf(const char* name) { std::lock_guard<std::mutex> g(mu); return bufs[name]; }
+    HbDevBuf& buf(const std::string& name) { std::lock_guard<std::mutex> g(mu); return bufs[name]; }
+    HbLane lane[3];
+    std::vector<HbHostBuf> part_cons;                                  // pinned consensus bytes per sub-batch
+    std::vector<std::pair<const uint8_t*, uint64_t>> cons_parts;       // last hb_adjust: parts in candidate order
+    bool last_overlapped = false;  // the hb_last_copies / hb_last_msa getters need a serial hb_adjust
     // genome state (HB-align S1/S2)
     bool have_genome = false, have_index = false;
     uint64_t g_tot = 0, g_nmm = 0;
@@ -75,10 +99,10 @@ struct hb_ctx {
 inline int hb_fail(hb_ctx* ctx, const char* what, cudaError_t e, const char* file, int line) {
     char buf[512];
     snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
-    if (ctx) ctx->err = buf;
+    if (ctx) { std::lock_guard<std::mutex> g(ctx->mu); ctx->err = buf; }
     return e == cudaErrorMemoryAllocation ? HB_ENOMEM : HB_ECUDA;
 }
 inline int hb_fail_msg(hb_ctx* ctx, int code, const std::string& msg) {
-    if (ctx) ctx->err = msg;
+    if (ctx) { std::lock_guard<std::mutex> g(ctx->mu); ctx->err = msg; }
     return code;
 }

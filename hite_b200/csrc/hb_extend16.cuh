@@ -117,28 +117,28 @@ constexpr uint32_t K_1 = 0x00010001u;
 
 // One DP cell for both halves.  PAR 0: even anti-diagonal (left neighbour was shuffled in, the lane at
 // the band edge has none -> emask), PAR 1: odd (up neighbour shuffled in -> fmask).
-// E and F are kept clamped at 0 like in hb_extend.cu.  hmz = max(H_neighbour - 6, 0) is the clamped
-// "open" value; the gap-extend flag is (E != hmz): it differs from the oracle's (E_l - 2 > H_l - 6)
+// E and F are kept clamped at 0 like in hb_extend.cu.  z = max(H_neighbour - 6, 0) is the clamped
+// "open" value; the gap-extend flag is (E != z): it differs from the oracle's (E_l - 2 > H_l - 6)
 // only where E == 0, and such a cell is never walked in gap state.
 // NW: traceback nibbles, pair A at bits 0-3, pair B at bits 16-19:
 //   bits0-1 source of H (0 stop, 1 diag, 2 E, 3 F), bit2 E extended, bit3 F extended
 template <int PAR>
-HB_HD void cell2(uint32_t hl, uint32_t el, uint32_t hu, uint32_t fu, uint32_t hd4, uint32_t qb, uint32_t tb,
-                 uint32_t edge_mask, uint32_t& H, uint32_t& E, uint32_t& F, uint32_t& NW) {
-    const uint32_t hmz_e = addmax_relu(hl, K_M6, K_M6);
-    const uint32_t hmz_f = addmax_relu(hu, K_M6, K_M6);
-    uint32_t e = addmax(el, K_M2, hmz_e);
-    uint32_t f = addmax(fu, K_M2, hmz_f);
+HB_HD void cell2(uint32_t zl, uint32_t el, uint32_t zu, uint32_t fu, uint32_t hd4, uint32_t qb, uint32_t tb,
+                 uint32_t edge_mask, uint32_t& H, uint32_t& E, uint32_t& F, uint32_t& Z, uint32_t& NW) {
+    // zl / zu: "open" values max(H - 6, 0) of the left / up neighbour -- computed ONCE per cell by its
+    // owner (Z below) and shuffled instead of H, so a step costs three VIADDMNMX, not four
+    uint32_t e = addmax(el, K_M2, zl);
+    uint32_t f = addmax(fu, K_M2, zu);
     if (PAR == 0) e &= edge_mask; else f &= edge_mask;
     const uint32_t s6 = minu2(qb & tb, K_6);              // 6 on a match, 0 otherwise
     const uint32_t dg = add2(hd4, s6);                    // H_diag - 4 + {6, 0}
     const uint32_t h = max3_relu(dg, e, f);
-    // e >= hmz_e, f >= hmz_f and h >= e hold per half (all >= 0), so plain 32-bit subtraction never borrows
+    // e >= zl, f >= zu and h >= e hold per half (all >= 0), so plain 32-bit subtraction never borrows
     // across the halves and can issue on the FMA pipe (IMAD.IADD); the kernel is ALU-pipe bound.  (At a
-    // band-edge lane the masked e / f may be below hmz: both halves sit on the edge there and the flag of
+    // band-edge lane the masked e / f may be below z: both halves sit on the edge there and the flag of
     // such a cell is never read, see above.)
-    const uint32_t fa = minu2(e - hmz_e, K_1);
-    const uint32_t fb = minu2(f - hmz_f, K_1);
+    const uint32_t fa = minu2(e - zl, K_1);
+    const uint32_t fb = minu2(f - zu, K_1);
     const uint32_t fc = minu2(dg ^ h, K_1);               // H != diag  (dg may be negative: xor, not minus)
     const uint32_t fd = minu2(h - e, K_1);                // H != E
     const uint32_t fp = minu2(h, K_1);                    // H > 0
@@ -146,6 +146,7 @@ HB_HD void cell2(uint32_t hl, uint32_t el, uint32_t hu, uint32_t fu, uint32_t hd
     const uint32_t s1 = fp & fc;
     NW = s0 + 2u * s1 + 4u * fa + 8u * fb;
     H = h; E = e; F = f;
+    Z = addmax_relu(h, K_M6, K_M6);
 }
 
 // ---- the warp body ---------------------------------------------------------------------------------
@@ -207,7 +208,7 @@ HB_HD void extend16_warp(W& w, uint32_t group0, const uint32_t* __restrict__ ord
     for (int t = sl; t < WIN; t += HB) { rq[t] = qcode(-HB + t); rt[t] = tcode(-HB + t); }
     w.sync();
 
-    uint32_t H1 = 0, E1 = 0, F1 = 0, Hd4 = K_M4;          // Hd4 = H two steps ago, minus 4
+    uint32_t H1 = 0, E1 = 0, F1 = 0, Z1 = 0, Hd4 = K_M4;  // Z1 = max(H1 - 6, 0); Hd4 = H two steps ago, minus 4
     uint32_t best = 0;                                    // running maximum of H per half
     int rbest[2] = {0, 0};                                // earliest anti-diagonal that reached it
     const uint32_t m_up = sl == 0 ? 0u : 0xffffffffu;     // band edge: neighbour outside = (H 0, E/F 0)
@@ -236,25 +237,25 @@ HB_HD void extend16_warp(W& w, uint32_t group0, const uint32_t* __restrict__ ord
             const uint32_t te = tnext;
             const uint32_t to = pt[u + 1];
             tnext = to;
-            uint32_t h, e, f, nw0, nw1;
+            uint32_t h, e, f, z, nw0, nw1;
             bool kh, kl;
             // even step (r = 64 sup + 2u): left from lane-1, up/diag own
             {
-                const uint32_t hl = w.shfl_up(H1, 1, HB), el = w.shfl_up(E1, 1, HB);
-                cell2<0>(hl, el, H1, F1, Hd4, qb, te, m_up, h, e, f, nw0);
+                const uint32_t zl = w.shfl_up(Z1, 1, HB), el = w.shfl_up(E1, 1, HB);
+                cell2<0>(zl, el, Z1, F1, Hd4, qb, te, m_up, h, e, f, z, nw0);
                 best = bmax(best, h, &kh, &kl);
                 if (!kl) rbest[0] = r0 + 2 * u;
                 if (!kh) rbest[1] = r0 + 2 * u;
-                Hd4 = add2(H1, K_M4); H1 = h; E1 = e; F1 = f;
+                Hd4 = add2(H1, K_M4); H1 = h; E1 = e; F1 = f; Z1 = z;
             }
             // odd step (r + 1): up from lane+1, left/diag own
             {
-                const uint32_t hu = w.shfl_down(H1, 1, HB), fu = w.shfl_down(F1, 1, HB);
-                cell2<1>(H1, E1, hu, fu, Hd4, qb, to, m_dn, h, e, f, nw1);
+                const uint32_t zu = w.shfl_down(Z1, 1, HB), fu = w.shfl_down(F1, 1, HB);
+                cell2<1>(Z1, E1, zu, fu, Hd4, qb, to, m_dn, h, e, f, z, nw1);
                 best = bmax(best, h, &kh, &kl);
                 if (!kl) rbest[0] = r0 + 2 * u + 1;
                 if (!kh) rbest[1] = r0 + 2 * u + 1;
-                Hd4 = add2(H1, K_M4); H1 = h; E1 = e; F1 = f;
+                Hd4 = add2(H1, K_M4); H1 = h; E1 = e; F1 = f; Z1 = z;
             }
             fq[u & 3] = nw0 + 16u * nw1;                  // byte 0: two nibbles of pair A, byte 2: pair B
             if ((u & 3) == 3) {

@@ -4,6 +4,7 @@
 // copies.  One stream per context; stage times are CUDA events on that stream.
 #include <algorithm>
 #include <chrono>
+#include <thread>
 #include <cstdlib>
 
 #include <chrono>
@@ -74,11 +75,11 @@ Layout make_layout(const uint64_t* off, uint32_t n) {
 }
 
 #define ENSURE(name, bytes) HB_CUDA_OK(ctx->buf(name).ensure((size_t)(bytes)))
+#define ENSURE_L(name, bytes) HB_CUDA_OK(LB(name).ensure((size_t)(bytes)))
 
 // pack + sketch a sequence set into (seq2, nmask, minimizer keys in position order). Returns count.
 int sketch(hb_ctx* ctx, const char* prefix, const uint8_t* h_ascii, const uint64_t* h_off, uint32_t n,
-           const Layout& L, uint64_t* n_mm_out) {
-    cudaStream_t s = ctx->stream;
+           const Layout& L, uint64_t* n_mm_out, cudaStream_t s) {
     std::string P(prefix);
     auto B = [&](const char* suffix) -> HbDevBuf& { return ctx->buf((P + suffix).c_str()); };
     const uint64_t ascii_bytes = h_off[n];
@@ -233,27 +234,16 @@ extern "C" int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap) {
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii, const uint64_t* cand_off,
-                         const hb_params* prm, hb_call* calls, uint64_t* cons_bytes) {
-    if (!ctx || !cand_ascii || !cand_off || !prm || !calls) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: null argument");
-    if (!ctx->have_index) return hb_fail_msg(ctx, HB_ESTATE, "hb_adjust: call hb_genome_load + hb_index_build first");
-    if (n_cand == 0) { if (cons_bytes) *cons_bytes = 0; return HB_OK; }
-    if (n_cand > (1u << 17)) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: at most 131072 candidates per call");
-    if (prm->te_type < HB_TE_TIR || prm->te_type > HB_TE_NON_LTR)
-        return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: te_type must be HB_TE_TIR, HB_TE_HELITRON or HB_TE_NON_LTR");
-    if (prm->max_loci < 1 || prm->max_loci > 512 || prm->max_rows < 2 || prm->max_rows > 100 || prm->occ_cap < 1 ||
-        prm->flank < 0 || prm->flank > 200)
-        return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: parameter out of range");
-    int any_long = 0;                 // candidates beyond the 16-bit extension kernel (hb_extend16.cuh)
-    for (uint32_t c = 0; c < n_cand; ++c) {
-        const uint64_t L = cand_off[c + 1] - cand_off[c];
-        if (L < 3 || L > 32000) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: candidate " + std::to_string(c) + " length must be in [3, 32000]");
-        if (L > HB_EXTEND16_MAX_L) any_long = 1;
-    }
+// One batch of candidates through the whole path on one lane (stream + buffer namespace).  The
+// consensus bytes land in `h_cons` (pinned), calls[i].cons_off indexes them.
+static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_cand, const uint8_t* cand_ascii,
+                        const uint64_t* cand_off, const hb_params* prm, int any_long, hb_call* calls,
+                        uint64_t* cons_bytes) {
     cudaSetDevice(ctx->device);
-    cudaStream_t s = ctx->stream;
-    memset(&ctx->timing, 0, sizeof(ctx->timing));
-    hb_timing& tm = ctx->timing;
+    cudaStream_t s = ln.stream;
+    memset(&ln.timing, 0, sizeof(ln.timing));
+    hb_timing& tm = ln.timing;
+    auto LB = [&](const char* name) -> HbDevBuf& { return ln.prefix.empty() ? ctx->buf(name) : ctx->buf(ln.prefix + name); };
     const int max_loci = prm->max_loci, flank = prm->flank;
     const uint64_t tot = ctx->g_tot;
     uint32_t launches = 0;
@@ -267,118 +257,118 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         fprintf(stderr, "[hb_adjust] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_host0).count());
     };
     // ---- S3: pack + sketch the candidates ----------------------------------------------------
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    HB_CUDA_OK(cudaEventRecord(ln.ev[0], s));
     Layout CL = make_layout(cand_off, n_cand);
     uint64_t n_cm = 0;
-    int rc = sketch(ctx, "c.", cand_ascii, cand_off, n_cand, CL, &n_cm);
+    int rc = sketch(ctx, (ln.prefix + "c.").c_str(), cand_ascii, cand_off, n_cand, CL, &n_cm, s);
     if (rc != HB_OK) return rc;
     launches += 6;
-    ENSURE("c.clen", sizeof(uint32_t) * (n_cand + 1));
-    clen_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(ctx->buf("c.src_off").as<uint64_t>(), n_cand, ctx->buf("c.clen").as<uint32_t>());
+    ENSURE_L("c.clen", sizeof(uint32_t) * (n_cand + 1));
+    clen_kernel<<<(n_cand + 255) / 256, 256, 0, s>>>(LB("c.src_off").as<uint64_t>(), n_cand, LB("c.clen").as<uint32_t>());
     ++launches;
     tm.h2d_bytes += cand_off[n_cand] + sizeof(uint64_t) * (3 * (uint64_t)n_cand + 1);
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    HB_CUDA_OK(cudaEventRecord(ln.ev[1], s));
     mark("sketch");
-    const uint64_t* d_cgoff = ctx->buf("c.goff").as<uint64_t>();
-    const uint64_t* d_coff = ctx->buf("c.src_off").as<uint64_t>();
-    const uint32_t* d_clen = ctx->buf("c.clen").as<uint32_t>();
+    const uint64_t* d_cgoff = LB("c.goff").as<uint64_t>();
+    const uint64_t* d_coff = LB("c.src_off").as<uint64_t>();
+    const uint32_t* d_clen = LB("c.clen").as<uint32_t>();
 
     // ---- S4: hits ------------------------------------------------------------------------------
     uint64_t n_hits = 0;
     if (n_cm > 0) {
-        ENSURE("s.m_cand", sizeof(uint32_t) * n_cm); ENSURE("s.m_qidx", sizeof(uint32_t) * n_cm);
-        ENSURE("s.m_lo", sizeof(uint32_t) * n_cm); ENSURE("s.m_cnt", sizeof(uint32_t) * n_cm);
-        ENSURE("s.m_off", sizeof(uint32_t) * n_cm);
-        ENSURE("s.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(std::max<uint64_t>(n_cm, n_cand + 1)));
-        ENSURE("s.total", sizeof(uint64_t));
-        HB_CUDA_OK(hb_seed_count_launch(ctx->buf("c.mm").as<uint64_t>(), (uint32_t)n_cm, d_cgoff, n_cand,
+        ENSURE_L("s.m_cand", sizeof(uint32_t) * n_cm); ENSURE_L("s.m_qidx", sizeof(uint32_t) * n_cm);
+        ENSURE_L("s.m_lo", sizeof(uint32_t) * n_cm); ENSURE_L("s.m_cnt", sizeof(uint32_t) * n_cm);
+        ENSURE_L("s.m_off", sizeof(uint32_t) * n_cm);
+        ENSURE_L("s.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(std::max<uint64_t>(n_cm, n_cand + 1)));
+        ENSURE_L("s.total", sizeof(uint64_t));
+        HB_CUDA_OK(hb_seed_count_launch(LB("c.mm").as<uint64_t>(), (uint32_t)n_cm, d_cgoff, n_cand,
                                         ctx->buf("g.idx_a").as<uint64_t>(), ctx->g_nmm, ctx->buf("g.bucket").as<uint32_t>(),
-                                        prm->occ_cap, ctx->buf("s.m_cand").as<uint32_t>(), ctx->buf("s.m_qidx").as<uint32_t>(),
-                                        ctx->buf("s.m_lo").as<uint32_t>(), ctx->buf("s.m_cnt").as<uint32_t>(), s));
-        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("s.m_cnt").as<uint32_t>(), ctx->buf("s.m_off").as<uint32_t>(), n_cm,
-                                         ctx->buf("s.scan_tmp").as<uint32_t>(), ctx->buf("s.total").as<uint64_t>(), s));
-        HB_CUDA_OK(cudaMemcpyAsync(&n_hits, ctx->buf("s.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+                                        prm->occ_cap, LB("s.m_cand").as<uint32_t>(), LB("s.m_qidx").as<uint32_t>(),
+                                        LB("s.m_lo").as<uint32_t>(), LB("s.m_cnt").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(LB("s.m_cnt").as<uint32_t>(), LB("s.m_off").as<uint32_t>(), n_cm,
+                                         LB("s.scan_tmp").as<uint32_t>(), LB("s.total").as<uint64_t>(), s));
+        HB_CUDA_OK(cudaMemcpyAsync(&n_hits, LB("s.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
         launches += 4;
     }
     if (n_hits >= (1ull << 31)) return hb_fail_msg(ctx, HB_ENOMEM, "hb_adjust: too many seed hits in one call; pass fewer candidates");
     uint32_t n_cl = 0, n_pairs = 0;
-    ENSURE("s.n_loci", sizeof(uint32_t) * (n_cand + 1));
-    ENSURE("s.pair_off", sizeof(uint32_t) * (n_cand + 2));
-    HB_CUDA_OK(cudaMemsetAsync(ctx->buf("s.n_loci").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
+    ENSURE_L("s.n_loci", sizeof(uint32_t) * (n_cand + 1));
+    ENSURE_L("s.pair_off", sizeof(uint32_t) * (n_cand + 2));
+    HB_CUDA_OK(cudaMemsetAsync(LB("s.n_loci").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
     uint64_t* d_hits = nullptr;
     if (n_hits > 0) {
-        ENSURE("s.hits_a", sizeof(uint64_t) * n_hits); ENSURE("s.hits_b", sizeof(uint64_t) * n_hits);
-        ENSURE("s.sort_tmp", sizeof(uint32_t) * hb_sort_tmp_words(n_hits));
-        HB_CUDA_OK(hb_seed_fill_launch(ctx->buf("c.mm").as<uint64_t>(), (uint32_t)n_cm, d_cgoff, ctx->buf("g.idx_a").as<uint64_t>(),
-                                       tot, ctx->k, ctx->buf("s.m_cand").as<uint32_t>(), ctx->buf("s.m_qidx").as<uint32_t>(),
-                                       ctx->buf("s.m_lo").as<uint32_t>(), ctx->buf("s.m_cnt").as<uint32_t>(),
-                                       ctx->buf("s.m_off").as<uint32_t>(), ctx->buf("s.hits_a").as<uint64_t>(), s));
+        ENSURE_L("s.hits_a", sizeof(uint64_t) * n_hits); ENSURE_L("s.hits_b", sizeof(uint64_t) * n_hits);
+        ENSURE_L("s.sort_tmp", sizeof(uint32_t) * hb_sort_tmp_words(n_hits));
+        HB_CUDA_OK(hb_seed_fill_launch(LB("c.mm").as<uint64_t>(), (uint32_t)n_cm, d_cgoff, ctx->buf("g.idx_a").as<uint64_t>(),
+                                       tot, ctx->k, LB("s.m_cand").as<uint32_t>(), LB("s.m_qidx").as<uint32_t>(),
+                                       LB("s.m_lo").as<uint32_t>(), LB("s.m_cnt").as<uint32_t>(),
+                                       LB("s.m_off").as<uint32_t>(), LB("s.hits_a").as<uint64_t>(), s));
         ++launches;
         int cand_bits = 1;
         while ((1u << cand_bits) < n_cand) ++cand_bits;
         // total order on (cand, strand, diagonal); the low 13 bits (minimizer ordinal) do not affect
         // any cluster statistic, so they are left unsorted
-        HB_CUDA_OK(hb_radix_sort_u64(ctx->buf("s.hits_a").as<uint64_t>(), ctx->buf("s.hits_b").as<uint64_t>(), n_hits, 13,
-                                     47 + cand_bits, ctx->buf("s.sort_tmp").as<uint32_t>(), &d_hits, &launches, s));
+        HB_CUDA_OK(hb_radix_sort_u64(LB("s.hits_a").as<uint64_t>(), LB("s.hits_b").as<uint64_t>(), n_hits, 13,
+                                     47 + cand_bits, LB("s.sort_tmp").as<uint32_t>(), &d_hits, &launches, s));
         // ---- S5: clusters -----------------------------------------------------------------------
-        ENSURE("s.flag", sizeof(uint32_t) * n_hits); ENSURE("s.cid", sizeof(uint32_t) * n_hits);
-        ENSURE("s.scan_tmp2", sizeof(uint32_t) * hb_scan_tmp_words(n_hits));
-        HB_CUDA_OK(hb_cluster_flag_launch(d_hits, n_hits, ctx->buf("s.flag").as<uint32_t>(), s));
-        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("s.flag").as<uint32_t>(), ctx->buf("s.cid").as<uint32_t>(), n_hits,
-                                         ctx->buf("s.scan_tmp2").as<uint32_t>(), ctx->buf("s.total").as<uint64_t>(), s));
+        ENSURE_L("s.flag", sizeof(uint32_t) * n_hits); ENSURE_L("s.cid", sizeof(uint32_t) * n_hits);
+        ENSURE_L("s.scan_tmp2", sizeof(uint32_t) * hb_scan_tmp_words(n_hits));
+        HB_CUDA_OK(hb_cluster_flag_launch(d_hits, n_hits, LB("s.flag").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(LB("s.flag").as<uint32_t>(), LB("s.cid").as<uint32_t>(), n_hits,
+                                         LB("s.scan_tmp2").as<uint32_t>(), LB("s.total").as<uint64_t>(), s));
         uint64_t ncl64 = 0;
-        HB_CUDA_OK(cudaMemcpyAsync(&ncl64, ctx->buf("s.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaMemcpyAsync(&ncl64, LB("s.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
         n_cl = (uint32_t)ncl64;
-        ENSURE("s.cl_start", sizeof(uint32_t) * (n_cl + 1));
-        ENSURE("s.cand_first", sizeof(uint32_t) * (n_cand + 1));
-        ENSURE("s.loci", sizeof(HbLocus) * (size_t)n_cand * max_loci);
-        HB_CUDA_OK(hb_cluster_start_launch(ctx->buf("s.flag").as<uint32_t>(), ctx->buf("s.cid").as<uint32_t>(), n_hits,
-                                           ctx->buf("s.cl_start").as<uint32_t>(), s));
-        HB_CUDA_OK(hb_rank_select_launch(d_hits, n_hits, ctx->buf("s.cl_start").as<uint32_t>(), n_cl,
-                                         ctx->buf("s.cand_first").as<uint32_t>(), n_cand, max_loci,
-                                         ctx->buf("s.loci").as<HbLocus>(), ctx->buf("s.n_loci").as<uint32_t>(), s));
+        ENSURE_L("s.cl_start", sizeof(uint32_t) * (n_cl + 1));
+        ENSURE_L("s.cand_first", sizeof(uint32_t) * (n_cand + 1));
+        ENSURE_L("s.loci", sizeof(HbLocus) * (size_t)n_cand * max_loci);
+        HB_CUDA_OK(hb_cluster_start_launch(LB("s.flag").as<uint32_t>(), LB("s.cid").as<uint32_t>(), n_hits,
+                                           LB("s.cl_start").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_rank_select_launch(d_hits, n_hits, LB("s.cl_start").as<uint32_t>(), n_cl,
+                                         LB("s.cand_first").as<uint32_t>(), n_cand, max_loci,
+                                         LB("s.loci").as<HbLocus>(), LB("s.n_loci").as<uint32_t>(), s));
         launches += 8;
     }
     // ---- S6: pair list ---------------------------------------------------------------------------
-    ENSURE("s.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(std::max<uint64_t>(n_cm, n_cand + 1)));
-    ENSURE("s.total", sizeof(uint64_t));
-    HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("s.n_loci").as<uint32_t>(), ctx->buf("s.pair_off").as<uint32_t>(), n_cand + 1,
-                                     ctx->buf("s.scan_tmp").as<uint32_t>(), ctx->buf("s.total").as<uint64_t>(), s));
+    ENSURE_L("s.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(std::max<uint64_t>(n_cm, n_cand + 1)));
+    ENSURE_L("s.total", sizeof(uint64_t));
+    HB_CUDA_OK(hb_exclusive_scan_u32(LB("s.n_loci").as<uint32_t>(), LB("s.pair_off").as<uint32_t>(), n_cand + 1,
+                                     LB("s.scan_tmp").as<uint32_t>(), LB("s.total").as<uint64_t>(), s));
     {
         uint64_t np64 = 0;
-        HB_CUDA_OK(cudaMemcpyAsync(&np64, ctx->buf("s.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaMemcpyAsync(&np64, LB("s.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
         n_pairs = (uint32_t)np64;
     }
     launches += 3;
-    ENSURE("p.pairs", sizeof(HbLocus) * ((size_t)n_pairs + 1));
-    ENSURE("p.alns", sizeof(HbAln) * ((size_t)n_pairs + 1));
-    ENSURE("p.tb_units", sizeof(uint32_t) * ((size_t)n_pairs + 1)); ENSURE("p.tb_off", sizeof(uint32_t) * ((size_t)n_pairs + 1));
-    ENSURE("p.qr_units", sizeof(uint32_t) * ((size_t)n_pairs + 1)); ENSURE("p.qr_off", sizeof(uint32_t) * ((size_t)n_pairs + 1));
-    ENSURE("p.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words((size_t)n_pairs + 1));
-    ENSURE("p.total", sizeof(uint64_t) * 2);
+    ENSURE_L("p.pairs", sizeof(HbLocus) * ((size_t)n_pairs + 1));
+    ENSURE_L("p.alns", sizeof(HbAln) * ((size_t)n_pairs + 1));
+    ENSURE_L("p.tb_units", sizeof(uint32_t) * ((size_t)n_pairs + 1)); ENSURE_L("p.tb_off", sizeof(uint32_t) * ((size_t)n_pairs + 1));
+    ENSURE_L("p.qr_units", sizeof(uint32_t) * ((size_t)n_pairs + 1)); ENSURE_L("p.qr_off", sizeof(uint32_t) * ((size_t)n_pairs + 1));
+    ENSURE_L("p.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words((size_t)n_pairs + 1));
+    ENSURE_L("p.total", sizeof(uint64_t) * 2);
     uint64_t tb_units_total = 0, qr_units_total = 0;
     std::vector<uint32_t> h_tb_off;
     if (n_pairs > 0) {
-        HB_CUDA_OK(hb_pair_emit_launch(ctx->buf("s.loci").as<HbLocus>(), ctx->buf("s.n_loci").as<uint32_t>(),
-                                       ctx->buf("s.pair_off").as<uint32_t>(), n_cand, max_loci, ctx->buf("p.pairs").as<HbLocus>(), s));
-        HB_CUDA_OK(hb_pair_sizes_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, d_clen, ctx->buf("p.tb_units").as<uint32_t>(),
-                                        ctx->buf("p.qr_units").as<uint32_t>(), s));
-        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("p.tb_units").as<uint32_t>(), ctx->buf("p.tb_off").as<uint32_t>(), n_pairs,
-                                         ctx->buf("p.scan_tmp").as<uint32_t>(), ctx->buf("p.total").as<uint64_t>(), s));
-        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("p.qr_units").as<uint32_t>(), ctx->buf("p.qr_off").as<uint32_t>(), n_pairs,
-                                         ctx->buf("p.scan_tmp").as<uint32_t>(), ctx->buf("p.total").as<uint64_t>() + 1, s));
+        HB_CUDA_OK(hb_pair_emit_launch(LB("s.loci").as<HbLocus>(), LB("s.n_loci").as<uint32_t>(),
+                                       LB("s.pair_off").as<uint32_t>(), n_cand, max_loci, LB("p.pairs").as<HbLocus>(), s));
+        HB_CUDA_OK(hb_pair_sizes_launch(LB("p.pairs").as<HbLocus>(), n_pairs, d_clen, LB("p.tb_units").as<uint32_t>(),
+                                        LB("p.qr_units").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(LB("p.tb_units").as<uint32_t>(), LB("p.tb_off").as<uint32_t>(), n_pairs,
+                                         LB("p.scan_tmp").as<uint32_t>(), LB("p.total").as<uint64_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(LB("p.qr_units").as<uint32_t>(), LB("p.qr_off").as<uint32_t>(), n_pairs,
+                                         LB("p.scan_tmp").as<uint32_t>(), LB("p.total").as<uint64_t>() + 1, s));
         uint64_t totals[2] = {0, 0};
         h_tb_off.resize(n_pairs);
-        HB_CUDA_OK(cudaMemcpyAsync(totals, ctx->buf("p.total").p, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost, s));
-        HB_CUDA_OK(cudaMemcpyAsync(h_tb_off.data(), ctx->buf("p.tb_off").p, sizeof(uint32_t) * n_pairs, cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaMemcpyAsync(totals, LB("p.total").p, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaMemcpyAsync(h_tb_off.data(), LB("p.tb_off").p, sizeof(uint32_t) * n_pairs, cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
         tb_units_total = totals[0]; qr_units_total = totals[1];
         launches += 8;
     }
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    HB_CUDA_OK(cudaEventRecord(ln.ev[2], s));
     mark("seed/sort/cluster/pairs");
 
     // ---- S7: banded extension, chunked by the traceback budget -----------------------------------
@@ -387,9 +377,9 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     uint64_t ext_steps = 0;
     if (n_pairs > 0) {
         const uint64_t alloc_units = std::min<uint64_t>(tb_units_total, budget_units);
-        ENSURE("p.tbuf", (alloc_units + 1) << 9);
-        ENSURE("p.qrec", ((qr_units_total + 1) << 5) * sizeof(uint32_t));
-        ENSURE("p.order", hb_extend_order_words(n_pairs) * sizeof(uint32_t));
+        ENSURE_L("p.tbuf", (alloc_units + 1) << 9);
+        ENSURE_L("p.qrec", ((qr_units_total + 1) << 5) * sizeof(uint32_t));
+        ENSURE_L("p.order", hb_extend_order_words(n_pairs) * sizeof(uint32_t));
         uint32_t lo = 0;
         while (lo < n_pairs) {
             uint32_t hi = lo + 1;
@@ -406,46 +396,46 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
                 const uint64_t end = (hi < n_pairs) ? h_tb_off[hi] : tb_units_total;
                 if (end - base > alloc_units) return hb_fail_msg(ctx, HB_ENOMEM, "hb_adjust: tb_budget_bytes is smaller than one candidate's traceback");
             }
-            HB_CUDA_OK(hb_extend_launch(ctx->buf("p.pairs").as<HbLocus>(), lo, hi, ctx->buf("g.seq2").as<uint32_t>(),
-                                        ctx->buf("g.nmask").as<uint32_t>(), tot, ctx->buf("c.seq2").as<uint32_t>(),
-                                        ctx->buf("c.nmask").as<uint32_t>(), d_cgoff, d_clen, ctx->buf("p.tb_off").as<uint32_t>(),
-                                        (uint32_t)base, ctx->buf("p.tbuf").as<uint32_t>(), ctx->buf("p.qr_off").as<uint32_t>(),
-                                        ctx->buf("p.qrec").as<uint32_t>(), ctx->buf("p.alns").as<HbAln>(),
-                                        ctx->buf("p.order").as<uint32_t>(), any_long, &launches, s));
+            HB_CUDA_OK(hb_extend_launch(LB("p.pairs").as<HbLocus>(), lo, hi, ctx->buf("g.seq2").as<uint32_t>(),
+                                        ctx->buf("g.nmask").as<uint32_t>(), tot, LB("c.seq2").as<uint32_t>(),
+                                        LB("c.nmask").as<uint32_t>(), d_cgoff, d_clen, LB("p.tb_off").as<uint32_t>(),
+                                        (uint32_t)base, LB("p.tbuf").as<uint32_t>(), LB("p.qr_off").as<uint32_t>(),
+                                        LB("p.qrec").as<uint32_t>(), LB("p.alns").as<HbAln>(),
+                                        LB("p.order").as<uint32_t>(), any_long, &launches, s));
             lo = hi;
         }
         ext_steps = tb_units_total * 32;                 // one 512 B unit = 64 anti-diagonals of 16 lanes
     }
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+    HB_CUDA_OK(cudaEventRecord(ln.ev[3], s));
     mark("extend");
 
     // ---- S8..S10: copy rules, star MSA -------------------------------------------------------------
-    ENSURE("m.n_rows", sizeof(uint32_t) * (n_cand + 1)); ENSURE("m.n_cols", sizeof(uint32_t) * (n_cand + 1));
-    ENSURE("m.n_trows", sizeof(uint32_t) * (n_cand + 1));
-    HB_CUDA_OK(cudaMemsetAsync(ctx->buf("m.n_trows").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
+    ENSURE_L("m.n_rows", sizeof(uint32_t) * (n_cand + 1)); ENSURE_L("m.n_cols", sizeof(uint32_t) * (n_cand + 1));
+    ENSURE_L("m.n_trows", sizeof(uint32_t) * (n_cand + 1));
+    HB_CUDA_OK(cudaMemsetAsync(LB("m.n_trows").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
     const int trunc_gate = prm->trunc_gate ? 1 : 0;
-    ENSURE("m.ins", sizeof(uint32_t) * (cand_off[n_cand] + 1));
-    HB_CUDA_OK(cudaMemsetAsync(ctx->buf("m.ins").p, 0, sizeof(uint32_t) * (cand_off[n_cand] + 1), s));
-    HB_CUDA_OK(cudaMemsetAsync(ctx->buf("m.n_rows").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
-    HB_CUDA_OK(hb_copy_filter_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, d_clen, ctx->buf("g.goff").as<uint64_t>(),
-                                     ctx->buf("g.glen").as<uint64_t>(), ctx->g_ncontig, tot, flank, ctx->buf("p.alns").as<HbAln>(), s));
-    HB_CUDA_OK(hb_copy_select_launch(ctx->buf("p.pairs").as<HbLocus>(), ctx->buf("s.pair_off").as<uint32_t>(), n_cand,
-                                     prm->max_rows, trunc_gate, ctx->buf("p.alns").as<HbAln>(),
-                                     ctx->buf("m.n_rows").as<uint32_t>(), ctx->buf("m.n_trows").as<uint32_t>(), s));
-    HB_CUDA_OK(hb_ins_max_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, ctx->buf("p.alns").as<HbAln>(),
-                                 ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(), d_coff,
-                                 ctx->buf("m.ins").as<uint32_t>(), s));
-    HB_CUDA_OK(hb_layout_launch(d_coff, d_clen, n_cand, flank, ctx->buf("m.ins").as<uint32_t>(), ctx->buf("m.n_cols").as<uint32_t>(), s));
+    ENSURE_L("m.ins", sizeof(uint32_t) * (cand_off[n_cand] + 1));
+    HB_CUDA_OK(cudaMemsetAsync(LB("m.ins").p, 0, sizeof(uint32_t) * (cand_off[n_cand] + 1), s));
+    HB_CUDA_OK(cudaMemsetAsync(LB("m.n_rows").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
+    HB_CUDA_OK(hb_copy_filter_launch(LB("p.pairs").as<HbLocus>(), n_pairs, d_clen, ctx->buf("g.goff").as<uint64_t>(),
+                                     ctx->buf("g.glen").as<uint64_t>(), ctx->g_ncontig, tot, flank, LB("p.alns").as<HbAln>(), s));
+    HB_CUDA_OK(hb_copy_select_launch(LB("p.pairs").as<HbLocus>(), LB("s.pair_off").as<uint32_t>(), n_cand,
+                                     prm->max_rows, trunc_gate, LB("p.alns").as<HbAln>(),
+                                     LB("m.n_rows").as<uint32_t>(), LB("m.n_trows").as<uint32_t>(), s));
+    HB_CUDA_OK(hb_ins_max_launch(LB("p.pairs").as<HbLocus>(), n_pairs, LB("p.alns").as<HbAln>(),
+                                 LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(), d_coff,
+                                 LB("m.ins").as<uint32_t>(), s));
+    HB_CUDA_OK(hb_layout_launch(d_coff, d_clen, n_cand, flank, LB("m.ins").as<uint32_t>(), LB("m.n_cols").as<uint32_t>(), s));
     // column offsets of the per-candidate column maps (device scan: no host round trip)
-    ENSURE("m.col_off", sizeof(uint32_t) * (n_cand + 1));
-    ENSURE("m.col_total", sizeof(uint64_t));
-    HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("m.n_cols").as<uint32_t>(), ctx->buf("m.col_off").as<uint32_t>(), n_cand,
-                                     ctx->buf("s.scan_tmp").as<uint32_t>(), ctx->buf("m.col_total").as<uint64_t>(), s));
+    ENSURE_L("m.col_off", sizeof(uint32_t) * (n_cand + 1));
+    ENSURE_L("m.col_total", sizeof(uint64_t));
+    HB_CUDA_OK(hb_exclusive_scan_u32(LB("m.n_cols").as<uint32_t>(), LB("m.col_off").as<uint32_t>(), n_cand,
+                                     LB("s.scan_tmp").as<uint32_t>(), LB("m.col_total").as<uint64_t>(), s));
     launches += 7;
     std::vector<uint32_t> h_rows(n_cand), h_cols(n_cand), h_trows(n_cand);
-    HB_CUDA_OK(cudaMemcpyAsync(h_trows.data(), ctx->buf("m.n_trows").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
-    HB_CUDA_OK(cudaMemcpyAsync(h_rows.data(), ctx->buf("m.n_rows").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
-    HB_CUDA_OK(cudaMemcpyAsync(h_cols.data(), ctx->buf("m.n_cols").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaMemcpyAsync(h_trows.data(), LB("m.n_trows").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaMemcpyAsync(h_rows.data(), LB("m.n_rows").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaMemcpyAsync(h_cols.data(), LB("m.n_cols").p, sizeof(uint32_t) * n_cand, cudaMemcpyDeviceToHost, s));
     HB_CUDA_OK(cudaStreamSynchronize(s));
     // candidates with >= 1 row become judge tasks (0 rows: no member file in the reference either,
     // flank_region_align_v5 only submits queries present in extend_all_copies, Util.py:8125-8137)
@@ -489,85 +479,85 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     h_tmat_off[n_cand] = mat_total;
     (void)tmat_base;
     const uint32_t n_tasks = (uint32_t)tasks.size();
-    ENSURE("m.mat_off", sizeof(uint64_t) * (n_cand + 1));
-    ENSURE("m.tmat_off", sizeof(uint64_t) * (n_cand + 1));
-    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("m.mat_off").p, h_mat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
-    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("m.tmat_off").p, h_tmat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
-    ENSURE("m.mat", mat_total + 4);
+    ENSURE_L("m.mat_off", sizeof(uint64_t) * (n_cand + 1));
+    ENSURE_L("m.tmat_off", sizeof(uint64_t) * (n_cand + 1));
+    HB_CUDA_OK(cudaMemcpyAsync(LB("m.mat_off").p, h_mat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(LB("m.tmat_off").p, h_tmat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
+    ENSURE_L("m.mat", mat_total + 4);
     // every byte of every row is written by msa_write_kernel (gaps included): no pre-fill
     {
         uint64_t all_cols = 0;
         for (uint32_t c = 0; c < n_cand; ++c) all_cols += h_cols[c];
         if (all_cols >= (1ull << 32)) return hb_fail_msg(ctx, HB_ENOMEM, "hb_adjust: too many MSA columns in one call; pass fewer candidates");
-        ENSURE("m.colq", sizeof(uint32_t) * (all_cols + 1));
-        HB_CUDA_OK(hb_colmap_launch(d_coff, d_clen, n_cand, flank, ctx->buf("m.ins").as<uint32_t>(), ctx->buf("m.n_cols").as<uint32_t>(),
-                                    ctx->buf("m.col_off").as<uint32_t>(), ctx->buf("m.colq").as<uint32_t>(), s));
+        ENSURE_L("m.colq", sizeof(uint32_t) * (all_cols + 1));
+        HB_CUDA_OK(hb_colmap_launch(d_coff, d_clen, n_cand, flank, LB("m.ins").as<uint32_t>(), LB("m.n_cols").as<uint32_t>(),
+                                    LB("m.col_off").as<uint32_t>(), LB("m.colq").as<uint32_t>(), s));
         ++launches;
     }
     for (int trunc = 0; trunc <= (n_tasks > n_full ? 1 : 0); ++trunc) {
-        HB_CUDA_OK(hb_msa_write_launch(ctx->buf("p.pairs").as<HbLocus>(), n_pairs, ctx->buf("p.alns").as<HbAln>(),
-                                       ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(),
-                                       ctx->buf("m.n_cols").as<uint32_t>(), ctx->buf("m.col_off").as<uint32_t>(),
-                                       ctx->buf("m.colq").as<uint32_t>(),
-                                       ctx->buf(trunc ? "m.tmat_off" : "m.mat_off").as<uint64_t>(), ctx->buf("g.seq2").as<uint32_t>(),
-                                       ctx->buf("g.nmask").as<uint32_t>(), tot, flank, trunc, ctx->buf("m.mat").as<uint8_t>(), s));
+        HB_CUDA_OK(hb_msa_write_launch(LB("p.pairs").as<HbLocus>(), n_pairs, LB("p.alns").as<HbAln>(),
+                                       LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(),
+                                       LB("m.n_cols").as<uint32_t>(), LB("m.col_off").as<uint32_t>(),
+                                       LB("m.colq").as<uint32_t>(),
+                                       LB(trunc ? "m.tmat_off" : "m.mat_off").as<uint64_t>(), ctx->buf("g.seq2").as<uint32_t>(),
+                                       ctx->buf("g.nmask").as<uint32_t>(), tot, flank, trunc, LB("m.mat").as<uint8_t>(), s));
         ++launches;
     }
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[4], s));
+    HB_CUDA_OK(cudaEventRecord(ln.ev[4], s));
     mark("copy rules + msa");
 
     // ---- kernel (iii): clean + judge ---------------------------------------------------------------
     std::vector<HbVoteCall> h_calls(n_tasks);
     uint64_t dense_total = 0;
-    ctx->last_cons_bytes = 0;
+    ln.cons_bytes = 0;
     if (n_tasks > 0) {
-        ENSURE("v.tasks", sizeof(HbVoteTask) * n_tasks);
-        ENSURE("v.clean", mat_total + 1);
-        ENSURE("v.planes", col_total * 24 * sizeof(uint32_t));
-        ENSURE("v.matches", match_total * hb_vote_match_entry_size());
-        ENSURE("v.cons", col_total + 2ull * n_tasks + 1);
-        ENSURE("v.anchors", sizeof(int) * (2 * row_total + 2));
-        ENSURE("v.calls", sizeof(HbVoteCall) * n_tasks);
-        ENSURE("v.len", sizeof(uint32_t) * (n_tasks + 1)); ENSURE("v.off", sizeof(uint32_t) * (n_tasks + 1));
-        ENSURE("v.dense", col_total + 2ull * n_tasks + 1);
-        ENSURE("v.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(n_tasks + 1));
-        ENSURE("v.total", sizeof(uint64_t));
-        HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("v.tasks").p, tasks.data(), sizeof(HbVoteTask) * n_tasks, cudaMemcpyHostToDevice, s));
-        HB_CUDA_OK(cudaMemsetAsync(ctx->buf("v.calls").p, 0, sizeof(HbVoteCall) * n_tasks, s));
-        HB_CUDA_OK(hb_vote_launch(ctx->buf("v.tasks").as<HbVoteTask>(), (int)n_tasks, ctx->buf("m.mat").as<uint8_t>(),
-                                  ctx->buf("v.clean").as<uint8_t>(), ctx->buf("v.planes").as<uint32_t>(), ctx->buf("v.matches").p,
-                                  ctx->buf("v.anchors").as<int>(), ctx->buf("c.ascii").as<uint8_t>(),
-                                  ctx->buf("v.cons").as<uint8_t>(), ctx->buf("v.calls").as<HbVoteCall>(), prm->te_type, s));
-        HB_CUDA_OK(cudaEventRecord(ctx->ev[5], s));
+        ENSURE_L("v.tasks", sizeof(HbVoteTask) * n_tasks);
+        ENSURE_L("v.clean", mat_total + 1);
+        ENSURE_L("v.planes", col_total * 24 * sizeof(uint32_t));
+        ENSURE_L("v.matches", match_total * hb_vote_match_entry_size());
+        ENSURE_L("v.cons", col_total + 2ull * n_tasks + 1);
+        ENSURE_L("v.anchors", sizeof(int) * (2 * row_total + 2));
+        ENSURE_L("v.calls", sizeof(HbVoteCall) * n_tasks);
+        ENSURE_L("v.len", sizeof(uint32_t) * (n_tasks + 1)); ENSURE_L("v.off", sizeof(uint32_t) * (n_tasks + 1));
+        ENSURE_L("v.dense", col_total + 2ull * n_tasks + 1);
+        ENSURE_L("v.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(n_tasks + 1));
+        ENSURE_L("v.total", sizeof(uint64_t));
+        HB_CUDA_OK(cudaMemcpyAsync(LB("v.tasks").p, tasks.data(), sizeof(HbVoteTask) * n_tasks, cudaMemcpyHostToDevice, s));
+        HB_CUDA_OK(cudaMemsetAsync(LB("v.calls").p, 0, sizeof(HbVoteCall) * n_tasks, s));
+        HB_CUDA_OK(hb_vote_launch(LB("v.tasks").as<HbVoteTask>(), (int)n_tasks, LB("m.mat").as<uint8_t>(),
+                                  LB("v.clean").as<uint8_t>(), LB("v.planes").as<uint32_t>(), LB("v.matches").p,
+                                  LB("v.anchors").as<int>(), LB("c.ascii").as<uint8_t>(),
+                                  LB("v.cons").as<uint8_t>(), LB("v.calls").as<HbVoteCall>(), prm->te_type, s));
+        HB_CUDA_OK(cudaEventRecord(ln.ev[5], s));
         if (n_tasks > n_full) {
-            ENSURE("v.t2f", sizeof(uint32_t) * trunc_to_full.size());
-            HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("v.t2f").p, trunc_to_full.data(), sizeof(uint32_t) * trunc_to_full.size(), cudaMemcpyHostToDevice, s));
-            gate_resolve_kernel<<<(n_tasks - n_full + 255) / 256, 256, 0, s>>>(ctx->buf("v.calls").as<HbVoteCall>(), n_full, n_tasks,
-                                                                              ctx->buf("v.t2f").as<uint32_t>());
+            ENSURE_L("v.t2f", sizeof(uint32_t) * trunc_to_full.size());
+            HB_CUDA_OK(cudaMemcpyAsync(LB("v.t2f").p, trunc_to_full.data(), sizeof(uint32_t) * trunc_to_full.size(), cudaMemcpyHostToDevice, s));
+            gate_resolve_kernel<<<(n_tasks - n_full + 255) / 256, 256, 0, s>>>(LB("v.calls").as<HbVoteCall>(), n_full, n_tasks,
+                                                                              LB("v.t2f").as<uint32_t>());
             ++launches;
         }
-        u32_field_kernel<<<(n_tasks + 255) / 256, 256, 0, s>>>(ctx->buf("v.calls").as<HbVoteCall>(), n_tasks, ctx->buf("v.len").as<uint32_t>());
-        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("v.len").as<uint32_t>(), ctx->buf("v.off").as<uint32_t>(), n_tasks,
-                                         ctx->buf("v.scan_tmp").as<uint32_t>(), ctx->buf("v.total").as<uint64_t>(), s));
-        cons_compact_kernel<<<(n_tasks * 32 + 255) / 256, 256, 0, s>>>(ctx->buf("v.calls").as<HbVoteCall>(), n_tasks,
-                                                                       ctx->buf("v.off").as<uint32_t>(), ctx->buf("v.cons").as<uint8_t>(),
-                                                                       ctx->buf("v.dense").as<uint8_t>());
+        u32_field_kernel<<<(n_tasks + 255) / 256, 256, 0, s>>>(LB("v.calls").as<HbVoteCall>(), n_tasks, LB("v.len").as<uint32_t>());
+        HB_CUDA_OK(hb_exclusive_scan_u32(LB("v.len").as<uint32_t>(), LB("v.off").as<uint32_t>(), n_tasks,
+                                         LB("v.scan_tmp").as<uint32_t>(), LB("v.total").as<uint64_t>(), s));
+        cons_compact_kernel<<<(n_tasks * 32 + 255) / 256, 256, 0, s>>>(LB("v.calls").as<HbVoteCall>(), n_tasks,
+                                                                       LB("v.off").as<uint32_t>(), LB("v.cons").as<uint8_t>(),
+                                                                       LB("v.dense").as<uint8_t>());
         launches += 7;
-        HB_CUDA_OK(cudaEventRecord(ctx->ev[6], s));
-        HB_CUDA_OK(cudaMemcpyAsync(&dense_total, ctx->buf("v.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        HB_CUDA_OK(cudaMemcpyAsync(h_calls.data(), ctx->buf("v.calls").p, sizeof(HbVoteCall) * n_full, cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaEventRecord(ln.ev[6], s));
+        HB_CUDA_OK(cudaMemcpyAsync(&dense_total, LB("v.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaMemcpyAsync(h_calls.data(), LB("v.calls").p, sizeof(HbVoteCall) * n_full, cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
-        HB_CUDA_OK(ctx->h_cons.ensure(dense_total + 1));
-        ctx->last_cons_bytes = dense_total;
+        HB_CUDA_OK(h_cons.ensure(dense_total + 1));
+        ln.cons_bytes = dense_total;
         if (dense_total)
-            HB_CUDA_OK(cudaMemcpyAsync(ctx->h_cons.p, ctx->buf("v.dense").p, dense_total, cudaMemcpyDeviceToHost, s));
-        HB_CUDA_OK(cudaEventRecord(ctx->ev[7], s));
+            HB_CUDA_OK(cudaMemcpyAsync(h_cons.p, LB("v.dense").p, dense_total, cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaEventRecord(ln.ev[7], s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
         tm.d2h_bytes += dense_total + sizeof(HbVoteCall) * n_full;
     } else {
-        HB_CUDA_OK(cudaEventRecord(ctx->ev[5], s));
-        HB_CUDA_OK(cudaEventRecord(ctx->ev[6], s));
-        HB_CUDA_OK(cudaEventRecord(ctx->ev[7], s));
+        HB_CUDA_OK(cudaEventRecord(ln.ev[5], s));
+        HB_CUDA_OK(cudaEventRecord(ln.ev[6], s));
+        HB_CUDA_OK(cudaEventRecord(ln.ev[7], s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
     }
     mark("vote + d2h");
@@ -580,16 +570,16 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     }
     for (uint32_t t = 0; t < n_full; ++t) memcpy(&calls[task_cand[t]], &h_calls[t], sizeof(hb_call));
     if (cons_bytes) *cons_bytes = dense_total;
-    ctx->last_ncand = n_cand; ctx->last_npairs = n_pairs;
-    ctx->last_mat_off = h_mat_off; ctx->last_rows = h_rows; ctx->last_cols = h_cols;
-    cudaEventElapsedTime(&tm.k_ms[0], ctx->ev[0], ctx->ev[1]);   // pack + sketch candidates (incl. H2D)
-    cudaEventElapsedTime(&tm.k_ms[1], ctx->ev[1], ctx->ev[2]);   // seed lookup, sort, cluster, rank
-    cudaEventElapsedTime(&tm.k_ms[2], ctx->ev[2], ctx->ev[3]);   // banded extension + traceback
-    cudaEventElapsedTime(&tm.k_ms[3], ctx->ev[3], ctx->ev[4]);   // copy rules + star MSA
-    cudaEventElapsedTime(&tm.k_ms[4], ctx->ev[4], ctx->ev[5]);   // clean + judge
-    cudaEventElapsedTime(&tm.k_ms[5], ctx->ev[5], ctx->ev[6]);   // consensus compaction
-    cudaEventElapsedTime(&tm.d2h_ms, ctx->ev[6], ctx->ev[7]);
-    cudaEventElapsedTime(&tm.kernel_ms, ctx->ev[0], ctx->ev[6]);
+    ln.n_pairs = n_pairs; ln.ext_steps = ext_steps;
+    ln.mat_off = h_mat_off; ln.rows = h_rows; ln.cols = h_cols;
+    cudaEventElapsedTime(&tm.k_ms[0], ln.ev[0], ln.ev[1]);   // pack + sketch candidates (incl. H2D)
+    cudaEventElapsedTime(&tm.k_ms[1], ln.ev[1], ln.ev[2]);   // seed lookup, sort, cluster, rank
+    cudaEventElapsedTime(&tm.k_ms[2], ln.ev[2], ln.ev[3]);   // banded extension + traceback
+    cudaEventElapsedTime(&tm.k_ms[3], ln.ev[3], ln.ev[4]);   // copy rules + star MSA
+    cudaEventElapsedTime(&tm.k_ms[4], ln.ev[4], ln.ev[5]);   // clean + judge
+    cudaEventElapsedTime(&tm.k_ms[5], ln.ev[5], ln.ev[6]);   // consensus compaction
+    cudaEventElapsedTime(&tm.d2h_ms, ln.ev[6], ln.ev[7]);
+    cudaEventElapsedTime(&tm.kernel_ms, ln.ev[0], ln.ev[6]);
     tm.h2d_ms = 0.f;
     tm.launches = launches;
     tm.k_ms[6] = (float)n_pairs;                                  // diagnostics: pairs extended
@@ -598,17 +588,148 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     return HB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii, const uint64_t* cand_off,
+                         const hb_params* prm, hb_call* calls, uint64_t* cons_bytes) {
+    if (!ctx || !cand_ascii || !cand_off || !prm || !calls) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: null argument");
+    if (!ctx->have_index) return hb_fail_msg(ctx, HB_ESTATE, "hb_adjust: call hb_genome_load + hb_index_build first");
+    if (n_cand == 0) { if (cons_bytes) *cons_bytes = 0; return HB_OK; }
+    if (n_cand > (1u << 17)) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: at most 131072 candidates per call");
+    if (prm->te_type < HB_TE_TIR || prm->te_type > HB_TE_NON_LTR)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: te_type must be HB_TE_TIR, HB_TE_HELITRON or HB_TE_NON_LTR");
+    if (prm->max_loci < 1 || prm->max_loci > 512 || prm->max_rows < 2 || prm->max_rows > 100 || prm->occ_cap < 1 ||
+        prm->flank < 0 || prm->flank > 200)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: parameter out of range");
+    int any_long = 0;                 // candidates beyond the 16-bit extension kernel (hb_extend16.cuh)
+    for (uint32_t c = 0; c < n_cand; ++c) {
+        const uint64_t L = cand_off[c + 1] - cand_off[c];
+        if (L < 3 || L > 32000) return hb_fail_msg(ctx, HB_EINVAL, "hb_adjust: candidate " + std::to_string(c) + " length must be in [3, 32000]");
+        if (L > HB_EXTEND16_MAX_L) any_long = 1;
+    }
+    cudaSetDevice(ctx->device);
+    // ---- serial: one batch on the context's stream (the hb_last_copies / hb_last_msa getters read it) ----
+    uint32_t n_parts = prm->overlap >= 2 ? (uint32_t)prm->overlap : 1u;
+    if (n_parts > 16) n_parts = 16;
+    if (n_cand < 64 * n_parts) n_parts = 1;
+    ctx->cons_parts.clear();
+    if (ctx->part_cons.size() < n_parts) ctx->part_cons.resize(n_parts);
+    if (n_parts == 1) {
+        HbLane& ln = ctx->lane[0];
+        uint64_t nb = 0;
+        const int rc = adjust_batch(ctx, ln, ctx->part_cons[0], n_cand, cand_ascii, cand_off, prm, any_long, calls, &nb);
+        if (rc != HB_OK) return rc;
+        ctx->timing = ln.timing;
+        ctx->last_overlapped = false;
+        ctx->last_cons_bytes = nb;
+        ctx->cons_parts.push_back({(const uint8_t*)ctx->part_cons[0].p, nb});
+        ctx->last_ncand = n_cand; ctx->last_npairs = ln.n_pairs;
+        ctx->last_mat_off = ln.mat_off; ctx->last_rows = ln.rows; ctx->last_cols = ln.cols;
+        if (cons_bytes) *cons_bytes = nb;
+        return HB_OK;
+    }
+    // ---- overlapped: n_parts sub-batches (contiguous candidate ranges of about equal bases) dealt to two
+    // lanes, each driven by its own host thread on its own stream.  The extension kernel saturates the
+    // integer ALU pipe while sort / traceback / MSA / judge are latency- or memory-bound, so sub-batches in
+    // different stages fill each other's idle issue slots; the host-side gaps (counts read back, task
+    // tables) of one lane hide behind the other lane's kernels.  Results do not depend on the split.
+    std::vector<uint32_t> cut(n_parts + 1, 0);
+    {
+        const uint64_t total = cand_off[n_cand] - cand_off[0];
+        uint32_t c = 0;
+        for (uint32_t k = 1; k < n_parts; ++k) {
+            const uint64_t want = cand_off[0] + total * k / n_parts;
+            while (c < n_cand && cand_off[c] < want) ++c;
+            cut[k] = std::max(c, cut[k - 1]);
+        }
+        cut[n_parts] = n_cand;
+    }
+    cudaStream_t s0 = ctx->stream;
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[8], s0));
+    for (int l = 1; l <= 2; ++l) HB_CUDA_OK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev[8], 0));
+    std::vector<uint64_t> part_bytes(n_parts, 0);
+    std::vector<hb_timing> part_tm(n_parts);
+    std::vector<uint32_t> part_pairs(n_parts, 0);
+    int lane_rc[2] = {HB_OK, HB_OK};
+    auto worker = [&](int t) {
+        cudaSetDevice(ctx->device);
+        HbLane& ln = ctx->lane[1 + t];
+        for (uint32_t k = (uint32_t)t; k < n_parts; k += 2) {
+            const uint32_t c0 = cut[k], c1 = cut[k + 1];
+            if (c1 <= c0) continue;
+            std::vector<uint64_t> off(c1 - c0 + 1);
+            for (uint32_t c = c0; c <= c1; ++c) off[c - c0] = cand_off[c] - cand_off[c0];
+            int sub_long = 0;
+            for (uint32_t c = c0; c < c1; ++c) if (cand_off[c + 1] - cand_off[c] > HB_EXTEND16_MAX_L) sub_long = 1;
+            const int rc = adjust_batch(ctx, ln, ctx->part_cons[k], c1 - c0, cand_ascii + cand_off[c0], off.data(), prm,
+                                        sub_long, calls + c0, &part_bytes[k]);
+            if (rc != HB_OK) { lane_rc[t] = rc; return; }
+            part_tm[k] = ln.timing; part_pairs[k] = ln.n_pairs;
+        }
+        cudaEventRecord(ln.ev[7], ln.stream);
+    };
+    {
+        std::thread th(worker, 1);
+        worker(0);
+        th.join();
+    }
+    if (lane_rc[0] != HB_OK) return lane_rc[0];
+    if (lane_rc[1] != HB_OK) return lane_rc[1];
+    for (int l = 1; l <= 2; ++l) HB_CUDA_OK(cudaStreamWaitEvent(s0, ctx->lane[l].ev[7], 0));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[9], s0));
+    HB_CUDA_OK(cudaStreamSynchronize(s0));
+    // stitch: consensus parts in candidate order, cons_off rebased; stage times are sums over the
+    // sub-batches (they overlap, so their sum exceeds kernel_ms = first launch .. last kernel end)
+    hb_timing tm;
+    memset(&tm, 0, sizeof(tm));
+    uint64_t base = 0;
+    uint32_t pairs = 0;
+    for (uint32_t k = 0; k < n_parts; ++k) {
+        if (base)
+            for (uint32_t c = cut[k]; c < cut[k + 1]; ++c) calls[c].cons_off += (int64_t)base;
+        ctx->cons_parts.push_back({(const uint8_t*)ctx->part_cons[k].p, part_bytes[k]});
+        base += part_bytes[k];
+        for (int i = 0; i < 6; ++i) tm.k_ms[i] += part_tm[k].k_ms[i];
+        tm.k_ms[6] += part_tm[k].k_ms[6]; tm.k_ms[7] += part_tm[k].k_ms[7];
+        tm.d2h_ms += part_tm[k].d2h_ms;
+        tm.h2d_bytes += part_tm[k].h2d_bytes; tm.d2h_bytes += part_tm[k].d2h_bytes;
+        tm.launches += part_tm[k].launches;
+        pairs += part_pairs[k];
+    }
+    cudaEventElapsedTime(&tm.kernel_ms, ctx->ev[8], ctx->ev[9]);
+    ctx->timing = tm;
+    ctx->last_overlapped = true;
+    ctx->last_cons_bytes = base;
+    ctx->last_ncand = n_cand; ctx->last_npairs = pairs;
+    ctx->last_mat_off.clear(); ctx->last_rows.clear(); ctx->last_cols.clear();
+    if (cons_bytes) *cons_bytes = base;
+    return HB_OK;
+}
+
 extern "C" int hb_last_cons(hb_ctx* ctx, uint8_t* out, uint64_t cap) {
     if (!ctx || !out) return HB_EINVAL;
     if (cap < ctx->last_cons_bytes) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_cons: buffer too small");
-    if (ctx->last_cons_bytes) memcpy(out, ctx->h_cons.p, ctx->last_cons_bytes);
+    uint64_t at = 0;
+    for (const auto& part : ctx->cons_parts) { if (part.second) memcpy(out + at, part.first, part.second); at += part.second; }
     return HB_OK;
 }
 
 extern "C" int hb_last_cons_device(hb_ctx* ctx, const void** dptr, uint64_t* nbytes) {
     if (!ctx || !dptr || !nbytes) return HB_EINVAL;
     *nbytes = ctx->last_cons_bytes;
-    *dptr = ctx->last_cons_bytes ? ctx->buf("v.dense").p : nullptr;
+    *dptr = nullptr;
+    if (!ctx->last_cons_bytes) return HB_OK;
+    if (!ctx->last_overlapped) { *dptr = ctx->buf("v.dense").p; return HB_OK; }
+    // overlapped run: the sub-batches' dense buffers were reused; stage the stitched bytes once more
+    cudaSetDevice(ctx->device);
+    HB_CUDA_OK(ctx->buf("v.dense_all").ensure(ctx->last_cons_bytes + 1));
+    uint64_t at = 0;
+    for (const auto& part : ctx->cons_parts) {
+        if (part.second)
+            HB_CUDA_OK(cudaMemcpyAsync((uint8_t*)ctx->buf("v.dense_all").p + at, part.first, part.second, cudaMemcpyHostToDevice, ctx->stream));
+        at += part.second;
+    }
+    HB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    *dptr = ctx->buf("v.dense_all").p;
     return HB_OK;
 }
 
@@ -616,6 +737,7 @@ extern "C" int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t*
     if (!ctx || !n) return HB_EINVAL;
     *n = ctx->last_npairs;
     if (!out) return HB_OK;
+    if (ctx->last_overlapped) return hb_fail_msg(ctx, HB_ESTATE, "hb_last_copies: needs a serial hb_adjust (hb_params.overlap < 2)");
     if (cap < ctx->last_npairs) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_copies: buffer too small");
     if (ctx->last_npairs == 0) return HB_OK;
     cudaSetDevice(ctx->device);
@@ -636,6 +758,7 @@ extern "C" int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t*
 
 extern "C" int hb_last_msa(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii, uint64_t cap, int32_t* R, int32_t* C) {
     if (!ctx || !R || !C) return HB_EINVAL;
+    if (ctx->last_overlapped) return hb_fail_msg(ctx, HB_ESTATE, "hb_last_msa: needs a serial hb_adjust (hb_params.overlap < 2)");
     if (cand >= ctx->last_ncand) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_msa: candidate out of range");
     *R = (int32_t)ctx->last_rows[cand]; *C = (int32_t)ctx->last_cols[cand];
     const uint64_t bytes = (uint64_t)*R * (uint64_t)*C;

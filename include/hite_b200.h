@@ -123,6 +123,9 @@ typedef struct {
     int32_t result_type;  /* 1 = 'cons' */
     int32_t trunc_gate;   /* 1 = truncated-member pass first (module/Util.py:8116-8124, :10442-10446); 1 */
     uint64_t tb_budget_bytes; /* HBM budget of the traceback stream, 0 = 16 GiB */
+    int32_t overlap;      /* 0 / 1 = one batch on the context's stream; N >= 2 = N sub-batches (contiguous candidate
+                           * ranges) software-pipelined over two CUDA streams: same results, stages overlap */
+    int32_t reserved;
 } hb_params;
 
 /* One candidate x locus pair: what get_copies_minimap2 (module/Util.py:7977-8030) returns per SAM

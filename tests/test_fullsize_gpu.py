@@ -15,8 +15,15 @@ def test_c2_full_size_properties(ctx):
     assert len(wl.cand_seqs) == 10_000
     ctx.load_genome(wl.contig_seqs)
     ctx.build_index(15, 10)
-    calls, cons = ctx.adjust_raw(wl.cand_seqs, "tir", 1)
+    calls, cons = ctx.adjust_raw(wl.cand_seqs, "tir", 1, overlap=0)
     copies = ctx.last_copies()
+    # 0. stream-overlapped sub-batches (the default from 2048 candidates up) return the very same bytes
+    for ov in (None, 2, 5):
+        c_ov, k_ov = ctx.adjust_raw(wl.cand_seqs, "tir", 1, overlap=ov)
+        assert c_ov.tobytes() == calls.tobytes() and np.array_equal(k_ov, cons), ov
+    with pytest.raises(Exception):
+        ctx.last_copies()                     # the per-pair getters need a serial run
+    calls, cons = ctx.adjust_raw(wl.cand_seqs, "tir", 1, overlap=0)
     text = cons.tobytes().decode("latin-1")
     seqs = [text[int(o):int(o) + int(l)] for o, l in zip(calls["cons_off"], calls["cons_len"])]
     te = calls["is_te"] != 0
