@@ -285,15 +285,6 @@ def main():
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     wall_max, dev_max = float(stats[0]), float(stats[1]) * 1e-3
     n_total = len(wl.cand_seqs)
-    # serial pass (one batch, one stream) after the timed region: per-stage times without the stream overlap
-    # of the timed steps, and the per-pair records (the getters need a serial run)
-    ser_stage = np.zeros(8)
-    ser_dev = []
-    for _ in range(3):
-        ctx.adjust_raw(host_cands, "tir", 1, overlap=0)
-        tms = ctx.timing()
-        ser_stage += np.array(tms["k_ms"]); ser_dev.append(tms["kernel_ms"])
-    ser_stage /= 3.0
     copies = ctx.last_copies()
     lens = np.array([len(c) for c in my_cands])
     pair_L = lens[copies["cand"]]
@@ -315,7 +306,6 @@ def main():
         except Exception:
             pass
         achieved = algo_bytes / ext_s / 1e9 if ext_s > 0 else 0.0
-        ser_ext_s = float(ser_stage[2]) * 1e-3
         dp_cells = float(stage[7] / args.steps) * 1e6 * 32
         line = {
             "metric": "candidate TEs boundary-adjusted/sec", "value": n_total * args.steps / dev_max, "unit": "candidates/s",
@@ -324,8 +314,7 @@ def main():
             "config": {"workload": wname, "genome_bp": wl.genome_bp, "candidates": n_total, "k": 15, "w": 10,
                        "max_loci": 128, "band": 64, "l2": "inputs larger than L2 (packed genome+index %.0f MB, traceback stream %.1f GB/step)"
                        % ((info["total_padded"] * 0.375 + info["n_minimizers"] * 8) / 1e6, float(stage[7] / args.steps) * 1e6 * 16 / 1e9),
-                       "parallelism": "candidates sharded over %d GPU(s), genome+index replicated, 1 NCCL all-gather/step; "
-                                      "per GPU 4 candidate sub-batches pipelined over 2 CUDA streams" % world},
+                       "parallelism": "candidates sharded over %d GPU(s), genome+index replicated, 1 NCCL all-gather/step" % world},
             "e2e": {"value": n_total * args.steps / wall_max, "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches) * args.steps,
@@ -333,19 +322,12 @@ def main():
             "roofline": {"kernel": "extend16_kernel + traceback_kernel (banded SW, two pairs per lane; hb_extend16.cuh)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "note": "integer-ALU-bound DP, not HBM-bound: %.2f GCUPS alone on the GPU (serial pass), ALU pipe %s %% of peak "
-                                 "(ncu, profiles/); kernel_ms is the stage's event time inside the timed, stream-overlapped steps "
-                                 "(sub-batches in other stages share the SMs), kernel_ms_exclusive the same stage run alone; "
+                         "note": "integer-ALU-bound DP, not HBM-bound: %.2f GCUPS, ALU pipe %s %% of peak (ncu, profiles/); "
                                  "algorithmic bytes/pair=(2L+64)*3/8+4L+56"
-                                 % (dp_cells / ser_ext_s / 1e9 if ser_ext_s else 0, "%.1f" % alu_pct if alu_pct else "n/a"),
-                         "kernel_ms": ext_s * 1e3, "kernel_ms_exclusive": ser_ext_s * 1e3,
-                         "achieved_exclusive": algo_bytes / ser_ext_s / 1e9 if ser_ext_s else 0.0, "pairs": int(len(copies))},
+                                 % (dp_cells / ext_s / 1e9 if ext_s else 0, "%.1f" % alu_pct if alu_pct else "n/a"),
+                         "kernel_ms": ext_s * 1e3, "pairs": int(len(copies))},
             "stages_ms": {k: float(v / args.steps) for k, v in zip(
                 ("sketch_cands", "seed_sort_cluster", "extend", "copy_rules_msa", "clean_judge", "compact"), stage[:6])},
-            "stages_note": "stages_ms: summed over the overlapped sub-batches of the timed steps (exceeds ms_per_step); "
-                           "stages_ms_serial: one batch on one stream, %.2f ms/step" % float(np.mean(ser_dev)),
-            "stages_ms_serial": {k: float(v) for k, v in zip(
-                ("sketch_cands", "seed_sort_cluster", "extend", "copy_rules_msa", "clean_judge", "compact"), ser_stage[:6])},
             "setup": {"genome_load_ms": t_load["kernel_ms"] + t_load["h2d_ms"], "index_build_ms": t_idx["kernel_ms"],
                       "index_Mbp_per_s": wl.genome_bp / 1e6 / max(1e-9, t_idx["kernel_ms"] * 1e-3), "setup_wall_s": setup_s,
                       "n_minimizers": int(info["n_minimizers"])},

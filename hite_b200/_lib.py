@@ -261,8 +261,9 @@ class Context:
         """One ``flank_region_align_v5``-equivalent round (kernels ii + iii) over the candidates.
         Returns ``(calls, cons)``: a structured array (CALL_DTYPE, one record per candidate) and the
         consensus bytes; candidate i's consensus is ``cons[calls['cons_off'][i] : +calls['cons_len'][i]]``.
-        ``overlap``: number of candidate sub-batches software-pipelined over two CUDA streams (same results;
-        default 4 from 2048 candidates up, else one serial batch -- which ``last_copies`` / ``last_msa`` need)."""
+        ``overlap`` >= 2: that many candidate sub-batches software-pipelined over two CUDA streams (same bytes
+        back; measured on B200 it does not beat the serial batch -- every stage already fills the SMs, see
+        tools/overlap_sweep.py -- so the default is one serial batch, which ``last_copies`` / ``last_msa`` need)."""
         if isinstance(cand_seqs, tuple):                      # pre-flattened (uint8 array, uint64 offsets)
             flat, off = cand_seqs
             n = len(off) - 1
@@ -277,7 +278,7 @@ class Context:
             return calls, np.zeros(0, dtype=np.uint8)
         prm = HbParams(occ_cap, max_loci, flank, max_rows, TE_TYPES[te_type], int(plant),
                        1 if result_type == "cons" else 0, 1 if trunc_gate else 0, int(tb_budget_bytes),
-                       int(overlap) if overlap is not None else (4 if n >= 2048 else 0), 0)
+                       int(overlap) if overlap is not None else 0, 0)
         nbytes = C.c_uint64(0)
         self._check(self._lib.hb_adjust(self._h, n, _ptr(flat), _ptr(off), C.byref(prm), _ptr(calls), C.byref(nbytes)),
                     "hb_adjust")

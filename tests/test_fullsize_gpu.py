@@ -17,8 +17,8 @@ def test_c2_full_size_properties(ctx):
     ctx.build_index(15, 10)
     calls, cons = ctx.adjust_raw(wl.cand_seqs, "tir", 1, overlap=0)
     copies = ctx.last_copies()
-    # 0. stream-overlapped sub-batches (the default from 2048 candidates up) return the very same bytes
-    for ov in (None, 2, 5):
+    # 0. stream-overlapped sub-batches (hb_params.overlap) return the very same bytes as the serial batch
+    for ov in (2, 5):
         c_ov, k_ov = ctx.adjust_raw(wl.cand_seqs, "tir", 1, overlap=ov)
         assert c_ov.tobytes() == calls.tobytes() and np.array_equal(k_ov, cons), ov
     with pytest.raises(Exception):
