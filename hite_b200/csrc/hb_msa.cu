@@ -205,8 +205,6 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
     const HbAln a = alns[p];
     const int my_row = trunc ? a.trow : a.row;
     if (my_row < 0) return;
-    // truncated pass keeps only the first 500 and last 500 bases of the extended copy
-    const int64_t ext_lo = a.j_s - flank, ext_hi = a.j_e + flank;
     const HbLocus pr = pairs[p];
     const uint32_t c = pr.cand;
     const int rel = (int)pr.rel;
@@ -214,21 +212,36 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
     const uint32_t* cq = colq + col_off[c];
     uint8_t* row = mat + mat_off[c] + (size_t)my_row * C;
     const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
+    // Every position a kept row reads lies inside its contig (copy_filter_kernel dropped rows whose
+    // +-flank extension leaves it), i.e. inside [0, tot) with tot < 2^32: positions are plain uint32,
+    // no bounds checks.  js / je: oriented position of the first / last aligned base.
+    const uint32_t j0 = (uint32_t)pr.j0, js = (uint32_t)a.j_s, je = (uint32_t)a.j_e;
+    const uint32_t totm1 = (uint32_t)(tot - 1);
+    const int i_s = a.i_s, i_e = a.i_e;
+    // truncated pass keeps only the first 500 and last 500 bases of the extended copy
+    const uint32_t ext_lo = js - (uint32_t)flank, ext_len = je - js + 2u * (uint32_t)flank + 1u;
     auto sym_at = [&](int col) -> uint32_t {
         const uint32_t e = cq[col];
-        const int q = (int)(e >> 8) - flank, slot = (int)(e & 255u);
-        int64_t j;
-        if (q >= a.i_s && q <= a.i_e) {
+        const int q = (int)(e >> 8) - flank;
+        const uint32_t slot = e & 255u;
+        uint32_t j;
+        if (q >= i_s && q <= i_e) {
             const uint32_t v = qr[q];
-            j = pr.j0 + q + ((int64_t)(v & 0xFFFF) - 32768) + slot;
-            if (slot == 0 ? ((v >> 24) & 1u) != 0 : slot > (int)((v >> 16) & 255u)) return HB_SYM_GAP;
+            if (slot == 0 ? ((v >> 24) & 1u) != 0 : slot > ((v >> 16) & 255u)) return HB_SYM_GAP;
+            j = j0 + (uint32_t)q + (v & 0xFFFFu) - 32768u + slot;
         } else {
             if (slot != 0) return HB_SYM_GAP;
-            if (q < a.i_s) { if (q < a.i_s - flank) return HB_SYM_GAP; j = a.j_s - (a.i_s - q); }
-            else { if (q > a.i_e + flank) return HB_SYM_GAP; j = a.j_e + (q - a.i_e); }
+            if (q < i_s) { if (q < i_s - flank) return HB_SYM_GAP; j = js - (uint32_t)(i_s - q); }
+            else { if (q > i_e + flank) return HB_SYM_GAP; j = je + (uint32_t)(q - i_e); }
         }
-        if (trunc && (j - ext_lo) >= 500 && (ext_hi - j) >= 500) return HB_SYM_GAP;
-        return (uint32_t)target_base(gseq2, gnmask, tot, rel, j);
+        if (trunc) {
+            const uint32_t d = j - ext_lo;                 // offset inside the extended copy
+            if (d >= 500u && ext_len - 1u - d >= 500u) return HB_SYM_GAP;
+        }
+        const uint32_t pos = rel ? totm1 - j : j;
+        if ((gnmask[pos >> 5] >> (pos & 31u)) & 1u) return HB_SYM_N;
+        const uint32_t b2 = (gseq2[pos >> 4] >> (2u * (pos & 15u))) & 3u;
+        return rel ? 3u - b2 : b2;
     };
     const int a0 = (int)(reinterpret_cast<uintptr_t>(row) & 3u);        // virtual column x = col + a0 is word aligned
     for (int x = 4 * lane; x < C + a0; x += 128) {
