@@ -312,9 +312,18 @@ HB_HD void extend16_warp(W& w, uint32_t group0, const uint32_t* __restrict__ ord
 }
 
 // ---- traceback of one pair (one thread per pair; the walk is inherently serial) ---------------------
-// A 32 B sector holds the nibbles of 64 consecutive anti-diagonals of one band column, so a run of
-// diagonal moves re-uses it 32 times.  Edit records are staged 8 query positions (one 32 B sector) at
-// a time instead of one scattered 4 B store per step.
+// A 32 B sector holds the nibbles of 64 consecutive anti-diagonals of one band column and a word the
+// nibbles of 8; a diagonal move stays in the column and steps two anti-diagonals back, so a word covers
+// up to 4 consecutive diagonal moves: they are recognised with one mask operation and retired together
+// (alignments are mostly diagonal runs).  Edit records are staged 8 query positions (one 32 B sector)
+// at a time instead of one scattered 4 B store per step.
+HB_HD int hb_clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
 HB_HD void traceback_pair(uint32_t p, const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ tb_unit_off,
                           uint32_t tb_unit_base, const uint32_t* __restrict__ tbuf,
                           const uint32_t* __restrict__ qrec_unit_off, uint32_t* __restrict__ qrec,
@@ -328,20 +337,26 @@ HB_HD void traceback_pair(uint32_t p, const HbLocus* __restrict__ pairs, const u
     uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
     int i = a.i_e, o = (int)(a.j_e - j0) - a.i_e, pending_d = 0;
     int i_s = i, o_s = o;
-    int c_sec = -1;
+    int c_sec = -1, c_g8 = -1;
     uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
-    auto fetch = [&](int ii, int oo) -> uint32_t {
+    uint32_t w = 0;                                       // cached word: anti-diagonals [8 g8, 8 g8 + 8) of the sector
+    // nibble of cell (ii, oo); leaves its word in w and its position inside the word in *k
+    auto fetch = [&](int ii, int oo, int* k) -> uint32_t {
         const int r = 2 * ii + oo + HB;
         const int sec = (r >> 6) * HB + ((oo + HB) >> 1);
+        const int g8 = (r >> 3) & 7;
         if (sec != c_sec) {
-            c_sec = sec;
+            c_sec = sec; c_g8 = -1;
             const uint4* src = reinterpret_cast<const uint4*>(tb + (size_t)sec * 8);
             s0 = src[0]; s1 = src[1];
         }
-        const int g8 = (r >> 3) & 7;
-        const uint32_t wv = g8 == 0 ? s0.x : g8 == 1 ? s0.y : g8 == 2 ? s0.z : g8 == 3 ? s0.w :
-                            g8 == 4 ? s1.x : g8 == 5 ? s1.y : g8 == 6 ? s1.z : s1.w;
-        return (wv >> (4 * (r & 7))) & 15u;
+        if (g8 != c_g8) {
+            c_g8 = g8;
+            w = g8 == 0 ? s0.x : g8 == 1 ? s0.y : g8 == 2 ? s0.z : g8 == 3 ? s0.w :
+                g8 == 4 ? s1.x : g8 == 5 ? s1.y : g8 == 6 ? s1.z : s1.w;
+        }
+        *k = r & 7;
+        return (w >> (4 * (r & 7))) & 15u;
     };
     uint32_t blk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     auto record = [&](int ii, uint32_t v) {
@@ -355,20 +370,31 @@ HB_HD void traceback_pair(uint32_t p, const HbLocus* __restrict__ pairs, const u
         }
     };
     while (i >= 0) {
-        uint32_t nib = fetch(i, o);
+        int k;
+        uint32_t nib = fetch(i, o, &k);
         const uint32_t src = nib & 3u;
         if (src == 0) break;
         if (src == 1) {
-            record(i, (uint32_t)(o + 32768) | ((uint32_t)(pending_d < 255 ? pending_d : 255) << 16) | (1u << 25));
-            pending_d = 0; i_s = i; o_s = o;
-            --i;
+            // diagonal run inside the cached word: nibbles k, k-2, ... whose source is "diag"
+            const uint32_t x = w ^ 0x11111111u;
+            const uint32_t notdiag = (x | (x >> 1)) & 0x11111111u;             // bit 4t: nibble t is not a diag cell
+            const uint32_t lanes = ((k & 1) ? 0x10101010u : 0x01010101u) & ((2u << (4 * k)) - 1u);
+            const uint32_t stop = notdiag & lanes;                             // same-parity nibbles <= k that end the run
+            int n = stop ? (k - ((31 - hb_clz32(stop)) >> 2)) >> 1 : (k >> 1) + 1;
+            if (n > i + 1) n = i + 1;
+            const uint32_t base = (uint32_t)(o + 32768) | (1u << 25);
+            record(i, base | ((uint32_t)(pending_d < 255 ? pending_d : 255) << 16));
+            for (int t = 1; t < n; ++t) record(i - t, base);
+            pending_d = 0;
+            i -= n;
+            i_s = i + 1; o_s = o;
         } else if (src == 2) {                            // run of target-only bases
             for (;;) {
                 ++pending_d;
                 const bool ext = (nib >> 2) & 1u;
                 --o;
                 if (!ext) break;
-                nib = fetch(i, o);
+                nib = fetch(i, o, &k);
             }
         } else {                                          // run of query-only bases
             for (;;) {
@@ -377,7 +403,7 @@ HB_HD void traceback_pair(uint32_t p, const HbLocus* __restrict__ pairs, const u
                 const bool ext = (nib >> 3) & 1u;
                 --i; ++o;
                 if (!ext || i < 0) break;
-                nib = fetch(i, o);
+                nib = fetch(i, o, &k);
             }
         }
     }
