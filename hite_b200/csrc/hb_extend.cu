@@ -211,7 +211,7 @@ struct DevWarp {
 };
 
 template <int HB>
-__global__ void __launch_bounds__(EXT_WARPS * 32)
+__global__ void __launch_bounds__(EXT_WARPS * 32, 4)
 extend16_kernel(const uint32_t* __restrict__ order, const uint64_t* __restrict__ n_order_p,
                 const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ gseq2,
                 const uint32_t* __restrict__ gnmask, uint64_t tot, const uint32_t* __restrict__ cseq2,

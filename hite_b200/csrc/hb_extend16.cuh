@@ -190,18 +190,31 @@ HB_HD void extend16_warp(W& w, uint32_t group0, const uint32_t* __restrict__ ord
     uint32_t* rq = s_rq + sub * WIN;
     uint32_t* rt = s_rt + sub * WIN;
 
+    // Branch-free one-hot fetches (the window refill runs once per 64 anti-diagonals but for both pairs,
+    // both sequences and 32 / HB positions per lane): out-of-range positions read word 0 and select 0.
+    auto code_at = [&](const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask, uint64_t pos, bool ok,
+                       bool comp) -> uint32_t {
+        const uint64_t p = ok ? pos : 0;
+        const uint32_t nm = (nmask[p >> 5] >> (p & 31)) & 1u;
+        const uint32_t b = (seq2[p >> 4] >> (2 * (p & 15))) & 3u;
+        const uint32_t oh = comp ? (64u >> b) : (8u << b);           // complement: 3 - b
+        return (ok && !nm) ? oh : 0u;
+    };
     auto qcode = [&](int x) -> uint32_t {
         uint32_t v = 0;
 #pragma unroll
         for (int z = 0; z < 2; ++z)
-            if (x >= 0 && x < L[z]) v |= onehot(base_at(cseq2, cnmask, cstart[z] + (uint64_t)x)) << (16 * z);
+            v |= code_at(cseq2, cnmask, cstart[z] + (uint64_t)(int64_t)x, (unsigned)x < (unsigned)L[z], false) << (16 * z);
         return v;
     };
     auto tcode = [&](int x) -> uint32_t {
         uint32_t v = 0;
 #pragma unroll
-        for (int z = 0; z < 2; ++z)
-            if (pid[z] != NONE) v |= onehot(oriented_base_at(gseq2, gnmask, tot, rel[z], j0[z] + x)) << (16 * z);
+        for (int z = 0; z < 2; ++z) {
+            const int64_t j = j0[z] + x;
+            const bool ok = pid[z] != NONE && j >= 0 && (uint64_t)j < tot;
+            v |= code_at(gseq2, gnmask, rel[z] ? tot - 1 - (uint64_t)j : (uint64_t)j, ok, rel[z] != 0) << (16 * z);
+        }
         return v;
     };
     // window of the first super-step: positions [-HB, 32)
