@@ -21,7 +21,7 @@
 namespace hb16 {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr int HB16_MAX_L = HB_EXTEND16_MAX_L;       // 2 * L + 6 < 32768
+constexpr int HB16_MAX_L = HB_EXTEND16_MAX_L;       // 2 * L + 4 + 6 < 32768
 constexpr int NARROW_SPREAD = 8;         // HB-align S7
 
 // ---- packed signed-16x2 primitives (device: one SASS instruction each; host: plain C) ------------
@@ -65,12 +65,31 @@ HB_HD uint32_t max3_relu(uint32_t a, uint32_t b, uint32_t c) {      // max(a, b,
     return h_pack(lo > 0 ? lo : 0, hi > 0 ? hi : 0);
 #endif
 }
+HB_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) {           // max(a, b, c)
+#ifdef __CUDA_ARCH__
+    return __vimax3_s16x2(a, b, c);
+#else
+    int lo = h_lo(a), hi = h_hi(a);
+    if (h_lo(b) > lo) lo = h_lo(b);
+    if (h_lo(c) > lo) lo = h_lo(c);
+    if (h_hi(b) > hi) hi = h_hi(b);
+    if (h_hi(c) > hi) hi = h_hi(c);
+    return h_pack(lo, hi);
+#endif
+}
 HB_HD uint32_t minu2(uint32_t a, uint32_t b) {                      // unsigned min per half
 #ifdef __CUDA_ARCH__
     return __vminu2(a, b);
 #else
     const uint32_t al = a & 0xFFFF, bl = b & 0xFFFF, ah = a >> 16, bh = b >> 16;
     return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+#endif
+}
+HB_HD uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c) {         // unsigned min(a, b, c) per half
+#ifdef __CUDA_ARCH__
+    return __vimin3_u16x2(a, b, c);
+#else
+    return minu2(minu2(a, b), c);
 #endif
 }
 // max(a, b) per half; *keep_x = (a >= b) for that half
@@ -110,43 +129,51 @@ HB_HD int oriented_base_at(const uint32_t* __restrict__ gseq2, const uint32_t* _
 HB_HD uint32_t onehot(int c) { return c < 4 ? (8u << c) : 0u; }
 
 constexpr uint32_t K_M2 = 0xFFFEFFFEu;   // (-2, -2)  gap extend
-constexpr uint32_t K_M4 = 0xFFFCFFFCu;   // (-4, -4)  mismatch
 constexpr uint32_t K_M6 = 0xFFFAFFFAu;   // (-6, -6)  gap open + extend
 constexpr uint32_t K_6 = 0x00060006u;    // match - mismatch
+constexpr uint32_t K_4 = 0x00040004u;    // the bias: stored E, F, Z and the H inside a cell are score + 4
 constexpr uint32_t K_1 = 0x00010001u;
 
 // One DP cell for both halves.  PAR 0: even anti-diagonal (left neighbour was shuffled in, the lane at
-// the band edge has none -> emask), PAR 1: odd (up neighbour shuffled in -> fmask).
-// E and F are kept clamped at 0 like in hb_extend.cu.  z = max(H_neighbour - 6, 0) is the clamped
-// "open" value; the gap-extend flag is (E != z): it differs from the oracle's (E_l - 2 > H_l - 6)
-// only where E == 0, and such a cell is never walked in gap state.
+// the band edge has none), PAR 1: odd (up neighbour shuffled in).
+//
+// Representation.  E and F are kept clamped at 0 like in hb_extend.cu, and every stored value carries a
+// +4 bias (E', F', Z' = score + 4, so "zero" is 4); the diagonal input hd is the UNBIASED H of two steps
+// ago.  With that, hd + {6, 0} is directly the biased diagonal candidate (H_d + 4 + {+2, -4}) and
+// h' - 4 the unbiased H: both are plain 32-bit adds of non-negative halves that can never carry across
+// the halves, so ptxas is free to issue them on the FMA pipe (IMAD.IADD) -- the kernel is bound by the
+// ALU pipe -- and the RELU disappears because E', F' >= 4 already floor the maximum.
+//   z = max(H' - 6, 4) is the clamped "open" value of a cell, computed ONCE by its owner (Z) and
+//   shuffled instead of H, so a step costs three VIADDMNMX, not four.
+//   Gap-extend flag = (E' != z): differs from the oracle's (E_l - 2 > H_l - 6) only where E == 0, and
+//   such a cell is never walked in gap state.  At a band-edge lane the forced "zero" E' / F' may be below
+//   the garbage z it was compared with: both halves sit on the edge there, the borrow stays inside
+//   that cell's flags, and they are never read.
 // NW: traceback nibbles, pair A at bits 0-3, pair B at bits 16-19:
 //   bits0-1 source of H (0 stop, 1 diag, 2 E, 3 F), bit2 E extended, bit3 F extended
 template <int PAR>
-HB_HD void cell2(uint32_t zl, uint32_t el, uint32_t zu, uint32_t fu, uint32_t hd4, uint32_t qb, uint32_t tb,
-                 uint32_t edge_mask, uint32_t& H, uint32_t& E, uint32_t& F, uint32_t& Z, uint32_t& NW) {
-    // zl / zu: "open" values max(H - 6, 0) of the left / up neighbour -- computed ONCE per cell by its
-    // owner (Z below) and shuffled instead of H, so a step costs three VIADDMNMX, not four
+HB_HD void cell2(uint32_t zl, uint32_t el, uint32_t zu, uint32_t fu, uint32_t hd, uint32_t qb, uint32_t tb,
+                 uint32_t edge_keep, uint32_t edge_fill, uint32_t& HU, uint32_t& E, uint32_t& F, uint32_t& Z,
+                 uint32_t& NW) {
     uint32_t e = addmax(el, K_M2, zl);
     uint32_t f = addmax(fu, K_M2, zu);
-    if (PAR == 0) e &= edge_mask; else f &= edge_mask;
+    if (PAR == 0) e = (e & edge_keep) | edge_fill; else f = (f & edge_keep) | edge_fill;
     const uint32_t s6 = minu2(qb & tb, K_6);              // 6 on a match, 0 otherwise
-    const uint32_t dg = add2(hd4, s6);                    // H_diag - 4 + {6, 0}
-    const uint32_t h = max3_relu(dg, e, f);
-    // e >= zl, f >= zu and h >= e hold per half (all >= 0), so plain 32-bit subtraction never borrows
-    // across the halves and can issue on the FMA pipe (IMAD.IADD); the kernel is ALU-pipe bound.  (At a
-    // band-edge lane the masked e / f may be below z: both halves sit on the edge there and the flag of
-    // such a cell is never read, see above.)
-    const uint32_t fa = minu2(e - zl, K_1);
-    const uint32_t fb = minu2(f - zu, K_1);
-    const uint32_t fc = minu2(dg ^ h, K_1);               // H != diag  (dg may be negative: xor, not minus)
-    const uint32_t fd = minu2(h - e, K_1);                // H != E
-    const uint32_t fp = minu2(h, K_1);                    // H > 0
-    const uint32_t s0 = fp & (~fc | fd);
-    const uint32_t s1 = fp & fc;
-    NW = s0 + 2u * s1 + 4u * fa + 8u * fb;
-    H = h; E = e; F = f;
-    Z = addmax_relu(h, K_M6, K_M6);
+    const uint32_t dg = hd + s6;                          // biased diagonal candidate, >= 0
+    const uint32_t h = max3(dg, e, f);                    // biased H (>= 4)
+    const uint32_t hu = h - K_4;                          // unbiased H, >= 0
+    // flags as 0 / 1 per half.  u = H - diag, v = H - E, hu = H are >= 0, so "x > 0" is min(x, 1) and a
+    // conjunction is a three-input min; v > 0 implies H > 0 (H' > E' >= 4).  Source of H:
+    //   0 stop, 1 diag, 2 E, 3 F  =  [H > 0] + [H > 0 and H != diag] + [H != diag and H != E]
+    const uint32_t u = h - dg, v = h - e;
+    const uint32_t fa = minu2(e - zl, K_1);               // E extended
+    const uint32_t fb = minu2(f - zu, K_1);               // F extended
+    const uint32_t p0 = minu2(hu, K_1);
+    const uint32_t p1 = min3u2(u, hu, K_1);
+    const uint32_t p2 = min3u2(u, v, K_1);
+    NW = p0 + p1 + p2 + 4u * fa + 8u * fb;
+    HU = hu; E = e; F = f;
+    Z = addmax(h, K_M6, K_4);
 }
 
 // ---- the warp body ---------------------------------------------------------------------------------
@@ -221,11 +248,12 @@ HB_HD void extend16_warp(W& w, uint32_t group0, const uint32_t* __restrict__ ord
     for (int t = sl; t < WIN; t += HB) { rq[t] = qcode(-HB + t); rt[t] = tcode(-HB + t); }
     w.sync();
 
-    uint32_t H1 = 0, E1 = 0, F1 = 0, Z1 = 0, Hd4 = K_M4;  // Z1 = max(H1 - 6, 0); Hd4 = H two steps ago, minus 4
+    uint32_t HU1 = 0, E1 = K_4, F1 = K_4, Z1 = K_4, Hd = 0;   // HU1 / Hd: unbiased H one / two steps ago; E1, F1, Z1 biased
     uint32_t best = 0;                                    // running maximum of H per half
     int rbest[2] = {0, 0};                                // earliest anti-diagonal that reached it
     const uint32_t m_up = sl == 0 ? 0u : 0xffffffffu;     // band edge: neighbour outside = (H 0, E/F 0)
     const uint32_t m_dn = sl == HB - 1 ? 0u : 0xffffffffu;
+    const uint32_t f_up = ~m_up & K_4, f_dn = ~m_dn & K_4;  // ... i.e. the biased zero
     const uint32_t* pq = rq + (HB - sl);                  // query index of pair-step u:  u - sl + HB
     const uint32_t* pt = rt + sl;                         // target index: u + sl (even), u + sl + 1 (odd)
     for (int sup = 0; sup < n_super; ++sup) {
@@ -244,31 +272,31 @@ HB_HD void extend16_warp(W& w, uint32_t group0, const uint32_t* __restrict__ ord
         uint32_t twA[8], twB[8];                          // the 8 traceback words of this super-step, per pair
         uint32_t fq[4];
         uint32_t tnext = pt[0];
-#pragma unroll 4
+#pragma unroll 8
         for (int u = 0; u < 32; ++u) {
             const uint32_t qb = pq[u];
             const uint32_t te = tnext;
             const uint32_t to = pt[u + 1];
             tnext = to;
-            uint32_t h, e, f, z, nw0, nw1;
+            uint32_t hu, e, f, z, nw0, nw1;
             bool kh, kl;
             // even step (r = 64 sup + 2u): left from lane-1, up/diag own
             {
                 const uint32_t zl = w.shfl_up(Z1, 1, HB), el = w.shfl_up(E1, 1, HB);
-                cell2<0>(zl, el, Z1, F1, Hd4, qb, te, m_up, h, e, f, z, nw0);
-                best = bmax(best, h, &kh, &kl);
+                cell2<0>(zl, el, Z1, F1, Hd, qb, te, m_up, f_up, hu, e, f, z, nw0);
+                best = bmax(best, hu, &kh, &kl);
                 if (!kl) rbest[0] = r0 + 2 * u;
                 if (!kh) rbest[1] = r0 + 2 * u;
-                Hd4 = add2(H1, K_M4); H1 = h; E1 = e; F1 = f; Z1 = z;
+                Hd = HU1; HU1 = hu; E1 = e; F1 = f; Z1 = z;
             }
             // odd step (r + 1): up from lane+1, left/diag own
             {
                 const uint32_t zu = w.shfl_down(Z1, 1, HB), fu = w.shfl_down(F1, 1, HB);
-                cell2<1>(Z1, E1, zu, fu, Hd4, qb, to, m_dn, h, e, f, z, nw1);
-                best = bmax(best, h, &kh, &kl);
+                cell2<1>(Z1, E1, zu, fu, Hd, qb, to, m_dn, f_dn, hu, e, f, z, nw1);
+                best = bmax(best, hu, &kh, &kl);
                 if (!kl) rbest[0] = r0 + 2 * u + 1;
                 if (!kh) rbest[1] = r0 + 2 * u + 1;
-                Hd4 = add2(H1, K_M4); H1 = h; E1 = e; F1 = f; Z1 = z;
+                Hd = HU1; HU1 = hu; E1 = e; F1 = f; Z1 = z;
             }
             fq[u & 3] = nw0 + 16u * nw1;                  // byte 0: two nibbles of pair A, byte 2: pair B
             if ((u & 3) == 3) {
