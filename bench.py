@@ -335,6 +335,29 @@ def main():
             "coarse_boundary": coarse,
             "mbp_per_s": coarse["Mbp_per_s"] if coarse else None,
         }
+        if world == 1 and not args.small:
+            # the metric is reported per TE type.  Helitron / non-LTR candidates take the same
+            # copy search + MSA and their own judges (judge_boundary_v6 / v9); 30 Mbp genome, 3000 candidates each.
+            from hite_b200 import synth
+            per_type = {"tir": float(n_total * args.steps / dev_max)}
+            for kind in ("helitron", "non_ltr"):
+                wk = synth.make_workload(genome_bp=30_000_000, n_contigs=3, n_families=300, cands_per_family=10, copies=(10, 40),
+                                         length=(200, 2000), seed=2, kind=kind)
+                ctx.load_genome(wk.contig_seqs)
+                ctx.build_index(15, 10)
+                fk = np.frombuffer(b"".join(wk.cand_seqs) + b"\0", dtype=np.uint8)
+                ok_ = np.zeros(len(wk.cand_seqs) + 1, dtype=np.uint64)
+                ok_[1:] = np.cumsum([len(c) for c in wk.cand_seqs])
+                ms = []
+                for it in range(2 + 5):
+                    ck, _ = ctx.adjust_raw((fk, ok_), kind, 1)
+                    if it >= 2:
+                        ms.append(ctx.timing()["kernel_ms"])
+                tmk = ctx.timing()
+                per_type[kind] = float(len(wk.cand_seqs) / (np.mean(ms) * 1e-3))
+                per_type[kind + "_stages_ms"] = [round(float(x), 3) for x in tmk["k_ms"][:6]]
+                per_type[kind + "_is_te"] = int((ck["is_te"] != 0).sum())
+            line["per_type_candidates_per_s"] = per_type
         if not args.no_cpu_baseline and world == 1:
             per = min(len(wl.cand_seqs), max(512, 128 * cores))
             dt, _, _ = cpu_reference_run(wl, list(range(per)), cores)

@@ -780,6 +780,12 @@ struct JState {
     uint32_t rowmask[4];
     unsigned short rows[MAX_KEPT + 3];
 };
+struct JState6 {        // Helitron judge (judge_boundary_v6)
+    int go, as, ae, hs, he, Cc;
+};
+__device__ __forceinline__ JState6* jstate6_of(Match* matches, const HbVoteTask& t) {
+    return reinterpret_cast<JState6*>(matches + t.match_off + 2 * ((size_t)t.C + 2));
+}
 __device__ __forceinline__ JState* jstate_of(Match* matches, const HbVoteTask& t) {
     return reinterpret_cast<JState*>(matches + t.match_off + 2 * ((size_t)t.C + 2));
 }
@@ -812,7 +818,8 @@ hb_judge_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 hb_judge_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
-                  uint32_t* __restrict__ planes, Match* __restrict__ matches, HbVoteCall* __restrict__ calls) {
+                  uint32_t* __restrict__ planes, Match* __restrict__ matches, HbVoteCall* __restrict__ calls,
+                  int fl1_copy_num_is_rows) {
     __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * WARPS_PER_CTA + wid;
@@ -824,7 +831,7 @@ hb_judge_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
     unsigned short* rows = s_rows[wid];
     Front F;
     F.Cc = st->Cc;
-    const bool go = front_members(t, call, clean + t.clean_off, planes, st->as, st->ae, 0, rows, lane, F);
+    const bool go = front_members(t, call, clean + t.clean_off, planes, st->as, st->ae, fl1_copy_num_is_rows, rows, lane, F);
     for (int k = lane; k < F.row_num; k += 32) st->rows[k] = rows[k];
     if (lane == 0) {
         st->go = go ? 1 : 0; st->row_num = F.row_num;
@@ -839,7 +846,7 @@ hb_judge_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 hb_judge_c_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, uint32_t* __restrict__ planes,
-                  Match* __restrict__ matches, HbVoteCall* __restrict__ calls) {
+                  Match* __restrict__ matches, HbVoteCall* __restrict__ calls, double thr_many) {
     __shared__ int s_vc[WARPS_PER_CTA][128];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * WARPS_PER_CTA + wid;
@@ -850,7 +857,7 @@ hb_judge_c_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, uint32_t* _
     HbVoteCall call = calls[ti];
     Front F;
     front_load(F, st, planes, t);
-    const bool go = front_boundaries(call, st->as, st->ae, 0.7, s_vc[wid], lane, F);
+    const bool go = front_boundaries(call, st->as, st->ae, thr_many, s_vc[wid], lane, F);
     if (lane == 0) {
         st->go = go ? 1 : 0; st->hs = F.hs; st->he = F.he; st->vl = F.vl; st->vr = F.vr;
         calls[ti] = call;
@@ -955,12 +962,9 @@ hb_judge_d_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
 // ------------------------------------------------------------------------------------------
 // kernel B': judge_boundary_v6 (Helitron, Util.py:9821-10159), one warp per candidate.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-hb_judge_v6_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
-                   uint32_t* __restrict__ planes, Match* __restrict__ matches, int* __restrict__ anchors,
-                   const uint8_t* __restrict__ cands, uint8_t* __restrict__ cons_buf, HbVoteCall* __restrict__ calls) {
-    __shared__ int s_vc[WARPS_PER_CTA][128];
-    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
-    __shared__ unsigned short s_rows2[WARPS_PER_CTA][104];
+hb_judge_v6_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                     Match* __restrict__ matches, int* __restrict__ anchors, const uint8_t* __restrict__ cands,
+                     HbVoteCall* __restrict__ calls) {
     __shared__ int s_cnt[WARPS_PER_CTA][2];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * WARPS_PER_CTA + wid;
@@ -972,9 +976,6 @@ hb_judge_v6_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint
     call.is_te = 0; call.info = 0; call.copy_num = 0; call.align_start = -1; call.align_end = -1;
     call.homo_start = -1; call.homo_end = -1; call.cons_len = 0; call.trim_lead = 0; call.trim_trail = 0;
     call.flags = 0; call.cons_off = (int64_t)t.cons_off;
-    int* vc = s_vc[wid];
-    unsigned short* rows = s_rows[wid];
-    unsigned short* rows2 = s_rows2[wid];
     // ---- 1. anchors of ALL rows, then the mode (:9837-9866) ------------------------------------
     int as = -1, ae = -1;
     if (t.cand_len > 2 && Cc > 0) {
@@ -1013,7 +1014,37 @@ hb_judge_v6_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint
         }
     }
     call.align_start = as; call.align_end = ae;
-    if (as < 0 || ae < 0) { call.info = 1; if (lane == 0) calls[ti] = call; return; }     // :9870-9873
+    const bool go = !(as < 0 || ae < 0);
+    if (!go) call.info = 1;                                                                 // :9870-9873
+    __syncwarp();                          // the match scratch is dead from here on; the state sits behind it
+    if (lane == 0) {
+        JState6* st = jstate6_of(matches, t);
+        st->go = go ? 1 : 0; st->as = as; st->ae = ae; st->Cc = Cc;
+        calls[ti] = call;
+    }
+}
+
+// phase B: start / end member sets, then the end and the start boundary (search_boundary_homo_v4)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_v6_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                     uint32_t* __restrict__ planes, Match* __restrict__ matches, HbVoteCall* __restrict__ calls) {
+    __shared__ int s_vc[WARPS_PER_CTA][128];
+    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    __shared__ unsigned short s_rows2[WARPS_PER_CTA][104];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    JState6* st = jstate6_of(matches, t);
+    if (!st->go) return;
+    HbVoteCall call = calls[ti];
+    const int R = t.R, C = t.C, Cc = st->Cc, as = st->as, ae = st->ae;
+    const uint8_t* m = clean + t.clean_off;
+    int* vc = s_vc[wid];
+    unsigned short* rows = s_rows[wid];
+    unsigned short* rows2 = s_rows2[wid];
+    __syncwarp();
+    if (lane == 0) st->go = 0;             // every early return below is a final verdict
     // ---- 2. start / end member sets (:9884-9936): the loop stops for both once either exceeds 100
     int ns = 0, ne = 0;
     {
@@ -1060,6 +1091,27 @@ hb_judge_v6_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint
         search_boundary_v4(P, ns / 2, as, Cc, true, thr, ithr, othr, 20, 10, vc, lane, &hs);
         call.homo_start = hs;
     }
+    if (lane == 0) { st->go = 1; st->hs = hs; st->he = he; calls[ti] = call; }
+}
+
+// phase C: full-length members, consensus, ATC ... CTRRT motif
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+hb_judge_v6_c_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                     uint32_t* __restrict__ planes, Match* __restrict__ matches, uint8_t* __restrict__ cons_buf,
+                     HbVoteCall* __restrict__ calls) {
+    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    if (ti >= n_tasks) return;
+    const HbVoteTask t = tasks[ti];
+    const JState6* st = jstate6_of(matches, t);
+    if (!st->go) return;
+    HbVoteCall call = calls[ti];
+    const int R = t.R, C = t.C, Cc = st->Cc, hs = st->hs, he = st->he;
+    const uint8_t* m = clean + t.clean_off;
+    unsigned short* rows = s_rows[wid];
+    Planes P;
+    uint32_t* pw = planes + t.plane_off;
     // ---- 3. full-length members (+-1 around the homology boundaries, :10012-10038) -------------
     int row_num;
     {
@@ -1227,25 +1279,25 @@ __device__ __noinline__ bool nonltr_row(const uint8_t* __restrict__ row, int Cc,
 // ------------------------------------------------------------------------------------------
 // kernel B'': judge_boundary_v9 (non-LTR, Util.py:9483-9720), one warp per candidate.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-hb_judge_v9_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
-                   uint32_t* __restrict__ planes, Match* __restrict__ matches, const uint8_t* __restrict__ cands,
-                   uint8_t* __restrict__ cons_buf, HbVoteCall* __restrict__ calls) {
-    __shared__ int s_vc[WARPS_PER_CTA][128];
+hb_judge_v9_tail_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
+                        uint32_t* __restrict__ planes, Match* __restrict__ matches, uint8_t* __restrict__ cons_buf,
+                        HbVoteCall* __restrict__ calls) {
+    // phases a, b, c are the TIR judge's kernels (thr_many 0.8, 'fl1' copy number = rows, Util.py:9490-9597)
     __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
-    __shared__ int s_cnt[WARPS_PER_CTA][2];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * WARPS_PER_CTA + wid;
     if (ti >= n_tasks) return;
     const HbVoteTask t = tasks[ti];
+    const JState* st = jstate_of(matches, t);
+    if (!st->go) return;
     HbVoteCall call = calls[ti];
     const int R = t.R, C = t.C;
     const uint8_t* m = clean + t.clean_off;
     unsigned short* rows = s_rows[wid];
     Front F;
-    if (!judge_front_v3(t, call, m, planes, matches, cands, 0.8, 1, s_vc[wid], rows, s_cnt[wid], lane, F)) {
-        if (lane == 0) calls[ti] = call;
-        return;
-    }
+    front_load(F, st, planes, t);
+    for (int k = lane; k < F.row_num; k += 32) rows[k] = st->rows[k];
+    __syncwarp();
     const int Cc = F.Cc, row_num = F.row_num, he = F.he;
     int hs = F.hs;
     // ---- per-copy 3' end + TSD (:9604-9664), all R rows, one row per lane -----------------------
@@ -1308,17 +1360,23 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (te_type == 0) {
         hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);
-        hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls);
-        hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls);
+        hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 0);
+        hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls, 0.7);
         hb_judge_d_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
                                                                    d_calls);
-    } else if (te_type == 1)
-        hb_judge_v6_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
-                                                                    d_anchors, d_cands, d_cons, d_calls);
-    else if (te_type == 2)
-        hb_judge_v9_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
-                                                                    d_cands, d_cons, d_calls);
-    else
+    } else if (te_type == 1) {
+        hb_judge_v6_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_anchors, d_cands,
+                                                                      d_calls);
+        hb_judge_v6_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls);
+        hb_judge_v6_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
+                                                                      d_calls);
+    } else if (te_type == 2) {
+        hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);
+        hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 1);
+        hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls, 0.8);
+        hb_judge_v9_tail_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
+                                                                         d_calls);
+    } else
         return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
