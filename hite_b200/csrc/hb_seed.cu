@@ -108,12 +108,16 @@ __global__ void cand_first_cluster_kernel(const uint64_t* __restrict__ hits, con
     (void)n_cand;
 }
 
+constexpr uint32_t RANK_SMEM_KEYS = 768;     // valid clusters per candidate ranked in shared memory (12 B each, 4 warps)
+
 // S5/S6: rank the clusters of a candidate (n desc, rel asc, dmin asc), keep the best max_loci.
 // One warp per candidate.
 __global__ void __launch_bounds__(128)
 rank_select_kernel(const uint64_t* __restrict__ hits, uint64_t n_hits, const uint32_t* __restrict__ cl_start,
                    uint32_t n_cl, const uint32_t* __restrict__ cand_first, uint32_t n_cand, int max_loci,
                    HbLocus* __restrict__ loci, uint32_t* __restrict__ n_loci) {
+    __shared__ uint64_t s_keys[4][RANK_SMEM_KEYS];
+    __shared__ uint32_t s_kcl[4][RANK_SMEM_KEYS];
     const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= n_cand) return;
@@ -134,6 +138,52 @@ rank_select_kernel(const uint64_t* __restrict__ hits, uint64_t n_hits, const uin
             const uint64_t e = (x + 1 < n_cl) ? cl_start[x + 1] : n_hits;
             return (uint32_t)(e - cl_start[x]);
         };
+        // Pass 1: the valid clusters (>= HB_MIN_SEEDS seeds) as sortable keys in shared memory -- smaller key =
+        // better cluster: (seeds desc, rel asc, first diagonal asc); keys are distinct.  A candidate with a
+        // low-complexity stretch (polyA tail) has thousands of one-hit clusters but few valid ones, so the
+        // ranking below is O(valid^2 / 32) on shared memory instead of O(clusters^2 / 32) on global memory.
+        uint64_t* keys = s_keys[threadIdx.x >> 5];
+        uint32_t* kcl = s_kcl[threadIdx.x >> 5];
+        uint32_t nv = 0;
+        for (uint32_t x0 = first; x0 < end; x0 += 32) {
+            const uint32_t x = x0 + lane;
+            bool valid = false;
+            uint64_t key = 0;
+            if (x < end) {
+                const uint32_t nx = cl_n(x);
+                valid = nx >= HB_MIN_SEEDS;
+                const uint64_t k0 = hits[cl_start[x]];
+                key = ((uint64_t)(0xFFFFFFFFu - nx) << 34) | (((k0 >> 46) & 1ull) << 33) | ((k0 >> 13) & 0x1FFFFFFFFull);
+            }
+            const uint32_t bal = __ballot_sync(HB_FULL, valid);
+            const uint32_t pos = nv + __popc(bal & ((1u << lane) - 1u));
+            if (valid && pos < RANK_SMEM_KEYS) { keys[pos] = key; kcl[pos] = x; }
+            nv += __popc(bal);
+        }
+        __syncwarp();
+        nvalid = nv;
+        if (nv <= RANK_SMEM_KEYS) {
+            for (uint32_t v0 = 0; v0 < nv; v0 += 32) {
+                const uint32_t v = v0 + lane;
+                if (v >= nv) continue;
+                const uint64_t kx = keys[v];
+                uint32_t rank = 0;
+                for (uint32_t y = 0; y < nv; ++y) rank += keys[y] < kx ? 1u : 0u;
+                if (rank < (uint32_t)max_loci) {
+                    const uint32_t x = kcl[v];
+                    const uint64_t e = (x + 1 < n_cl) ? cl_start[x + 1] : n_hits;
+                    const int64_t dmin = (int64_t)(kx & 0x1FFFFFFFFull);
+                    const int64_t dmax = (int64_t)((hits[e - 1] >> 13) & 0x1FFFFFFFFull);
+                    HbLocus L;
+                    L.cand = c; L.rel = (uint32_t)((kx >> 33) & 1ull); L.nseeds = 0xFFFFFFFFu - (uint32_t)(kx >> 34);
+                    L.rank = rank; L.dmin = dmin; L.dmax = dmax;
+                    L.j0 = ((dmin + dmax) >> 1) - HB_DIAG_OFF;
+                    loci[(size_t)c * max_loci + rank] = L;
+                }
+            }
+        } else {
+        // more valid clusters than the shared-memory buffer holds: rank against global memory
+        nvalid = 0;
         for (uint32_t x0 = first; x0 < end; x0 += 32) {
             const uint32_t x = x0 + lane;
             bool valid = false;
@@ -167,6 +217,7 @@ rank_select_kernel(const uint64_t* __restrict__ hits, uint64_t n_hits, const uin
             nvalid += __popc(__ballot_sync(HB_FULL, valid));
         }
     }
+        }
     if (lane == 0) n_loci[c] = min(nvalid, (uint32_t)max_loci);
 }
 

@@ -86,11 +86,14 @@ def test_stress_shapes_bit_exact(ctx):
                              length=(300, 700), seed=21, indel=0.002)
     wl2 = synth.make_workload(genome_bp=1_500_000, n_contigs=1, n_families=4, cands_per_family=2, copies=(6, 12),
                               length=(4000, 9000), seed=22, indel=0.004, sub=(0.0, 0.05))
-    contigs = [c.copy() for c in wl.contig_seqs] + [c.copy() for c in wl2.contig_seqs]
+    # > 768 valid seed clusters for one candidate: the cluster ranking leaves its shared-memory fast path
+    wl3 = synth.make_workload(genome_bp=1_500_000, n_contigs=1, n_families=1, cands_per_family=2, copies=(900, 950),
+                              length=(250, 300), seed=23, indel=0.002, sub=(0.0, 0.03))
+    contigs = [c.copy() for c in wl.contig_seqs] + [c.copy() for c in wl2.contig_seqs] + [c.copy() for c in wl3.contig_seqs]
     contigs[0][1000:1400] = ord("N")
     contigs[1][5000:5003] = ord("n")
     contigs[2] = np.frombuffer(contigs[2].tobytes().lower(), dtype=np.uint8).copy()
-    cands = list(wl.cand_seqs) + list(wl2.cand_seqs)
+    cands = list(wl.cand_seqs) + list(wl2.cand_seqs) + list(wl3.cand_seqs)
     G = oracle.Genome(contigs)
     ctx.load_genome(contigs)
     ctx.build_index(15, 10)
@@ -112,4 +115,4 @@ def test_stress_shapes_bit_exact(ctx):
             for k in ("is_te", "info", "cons", "copy_num"):
                 assert res[ci][k] == exp[k], (ci, k)
     assert n_big >= 1                       # the 100-longest rule was exercised
-    assert sum(r["is_te"] for r in res[len(wl.cand_seqs):]) >= 1      # long elements come through
+    assert sum(r["is_te"] for r in res[len(wl.cand_seqs):len(wl.cand_seqs) + len(wl2.cand_seqs)]) >= 1      # long elements come through
