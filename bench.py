@@ -325,7 +325,9 @@ def main():
                          "note": "integer-ALU-bound DP, not HBM-bound: %.2f GCUPS, ALU pipe %s %% of peak (ncu, profiles/); "
                                  "algorithmic bytes/pair=(2L+64)*3/8+4L+56"
                                  % (dp_cells / ext_s / 1e9 if ext_s else 0, "%.1f" % alu_pct if alu_pct else "n/a"),
-                         "kernel_ms": ext_s * 1e3, "pairs": int(len(copies))},
+                         "kernel_ms": ext_s * 1e3, "pairs": int(len(copies)),
+                         "binding_resource": {"name": "integer ALU pipe (sm__inst_executed_pipe_alu)", "pct_of_peak": alu_pct,
+                                              "source": "ncu --set full, profiles/r1_g_full_extend16_C2.md"}},
             "stages_ms": {k: float(v / args.steps) for k, v in zip(
                 ("sketch_cands", "seed_sort_cluster", "extend", "copy_rules_msa", "clean_judge", "compact"), stage[:6])},
             "setup": {"genome_load_ms": t_load["kernel_ms"] + t_load["h2d_ms"], "index_build_ms": t_idx["kernel_ms"],
