@@ -8,6 +8,8 @@ Python host side of ``libhite_b200.so`` (hand-written sm_100a CUDA kernels behin
 * ``hite_b200.boundary.is_TE_from_align_file``        (reference module/Util.py:10407)
 * ``hite_b200.coarse.determine_repeat_boundary_v5``   (reference module/Util.py:4637)
 * ``hite_b200.coarse.flanking_seq``                   (reference module/Util.py:4614)
+* ``hite_b200.tir_prefilter.search_confident_tir_v4`` / ``get_short_tir_contigs`` / ``search_confident_tir_batch``
+  (reference module/Util.py:7734, :7297, :7358 -- the step right before the path)
 
 There is no CPU fallback: without the built extension and a CUDA device every entry point raises.
 """

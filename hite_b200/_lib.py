@@ -44,6 +44,7 @@ COPY_DTYPE = np.dtype([("cand", "<u4"), ("rank", "<i4"), ("rel", "<i4"), ("nseed
 assert COPY_DTYPE.itemsize == 88
 
 
+TSD_DTYPE = np.dtype([("k", "<i4"), ("start", "<i4"), ("end", "<i4"), ("dist", "<i4"), ("idx", "<i4"), ("short_class", "<i4")])
 HSP_DTYPE = np.dtype([("subj", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("ss", "<i4"), ("se", "<i4")])
 SEG_DTYPE = np.dtype([("chr", "<i4"), ("pad", "<i4"), ("start", "<i8")])
 INTERVAL_DTYPE = np.dtype([("chr", "<i4"), ("qseg", "<i4"), ("start", "<i8"), ("end", "<i8")])
@@ -134,6 +135,7 @@ def load():
                                     C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_coarse_boundary.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
     lib.hb_last_hsps.argtypes = [vp, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.hb_tsd_candidates.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp]
     _LIB = lib
     return lib
 
@@ -340,6 +342,24 @@ class Context:
                 cap = int(n.value)
                 continue
             self._check(rc, "hb_coarse_boundary")
+
+    def tsd_candidates(self, seqs, raw_starts, raw_ends, tsd_search_distance, plant):
+        """TSD-bounded variants of flanked candidates (reference ``search_confident_tir_v4`` + the classes of
+        ``get_short_tir_contigs``; module/Util.py:7734, :7297) -> (records [n, 100] TSD_DTYPE, counts [n])."""
+        cb = [c if isinstance(c, (bytes, bytearray)) else c.encode("ascii") for c in seqs]
+        n = len(cb)
+        out = np.zeros((n, 100), dtype=TSD_DTYPE)
+        cnt = np.zeros(n, dtype=np.uint32)
+        if n == 0:
+            return out, cnt
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(c) for c in cb])
+        flat = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
+        rs = np.ascontiguousarray(raw_starts, dtype=np.int32)
+        re_ = np.ascontiguousarray(raw_ends, dtype=np.int32)
+        self._check(self._lib.hb_tsd_candidates(self._h, n, _ptr(flat), _ptr(off), _ptr(rs), _ptr(re_), int(tsd_search_distance),
+                                                int(plant), _ptr(out), _ptr(cnt)), "hb_tsd_candidates")
+        return out, cnt
 
     def last_hsps(self):
         n, ns = C.c_uint64(0), C.c_uint32(0)

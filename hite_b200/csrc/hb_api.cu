@@ -163,3 +163,55 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
     tm.launches = 2;
     return HB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// TSD-bounded variant generation (hb_tsd.cu)
+#include "hb_tsd.cuh"
+extern "C" int hb_tsd_candidates(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off,
+                                 const int32_t* raw_start1, const int32_t* raw_end1, int32_t d, int32_t plant,
+                                 hb_tsd_rec* out, uint32_t* n_out) {
+    if (!ctx || !seq_ascii || !seq_off || !raw_start1 || !raw_end1 || !out || !n_out)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_tsd_candidates: null argument");
+    if (d < 1 || d > 128) return hb_fail_msg(ctx, HB_EINVAL, "hb_tsd_candidates: tsd_search_distance must be in [1, 128]");
+    if (n == 0) return HB_OK;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = seq_off[i + 1] - seq_off[i];
+        if (len < 1 || len >= (1u << 20)) return hb_fail_msg(ctx, HB_EINVAL, "hb_tsd_candidates: candidate " + std::to_string(i) + " length must be in [1, 2^20)");
+        if (raw_start1[i] < 1 || raw_end1[i] < 1 || (uint64_t)raw_start1[i] > len || (uint64_t)raw_end1[i] > len)
+            return hb_fail_msg(ctx, HB_EINVAL, "hb_tsd_candidates: candidate " + std::to_string(i) + " boundary outside the sequence");
+    }
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    const uint64_t bytes = seq_off[n] - seq_off[0];
+    HB_CUDA_OK(ctx->buf("t.seq").ensure(bytes + 16));
+    HB_CUDA_OK(ctx->buf("t.off").ensure(sizeof(uint64_t) * (n + 1)));
+    HB_CUDA_OK(ctx->buf("t.rs").ensure(sizeof(int32_t) * n));
+    HB_CUDA_OK(ctx->buf("t.re").ensure(sizeof(int32_t) * n));
+    HB_CUDA_OK(ctx->buf("t.out").ensure(sizeof(hb_tsd_rec) * 100 * (size_t)n));
+    HB_CUDA_OK(ctx->buf("t.n").ensure(sizeof(uint32_t) * n));
+    std::vector<uint64_t> off(n + 1);
+    for (uint32_t i = 0; i <= n; ++i) off[i] = seq_off[i] - seq_off[0];
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("t.seq").p, seq_ascii + seq_off[0], bytes, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("t.off").p, off.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("t.rs").p, raw_start1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("t.re").p, raw_end1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    HB_CUDA_OK(hb_tsd_launch(ctx->buf("t.seq").as<uint8_t>(), ctx->buf("t.off").as<uint64_t>(), ctx->buf("t.rs").as<int32_t>(),
+                             ctx->buf("t.re").as<int32_t>(), n, d, plant, ctx->buf("t.out").as<hb_tsd_rec>(),
+                             ctx->buf("t.n").as<uint32_t>(), s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    HB_CUDA_OK(cudaMemcpyAsync(n_out, ctx->buf("t.n").p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaMemcpyAsync(out, ctx->buf("t.out").p, sizeof(hb_tsd_rec) * 100 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->timing.k_ms[0] = ctx->timing.kernel_ms;
+    ctx->timing.h2d_bytes = bytes + sizeof(uint64_t) * (n + 1) + 2 * sizeof(int32_t) * (uint64_t)n;
+    ctx->timing.d2h_bytes = (sizeof(hb_tsd_rec) * 100 + sizeof(uint32_t)) * (uint64_t)n;
+    ctx->timing.launches = 1;
+    return HB_OK;
+}

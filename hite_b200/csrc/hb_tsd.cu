@@ -1,0 +1,188 @@
+// hite_b200 -- TSD-bounded variant generation, the step right before the boundary-adjustment path in
+// HiTE's TIR module.  One warp per flanked candidate.
+//
+// Replaces (reference module/Util.py):
+//   search_confident_tir_v4   :7734-7845   k-mer dictionary of the +-d window around the left boundary, matched
+//                                          against the k-mers around the right boundary, k in {2,3,4,5,6,8,9,10,11}
+//   get_short_tir_contigs     :7297-7334   (classification of each emitted variant)
+// Bit-identical to oracle/hbo_tsd.c, which is pinned on outputs of the imported reference
+// (tests/golden/tsd_v4.json.gz).  Like the oracle, equal-distance entries are ordered by
+// (distance, start, end, k): the reference's own order among them is Python set iteration order.
+#include "hb_common.cuh"
+#include "hb_tsd.cuh"
+
+namespace {
+
+__constant__ int c_ks[9] = {2, 3, 4, 5, 6, 8, 9, 10, 11};   // TIR_TSDs, Util.py:7760
+
+struct Win {             // 11-byte look-ahead of every window position: bytes 0-7 in lo, 8-10 in hi
+    unsigned long long* lo;
+    uint32_t* hi;
+};
+__device__ __forceinline__ bool kmer_eq(const Win& a, int i, const Win& b, int j, unsigned long long mlo, uint32_t mhi) {
+    return ((a.lo[i] ^ b.lo[j]) & mlo) == 0 && ((a.hi[i] ^ b.hi[j]) & mhi) == 0;
+}
+__device__ __forceinline__ uint8_t rc_base(uint8_t c) {     // getReverseSequence, Util.py:1635
+    return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'N';
+}
+__device__ __forceinline__ bool eq_lit(const uint8_t* s, const char* lit, int n) {
+    for (int i = 0; i < n; ++i) if (s[i] != (uint8_t)lit[i]) return false;
+    return true;
+}
+// get_short_tir_contigs (Util.py:7297-7334): 0 none, 1 hAT, 2 Mutator, 3 CACTA, 4 CCC
+__device__ int short_tir_class(const uint8_t* tir, int len, int tsd_len, int plant) {
+    if (len < 5) return 0;
+    bool eq5 = true, eq3 = true;
+    for (int i = 0; i < 5; ++i) if (tir[i] != rc_base(tir[len - 1 - i])) eq5 = false;
+    for (int i = 0; i < 3; ++i) if (tir[i] != rc_base(tir[len - 1 - i])) eq3 = false;
+    if (eq5) {
+        if (tsd_len == 8 && len < 4000) return 1;
+        if (tsd_len >= 9 && tsd_len <= 11) return 2;
+        if (plant == 1 && tsd_len == 3 && (eq_lit(tir, "CACTA", 5) || eq_lit(tir, "CACTG", 5))) return 3;
+        return 0;
+    }
+    if (eq3 && eq_lit(tir, "CCC", 3)) return 4;
+    return 0;
+}
+
+// key of a (dist, start, end, k) tuple: the canonical order is the numeric order of the key
+__device__ __forceinline__ unsigned long long tup_key(int dist, int start, int end, int k) {
+    return ((unsigned long long)dist << 44) | ((unsigned long long)start << 24) | ((unsigned long long)end << 4) | (unsigned long long)k;
+}
+
+__global__ void __launch_bounds__(32)
+tsd_kernel(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_off, const int32_t* __restrict__ raw_start1,
+           const int32_t* __restrict__ raw_end1, uint32_t n_cand, int d, int plant, int wcap, hb_tsd_rec* __restrict__ out,
+           uint32_t* __restrict__ n_out) {
+    extern __shared__ unsigned long long smem[];
+    const uint32_t c = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (c >= n_cand) return;
+    // shared layout: Llo[wcap] Rlo[wcap] keys[9 wcap] sorted[9 wcap] | Lhi[wcap] Rhi[wcap] | counter
+    Win L, R;
+    L.lo = smem; R.lo = smem + wcap;
+    unsigned long long* keys = smem + 2 * wcap;
+    unsigned long long* sorted = keys + 9 * wcap;
+    L.hi = reinterpret_cast<uint32_t*>(sorted + 9 * wcap); R.hi = L.hi + wcap;
+    int* counter = reinterpret_cast<int*>(R.hi + wcap);
+    const uint8_t* seq = seqs + seq_off[c];
+    const int n = (int)(seq_off[c + 1] - seq_off[c]);
+    const int rs = raw_start1[c] - 1, re = raw_end1[c] - 1;                     // :7736-7737
+    int ls = max(0, rs - d), le = min(n, rs + d + 1);                            // :7743-7747
+    int rts = max(0, re - d), rte = min(n, re + d + 1);                          // :7750-7754
+    ls = min(ls, n); rts = min(rts, n); le = max(le, ls); rte = max(rte, rts);
+    const int nl = le - ls, nr = rte - rts;
+    for (int i = lane; i < nl; i += 32) {
+        unsigned long long lo = 0; uint32_t hi = 0;
+        for (int z = 0; z < 11 && ls + i + z < le; ++z) {
+            const unsigned long long b = seq[ls + i + z];
+            if (z < 8) lo |= b << (8 * z); else hi |= (uint32_t)b << (8 * (z - 8));
+        }
+        L.lo[i] = lo; L.hi[i] = hi;
+    }
+    for (int j = lane; j < nr; j += 32) {
+        unsigned long long lo = 0; uint32_t hi = 0;
+        for (int z = 0; z < 11 && rts + j + z < rte; ++z) {
+            const unsigned long long b = seq[rts + j + z];
+            if (z < 8) lo |= b << (8 * z); else hi |= (uint32_t)b << (8 * (z - 8));
+        }
+        R.lo[j] = lo; R.hi[j] = hi;
+    }
+    if (lane == 0) *counter = 0;
+    __syncwarp();
+    // ---- tuples: every right k-mer occurrence that sets a new "closest to the raw end" for its string ----
+    for (int ki = 0; ki < 9; ++ki) {
+        const int k = c_ks[ki];
+        const unsigned long long mlo = k >= 8 ? ~0ull : ((1ull << (8 * k)) - 1ull);
+        const uint32_t mhi = k <= 8 ? 0u : ((1u << (8 * (k - 8))) - 1u);
+        for (int j = lane; j + k <= nr; j += 32) {
+            const int pos = rts + j - 1;                                        // :7783
+            if (pos < 0 || pos > n - 1) continue;
+            int best_l = -1, best_ld = 0;                                       // left_pos: closest to rs, first on ties
+            for (int i = 0; i + k <= nl; ++i) {
+                const int lp = ls + i + k;
+                if (lp > n - 1) break;
+                if (!kmer_eq(L, i, R, j, mlo, mhi)) continue;
+                const int dd = abs(lp - rs);
+                if (best_l < 0 || dd < best_ld) { best_l = lp; best_ld = dd; }
+            }
+            if (best_l < 0) continue;
+            const int my = abs(pos - re);
+            bool is_best = true;                                                // :7788-7796
+            for (int j2 = 0; j2 < j && is_best; ++j2) {
+                const int p2 = rts + j2 - 1;
+                if (p2 < 0) continue;
+                if (kmer_eq(R, j2, R, j, mlo, mhi) && abs(p2 - re) <= my) is_best = false;
+            }
+            if (!is_best) continue;
+            const uint8_t* km = seq + rts + j;
+            bool ok;                                                            // :7802-7805
+            if (k != 2 && k != 4) ok = true;
+            else if (k == 4) ok = eq_lit(km, "TTAA", 4);
+            else {
+                ok = eq_lit(km, "TA", 2);
+                if (!ok && plant == 0)
+                    ok = best_l + 3 <= n && eq_lit(seq + best_l, "CCC", 3) && pos >= 2 && pos + 1 <= n && eq_lit(seq + pos - 2, "GGG", 3);
+            }
+            if (!ok) continue;
+            const int slot = atomicAdd(counter, 1);
+            keys[slot] = tup_key(abs(best_l - rs) + my, best_l, pos, k);
+        }
+    }
+    __syncwarp();
+    const int nt = *counter;
+    // ---- canonical order: rank by counting (keys are distinct) ------------------------------------------------
+    for (int t = lane; t < nt; t += 32) {
+        const unsigned long long kt = keys[t];
+        int rank = 0;
+        for (int u = 0; u < nt; ++u) rank += keys[u] < kt ? 1 : 0;
+        sorted[rank] = kt;
+    }
+    __syncwarp();
+    // ---- filters (:7811-7833) and the 100-record cut (:7836-7844), in sorted order ----------------------------
+    int emitted = 0;
+    for (int t0 = 0; t0 < nt && emitted < 100; t0 += 32) {
+        const int t = t0 + lane;
+        bool keep = false;
+        int k = 0, start = 0, end = 0, dist = 0;
+        if (t < nt) {
+            const unsigned long long kt = sorted[t];
+            k = (int)(kt & 15ull); end = (int)((kt >> 4) & 0xFFFFFull); start = (int)((kt >> 24) & 0xFFFFFull); dist = (int)(kt >> 44);
+            const uint8_t* km = seq + end + 1;
+            bool has_nn = false;
+            for (int z = 0; z + 1 < k; ++z) if (km[z] == 'N' && km[z + 1] == 'N') has_nn = true;
+            const int len = end >= start ? end - start + 1 : 0;
+            keep = !has_nn && len >= 100;
+            if (keep) {
+                const uint8_t* tir = seq + start;
+                if (tir[0] == 'T' && tir[1] == 'G' && tir[len - 2] == 'C' && tir[len - 1] == 'A') keep = false;
+                if (eq_lit(tir, "TATATATA", 8) || eq_lit(tir, "ATATATAT", 8)) keep = false;
+            }
+        }
+        const uint32_t bal = __ballot_sync(HB_FULL, keep);
+        const int slot = emitted + __popc(bal & ((1u << lane) - 1u));
+        if (keep && slot < 100) {
+            hb_tsd_rec r;
+            r.k = k; r.start = start; r.end = end; r.dist = dist; r.idx = t;
+            r.short_class = short_tir_class(seq + start, end - start + 1, k, plant);
+            out[(size_t)c * 100 + slot] = r;
+        }
+        emitted += __popc(bal);
+    }
+    if (lane == 0) n_out[c] = (uint32_t)min(emitted, 100);
+}
+
+}  // namespace
+
+size_t hb_tsd_smem_bytes(int d) {
+    const size_t wcap = (size_t)(2 * d + 1 + 3) & ~(size_t)3;
+    return wcap * (2 + 18) * sizeof(unsigned long long) + wcap * 2 * sizeof(uint32_t) + 16;
+}
+
+cudaError_t hb_tsd_launch(const uint8_t* seqs, const uint64_t* seq_off, const int32_t* raw_start1, const int32_t* raw_end1,
+                          uint32_t n_cand, int d, int plant, hb_tsd_rec* out, uint32_t* n_out, cudaStream_t s) {
+    if (n_cand == 0) return cudaSuccess;
+    const int wcap = (2 * d + 1 + 3) & ~3;
+    tsd_kernel<<<n_cand, 32, hb_tsd_smem_bytes(d), s>>>(seqs, seq_off, raw_start1, raw_end1, n_cand, d, plant, wcap, out, n_out);
+    return cudaGetLastError();
+}

@@ -203,6 +203,23 @@ int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, 
 int hb_last_hsps(hb_ctx* ctx, hb_hsp* out, uint64_t cap, uint64_t* n, uint64_t* q_off, hb_segment* segs,
                  uint32_t seg_cap, uint32_t* n_seg);
 
+/*
+ * hb_tsd_candidates -- TSD-bounded variants of n flanked candidates, the step right before the boundary-adjustment
+ * path in the TIR module: search_confident_tir_v4 (module/Util.py:7734-7845, driven per candidate by
+ * search_confident_tir_batch :7358-7376 with raw_tir_start = flanking_len + 1, raw_tir_end = len - flanking_len,
+ * tsd_search_distance = flanking_len) plus the classification of get_short_tir_contigs (:7297-7334).
+ * Candidate i is seq_ascii[seq_off[i] .. seq_off[i+1]) (upper case, < 2^20 bytes); raw_start1 / raw_end1 are the
+ * 1-based boundaries the reference receives; 1 <= tsd_search_distance <= 128.  out holds 100 records per candidate
+ * (the reference's max_top_num), n_out[i] of them valid, in the reference's output order: variant = seq[start .. end]
+ * (0-based, inclusive), TSD = the k bytes after `end`, distance = |start - (raw_start1-1)| + |end - (raw_end1-1)|,
+ * idx = position in the distance-sorted candidate list (the '-C_<idx>-' of the reference's record name; among equal
+ * distances the reference's order is Python set order, here (start, end, k)), short_class = 0 none / 1 hAT /
+ * 2 Mutator / 3 CACTA / 4 CCC (which records get_short_tir_contigs keeps).  One warp per candidate.
+ */
+typedef struct { int32_t k, start, end, dist, idx, short_class; } hb_tsd_rec;
+int hb_tsd_candidates(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off, const int32_t* raw_start1,
+                      const int32_t* raw_end1, int32_t tsd_search_distance, int32_t plant, hb_tsd_rec* out, uint32_t* n_out);
+
 /* parity/debug getters: the sorted minimizer index (hash<<33 | pos<<1 | strand) and the raw
  * (pre-clean) MSA of one candidate of the last hb_adjust as ASCII */
 int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap);

@@ -87,7 +87,15 @@ int hbo_run_batch(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int 
                   const uint64_t *coff, uint32_t n_cand, int occ_cap, int max_loci, int flank, int max_rows, int plant,
                   int threads, hbo_result *out);
 
+/* ---- TSD-bounded variant generation (hbo_tsd.c): search_confident_tir_v4 + get_short_tir_contigs ---- */
+typedef struct { int32_t k, start, end, dist, idx, idx_lo, idx_hi, short_class; } hbo_tsd_rec;
+int hbo_short_tir_class(const char *tir, int len, int tsd_len, int plant);
+int hbo_search_confident_tir_v4(const char *seq, int n, int raw_start1, int raw_end1, int d, int plant,
+                                hbo_tsd_rec *out, int cap);
+
+
 #ifdef __cplusplus
 }
 #endif
+
 #endif

@@ -179,6 +179,21 @@ class HboCopy(C.Structure):
                 ("start1", C.c_int64), ("end1", C.c_int64), ("keep", C.c_int32), ("ext_len", C.c_int32)]
 
 
+class HboTsdRec(C.Structure):
+    _fields_ = [("k", C.c_int32), ("start", C.c_int32), ("end", C.c_int32), ("dist", C.c_int32), ("idx", C.c_int32),
+                ("idx_lo", C.c_int32), ("idx_hi", C.c_int32), ("short_class", C.c_int32)]
+
+
+def search_confident_tir_v4(seq, raw_start1, raw_end1, d, plant):
+    """C restatement of search_confident_tir_v4 (+ get_short_tir_contigs class) -> list of dicts in output order."""
+    L = lib()
+    sb = seq if isinstance(seq, (bytes, bytearray)) else seq.encode()
+    out = (HboTsdRec * 100)()
+    L.hbo_search_confident_tir_v4.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = L.hbo_search_confident_tir_v4(sb, len(sb), int(raw_start1), int(raw_end1), int(d), int(plant), out, 100)
+    return [{f: getattr(out[i], f) for f, _ in HboTsdRec._fields_} for i in range(n)]
+
+
 class HboLocus(C.Structure):
     _fields_ = [("cand", C.c_uint32), ("rel", C.c_uint32), ("nseeds", C.c_uint32), ("rank", C.c_uint32),
                 ("dmin", C.c_int64), ("dmax", C.c_int64), ("j0", C.c_int64)]

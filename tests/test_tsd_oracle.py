@@ -1,0 +1,94 @@
+"""Oracle (oracle/hbo_tsd.c) vs the reference's own search_confident_tir_v4 / get_short_tir_contigs outputs
+(tests/golden/tsd_v4.json.gz, made by tests/golden/make_golden_tsd.py from the imported reference).
+
+The reference orders equal-distance entries by Python set iteration (hash-seed dependent), so records are matched as
+multisets of (tsd, distance, length, crc32(sequence), short flag); the reference's index i must lie in the tie range the
+oracle reports for the record; and only at a tie straddling the 100-record cut may the two selections differ."""
+import collections
+import gzip
+import json
+import os
+import zlib
+
+import pytest
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def golden_tsd():
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "tsd_v4.json.gz")) as f:
+        return json.loads(f.read())
+
+
+def expand(case, recs):
+    """oracle records -> comparable tuples + index ranges"""
+    seq = case["seq"]
+    out = []
+    for r in recs:
+        s = seq[r["start"]:r["end"] + 1]
+        kmer = seq[r["end"] + 1:r["end"] + 1 + r["k"]]           # the right TSD copy starts right after the element
+        out.append(((kmer, r["dist"], len(s), zlib.crc32(s.encode()) & 0xFFFFFFFF, 1 if r["short_class"] else 0),
+                    (r["idx_lo"], r["idx_hi"])))
+    return out
+
+
+def check_case(case, recs):
+    exp = [((e[1], e[2], e[3], e[4], e[5]), e[0]) for e in case["expect"]]
+    got = expand(case, recs)
+    ce, cg = collections.Counter(t for t, _ in exp), collections.Counter(t for t, _ in got)
+    if ce != cg:
+        # only a distance tie cut by the 100-record limit may differ
+        assert len(exp) == 100 and len(got) == 100, (case["seed"], (ce - cg), (cg - ce))
+        dmax = max(t[1] for t, _ in exp)
+        assert dmax == max(t[1] for t, _ in got), case["seed"]
+        assert all(t[1] == dmax for t in list((ce - cg).elements()) + list((cg - ce).elements())), case["seed"]
+    ranges = collections.defaultdict(list)
+    for t, rg in got:
+        ranges[t].append(rg)
+    for t, i in exp:
+        if t in ranges:
+            assert any(lo <= i <= hi for lo, hi in ranges[t]), (case["seed"], t, i, ranges[t])
+
+
+def test_oracle_matches_reference_goldens(golden_tsd):
+    n_rec = n_short = 0
+    for case in golden_tsd:
+        recs = O.search_confident_tir_v4(case["seq"], case["raw_start"], case["raw_end"], case["d"], case["plant"])
+        check_case(case, recs)
+        n_rec += len(recs)
+        n_short += sum(1 for r in recs if r["short_class"])
+    assert n_rec > 10_000 and n_short > 50
+
+
+def test_oracle_output_is_sorted_and_capped(golden_tsd):
+    for case in golden_tsd[:60]:
+        recs = O.search_confident_tir_v4(case["seq"], case["raw_start"], case["raw_end"], case["d"], case["plant"])
+        assert len(recs) <= 100
+        assert [r["dist"] for r in recs] == sorted(r["dist"] for r in recs)
+        assert [r["idx"] for r in recs] == sorted(r["idx"] for r in recs)
+        for r in recs:
+            assert r["end"] - r["start"] + 1 >= 100 and r["idx_lo"] <= r["idx"] <= r["idx_hi"]
+
+
+def test_host_short_tir_rule_matches_reference_goldens(golden_tsd):
+    """hite_b200.tir_prefilter.get_short_tir_contigs (string rule, no GPU) keeps exactly the records the reference's
+    get_short_tir_contigs kept, on records rebuilt from the oracle's coordinates."""
+    from hite_b200 import tir_prefilter as TP
+    kept = 0
+    for case in golden_tsd:
+        if len(case["expect"]) >= 100:
+            continue                                     # a tie at the cut may select other members
+        seq = case["seq"]
+        recs = O.search_confident_tir_v4(seq, case["raw_start"], case["raw_end"], case["d"], case["plant"])
+        d = {"q-C_%d-tsd_%s-distance_%d" % (r["idx"], seq[r["end"] + 1:r["end"] + 1 + r["k"]], r["dist"]): seq[r["start"]:r["end"] + 1]
+             for r in recs}
+        short = TP.get_short_tir_contigs(d, case["plant"])
+        exp = collections.Counter((e[1], e[2], e[3], e[4]) for e in case["expect"] if e[5])
+        got = collections.Counter((n.split("-tsd_")[1].split("-")[0], int(n.split("-distance_")[1]), len(s),
+                                   zlib.crc32(s.encode()) & 0xFFFFFFFF) for n, s in short.items())
+        assert got == exp, case["seed"]
+        kept += len(short)
+    assert kept > 20
