@@ -360,6 +360,20 @@ def main():
                 per_type[kind + "_stages_ms"] = [round(float(x), 3) for x in tmk["k_ms"][:6]]
                 per_type[kind + "_is_te"] = int((ck["is_te"] != 0).sum())
             line["per_type_candidates_per_s"] = per_type
+            # the TSD-bounded variant generation that runs right before the path in the TIR module
+            # (search_confident_tir_v4, module/Util.py:7734) on this step's flanked candidates, through the C-ABI
+            tc = [c for c in my_cands if len(c) > 100]
+            ms, wl_s, nrec = [], [], 0
+            for it in range(2 + 5):
+                tw = time.perf_counter()
+                _, cnt = ctx.tsd_candidates(tc, [51] * len(tc), [len(c) - 50 for c in tc], 50, 1)
+                if it >= 2:
+                    wl_s.append(time.perf_counter() - tw)
+                    ms.append(ctx.timing()["kernel_ms"])
+                    nrec = int(cnt.sum())
+            line["tir_prefilter"] = {"candidates": len(tc), "variants": nrec, "kernel_ms": float(np.mean(ms)),
+                                     "candidates_per_s": float(len(tc) / (np.mean(ms) * 1e-3)),
+                                     "e2e_candidates_per_s": float(len(tc) / np.mean(wl_s))}
         if not args.no_cpu_baseline and world == 1:
             per = min(len(wl.cand_seqs), max(512, 128 * cores))
             dt, _, _ = cpu_reference_run(wl, list(range(per)), cores)

@@ -44,6 +44,9 @@ COPY_DTYPE = np.dtype([("cand", "<u4"), ("rank", "<i4"), ("rel", "<i4"), ("nseed
 assert COPY_DTYPE.itemsize == 88
 
 
+QHSP_DTYPE = np.dtype([("query", "<u4"), ("contig", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("ss", "<i4"), ("se", "<i4"),
+                       ("n_match", "<i4"), ("aln_len", "<i4"), ("score", "<i4"), ("rank", "<i4")])
+assert QHSP_DTYPE.itemsize == 40
 TSD_DTYPE = np.dtype([("k", "<i4"), ("start", "<i4"), ("end", "<i4"), ("dist", "<i4"), ("idx", "<i4"), ("short_class", "<i4")])
 HSP_DTYPE = np.dtype([("subj", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("ss", "<i4"), ("se", "<i4")])
 SEG_DTYPE = np.dtype([("chr", "<i4"), ("pad", "<i4"), ("start", "<i8")])
@@ -135,6 +138,8 @@ def load():
                                     C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_coarse_boundary.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
     lib.hb_last_hsps.argtypes = [vp, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.hb_query_hsps.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(HbParams), u64p]
+    lib.hb_last_query_hsps.argtypes = [vp, vp, C.c_uint64, u64p]
     lib.hb_tsd_candidates.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp]
     _LIB = lib
     return lib
@@ -342,6 +347,24 @@ class Context:
                 cap = int(n.value)
                 continue
             self._check(rc, "hb_coarse_boundary")
+
+    def query_hsps(self, query_seqs, occ_cap=512, max_loci=128):
+        """Library-vs-genome local alignments (``hb_query_hsps``; replaces the blastn of reference module/Util.py:7213-7225)
+        -> QHSP_DTYPE records ordered by (query, locus rank)."""
+        if isinstance(query_seqs, tuple):
+            flat, off = query_seqs
+        else:
+            qb = [q if isinstance(q, (bytes, bytearray)) else q.encode("ascii") for q in query_seqs]
+            off = np.zeros(len(qb) + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([len(q) for q in qb])
+            flat = np.frombuffer(b"".join(qb) + b"\0", dtype=np.uint8)
+        prm = HbParams(occ_cap=occ_cap, max_loci=max_loci, flank=50, max_rows=100, te_type=0, plant=1, result_type=1, trunc_gate=0)
+        n = C.c_uint64(0)
+        self._check(self._lib.hb_query_hsps(self._h, len(off) - 1, _ptr(flat), _ptr(off), C.byref(prm), C.byref(n)), "hb_query_hsps")
+        out = np.zeros(n.value, dtype=QHSP_DTYPE)
+        if n.value:
+            self._check(self._lib.hb_last_query_hsps(self._h, _ptr(out), n.value, C.byref(n)), "hb_last_query_hsps")
+        return out
 
     def tsd_candidates(self, seqs, raw_starts, raw_ends, tsd_search_distance, plant):
         """TSD-bounded variants of flanked candidates (reference ``search_confident_tir_v4`` + the classes of

@@ -94,6 +94,7 @@ struct hb_ctx {
     std::vector<uint64_t> last_hsp_off;
     std::vector<hb_segment> last_segs;
     std::vector<uint32_t> last_rows, last_cols;
+    std::vector<hb_qhsp> last_qhsps;          // last hb_query_hsps, ordered by (query, rank)
 };
 
 inline int hb_fail(hb_ctx* ctx, const char* what, cudaError_t e, const char* file, int line) {

@@ -58,6 +58,56 @@ __global__ void copy_filter_kernel(const HbLocus* __restrict__ pairs, uint32_t n
     alns[p] = a;
 }
 
+// Library-vs-genome HSPs (hb_query_hsps): every positive local alignment of a query x locus pair as the outfmt-6
+// fields get_copies_v1 reads (module/Util.py:7032-7056): 1-based inclusive query / subject spans (minus strand as
+// s_start > s_end), matches and alignment length (pident = 100 * n_match / aln_len).  Warp per pair over the
+// traceback's per-query-base edit record: word & 0xFFFF = diagonal drift + 32768, bits 16-23 = target-only bases
+// after the query base, bit 24 = query base without a target base.
+__global__ void __launch_bounds__(256)
+qhsp_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAln* __restrict__ alns,
+            const uint32_t* __restrict__ qrec_unit_off, const uint32_t* __restrict__ qrec, const uint32_t* __restrict__ cseq2,
+            const uint32_t* __restrict__ cnmask, const uint64_t* __restrict__ cgoff, const uint32_t* __restrict__ gseq2,
+            const uint32_t* __restrict__ gnmask, const uint64_t* __restrict__ goff, const uint64_t* __restrict__ glen,
+            uint32_t n_contig, uint64_t tot, hb_qhsp* __restrict__ out) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= n_pairs) return;
+    const HbAln a = alns[p];
+    const HbLocus pr = pairs[p];
+    hb_qhsp r;
+    r.query = pr.cand; r.contig = -1; r.qs = r.qe = r.ss = r.se = 0; r.n_match = r.aln_len = 0;
+    r.score = a.score; r.rank = (int32_t)pr.rank;
+    if (a.score > 0) {
+        const int rel = (int)pr.rel;
+        const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
+        const uint64_t cbase = cgoff[pr.cand];
+        int match = 0, extra = 0;
+        for (int q = a.i_s + lane; q <= a.i_e; q += 32) {
+            const uint32_t v = qr[q];
+            extra += (int)((v >> 16) & 255u);
+            if ((v >> 24) & 1u) continue;
+            const int qb = packed_base(cseq2, cnmask, cbase + (uint64_t)q);
+            const int tb = target_base(gseq2, gnmask, tot, rel, pr.j0 + q + (int64_t)(v & 0xFFFFu) - 32768);
+            match += (qb < 4 && qb == tb) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { match += __shfl_xor_sync(HB_FULL, match, o); extra += __shfl_xor_sync(HB_FULL, extra, o); }
+        const int64_t fs = rel ? (int64_t)tot - 1 - a.j_e : a.j_s;
+        const int64_t fe = rel ? (int64_t)tot - 1 - a.j_s : a.j_e;
+        int lo = 0, hi = (int)n_contig;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if ((int64_t)goff[mid] <= fs) lo = mid + 1; else hi = mid; }
+        const int c = lo - 1;
+        if (c >= 0 && (uint64_t)fe < goff[c] + glen[c]) {
+            const int32_t s1 = (int32_t)(fs - (int64_t)goff[c] + 1), e1 = (int32_t)(fe - (int64_t)goff[c] + 1);
+            r.contig = c;
+            r.qs = a.i_s + 1; r.qe = a.i_e + 1;
+            r.ss = rel ? e1 : s1; r.se = rel ? s1 : e1;
+            r.n_match = match; r.aln_len = a.i_e - a.i_s + 1 + extra;
+        }
+    }
+    if (lane == 0) out[p] = r;
+}
+
 // S8 dedup + S9 "max_rows longest": warp per candidate
 constexpr int SEL_MAX = 512;
 __global__ void __launch_bounds__(128)
@@ -310,5 +360,15 @@ cudaError_t hb_msa_write_launch(const HbLocus* pairs, uint32_t n_pairs, const Hb
     msa_write_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(pairs, n_pairs, alns, qrec_unit_off, qrec, n_cols,
                                                                        col_off, colq, mat_off, gseq2, gnmask, tot, flank,
                                                                        trunc, mat);
+    return cudaGetLastError();
+}
+cudaError_t hb_qhsp_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
+                           const uint32_t* qrec, const uint32_t* cseq2, const uint32_t* cnmask, const uint64_t* cgoff,
+                           const uint32_t* gseq2, const uint32_t* gnmask, const uint64_t* goff, const uint64_t* glen,
+                           uint32_t n_contig, uint64_t tot, hb_qhsp* out, cudaStream_t s) {
+    if (n_pairs == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)n_pairs * 32;
+    qhsp_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(pairs, n_pairs, alns, qrec_unit_off, qrec, cseq2, cnmask, cgoff,
+                                                                  gseq2, gnmask, goff, glen, n_contig, tot, out);
     return cudaGetLastError();
 }

@@ -1,6 +1,7 @@
 // hite_b200 -- copy selection + star-MSA launchers (hb_msa.cu)
 #pragma once
 #include "hb_seed.cuh"
+#include "../../include/hite_b200.h"
 
 cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const uint32_t* clen, const uint64_t* goff,
                                   const uint64_t* glen, uint32_t n_contig, uint64_t tot, int flank, HbAln* alns,
@@ -19,3 +20,8 @@ cudaError_t hb_msa_write_launch(const HbLocus* pairs, uint32_t n_pairs, const Hb
                                 const uint32_t* colq, const uint64_t* mat_off, const uint32_t* gseq2,
                                 const uint32_t* gnmask, uint64_t tot, int flank, int trunc, uint8_t* mat,
                                 cudaStream_t s);
+// one hb_qhsp per pair (contig = -1 when the pair has no positive alignment inside one contig)
+cudaError_t hb_qhsp_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
+                           const uint32_t* qrec, const uint32_t* cseq2, const uint32_t* cnmask, const uint64_t* cgoff,
+                           const uint32_t* gseq2, const uint32_t* gnmask, const uint64_t* goff, const uint64_t* glen,
+                           uint32_t n_contig, uint64_t tot, hb_qhsp* out, cudaStream_t s);

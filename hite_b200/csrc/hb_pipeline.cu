@@ -238,7 +238,7 @@ extern "C" int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap) {
 // consensus bytes land in `h_cons` (pinned), calls[i].cons_off indexes them.
 static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_cand, const uint8_t* cand_ascii,
                         const uint64_t* cand_off, const hb_params* prm, int any_long, hb_call* calls,
-                        uint64_t* cons_bytes) {
+                        uint64_t* cons_bytes, std::vector<hb_qhsp>* hsp_out = nullptr) {
     cudaSetDevice(ctx->device);
     cudaStream_t s = ln.stream;
     memset(&ln.timing, 0, sizeof(ln.timing));
@@ -408,6 +408,37 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
     }
     HB_CUDA_OK(cudaEventRecord(ln.ev[3], s));
     mark("extend");
+
+    if (hsp_out) {
+        // ---- hb_query_hsps: the local alignments themselves are the result (no copy rules, no MSA, no judge) ----
+        ENSURE_L("h.recs", sizeof(hb_qhsp) * ((size_t)n_pairs + 1));
+        HB_CUDA_OK(hb_qhsp_launch(LB("p.pairs").as<HbLocus>(), n_pairs, LB("p.alns").as<HbAln>(), LB("p.qr_off").as<uint32_t>(),
+                                  LB("p.qrec").as<uint32_t>(), LB("c.seq2").as<uint32_t>(), LB("c.nmask").as<uint32_t>(), d_cgoff,
+                                  ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(),
+                                  ctx->buf("g.goff").as<uint64_t>(), ctx->buf("g.glen").as<uint64_t>(), ctx->g_ncontig, tot,
+                                  LB("h.recs").as<hb_qhsp>(), s));
+        ++launches;
+        HB_CUDA_OK(cudaEventRecord(ln.ev[4], s));
+        std::vector<hb_qhsp> all(n_pairs);
+        if (n_pairs)
+            HB_CUDA_OK(cudaMemcpyAsync(all.data(), LB("h.recs").p, sizeof(hb_qhsp) * n_pairs, cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaEventRecord(ln.ev[5], s));
+        HB_CUDA_OK(cudaStreamSynchronize(s));
+        hsp_out->clear();
+        for (const hb_qhsp& r : all) if (r.score > 0 && r.contig >= 0) hsp_out->push_back(r);
+        cudaEventElapsedTime(&tm.k_ms[0], ln.ev[0], ln.ev[1]);
+        cudaEventElapsedTime(&tm.k_ms[1], ln.ev[1], ln.ev[2]);
+        cudaEventElapsedTime(&tm.k_ms[2], ln.ev[2], ln.ev[3]);
+        cudaEventElapsedTime(&tm.k_ms[3], ln.ev[3], ln.ev[4]);
+        cudaEventElapsedTime(&tm.d2h_ms, ln.ev[4], ln.ev[5]);
+        cudaEventElapsedTime(&tm.kernel_ms, ln.ev[0], ln.ev[4]);
+        tm.d2h_bytes += sizeof(hb_qhsp) * (uint64_t)n_pairs;
+        tm.launches = launches;
+        tm.k_ms[6] = (float)n_pairs;
+        tm.k_ms[7] = (float)((double)ext_steps * 1e-6);
+        ln.n_pairs = n_pairs; ln.ext_steps = ext_steps;
+        return HB_OK;
+    }
 
     // ---- S8..S10: copy rules, star MSA -------------------------------------------------------------
     ENSURE_L("m.n_rows", sizeof(uint32_t) * (n_cand + 1)); ENSURE_L("m.n_cols", sizeof(uint32_t) * (n_cand + 1));
@@ -702,6 +733,44 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
     ctx->last_ncand = n_cand; ctx->last_npairs = pairs;
     ctx->last_mat_off.clear(); ctx->last_rows.clear(); ctx->last_cols.clear();
     if (cons_bytes) *cons_bytes = base;
+    return HB_OK;
+}
+
+extern "C" int hb_query_hsps(hb_ctx* ctx, uint32_t n_query, const uint8_t* query_ascii, const uint64_t* query_off,
+                             const hb_params* prm, uint64_t* n_out) {
+    if (!ctx || !query_ascii || !query_off || !prm || !n_out) return hb_fail_msg(ctx, HB_EINVAL, "hb_query_hsps: null argument");
+    if (!ctx->have_index) return hb_fail_msg(ctx, HB_ESTATE, "hb_query_hsps: call hb_genome_load + hb_index_build first");
+    ctx->last_qhsps.clear();
+    *n_out = 0;
+    if (n_query == 0) return HB_OK;
+    if (n_query > (1u << 17)) return hb_fail_msg(ctx, HB_EINVAL, "hb_query_hsps: at most 131072 queries per call");
+    if (prm->max_loci < 1 || prm->max_loci > 512 || prm->occ_cap < 1)
+        return hb_fail_msg(ctx, HB_EINVAL, "hb_query_hsps: parameter out of range");
+    int any_long = 0;
+    for (uint32_t c = 0; c < n_query; ++c) {
+        const uint64_t L = query_off[c + 1] - query_off[c];
+        if (L < 3 || L > 32000) return hb_fail_msg(ctx, HB_EINVAL, "hb_query_hsps: query " + std::to_string(c) + " length must be in [3, 32000]");
+        if (L > HB_EXTEND16_MAX_L) any_long = 1;
+    }
+    cudaSetDevice(ctx->device);
+    HbLane& ln = ctx->lane[0];
+    const int rc = adjust_batch(ctx, ln, ctx->part_cons.empty() ? ctx->h_cons : ctx->part_cons[0], n_query, query_ascii, query_off,
+                                prm, any_long, nullptr, nullptr, &ctx->last_qhsps);
+    if (rc != HB_OK) return rc;
+    ctx->timing = ln.timing;
+    // the hb_last_copies / hb_last_msa / hb_last_cons getters describe an hb_adjust: none is current now
+    ctx->last_ncand = 0; ctx->last_npairs = 0; ctx->last_cons_bytes = 0; ctx->cons_parts.clear();
+    ctx->last_mat_off.clear(); ctx->last_rows.clear(); ctx->last_cols.clear();
+    *n_out = ctx->last_qhsps.size();
+    return HB_OK;
+}
+
+extern "C" int hb_last_query_hsps(hb_ctx* ctx, hb_qhsp* out, uint64_t cap, uint64_t* n) {
+    if (!ctx || !n) return HB_EINVAL;
+    *n = ctx->last_qhsps.size();
+    if (!out) return HB_OK;
+    if (cap < ctx->last_qhsps.size()) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_query_hsps: buffer too small");
+    if (!ctx->last_qhsps.empty()) memcpy(out, ctx->last_qhsps.data(), sizeof(hb_qhsp) * ctx->last_qhsps.size());
     return HB_OK;
 }
 

@@ -13,15 +13,11 @@
 
 namespace {
 
-__constant__ int c_ks[9] = {2, 3, 4, 5, 6, 8, 9, 10, 11};   // TIR_TSDs, Util.py:7760
-
+// k runs over TIR_TSDs = {2, 3, 4, 5, 6, 8, 9, 10, 11} (Util.py:7760)
 struct Win {             // 11-byte look-ahead of every window position: bytes 0-7 in lo, 8-10 in hi
     unsigned long long* lo;
     uint32_t* hi;
 };
-__device__ __forceinline__ bool kmer_eq(const Win& a, int i, const Win& b, int j, unsigned long long mlo, uint32_t mhi) {
-    return ((a.lo[i] ^ b.lo[j]) & mlo) == 0 && ((a.hi[i] ^ b.hi[j]) & mhi) == 0;
-}
 __device__ __forceinline__ uint8_t rc_base(uint8_t c) {     // getReverseSequence, Util.py:1635
     return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'N';
 }
@@ -58,13 +54,13 @@ tsd_kernel(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_of
     const uint32_t c = blockIdx.x;
     const int lane = threadIdx.x;
     if (c >= n_cand) return;
-    // shared layout: Llo[wcap] Rlo[wcap] keys[9 wcap] sorted[9 wcap] | Lhi[wcap] Rhi[wcap] | counter
+    // shared layout: Llo[wcap] Rlo[wcap] keys[9 wcap] | Lhi[wcap] Rhi[wcap] | counter | order[9 wcap] (16-bit)
     Win L, R;
     L.lo = smem; R.lo = smem + wcap;
     unsigned long long* keys = smem + 2 * wcap;
-    unsigned long long* sorted = keys + 9 * wcap;
-    L.hi = reinterpret_cast<uint32_t*>(sorted + 9 * wcap); R.hi = L.hi + wcap;
+    L.hi = reinterpret_cast<uint32_t*>(keys + 9 * wcap); R.hi = L.hi + wcap;
     int* counter = reinterpret_cast<int*>(R.hi + wcap);
+    uint16_t* order = reinterpret_cast<uint16_t*>(counter + 4);
     const uint8_t* seq = seqs + seq_off[c];
     const int n = (int)(seq_off[c + 1] - seq_off[c]);
     const int rs = raw_start1[c] - 1, re = raw_end1[c] - 1;                     // :7736-7737
@@ -91,31 +87,51 @@ tsd_kernel(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_of
     if (lane == 0) *counter = 0;
     __syncwarp();
     // ---- tuples: every right k-mer occurrence that sets a new "closest to the raw end" for its string ----
-    for (int ki = 0; ki < 9; ++ki) {
-        const int k = c_ks[ki];
-        const unsigned long long mlo = k >= 8 ? ~0ull : ((1ull << (8 * k)) - 1ull);
-        const uint32_t mhi = k <= 8 ? 0u : ((1u << (8 * (k - 8))) - 1u);
-        for (int j = lane; j + k <= nr; j += 32) {
-            const int pos = rts + j - 1;                                        // :7783
-            if (pos < 0 || pos > n - 1) continue;
-            int best_l = -1, best_ld = 0;                                       // left_pos: closest to rs, first on ties
-            for (int i = 0; i + k <= nl; ++i) {
-                const int lp = ls + i + k;
-                if (lp > n - 1) break;
-                if (!kmer_eq(L, i, R, j, mlo, mhi)) continue;
-                const int dd = abs(lp - rs);
-                if (best_l < 0 || dd < best_ld) { best_l = lp; best_ld = dd; }
+    // One pass over the (left i, right j) pairs serves all nine k: the pair's common-prefix length m says for which k
+    // the two k-mers are equal.  Lanes own right positions; i is warp-uniform, so L is a shared-memory broadcast.
+    for (int j = lane; j < nr; j += 32) {
+        const int pos = rts + j - 1;                                            // :7783
+        if (pos < 0 || pos > n - 1) continue;
+        const unsigned long long rlo = R.lo[j];
+        const uint32_t rhi = R.hi[j];
+        const int kmax_r = nr - j;                                              // k-mer must end inside the right window
+        int best[9];                                                            // left_pos per k: closest to rs, first on ties
+#pragma unroll
+        for (int ki = 0; ki < 9; ++ki) best[ki] = -1;
+        const int i_end = min(nl, n - 1 - ls) - 2;                              // i + k <= nl and ls + i + k <= n - 1 for k = 2
+        for (int i = 0; i <= i_end; ++i) {
+            const unsigned long long x = L.lo[i] ^ rlo;
+            if ((x & 0xFFFFull) != 0) continue;                                 // first two bytes differ: no k matches
+            int m = x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
+            if (m == 8) { const uint32_t y = (L.hi[i] ^ rhi) & 0xFFFFFFu; m = 8 + (y ? ((__ffs((int)y) - 1) >> 3) : 3); }
+            m = min(m, min(kmax_r, min(nl - i, n - 1 - ls - i)));
+#pragma unroll
+            for (int ki = 0; ki < 9; ++ki) {
+                const int k = ki < 5 ? ki + 2 : ki + 3;                         // 2 3 4 5 6 8 9 10 11
+                if (k <= m) {
+                    const int lp = ls + i + k;
+                    if (best[ki] < 0 || abs(lp - rs) < abs(best[ki] - rs)) best[ki] = lp;
+                }
             }
-            if (best_l < 0) continue;
-            const int my = abs(pos - re);
-            bool is_best = true;                                                // :7788-7796
-            for (int j2 = 0; j2 < j && is_best; ++j2) {
-                const int p2 = rts + j2 - 1;
-                if (p2 < 0) continue;
-                if (kmer_eq(R, j2, R, j, mlo, mhi) && abs(p2 - re) <= my) is_best = false;
-            }
-            if (!is_best) continue;
-            const uint8_t* km = seq + rts + j;
+        }
+        // right_pos after this occurrence = running closest to re over the occurrences so far (:7788-7796): this
+        // occurrence contributes a NEW tuple only when no earlier equal k-mer is at least as close
+        const int my = abs(pos - re);
+        int not_best = 0;                                                       // smallest m-bound: k <= not_best are beaten
+        for (int j2 = max(0, 1 - rts); j2 < j; ++j2) {
+            const unsigned long long x = R.lo[j2] ^ rlo;
+            if ((x & 0xFFFFull) != 0) continue;
+            if (abs(rts + j2 - 1 - re) > my) continue;
+            int m = x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
+            if (m == 8) { const uint32_t y = (R.hi[j2] ^ rhi) & 0xFFFFFFu; m = 8 + (y ? ((__ffs((int)y) - 1) >> 3) : 3); }
+            not_best = max(not_best, m);                                        // j2 < j: its k-mers end inside the window too
+        }
+        const uint8_t* km = seq + rts + j;
+#pragma unroll
+        for (int ki = 0; ki < 9; ++ki) {
+            const int k = ki < 5 ? ki + 2 : ki + 3;
+            const int best_l = best[ki];
+            if (best_l < 0 || k <= not_best) continue;
             bool ok;                                                            // :7802-7805
             if (k != 2 && k != 4) ok = true;
             else if (k == 4) ok = eq_lit(km, "TTAA", 4);
@@ -136,7 +152,7 @@ tsd_kernel(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_of
         const unsigned long long kt = keys[t];
         int rank = 0;
         for (int u = 0; u < nt; ++u) rank += keys[u] < kt ? 1 : 0;
-        sorted[rank] = kt;
+        order[rank] = (uint16_t)t;
     }
     __syncwarp();
     // ---- filters (:7811-7833) and the 100-record cut (:7836-7844), in sorted order ----------------------------
@@ -146,7 +162,7 @@ tsd_kernel(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_of
         bool keep = false;
         int k = 0, start = 0, end = 0, dist = 0;
         if (t < nt) {
-            const unsigned long long kt = sorted[t];
+            const unsigned long long kt = keys[order[t]];
             k = (int)(kt & 15ull); end = (int)((kt >> 4) & 0xFFFFFull); start = (int)((kt >> 24) & 0xFFFFFull); dist = (int)(kt >> 44);
             const uint8_t* km = seq + end + 1;
             bool has_nn = false;
@@ -176,7 +192,7 @@ tsd_kernel(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_of
 
 size_t hb_tsd_smem_bytes(int d) {
     const size_t wcap = (size_t)(2 * d + 1 + 3) & ~(size_t)3;
-    return wcap * (2 + 18) * sizeof(unsigned long long) + wcap * 2 * sizeof(uint32_t) + 16;
+    return wcap * (2 + 9) * sizeof(unsigned long long) + wcap * 2 * sizeof(uint32_t) + 16 + 9 * wcap * sizeof(uint16_t);
 }
 
 cudaError_t hb_tsd_launch(const uint8_t* seqs, const uint64_t* seq_off, const int32_t* raw_start1, const int32_t* raw_end1,

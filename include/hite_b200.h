@@ -162,6 +162,28 @@ int hb_last_cons_device(hb_ctx* ctx, const void** dptr, uint64_t* nbytes);
 /* copies of the last hb_adjust, ordered by (candidate, rank); pass out=NULL to query the count */
 int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t* n);
 
+/*
+ * hb_query_hsps -- library-vs-genome local alignments for the homology non-LTR module (module/judge_Other_transposons.py:45
+ * -> multi_process_align_and_get_copies, module/Util.py:8382-8430: makeblastdb + blastn -outfmt 6 of 50-query files,
+ * :7213-7245).  Runs the seeding and banded-extension stages of hb_adjust (same kernels, same hb_params: occ_cap,
+ * max_loci) with the library sequences as queries and reports every positive local alignment that lies inside one
+ * contig as the fields get_copies_v1 reads from outfmt 6 (:7032-7056); pident = 100 * n_match / aln_len.  The records
+ * are kept in the context, ordered by (query, locus rank); fetch them with hb_last_query_hsps (out = NULL: count only).
+ * Chaining them into copies is hb_query_copies.  Timing: k_ms[0] sketch queries, [1] seed/sort/cluster/rank,
+ * [2] extension + traceback, [3] HSP records, [6] #pairs, [7] million DP steps.
+ */
+typedef struct {
+    uint32_t query;          /* index of the query in the call's input */
+    int32_t contig;          /* subject: contig index of hb_genome_load */
+    int32_t qs, qe;          /* 1-based inclusive query span */
+    int32_t ss, se;          /* 1-based inclusive subject span; ss > se = minus strand */
+    int32_t n_match, aln_len;
+    int32_t score, rank;
+} hb_qhsp;
+int hb_query_hsps(hb_ctx* ctx, uint32_t n_query, const uint8_t* query_ascii, const uint64_t* query_off, const hb_params* prm,
+                  uint64_t* n_out);
+int hb_last_query_hsps(hb_ctx* ctx, hb_qhsp* out, uint64_t cap, uint64_t* n);
+
 /* ---- coarse boundary (module/coarse_boundary.py -> determine_repeat_boundary_v5, module/Util.py:4637) ---- */
 typedef struct { int32_t subj, qs, qe, ss, se; } hb_hsp;      /* one HSP of a query segment against segment `subj`;
                                                                   1-based inclusive, ss > se = minus strand: the fields

@@ -87,6 +87,11 @@ int hbo_run_batch(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int 
                   const uint64_t *coff, uint32_t n_cand, int occ_cap, int max_loci, int flank, int max_rows, int plant,
                   int threads, hbo_result *out);
 
+/* ---- library-vs-genome HSPs (hbo_align.c): checker of hb_query_hsps ---- */
+typedef struct { int32_t rank, contig, qs, qe, ss, se, n_match, aln_len, score; } hbo_qhsp;
+int hbo_query_hsps(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w, const uint8_t *query_ascii,
+                   int L, int occ_cap, int max_loci, hbo_qhsp *out, int cap);
+
 /* ---- TSD-bounded variant generation (hbo_tsd.c): search_confident_tir_v4 + get_short_tir_contigs ---- */
 typedef struct { int32_t k, start, end, dist, idx, idx_lo, idx_hi, short_class; } hbo_tsd_rec;
 int hbo_short_tir_class(const char *tir, int len, int tsd_len, int plant);

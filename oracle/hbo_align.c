@@ -438,3 +438,43 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
     free(ins); free(colb); free(qrecs); free(loci); free(q);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Library-vs-genome HSPs (checker of hb_query_hsps): every positive local alignment of a query x ranked locus
+   pair inside one contig, as the outfmt-6 fields get_copies_v1 reads (Util.py:7032-7056): 1-based inclusive
+   spans, minus strand as ss > se, matches and alignment length from the traceback's edit record. */
+int hbo_query_hsps(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w, const uint8_t *query_ascii,
+                   int L, int occ_cap, int max_loci, hbo_qhsp *out, int cap) {
+    uint8_t *q = (uint8_t *)malloc((size_t)L + 1);
+    for (int i = 0; i < L; ++i) q[i] = code_of(query_ascii[i]);
+    uint64_t coff[2] = {0, (uint64_t)L};
+    hbo_locus *loci = (hbo_locus *)malloc(sizeof(hbo_locus) * (size_t)(max_loci + 1));
+    int nl = (int)hbo_find_loci(g, idx, n_idx, k, w, q, coff, 1, occ_cap, max_loci, loci, (uint64_t)max_loci);
+    uint32_t *qr = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)L);
+    int n = 0;
+    for (int x = 0; x < nl && n < cap; ++x) {
+        hbo_aln a;
+        const int rel = (int)loci[x].rel;
+        hbo_align_pair(g, q, L, rel, loci[x].j0, (loci[x].dmax - loci[x].dmin <= HB_NARROW_SPREAD) ? 16 : 32, &a, qr);
+        if (a.score <= 0) continue;
+        const int64_t fs = rel ? (int64_t)g->tot - 1 - a.j_e : a.j_s;
+        const int64_t fe = rel ? (int64_t)g->tot - 1 - a.j_s : a.j_e;
+        const int c = contig_of(g, fs, fe);
+        if (c < 0) continue;
+        int match = 0, extra = 0;
+        for (int i = a.i_s; i <= a.i_e; ++i) {
+            const uint32_t v = qr[i];
+            extra += (int)((v >> 16) & 255u);
+            if ((v >> 24) & 1u) continue;
+            const int tb = gbase(g, rel, loci[x].j0 + i + (int64_t)(v & 0xFFFFu) - 32768);
+            if (q[i] < 4 && q[i] == tb) ++match;
+        }
+        const int32_t s1 = (int32_t)(fs - (int64_t)g->goff[c] + 1), e1 = (int32_t)(fe - (int64_t)g->goff[c] + 1);
+        hbo_qhsp *o = &out[n++];
+        o->rank = x; o->contig = c; o->qs = a.i_s + 1; o->qe = a.i_e + 1;
+        o->ss = rel ? e1 : s1; o->se = rel ? s1 : e1;
+        o->n_match = match; o->aln_len = a.i_e - a.i_s + 1 + extra; o->score = a.score;
+    }
+    free(qr); free(loci); free(q);
+    return n;
+}

@@ -194,6 +194,10 @@ def search_confident_tir_v4(seq, raw_start1, raw_end1, d, plant):
     return [{f: getattr(out[i], f) for f, _ in HboTsdRec._fields_} for i in range(n)]
 
 
+class HboQhsp(C.Structure):
+    _fields_ = [(f, C.c_int32) for f in ("rank", "contig", "qs", "qe", "ss", "se", "n_match", "aln_len", "score")]
+
+
 class HboLocus(C.Structure):
     _fields_ = [("cand", C.c_uint32), ("rel", C.c_uint32), ("nseeds", C.c_uint32), ("rank", C.c_uint32),
                 ("dmin", C.c_int64), ("dmax", C.c_int64), ("j0", C.c_int64)]
@@ -262,6 +266,17 @@ class Genome:
         raw = mat[:R.value * Cn.value].tobytes()
         rows = [raw[r * Cn.value:(r + 1) * Cn.value].decode() for r in range(R.value)]
         return cps, rows
+
+    def query_hsps(self, query, occ_cap=512, max_loci=128):
+        """Library-vs-genome HSPs of one query -> list of dicts (rank, contig, qs, qe, ss, se, n_match, aln_len, score)."""
+        L = self._L
+        qb = query if isinstance(query, (bytes, bytearray)) else query.encode()
+        out = (HboQhsp * (max_loci + 1))()
+        L.hbo_query_hsps.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_int]
+        n = L.hbo_query_hsps(self.g, self.index.ctypes.data, len(self.index), self.k, self.w, qb, len(qb), occ_cap, max_loci,
+                             out, max_loci + 1)
+        return [{f: getattr(out[i], f) for f, _ in HboQhsp._fields_} for i in range(n)]
 
     def run_batch(self, cand_seqs, threads, occ_cap=512, max_loci=128, flank=50, max_rows=100, plant=1):
         """Whole per-candidate path (copy search + MSA + clean + judge) on ``threads`` host threads.

@@ -222,8 +222,14 @@ def test_drop_in_stage_scripts_patch_the_reference_namespace(monkeypatch, tmp_pa
         patch.run_stage("coarse_boundary.py", patch_names=("determine_repeat_boundary_v5",), source="hite_b200.coarse")
         import hite_b200.coarse as hc
         assert U.determine_repeat_boundary_v5 is hc.determine_repeat_boundary_v5
+        saved["multi_process_align_and_get_copies"] = U.multi_process_align_and_get_copies
+        patch.run_stage("judge_Other_transposons.py", patch_names=("multi_process_align_and_get_copies",), source="hite_b200.other")
+        import hite_b200.other as ho
+        assert U.multi_process_align_and_get_copies is ho.multi_process_align_and_get_copies
+        assert ran["path"].endswith("module/judge_TIR_transposons.py")      # setdefault keeps the first; the call itself ran
     finally:
         for n, f in saved.items():
             setattr(U, n, f)
-    for s in ("coarse_boundary.py", "judge_TIR_transposons.py", "judge_Helitron_transposons.py", "judge_Non_LTR_transposons.py"):
+    for s in ("coarse_boundary.py", "judge_TIR_transposons.py", "judge_Helitron_transposons.py", "judge_Non_LTR_transposons.py",
+              "judge_Other_transposons.py"):
         assert os.access(os.path.join(ROOT, "module", s), os.X_OK)

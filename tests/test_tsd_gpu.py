@@ -137,10 +137,10 @@ def test_host_mirror_batch(ctx, golden_tsd):
     contigs["with_gap"] = "ACGT" * 30 + "N" * 10 + "ACGT" * 60      # skipped, Util.py:7368
     for plant in (0, 1):
         allc, short = TP.search_confident_tir_batch(contigs, 50, plant, ctx=ctx)
-        assert not any(n.startswith("with_gap") for n in allc)
+        assert not any(n.startswith("with_gap") for n in allc) and len(allc) > 3000
         exp_all, exp_short = {}, {}
         for qn, seq in contigs.items():
-            if qn == "with_gap":
+            if "NNNNNNNNNN" in seq:                                  # Util.py:7368
                 continue
             for r in O.search_confident_tir_v4(seq, 51, len(seq) - 50, 50, plant):
                 name = "%s-C_%d-tsd_%s-distance_%d" % (qn, r["idx"], seq[r["end"] + 1:r["end"] + 1 + r["k"]], r["dist"])
