@@ -92,6 +92,19 @@ def query_copies(hsps, idents, query_len, subj_lens, query_coverage=0.95, subjec
     return out[:n.value]
 
 
+def full_length_copies(hsps, query_len, full_length_threshold=0.95):
+    """``hb_full_length_copies``: get_full_length_copies_from_blastn_v1 (reference module/Util.py:5907) for one query.
+    ``hsps`` is an HSP_DTYPE array; returns QCOPY_DTYPE records (subj, start 0-based, end exclusive, qlen, strand)."""
+    lib = load()
+    hs = np.ascontiguousarray(hsps, dtype=HSP_DTYPE)
+    out = np.zeros(len(hs) + 1, dtype=QCOPY_DTYPE)
+    n = C.c_uint32(0)
+    rc = lib.hb_full_length_copies(_ptr(hs), len(hs), int(query_len), float(full_length_threshold), _ptr(out), len(out), C.byref(n))
+    if rc != 0:
+        raise HiteB200Error("hb_full_length_copies failed (%d)" % rc)
+    return out[:n.value]
+
+
 class HbTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("k_ms", C.c_float * 8), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
@@ -138,6 +151,9 @@ def load():
                                     C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_coarse_boundary.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
     lib.hb_last_hsps.argtypes = [vp, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.hb_full_length_copies.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.hb_genome_mask.argtypes = [vp, C.c_uint32, vp, vp, vp, u64p]
+    lib.hb_genome_export.argtypes = [vp, C.c_uint32, vp, C.c_uint64]
     lib.hb_query_hsps.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(HbParams), u64p]
     lib.hb_last_query_hsps.argtypes = [vp, vp, C.c_uint64, u64p]
     lib.hb_tsd_candidates.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp]
@@ -347,6 +363,21 @@ class Context:
                 cap = int(n.value)
                 continue
             self._check(rc, "hb_coarse_boundary")
+
+    def mask_genome(self, contig, start, end):
+        """N-fill [start, end) (0-based) of the resident packed genome (``hb_genome_mask``; reference module/Util.py:6414-6420)
+        -> bases newly masked.  The index must be rebuilt afterwards."""
+        c = np.ascontiguousarray(contig, dtype=np.int32)
+        a = np.ascontiguousarray(start, dtype=np.int64)
+        b = np.ascontiguousarray(end, dtype=np.int64)
+        n = C.c_uint64(0)
+        self._check(self._lib.hb_genome_mask(self._h, len(c), _ptr(c), _ptr(a), _ptr(b), C.byref(n)), "hb_genome_mask")
+        return int(n.value)
+
+    def export_contig(self, contig, length):
+        out = np.zeros(int(length), dtype=np.uint8)
+        self._check(self._lib.hb_genome_export(self._h, int(contig), _ptr(out), len(out)), "hb_genome_export")
+        return out.tobytes()
 
     def query_hsps(self, query_seqs, occ_cap=512, max_loci=128):
         """Library-vs-genome local alignments (``hb_query_hsps``; replaces the blastn of reference module/Util.py:7213-7225)

@@ -4,8 +4,9 @@
   ``blastn`` of 1 Mbp segments (process_blast_alignments, :4724-4780) becomes one self-join of the minimizer
   index on the GPU (``hb_coarse_boundary``); FMEA chaining (get_longest_repeats_v4, :4122) runs in the C-ABI
   library; ``generate_final_result`` (:4783-4796) slices the intervals out of the reference genome.
-  NOT reproduced (out of scope; external ``trf`` / ``minimap2``): the tandem-repeat and
-  known-TE masking of :4651-4654 -- the chunk is taken as given (mask it beforehand if needed).
+  The known-TE masking of :4654 (``mask_genome_with_TE``) runs on the chunk already resident in HBM
+  (``hite_b200.masking.mask_context``: ``prev_TE`` vs chunk HSPs, full-length chaining, N-fill kernel, index rebuild).
+  NOT reproduced (external ``trf``): the tandem-repeat filter of :4650-4651 -- the chunk is taken as given.
 * ``flanking_seq``  reference module/Util.py:4614-4634 -- same signature and clamping rules.
 """
 import os
@@ -13,7 +14,7 @@ import os
 import numpy as np
 
 from .boundary import _GENOME, get_context
-from .fasta import read_fasta, store_fasta
+from .fasta import file_exist, read_fasta, store_fasta
 
 
 def _chunk_to_chromosomes(repeats_path):
@@ -52,6 +53,11 @@ def determine_repeat_boundary_v5(repeats_path, longest_repeats_path, prev_TE, fi
     _GENOME.pop(ctx.device, None)                 # this context now holds the chunk, not the reference
     ctx.load_genome(chroms)
     ctx.build_index(15, 10)
+    ctx.contig_names = chr_names
+    if prev_TE is not None and file_exist(prev_TE):              # mask_genome_with_TE (module/Util.py:4654)
+        from . import masking
+        te_names, te_contigs = read_fasta(prev_TE)
+        masking.mask_context(ctx, te_names, te_contigs)
     iv = ctx.coarse_boundary(seg_len=int(chrom_seg_length), skip_gap=int(fixed_extend_base_threshold),
                              max_len=int(max_single_repeat_len), occ_cap=int(occ_cap), threads=max(1, int(threads)))
     ref_names, ref_contigs = read_fasta(reference)

@@ -328,3 +328,85 @@ int hb_query_copies_run(const hb_hsp* h, const double* ident, size_t n, int quer
     }
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// get_full_length_copies_from_blastn_v1 (reference module/Util.py:5907-6128) for one query, as the known-TE genome
+// masking drives it (mask_genome_intactTE :6389-6431 -> generate_full_length_out_v1 :6288-6316, search_struct = False).
+// Host code for the same reason as FMEA: value-keyed visited sets and data-dependent early exits over a few dozen HSPs
+// per (query, subject) -- the GPU's share of the masking is the HSP generation (hb_query_hsps) and the N-fill.
+namespace {
+struct MFrag { int32_t qs, qe, ss, se; };
+inline bool same_frag(const MFrag& a, const MFrag& b) { return a.qs == b.qs && a.qe == b.qe && a.ss == b.ss && a.se == b.se; }
+
+// one cluster of one subject (:6021-6094): greedy extension from every not-yet-visited fragment in query order
+void full_length_cluster(std::vector<MFrag>& cl, double skip_gap, double thr, int query_len, int32_t subj,
+                         std::vector<hb_query_copy>& result) {
+    std::stable_sort(cl.begin(), cl.end(), [](const MFrag& a, const MFrag& b) { return a.qs != b.qs ? a.qs < b.qs : a.qe < b.qe; });
+    std::vector<MFrag> visited;                       // the reference keys its visited dict by the tuple's value
+    auto seen = [&](const MFrag& f) { for (const MFrag& v : visited) if (same_frag(v, f)) return true; return false; };
+    for (size_t i = 0; i < cl.size(); ++i) {
+        if (seen(cl[i])) continue;
+        int32_t pqs = cl[i].qs, pqe = cl[i].qe, pss = cl[i].ss, pse = cl[i].se;
+        int32_t longest = std::abs(pqe - pqs);
+        visited.push_back(cl[i]);
+        for (size_t j = i + 1; j < cl.size(); ++j) {
+            const MFrag& c = cl[j];
+            if (seen(c)) continue;
+            if (c.qe <= pqe) continue;
+            const bool fwd = pss < pse && c.ss < c.se, rev = pss > pse && c.ss > c.se;
+            if (!(fwd ? c.se > pse : rev ? c.se < pse : false)) continue;
+            const double sgap = fwd ? (double)(c.ss - pse) : (double)(pse - c.ss);
+            if ((double)(c.qs - pqe) < skip_gap && sgap < skip_gap) {
+                pqe = c.qe;
+                pss = fwd ? std::min(pss, c.ss) : std::max(pss, c.ss);
+                pse = c.se;
+                longest = pqe - pqs;
+                visited.push_back(c);
+            } else if ((double)(c.qs - pqe) >= skip_gap) break;
+        }
+        if ((double)longest < thr * (double)query_len) continue;                                   // :6098
+        if (!((double)longest / (double)query_len >= thr)) continue;                               // :6123-6124
+        const int32_t strand = pss > pse ? 1 : 0;
+        const int32_t start = (strand ? pse : pss) - 1, end = strand ? pss : pse;                  // :6105-6112
+        bool dup = false;
+        for (hb_query_copy& o : result) if (o.subj == subj && o.start == start && o.end == end) { o.strand = strand; dup = true; break; }
+        if (!dup) result.push_back(hb_query_copy{subj, start, end, longest, strand});
+    }
+}
+}  // namespace
+
+int hb_full_length_copies_run(const hb_hsp* h, size_t n, int query_len, double full_length_threshold,
+                              std::vector<hb_query_copy>& result) {
+    const double skip_gap = (double)query_len * full_length_threshold;                             // :5947
+    std::vector<int32_t> order, slot;
+    std::vector<std::vector<MFrag>> per;
+    for (size_t i = 0; i < n; ++i) {
+        const hb_hsp& x = h[i];
+        if ((size_t)x.subj >= slot.size()) slot.resize((size_t)x.subj + 1, -1);
+        if (slot[x.subj] < 0) { slot[x.subj] = (int32_t)order.size(); order.push_back(x.subj); per.emplace_back(); }
+        per[slot[x.subj]].push_back(MFrag{x.qs, x.qe, x.ss, x.se});
+    }
+    result.clear();
+    std::vector<MFrag> cl;
+    for (size_t oi = 0; oi < order.size(); ++oi) {
+        std::vector<MFrag> fw, rv;
+        for (const MFrag& f : per[oi]) (f.ss > f.se ? rv : fw).push_back(f);                       // :5960-5964
+        std::stable_sort(fw.begin(), fw.end(), [](const MFrag& a, const MFrag& b) { return a.ss != b.ss ? a.ss < b.ss : a.se < b.se; });
+        std::stable_sort(rv.begin(), rv.end(), [](const MFrag& a, const MFrag& b) { return a.ss != b.ss ? a.ss > b.ss : a.se > b.se; });
+        for (int pass = 0; pass < 2; ++pass) {
+            const std::vector<MFrag>& p = pass ? rv : fw;
+            cl.clear();
+            for (size_t k = 0; k < p.size(); ++k) {
+                bool closed = false;
+                for (size_t e = cl.size(); e-- > 0;) {                                             // :5977-5984
+                    const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
+                    if ((double)gap < skip_gap && p[k].qe > cl[e].qe) { closed = true; break; }
+                }
+                if (!cl.empty() && !closed) { full_length_cluster(cl, skip_gap, full_length_threshold, query_len, order[oi], result); cl.clear(); }
+                cl.push_back(p[k]);
+            }
+            if (!cl.empty()) full_length_cluster(cl, skip_gap, full_length_threshold, query_len, order[oi], result);
+        }
+    }
+    return 0;
+}

@@ -11,3 +11,5 @@ int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const 
 int hb_query_copies_run(const hb_hsp* h, const double* ident, size_t n, int query_len, const int32_t* subj_len,
                         double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
                         std::vector<hb_query_copy>& result);
+int hb_full_length_copies_run(const hb_hsp* h, size_t n, int query_len, double full_length_threshold,
+                              std::vector<hb_query_copy>& result);

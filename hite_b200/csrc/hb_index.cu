@@ -46,6 +46,55 @@ __global__ void pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* _
     seq2[grp * 2] = w0; seq2[grp * 2 + 1] = w1; nmask[grp] = nm;
 }
 
+// ---- known-TE masking: N-fill of [start, end) intervals (mask_genome_intactTE, module/Util.py:6414-6420) -------------
+// One warp per interval; the interval's span of the N-mask is OR-ed word by word (atomicOr: intervals overlap).  The
+// 2-bit codes stay: every reader tests the mask first.  *n_new counts bases that were not N before.
+__global__ void __launch_bounds__(256)
+mask_fill_kernel(const int32_t* __restrict__ contig, const int64_t* __restrict__ start, const int64_t* __restrict__ end,
+                 uint32_t n, const uint64_t* __restrict__ goff, const uint64_t* __restrict__ glen, uint32_t n_contig,
+                 uint32_t* __restrict__ nmask, unsigned long long* __restrict__ n_new) {
+    const uint32_t iv = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (iv >= n) return;
+    const int32_t c = contig[iv];
+    if (c < 0 || (uint32_t)c >= n_contig) return;
+    // numpy slice semantics of ref_seq_array[start:end] (non-negative bounds): clipped to the contig
+    int64_t a = start[iv], b = end[iv];
+    if (a < 0) a = 0;
+    if (b > (int64_t)glen[c]) b = (int64_t)glen[c];
+    if (b <= a) return;
+    const uint64_t g0 = goff[c] + (uint64_t)a, g1 = goff[c] + (uint64_t)b;     // [g0, g1) in the padded space
+    const uint64_t w0 = g0 >> 5, w1 = (g1 - 1) >> 5;
+    unsigned long long fresh = 0;
+    for (uint64_t w = w0 + lane; w <= w1; w += 32) {
+        uint32_t m = 0xffffffffu;
+        if (w == w0) m &= 0xffffffffu << (g0 & 31);
+        if (w == w1) m &= 0xffffffffu >> (31 - ((g1 - 1) & 31));
+        const uint32_t old = atomicOr(&nmask[w], m);
+        fresh += __popc(m & ~old);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) fresh += __shfl_xor_sync(HB_FULL, fresh, o);
+    if (lane == 0 && fresh) atomicAdd(n_new, fresh);
+}
+
+// packed contig -> ASCII (A C G T N), 16 bases per thread, one 16 B store
+__global__ void export_kernel(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask, uint64_t g0, uint64_t len,
+                              uint8_t* __restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t o = t * 16;
+    if (o >= len) return;
+    uint8_t b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint64_t p = g0 + o + i;
+        const bool isn = (nmask[p >> 5] >> (p & 31)) & 1u;
+        b[i] = isn ? (uint8_t)'N' : (uint8_t)"ACGT"[(seq2[p >> 4] >> (2 * (p & 15))) & 3u];
+    }
+    if (o + 16 <= len && (((uintptr_t)(out + o)) & 15) == 0) *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(b);
+    else for (int i = 0; i < 16 && o + i < len; ++i) out[o + i] = b[i];
+}
+
 // ---- S2: minimizers -----------------------------------------------------------------------------
 constexpr int MM_THREADS = 256;
 constexpr int MM_PER_THREAD = 8;
@@ -192,5 +241,19 @@ cudaError_t hb_minimizer_write_launch(const uint32_t* d_seq2, const uint32_t* d_
 cudaError_t hb_bucket_count_launch(const uint64_t* d_idx, uint64_t n, int shift, uint32_t* d_cnt, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     bucket_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_idx, n, shift, d_cnt);
+    return cudaGetLastError();
+}
+cudaError_t hb_mask_fill_launch(const int32_t* d_contig, const int64_t* d_start, const int64_t* d_end, uint32_t n,
+                                const uint64_t* d_goff, const uint64_t* d_glen, uint32_t n_contig, uint32_t* d_nmask,
+                                unsigned long long* d_n_new, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)n * 32;
+    mask_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d_contig, d_start, d_end, n, d_goff, d_glen, n_contig, d_nmask, d_n_new);
+    return cudaGetLastError();
+}
+cudaError_t hb_export_launch(const uint32_t* d_seq2, const uint32_t* d_nmask, uint64_t g0, uint64_t len, uint8_t* d_out, cudaStream_t s) {
+    if (len == 0) return cudaSuccess;
+    const uint64_t threads = (len + 15) / 16;
+    export_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d_seq2, d_nmask, g0, len, d_out);
     return cudaGetLastError();
 }

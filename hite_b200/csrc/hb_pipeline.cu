@@ -866,6 +866,81 @@ extern "C" int hb_query_copies(const hb_hsp* hsp, const double* ident, uint32_t 
     return HB_OK;
 }
 
+extern "C" int hb_full_length_copies(const hb_hsp* hsp, uint32_t n, int query_len, double full_length_threshold,
+                                     hb_query_copy* out, uint32_t cap, uint32_t* n_out) {
+    if ((!hsp && n) || !n_out || query_len < 1) return HB_EINVAL;
+    for (uint32_t i = 0; i < n; ++i) if (hsp[i].subj < 0) return HB_EINVAL;
+    std::vector<hb_query_copy> res;
+    hb_full_length_copies_run(hsp, n, query_len, full_length_threshold, res);
+    *n_out = (uint32_t)res.size();
+    if (!out) return HB_OK;
+    if (cap < res.size()) return HB_EINVAL;
+    if (!res.empty()) memcpy(out, res.data(), sizeof(hb_query_copy) * res.size());
+    return HB_OK;
+}
+
+extern "C" int hb_genome_mask(hb_ctx* ctx, uint32_t n, const int32_t* contig, const int64_t* start, const int64_t* end,
+                              uint64_t* n_masked) {
+    if (!ctx || (n && (!contig || !start || !end))) return hb_fail_msg(ctx, HB_EINVAL, "hb_genome_mask: null argument");
+    if (!ctx->have_genome) return hb_fail_msg(ctx, HB_ESTATE, "hb_genome_mask: call hb_genome_load first");
+    for (uint32_t i = 0; i < n; ++i)
+        if (contig[i] < 0 || (uint32_t)contig[i] >= ctx->g_ncontig)
+            return hb_fail_msg(ctx, HB_EINVAL, "hb_genome_mask: interval " + std::to_string(i) + " names an unknown contig");
+    if (n_masked) *n_masked = 0;
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    if (n == 0) return HB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ENSURE("k.contig", sizeof(int32_t) * n); ENSURE("k.start", sizeof(int64_t) * n); ENSURE("k.end", sizeof(int64_t) * n);
+    ENSURE("k.count", sizeof(unsigned long long));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("k.contig").p, contig, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("k.start").p, start, sizeof(int64_t) * n, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("k.end").p, end, sizeof(int64_t) * n, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemsetAsync(ctx->buf("k.count").p, 0, sizeof(unsigned long long), s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    HB_CUDA_OK(hb_mask_fill_launch(ctx->buf("k.contig").as<int32_t>(), ctx->buf("k.start").as<int64_t>(), ctx->buf("k.end").as<int64_t>(), n,
+                                   ctx->buf("g.goff").as<uint64_t>(), ctx->buf("g.glen").as<uint64_t>(), ctx->g_ncontig,
+                                   ctx->buf("g.nmask").as<uint32_t>(), ctx->buf("k.count").as<unsigned long long>(), s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    unsigned long long fresh = 0;
+    HB_CUDA_OK(cudaMemcpyAsync(&fresh, ctx->buf("k.count").p, sizeof(fresh), cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    ctx->have_index = false;                       // the sketch of the unmasked genome is stale
+    if (n_masked) *n_masked = fresh;
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    ctx->timing.k_ms[0] = ctx->timing.kernel_ms;
+    ctx->timing.h2d_bytes = 20ull * n;
+    ctx->timing.launches = 1;
+    return HB_OK;
+}
+
+extern "C" int hb_genome_export(hb_ctx* ctx, uint32_t contig, uint8_t* out_ascii, uint64_t cap) {
+    if (!ctx || !out_ascii) return hb_fail_msg(ctx, HB_EINVAL, "hb_genome_export: null argument");
+    if (!ctx->have_genome) return hb_fail_msg(ctx, HB_ESTATE, "hb_genome_export: call hb_genome_load first");
+    if (contig >= ctx->g_ncontig) return hb_fail_msg(ctx, HB_EINVAL, "hb_genome_export: contig out of range");
+    const uint64_t len = ctx->g_glen[contig];
+    if (cap < len) return hb_fail_msg(ctx, HB_EINVAL, "hb_genome_export: buffer too small");
+    if (len == 0) return HB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ENSURE("k.ascii", len + 16);
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    HB_CUDA_OK(hb_export_launch(ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(), ctx->g_goff[contig], len,
+                                ctx->buf("k.ascii").as<uint8_t>(), s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    HB_CUDA_OK(cudaMemcpyAsync(out_ascii, ctx->buf("k.ascii").p, len, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[1], ctx->ev[2]);
+    ctx->timing.d2h_bytes = len;
+    ctx->timing.launches = 1;
+    return HB_OK;
+}
+
 extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
                                   hb_interval* out, uint64_t cap, uint64_t* n_out) {
     if (!ctx || !n_out) return HB_EINVAL;

@@ -213,6 +213,23 @@ int hb_query_copies(const hb_hsp* hsp, const double* ident, uint32_t n, int quer
                     hb_query_copy* out, uint32_t cap, uint32_t* n_out);
 
 /*
+ * Known-TE genome masking: mask_genome_intactTE (module/Util.py:6389-6431; the step before the all-vs-all search in
+ * determine_repeat_boundary_v5 :4654 and before LTR detection, judge_LTR_transposons.py:111).  The reference maps the
+ * TE library to the genome (minimap2 -> PAF -> outfmt-6, :6318-6374), chains every query's records into full-length
+ * copies (get_full_length_copies_from_blastn_v1, :5907-6128, threshold 0.95) and overwrites each copy with N (:6414-6420).
+ * Here: hb_query_hsps gives the records, hb_full_length_copies is the chaining (host code, bit-identical to the reference
+ * on the same HSP list: hsp[i].subj = subject index, spans 1-based inclusive, ss > se = minus strand as in outfmt 6),
+ * hb_genome_mask N-fills [start, end) (0-based, end exclusive: the 'chr:start-end' of :6107) in the context's packed
+ * genome -- clipped to the contig like the numpy slice -- and invalidates the index (call hb_index_build again);
+ * *n_masked = bases that were not N before.  hb_genome_export returns a contig of the packed genome as ASCII
+ * (A C G T N; letters outside ACGT were read as N by hb_genome_load).
+ */
+int hb_full_length_copies(const hb_hsp* hsp, uint32_t n, int query_len, double full_length_threshold,
+                          hb_query_copy* out, uint32_t cap, uint32_t* n_out);
+int hb_genome_mask(hb_ctx* ctx, uint32_t n, const int32_t* contig, const int64_t* start, const int64_t* end, uint64_t* n_masked);
+int hb_genome_export(hb_ctx* ctx, uint32_t contig, uint8_t* out_ascii, uint64_t cap);
+
+/*
  * hb_coarse_boundary -- the all-vs-all step of process_blast_alignments (module/Util.py:4724-4780: n^2 blastn
  * runs of 1 Mbp segments) as one self-join of the minimizer index on the GPU (seed pairs -> radix sort ->
  * exact-diagonal runs = HSPs), followed by hb_fmea_chain.  Uses the genome + index of the context; segments

@@ -82,6 +82,8 @@ int hbo_query_copies(const hbo_hsp *h, const double *ident, int n, int query_len
                      double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
                      hbo_copy_out *out, int cap);
 
+int hbo_full_length_copies_v1(const hbo_hsp *h, int n, int query_len, double full_length_threshold, hbo_copy_out *out, int cap);
+
 typedef struct { int32_t is_te, info, copy_num, cons_len; } hbo_result;
 int hbo_run_batch(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w, const uint8_t *cand_ascii,
                   const uint64_t *coff, uint32_t n_cand, int occ_cap, int max_loci, int flank, int max_rows, int plant,

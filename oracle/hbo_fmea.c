@@ -328,3 +328,119 @@ int hbo_query_copies(const hbo_hsp *h, const double *ident, int n, int query_len
     free(lq); free(fw); free(rv); free(cl); free(order); free(seen);
     return no;
 }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* get_full_length_copies_from_blastn_v1 (reference module/Util.py:5907-6128) for ONE query, as mask_genome_intactTE
+   drives it (Util.py:6389-6431 -> generate_full_length_out_v1 :6288-6316: search_struct = False): the HSPs of the query
+   are chained per subject into candidate copies; copies covering >= full_length_threshold of the query are returned as
+   (subject, start, end, strand) with start 0-based and end exclusive -- the 'chr:start-end' key of :6107, i.e. the slice
+   the caller fills with N (:6414-6420).  Keys are unique, in first-insertion order (Python dict).  Pinned against
+   tests/golden/full_length_copies.json.gz (outputs of the imported reference). */
+typedef struct { int32_t qs, qe, ss, se; int order; } mfrag_t;
+
+static int mcmp_fwd(const void *a, const void *b) {           /* key (s_start, s_end), stable (:5965) */
+    const mfrag_t *x = (const mfrag_t *)a, *y = (const mfrag_t *)b;
+    if (x->ss != y->ss) return x->ss < y->ss ? -1 : 1;
+    if (x->se != y->se) return x->se < y->se ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int mcmp_rev(const void *a, const void *b) {           /* key (-s_start, -s_end), stable (:5966) */
+    const mfrag_t *x = (const mfrag_t *)a, *y = (const mfrag_t *)b;
+    if (x->ss != y->ss) return x->ss > y->ss ? -1 : 1;
+    if (x->se != y->se) return x->se > y->se ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int mcmp_q(const void *a, const void *b) {             /* key (q_start, q_end), stable (:6023) */
+    const mfrag_t *x = (const mfrag_t *)a, *y = (const mfrag_t *)b;
+    if (x->qs != y->qs) return x->qs < y->qs ? -1 : 1;
+    if (x->qe != y->qe) return x->qe < y->qe ? -1 : 1;
+    return (x->order > y->order) - (x->order < y->order);
+}
+static int mfrag_same(const mfrag_t *a, const mfrag_t *b) { return a->qs == b->qs && a->qe == b->qe && a->ss == b->ss && a->se == b->se; }
+
+int hbo_full_length_copies_v1(const hbo_hsp *h, int n, int query_len, double full_length_threshold, hbo_copy_out *out, int cap) {
+    const double skip_gap = (double)query_len * full_length_threshold;                    /* :5947 */
+    int n_subj = 0;
+    for (int i = 0; i < n; ++i) if (h[i].subj + 1 > n_subj) n_subj = h[i].subj + 1;
+    int *order = (int *)malloc(sizeof(int) * (size_t)(n_subj + 1));
+    int *seen = (int *)calloc((size_t)n_subj + 1, sizeof(int));
+    int n_order = 0;
+    for (int i = 0; i < n; ++i) if (!seen[h[i].subj]) { seen[h[i].subj] = 1; order[n_order++] = h[i].subj; }
+    mfrag_t *fw = (mfrag_t *)malloc(sizeof(mfrag_t) * (size_t)(n + 1)), *rv = (mfrag_t *)malloc(sizeof(mfrag_t) * (size_t)(n + 1));
+    mfrag_t *cl = (mfrag_t *)malloc(sizeof(mfrag_t) * (size_t)(n + 1));
+    char *visited = (char *)malloc((size_t)n + 1);
+    int n_out = 0;
+    for (int oi = 0; oi < n_order; ++oi) {
+        const int s = order[oi];
+        int nf = 0, nr = 0;
+        for (int i = 0; i < n; ++i) {
+            if (h[i].subj != s) continue;
+            mfrag_t f = {h[i].qs, h[i].qe, h[i].ss, h[i].se, 0};
+            if (f.ss > f.se) { f.order = nr; rv[nr++] = f; } else { f.order = nf; fw[nf++] = f; }   /* :5960-5964 */
+        }
+        qsort(fw, (size_t)nf, sizeof(mfrag_t), mcmp_fwd);
+        qsort(rv, (size_t)nr, sizeof(mfrag_t), mcmp_rev);
+        for (int pass = 0; pass < 2; ++pass) {
+            const mfrag_t *p = pass ? rv : fw; const int np = pass ? nr : nf;
+            int k = 0;
+            while (k < np) {
+                /* one cluster: consecutive fragments each "closed" to some earlier member (:5970-6018) */
+                int nc = 0;
+                cl[nc++] = p[k++];
+                for (; k < np; ++k) {
+                    int closed = 0;
+                    for (int e = nc - 1; e >= 0; --e) {
+                        const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
+                        if ((double)gap < skip_gap && p[k].qe > cl[e].qe) { closed = 1; break; }
+                    }
+                    if (!closed) break;
+                    cl[nc++] = p[k];
+                }
+                for (int i = 0; i < nc; ++i) cl[i].order = i;
+                qsort(cl, (size_t)nc, sizeof(mfrag_t), mcmp_q);
+                memset(visited, 0, (size_t)nc);
+                for (int i = 0; i < nc; ++i) {
+                    /* visited_frag is keyed by the tuple's VALUE: an identical tuple seen earlier counts (:6029) */
+                    int vis = visited[i];
+                    for (int z = 0; z < nc && !vis; ++z) if (visited[z] && mfrag_same(&cl[z], &cl[i])) vis = 1;
+                    if (vis) continue;
+                    int32_t pqs = cl[i].qs, pqe = cl[i].qe, pss = cl[i].ss, pse = cl[i].se;
+                    int32_t longest = pqe - pqs; if (longest < 0) longest = -longest;                  /* :6038, 6040 */
+                    visited[i] = 1;
+                    for (int j = i + 1; j < nc; ++j) {
+                        int vj = visited[j];
+                        for (int z = 0; z < nc && !vj; ++z) if (visited[z] && mfrag_same(&cl[z], &cl[j])) vj = 1;
+                        if (vj) continue;
+                        const int32_t cqs = cl[j].qs, cqe = cl[j].qe, css = cl[j].ss, cse = cl[j].se;
+                        if (!(cqe > pqe)) continue;                                                      /* :6058 */
+                        if (pss < pse && css < cse) {
+                            if (cse > pse) {
+                                if ((double)(cqs - pqe) < skip_gap && cqe > pqe && (double)(css - pse) < skip_gap) {
+                                    pqe = cqe; if (css < pss) pss = css; pse = cse; longest = pqe - pqs; visited[j] = 1;
+                                } else if ((double)(cqs - pqe) >= skip_gap) break;
+                            }
+                        } else if (pss > pse && css > cse) {
+                            if (cse < pse) {
+                                if ((double)(cqs - pqe) < skip_gap && cqe > pqe && (double)(pse - css) < skip_gap) {
+                                    pqe = cqe; if (css > pss) pss = css; pse = cse; longest = pqe - pqs; visited[j] = 1;
+                                } else if ((double)(cqs - pqe) >= skip_gap) break;
+                            }
+                        }
+                    }
+                    /* :6096-6125 */
+                    if ((double)longest < full_length_threshold * (double)query_len) continue;
+                    int32_t start, end, strand;
+                    if (pss > pse) { strand = 1; start = pse - 1; end = pss; } else { strand = 0; start = pss - 1; end = pse; }
+                    if (!((double)longest / (double)query_len >= full_length_threshold)) continue;
+                    int dup = 0;
+                    for (int z = 0; z < n_out; ++z) if (out[z].subj == s && out[z].start == start && out[z].end == end) { dup = 1; out[z].strand = strand; break; }
+                    if (dup) continue;
+                    if (n_out < cap) { out[n_out].subj = s; out[n_out].start = start; out[n_out].end = end; out[n_out].qlen = longest; out[n_out].strand = strand; }
+                    ++n_out;
+                }
+            }
+        }
+    }
+    free(visited); free(cl); free(fw); free(rv); free(order); free(seen);
+    return n_out;
+}

@@ -160,6 +160,18 @@ def query_copies(hsps, idents, query_len, subj_lens, query_coverage=0.95, subjec
     return [(out[i].subj, out[i].start, out[i].end, out[i].qlen, "-" if out[i].strand else "+") for i in range(k)]
 
 
+def full_length_copies_v1(hsps, query_len, full_length_threshold=0.95):
+    """get_full_length_copies_from_blastn_v1 (Util.py:5907) for one query -> [(subj, start0, end_excl, '+'|'-')], unique."""
+    n = len(hsps)
+    arr = (HboHsp * max(1, n))(*[HboHsp(*h) for h in hsps])
+    cap = n + 8
+    out = (HboCopyOut * cap)()
+    L = lib()
+    L.hbo_full_length_copies_v1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    k = L.hbo_full_length_copies_v1(arr, n, query_len, full_length_threshold, out, cap)
+    return [(out[i].subj, out[i].start, out[i].end, "-" if out[i].strand else "+") for i in range(k)]
+
+
 def find_near_matches_ends(p, s, d):
     fs, fe, ls, le = C.c_int(-1), C.c_int(-1), C.c_int(-1), C.c_int(-1)
     n = lib().hbo_find_near_matches(p.encode(), len(p), s.encode(), len(s), d,
