@@ -374,6 +374,39 @@ def main():
             line["tir_prefilter"] = {"candidates": len(tc), "variants": nrec, "kernel_ms": float(np.mean(ms)),
                                      "candidates_per_s": float(len(tc) / (np.mean(ms) * 1e-3)),
                                      "e2e_candidates_per_s": float(len(tc) / np.mean(wl_s))}
+            # known-TE masking of the genome (mask_genome_intactTE, module/Util.py:6389) with
+            # the planted families' consensus sequences as the library, and the homology copy search of
+            # judge_Other_transposons.py on the same records (get_query_copies chaining)
+            from hite_b200 import boundary as hb_boundary, masking as hb_masking, other as hb_other
+            fams = {}
+            for t in wl.truth:
+                fams.setdefault("fam%d#DNA/TIR" % t["family"], t["consensus"].decode())
+            ctx.load_genome(wl.contig_seqs)
+            ctx.build_index(15, 10)
+            ctx.contig_names = list(wl.contig_names)
+            lib_names = list(fams.keys())
+            tq = time.perf_counter()
+            rec = hb_other.query_hsp_records(ctx, lib_names, fams)
+            t_hsp = time.perf_counter() - tq
+            hsp_tm = dict(hb_other.query_hsp_records.last)
+            tq = time.perf_counter()
+            copies = hb_other.copies_from_records(rec, lib_names, fams, ctx.contig_names, 0.95, max(1, cores))
+            t_chain_other = time.perf_counter() - tq
+            tq = time.perf_counter()
+            iv = hb_masking.intervals_from_hsp_records(rec, lib_names, fams, 0.95, max(1, cores))
+            t_chain = time.perf_counter() - tq
+            fresh = ctx.mask_genome([i[1] for i in iv], [i[2] for i in iv], [i[3] for i in iv])
+            t_fill = ctx.timing()["kernel_ms"]
+            t_re = ctx.build_index(15, 10)["kernel_ms"]
+            line["known_te_masking"] = {
+                "library_seqs": len(fams), "library_bp": int(sum(len(s) for s in fams.values())), "hsps": hsp_tm["hsps"],
+                "pairs_extended": hsp_tm["pairs"], "hsp_device_ms": hsp_tm["kernel_ms"], "hsp_wall_ms": t_hsp * 1e3,
+                "full_length_copies": len(iv), "chain_host_ms": t_chain * 1e3, "mask_fill_kernel_ms": t_fill,
+                "masked_bp": int(fresh), "reindex_ms": t_re,
+                "genome_Mbp_per_s": wl.genome_bp / 1e6 / max(1e-9, t_hsp + t_chain + (t_fill + t_re) * 1e-3)}
+            line["homology_copy_search"] = {"queries": len(fams), "copies": int(sum(len(v) for v in copies.values())),
+                                            "hsp_device_ms": hsp_tm["kernel_ms"], "chain_host_ms": t_chain_other * 1e3,
+                                            "queries_per_s": len(fams) / max(1e-9, t_hsp + t_chain_other)}
         if not args.no_cpu_baseline and world == 1:
             per = min(len(wl.cand_seqs), max(512, 128 * cores))
             dt, _, _ = cpu_reference_run(wl, list(range(per)), cores)

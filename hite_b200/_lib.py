@@ -105,6 +105,39 @@ def full_length_copies(hsps, query_len, full_length_threshold=0.95):
     return out[:n.value]
 
 
+def _chain_batch(call, hsps, q_off):
+    out = np.zeros(len(hsps) + 1, dtype=QCOPY_DTYPE)
+    oq = np.zeros(len(hsps) + 1, dtype=np.uint32)
+    n = C.c_uint64(0)
+    rc = call(out, oq, n)
+    if rc != 0:
+        raise HiteB200Error("batched chaining failed (%d)" % rc)
+    return out[:n.value], oq[:n.value]
+
+
+def full_length_copies_batch(hsps, q_off, query_lens, full_length_threshold=0.95, threads=8):
+    """``hb_full_length_copies_batch``: query g owns hsps[q_off[g]:q_off[g+1]] -> (QCOPY_DTYPE records, query of each)."""
+    lib = load()
+    hs = np.ascontiguousarray(hsps, dtype=HSP_DTYPE)
+    qo = np.ascontiguousarray(q_off, dtype=np.uint64)
+    ql = np.ascontiguousarray(query_lens, dtype=np.int32)
+    return _chain_batch(lambda out, oq, n: lib.hb_full_length_copies_batch(
+        _ptr(hs), _ptr(qo), len(ql), _ptr(ql), float(full_length_threshold), int(threads), _ptr(out), _ptr(oq), len(out), C.byref(n)),
+        hs, qo)
+
+
+def query_copies_batch(hsps, idents, q_off, query_lens, query_coverage=0.95, qthr=200, sthr=200, max_copy_num=100, threads=8):
+    """``hb_query_copies_batch`` (subject_coverage = 0) -> (QCOPY_DTYPE records, query of each)."""
+    lib = load()
+    hs = np.ascontiguousarray(hsps, dtype=HSP_DTYPE)
+    idn = np.ascontiguousarray(idents, dtype=np.float64)
+    qo = np.ascontiguousarray(q_off, dtype=np.uint64)
+    ql = np.ascontiguousarray(query_lens, dtype=np.int32)
+    return _chain_batch(lambda out, oq, n: lib.hb_query_copies_batch(
+        _ptr(hs), _ptr(idn), _ptr(qo), len(ql), _ptr(ql), float(query_coverage), int(qthr), int(sthr), int(max_copy_num),
+        int(threads), _ptr(out), _ptr(oq), len(out), C.byref(n)), hs, qo)
+
+
 class HbTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("k_ms", C.c_float * 8), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
@@ -152,6 +185,9 @@ def load():
     lib.hb_coarse_boundary.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
     lib.hb_last_hsps.argtypes = [vp, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_full_length_copies.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.hb_full_length_copies_batch.argtypes = [vp, vp, C.c_uint32, vp, C.c_double, C.c_int, vp, vp, C.c_uint64, u64p]
+    lib.hb_query_copies_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                          C.c_uint64, u64p]
     lib.hb_genome_mask.argtypes = [vp, C.c_uint32, vp, vp, vp, u64p]
     lib.hb_genome_export.argtypes = [vp, C.c_uint32, vp, C.c_uint64]
     lib.hb_query_hsps.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(HbParams), u64p]

@@ -3,6 +3,7 @@
 // hb_seed.cu, hb_extend.cu, hb_msa.cu and hb_vote.cu; this file only sizes buffers, launches and
 // copies.  One stream per context; stage times are CUDA events on that stream.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <thread>
 #include <cstdlib>
@@ -877,6 +878,59 @@ extern "C" int hb_full_length_copies(const hb_hsp* hsp, uint32_t n, int query_le
     if (cap < res.size()) return HB_EINVAL;
     if (!res.empty()) memcpy(out, res.data(), sizeof(hb_query_copy) * res.size());
     return HB_OK;
+}
+
+// Batched chaining over the records of many queries (query g owns hsp[q_off[g] .. q_off[g+1])), `threads` host threads over
+// queries; copies come back grouped by query, out_query[i] = query of out[i].  cap >= q_off[n_query] always suffices (every copy
+// consumes at least one record of its own).
+template <class F>
+static int chain_batch(uint32_t n_query, int threads, hb_query_copy* out, uint32_t* out_query, uint64_t cap, uint64_t* n_out, F one) {
+    const int T = std::max(1, std::min<int>(threads, 64));
+    std::vector<std::vector<hb_query_copy>> res(n_query);
+    std::atomic<uint32_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t g0 = next.fetch_add(64);
+            if (g0 >= n_query) break;
+            for (uint32_t g = g0; g < std::min(n_query, g0 + 64); ++g) one(g, res[g]);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    uint64_t n = 0;
+    for (uint32_t g = 0; g < n_query; ++g) n += res[g].size();
+    *n_out = n;
+    if (!out) return HB_OK;
+    if (cap < n) return HB_EINVAL;
+    uint64_t at = 0;
+    for (uint32_t g = 0; g < n_query; ++g)
+        for (const hb_query_copy& c : res[g]) { out[at] = c; if (out_query) out_query[at] = g; ++at; }
+    return HB_OK;
+}
+
+extern "C" int hb_full_length_copies_batch(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_query, const int32_t* query_len,
+                                           double full_length_threshold, int threads, hb_query_copy* out, uint32_t* out_query,
+                                           uint64_t cap, uint64_t* n_out) {
+    if (!q_off || !query_len || !n_out || (!hsp && n_query && q_off[n_query] > q_off[0])) return HB_EINVAL;
+    for (uint64_t i = q_off[0]; i < q_off[n_query]; ++i) if (hsp[i].subj < 0) return HB_EINVAL;
+    return chain_batch(n_query, threads, out, out_query, cap, n_out, [&](uint32_t g, std::vector<hb_query_copy>& r) {
+        if (q_off[g + 1] > q_off[g] && query_len[g] > 0)
+            hb_full_length_copies_run(hsp + q_off[g], (size_t)(q_off[g + 1] - q_off[g]), query_len[g], full_length_threshold, r);
+    });
+}
+
+extern "C" int hb_query_copies_batch(const hb_hsp* hsp, const double* ident, const uint64_t* q_off, uint32_t n_query,
+                                     const int32_t* query_len, double query_coverage, int qthr, int sthr, int max_copy_num,
+                                     int threads, hb_query_copy* out, uint32_t* out_query, uint64_t cap, uint64_t* n_out) {
+    if (!q_off || !query_len || !n_out || ((!hsp || !ident) && n_query && q_off[n_query] > q_off[0])) return HB_EINVAL;
+    for (uint64_t i = q_off[0]; i < q_off[n_query]; ++i) if (hsp[i].subj < 0) return HB_EINVAL;
+    return chain_batch(n_query, threads, out, out_query, cap, n_out, [&](uint32_t g, std::vector<hb_query_copy>& r) {
+        if (q_off[g + 1] > q_off[g] && query_len[g] > 0)
+            hb_query_copies_run(hsp + q_off[g], ident + q_off[g], (size_t)(q_off[g + 1] - q_off[g]), query_len[g], nullptr,
+                                query_coverage, 0.0, qthr, sthr, max_copy_num, r);
+    });
 }
 
 extern "C" int hb_genome_mask(hb_ctx* ctx, uint32_t n, const int32_t* contig, const int64_t* start, const int64_t* end,

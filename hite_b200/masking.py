@@ -57,11 +57,33 @@ def fill_text(contigs, names, intervals):
     return {n: arrs[n].tobytes().decode("ascii") for n in names}
 
 
-def mask_context(ctx, lib_names, lib_contigs, full_length_threshold=0.95):
+def intervals_from_hsp_records(rec, names, contigs, full_length_threshold=0.95, threads=8):
+    """The array form of ``records_to_intervals`` over ``other.query_hsp_records`` output: one
+    ``hb_full_length_copies_batch`` call.  Queries whose names agree up to '#' are merged (:5913-5917, :5924)."""
+    keys = [n.split("#")[0] for n in names]
+    gid_of, glen = {}, []
+    for n, k in zip(names, keys):
+        if k not in gid_of:
+            gid_of[k] = len(glen); glen.append(0)
+        glen[gid_of[k]] = len(contigs[n])                     # later names win, like new_query_contigs
+    gid = np.array([gid_of[k] for k in keys], dtype=np.int64)[rec["query"]] if len(rec) else np.zeros(0, dtype=np.int64)
+    order = np.argsort(gid, kind="stable")
+    g = gid[order]
+    hs = np.zeros(len(rec), dtype=_lib.HSP_DTYPE)
+    hs["subj"] = rec["subj"][order]; hs["qs"] = rec["qs"][order]; hs["qe"] = rec["qe"][order]
+    hs["ss"] = np.minimum(rec["ss"], rec["se"])[order]        # the PAF -> outfmt-6 rewrite drops the strand (:6351-6354)
+    hs["se"] = np.maximum(rec["ss"], rec["se"])[order]
+    q_off = np.searchsorted(g, np.arange(len(glen) + 1)).astype(np.uint64)
+    out, oq = _lib.full_length_copies_batch(hs, q_off, np.asarray(glen, dtype=np.int32), full_length_threshold, threads)
+    gkeys = list(gid_of.keys())
+    return [(gkeys[qg], subj, start, end) for qg, (subj, start, end, _, _) in zip(oq.tolist(), out.tolist())]
+
+
+def mask_context(ctx, lib_names, lib_contigs, full_length_threshold=0.95, threads=8):
     """Mask the genome resident in ``ctx`` with the library: HSPs -> full-length copies -> ``hb_genome_mask`` + index
     rebuild.  Returns (intervals, newly masked bases)."""
-    records = other.query_hsps(ctx, lib_names, lib_contigs)
-    intervals = records_to_intervals(records, {n: len(lib_contigs[n]) for n in lib_names}, ctx.contig_names, full_length_threshold)
+    rec = other.query_hsp_records(ctx, lib_names, lib_contigs)
+    intervals = intervals_from_hsp_records(rec, lib_names, lib_contigs, full_length_threshold, threads)
     fresh = 0
     if intervals:
         fresh = ctx.mask_genome([i[1] for i in intervals], [i[2] for i in intervals], [i[3] for i in intervals])
@@ -74,7 +96,7 @@ def mask_genome_intactTE(TE_lib, genome_path, work_dir, thread, ref_index, debug
     if TE_lib is not None and file_exist(TE_lib):
         lib_names, lib_contigs = read_fasta(TE_lib)
         ctx = boundary.ensure_genome(boundary.get_context(), genome_path)
-        intervals, _ = mask_context(ctx, lib_names, lib_contigs)
+        intervals, _ = mask_context(ctx, lib_names, lib_contigs, threads=max(1, int(thread)))
         boundary._GENOME.pop(ctx.device, None)                 # the resident genome is now the masked one, not the file
         ref_names, ref_contigs = read_fasta(genome_path)
         store_fasta(fill_text(ref_contigs, ref_names, intervals), masked_genome_path)

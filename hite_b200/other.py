@@ -6,8 +6,8 @@ The reference formats a BLAST database of the genome, splits the library into 50
 ``blastn -evalue 1e-20 -outfmt 6`` on each in a process pool (``multiple_alignment_blast_and_get_copies``, :7213-7225)
 and chains every file's HSPs with ``get_copies_v1`` -> ``get_query_copies`` (:7032-7060, :6828-7030).  Here the HSPs
 come from one ``hb_query_hsps`` call per query batch (the seeding + banded extension kernels of the boundary path, the
-library sequences as queries) and the chaining is ``hb_query_copies`` (bit-identical to the reference on the same HSP
-list).  There is no CPU fallback.
+library sequences as queries) and the chaining is ``hb_query_copies_batch`` (bit-identical to the reference on the same
+HSP list).  There is no CPU fallback.
 
 Parity note: BLAST's own HSP set is not reproducible here (rmblast is a third-party binary absent from the reference
 repo); the HSPs are HB-align local alignments -- what is pinned is everything downstream of the
@@ -18,12 +18,16 @@ import shutil
 
 import numpy as np
 
-from . import boundary
+from . import _lib, boundary
 from .fasta import read_fasta
 
 MAX_QUERY = 32000          # hb_query_hsps limit per query; longer library entries are tiled
 BATCH_BASES = 8_000_000    # query bases per hb_query_hsps call
 BATCH_QUERIES = 8192
+
+# one record per HSP, query-major, locus-rank order inside a query (the order of "file lines" the chaining sees)
+REC_DTYPE = np.dtype([("query", "<i4"), ("subj", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("ss", "<i4"), ("se", "<i4"),
+                      ("ident", "<f8")])
 
 
 def _tiles(seq):
@@ -34,38 +38,78 @@ def _tiles(seq):
     return [(o, seq[o:o + MAX_QUERY]) for o in range(0, len(seq), MAX_QUERY)]
 
 
-def query_hsps(ctx, names, contigs, occ_cap=512, max_loci=128):
-    """{query_name: {subject_name: [(q_start, q_end, s_start, s_end, identity), ...]}} -- the ``query_records`` dict of
-    get_copies_v1 (module/Util.py:7033-7055), HSPs of a query in (locus rank) order."""
-    subj_names = ctx.contig_names
-    records = {}
-    units = []                                   # (query index, tile offset, bytes)
+def query_hsp_records(ctx, names, contigs, occ_cap=512, max_loci=128):
+    """All HSPs of the library against the genome resident in ``ctx`` as one REC_DTYPE array (query = index into
+    ``names``, subj = contig index; 1-based inclusive spans, ss > se = minus strand, ident = 100 * matches / columns
+    rounded to 3 decimals like outfmt 6).  Self hits (query name == subject name) are dropped (module/Util.py:7045)."""
+    units_q, units_off, units_seq = [], [], []
     for qi, name in enumerate(names):
         for off, piece in _tiles(contigs[name]):
             if len(piece) >= 3:
-                units.append((qi, off, piece.encode("ascii")))
+                units_q.append(qi); units_off.append(off); units_seq.append(piece.encode("ascii"))
+    units_q = np.asarray(units_q, dtype=np.int64)
+    units_off = np.asarray(units_off, dtype=np.int64)
     timing = dict(kernel_ms=0.0, pairs=0, hsps=0, calls=0)
+    parts = []
     lo = 0
-    while lo < len(units):
+    while lo < len(units_seq):
         hi, bases = lo, 0
-        while hi < len(units) and hi - lo < BATCH_QUERIES and (hi == lo or bases + len(units[hi][2]) <= BATCH_BASES):
-            bases += len(units[hi][2])
+        while hi < len(units_seq) and hi - lo < BATCH_QUERIES and (hi == lo or bases + len(units_seq[hi]) <= BATCH_BASES):
+            bases += len(units_seq[hi])
             hi += 1
-        recs = ctx.query_hsps([u[2] for u in units[lo:hi]], occ_cap=occ_cap, max_loci=max_loci)
+        recs = ctx.query_hsps(units_seq[lo:hi], occ_cap=occ_cap, max_loci=max_loci)
         tm = ctx.timing()
         timing["kernel_ms"] += tm["kernel_ms"]; timing["pairs"] += int(tm["k_ms"][6]); timing["hsps"] += len(recs)
         timing["calls"] += 1
-        ident = np.round(100.0 * recs["n_match"] / np.maximum(recs["aln_len"], 1), 3)
-        for r, idn in zip(recs, ident):
-            qi, off, _ = units[lo + int(r["query"])]
-            qname, sname = names[qi], subj_names[int(r["contig"])]
-            if qname == sname:                                   # :7045
-                continue
-            records.setdefault(qname, {}).setdefault(sname, []).append(
-                (int(r["qs"]) + off, int(r["qe"]) + off, int(r["ss"]), int(r["se"]), float(idn)))
+        u = recs["query"].astype(np.int64) + lo
+        out = np.zeros(len(recs), dtype=REC_DTYPE)
+        out["query"] = units_q[u]
+        out["subj"] = recs["contig"]
+        out["qs"] = recs["qs"] + units_off[u]
+        out["qe"] = recs["qe"] + units_off[u]
+        out["ss"] = recs["ss"]; out["se"] = recs["se"]
+        out["ident"] = np.round(100.0 * recs["n_match"] / np.maximum(recs["aln_len"], 1), 3)
+        parts.append(out)
         lo = hi
-    query_hsps.last = timing
+    rec = np.concatenate(parts) if parts else np.zeros(0, dtype=REC_DTYPE)
+    subj_names = ctx.contig_names
+    if len(rec):
+        self_hit = np.fromiter((names[q] == subj_names[s] for q, s in zip(rec["query"], rec["subj"])), dtype=bool, count=len(rec)) \
+            if set(names) & set(subj_names) else np.zeros(len(rec), dtype=bool)
+        rec = rec[~self_hit]
+    query_hsp_records.last = timing
+    return rec
+
+
+def query_hsps(ctx, names, contigs, occ_cap=512, max_loci=128):
+    """{query_name: {subject_name: [(q_start, q_end, s_start, s_end, identity), ...]}} -- the ``query_records`` dict of
+    get_copies_v1 (module/Util.py:7033-7055), HSPs of a query in (locus rank) order."""
+    rec = query_hsp_records(ctx, names, contigs, occ_cap, max_loci)
+    query_hsps.last = query_hsp_records.last
+    subj_names = ctx.contig_names
+    records = {}
+    for q, s, qs, qe, ss, se, idn in rec.tolist():
+        records.setdefault(names[q], {}).setdefault(subj_names[s], []).append((qs, qe, ss, se, idn))
     return records
+
+
+def copies_from_records(rec, names, contigs, subj_names, query_coverage=0.95, threads=8):
+    """get_query_copies over all queries at once (``hb_query_copies_batch``) -> the reference's ``all_copies`` dict.
+    Subjects are numbered per query by first appearance, as the reference's per-query subject dict orders them."""
+    q = rec["query"]
+    bounds = np.flatnonzero(np.diff(q)) + 1 if len(q) else np.zeros(0, dtype=np.int64)
+    starts = np.concatenate([[0], bounds]).astype(np.int64) if len(q) else np.zeros(0, dtype=np.int64)
+    q_off = np.concatenate([starts, [len(q)]]).astype(np.uint64)
+    qidx = q[starts] if len(q) else np.zeros(0, dtype=np.int32)
+    hs = np.zeros(len(rec), dtype=_lib.HSP_DTYPE)
+    for f in ("subj", "qs", "qe", "ss", "se"):
+        hs[f] = rec[f]
+    qlens = np.array([len(contigs[names[i]]) for i in qidx], dtype=np.int32)
+    out, oq = _lib.query_copies_batch(hs, rec["ident"], q_off, qlens, query_coverage=query_coverage, threads=threads)
+    all_copies = {names[i]: [] for i in qidx}
+    for g, (subj, start, end, qlen, strand) in zip(oq.tolist(), out.tolist()):
+        all_copies[names[qidx[g]]].append((subj_names[subj], start, end, qlen, "-" if strand else "+"))
+    return all_copies
 
 
 def multi_process_align_and_get_copies(query_path, subject_path, tmp_blast_dir, TE_type, threads, is_removed_dir=True,
@@ -78,5 +122,5 @@ def multi_process_align_and_get_copies(query_path, subject_path, tmp_blast_dir, 
     os.makedirs(tmp_blast_dir, exist_ok=True)
     names, contigs = read_fasta(query_path)
     ctx = boundary.ensure_genome(boundary.get_context(), subject_path)
-    records = query_hsps(ctx, names, contigs)
-    return boundary.get_query_copies(list(records.items()), contigs, "", 0.95, 0)
+    rec = query_hsp_records(ctx, names, contigs)
+    return copies_from_records(rec, names, contigs, ctx.contig_names, 0.95, max(1, int(threads)))

@@ -226,6 +226,15 @@ int hb_query_copies(const hb_hsp* hsp, const double* ident, uint32_t n, int quer
  */
 int hb_full_length_copies(const hb_hsp* hsp, uint32_t n, int query_len, double full_length_threshold,
                           hb_query_copy* out, uint32_t cap, uint32_t* n_out);
+/* Batched forms over the records of many queries -- query g owns hsp[q_off[g] .. q_off[g+1]) and has length query_len[g];
+ * `threads` host threads over queries.  Copies come back grouped by query (out_query[i] = query of out[i]); cap = number of
+ * records always suffices.  hb_query_copies_batch chains with subject_coverage = 0 (what get_copies_v1 passes, :7032). */
+int hb_full_length_copies_batch(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_query, const int32_t* query_len,
+                                double full_length_threshold, int threads, hb_query_copy* out, uint32_t* out_query,
+                                uint64_t cap, uint64_t* n_out);
+int hb_query_copies_batch(const hb_hsp* hsp, const double* ident, const uint64_t* q_off, uint32_t n_query,
+                          const int32_t* query_len, double query_coverage, int qthr, int sthr, int max_copy_num, int threads,
+                          hb_query_copy* out, uint32_t* out_query, uint64_t cap, uint64_t* n_out);
 int hb_genome_mask(hb_ctx* ctx, uint32_t n, const int32_t* contig, const int64_t* start, const int64_t* end, uint64_t* n_masked);
 int hb_genome_export(hb_ctx* ctx, uint32_t contig, uint8_t* out_ascii, uint64_t cap);
 

@@ -95,3 +95,32 @@ def test_product_mask_text_matches_reference_goldens():
         for name, crc, n_count in g["expect"]:
             s = masked[name]
             assert (zlib.crc32(s.encode()) & 0xFFFFFFFF, s.count("N")) == (crc, n_count), (g["seed"], name)
+
+
+def test_product_batched_chaining_matches_reference_goldens():
+    """hb_full_length_copies_batch / hb_query_copies_batch (threads over queries) == the per-query goldens."""
+    import numpy as np
+    from hite_b200 import _lib
+    cases = load("full_length_copies.json.gz")
+    for thr in (0.95, 0.8):
+        sub = [c for c in cases if c["threshold"] == thr]
+        hs = np.array([tuple(h) for c in sub for h in c["hsps"]], dtype=_lib.HSP_DTYPE)
+        q_off = np.cumsum([0] + [len(c["hsps"]) for c in sub])
+        out, oq = _lib.full_length_copies_batch(hs, q_off, [c["qlen"] for c in sub], thr, threads=4)
+        for g, c in enumerate(sub):
+            got = [[int(o["subj"]), int(o["start"]), int(o["end"])] for o in out[oq == g]]
+            assert got == c["expect"], c["seed"]
+    cases = [c for c in load("query_copies.json.gz") if c["subject_coverage"] == 0]
+    assert len(cases) > 50
+    for cov in (0.95, 0.8):
+        for mc in (100, 3):
+            sub = [c for c in cases if c["query_coverage"] == cov and c["max_copy_num"] == mc]
+            if not sub:
+                continue
+            hs = np.array([tuple(h) for c in sub for h in c["hsps"]], dtype=_lib.HSP_DTYPE)
+            idn = [i for c in sub for i in c["idents"]]
+            q_off = np.cumsum([0] + [len(c["hsps"]) for c in sub])
+            out, oq = _lib.query_copies_batch(hs, idn, q_off, [c["qlen"] for c in sub], query_coverage=cov, max_copy_num=mc, threads=3)
+            for g, c in enumerate(sub):
+                got = [[int(o["subj"]), int(o["start"]), int(o["end"]), int(o["qlen"]), "-" if o["strand"] else "+"] for o in out[oq == g]]
+                assert got == c["expect"], c["seed"]
