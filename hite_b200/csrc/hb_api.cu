@@ -215,3 +215,41 @@ extern "C" int hb_tsd_candidates(hb_ctx* ctx, uint32_t n, const uint8_t* seq_asc
     ctx->timing.launches = 1;
     return HB_OK;
 }
+
+extern "C" int hb_nonltr_candidates(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off, int32_t flank,
+                                    hb_polya_rec* out) {
+    if (!ctx || !seq_ascii || !seq_off || !out) return hb_fail_msg(ctx, HB_EINVAL, "hb_nonltr_candidates: null argument");
+    if (flank < 0 || flank > 1000) return hb_fail_msg(ctx, HB_EINVAL, "hb_nonltr_candidates: flanking_len must be in [0, 1000]");
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    if (n == 0) return HB_OK;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = seq_off[i + 1] - seq_off[i];
+        if (len < 1 || len >= (1u << 20)) return hb_fail_msg(ctx, HB_EINVAL, "hb_nonltr_candidates: candidate " + std::to_string(i) + " length must be in [1, 2^20)");
+    }
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const uint64_t bytes = seq_off[n] - seq_off[0];
+    HB_CUDA_OK(ctx->buf("t.seq").ensure(bytes + 16));
+    HB_CUDA_OK(ctx->buf("t.off").ensure(sizeof(uint64_t) * (n + 1)));
+    HB_CUDA_OK(ctx->buf("t.polya").ensure(sizeof(hb_polya_rec) * (size_t)n));
+    std::vector<uint64_t> off(n + 1);
+    for (uint32_t i = 0; i <= n; ++i) off[i] = seq_off[i] - seq_off[0];
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("t.seq").p, seq_ascii + seq_off[0], bytes, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("t.off").p, off.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    HB_CUDA_OK(hb_polya_tsd_launch(ctx->buf("t.seq").as<uint8_t>(), ctx->buf("t.off").as<uint64_t>(), n, flank,
+                                   ctx->buf("t.polya").as<hb_polya_rec>(), s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    HB_CUDA_OK(cudaMemcpyAsync(out, ctx->buf("t.polya").p, sizeof(hb_polya_rec) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->timing.k_ms[0] = ctx->timing.kernel_ms;
+    ctx->timing.h2d_bytes = bytes + sizeof(uint64_t) * (n + 1);
+    ctx->timing.d2h_bytes = sizeof(hb_polya_rec) * (uint64_t)n;
+    ctx->timing.launches = 1;
+    return HB_OK;
+}

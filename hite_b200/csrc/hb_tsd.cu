@@ -188,6 +188,110 @@ tsd_kernel(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_of
     if (lane == 0) n_out[c] = (uint32_t)min(emitted, 100);
 }
 
+// ------------------------------------------------------------------------------------------------
+// search_polyA_TSD (module/Util.py:10915-11006): the per-candidate scan of the non-LTR candidate generator
+// (get_candidate_non_LTR :11008, judge_Non_LTR_transposons.py:34).  One warp per flanked candidate; the four +-25 bp window
+// scans are warp-uniform (every lane walks the same 50 bytes), the TSD search spreads the window positions over the lanes
+// and takes the first hit of the longest k by ballot.  Bit-identical to oracle/hbo_tsd.c::hbo_search_polyA_TSD.
+__device__ __forceinline__ int py_clip(int x, int n) { return x < 0 ? 0 : (x > n ? n : x); }
+
+// find_nearest_polyA / polyT (:10865, :10903) -> start, end, len(sequence[start:end])
+__device__ void nearest_run(const uint8_t* seq, int n, int position, uint8_t base, int& ps, int& pe, int& plen) {
+    const int lo = py_clip(max(0, position - 25), n), hi = py_clip(position + 25, n);
+    int max_len = 0, cur = 0, start = 0, ms = -1, me = -1;
+    for (int i = lo; i < hi; ++i) {
+        if (seq[i] == base) { if (++cur == 1) start = i - lo; }
+        else { if (cur >= 6 && cur > max_len) { max_len = cur; ms = start; me = i - lo; } cur = 0; }
+    }
+    if (cur >= 6 && cur > max_len) { ms = start; me = hi - lo; }
+    if (ms == -1 || me == -1) { ps = -1; pe = -1; plen = 0; return; }
+    ms = max(0, position - 25 + ms);                           // the offset ignores the clipping of the window (:10872)
+    me = max(0, position - 25 + me);
+    ps = ms; pe = me;
+    plen = max(0, py_clip(me, n) - py_clip(ms, n));
+}
+// find_nearest_tandem (:9772-9819): four exact copies of a 2..6-mer; longest motif wins, first position
+__device__ void nearest_tandem(const uint8_t* seq, int n, int pos, int& ps, int& pe, int& plen) {
+    const int start = max(0, pos - 25), end = min(n, pos + 25);
+    ps = -1; pe = -1; plen = 0;
+    for (int m = 2; m <= 6; ++m)
+        for (int i = start; i <= end - 4 * m; ++i) {
+            bool ok = true;
+            for (int z = m; z < 4 * m && ok; ++z) ok = seq[i + z] == seq[i + z % m];
+            if (ok && 4 * m > plen) { plen = 4 * m; ps = i; pe = i + 4 * m; }
+        }
+}
+// some substring of kmer[0..k) within Levenshtein distance 1 of tsd[0..k): one substitution, or tsd minus one character
+// equal to the k-mer without its last / first character
+__device__ bool near1(const uint8_t* tsd, const uint8_t* kmer, int k) {
+    int ham = 0;
+    for (int i = 0; i < k; ++i) ham += tsd[i] != kmer[i] ? 1 : 0;
+    if (ham <= 1) return true;
+    for (int off = 0; off <= 1; ++off) {
+        const uint8_t* x = kmer + off;
+        int lcp = 0, lcs = 0;
+        while (lcp < k - 1 && tsd[lcp] == x[lcp]) ++lcp;
+        while (lcs < k - 1 && tsd[k - 1 - lcs] == x[k - 2 - lcs]) ++lcs;
+        if (lcp + lcs >= k - 1) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(128)
+polya_tsd_kernel(const uint8_t* __restrict__ seqs, const uint64_t* __restrict__ seq_off, uint32_t n_cand, int flank,
+                 hb_polya_rec* __restrict__ out) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= n_cand) return;
+    const uint8_t* seq = seqs + seq_off[c];
+    const int n = (int)(seq_off[c + 1] - seq_off[c]);
+    const int raw_start = flank + 1, raw_end = n - flank;                           // :10917-10918
+    int end_3 = -1, end_5 = -1, direct = 0;
+    int as, ae, alen, ts, te, tlen;
+    if (raw_end >= 0) {
+        nearest_run(seq, n, raw_end, 'A', as, ae, alen);
+        nearest_tandem(seq, n, raw_end, ts, te, tlen);
+        if (min(alen, tlen) > 0) { end_3 = alen > tlen ? ae : te; end_5 = raw_start; direct = 1; }     // :10926-10934
+    }
+    nearest_run(seq, n, raw_start, 'T', as, ae, alen);
+    nearest_tandem(seq, n, raw_start, ts, te, tlen);
+    if (min(alen, tlen) > 0) { end_3 = alen > tlen ? as : ts; end_5 = raw_end; direct = 2; }           // :10940-10948
+    int found = 0, tsd_k = 0;
+    if (end_3 != -1 && end_5 != -1 && direct) {
+        const int lo5 = max(0, end_5 - 25);
+        const int lo = py_clip(lo5, n), hi = py_clip(max(0, end_5 + 25), n);
+        const int sublen = max(0, hi - lo);
+        for (int k = 20; k >= 8 && !found; --k) {
+            const int t0 = direct == 2 ? end_3 - k : end_3;
+            if (t0 < 0 || t0 + k > n) continue;                                     // len(TSD) != k
+            const uint8_t* tsd = seq + t0;
+            bool has_n = false;
+            for (int z = 0; z < k; ++z) has_n |= tsd[z] == 'N';
+            if (has_n) continue;
+            for (int i0 = 0; i0 + k <= sublen && !found; i0 += 32) {
+                const int i = i0 + lane;
+                const bool hit = i + k <= sublen && near1(tsd, seq + lo + i, k);
+                const uint32_t bal = __ballot_sync(HB_FULL, hit);
+                if (bal) {
+                    const int first = i0 + __ffs((int)bal) - 1;
+                    end_5 = lo5 + first + (direct == 1 ? k : 0);                    // :10971 / :10992
+                    found = 1; tsd_k = k;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        hb_polya_rec r;
+        r.found = found; r.direct = direct; r.end_5 = end_5; r.end_3 = end_3; r.tsd_k = tsd_k;
+        int a = min(end_5, end_3), b = max(end_5, end_3);
+        if (!direct) a = b = 0;
+        r.seq_start = a < 0 ? max(0, a + n) : py_clip(a, n);                        // Python slice bounds of seq[min:max] (:11002)
+        r.seq_end = b < 0 ? max(0, b + n) : py_clip(b, n);
+        if (r.seq_end < r.seq_start) r.seq_end = r.seq_start;
+        out[c] = r;
+    }
+}
+
 }  // namespace
 
 size_t hb_tsd_smem_bytes(int d) {
@@ -200,5 +304,13 @@ cudaError_t hb_tsd_launch(const uint8_t* seqs, const uint64_t* seq_off, const in
     if (n_cand == 0) return cudaSuccess;
     const int wcap = (2 * d + 1 + 3) & ~3;
     tsd_kernel<<<n_cand, 32, hb_tsd_smem_bytes(d), s>>>(seqs, seq_off, raw_start1, raw_end1, n_cand, d, plant, wcap, out, n_out);
+    return cudaGetLastError();
+}
+
+cudaError_t hb_polya_tsd_launch(const uint8_t* seqs, const uint64_t* seq_off, uint32_t n_cand, int flank, hb_polya_rec* out,
+                                cudaStream_t s) {
+    if (n_cand == 0) return cudaSuccess;
+    const uint64_t threads = (uint64_t)n_cand * 32;
+    polya_tsd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(seqs, seq_off, n_cand, flank, out);
     return cudaGetLastError();
 }

@@ -268,6 +268,19 @@ typedef struct { int32_t k, start, end, dist, idx, short_class; } hb_tsd_rec;
 int hb_tsd_candidates(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off, const int32_t* raw_start1,
                       const int32_t* raw_end1, int32_t tsd_search_distance, int32_t plant, hb_tsd_rec* out, uint32_t* n_out);
 
+/*
+ * hb_nonltr_candidates -- search_polyA_TSD (module/Util.py:10915-11006, with find_nearest_polyA / polyT :10865 / :10903 and
+ * find_nearest_tandem :9772-9819) for n flanked candidates: the scan get_candidate_non_LTR (:11008-11045) runs on every
+ * 100-8000 bp record of longest_repeats.flanked.fa right before the non-LTR boundary adjustment
+ * (judge_Non_LTR_transposons.py:34).  end_5_window_size = 25 and TSD_sizes = 8..20 as that caller fixes them (:11009-11010).
+ * Per candidate: found (a TSD of 8-20 bp, one edit allowed), direct 0 none / 1 '+' / 2 '-', the 3' / 5' ends, the TSD length
+ * (TSD = seq[end_3 : end_3 + tsd_k] for '+', seq[end_3 - tsd_k : end_3] for '-') and non_ltr_seq = seq[seq_start : seq_end]
+ * (to be reverse-complemented for '-').  Sequences are upper-case ASCII, < 2^20 bytes each; 0 <= flanking_len <= 1000.
+ */
+typedef struct { int32_t found, direct, end_5, end_3, tsd_k, seq_start, seq_end; } hb_polya_rec;
+int hb_nonltr_candidates(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off, int32_t flanking_len,
+                         hb_polya_rec* out);
+
 /* parity/debug getters: the sorted minimizer index (hash<<33 | pos<<1 | strand) and the raw
  * (pre-clean) MSA of one candidate of the last hb_adjust as ASCII */
 int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap);

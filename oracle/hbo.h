@@ -100,6 +100,10 @@ int hbo_short_tir_class(const char *tir, int len, int tsd_len, int plant);
 int hbo_search_confident_tir_v4(const char *seq, int n, int raw_start1, int raw_end1, int d, int plant,
                                 hbo_tsd_rec *out, int cap);
 
+/* search_polyA_TSD: direct 0 none / 1 '+' / 2 '-'; non_ltr_seq = seq[seq_start:seq_end] (reverse-complemented when '-');
+   the TSD is seq[end_3 : end_3 + tsd_k] ('+') or seq[end_3 - tsd_k : end_3] ('-') */
+typedef struct { int32_t found, direct, end_5, end_3, tsd_k, seq_start, seq_end; } hbo_polya_rec;
+int hbo_search_polyA_TSD(const char *seq, int n, int flanking_len, hbo_polya_rec *out);
 
 #ifdef __cplusplus
 }

@@ -139,3 +139,104 @@ int hbo_search_confident_tir_v4(const char *seq, int n, int raw_start1, int raw_
     free(tups);
     return n_out;
 }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* search_polyA_TSD (reference module/Util.py:10915-11006) with find_nearest_polyA / find_nearest_polyT (:10865, :10903),
+   find_longest_polyA / polyT (:10839, :10877) and find_nearest_tandem (:9772-9819): the per-candidate scan of the non-LTR
+   candidate generator (get_candidate_non_LTR :11008, called right before flank_region_align_v5 in
+   judge_Non_LTR_transposons.py:34).  Pinned against tests/golden/polya_tsd.json.gz (outputs of the imported reference;
+   fuzzysearch.find_near_matches is only asked "is there a match", which is unambiguous: some substring of the k-mer
+   within Levenshtein distance 1 of the TSD). */
+static int py_clip(int x, int n) { return x < 0 ? 0 : (x > n ? n : x); }
+
+/* longest run of `base` of length >= min_length in s[0..n): first longest; -> start/end or -1 */
+static void longest_run(const char *s, int n, char base, int min_length, int *out_start, int *out_end) {
+    int max_len = 0, cur = 0, start = 0, ms = -1, me = -1;
+    for (int i = 0; i < n; ++i) {
+        if (s[i] == base) { if (++cur == 1) start = i; }
+        else { if (cur >= min_length && cur > max_len) { max_len = cur; ms = start; me = i; } cur = 0; }
+    }
+    if (cur >= min_length && cur > max_len) { ms = start; me = n; }
+    *out_start = ms; *out_end = me;
+}
+
+/* find_nearest_polyA / polyT: -> (start, end, len of sequence[start:end]) or (-1, -1, 0) */
+static void nearest_run(const char *seq, int n, int position, char base, int *ps, int *pe, int *plen) {
+    const int lo = py_clip(position - 25 < 0 ? 0 : position - 25, n), hi = py_clip(position + 25, n);
+    int ms = -1, me = -1;
+    if (hi > lo) longest_run(seq + lo, hi - lo, base, 6, &ms, &me);
+    if (ms == -1 || me == -1) { *ps = -1; *pe = -1; *plen = 0; return; }
+    ms = position - 25 + ms; if (ms < 0) ms = 0;               /* the offset ignores the clipping of the window (:10872) */
+    me = position - 25 + me; if (me < 0) me = 0;
+    *ps = ms; *pe = me;
+    const int a = py_clip(ms, n), b = py_clip(me, n);
+    *plen = b > a ? b - a : 0;
+}
+
+/* find_nearest_tandem: 4 exact copies of a 2..6-mer starting inside the +-25 window; longest motif wins, first position */
+static void nearest_tandem(const char *seq, int n, int pos, int *ps, int *pe, int *plen) {
+    const int start = pos - 25 < 0 ? 0 : pos - 25, end = pos + 25 < n ? pos + 25 : n;
+    *ps = -1; *pe = -1; *plen = 0;
+    for (int m = 2; m <= 6; ++m)
+        for (int i = start; i <= end - 4 * m; ++i) {
+            int ok = 1;
+            for (int z = m; z < 4 * m && ok; ++z) if (seq[i + z] != seq[i + z % m]) ok = 0;
+            if (ok && 4 * m > *plen) { *plen = 4 * m; *ps = i; *pe = i + 4 * m; }
+        }
+}
+
+/* is some substring of kmer[0..k) within Levenshtein distance 1 of tsd[0..k) ? */
+static int near1(const char *tsd, const char *kmer, int k) {
+    int ham = 0;
+    for (int i = 0; i < k; ++i) ham += tsd[i] != kmer[i];
+    if (ham <= 1) return 1;
+    /* tsd minus one character == kmer[0..k-1) or kmer[1..k) */
+    for (int off = 0; off <= 1; ++off) {
+        const char *x = kmer + off;
+        int lcp = 0, lcs = 0;
+        while (lcp < k - 1 && tsd[lcp] == x[lcp]) ++lcp;
+        while (lcs < k - 1 && tsd[k - 1 - lcs] == x[k - 2 - lcs]) ++lcs;
+        if (lcp + lcs >= k - 1) return 1;
+    }
+    return 0;
+}
+
+int hbo_search_polyA_TSD(const char *seq, int n, int flanking_len, hbo_polya_rec *out) {
+    const int raw_start = flanking_len + 1, raw_end = n - flanking_len;          /* :10917-10918 */
+    int end_3 = -1, end_5 = -1, direct = 0;
+    int as, ae, alen, ts, te, tlen;
+    if (raw_end >= 0) {
+        nearest_run(seq, n, raw_end, 'A', &as, &ae, &alen);
+        nearest_tandem(seq, n, raw_end, &ts, &te, &tlen);
+        if ((alen < tlen ? alen : tlen) > 0) { end_3 = alen > tlen ? ae : te; end_5 = raw_start; direct = 1; }   /* :10926-10934 */
+    }
+    nearest_run(seq, n, raw_start, 'T', &as, &ae, &alen);
+    nearest_tandem(seq, n, raw_start, &ts, &te, &tlen);
+    if ((alen < tlen ? alen : tlen) > 0) { end_3 = alen > tlen ? as : ts; end_5 = raw_end; direct = 2; }         /* :10940-10948 */
+    int found = 0, tsd_k = 0;
+    if (end_3 != -1 && end_5 != -1 && direct) {
+        const int lo5 = end_5 - 25 < 0 ? 0 : end_5 - 25;
+        const int lo = py_clip(lo5, n), hi = py_clip(end_5 + 25 < 0 ? 0 : end_5 + 25, n);
+        const int sublen = hi > lo ? hi - lo : 0;
+        for (int k = 20; k >= 8 && !found; --k) {
+            const int t0 = direct == 2 ? end_3 - k : end_3;
+            if (t0 < 0 || t0 + k > n) continue;                                   /* len(TSD) != k */
+            const char *tsd = seq + t0;
+            int has_n = 0;
+            for (int z = 0; z < k; ++z) if (tsd[z] == 'N') has_n = 1;
+            for (int i = 0; i + k <= sublen; ++i)
+                if (near1(tsd, seq + lo + i, k) && !has_n) {
+                    end_5 = lo5 + i + (direct == 1 ? k : 0);                      /* :10971 / :10992 */
+                    found = 1; tsd_k = k;
+                    break;
+                }
+        }
+    }
+    out->found = found; out->direct = direct; out->end_5 = end_5; out->end_3 = end_3; out->tsd_k = tsd_k;
+    int a = end_5 < end_3 ? end_5 : end_3, b = end_5 < end_3 ? end_3 : end_5;
+    if (!direct) { a = b = 0; }
+    out->seq_start = a < 0 ? (a + n < 0 ? 0 : a + n) : py_clip(a, n);               /* Python slice bounds of seq[min:max] (:11002) */
+    out->seq_end = b < 0 ? (b + n < 0 ? 0 : b + n) : py_clip(b, n);
+    if (out->seq_end < out->seq_start) out->seq_end = out->seq_start;
+    return found;
+}

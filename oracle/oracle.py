@@ -210,6 +210,28 @@ class HboQhsp(C.Structure):
     _fields_ = [(f, C.c_int32) for f in ("rank", "contig", "qs", "qe", "ss", "se", "n_match", "aln_len", "score")]
 
 
+class HboPolyaRec(C.Structure):
+    _fields_ = [(f, C.c_int32) for f in ("found", "direct", "end_5", "end_3", "tsd_k", "seq_start", "seq_end")]
+
+
+def search_polyA_TSD(seq, flanking_len):
+    """C restatement of search_polyA_TSD (Util.py:10915) -> (found_TSD, TSD_seq, non_ltr_seq, record dict)."""
+    L = lib()
+    sb = seq if isinstance(seq, (bytes, bytearray)) else seq.encode()
+    r = HboPolyaRec()
+    L.hbo_search_polyA_TSD.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    L.hbo_search_polyA_TSD(sb, len(sb), int(flanking_len), C.byref(r))
+    rec = {f: getattr(r, f) for f, _ in HboPolyaRec._fields_}
+    s = sb.decode()
+    tsd = ""
+    if rec["found"]:
+        tsd = s[rec["end_3"]:rec["end_3"] + rec["tsd_k"]] if rec["direct"] == 1 else s[rec["end_3"] - rec["tsd_k"]:rec["end_3"]]
+    body = s[rec["seq_start"]:rec["seq_end"]] if rec["direct"] else ""
+    if rec["direct"] == 2:
+        body = body[::-1].translate(str.maketrans("ACGT", "TGCA", "")).translate({ord(c): "N" for c in set(body) - set("ACGT")})
+    return bool(rec["found"]), tsd, body, rec
+
+
 class HboLocus(C.Structure):
     _fields_ = [("cand", C.c_uint32), ("rel", C.c_uint32), ("nseeds", C.c_uint32), ("rank", C.c_uint32),
                 ("dmin", C.c_int64), ("dmax", C.c_int64), ("j0", C.c_int64)]
