@@ -374,6 +374,17 @@ def main():
             line["tir_prefilter"] = {"candidates": len(tc), "variants": nrec, "kernel_ms": float(np.mean(ms)),
                                      "candidates_per_s": float(len(tc) / (np.mean(ms) * 1e-3)),
                                      "e2e_candidates_per_s": float(len(tc) / np.mean(wl_s))}
+            # the non-LTR candidate generator's scan (search_polyA_TSD, module/Util.py:10915)
+            ms, wl_s = [], []
+            for it in range(2 + 5):
+                tw = time.perf_counter()
+                pr = ctx.nonltr_candidates(tc, 50)
+                if it >= 2:
+                    wl_s.append(time.perf_counter() - tw)
+                    ms.append(ctx.timing()["kernel_ms"])
+            line["nonltr_prefilter"] = {"candidates": len(tc), "with_tsd": int(pr["found"].sum()), "kernel_ms": float(np.mean(ms)),
+                                        "candidates_per_s": float(len(tc) / (np.mean(ms) * 1e-3)),
+                                        "e2e_candidates_per_s": float(len(tc) / np.mean(wl_s))}
             # known-TE masking of the genome (mask_genome_intactTE, module/Util.py:6389) with
             # the planted families' consensus sequences as the library, and the homology copy search of
             # judge_Other_transposons.py on the same records (get_query_copies chaining)

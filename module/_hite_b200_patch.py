@@ -10,6 +10,9 @@ reference's ``Util`` namespace with the B200 implementations:
     Util.run_find_members_v8     -> hite_b200.boundary.run_find_members_v8
     Util.is_TE_from_align_file   -> hite_b200.boundary.is_TE_from_align_file
     Util.determine_repeat_boundary_v5 -> hite_b200.coarse.determine_repeat_boundary_v5   (coarse_boundary.py)
+    Util.get_candidate_non_ltr_parallel -> hite_b200.nonltr_prefilter.*                  (judge_Non_LTR_transposons.py)
+    Util.multi_process_align_and_get_copies -> hite_b200.other.*                         (judge_Other_transposons.py)
+    Util.mask_genome_with_TE         -> hite_b200.masking.mask_genome_with_TE            (judge_LTR_transposons.py)
 
 Everything else on the stage (TSD pre-filter, cd-hit-est, renaming, prev_TE bookkeeping) stays the
 reference's code.  ``HITE_HOME`` must point at the HiTE checkout.  There is no CPU fallback: if the
@@ -38,7 +41,8 @@ def hite_home():
 
 
 def run_stage(script_name, patch_names=("flank_region_align_v5", "run_find_members_v8", "is_TE_from_align_file"),
-              source="hite_b200.boundary"):
+              source="hite_b200.boundary", extra=()):
+    """``extra``: further (name, source module) pairs to rebind."""
     home = hite_home()
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
@@ -50,6 +54,8 @@ def run_stage(script_name, patch_names=("flank_region_align_v5", "run_find_membe
     import Util  # the reference's own module, unmodified
     for name in patch_names:
         setattr(Util, name, getattr(hb, name))
+    for name, src in extra:
+        setattr(Util, name, getattr(importlib.import_module(src), name))
     target = os.path.join(moddir, script_name)
     sys.argv[0] = target
     runpy.run_path(target, run_name="__main__")

@@ -8,4 +8,4 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from _hite_b200_patch import run_stage  # noqa: E402
 
 if __name__ == "__main__":
-    run_stage("judge_Non_LTR_transposons.py")
+    run_stage("judge_Non_LTR_transposons.py", extra=(("get_candidate_non_ltr_parallel", "hite_b200.nonltr_prefilter"),))

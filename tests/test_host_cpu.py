@@ -227,9 +227,17 @@ def test_drop_in_stage_scripts_patch_the_reference_namespace(monkeypatch, tmp_pa
         import hite_b200.other as ho
         assert U.multi_process_align_and_get_copies is ho.multi_process_align_and_get_copies
         assert ran["path"].endswith("module/judge_TIR_transposons.py")      # setdefault keeps the first; the call itself ran
+        saved["get_candidate_non_ltr_parallel"] = U.get_candidate_non_ltr_parallel
+        saved["mask_genome_with_TE"] = U.mask_genome_with_TE
+        patch.run_stage("judge_Non_LTR_transposons.py", extra=(("get_candidate_non_ltr_parallel", "hite_b200.nonltr_prefilter"),))
+        import hite_b200.nonltr_prefilter as hn
+        assert U.get_candidate_non_ltr_parallel is hn.get_candidate_non_ltr_parallel
+        patch.run_stage("judge_LTR_transposons.py", patch_names=("mask_genome_with_TE",), source="hite_b200.masking")
+        import hite_b200.masking as hm
+        assert U.mask_genome_with_TE is hm.mask_genome_with_TE
     finally:
         for n, f in saved.items():
             setattr(U, n, f)
     for s in ("coarse_boundary.py", "judge_TIR_transposons.py", "judge_Helitron_transposons.py", "judge_Non_LTR_transposons.py",
-              "judge_Other_transposons.py"):
+              "judge_Other_transposons.py", "judge_LTR_transposons.py"):
         assert os.access(os.path.join(ROOT, "module", s), os.X_OK)
