@@ -6,7 +6,7 @@ extern "C" size_t hb_vote_match_entry_size();
 extern "C" size_t hb_vote_state_entries();
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
                                       uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
-                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, cudaStream_t stream);
+                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, int avg_rows, cudaStream_t stream);
 
 static std::string g_last_global_error;
 
@@ -147,7 +147,7 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
     HB_CUDA_OK(hb_vote_launch(ctx->v_tasks.as<HbVoteTask>(), (int)n, ctx->v_raw.as<uint8_t>(), ctx->v_clean.as<uint8_t>(),
                               ctx->v_planes.as<uint32_t>(), ctx->v_matches.p, ctx->buf("v.anchors").as<int>(),
                               ctx->v_cands.as<uint8_t>(), ctx->v_cons.as<uint8_t>(), ctx->v_calls.as<HbVoteCall>(),
-                              te_type, s));
+                              te_type, (int)(row_total / n), s));
     HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
     HB_CUDA_OK(cudaMemcpyAsync(calls, ctx->v_calls.p, sizeof(HbVoteCall) * n, cudaMemcpyDeviceToHost, s));
     HB_CUDA_OK(cudaMemcpyAsync(cons_out, ctx->v_cons.p, cons_total, cudaMemcpyDeviceToHost, s));

@@ -22,7 +22,7 @@ extern "C" size_t hb_vote_match_entry_size();
 extern "C" size_t hb_vote_state_entries();
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
                                       uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
-                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, cudaStream_t stream);
+                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, int avg_rows, cudaStream_t stream);
 
 namespace {
 
@@ -559,7 +559,8 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
         HB_CUDA_OK(hb_vote_launch(LB("v.tasks").as<HbVoteTask>(), (int)n_tasks, LB("m.mat").as<uint8_t>(),
                                   LB("v.clean").as<uint8_t>(), LB("v.planes").as<uint32_t>(), LB("v.matches").p,
                                   LB("v.anchors").as<int>(), LB("c.ascii").as<uint8_t>(),
-                                  LB("v.cons").as<uint8_t>(), LB("v.calls").as<HbVoteCall>(), prm->te_type, s));
+                                  LB("v.cons").as<uint8_t>(), LB("v.calls").as<HbVoteCall>(), prm->te_type,
+                                  (int)(row_total / n_tasks), s));
         HB_CUDA_OK(cudaEventRecord(ln.ev[5], s));
         if (n_tasks > n_full) {
             ENSURE_L("v.t2f", sizeof(uint32_t) * trunc_to_full.size());

@@ -960,14 +960,20 @@ hb_judge_d_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel B': judge_boundary_v6 (Helitron, Util.py:9821-10159), one warp per candidate.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+// kernel B': judge_boundary_v6 (Helitron, Util.py:9821-10159).  Phase a anchors EVERY row (two 20-mers by Myers over the
+// whole row), ~R times the work of the TIR judge's phase a: one CTA of ROW_WARPS warps per candidate, rows dealt round-robin
+// to the warps (one warp per candidate left the GPU a third full at 3 000 candidates and serialised <= 100 row scans).
+// Warp 0 scans into the task's match scratch, warps 1.. into the task's bit-plane area, which phase b only builds later
+// (96 C bytes >= (ROW_WARPS - 1) * 2 (C + 2) * 12 for every MSA width).  Per-row anchors land at an[r] / an[R + r] (-1 =
+// none) and are compacted in row order by warp 0: the mode's tie-break is "first inserted" (:9722-9730).
+constexpr int ROW_WARPS = 4;
+__global__ void __launch_bounds__(ROW_WARPS * 32)
 hb_judge_v6_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
-                     Match* __restrict__ matches, int* __restrict__ anchors, const uint8_t* __restrict__ cands,
-                     HbVoteCall* __restrict__ calls) {
-    __shared__ int s_cnt[WARPS_PER_CTA][2];
+                     uint32_t* __restrict__ planes, Match* __restrict__ matches, int* __restrict__ anchors,
+                     const uint8_t* __restrict__ cands, HbVoteCall* __restrict__ calls) {
+    __shared__ int s_cnt[ROW_WARPS][2];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    const int ti = blockIdx.x;
     if (ti >= n_tasks) return;
     const HbVoteTask t = tasks[ti];
     HbVoteCall call = calls[ti];
@@ -978,24 +984,38 @@ hb_judge_v6_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
     call.flags = 0; call.cons_off = (int64_t)t.cons_off;
     // ---- 1. anchors of ALL rows, then the mode (:9837-9866) ------------------------------------
     int as = -1, ae = -1;
-    if (t.cand_len > 2 && Cc > 0) {
+    const bool scan = t.cand_len > 2 && Cc > 0;
+    int* an = anchors + t.anchor_off;              // [0..R) starts, [R..2R) ends
+    if (scan) {
         const uint8_t* cand = cands + t.cand_off;
         const int alen = min(20, t.cand_len);
         Pattern P1, P2;
         pattern_init(P1, cand, alen);
         pattern_init(P2, cand + (t.cand_len - alen), alen);
-        Match* ml = matches + t.match_off;
-        int* an = anchors + t.anchor_off;          // [0..R) starts, [R..2R) ends
-        int na = 0;
-        for (int r = 0; r < R; ++r) {
+        Match* ml = wid == 0 ? matches + t.match_off
+                             : reinterpret_cast<Match*>(planes + t.plane_off) + (size_t)(wid - 1) * 2 * ((size_t)C + 2);
+        const int nw = C >= 6 ? ROW_WARPS : 1;     // narrower matrices: the plane area cannot hold the extra scratch
+        for (int r = wid; r < R && wid < nw; r += nw) {
             int a = -1, b = -1;
-            if (row_anchor(m + (size_t)r * C, Cc, C + 2, P1, P2, ml, s_cnt[wid], lane, &a, &b)) {
-                if (lane == 0) { an[na] = a; an[R + na] = b; }
-                ++na;
-            }
+            const bool hit = row_anchor(m + (size_t)r * C, Cc, C + 2, P1, P2, ml, s_cnt[wid], lane, &a, &b);
+            if (lane == 0) { an[r] = hit ? a : -1; an[R + r] = hit ? b : -1; }
             __syncwarp();
         }
-        __syncwarp();
+    }
+    __syncthreads();
+    if (wid != 0) return;
+    if (scan) {
+        // rows with both anchors, in row order (in place: a chunk's survivors never land beyond the chunk)
+        int na = 0;
+        for (int r0 = 0; r0 < R; r0 += 32) {
+            const int r = r0 + lane;
+            const int a = r < R ? an[r] : -1, b = r < R ? an[R + r] : -1;
+            const uint32_t bal = __ballot_sync(HB_FULL, a >= 0);
+            __syncwarp();
+            if (a >= 0) { const int pos = na + __popc(bal & lanemask_lt(lane)); an[pos] = a; an[R + pos] = b; }
+            na += __popc(bal);
+            __syncwarp();
+        }
         // most_common_element (:9722-9730): highest count, ties -> first inserted
         for (int which = 0; which < 2; ++which) {
             const int* arr = an + which * R;
@@ -1198,26 +1218,31 @@ hb_judge_v6_c_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
 
 // fuzzysearch.find_near_matches(TSD, kmer, max_l_dist=1) non-empty for |TSD| == |kmer| == k:
 // Hamming <= 1, or TSD minus one symbol equals kmer[1:] / kmer[:-1]
-__device__ bool near1(const uint8_t* ring, int tsd0, const uint8_t* sub, int k0, int k) {
+__device__ __forceinline__ bool near1(const uint8_t* tsd, const uint8_t* kmer, int k) {
     int mm = 0;
-    for (int t = 0; t < k; ++t) mm += (ring[(tsd0 + t) & 63] != sub[k0 + t]);
+    for (int t = 0; t < k; ++t) mm += (tsd[t] != kmer[t]);
     if (mm <= 1) return true;
     for (int which = 0; which < 2; ++which) {
-        const int s0 = k0 + (which == 0 ? 1 : 0);
+        const uint8_t* x = kmer + (which == 0 ? 1 : 0);
         int a = 0;
-        while (a < k - 1 && ring[(tsd0 + a) & 63] == sub[s0 + a]) ++a;
+        while (a < k - 1 && tsd[a] == x[a]) ++a;
         bool ok = true;
-        for (int t = a; t < k - 1; ++t) if (ring[(tsd0 + t + 1) & 63] != sub[s0 + t]) { ok = false; break; }
+        for (int t = a; t < k - 1; ++t) if (tsd[t + 1] != x[t]) { ok = false; break; }
         if (ok) return true;
     }
     return false;
 }
 
-// one row of the per-copy 3'-end / TSD search.  hs0/he: homology boundary columns.
-// returns found; *end5 (new 5' end) and *end3 in ungapped coordinates of the row
-__device__ __noinline__ bool nonltr_row(const uint8_t* __restrict__ row, int Cc, int hs0, int he, int* end5_out, int* end3_out) {
+constexpr int NL_SUB = 52;     // <= 50 symbols before the 5' end (align_seq[left_pos:end_5]), oldest first
+constexpr int NL_TSD = 20;     // the <= 20 symbols from the 3' end on (the TSD source)
+
+// One row of the per-copy 3'-end / TSD search, part 1 (one lane per row): the serial pass over the row -- 5' end, poly-A or
+// tandem 3' end (find_tail_polyA :10832, find_longest_tandem_repeat_tail :9732) -- and the two short symbol windows the TSD
+// search needs, copied to shared memory.  Returns true iff the TSD search has to run (:9632); *avail = symbols available
+// from end_3 on (< 20 only where the row ends).  hs0 / he: homology boundary columns.
+__device__ __noinline__ bool nonltr_row_scan(const uint8_t* __restrict__ row, int Cc, int hs0, int he, int* end5_out, int* end3_out,
+                                             int* sl_out, int* avail_out, uint8_t* sub, uint8_t* tsd) {
     uint8_t ring[64];      // last 64 non-gap symbols, index = ungapped position & 63
-    uint8_t sub[50];       // the <= 50 symbols before column hs0 (align_seq[left_pos:end_5]), oldest first
     int n = 0, end_5 = -1, h3 = -1, sl = 0;
     int run = 0, pa_end = -1;
     bool done = false;
@@ -1261,31 +1286,52 @@ __device__ __noinline__ bool nonltr_row(const uint8_t* __restrict__ row, int Cc,
     }
     *end3_out = end_3;
     *end5_out = end_5;
+    *sl_out = sl;
+    *avail_out = 0;
     if (abs(end_3 - h3) > 10) return false;                                // :9632
     if (end_3 == -1 || end_5 == -1) return false;
-    const int left_pos = max(0, end_5 - 50);
+    // the scan stops 30 symbols past h3, so n >= end_3 + 20 unless the row really ends here; the ring still holds them
+    const int avail = min(NL_TSD, max(0, n - end_3));
+    for (int t = 0; t < avail; ++t) tsd[t] = ring[(end_3 + t) & 63];
+    *avail_out = avail;
+    return true;
+}
+
+// part 2 (the whole warp on one row): TSDs of 20 .. 8 symbols, the window positions spread over the lanes, first hit of the
+// longest length by ballot (:9640-9658).  Returns the hit's end (i + k) or -1.
+__device__ __forceinline__ int nonltr_tsd_search(const uint8_t* sub, int sl, const uint8_t* tsd, int avail, int lane) {
     for (int k = 20; k >= 8; --k) {
-        if (min(k, max(0, n - end_3)) != k) {
-            // the scan stops 30 symbols past h3, so n >= end_3 + 20 unless the row really ends here
-            continue;
-        }
-        for (int i = 0; i + k <= sl; ++i) {
-            if (near1(ring, end_3, sub, i, k)) { *end5_out = left_pos + i + k; return true; }
+        if (avail < k) continue;
+        for (int i0 = 0; i0 + k <= sl; i0 += 32) {
+            const int i = i0 + lane;
+            const bool hit = i + k <= sl && near1(tsd, sub + i, k);
+            const uint32_t bal = __ballot_sync(HB_FULL, hit);
+            if (bal) return i0 + __ffs((int)bal) - 1 + k;
         }
     }
-    return false;
+    return -1;
 }
 
 // ------------------------------------------------------------------------------------------
 // kernel B'': judge_boundary_v9 (non-LTR, Util.py:9483-9720), one warp per candidate.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+// NW = warps per candidate.  The per-copy 3'-end / TSD scan is one serial pass per row, one row per lane: with NW = 4 a
+// candidate's <= 100 rows run as four chunks of 32 side by side (one CTA per candidate); with NW = 1 (batches whose matrices
+// average <= 48 rows: extra warps would only hold warp slots) a CTA judges four candidates, one warp each.
+template <int NW>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
 hb_judge_v9_tail_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
                         uint32_t* __restrict__ planes, Match* __restrict__ matches, uint8_t* __restrict__ cons_buf,
                         HbVoteCall* __restrict__ calls) {
     // phases a, b, c are the TIR judge's kernels (thr_many 0.8, 'fl1' copy number = rows, Util.py:9490-9597)
-    __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
+    constexpr int TPB = ROW_WARPS / NW;                  // candidates per CTA
+    __shared__ unsigned short s_rows[TPB][104];
+    __shared__ int s_part[ROW_WARPS][3];
+    __shared__ int s_ends[TPB][128][2];                  // (end_5, end_3) of every TSD-bearing row
+    __shared__ uint8_t s_sub[ROW_WARPS][32][NL_SUB];
+    __shared__ uint8_t s_tsd[ROW_WARPS][32][NL_TSD];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ti = blockIdx.x * WARPS_PER_CTA + wid;
+    const int slot = wid / NW, sub = wid % NW;
+    const int ti = blockIdx.x * TPB + slot;
     if (ti >= n_tasks) return;
     const HbVoteTask t = tasks[ti];
     const JState* st = jstate_of(matches, t);
@@ -1293,36 +1339,64 @@ hb_judge_v9_tail_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const
     HbVoteCall call = calls[ti];
     const int R = t.R, C = t.C;
     const uint8_t* m = clean + t.clean_off;
-    unsigned short* rows = s_rows[wid];
+    unsigned short* rows = s_rows[slot];
     Front F;
     front_load(F, st, planes, t);
-    for (int k = lane; k < F.row_num; k += 32) rows[k] = st->rows[k];
+    if (sub == 0) for (int k = lane; k < F.row_num; k += 32) rows[k] = st->rows[k];
     __syncwarp();
     const int Cc = F.Cc, row_num = F.row_num, he = F.he;
     int hs = F.hs;
-    // ---- per-copy 3' end + TSD (:9604-9664), all R rows, one row per lane -----------------------
+    // ---- per-copy 3' end + TSD (:9604-9664), all R rows: serial row pass one row per lane, then the TSD search of every
+    // row that needs one by the whole warp ------------------------------------------------------------------------
     int tsd_count = 0;
     int first_nonempty = 0x7fffffff, last_found = -1;    // row indices
-    for (int r0 = 0; r0 < R; r0 += 32) {
+    for (int r0 = 32 * sub; r0 < R; r0 += 32 * NW) {
         const int r = r0 + lane;
-        bool found = false, nonempty = false;
-        if (r < R) {
-            int e5, e3;
-            found = nonltr_row(m + (size_t)r * C, Cc, F.hs, he, &e5, &e3);
-            nonempty = found && (max(e5, e3) > min(e5, e3));
+        bool search = false, found = false;
+        int e5 = -1, e3 = -1, sl = 0, avail = 0;
+        if (r < R) search = nonltr_row_scan(m + (size_t)r * C, Cc, F.hs, he, &e5, &e3, &sl, &avail, s_sub[wid][lane], s_tsd[wid][lane]);
+        __syncwarp();
+        uint32_t todo = __ballot_sync(HB_FULL, search);
+        while (todo) {
+            const int src = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const int sl_s = __shfl_sync(HB_FULL, sl, src), av_s = __shfl_sync(HB_FULL, avail, src);
+            const int end = nonltr_tsd_search(s_sub[wid][src], sl_s, s_tsd[wid][src], av_s, lane);
+            if (lane == src && end >= 0) { found = true; e5 = max(0, e5 - 50) + end; }   // left_pos + i + k (:9654)
         }
+        const bool nonempty = found && (max(e5, e3) > min(e5, e3));
+        if (found && r < 128) { s_ends[slot][r][0] = e5; s_ends[slot][r][1] = e3; }
         const uint32_t bf = __ballot_sync(HB_FULL, found), bn = __ballot_sync(HB_FULL, nonempty);
         tsd_count += __popc(bf);
         if (bf) last_found = r0 + (31 - __clz(bf));
         if (bn && first_nonempty == 0x7fffffff) first_nonempty = r0 + __ffs(bn) - 1;
     }
+    if (NW > 1) {                                        // TPB == 1: the CTA is this candidate's warps
+        if (lane == 0) { s_part[wid][0] = tsd_count; s_part[wid][1] = first_nonempty; s_part[wid][2] = last_found; }
+        __syncthreads();
+        if (sub != 0) return;
+        tsd_count = 0; first_nonempty = 0x7fffffff; last_found = -1;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            tsd_count += s_part[k][0]; first_nonempty = min(first_nonempty, s_part[k][1]); last_found = max(last_found, s_part[k][2]);
+        }
+    } else
+        __syncwarp();
     // homo_boundary_start follows every TSD-bearing row until the first with a non-empty element (:9660-9664)
     const int src_row = (first_nonempty != 0x7fffffff) ? first_nonempty : last_found;
     if (src_row >= 0) {
         const uint8_t* row = m + (size_t)src_row * C;
-        int e5 = 0, e3 = 0;
-        if (lane == 0) nonltr_row(row, Cc, F.hs, he, &e5, &e3);
-        e5 = __shfl_sync(HB_FULL, e5, 0); e3 = __shfl_sync(HB_FULL, e3, 0);
+        int e5, e3;
+        if (src_row < 128) { e5 = s_ends[slot][src_row][0]; e3 = s_ends[slot][src_row][1]; }
+        else {                                           // beyond the stored rows (only via hb_vote_matrices): redo that row
+            int sl = 0, avail = 0, srch = 0;
+            e5 = -1; e3 = -1;
+            if (lane == 0) srch = nonltr_row_scan(row, Cc, F.hs, he, &e5, &e3, &sl, &avail, s_sub[wid][0], s_tsd[wid][0]) ? 1 : 0;
+            __syncwarp();
+            srch = __shfl_sync(HB_FULL, srch, 0); sl = __shfl_sync(HB_FULL, sl, 0); avail = __shfl_sync(HB_FULL, avail, 0);
+            e5 = __shfl_sync(HB_FULL, e5, 0); e3 = __shfl_sync(HB_FULL, e3, 0);
+            if (srch) { const int end = nonltr_tsd_search(s_sub[wid][0], sl, s_tsd[wid][0], avail, lane); if (end >= 0) e5 = max(0, e5 - 50) + end; }
+        }
         const int fbs = min(e5, e3);
         // column of ungapped index fbs
         const int chunk = (Cc + 31) >> 5;
@@ -1354,8 +1428,9 @@ extern "C" size_t hb_vote_state_entries() { return (sizeof(JState) + sizeof(Matc
 
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
                                       uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
-                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, cudaStream_t stream) {
+                                      uint8_t* d_cons, HbVoteCall* d_calls, int te_type, int avg_rows, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
+    static_assert(ROW_WARPS == WARPS_PER_CTA, "the NW = 1 tail kernel shares the one-warp-per-candidate grid");
     hb_clean_kernel<<<n, CLEAN_THREADS, 0, stream>>>(d_tasks, d_raw, d_clean, d_calls);
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (te_type == 0) {
@@ -1365,8 +1440,8 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
         hb_judge_d_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
                                                                    d_calls);
     } else if (te_type == 1) {
-        hb_judge_v6_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_anchors, d_cands,
-                                                                      d_calls);
+        hb_judge_v6_a_kernel<<<n, ROW_WARPS * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_anchors, d_cands,
+                                                               d_calls);
         hb_judge_v6_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls);
         hb_judge_v6_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
                                                                       d_calls);
@@ -1374,8 +1449,12 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
         hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);
         hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 1);
         hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls, 0.8);
-        hb_judge_v9_tail_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
-                                                                         d_calls);
+        if (avg_rows > 48)
+            hb_judge_v9_tail_kernel<ROW_WARPS><<<n, ROW_WARPS * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
+                                                                                 d_cons, d_calls);
+        else
+            hb_judge_v9_tail_kernel<1><<<grid, ROW_WARPS * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
+                                                                            d_cons, d_calls);
     } else
         return cudaErrorInvalidValue;
     return cudaGetLastError();

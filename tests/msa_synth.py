@@ -180,16 +180,19 @@ def synth_case_helitron(seed, scenario=None):
     return dict(cand=cand, rows=rows, plant=1, te_type="helitron", scenario=scen, truth=elem)
 
 
-def synth_case_nonltr(seed, scenario=None):
+def synth_case_nonltr(seed, scenario=None, nrows=None):
     """non-LTR-shaped cases for judge_boundary_v9 (reference Util.py:9483): element with a polyA (or
     short tandem) 3' tail, flanked by 8-20 bp target-site duplications; some copies 5'-truncated."""
     rng = random.Random(seed)
     scen = scenario or rng.choice(["clean", "clean", "clean", "tandem_tail", "trunc5", "no_tsd", "few_rows",
                                    "no_anchor", "fp_homolog_flank", "shift_out", "short"])
     flank = 50
+    nrows_in = nrows
     nrows = rng.randint(4, 30)
     if scen == "few_rows":
         nrows = rng.randint(1, 6)
+    if nrows_in is not None:                      # same random stream as the golden cases, only more rows
+        nrows = nrows_in
     length = rng.randint(120, 400) if scen != "short" else rng.randint(60, 95)
     sub = rng.choice([0.0, 0.02, 0.05])
     dele = rng.choice([0.0, 0.005, 0.01])

@@ -96,3 +96,33 @@ def test_nonltr_vote_matches_oracle_on_fresh_seeds(ctx):
         exp = oracle.judge_v9(c["cand"], oracle.remove_sparse_cols(c["rows"]))
         for k in KEYS + ("homo_start", "homo_end", "align_start", "align_end"):
             assert r[k] == exp[k], (c["scenario"], k, r[k], exp[k])
+
+
+def test_nonltr_vote_many_rows_matches_oracle(ctx):
+    """Matrices of 50-110 rows: the batch average is above 48 rows, so the tail phase runs as one CTA of four warps per
+    candidate (hb_judge_v9_tail_kernel<4>); small-matrix batches (every other non-LTR test) take the one-warp form."""
+    import random
+    rng = random.Random(3)
+    cases = [msa_synth.synth_case_nonltr(s, nrows=rng.randint(50, 110)) for s in range(12000, 12120)]
+    res = ctx.vote_matrices([c["cand"] for c in cases], [c["rows"] for c in cases], "non_ltr", 1)
+    n_te = 0
+    for r, c in zip(res, cases):
+        exp = oracle.judge_v9(c["cand"], oracle.remove_sparse_cols(c["rows"]))
+        for k in KEYS + ("homo_start", "homo_end", "align_start", "align_end"):
+            assert r[k] == exp[k], (c["scenario"], len(c["rows"]), k, r[k], exp[k])
+        n_te += bool(r["is_te"])
+    assert n_te > 30
+
+
+def test_nonltr_vote_beyond_128_rows(ctx):
+    """hb_vote_matrices accepts any number of rows (the pipeline never passes more than 100): the row that sets the 5'
+    boundary may lie beyond the per-candidate table of the tail kernel."""
+    cases = [msa_synth.synth_case_nonltr(s, nrows=n) for s, n in ((13001, 150), (13002, 200), (13003, 131))]
+    for c in cases:                                   # TSD-less rows first, so the first TSD-bearing row comes late
+        rows = c["rows"]
+        c["rows"] = [rows[0]] + ["-" * 50 + r[50:-50] + "-" * 50 for r in rows[1:135]] + rows[135:]
+    res = ctx.vote_matrices([c["cand"] for c in cases], [c["rows"] for c in cases], "non_ltr", 1)
+    for r, c in zip(res, cases):
+        exp = oracle.judge_v9(c["cand"], oracle.remove_sparse_cols(c["rows"]))
+        for k in KEYS + ("homo_start", "homo_end", "align_start", "align_end"):
+            assert r[k] == exp[k], (c["scenario"], len(c["rows"]), k, r[k], exp[k])
