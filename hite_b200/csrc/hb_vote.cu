@@ -1216,54 +1216,67 @@ hb_judge_v6_c_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
 // ------------------------------------------------------------------------------------------
 // non-LTR helpers (Util.py:9604-9664, find_tail_polyA :10832, find_longest_tandem_repeat_tail :9732)
 
-// fuzzysearch.find_near_matches(TSD, kmer, max_l_dist=1) non-empty for |TSD| == |kmer| == k:
-// Hamming <= 1, or TSD minus one symbol equals kmer[1:] / kmer[:-1]
-__device__ __forceinline__ bool near1(const uint8_t* tsd, const uint8_t* kmer, int k) {
-    int mm = 0;
-    for (int t = 0; t < k; ++t) mm += (tsd[t] != kmer[t]);
-    if (mm <= 1) return true;
-    for (int which = 0; which < 2; ++which) {
-        const uint8_t* x = kmer + (which == 0 ? 1 : 0);
-        int a = 0;
-        while (a < k - 1 && tsd[a] == x[a]) ++a;
-        bool ok = true;
-        for (int t = a; t < k - 1; ++t) if (tsd[t + 1] != x[t]) { ok = false; break; }
-        if (ok) return true;
-    }
-    return false;
-}
+constexpr int NL_SUB = 76;     // <= 50 symbols before the 5' end (align_seq[left_pos:end_5]), oldest first; rest = fill 6
+constexpr int NL_TSD = 24;     // the <= 20 symbols from the 3' end on (the TSD source); rest = fill 7
+constexpr int NL_TSD_MAX = 20;
 
-constexpr int NL_SUB = 52;     // <= 50 symbols before the 5' end (align_seq[left_pos:end_5]), oldest first
-constexpr int NL_TSD = 20;     // the <= 20 symbols from the 3' end on (the TSD source)
-
-// One row of the per-copy 3'-end / TSD search, part 1 (one lane per row): the serial pass over the row -- 5' end, poly-A or
-// tandem 3' end (find_tail_polyA :10832, find_longest_tandem_repeat_tail :9732) -- and the two short symbol windows the TSD
-// search needs, copied to shared memory.  Returns true iff the TSD search has to run (:9632); *avail = symbols available
-// from end_3 on (< 20 only where the row ends).  hs0 / he: homology boundary columns.
-__device__ __noinline__ bool nonltr_row_scan(const uint8_t* __restrict__ row, int Cc, int hs0, int he, int* end5_out, int* end3_out,
-                                             int* sl_out, int* avail_out, uint8_t* sub, uint8_t* tsd) {
-    uint8_t ring[64];      // last 64 non-gap symbols, index = ungapped position & 63
+// The per-copy 3'-end / TSD search, part 1, for up to 32 rows (r0 + lane < r_end) at once: the serial pass over each row -- 5'
+// end, poly-A or tandem 3' end (find_tail_polyA :10832, find_longest_tandem_repeat_tail :9732) -- and the two short symbol
+// windows the TSD search needs, copied to shared memory (sub / tsd of this lane).  The rows are walked one lane each, but
+// the matrix is read through a 32 x 128 tile staged in shared memory with coalesced loads (row stride 132: the lanes'
+// byte reads fall in distinct banks) and the 64-symbol history ring lives in shared memory too: read straight from
+// global / local memory every step of the walk touches 32 different cache lines per warp and the kernel is bound by L1
+// wavefronts.  Returns true iff the TSD search has to run for this lane's row (:9632); *avail = symbols available from
+// end_3 on (< 20 only where the row ends).  hs0 / he: homology boundary columns.
+constexpr int NL_TILE = 128, NL_TSTRIDE = 132, NL_RSTRIDE = 68;
+__device__ __noinline__ bool nonltr_rows_scan(const uint8_t* __restrict__ m, int C, int Cc, int r0, int r_end, int hs0, int he,
+                                              int lane, uint8_t* tile, uint8_t* ring_all, int* end5_out, int* end3_out,
+                                              int* sl_out, int* avail_out, uint8_t* sub, uint8_t* tsd) {
+    uint8_t* ring = ring_all + lane * NL_RSTRIDE;      // last 64 non-gap symbols, index = ungapped position & 63
+    const bool active = r0 + lane < r_end;
     int n = 0, end_5 = -1, h3 = -1, sl = 0;
     int run = 0, pa_end = -1;
-    bool done = false;
-    for (int c = 0; c < Cc && !done; ++c) {
-        if (c == hs0) {
-            end_5 = n;
-            sl = min(50, n);
-            for (int t = 0; t < sl; ++t) sub[t] = ring[(n - sl + t) & 63];
+    bool done = !active;
+    const int n_rows = min(32, r_end - r0);
+    for (int c0 = 0; c0 < Cc; c0 += NL_TILE) {
+        if (__all_sync(HB_FULL, done)) break;
+        const int w = min(NL_TILE, Cc - c0);
+        for (int rr = 0; rr < n_rows; ++rr) {
+            const uint8_t* src = m + (size_t)(r0 + rr) * C + c0;
+#pragma unroll
+            for (int z = 0; z < NL_TILE / 32; ++z) {
+                const int cc = z * 32 + lane;
+                if (cc < w) tile[rr * NL_TSTRIDE + cc] = src[cc];
+            }
         }
-        if (c == he) h3 = n;
-        const uint8_t s = row[c];
-        if (s == HB_SYM_GAP) continue;
-        ring[n & 63] = s;
-        ++n;
-        // cur_seq = align_seq[0 : h3 + 10]: A-runs only count while inside it
-        if (h3 < 0 || n <= h3 + 10) {
-            run = (s == 0) ? run + 1 : 0;
-            if (run >= 6) pa_end = n;
+        __syncwarp();
+        const uint8_t* mine = tile + lane * NL_TSTRIDE;
+        for (int cc = 0; cc < w; ++cc) {
+            if (done) continue;
+            const int c = c0 + cc;
+            if (c == hs0) {
+                end_5 = n;
+                sl = min(50, n);
+                for (int t = 0; t < sl; ++t) sub[t] = ring[(n - sl + t) & 63];
+            }
+            if (c == he) h3 = n;
+            const uint8_t s = mine[cc];
+            if (s == HB_SYM_GAP) continue;
+            ring[n & 63] = s;
+            ++n;
+            // cur_seq = align_seq[0 : h3 + 10]: A-runs only count while inside it
+            if (h3 < 0 || n <= h3 + 10) {
+                run = (s == 0) ? run + 1 : 0;
+                if (run >= 6) pa_end = n;
+            }
+            if (h3 >= 0 && n >= h3 + 30) done = true;
         }
-        if (h3 >= 0 && n >= h3 + 30) done = true;
+        __syncwarp();
     }
+    *end3_out = -1; *end5_out = -1; *sl_out = 0; *avail_out = 0;
+    if (!active) return false;
+    for (int t = sl; t < NL_SUB; ++t) sub[t] = 6;      // (sub[0 .. sl) was written when the walk passed column hs0)
+    for (int t = 0; t < NL_TSD; ++t) tsd[t] = 7;
     if (h3 < 0) h3 = n;            // he beyond the last column never happens (he < Cc); keeps the maths defined
     if (end_5 < 0) end_5 = n;
     const int cl = min(n, h3 + 10);
@@ -1287,11 +1300,10 @@ __device__ __noinline__ bool nonltr_row_scan(const uint8_t* __restrict__ row, in
     *end3_out = end_3;
     *end5_out = end_5;
     *sl_out = sl;
-    *avail_out = 0;
     if (abs(end_3 - h3) > 10) return false;                                // :9632
     if (end_3 == -1 || end_5 == -1) return false;
     // the scan stops 30 symbols past h3, so n >= end_3 + 20 unless the row really ends here; the ring still holds them
-    const int avail = min(NL_TSD, max(0, n - end_3));
+    const int avail = min(NL_TSD_MAX, max(0, n - end_3));
     for (int t = 0; t < avail; ++t) tsd[t] = ring[(end_3 + t) & 63];
     *avail_out = avail;
     return true;
@@ -1299,14 +1311,59 @@ __device__ __noinline__ bool nonltr_row_scan(const uint8_t* __restrict__ row, in
 
 // part 2 (the whole warp on one row): TSDs of 20 .. 8 symbols, the window positions spread over the lanes, first hit of the
 // longest length by ballot (:9640-9658).  Returns the hit's end (i + k) or -1.
+// fuzzysearch.find_near_matches(TSD, kmer, max_l_dist=1) is non-empty for |TSD| == |kmer| == k iff Hamming <= 1, or TSD minus
+// one symbol equals kmer[1:] / kmer[:-1].  All 13 lengths are answered from three 20-bit mismatch masks of the position,
+//   M  bit t: tsd[t]     != kmer[t]        M1 bit t: tsd[t] != kmer[t + 1]        M2 bit t: tsd[t + 1] != kmer[t]
+// built four symbols at a time (symbols are bytes < 8: (x ^ y) + 0x7f sets bit 7 of every differing byte, one multiply
+// gathers the four flags): Hamming_k = popc(M & ones(k)); "minus one symbol == kmer[1:]" = M1 clear below a and M clear on
+// (a, k) with a the length of the common prefix; "== kmer[:-1]" = M clear below a and M2 clear on [a, k - 1).
+__device__ __forceinline__ uint32_t diff4(uint32_t x, uint32_t y) {            // 4 flags: byte z of x != byte z of y
+    return (((((x ^ y) + 0x7f7f7f7fu) >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ void diff_masks(const uint32_t* __restrict__ tw, const uint32_t* __restrict__ subw, int i,
+                                           uint32_t& M, uint32_t& M1, uint32_t& M2) {
+    const int j = i >> 2, sh = 8 * (i & 3);
+    uint32_t w[7];
+#pragma unroll
+    for (int z = 0; z < 7; ++z) w[z] = subw[j + z];
+    M = 0; M1 = 0; M2 = 0;
+#pragma unroll
+    for (int z = 0; z < 5; ++z) {
+        const uint32_t k0 = __funnelshift_r(w[z], w[z + 1], sh);               // kmer[4z .. 4z+4)
+        const uint32_t k1 = __funnelshift_r(w[z], w[z + 1], sh + 8);           // kmer[4z+1 .. 4z+5)  (sh + 8 <= 32)
+        const uint32_t k1b = sh == 24 ? w[z + 1] : k1;                         // shift 32 = the next word itself
+        const uint32_t t0 = tw[z];
+        const uint32_t t1 = __funnelshift_r(tw[z], tw[z + 1], 8);              // tsd[4z+1 .. 4z+5)
+        M |= diff4(t0, k0) << (4 * z);
+        M1 |= diff4(t0, k1b) << (4 * z);
+        M2 |= diff4(t1, k0) << (4 * z);
+    }
+}
+__device__ __forceinline__ bool near1_masks(uint32_t M, uint32_t M1, uint32_t M2, int k) {
+    const uint32_t ones = (1u << k) - 1u;
+    if (__popc(M & ones) <= 1) return true;
+    const int a0 = min(__ffs((int)(M1 | (1u << 20))) - 1, k - 1);
+    if (((M >> (a0 + 1)) & ((1u << (k - 1 - a0)) - 1u)) == 0) return true;
+    const int a1 = min(__ffs((int)(M | (1u << 20))) - 1, k - 1);
+    return ((M2 >> a1) & ((1u << (k - 1 - a1)) - 1u)) == 0;
+}
 __device__ __forceinline__ int nonltr_tsd_search(const uint8_t* sub, int sl, const uint8_t* tsd, int avail, int lane) {
-    for (int k = 20; k >= 8; --k) {
-        if (avail < k) continue;
-        for (int i0 = 0; i0 + k <= sl; i0 += 32) {
-            const int i = i0 + lane;
-            const bool hit = i + k <= sl && near1(tsd, sub + i, k);
-            const uint32_t bal = __ballot_sync(HB_FULL, hit);
-            if (bal) return i0 + __ffs((int)bal) - 1 + k;
+    if (avail < 8 || sl < 8) return -1;
+    const uint32_t* subw = reinterpret_cast<const uint32_t*>(sub);
+    const uint32_t* tsw = reinterpret_cast<const uint32_t*>(tsd);
+    uint32_t tw[6];
+#pragma unroll
+    for (int z = 0; z < 6; ++z) tw[z] = tsw[z];
+    // positions 0 .. sl - 8 <= 42: two rounds of 32 lanes
+    uint32_t Ma, M1a, M2a, Mb, M1b, M2b;
+    diff_masks(tw, subw, min(lane, 43), Ma, M1a, M2a);
+    diff_masks(tw, subw, min(32 + lane, 43), Mb, M1b, M2b);
+    for (int k = min(20, avail); k >= 8; --k) {
+        uint32_t bal = __ballot_sync(HB_FULL, lane + k <= sl && near1_masks(Ma, M1a, M2a, k));
+        if (bal) return __ffs((int)bal) - 1 + k;
+        if (32 + k <= sl) {
+            bal = __ballot_sync(HB_FULL, 32 + lane + k <= sl && near1_masks(Mb, M1b, M2b, k));
+            if (bal) return 32 + __ffs((int)bal) - 1 + k;
         }
     }
     return -1;
@@ -1327,8 +1384,10 @@ hb_judge_v9_tail_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const
     __shared__ unsigned short s_rows[TPB][104];
     __shared__ int s_part[ROW_WARPS][3];
     __shared__ int s_ends[TPB][128][2];                  // (end_5, end_3) of every TSD-bearing row
-    __shared__ uint8_t s_sub[ROW_WARPS][32][NL_SUB];
-    __shared__ uint8_t s_tsd[ROW_WARPS][32][NL_TSD];
+    __shared__ __align__(16) uint8_t s_sub[ROW_WARPS][32][NL_SUB];     // rows are read as 32-bit words
+    __shared__ __align__(16) uint8_t s_tsd[ROW_WARPS][32][NL_TSD];
+    __shared__ uint8_t s_tile[ROW_WARPS][32 * NL_TSTRIDE];
+    __shared__ uint8_t s_ring[ROW_WARPS][32 * NL_RSTRIDE];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = wid / NW, sub = wid % NW;
     const int ti = blockIdx.x * TPB + slot;
@@ -1352,9 +1411,10 @@ hb_judge_v9_tail_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const
     int first_nonempty = 0x7fffffff, last_found = -1;    // row indices
     for (int r0 = 32 * sub; r0 < R; r0 += 32 * NW) {
         const int r = r0 + lane;
-        bool search = false, found = false;
+        bool found = false;
         int e5 = -1, e3 = -1, sl = 0, avail = 0;
-        if (r < R) search = nonltr_row_scan(m + (size_t)r * C, Cc, F.hs, he, &e5, &e3, &sl, &avail, s_sub[wid][lane], s_tsd[wid][lane]);
+        const bool search = nonltr_rows_scan(m, C, Cc, r0, R, F.hs, he, lane, s_tile[wid], s_ring[wid], &e5, &e3, &sl, &avail,
+                                             s_sub[wid][lane], s_tsd[wid][lane]);
         __syncwarp();
         uint32_t todo = __ballot_sync(HB_FULL, search);
         while (todo) {
@@ -1389,9 +1449,9 @@ hb_judge_v9_tail_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const
         int e5, e3;
         if (src_row < 128) { e5 = s_ends[slot][src_row][0]; e3 = s_ends[slot][src_row][1]; }
         else {                                           // beyond the stored rows (only via hb_vote_matrices): redo that row
-            int sl = 0, avail = 0, srch = 0;
-            e5 = -1; e3 = -1;
-            if (lane == 0) srch = nonltr_row_scan(row, Cc, F.hs, he, &e5, &e3, &sl, &avail, s_sub[wid][0], s_tsd[wid][0]) ? 1 : 0;
+            int sl = 0, avail = 0;
+            int srch = nonltr_rows_scan(m, C, Cc, src_row, src_row + 1, F.hs, he, lane, s_tile[wid], s_ring[wid], &e5, &e3, &sl, &avail,
+                                        s_sub[wid][lane], s_tsd[wid][lane]) ? 1 : 0;
             __syncwarp();
             srch = __shfl_sync(HB_FULL, srch, 0); sl = __shfl_sync(HB_FULL, sl, 0); avail = __shfl_sync(HB_FULL, avail, 0);
             e5 = __shfl_sync(HB_FULL, e5, 0); e3 = __shfl_sync(HB_FULL, e3, 0);
