@@ -17,6 +17,7 @@ rescue (module/Util.py:8284-8287).
 """
 import os
 import re
+import threading
 import time
 
 from . import _lib
@@ -28,32 +29,92 @@ _GENOME = {}       # device -> (path, mtime, size)
 
 def _device():
     env = os.environ.get("HITE_GPU_DEVICES")
-    if env:
+    if env and env.strip().lower() != "all":
         devs = [int(x) for x in env.split(",") if x.strip() != ""]
         rank = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
         return devs[rank % len(devs)]
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def stage_devices():
+    """The GPUs ONE stage process spreads its candidates over.  Under torchrun (WORLD_SIZE > 1) a rank owns one GPU (its
+    shard comes from hite_b200.dist); a plain stage process -- how main.py runs the stages (main.py:532-628) -- takes every
+    GPU listed in HITE_GPU_DEVICES ("0,1,2,3" or "all"), one context and one host thread per GPU, default GPU 0."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return [_device()]
+    env = os.environ.get("HITE_GPU_DEVICES", "").strip()
+    if env.lower() == "all":
+        return list(range(max(1, _lib.load().hb_device_count())))
+    if env:
+        return [int(x) for x in env.split(",") if x.strip() != ""]
+    return [0]
+
+
+_LOCK = threading.Lock()
+
+
 def get_context(device=None):
     d = _device() if device is None else device
-    if d not in _CTX:
-        _CTX[d] = _lib.Context(d)
-    return _CTX[d]
+    with _LOCK:
+        if d not in _CTX:
+            _CTX[d] = _lib.Context(d)
+        return _CTX[d]
 
 
-def ensure_genome(ctx, reference, k=15, w=10):
-    """Load + index the reference once per process (the analogue of the ``ref.mmi`` existence check,
-    module/Util.py:7938-7947)."""
+def ensure_genome(ctx, reference, k=15, w=10, _parsed=None):
+    """Load + index the reference once per process and GPU (the analogue of the ``ref.mmi`` existence check,
+    module/Util.py:7938-7947).  ``_parsed``: (names, contigs) already read by the caller."""
     st = os.stat(reference)
     key = (os.path.abspath(reference), st.st_mtime_ns, st.st_size, k, w)
     if _GENOME.get(ctx.device) != key:
-        names, contigs = read_fasta(reference)
+        names, contigs = _parsed if _parsed is not None else read_fasta(reference)
         ctx.contig_names = names
         ctx.load_genome([contigs[n].encode("ascii") for n in names])
         ctx.build_index(k, w)
         _GENOME[ctx.device] = key
     return ctx
+
+
+def adjust_on_devices(seqs, reference, TE_type, plant, result_type, flanking_len, devices=None):
+    """One adjust round over ``seqs`` spread over the stage's GPUs: candidates are dealt longest-first to the GPUs
+    (hite_b200.dist.shard_indices, the reference's own longest-processing-time deal, module/Util.py:1771-1798), every
+    GPU holds the whole genome + index, each shard runs on its own context from its own host thread (ctypes releases the
+    GIL inside hb_adjust), and the per-candidate results come back in input order.  No collective: the shards meet in host
+    memory.  Results do not depend on the number of GPUs."""
+    from .dist import shard_indices
+    devices = stage_devices() if devices is None else list(devices)
+    if len(seqs) < 2 * len(devices):
+        devices = devices[:1]
+    lens = [len(s) for s in seqs]
+    shards = [shard_indices(len(seqs), r, len(devices), lens) for r in range(len(devices))]
+    parsed = None
+    st = os.stat(reference)
+    if any(_GENOME.get(d) != (os.path.abspath(reference), st.st_mtime_ns, st.st_size, 15, 10) for d in devices):
+        parsed = read_fasta(reference)                       # read the FASTA once, not once per GPU
+    results = [None] * len(seqs)
+    errors = []
+
+    def work(dev, mine):
+        try:
+            ctx = ensure_genome(get_context(dev), reference, _parsed=parsed)
+            for b in range(0, len(mine), 65536):
+                chunk = mine[b:b + 65536]
+                res = ctx.adjust([seqs[i] for i in chunk], TE_type, int(plant), result_type, flank=int(flanking_len))
+                for i, r in zip(chunk, res):
+                    results[i] = r
+        except Exception as e:                               # surfaced in the caller's thread: no silent partial result
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d, m)) for d, m in zip(devices[1:], shards[1:]) if m]
+    for t in threads:
+        t.start()
+    if shards[0]:
+        work(devices[0], shards[0])
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
 
 
 def _post_filter(names, seqs, results, TE_type):
@@ -83,16 +144,12 @@ def flank_region_align_v5(candidate_sequence_path, real_TEs, flanking_len, refer
         log.logger.info("------Determination of homology in regions outside the boundaries of " + TE_type + " copies")
     starttime = time.time()
     names, contigs = read_fasta(candidate_sequence_path)
-    ctx = ensure_genome(get_context(), reference)
     seqs = [contigs[n] for n in names]
     # HB-align limits: a candidate must be 3..32000 bp (max_repeat_len defaults to 30000, main.py:25)
     ok = [i for i, s in enumerate(seqs) if 3 <= len(s) <= 32000]
     results = [dict(is_te=False, info="", cons="", copy_num=0)] * len(seqs)
     if ok:
-        res = []
-        for b in range(0, len(ok), 65536):
-            chunk = ok[b:b + 65536]
-            res.extend(ctx.adjust([seqs[i] for i in chunk], TE_type, int(plant), result_type, flank=int(flanking_len)))
+        res = adjust_on_devices([seqs[i] for i in ok], reference, TE_type, plant, result_type, flanking_len)
         results = list(results)
         for i, r in zip(ok, res):
             results[i] = r

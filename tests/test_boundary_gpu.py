@@ -76,3 +76,25 @@ def test_run_find_members_v8_on_member_files(tmp_path):
     fasta.store_fasta({"r%d" % i: r for i, r in enumerate(rows)}, af)
     name2, cons2, _, copy2, _ = boundary.is_TE_from_align_file(af, "q", seq.decode(), str(tmp_path), None, 1, "tir", 0, "cons")
     assert (name2, cons2, copy2) == ("q", exp["cons"], exp["copy_num"])
+
+
+def test_stage_process_uses_every_listed_gpu(tmp_path, monkeypatch):
+    """HITE_GPU_DEVICES=0,1: flank_region_align_v5 spreads its candidates over both GPUs (one context + host thread each)
+    and returns exactly what one GPU returns.  Needs a box with >= 2 GPUs (gpurun --gpus 2); skipped on one."""
+    from hite_b200 import _lib
+    if _lib.load().hb_device_count() < 2:
+        pytest.skip("one GPU visible")
+    wl = synth.make_workload(genome_bp=2_000_000, n_contigs=2, n_families=30, cands_per_family=4, seed=17)
+    ref, cand = str(tmp_path / "genome.fa"), str(tmp_path / "cand.fa")
+    wl.write_fasta(ref, cand)
+    outs = []
+    for devs in ("0", "0,1"):
+        monkeypatch.setenv("HITE_GPU_DEVICES", devs)
+        monkeypatch.setattr(boundary, "_CTX", {})
+        monkeypatch.setattr(boundary, "_GENOME", {})
+        out, low = str(tmp_path / ("real_%s.fa" % devs)), str(tmp_path / ("low_%s.fa" % devs))
+        res = boundary.flank_region_align_v5(cand, out, 50, ref, None, "tir", str(tmp_path), 4, 0, _Log, None, 1, 0, 0, low, "cons")
+        outs.append((res, open(out).read(), open(low).read()))
+        assert sorted(boundary._CTX) == [int(x) for x in devs.split(",")]
+    assert outs[0] == outs[1]
+    assert sum(1 for r in outs[0][0] if r["is_te"]) > 60

@@ -241,3 +241,68 @@ def test_drop_in_stage_scripts_patch_the_reference_namespace(monkeypatch, tmp_pa
     for s in ("coarse_boundary.py", "judge_TIR_transposons.py", "judge_Helitron_transposons.py", "judge_Non_LTR_transposons.py",
               "judge_Other_transposons.py", "judge_LTR_transposons.py"):
         assert os.access(os.path.join(ROOT, "module", s), os.X_OK)
+
+
+def test_stage_process_shards_candidates_over_gpus(monkeypatch, tmp_path):
+    """hite_b200.boundary.adjust_on_devices / flank_region_align_v5: one context and host thread per GPU of HITE_GPU_DEVICES,
+    longest-first deal, results back in input order and independent of the GPU count (fake contexts: no GPU here)."""
+    import threading
+    from hite_b200 import boundary, fasta
+    made, calls = [], []
+
+    class FakeCtx:
+        def __init__(self, device):
+            self.device = device
+            self.genome = None
+            made.append(device)
+
+        def load_genome(self, contigs):
+            self.genome = [bytes(c) for c in contigs]
+
+        def build_index(self, k, w):
+            assert self.genome is not None
+
+        def adjust(self, seqs, te_type, plant, result_type, flank=50):
+            calls.append((self.device, threading.get_ident(), list(seqs)))
+            return [dict(is_te=len(s) % 3 != 0, info="", cons=s[2:-2], copy_num=7 + len(s) % 5) for s in seqs]
+
+    monkeypatch.setattr(boundary._lib, "Context", FakeCtx)
+    monkeypatch.setattr(boundary, "_CTX", {})
+    monkeypatch.setattr(boundary, "_GENOME", {})
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    ref = tmp_path / "genome.fa"
+    ref.write_text(">chr1\nACGTACGTAC\n>chr2\nGGGGCCCC\n")
+    cand = tmp_path / "cand.fa"
+    seqs = {"c%d" % i: "ACGT" * (3 + (i * 7) % 11) + "A" * (i % 4) for i in range(23)}
+    fasta.store_fasta(seqs, str(cand))
+    outs = {}
+    for devs in ("0", "0,1,2", "3,1"):
+        monkeypatch.setenv("HITE_GPU_DEVICES", devs)
+        made.clear(); calls.clear()
+        monkeypatch.setattr(boundary, "_CTX", {})
+        monkeypatch.setattr(boundary, "_GENOME", {})
+        assert boundary.stage_devices() == [int(x) for x in devs.split(",")]
+        real, low = str(tmp_path / ("real_%s.fa" % devs)), str(tmp_path / ("low_%s.fa" % devs))
+        res = boundary.flank_region_align_v5(str(cand), real, 50, str(ref), "", "tir", str(tmp_path), 8, 0, None, "", 1, 0, 0, low)
+        outs[devs] = (res, open(real).read(), open(low).read())
+        assert sorted(made) == sorted(int(x) for x in devs.split(","))
+        assert sorted(d for d, _, _ in calls) == sorted(made)                    # one adjust call per GPU
+        if len(made) > 1:
+            assert len({t for _, t, _ in calls}) == len(made)                    # each from its own host thread
+            sizes = sorted(sum(len(s) for s in sq) for _, _, sq in calls)
+            assert sizes[-1] - sizes[0] <= max(len(s) for s in seqs.values())    # longest-first deal balances the bases
+        assert sorted(s for _, _, sq in calls for s in sq) == sorted(seqs.values())
+    assert outs["0"] == outs["0,1,2"] == outs["3,1"]
+    monkeypatch.setenv("WORLD_SIZE", "4"); monkeypatch.setenv("LOCAL_RANK", "1"); monkeypatch.setenv("HITE_GPU_DEVICES", "4,5,6,7")
+    assert boundary.stage_devices() == [5]                                       # under torchrun a rank owns one GPU
+
+    class Boom(FakeCtx):
+        def adjust(self, *a, **k):
+            if self.device == 2:
+                raise RuntimeError("device 2 failed")
+            return FakeCtx.adjust(self, *a, **k)
+    monkeypatch.delenv("WORLD_SIZE"); monkeypatch.setenv("HITE_GPU_DEVICES", "0,1,2")
+    monkeypatch.setattr(boundary._lib, "Context", Boom)
+    monkeypatch.setattr(boundary, "_CTX", {}); monkeypatch.setattr(boundary, "_GENOME", {})
+    with pytest.raises(RuntimeError):                                            # a failing GPU fails the stage loudly
+        boundary.adjust_on_devices(list(seqs.values()), str(ref), "tir", 1, "cons", 50)
