@@ -124,3 +124,31 @@ def test_product_batched_chaining_matches_reference_goldens():
             for g, c in enumerate(sub):
                 got = [[int(o["subj"]), int(o["start"]), int(o["end"]), int(o["qlen"]), "-" if o["strand"] else "+"] for o in out[oq == g]]
                 assert got == c["expect"], c["seed"]
+
+
+def test_product_full_length_copies_fuzz_vs_oracle():
+    """Adversarial HSP lists (tiny coordinate ranges, duplicates, reversed query spans, single-base subjects, mixed strands):
+    product host code == oracle.  The same generator was run against the imported reference in the build container
+    (1 500 cases, thresholds 0.95 / 0.8 / 0.5 / 0.3: reference == oracle == product)."""
+    import random
+    import numpy as np
+    import msa_synth
+    from hite_b200 import _lib
+    for seed in range(600):
+        rng = random.Random(seed)
+        if seed % 2 == 0:
+            c = msa_synth.synth_copy_hsps(70000 + seed)
+            hs, qlen = [tuple(h) for h in c["hsps"]], c["qlen"]
+        else:
+            qlen, nsubj, hs = rng.randint(20, 200), rng.randint(1, 3), []
+            for _ in range(rng.randint(1, 25)):
+                qs, qe = rng.randint(1, qlen), rng.randint(1, qlen)
+                if rng.random() < 0.8 and qs > qe:
+                    qs, qe = qe, qs
+                hs.append((rng.randrange(nsubj), qs, qe, rng.randint(1, 400), rng.randint(1, 400)))
+                if rng.random() < 0.2:
+                    hs.append(hs[-1])
+        thr = rng.choice([0.95, 0.8, 0.5, 0.3])
+        exp = [(g[0], g[1], g[2]) for g in O.full_length_copies_v1(hs, qlen, thr)]
+        got = _lib.full_length_copies(np.array(hs, dtype=_lib.HSP_DTYPE), qlen, thr)
+        assert [(int(g["subj"]), int(g["start"]), int(g["end"])) for g in got] == exp, seed
