@@ -108,6 +108,14 @@ for r in range(world):
 assert merged == exp, (merged, exp)
 empty = hd.allgather_records([] if rank == 0 else [("x", "A")])
 assert empty == [("x", "A")] * (world - 1)
+class FakeCtx:                                                        # sharded_adjust: shard -> adjust -> all-gather of the accepted
+    def adjust(self, seqs, **kw):
+        return [dict(is_te=len(s) %% 8 != 0, cons=s.lower()) for s in seqs]
+got = hd.sharded_adjust(FakeCtx(), names, seqs)
+exp = []
+for r in range(world):
+    exp += [(names[i], seqs[i].lower()) for i in hd.shard_indices(len(seqs), r, world, [len(s) for s in seqs]) if len(seqs[i]) %% 8 != 0]
+assert got == exp, (got, exp)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
@@ -306,3 +314,50 @@ def test_stage_process_shards_candidates_over_gpus(monkeypatch, tmp_path):
     monkeypatch.setattr(boundary, "_CTX", {}); monkeypatch.setattr(boundary, "_GENOME", {})
     with pytest.raises(RuntimeError):                                            # a failing GPU fails the stage loudly
         boundary.adjust_on_devices(list(seqs.values()), str(ref), "tir", 1, "cons", 50)
+
+
+def test_other_and_masking_host_logic_with_fake_context():
+    """hite_b200.other / hite_b200.masking above the C-ABI: record arrays -> reference dict shapes, self hits dropped
+    (module/Util.py:7045), '#' cut and strand dropped before the full-length chaining (:5913-5924, :6351-6354), empty inputs."""
+    import numpy as np
+    from hite_b200 import _lib, masking, other
+
+    class Fake:
+        contig_names = ["chr1", "chr2"]
+        recs = np.zeros(0, dtype=_lib.QHSP_DTYPE)
+
+        def query_hsps(self, seqs, occ_cap=512, max_loci=128):
+            self.n = len(seqs)
+            return self.recs
+
+        def timing(self):
+            return dict(kernel_ms=0.0, k_ms=[0] * 8)
+
+    f = Fake()
+    rec = other.query_hsp_records(f, [], {})
+    assert len(rec) == 0 and other.copies_from_records(rec, [], {}, f.contig_names) == {}
+    assert masking.intervals_from_hsp_records(rec, [], {}) == []
+    contigs = {"a": "AC", "b": "ACGT" * 10}
+    rec = other.query_hsp_records(f, ["a", "b"], contigs)          # "a" is shorter than a seed: never sent
+    assert f.n == 1 and len(rec) == 0 and other.query_hsps(f, ["b"], contigs) == {}
+    r = np.zeros(3, dtype=_lib.QHSP_DTYPE)
+    r["query"] = [0, 0, 1]; r["contig"] = [0, 1, 0]; r["qs"] = 1; r["qe"] = 40
+    r["ss"] = [101, 240, 501]; r["se"] = [140, 201, 540]; r["n_match"] = [40, 39, 40]; r["aln_len"] = 40
+    f.recs = r
+    names = ["x#DNA/TIR", "chr1"]
+    contigs = {"x#DNA/TIR": "ACGT" * 10, "chr1": "ACGT" * 10}
+    rec = other.query_hsp_records(f, names, contigs)
+    assert [tuple(x) for x in rec.tolist()] == [(0, 0, 1, 40, 101, 140, 100.0), (0, 1, 1, 40, 240, 201, 97.5)]   # self hit gone
+    assert other.query_hsps(f, names, contigs) == {"x#DNA/TIR": {"chr1": [(1, 40, 101, 140, 100.0)], "chr2": [(1, 40, 240, 201, 97.5)]}}
+    cps = other.copies_from_records(rec, names, contigs, f.contig_names)
+    assert [c[:3] + c[4:] for c in cps["x#DNA/TIR"]] == [("chr1", 101, 140, "+"), ("chr2", 201, 240, "-")]
+    assert masking.intervals_from_hsp_records(rec, names, contigs) == [("x", 0, 100, 140), ("x", 1, 200, 240)]
+    # a library entry beyond the kernel's query limit is tiled and its coordinates shifted back
+    big = {"big": "A" * 70_000}
+    r = np.zeros(3, dtype=_lib.QHSP_DTYPE)
+    r["query"] = [0, 1, 2]; r["qs"] = 1; r["qe"] = [32000, 32000, 6000]; r["ss"] = [1, 32001, 64001]; r["se"] = [32000, 64000, 70000]
+    r["n_match"] = r["aln_len"] = [32000, 32000, 6000]
+    f.recs = r
+    rec = other.query_hsp_records(f, ["big"], big)
+    assert f.n == 3 and [(int(x["qs"]), int(x["qe"])) for x in rec] == [(1, 32000), (32001, 64000), (64001, 70000)]
+    assert [c[:3] for c in other.copies_from_records(rec, ["big"], big, f.contig_names)["big"]] == [("chr1", 1, 70000)]
