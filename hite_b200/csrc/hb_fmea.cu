@@ -29,14 +29,14 @@ struct Frag { int32_t qs, qe, ss, se; int32_t ord; };      // ord: position befo
 struct Chain { int32_t qs, qe, ss, se, subj; };
 
 // greedy extension inside one subject cluster (module/Util.py:4229-4319)
-struct Key { int32_t chr; int64_t a, b; bool operator==(const Key& o) const { return chr == o.chr && a == o.a && b == o.b; } };
+struct Pt { int32_t chr, da, db, used; };     // one stored point per interval of the de-duplication (see dedup_query)
 // Per-worker scratch, reused across work items: repeated large malloc/free from many threads serialises on
 // the kernel's address-space lock (mmap/munmap), which made the pool anti-scale.
 struct Scratch {
     std::vector<Frag> fw, rv, cl;
     std::vector<char> used;
     std::vector<Chain> chains;
-    std::vector<Key> table;
+    std::vector<Pt> table;
 };
 
 void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Chain>& out, std::vector<char>& used) {
@@ -74,15 +74,6 @@ void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Cha
         out.push_back(ch);
     }
 }
-
-struct KeyHash {
-    size_t operator()(const Key& k) const {
-        uint64_t h = (uint64_t)k.chr * 0x9E3779B97F4A7C15ull;
-        h ^= (uint64_t)k.a + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-        h ^= (uint64_t)k.b + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-        return (size_t)h;
-    }
-};
 
 // chains of one (query, subject) pair: forward clusters, then reverse clusters (module/Util.py:4162-4319)
 void chain_subject(const std::vector<Frag>& frags, int skip_gap, int subj, std::vector<Chain>& chains, Scratch& S) {
@@ -127,59 +118,88 @@ void group_query(const hb_hsp* h, size_t n, int32_t q_index, QueryWork& w) {
     w.chains.resize(w.order.size());
 }
 
+// One point per interval: (chromosome, start decade, end decade).  The reference rounds every interval end down and up to a
+// multiple of 10 and stores all four (start, end) combinations (module/Util.py:4330-4390); two intervals share a key iff
+// their start decades differ by at most one AND their end decades differ by at most one, so one stored point and a look-up of
+// the nine neighbouring decade pairs answers the same question with a table a quarter of the size.
 void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const hb_segment* segs, int max_len,
                  std::vector<hb_interval>& out, Scratch& S) {
     std::vector<Chain>& chains = S.chains;
     chains.clear();
     for (const auto& c : w.chains) chains.insert(chains.end(), c.begin(), c.end());
-    // 10-bp-rounded position de-duplication in visiting order (module/Util.py:4330-4390); the set is a flat
-    // open-addressing table (8 keys per chain, no per-node allocation)
+    // 10-bp-rounded position de-duplication in visiting order; the set is a flat open-addressing table (2 points per chain,
+    // no per-node allocation)
     size_t cap = 64;
-    while (cap < chains.size() * 16 + 16) cap <<= 1;
-    std::vector<Key>& table = S.table;
-    table.assign(cap, Key{-1, 0, 0});
-    KeyHash hasher;
-    auto probe = [&](const Key& k, bool insert) -> bool {       // returns whether k was present
-        size_t i = hasher(k) & (cap - 1);
-        while (table[i].chr != -1) {
-            if (table[i] == k) return true;
+    while (cap < chains.size() * 4 + 16) cap <<= 1;
+    std::vector<Pt>& table = S.table;
+    table.assign(cap, Pt{0, 0, 0, 0});
+    // hashed on (chromosome, start decade) only: the three end decades of a neighbourhood sit in one probe run
+    auto slot_of = [&](int32_t chr, int32_t da) -> size_t {
+        uint64_t h = ((uint64_t)(uint32_t)chr << 32 | (uint32_t)da) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 31;
+        return (size_t)h & (cap - 1);
+    };
+    auto insert = [&](int32_t chr, int32_t da, int32_t db) {
+        size_t i = slot_of(chr, da);
+        while (table[i].used) {
+            if (table[i].chr == chr && table[i].da == da && table[i].db == db) return;
             i = (i + 1) & (cap - 1);
         }
-        if (insert) table[i] = k;
+        table[i] = Pt{chr, da, db, 1};
+    };
+    auto near = [&](int32_t chr, int32_t da, int32_t db) -> bool {
+        for (int x = -1; x <= 1; ++x) {
+            size_t i = slot_of(chr, da + x);
+            while (table[i].used) {
+                if (table[i].chr == chr && table[i].da == da + x && (uint32_t)(table[i].db - db + 1) <= 2u) return true;
+                i = (i + 1) & (cap - 1);
+            }
+        }
         return false;
     };
     struct Iv { int64_t a, b; };
     std::vector<Iv> names;
-    auto round10 = [](int64_t x, int64_t& lo, int64_t& hi) { lo = (x / 10) * 10; hi = lo + 10; };
     for (const Chain& ch : chains) {
         const hb_segment& s = segs[ch.subj];
         const int64_t sa = s.start + (ch.ss - 1), sb = s.start + ch.se;
         const int64_t qa = q.start + (ch.qs - 1), qb = q.start + ch.qe;
-        int64_t sa1, sa2, sb1, sb2, qa1, qa2, qb1, qb2;
-        round10(sa, sa1, sa2); round10(sb, sb1, sb2); round10(qa, qa1, qa2); round10(qb, qb1, qb2);
-        const Key ks[8] = {{s.chr, sa1, sb1}, {s.chr, sa1, sb2}, {s.chr, sa2, sb1}, {s.chr, sa2, sb2},
-                           {q.chr, qa1, qb1}, {q.chr, qa1, qb2}, {q.chr, qa2, qb1}, {q.chr, qa2, qb2}};
-        bool hit = false;
-        for (const Key& k : ks) hit = hit || probe(k, false);
+        const int32_t sda = (int32_t)(sa / 10), sdb = (int32_t)(sb / 10), qda = (int32_t)(qa / 10), qdb = (int32_t)(qb / 10);
+        const bool hit = near(s.chr, sda, sdb) || near(q.chr, qda, qdb);
         const int64_t qlen = std::llabs((long long)ch.qe - (ch.qs - 1));
         if (!hit && qlen >= 80 && qlen < max_len) names.push_back(Iv{qa, qb});
-        for (const Key& k : ks) probe(k, true);
+        insert(s.chr, sda, sdb);
+        insert(q.chr, qda, qdb);
     }
-    // >= 95 % overlap merge, longest first (module/Util.py:4529-4549)
+    // >= 95 % overlap merge, longest first (module/Util.py:4529-4549): interval i removes every later (not longer) interval j
+    // with overlap / len_j >= 0.95.  Such a j starts inside [a_i - 0.05 len_j, b_i), so only the intervals whose start lies in
+    // [a_i - 0.06 len_i - 1, b_i) are looked at (found in a start-sorted index) -- the predicate itself is unchanged.
     std::stable_sort(names.begin(), names.end(), [](const Iv& x, const Iv& y) { return (x.b - x.a) > (y.b - y.a); });
-    std::vector<char> keep(names.size(), 1);
-    for (size_t i = 0; i < names.size(); ++i) {
+    const size_t nn = names.size();
+    std::vector<uint32_t> by_start(nn);
+    for (size_t i = 0; i < nn; ++i) by_start[i] = (uint32_t)i;
+    std::sort(by_start.begin(), by_start.end(), [&](uint32_t x, uint32_t y) { return names[x].a != names[y].a ? names[x].a < names[y].a : x < y; });
+    std::vector<char> keep(nn, 1);
+    for (size_t i = 0; i < nn; ++i) {
         if (!keep[i]) continue;
-        for (size_t j = i + 1; j < names.size(); ++j) {
-            if (!keep[j]) continue;
+        const int64_t len_i = names[i].b - names[i].a;
+        const int64_t lo = names[i].a - (len_i * 6) / 100 - 1;
+        size_t p = (size_t)(std::lower_bound(by_start.begin(), by_start.end(), lo, [&](uint32_t x, int64_t v) { return names[x].a < v; }) - by_start.begin());
+        for (; p < nn && names[by_start[p]].a < names[i].b; ++p) {
+            const size_t j = by_start[p];
+            if (j <= i || !keep[j]) continue;
             const int64_t ov = std::max<int64_t>(0, std::min(names[i].b, names[j].b) - std::max(names[i].a, names[j].a));
             if ((double)ov / (double)(names[j].b - names[j].a) >= 0.95) keep[j] = 0;
         }
     }
-    for (size_t i = 0; i < names.size(); ++i) {
+    // a name can only repeat among the kept intervals of this query (dict keys, :4551-4560)
+    std::vector<std::pair<int64_t, int64_t>> seen;
+    for (size_t i = 0; i < nn; ++i) if (keep[i]) seen.emplace_back(names[i].a, names[i].b);
+    std::sort(seen.begin(), seen.end());
+    const bool has_dup = std::adjacent_find(seen.begin(), seen.end()) != seen.end();
+    for (size_t i = 0; i < nn; ++i) {
         if (!keep[i]) continue;
         bool dup = false;
-        for (const hb_interval& o : out) if (o.start == names[i].a && o.end == names[i].b) { dup = true; break; }
+        if (has_dup) for (const hb_interval& o : out) if (o.start == names[i].a && o.end == names[i].b) { dup = true; break; }
         if (!dup) out.push_back(hb_interval{q.chr, q_index, names[i].a, names[i].b});
     }
 }
