@@ -75,3 +75,20 @@ def search_confident_tir_batch(cur_contigs, flanking_len, plant, ctx=None):
             classes[name] = int(r["short_class"])
         all_contigs.update(d)
     return all_contigs, get_short_tir_contigs(all_contigs, plant, classes)
+
+
+def filter_dup_itr_v3(cur_copies_out_contigs, TIR_len_dict):
+    """reference module/Util.py:2791-2812: of one candidate's TSD-bounded variants keep the one closest to the raw boundaries
+    (first among equals, in the dict's order), renamed ``<query>-tir_<len>-tsd_<tsd>``; nothing if it is 30 000 bp or longer.
+    Host-side selection only (one string split per variant)."""
+    best_name, best_dist = "", 100000
+    for name in cur_copies_out_contigs:
+        dist = int(name.split("-distance_")[1])
+        if dist < best_dist:
+            best_name, best_dist = name, dist
+    query, rest = best_name.split("-C_")[0], best_name.split("-C_")[1]
+    tsd = rest.split("-tsd_")[1].split("-")[0]
+    seq = cur_copies_out_contigs[best_name]
+    if len(seq) >= 30_000:
+        return {}
+    return {"%s-tir_%d-tsd_%s" % (query, TIR_len_dict.get(best_name, 0), tsd): seq}

@@ -92,3 +92,31 @@ def test_host_short_tir_rule_matches_reference_goldens(golden_tsd):
         assert got == exp, case["seed"]
         kept += len(short)
     assert kept > 20
+
+
+def test_filter_dup_itr_v3_mirror():
+    """hite_b200.tir_prefilter.filter_dup_itr_v3 (reference module/Util.py:2791): fixed cases, and -- where the reference
+    checkout is mounted -- a seeded fuzz against the imported function (first-among-equals, missing TIR length, 30 kbp cut,
+    the IndexError when every distance is >= 100000)."""
+    import random
+    from hite_b200 import tir_prefilter as TP
+    d = {"chr1:5-900-C_3-tsd_TA-distance_4": "A" * 500, "chr1:5-900-C_0-tsd_TTAA-distance_1": "C" * 400,
+         "chr1:5-900-C_1-tsd_ACGTACGTA-distance_1": "G" * 300}
+    assert TP.filter_dup_itr_v3(d, {"chr1:5-900-C_0-tsd_TTAA-distance_1": 13}) == {"chr1:5-900-tir_13-tsd_TTAA": "C" * 400}
+    assert TP.filter_dup_itr_v3(d, {}) == {"chr1:5-900-tir_0-tsd_TTAA": "C" * 400}
+    assert TP.filter_dup_itr_v3({"q-C_0-tsd_TA-distance_0": "A" * 30_000}, {}) == {}
+    with pytest.raises(IndexError):
+        TP.filter_dup_itr_v3({"q-C_0-tsd_TA-distance_100000": "A" * 300}, {})
+    from oracle import ref_import
+    if not ref_import.available():
+        return
+    U = ref_import.load_util()
+    rng = random.Random(1)
+    for _ in range(500):
+        q = "chr%d:%d-%d" % (rng.randint(1, 5), rng.randint(0, 10 ** 6), rng.randint(0, 10 ** 6))
+        d = {}
+        for i in rng.sample(range(100), rng.randint(1, 12)):
+            tsd = "".join(rng.choice("ACGT") for _ in range(rng.choice([2, 3, 4, 8, 9, 10, 11])))
+            d["%s-C_%d-tsd_%s-distance_%d" % (q, i, tsd, rng.choice([0, 1, 2, 3, 5, 8, 50]))] = "A" * rng.choice([120, 900, 29_999, 30_000])
+        tl = {n: rng.randint(7, 40) for n in d if rng.random() < 0.6}
+        assert TP.filter_dup_itr_v3(dict(d), dict(tl)) == U.filter_dup_itr_v3(dict(d), dict(tl))
