@@ -1,0 +1,90 @@
+"""The homology non-LTR stage end to end on the CPU: the REFERENCE's own run_Other_detection (module/judge_Other_transposons.py:
+32-83, imported unmodified) consumes hite_b200.other.multi_process_align_and_get_copies exactly as the drop-in stage script
+wires it (module/judge_Other_transposons.py in this repo), with the GPU context replaced by a stand-in whose HSPs come from the
+oracle.  What is checked is the boundary: the mirror's return value drives the reference's longest-copy selection, length
+filter, store_fasta and rename_fasta into the confident_other.fa the reference would write.  Needs the reference checkout and
+its shipped library/non_LTR.lib (skipped on the GPU box)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference checkout not mounted")
+
+_B = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = {"A": "T", "C": "G", "G": "C", "T": "A"}
+
+
+def test_run_other_detection_consumes_the_mirror(tmp_path, monkeypatch):
+    from hite_b200 import _lib, boundary, fasta, other
+    U = ref_import.load_util()
+    lib_names, lib = fasta.read_fasta(os.path.join(ref_import.REF_ROOT, "library", "non_LTR.lib"))
+    assert len(lib_names) > 5000
+    # a genome holding copies of a few library entries: two full-length copies (one reverse), one 60 % fragment
+    rng = np.random.default_rng(8)
+    chosen = [n for n in lib_names if 400 <= len(lib[n]) <= 3000 and set(lib[n]) <= set("ACGT")][::97][:12]
+    contigs = [bytearray(_B[rng.integers(0, 4, 300_000)].tobytes()) for _ in range(2)]
+    planted, pos = {}, 5_000
+    for k, name in enumerate(chosen):
+        s = lib[name]
+        rc = "".join(_COMP[b] for b in reversed(s))
+        c = k % 2
+        for piece in (s, rc, s[: int(0.6 * len(s))]):
+            contigs[c][pos:pos + len(piece)] = piece.encode()
+            planted.setdefault(name, []).append((c, pos + 1, pos + len(piece)))
+            pos += len(piece) + 1_000
+    names = ["chr_0", "chr_1"]
+    gpath = str(tmp_path / "genome.fa")
+    fasta.store_fasta({n: bytes(c).decode() for n, c in zip(names, contigs)}, gpath)
+
+    G = O.Genome([bytes(c) for c in contigs])
+
+    class OracleBackedCtx:                       # stands in for _lib.Context: same record layout, HSPs from the oracle
+        device = 0
+        contig_names = names
+
+        def query_hsps(self, seqs, occ_cap=512, max_loci=128):
+            rows = []
+            for qi, q in enumerate(seqs):
+                for h in G.query_hsps(q, occ_cap, max_loci):
+                    rows.append((qi, h["contig"], h["qs"], h["qe"], h["ss"], h["se"], h["n_match"], h["aln_len"], h["score"], h["rank"]))
+            return np.array(rows, dtype=_lib.QHSP_DTYPE) if rows else np.zeros(0, dtype=_lib.QHSP_DTYPE)
+
+        def timing(self):
+            return dict(kernel_ms=0.0, k_ms=[0.0] * 8)
+
+    ctx = OracleBackedCtx()
+    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "ensure_genome", lambda c, ref, k=15, w=10, _parsed=None: c)
+    # wire it the way module/_hite_b200_patch.run_stage does, then import the reference's stage module
+    monkeypatch.setattr(U, "multi_process_align_and_get_copies", other.multi_process_align_and_get_copies)
+    moddir = os.path.join(ref_import.REF_ROOT, "module")
+    monkeypatch.syspath_prepend(moddir)
+    sys.modules.pop("judge_Other_transposons", None)
+    stage = importlib.import_module("judge_Other_transposons")
+    assert stage.multi_process_align_and_get_copies is other.multi_process_align_and_get_copies
+    out_dir = str(tmp_path / "out")
+    os.makedirs(out_dir)
+    stage.run_Other_detection(out_dir, gpath, 4, 80, False, None)
+    sys.modules.pop("judge_Other_transposons", None)
+    G.close()
+
+    got_names, got = fasta.read_fasta(os.path.join(out_dir, "confident_other.fa"))
+    # rename_fasta (:7500): sequential names, class kept.  Library relatives of a planted entry (e.g. the ACASINE2 family) also
+    # reach 95 % coverage on its copies and are reported too, exactly as with BLAST.
+    assert len(got_names) >= len(chosen) >= 8
+    assert [n.split("#")[0] for n in got_names] == ["Homology_Non_LTR_%d" % i for i in range(len(got_names))]
+    genome = {n: bytes(c).decode() for n, c in zip(names, contigs)}
+    for name in chosen:
+        cls = name.split("#")[1]
+        spans = planted[name][:2]                 # the two full-length plants; the 60 % fragment must never be the answer
+        # the longest copy, sliced from the genome as the reference does (:62-66)
+        hits = [n for n in got_names if n.split("#")[1] == cls and
+                any(abs(len(got[n]) - (b - a + 1)) <= 4 and got[n] in genome[names[c]][a - 9:b + 8] for c, a, b in spans)]
+        assert hits, (name, [len(got[n]) for n in got_names if n.split("#")[1] == cls])
+    assert all(len(s) >= 80 for s in got.values())                           # min_TE_len filter (:78-81)
