@@ -122,17 +122,20 @@ void group_query(const hb_hsp* h, size_t n, int32_t q_index, QueryWork& w) {
 // multiple of 10 and stores all four (start, end) combinations (module/Util.py:4330-4390); two intervals share a key iff
 // their start decades differ by at most one AND their end decades differ by at most one, so one stored point and a look-up of
 // the nine neighbouring decade pairs answers the same question with a table a quarter of the size.
+// `file_chains`: chains of ALL the query records that share this query's BLAST result file (the reference creates
+// chr_pos_candidates once per file, module/Util.py:4155); `first_of_file`: this is the file's first query, the table starts empty.
 void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const hb_segment* segs, int max_len,
-                 std::vector<hb_interval>& out, Scratch& S) {
+                 std::vector<hb_interval>& out, Scratch& S, size_t file_chains, bool first_of_file) {
     std::vector<Chain>& chains = S.chains;
     chains.clear();
     for (const auto& c : w.chains) chains.insert(chains.end(), c.begin(), c.end());
     // 10-bp-rounded position de-duplication in visiting order; the set is a flat open-addressing table (2 points per chain,
     // no per-node allocation)
     size_t cap = 64;
-    while (cap < chains.size() * 4 + 16) cap <<= 1;
+    while (cap < file_chains * 4 + 16) cap <<= 1;
     std::vector<Pt>& table = S.table;
-    table.assign(cap, Pt{0, 0, 0, 0});
+    if (first_of_file) table.assign(cap, Pt{0, 0, 0, 0});
+    else cap = table.size();
     // hashed on (chromosome, start decade) only: the three end decades of a neighbourhood sit in one probe run
     auto slot_of = [&](int32_t chr, int32_t da) -> size_t {
         uint64_t h = ((uint64_t)(uint32_t)chr << 32 | (uint32_t)da) * 0x9E3779B97F4A7C15ull;
@@ -210,7 +213,7 @@ void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const
 // Three phases over a thread pool: group per query, chain per (query, subject) pair (the bulk of the work,
 // 10^4 independent items for a 100-segment chunk), order-dependent de-duplication per query.
 int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
-                int max_len, int threads, std::vector<hb_interval>& result) {
+                int max_len, int threads, std::vector<hb_interval>& result, const uint32_t* file_of_seg) {
     std::vector<QueryWork> work(n_seg);
     std::vector<std::vector<hb_interval>> per(n_seg);
     const int nt = std::max(1, threads);
@@ -248,8 +251,34 @@ int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const 
         chain_subject(w.per[k], skip_gap, w.order[k], w.chains[k], S);
     });
     lap("chain");
-    run_pool(n_seg, [&](size_t g, Scratch& S) {
-        if (!work[g].order.empty()) dedup_query(work[g], segs[g], (int32_t)g, segs, max_len, per[g], S);
+    // de-duplication per BLAST result FILE: the query records of one file share the rounded-position table and the file's
+    // name dict, in record order (file_of_seg: non-decreasing file id per segment; NULL = one record per file)
+    std::vector<std::pair<uint32_t, uint32_t>> files;           // [first, last) segment of every file
+    for (uint32_t g = 0; g < n_seg;) {
+        uint32_t e = g + 1;
+        while (file_of_seg && e < n_seg && file_of_seg[e] == file_of_seg[g]) ++e;
+        files.emplace_back(g, e);
+        g = e;
+    }
+    run_pool(files.size(), [&](size_t f, Scratch& S) {
+        const uint32_t g0 = files[f].first, g1 = files[f].second;
+        size_t file_chains = 0;
+        for (uint32_t g = g0; g < g1; ++g) for (const auto& c : work[g].chains) file_chains += c.size();
+        bool first = true;
+        for (uint32_t g = g0; g < g1; ++g) {
+            if (work[g].order.empty()) continue;
+            dedup_query(work[g], segs[g], (int32_t)g, segs, max_len, per[g], S, file_chains, first);
+            first = false;
+            // longest_repeats is one dict per file (:4152): a name an earlier record of the file produced is not repeated
+            if (g > g0) {
+                auto& mine = per[g];
+                mine.erase(std::remove_if(mine.begin(), mine.end(), [&](const hb_interval& x) {
+                    for (uint32_t p = g0; p < g; ++p)
+                        for (const hb_interval& o : per[p]) if (o.chr == x.chr && o.start == x.start && o.end == x.end) return true;
+                    return false;
+                }), mine.end());
+            }
+        }
     });
     lap("dedup");
     result.clear();

@@ -7,7 +7,7 @@
 #include "../../include/hite_b200.h"
 
 int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
-                int max_len, int threads, std::vector<hb_interval>& result);
+                int max_len, int threads, std::vector<hb_interval>& result, const uint32_t* file_of_seg = nullptr);
 int hb_query_copies_run(const hb_hsp* h, const double* ident, size_t n, int query_len, const int32_t* subj_len,
                         double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
                         std::vector<hb_query_copy>& result);

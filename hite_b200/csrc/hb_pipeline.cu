@@ -855,6 +855,20 @@ extern "C" int hb_fmea_chain(const hb_hsp* hsp, const uint64_t* q_off, uint32_t 
     return HB_OK;
 }
 
+extern "C" int hb_fmea_chain_files(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs,
+                                   const uint32_t* file_of_seg, int skip_gap, int max_len, int threads, hb_interval* out,
+                                   uint64_t cap, uint64_t* n_out) {
+    if (!q_off || !segs || !n_out || !file_of_seg || (n_seg && q_off[n_seg] && !hsp)) return HB_EINVAL;
+    for (uint32_t g = 1; g < n_seg; ++g) if (file_of_seg[g] < file_of_seg[g - 1]) return HB_EINVAL;
+    std::vector<hb_interval> res;
+    hb_fmea_run(hsp, q_off, n_seg, segs, skip_gap, max_len, threads, res, file_of_seg);
+    *n_out = res.size();
+    if (!out) return HB_OK;
+    if (cap < res.size()) return HB_EINVAL;
+    if (!res.empty()) memcpy(out, res.data(), sizeof(hb_interval) * res.size());
+    return HB_OK;
+}
+
 extern "C" int hb_query_copies(const hb_hsp* hsp, const double* ident, uint32_t n, int query_len, const int32_t* subj_len,
                                double query_coverage, double subject_coverage, int qthr, int sthr, int max_copy_num,
                                hb_query_copy* out, uint32_t cap, uint32_t* n_out) {
@@ -1094,7 +1108,21 @@ extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, in
     ctx->last_segs = segs;
     auto t0 = std::chrono::steady_clock::now();
     std::vector<hb_interval> res;
-    hb_fmea_run(ctx->last_hsps.data(), ctx->last_hsp_off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, res);
+    // BLAST result files of the reference: split_and_store_sequences packs the segment records into a file until it holds
+    // >= 1 000 000 bases (module/Util.py:4737, :4987-5012), so a contig's short tail shares a file -- and FMEA's
+    // de-duplication state -- with the records that follow it
+    std::vector<uint32_t> file_of_seg((size_t)n_seg);
+    {
+        uint32_t f = 0;
+        uint64_t count = 0;
+        for (int g = 0; g < n_seg; ++g) {
+            file_of_seg[(size_t)g] = f;
+            count += std::min<uint64_t>((uint64_t)seg_len, ctx->g_glen[(size_t)segs[(size_t)g].chr] - (uint64_t)segs[(size_t)g].start);
+            if (count >= 1000000ull) { ++f; count = 0; }
+        }
+    }
+    hb_fmea_run(ctx->last_hsps.data(), ctx->last_hsp_off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, res,
+                file_of_seg.data());
     tm.k_ms[3] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     tm.k_ms[6] = (float)h_recs.size();
     tm.k_ms[7] = (float)((double)n_pairs * 1e-6);

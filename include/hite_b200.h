@@ -199,6 +199,14 @@ typedef struct { int32_t chr, qseg; int64_t start, end; } hb_interval; /* 'chr:s
  */
 int hb_fmea_chain(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
                   int max_len, int threads, hb_interval* out, uint64_t cap, uint64_t* n_out);
+/* The same with the reference's BLAST result files made explicit: the reference packs the segment records into query files of
+ * >= 1 000 000 bases (split_and_store_sequences, module/Util.py:4737, :4987-5012) and get_longest_repeats_v4 keeps ONE
+ * rounded-position dict and ONE name dict per file (:4152-4155), so the records of a file -- a contig's short tail segment and
+ * whatever follows it -- de-duplicate against each other.  file_of_seg[g] = file of segment g (non-decreasing).
+ * hb_fmea_chain is the case "one record per file"; hb_coarse_boundary derives the files from its segment lengths. */
+int hb_fmea_chain_files(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs,
+                        const uint32_t* file_of_seg, int skip_gap, int max_len, int threads, hb_interval* out,
+                        uint64_t cap, uint64_t* n_out);
 
 /*
  * hb_query_copies -- get_query_copies (module/Util.py:6828-7030; used by judge_Other_transposons.py:45 through

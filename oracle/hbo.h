@@ -72,6 +72,12 @@ int hbo_fmea(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_s
              const int32_t *subj_chr, const int64_t *subj_seg_start, int n_subj,
              int skip_gap, int max_len, hbo_interval *out, int cap);
 
+void *hbo_fmea_set_new(void);
+void hbo_fmea_set_free(void *set);
+int hbo_fmea_shared(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_subj,
+                    const int32_t *subj_chr, const int64_t *subj_seg_start, int n_subj,
+                    int skip_gap, int max_len, void *shared_set, hbo_interval *out, int cap);
+
 /* ---- HB-hsp restatement (hbo_hsp.c) ---- */
 typedef struct { int32_t qseg, subj, qs, qe, ss, se; } hbo_hsp_rec;
 uint64_t hbo_self_hsps(const uint64_t *mm_pos, const uint64_t *idx, uint64_t n, uint64_t tot, int k,

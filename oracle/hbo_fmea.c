@@ -109,9 +109,30 @@ static int cmp_len_desc(const void *x, const void *y) {      /* sort by length d
     return (p->order > q->order) - (p->order < q->order);
 }
 
+/* chr_pos_candidates is created once per BLAST result FILE (:4155), i.e. it is shared by all the query records of one split
+   file (split_and_store_sequences :4987: records are packed into a file until it holds >= 1 000 000 bases, so a contig's
+   short tail segment shares a file with the records that follow it).  `shared` carries that dict from one query of a file to
+   the next; NULL = a file with this single query. */
+void *hbo_fmea_set_new(void) {
+    set_t *s = (set_t *)malloc(sizeof(set_t));
+    s->cap = 1024; s->n = 0; s->t = (key_t *)calloc(s->cap, sizeof(key_t));
+    return s;
+}
+void hbo_fmea_set_free(void *p) { if (p) { free(((set_t *)p)->t); free(p); } }
+
+int hbo_fmea_shared(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_subj,
+                    const int32_t *subj_chr, const int64_t *subj_seg_start, int n_subj,
+                    int skip_gap, int max_len, void *shared, hbo_interval *out, int cap);
+
 int hbo_fmea(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_subj,
              const int32_t *subj_chr, const int64_t *subj_seg_start, int n_subj,
              int skip_gap, int max_len, hbo_interval *out, int cap) {
+    return hbo_fmea_shared(h, n, q_chr, q_seg_start, self_subj, subj_chr, subj_seg_start, n_subj, skip_gap, max_len, NULL, out, cap);
+}
+
+int hbo_fmea_shared(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_subj,
+                    const int32_t *subj_chr, const int64_t *subj_seg_start, int n_subj,
+                    int skip_gap, int max_len, void *shared, hbo_interval *out, int cap) {
     /* subjects in first-appearance order (:4140-4147) */
     int *order = (int *)malloc(sizeof(int) * (size_t)(n_subj + 1));
     int *seen = (int *)calloc((size_t)n_subj + 1, sizeof(int));
@@ -152,7 +173,9 @@ int hbo_fmea(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_s
         }
     }
     /* position de-duplication (:4330-4390) */
-    set_t set; set.cap = 1024; set.n = 0; set.t = (key_t *)calloc(set.cap, sizeof(key_t));
+    set_t own; own.cap = 1024; own.n = 0; own.t = shared ? NULL : (key_t *)calloc(own.cap, sizeof(key_t));
+    set_t *setp = shared ? (set_t *)shared : &own;
+#define set (*setp)
     iv_t *names = (iv_t *)malloc(sizeof(iv_t) * (size_t)(nlq + 1));
     int nn = 0;
     for (int r = 0; r < nlq; ++r) {
@@ -193,7 +216,8 @@ int hbo_fmea(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int self_s
         if (no < cap) { out[no].chr = q_chr; out[no].start = names[i].a; out[no].end = names[i].b; }
         ++no;
     }
-    free(keep); free(names); free(set.t); free(lq); free(fw); free(rv); free(cl); free(order); free(seen);
+#undef set
+    free(keep); free(names); free(own.t); free(lq); free(fw); free(rv); free(cl); free(order); free(seen);
     return no;
 }
 

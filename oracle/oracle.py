@@ -121,10 +121,11 @@ class HboInterval(C.Structure):
     _fields_ = [("chr", C.c_int32), ("pad", C.c_int32), ("start", C.c_int64), ("end", C.c_int64)]
 
 
-def fmea(query, subjects, self_subj, hsps, skip_gap, max_len):
-    """get_longest_repeats_v4 for one query segment -> ['chr:start-end', ...] in the reference's order."""
-    chr_ids = {}
-    for name in [query[0]] + [s[0] for s in subjects]:
+def fmea(query, subjects, self_subj, hsps, skip_gap, max_len, shared=None):
+    """get_longest_repeats_v4 for one query segment -> ['chr:start-end', ...] in the reference's order.  ``shared``: a handle
+    from ``fmea_file_state()`` carrying chr_pos_candidates from one query record of a BLAST result file to the next."""
+    chr_ids = shared["chr_ids"] if shared is not None else {}
+    for name in [s[0] for s in subjects] + [query[0]]:
         chr_ids.setdefault(name, len(chr_ids))
     n = len(hsps)
     arr = (HboHsp * max(1, n))(*[HboHsp(*h) for h in hsps])
@@ -133,10 +134,43 @@ def fmea(query, subjects, self_subj, hsps, skip_gap, max_len):
     cap = n + 8
     out = (HboInterval * cap)()
     L = lib()
-    L.hbo_fmea.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                           C.c_int, C.c_void_p, C.c_int]
-    k = L.hbo_fmea(arr, n, chr_ids[query[0]], query[1], self_subj, sc, so, len(subjects), skip_gap, max_len, out, cap)
+    L.hbo_fmea_shared.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    k = L.hbo_fmea_shared(arr, n, chr_ids[query[0]], query[1], self_subj, sc, so, len(subjects), skip_gap, max_len,
+                          shared["set"] if shared is not None else None, out, cap)
     return ["%s:%d-%d" % (query[0], out[i].start, out[i].end) for i in range(k)]
+
+
+class fmea_file_state:
+    """chr_pos_candidates of one BLAST result file (module/Util.py:4155): shared by the query records of that file."""
+
+    def __init__(self):
+        L = lib()
+        L.hbo_fmea_set_new.restype = C.c_void_p
+        L.hbo_fmea_set_free.argtypes = [C.c_void_p]
+        self._L = L
+        self.d = {"set": C.c_void_p(L.hbo_fmea_set_new()), "chr_ids": {}}
+
+    def __getitem__(self, k):
+        return self.d[k]
+
+    def close(self):
+        if self.d["set"]:
+            self._L.hbo_fmea_set_free(self.d["set"])
+            self.d["set"] = None
+
+
+def split_file_groups(seg_lens, base_threshold=1_000_000):
+    """split_and_store_sequences (module/Util.py:4987-5012): records are packed into one file until it holds at least
+    ``base_threshold`` bases -> group id per record."""
+    groups, g, count = [], 0, 0
+    for ln in seg_lens:
+        groups.append(g)
+        count += ln
+        if count >= base_threshold:
+            g += 1
+            count = 0
+    return groups
 
 
 class HboCopyOut(C.Structure):
@@ -350,13 +384,26 @@ class Genome:
                         goff.ctypes.data, len(segs), occ_cap, recs.ctypes.data, n)
         recs = recs[:n]
         intervals = []
+        # the query records of one split file share chr_pos_candidates and the file's longest_repeats dict (:4152-4155)
+        seg_lens = [min(seg_len, contig_lens[c] - o) for c, o in segs]
+        groups = split_file_groups(seg_lens)
+        state, cur_group, file_names = None, -1, set()
         for g, (qc, qo) in enumerate(segs):
+            if groups[g] != cur_group:
+                if state is not None:
+                    state.close()
+                state, cur_group, file_names = fmea_file_state(), groups[g], set()
             mine = recs[recs[:, 0] == g]
             if len(mine) == 0:
                 continue
             hs = [(int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5])) for r in mine]
-            names = fmea(("c%d" % qc, qo), [("c%d" % c, o) for c, o in segs], g, hs, skip_gap, max_len)
+            names = fmea(("c%d" % qc, qo), [("c%d" % c, o) for c, o in segs], g, hs, skip_gap, max_len, shared=state)
             for nm in names:
+                if nm in file_names:
+                    continue
+                file_names.add(nm)
                 a, b = nm.split(":")[1].split("-")
                 intervals.append((qc, int(a), int(b)))
+        if state is not None:
+            state.close()
         return recs, segs, intervals

@@ -1,0 +1,111 @@
+"""The coarse-boundary stage end to end on the CPU, reference against mirror, on the same HSPs.
+
+The REFERENCE's own determine_repeat_boundary_v5 (module/Util.py:4637-4669, imported unmodified) runs its segment files,
+process pools, get_longest_repeats_v4 (FMEA) and generate_final_result.  Only its externals are replaced: the trf tandem filter
+passes the chunk through, and the per-pair blastn (sequence2sequenceBlastn, :4068) writes the oracle's HSPs of that query file
+in outfmt 6.  The MIRROR hite_b200.coarse.determine_repeat_boundary_v5 runs with a stand-in context whose intervals are
+the oracle's HSPs chained by the product's host FMEA.  Both must write the same longest_repeats records ('chr:start-end' names and sequences): this pins the segment
+naming (chr$start), the coordinate conventions between HSPs and interval names and the final slicing on the reference's own
+code, and runs the reference's FMEA itself on a realistic HSP set.  Needs the reference checkout (skipped on the GPU box)."""
+import os
+
+import numpy as np
+import pytest
+
+from hite_b200 import synth
+from oracle import oracle as O
+from oracle import ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference checkout not mounted")
+
+
+def _fake_blastn(query_path, target_path):
+    """Stand-in for sequence2sequenceBlastn (module/Util.py:4068): module level, because the reference submits it to a process
+    pool.  Every HSP of the query file is written once (for the first target file), in the oracle's order."""
+    import json
+    out = "%s_vs_%s.out" % (query_path, os.path.basename(target_path))
+    with open(out, "w") as f:
+        if os.path.basename(target_path) == "0_target.fa":
+            by_q = json.load(open(os.environ["HB_FAKE_BLAST_DB"]))
+            for line in open(query_path):
+                if line.startswith(">"):
+                    f.writelines(by_q.get(line[1:].strip(), []))
+    return out
+
+
+def test_reference_coarse_stage_equals_mirror_on_the_same_hsps(tmp_path, monkeypatch):
+    from hite_b200 import _lib, boundary, coarse, fasta
+    U = ref_import.load_util()
+    wl = synth.make_workload(genome_bp=3_200_000, n_contigs=2, n_families=25, cands_per_family=1, copies=(5, 14),
+                             length=(200, 1500), seed=31)
+    ref = str(tmp_path / "genome.fa")
+    wl.write_fasta(ref, str(tmp_path / "cand.fa"))
+    lens = [len(c) for c in wl.contig_seqs]
+    G = O.Genome(wl.contig_seqs)
+    hsps, segs, iv = G.coarse_boundary(lens, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64)
+    G.close()
+    assert len(hsps) > 2000 and len(iv) > 100
+    seg_name = ["%s$%d" % (wl.contig_names[c], o) for c, o in segs]
+    cut = str(tmp_path / "genome.cut0.fa")                        # split_genome_chunks.py:44-52 layout
+    with open(cut, "w") as f:
+        for (c, o), n in zip(segs, seg_name):
+            f.write(">%s\n%s\n" % (n, wl.contig_seqs[c][o:o + 1_000_000].tobytes().decode()))
+
+    # ---- the reference, externals replaced --------------------------------------------------------------------
+    def pass_through(repeat_names, repeat_contigs, tmp_output_dir, ref_index, threads):
+        fasta.store_fasta({n: repeat_contigs[n] for n in repeat_names}, os.path.join(tmp_output_dir, "filter_tandem_%s.fa" % ref_index))
+
+    by_q = {}
+    for q, s, qs, qe, ss, se in hsps.tolist():
+        by_q.setdefault(seg_name[q], []).append("%s\t%s\t100.0\t%d\t0\t0\t%d\t%d\t%d\t%d\t0.0\t100\n"
+                                                % (seg_name[q], seg_name[s], qe - qs + 1, qs, qe, ss, se))
+
+    import json
+    dbpath = str(tmp_path / "hsp_db.json")
+    json.dump(by_q, open(dbpath, "w"))
+    monkeypatch.setenv("HB_FAKE_BLAST_DB", dbpath)
+    monkeypatch.setattr(U, "filter_tandem_repeats", pass_through)
+    monkeypatch.setattr(U, "sequence2sequenceBlastn", _fake_blastn)
+    out_ref = str(tmp_path / "ref_longest_repeats_0.fa")
+    U.determine_repeat_boundary_v5(cut, out_ref, None, 2000, 30000, str(tmp_path / "refwork"), 4, 0, ref, 1)
+
+    # ---- the mirror, intervals from the oracle ----------------------------------------------------------------
+    class OracleBackedCtx:
+        device = 0
+
+        def load_genome(self, chroms):
+            assert [len(c) for c in chroms] == lens
+
+        def build_index(self, k, w):
+            return dict(kernel_ms=0.0)
+
+        def coarse_boundary(self, seg_len, skip_gap, max_len, occ_cap, threads):
+            # the HSPs are the oracle's; the chaining is the PRODUCT's host code (hb_fmea_chain_files), files as
+            # hb_coarse_boundary derives them from the segment lengths
+            assert (seg_len, skip_gap, max_len) == (1_000_000, 2000, 30000)
+            h = np.asarray(hsps)
+            h = h[np.argsort(h[:, 0], kind="stable")]
+            q_off = np.searchsorted(h[:, 0], np.arange(len(segs) + 1)).astype(np.uint64)
+            hs = np.zeros(len(h), dtype=_lib.HSP_DTYPE)
+            for k, f in enumerate(("subj", "qs", "qe", "ss", "se")):
+                hs[f] = h[:, k + 1]
+            sg = np.zeros(len(segs), dtype=_lib.SEG_DTYPE)
+            sg["chr"] = [x[0] for x in segs]; sg["start"] = [x[1] for x in segs]
+            files = O.split_file_groups([min(seg_len, lens[c] - o) for c, o in segs])
+            out = _lib.fmea_chain_files(hs, q_off, sg, files, skip_gap, max_len, threads=threads)
+            assert [(int(o["chr"]), int(o["start"]), int(o["end"])) for o in out] == iv
+            return out
+
+    monkeypatch.setattr(coarse, "get_context", lambda device=None: OracleBackedCtx())
+    out_mine = str(tmp_path / "mine_longest_repeats_0.fa")
+    coarse.determine_repeat_boundary_v5(cut, out_mine, None, 2000, 30000, str(tmp_path / "minework"), 4, 0, ref, 0)
+
+    def records(p):
+        lines = open(p).read().splitlines()
+        return sorted(zip(lines[0::2], lines[1::2]))
+    assert records(out_mine) == records(out_ref)
+    assert len(records(out_ref)) > 100
+    # flanking_seq on top (module/Util.py:4614): byte-identical files for the same input
+    U.flanking_seq(out_ref, out_ref + ".flanked", ref, 50)
+    coarse.flanking_seq(out_ref, out_mine + ".flanked", ref, 50)
+    assert open(out_ref + ".flanked").read() == open(out_mine + ".flanked").read()

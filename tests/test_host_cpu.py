@@ -361,3 +361,35 @@ def test_other_and_masking_host_logic_with_fake_context():
     rec = other.query_hsp_records(f, ["big"], big)
     assert f.n == 3 and [(int(x["qs"]), int(x["qe"])) for x in rec] == [(1, 32000), (32001, 64000), (64001, 70000)]
     assert [c[:3] for c in other.copies_from_records(rec, ["big"], big, f.contig_names)["big"]] == [("chr1", 1, 70000)]
+
+
+def test_product_fmea_shares_state_inside_a_blast_file():
+    """A contig's short tail segment shares its BLAST result file -- and FMEA's de-duplication dicts -- with the records that
+    follow it (reference split_and_store_sequences module/Util.py:4987, chr_pos_candidates :4155).  Product host code
+    (hb_fmea_chain_files) == oracle on a genome with 600 kbp tails; the per-record form differs there, as it must."""
+    import numpy as np
+    from hite_b200 import _lib, synth
+    from oracle import oracle as O
+    wl = synth.make_workload(genome_bp=3_200_000, n_contigs=2, n_families=25, cands_per_family=1, copies=(5, 14),
+                             length=(200, 1500), seed=31)
+    lens = [len(c) for c in wl.contig_seqs]
+    G = O.Genome(wl.contig_seqs)
+    hsps, segs, iv = G.coarse_boundary(lens, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64)
+    G.close()
+    files = O.split_file_groups([min(1_000_000, lens[c] - o) for c, o in segs])
+    assert files == [0, 1, 1, 2]                                   # chr1 tail + chr2 head share a file
+    h = np.asarray(hsps)
+    h = h[np.argsort(h[:, 0], kind="stable")]
+    q_off = np.searchsorted(h[:, 0], np.arange(len(segs) + 1)).astype(np.uint64)
+    hs = np.zeros(len(h), dtype=_lib.HSP_DTYPE)
+    for k, f in enumerate(("subj", "qs", "qe", "ss", "se")):
+        hs[f] = h[:, k + 1]
+    sg = np.zeros(len(segs), dtype=_lib.SEG_DTYPE)
+    sg["chr"] = [s[0] for s in segs]; sg["start"] = [s[1] for s in segs]
+    for threads in (1, 4):
+        out = _lib.fmea_chain_files(hs, q_off, sg, files, 2000, 30000, threads=threads)
+        assert [(int(o["chr"]), int(o["start"]), int(o["end"])) for o in out] == iv
+    solo = _lib.fmea_chain(hs, q_off, sg, 2000, 30000, threads=2)
+    assert [(int(o["chr"]), int(o["start"]), int(o["end"])) for o in solo] != iv
+    same = _lib.fmea_chain_files(hs, q_off, sg, list(range(len(segs))), 2000, 30000, threads=2)
+    assert [tuple(x) for x in same.tolist()] == [tuple(x) for x in solo.tolist()]
