@@ -33,16 +33,17 @@ def _fake_blastn(query_path, target_path):
     return out
 
 
-def test_reference_coarse_stage_equals_mirror_on_the_same_hsps(tmp_path, monkeypatch):
+@pytest.mark.parametrize("genome_bp,n_contigs,seed,skip_gap", [(3_200_000, 2, 31, 2000), (3_900_000, 3, 57, 4000)])
+def test_reference_coarse_stage_equals_mirror_on_the_same_hsps(tmp_path, monkeypatch, genome_bp, n_contigs, seed, skip_gap):
     from hite_b200 import _lib, boundary, coarse, fasta
     U = ref_import.load_util()
-    wl = synth.make_workload(genome_bp=3_200_000, n_contigs=2, n_families=25, cands_per_family=1, copies=(5, 14),
-                             length=(200, 1500), seed=31)
+    wl = synth.make_workload(genome_bp=genome_bp, n_contigs=n_contigs, n_families=25, cands_per_family=1, copies=(5, 14),
+                             length=(200, 1500), seed=seed)
     ref = str(tmp_path / "genome.fa")
     wl.write_fasta(ref, str(tmp_path / "cand.fa"))
     lens = [len(c) for c in wl.contig_seqs]
     G = O.Genome(wl.contig_seqs)
-    hsps, segs, iv = G.coarse_boundary(lens, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64)
+    hsps, segs, iv = G.coarse_boundary(lens, seg_len=1_000_000, skip_gap=skip_gap, max_len=30000, occ_cap=64)
     G.close()
     assert len(hsps) > 2000 and len(iv) > 100
     seg_name = ["%s$%d" % (wl.contig_names[c], o) for c, o in segs]
@@ -67,7 +68,7 @@ def test_reference_coarse_stage_equals_mirror_on_the_same_hsps(tmp_path, monkeyp
     monkeypatch.setattr(U, "filter_tandem_repeats", pass_through)
     monkeypatch.setattr(U, "sequence2sequenceBlastn", _fake_blastn)
     out_ref = str(tmp_path / "ref_longest_repeats_0.fa")
-    U.determine_repeat_boundary_v5(cut, out_ref, None, 2000, 30000, str(tmp_path / "refwork"), 4, 0, ref, 1)
+    U.determine_repeat_boundary_v5(cut, out_ref, None, skip_gap, 30000, str(tmp_path / "refwork"), 4, 0, ref, 1)
 
     # ---- the mirror, intervals from the oracle ----------------------------------------------------------------
     class OracleBackedCtx:
@@ -82,7 +83,7 @@ def test_reference_coarse_stage_equals_mirror_on_the_same_hsps(tmp_path, monkeyp
         def coarse_boundary(self, seg_len, skip_gap, max_len, occ_cap, threads):
             # the HSPs are the oracle's; the chaining is the PRODUCT's host code (hb_fmea_chain_files), files as
             # hb_coarse_boundary derives them from the segment lengths
-            assert (seg_len, skip_gap, max_len) == (1_000_000, 2000, 30000)
+            assert (seg_len, max_len) == (1_000_000, 30000)
             h = np.asarray(hsps)
             h = h[np.argsort(h[:, 0], kind="stable")]
             q_off = np.searchsorted(h[:, 0], np.arange(len(segs) + 1)).astype(np.uint64)
@@ -98,7 +99,7 @@ def test_reference_coarse_stage_equals_mirror_on_the_same_hsps(tmp_path, monkeyp
 
     monkeypatch.setattr(coarse, "get_context", lambda device=None: OracleBackedCtx())
     out_mine = str(tmp_path / "mine_longest_repeats_0.fa")
-    coarse.determine_repeat_boundary_v5(cut, out_mine, None, 2000, 30000, str(tmp_path / "minework"), 4, 0, ref, 0)
+    coarse.determine_repeat_boundary_v5(cut, out_mine, None, skip_gap, 30000, str(tmp_path / "minework"), 4, 0, ref, 0)
 
     def records(p):
         lines = open(p).read().splitlines()
