@@ -50,17 +50,17 @@ class _Log:
             pass
 
 
-@pytest.mark.parametrize("te_type", ["tir", "helitron", "non_ltr"])
-def test_reference_loop_equals_mirror_on_the_same_copies_and_msa(tmp_path, monkeypatch, te_type):
+@pytest.mark.parametrize("te_type,seed,plant", [("tir", 23, 1), ("tir", 24, 0), ("helitron", 23, 1), ("non_ltr", 23, 1)])
+def test_reference_loop_equals_mirror_on_the_same_copies_and_msa(tmp_path, monkeypatch, te_type, seed, plant):
     from hite_b200 import boundary, fasta
     U = ref_import.load_util()
-    wl = synth.make_workload(genome_bp=1_500_000, n_contigs=2, n_families=14, cands_per_family=3, copies=(4, 30),
-                             length=(150, 1900), seed=23, kind=te_type)
+    wl = synth.make_workload(genome_bp=1_500_000, n_contigs=2, n_families=14, cands_per_family=3, copies=(3, 30),
+                             length=(150, 1900), seed=seed, kind=te_type)
     ref, cand = str(tmp_path / "genome.fa"), str(tmp_path / "cand.fa")
     wl.write_fasta(ref, cand)
     names, contigs = fasta.read_fasta(cand)
     G = O.Genome(wl.contig_seqs)
-    judge = {"tir": None, "helitron": lambda c, r: O.judge_v6(c, r), "non_ltr": lambda c, r: O.judge_v9(c, r)}[te_type]
+    judge = {"tir": (lambda c, r: O.judge_v5(c, r, plant)), "helitron": lambda c, r: O.judge_v6(c, r), "non_ltr": lambda c, r: O.judge_v9(c, r)}[te_type]
     all_copies, db, verdicts = {}, {}, {}
     n_trunc = 0
     for name in names:
@@ -76,7 +76,7 @@ def test_reference_loop_equals_mirror_on_the_same_copies_and_msa(tmp_path, monke
             if t:
                 db[fname + ".trunc.blast.bed.fa"] = t
                 n_trunc += 1
-            verdicts[seq] = O.judge_with_trunc_gate(seq, cps, rows, judge=judge, plant=1)
+            verdicts[seq] = O.judge_with_trunc_gate(seq, cps, rows, judge=judge, plant=plant)
         else:
             verdicts[seq] = dict(is_te=False, info="", cons="", copy_num=0)
     G.close()
@@ -104,22 +104,23 @@ def test_reference_loop_equals_mirror_on_the_same_copies_and_msa(tmp_path, monke
     monkeypatch.setattr(U, "remove_no_tirs", no_tirs)
     monkeypatch.setattr(U, "get_domain_info", no_domains)
     out_ref, low_ref = str(tmp_path / "ref_real.fa"), str(tmp_path / "ref_low.fa")
-    U.flank_region_align_v5(cand, out_ref, 50, ref, None, te_type, str(tmp_path / "refwork"), 4, 0, _Log, "", 1, 0, 0, low_ref, "cons")
+    U.flank_region_align_v5(cand, out_ref, 50, ref, None, te_type, str(tmp_path / "refwork"), 4, 0, _Log, "", plant, 0, 0, low_ref, "cons")
 
     # ---- the mirror, verdicts from the oracle -------------------------------------------------------------------
     class OracleBackedCtx:
         device = 0
 
         def adjust(self, seqs, te, plant, result_type, flank=50):
-            assert te == te_type and flank == 50
+            assert te == te_type and flank == 50 and plant == globals_plant
             return [dict(verdicts[s]) for s in seqs]
 
+    globals_plant = plant
     ctx = OracleBackedCtx()
     monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
     monkeypatch.setattr(boundary, "ensure_genome", lambda c, r, k=15, w=10, _parsed=None: c)
     monkeypatch.setenv("HITE_GPU_DEVICES", "0")
     out_mine, low_mine = str(tmp_path / "mine_real.fa"), str(tmp_path / "mine_low.fa")
-    boundary.flank_region_align_v5(cand, out_mine, 50, ref, None, te_type, str(tmp_path / "minework"), 4, 0, _Log, "", 1, 0, 0, low_mine, "cons")
+    boundary.flank_region_align_v5(cand, out_mine, 50, ref, None, te_type, str(tmp_path / "minework"), 4, 0, _Log, "", plant, 0, 0, low_mine, "cons")
 
     def records(p):
         lines = open(p).read().splitlines() if os.path.exists(p) else []
