@@ -57,7 +57,7 @@ def determine_repeat_boundary_v5(repeats_path, longest_repeats_path, prev_TE, fi
     if prev_TE is not None and file_exist(prev_TE):              # mask_genome_with_TE (module/Util.py:4654)
         from . import masking
         te_names, te_contigs = read_fasta(prev_TE)
-        masking.mask_context(ctx, te_names, te_contigs)
+        masking.mask_context(ctx, te_names, te_contigs, threads=max(1, int(threads)), record_len=int(chrom_seg_length))
     iv = ctx.coarse_boundary(seg_len=int(chrom_seg_length), skip_gap=int(fixed_extend_base_threshold),
                              max_len=int(max_single_repeat_len), occ_cap=int(occ_cap), threads=max(1, int(threads)))
     ref_names, ref_contigs = read_fasta(reference)

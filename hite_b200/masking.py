@@ -79,11 +79,16 @@ def intervals_from_hsp_records(rec, names, contigs, full_length_threshold=0.95, 
     return [(gkeys[qg], subj, start, end) for qg, (subj, start, end, _, _) in zip(oq.tolist(), out.tolist())]
 
 
-def mask_context(ctx, lib_names, lib_contigs, full_length_threshold=0.95, threads=8):
+def mask_context(ctx, lib_names, lib_contigs, full_length_threshold=0.95, threads=8, record_len=None):
     """Mask the genome resident in ``ctx`` with the library: HSPs -> full-length copies -> ``hb_genome_mask`` + index
-    rebuild.  Returns (intervals, newly masked bases)."""
+    rebuild.  Returns (intervals, newly masked bases).  ``record_len``: the resident contigs stand for FASTA records of this
+    length (the 1 Mbp ``chr$start`` records of a genome chunk, split_genome_chunks.py:44-52): the reference aligns the
+    library to those records, so a copy lying across a record border is two partial hits on two subjects, never a
+    full-length copy, and stays unmasked -- such intervals are dropped here too."""
     rec = other.query_hsp_records(ctx, lib_names, lib_contigs)
     intervals = intervals_from_hsp_records(rec, lib_names, lib_contigs, full_length_threshold, threads)
+    if record_len:
+        intervals = [iv for iv in intervals if iv[2] // record_len == (iv[3] - 1) // record_len]
     fresh = 0
     if intervals:
         fresh = ctx.mask_genome([i[1] for i in intervals], [i[2] for i in intervals], [i[3] for i in intervals])

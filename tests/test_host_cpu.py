@@ -393,3 +393,36 @@ def test_product_fmea_shares_state_inside_a_blast_file():
     assert [(int(o["chr"]), int(o["start"]), int(o["end"])) for o in solo] != iv
     same = _lib.fmea_chain_files(hs, q_off, sg, list(range(len(segs))), 2000, 30000, threads=2)
     assert [tuple(x) for x in same.tolist()] == [tuple(x) for x in solo.tolist()]
+
+
+def test_coarse_masking_leaves_border_crossing_copies(monkeypatch):
+    """masking.mask_context(record_len=...): a full-length copy lying across a 1 Mbp record border is not masked, as in the
+    reference, where the two halves are partial hits on two subject records (module/Util.py:4654 on chr$start records)."""
+    import numpy as np
+    from hite_b200 import _lib, masking
+
+    class Fake:
+        contig_names = ["chr1"]
+        masked = None
+
+        def query_hsps(self, seqs, occ_cap=512, max_loci=128):
+            r = np.zeros(3, dtype=_lib.QHSP_DTYPE)
+            r["query"] = 0; r["contig"] = 0; r["qs"] = 1; r["qe"] = 1000; r["n_match"] = r["aln_len"] = 1000
+            r["ss"] = [5001, 999_501, 1_999_001]; r["se"] = [6000, 1_000_500, 2_000_000]
+            return r
+
+        def timing(self):
+            return dict(kernel_ms=0.0, k_ms=[0] * 8)
+
+        def mask_genome(self, contig, start, end):
+            self.masked = sorted(zip(contig, start, end))
+            return sum(b - a for _, a, b in self.masked)
+
+        def build_index(self, k, w):
+            return dict(kernel_ms=0.0)
+
+    f = Fake()
+    iv, fresh = masking.mask_context(f, ["te1"], {"te1": "A" * 1000}, record_len=1_000_000)
+    assert f.masked == [(0, 5000, 6000), (0, 1_999_000, 2_000_000)] and fresh == 2000     # the copy across 1 000 000 stays
+    iv, fresh = masking.mask_context(f, ["te1"], {"te1": "A" * 1000})
+    assert len(f.masked) == 3
