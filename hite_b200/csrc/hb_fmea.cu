@@ -40,6 +40,7 @@ struct Scratch {
 };
 
 void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Chain>& out, std::vector<char>& used) {
+    if (c.size() == 1) { out.push_back(Chain{c[0].qs, c[0].qe, c[0].ss, c[0].se, subj}); return; }   // the common case
     for (size_t i = 0; i < c.size(); ++i) c[i].ord = (int32_t)i;
     std::sort(c.begin(), c.end(), [](const Frag& a, const Frag& b) {          // == stable sort on (qs, qe)
         return a.qs != b.qs ? a.qs < b.qs : (a.qe != b.qe ? a.qe < b.qe : a.ord < b.ord);
