@@ -130,3 +130,62 @@ def test_reference_loop_equals_mirror_on_the_same_copies_and_msa(tmp_path, monke
     assert len(records(out_ref)) + len(records(low_ref)) >= 15
     print("%s: %d candidates, %d with copies, %d through the truncated-member gate -> %d confident, %d low-copy records (reference == mirror)"
           % (te_type, len(names), len(all_copies), n_trunc, len(records(out_ref)), len(records(low_ref))))
+
+
+FAKE_SAMTOOLS = r'''#!%s
+import sys
+assert sys.argv[1] == "faidx"
+path = sys.argv[2]
+out, off = [], 0
+data = open(path, "rb").read().split(b"\n")
+i = 0
+while i + 1 < len(data):
+    if data[i].startswith(b">"):
+        name = data[i][1:].split()[0].decode()
+        off += len(data[i]) + 1
+        out.append("%%s\t%%d\t%%d\t%%d\t%%d" %% (name, len(data[i + 1]), off, len(data[i + 1]), len(data[i + 1]) + 1))
+        off += len(data[i + 1]) + 1
+        i += 2
+    else:
+        i += 1
+open(path + ".fai", "w").write("\n".join(out) + "\n")
+'''
+
+
+def test_ready_for_msa_subset_rule(tmp_path, monkeypatch):
+    """What the reference's tools/ready_for_MSA.sh (run for real; only `samtools faidx` is a stand-in) keeps of a member file
+    with more than 100 records (module/Util.py:10409-10412): the 100 longest, output in file order, and among records of EQUAL
+    length at the cut the ones whose NAME is larger bytewise (`sort -nk 2 -r` falls back to a reversed whole-line comparison;
+    C / POSIX locale).  HB-align's S9 keeps the earlier-ranked records on such a tie instead -- with real high-copy families
+    (many copies of identical length) the two subsets differ, which is the first item of DESIGN.md's "Next"."""
+    import functools
+    import random
+    import subprocess
+    rng = random.Random(5)
+    recs = []
+    for _ in range(130):
+        chrom = rng.choice(["chr1", "chr10", "chr2", "scaffold_3"])
+        s0, L = rng.randint(1, 2_000_000), rng.choice([300, 300, 300, 300, 301, 299, 305, 310, 290])
+        recs.append(("%s:%d-%d(%s)" % (chrom, s0, s0 + L - 101, rng.choice("+-")), "A" * L))
+    assert len({n for n, _ in recs}) == len(recs)
+    member = tmp_path / "q.blast.bed.fa"
+    member.write_text("".join(">%s\n%s\n" % r for r in recs))
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    tool = bindir / "samtools"
+    tool.write_text(FAKE_SAMTOOLS % sys.executable)
+    tool.chmod(tool.stat().st_mode | stat.S_IEXEC)
+    env = dict(os.environ, PATH=str(bindir) + os.pathsep + os.environ["PATH"], LC_ALL="C")
+    subprocess.run(["sh", os.path.join(ref_import.REF_ROOT, "tools", "ready_for_MSA.sh"), str(member), "100", "100"], env=env,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    kept = [l[1:].strip() for l in open(str(member) + ".rdmSubset.fa") if l.startswith(">")]
+
+    def cmp(i, j):
+        (ni, si), (nj, sj) = recs[i], recs[j]
+        if len(si) != len(sj):
+            return -1 if len(si) > len(sj) else 1
+        return -1 if ni.encode() > nj.encode() else 1
+    order = sorted(range(len(recs)), key=functools.cmp_to_key(cmp))[:100]
+    assert kept == [recs[i][0] for i in sorted(order)]
+    earlier = sorted(sorted(range(len(recs)), key=lambda i: (-len(recs[i][1]), i))[:100])
+    assert kept != [recs[i][0] for i in earlier]                  # the current S9 tie rule picks other members
