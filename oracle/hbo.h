@@ -52,6 +52,7 @@ typedef struct {
 
 hbo_genome *hbo_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_t n);
 void hbo_genome_free(hbo_genome *g);
+void hbo_genome_set_tie_rule(hbo_genome *g, int tie_rule, const int32_t *contig_rank);
 uint64_t hbo_genome_total(const hbo_genome *g);
 uint64_t hbo_genome_contig_off(const hbo_genome *g, uint32_t c);
 uint64_t hbo_minimizers_codes(const uint8_t *code, uint64_t tot, int k, int w, uint64_t *out, uint64_t cap);

@@ -33,6 +33,8 @@ struct hbo_genome {
     uint32_t n_contig;
     uint64_t *goff;    /* n_contig global offsets */
     uint64_t *glen;
+    int32_t *crank;    /* rank of every contig by (name + ':') bytewise, or NULL: see hbo_genome_set_tie_rule */
+    int tie_rule;      /* S9 tie rule: 0 = earlier-ranked copy (what the kernels do today), 1 = ready_for_MSA.sh's */
 };
 
 static inline uint8_t code_of(uint8_t c) {
@@ -53,7 +55,38 @@ hbo_genome *hbo_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_
         for (uint64_t i = 0; i < g->glen[c]; ++i) g->code[g->goff[c] + i] = code_of(ascii[off[c] + i]);
     return g;
 }
-void hbo_genome_free(hbo_genome *g) { if (g) { free(g->code); free(g->goff); free(g->glen); free(g); } }
+void hbo_genome_free(hbo_genome *g) { if (g) { free(g->code); free(g->goff); free(g->glen); free(g->crank); free(g); } }
+
+/* S9 tie rule of the reference's tools/ready_for_MSA.sh, kept next to the current one until the kernels follow (DESIGN.md
+   section 9, item 1): `sort -nk 2 -r` on the .fai lines breaks a length tie by a reversed whole-line comparison, i.e. the member
+   whose name "contig:start1-end1(strand)" is LARGER bytewise is the "longer" one (C / POSIX locale; pinned by running the real
+   script, tests/test_flank_loop_dropin_cpu.py).  contig_rank[c] = rank of contig c by (name + ':') bytewise ascending. */
+void hbo_genome_set_tie_rule(hbo_genome *g, int tie_rule, const int32_t *contig_rank) {
+    g->tie_rule = tie_rule;
+    free(g->crank); g->crank = NULL;
+    if (contig_rank) {
+        g->crank = (int32_t *)malloc(sizeof(int32_t) * (g->n_contig + 1));
+        memcpy(g->crank, contig_rank, sizeof(int32_t) * g->n_contig);
+    }
+}
+/* decimal strings of two non-negative numbers compared bytewise, a shorter string that is a prefix being smaller (what follows
+   it in the name, '-' or '(', sorts below every digit) */
+static int dec_lex_cmp(int64_t a, int64_t b) {
+    char sa[24], sb[24];
+    snprintf(sa, sizeof(sa), "%lld", (long long)a);
+    snprintf(sb, sizeof(sb), "%lld", (long long)b);
+    return strcmp(sa, sb);
+}
+/* is copy y's member name bytewise larger than copy x's ? */
+static int name_greater(const hbo_genome *g, const hbo_copy *y, const hbo_copy *x) {
+    const int ry = g->crank ? g->crank[y->contig] : y->contig, rx = g->crank ? g->crank[x->contig] : x->contig;
+    if (ry != rx) return ry > rx;
+    int c = dec_lex_cmp(y->start1, x->start1);
+    if (c) return c > 0;
+    c = dec_lex_cmp(y->end1, x->end1);
+    if (c) return c > 0;
+    return y->rel > x->rel;                                   /* '-' (0x2D) > '+' (0x2B) */
+}
 uint64_t hbo_genome_total(const hbo_genome *g) { return g->tot; }
 uint64_t hbo_genome_contig_off(const hbo_genome *g, uint32_t c) { return g->goff[c]; }
 
@@ -384,7 +417,8 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
             int longer = 0;
             for (int y = 0; y < nl; ++y) {
                 if (y == x || !copies[y].keep) continue;
-                if (copies[y].ext_len > copies[x].ext_len || (copies[y].ext_len == copies[x].ext_len && y < x)) ++longer;
+                const int first = g->tie_rule ? name_greater(g, &copies[y], &copies[x]) : (y < x);
+                if (copies[y].ext_len > copies[x].ext_len || (copies[y].ext_len == copies[x].ext_len && first)) ++longer;
             }
             if (longer >= max_rows) copies[x].keep = 2;    /* mark, drop after the pass */
         }

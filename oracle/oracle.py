@@ -300,6 +300,18 @@ class Genome:
         self.index = self.mm_pos_order.copy()
         L.hbo_sort_u64(self.index.ctypes.data, n)
 
+    def set_tie_rule(self, tie_rule, contig_names=None):
+        """S9 tie rule: 0 = earlier-ranked copy (the kernels' rule today), 1 = the reference's ready_for_MSA.sh rule (larger
+        member name wins a length tie).  ``contig_names`` give the name order the rule needs."""
+        import numpy as np
+        self._L.hbo_genome_set_tie_rule.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        rank = None
+        if contig_names is not None:
+            order = sorted(range(len(contig_names)), key=lambda i: (contig_names[i] + ":").encode())
+            rank = np.zeros(len(contig_names), dtype=np.int32)
+            rank[order] = np.arange(len(contig_names), dtype=np.int32)
+        self._L.hbo_genome_set_tie_rule(self.g, int(tie_rule), rank.ctypes.data if rank is not None else None)
+
     def close(self):
         if self.g:
             self._L.hbo_genome_free(self.g)

@@ -189,3 +189,88 @@ def test_ready_for_msa_subset_rule(tmp_path, monkeypatch):
     assert kept == [recs[i][0] for i in sorted(order)]
     earlier = sorted(sorted(range(len(recs)), key=lambda i: (-len(recs[i][1]), i))[:100])
     assert kept != [recs[i][0] for i in earlier]                  # the current S9 tie rule picks other members
+
+
+def test_reference_loop_with_more_than_100_copies_under_the_scripts_tie_rule(tmp_path, monkeypatch):
+    """Families with 110-140 kept copies through the reference's loop: it subsets the member file with its own
+    tools/ready_for_MSA.sh (run for real, `samtools faidx` stood in) before mafft.  With the oracle switched to the script's tie
+    rule (Genome.set_tie_rule(1): DESIGN.md section 9 item 1, what the kernels are to follow next) the stand-in mafft finds
+    exactly the oracle's 100 members, in file order, and both sides write the same records."""
+    from hite_b200 import boundary, fasta
+    U = ref_import.load_util()
+    wl = synth.make_workload(genome_bp=2_000_000, n_contigs=2, n_families=4, cands_per_family=1, copies=(110, 140),
+                             length=(150, 700), seed=77)
+    ref, cand = str(tmp_path / "genome.fa"), str(tmp_path / "cand.fa")
+    wl.write_fasta(ref, cand)
+    names, contigs = fasta.read_fasta(cand)
+    lens = [len(c) for c in wl.contig_seqs]
+    G = O.Genome(wl.contig_seqs)
+    G.set_tie_rule(1, wl.contig_names)
+    all_copies, db, verdicts = {}, {}, {}
+    n_cut = n_tie = 0
+    for name in names:
+        seq = contigs[name]
+        cps, rows = G.candidate_msa(seq.encode())
+        pre, seen = [], set()                                        # every copy that reaches the member file (:8095-8115)
+        for c in cps:
+            if c["contig"] < 0 or c["start1"] - 1 - 50 < 0 or c["end1"] + 50 > lens[c["contig"]] or c["end1"] - c["start1"] + 101 < 100:
+                continue
+            if (c["rel"], c["j_s"], c["j_e"]) in seen:
+                continue
+            seen.add((c["rel"], c["j_s"], c["j_e"]))
+            pre.append(c)
+        all_copies[name] = [(wl.contig_names[c["contig"]], c["start1"], c["end1"], c["end1"] - c["start1"] + 1, "-" if c["rel"] else "+")
+                            for c in pre]
+        ext = sorted((c["end1"] - c["start1"] + 101 for c in pre), reverse=True)
+        fname = re.sub(r'[<>:"/\\|?*]', "-", name)
+        if len(pre) > 100:
+            n_cut += 1
+            n_tie += ext[99] == ext[100]
+            assert len(rows) == 100
+            db[fname + ".blast.bed.fa.rdmSubset.fa"] = rows
+        else:
+            db[fname + ".blast.bed.fa"] = rows
+        verdicts[seq] = O.judge_with_trunc_gate(seq, cps, rows, judge=lambda c, r: O.judge_v5(c, r, 1), plant=1)
+    G.close()
+    assert n_cut >= 3 and n_tie >= 2                                 # the tie at the cut is the normal case
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    for tool, body in (("mafft", FAKE_MAFFT), ("samtools", FAKE_SAMTOOLS)):
+        p = bindir / tool
+        p.write_text(body % sys.executable)
+        p.chmod(p.stat().st_mode | stat.S_IEXEC)
+    dbpath = str(tmp_path / "msa_db.json")
+    json.dump(db, open(dbpath, "w"))
+    monkeypatch.setenv("PATH", str(bindir) + os.pathsep + os.environ["PATH"])
+    monkeypatch.setenv("HB_FAKE_MAFFT_DB", dbpath)
+    monkeypatch.setenv("LC_ALL", "C")
+    monkeypatch.setattr(U, "get_full_length_copies_minimap2", lambda q, r, t, m, th: dict(all_copies))
+
+    def no_tirs(confident_tir_path, plant, TRsearch_dir, temp_dir):
+        a, b = confident_tir_path + ".with", confident_tir_path + ".without"
+        open(a, "w").close()
+        open(b, "w").close()
+        return a, b
+    monkeypatch.setattr(U, "remove_no_tirs", no_tirs)
+    monkeypatch.setattr(U, "get_domain_info", lambda cons, lib, table, th, t: open(table, "w").write("#\n#\n"))
+    subset_script = os.path.join(ref_import.REF_ROOT, "tools", "ready_for_MSA.sh")
+    out_ref, low_ref = str(tmp_path / "ref_real.fa"), str(tmp_path / "ref_low.fa")
+    U.flank_region_align_v5(cand, out_ref, 50, ref, None, "tir", str(tmp_path / "refwork"), 2, 0, _Log, subset_script, 1, 0, 0, low_ref, "cons")
+
+    class OracleBackedCtx:
+        device = 0
+
+        def adjust(self, seqs, te, plant, result_type, flank=50):
+            return [dict(verdicts[s]) for s in seqs]
+    ctx = OracleBackedCtx()
+    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "ensure_genome", lambda c, r, k=15, w=10, _parsed=None: c)
+    monkeypatch.setenv("HITE_GPU_DEVICES", "0")
+    out_mine, low_mine = str(tmp_path / "mine_real.fa"), str(tmp_path / "mine_low.fa")
+    boundary.flank_region_align_v5(cand, out_mine, 50, ref, None, "tir", str(tmp_path / "minework"), 2, 0, _Log, "", 1, 0, 0, low_mine, "cons")
+
+    def records(p):
+        lines = open(p).read().splitlines() if os.path.exists(p) else []
+        return sorted(zip(lines[0::2], lines[1::2]))
+    assert records(out_mine) == records(out_ref) and records(low_mine) == records(low_ref)
+    assert len(records(out_ref)) >= 3
