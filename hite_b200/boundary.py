@@ -168,6 +168,23 @@ def flank_region_align_v5(candidate_sequence_path, real_TEs, flanking_len, refer
     return results
 
 
+def subset_100_longest(member_names, member_contigs, keep=100):
+    """What ``sh ready_for_MSA.sh <file> 100 100`` keeps of a member file (reference tools/ready_for_MSA.sh, module/Util.py:
+    10409-10412): the 100 longest records in file order; records of equal length at the cut are taken in DESCENDING bytewise
+    order of their names (the script's ``sort -nk 2 -r`` falls back to a reversed whole-line comparison; C / POSIX locale --
+    checked against the real script in tests/test_flank_loop_dropin_cpu.py)."""
+    import functools
+
+    def cmp(i, j):
+        li, lj = len(member_contigs[member_names[i]]), len(member_contigs[member_names[j]])
+        if li != lj:
+            return -1 if li > lj else 1
+        a, b = member_names[i].encode(), member_names[j].encode()
+        return -1 if a > b else (1 if a < b else 0)
+    chosen = sorted(range(len(member_names)), key=functools.cmp_to_key(cmp))[:keep]
+    return [member_names[i] for i in sorted(chosen)]
+
+
 def _is_aligned(member_contigs):
     lens = {len(s) for s in member_contigs.values()}
     return len(lens) == 1 and any("-" in s for s in member_contigs.values())
@@ -186,8 +203,7 @@ def is_TE_from_align_file(cur_align_file, query_name, cur_seq, temp_dir, subset_
         r = ctx.vote_matrices([cur_seq], [rows], TE_type, int(plant), result_type)[0]
     else:
         if len(member_names) > 100:                                              # :10409-10412, 100 longest
-            order = sorted(range(len(member_names)), key=lambda i: (-len(member_contigs[member_names[i]]), i))[:100]
-            member_names = [member_names[i] for i in sorted(order)]
+            member_names = subset_100_longest(member_names, member_contigs)
         _GENOME.pop(ctx.device, None)
         ctx.load_genome([member_contigs[n].encode("ascii") for n in member_names])
         ctx.build_index(15, 10)

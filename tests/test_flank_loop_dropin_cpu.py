@@ -189,6 +189,9 @@ def test_ready_for_msa_subset_rule(tmp_path, monkeypatch):
     assert kept == [recs[i][0] for i in sorted(order)]
     earlier = sorted(sorted(range(len(recs)), key=lambda i: (-len(recs[i][1]), i))[:100])
     assert kept != [recs[i][0] for i in earlier]                  # the current S9 tie rule picks other members
+    # the host mirror's subset for member FILES (run_find_members_v8 / is_TE_from_align_file on unaligned members) follows the script
+    from hite_b200 import boundary
+    assert boundary.subset_100_longest([n for n, _ in recs], dict(recs)) == kept
 
 
 def test_reference_loop_with_more_than_100_copies_under_the_scripts_tie_rule(tmp_path, monkeypatch):
