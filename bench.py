@@ -163,7 +163,7 @@ def main():
         dt = float(np.mean(times))
         val = per_step / dt
         line = {"impl": "reference", "metric": "candidate TEs boundary-adjusted/sec", "value": val, "unit": "candidates/s",
-                "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": wname, "sample": "%d candidates per step" % per_step},
                 "cpu_baseline": {"value": val, "unit": "candidates/s", "cores": cores, "kind": "port",
