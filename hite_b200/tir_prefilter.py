@@ -92,3 +92,98 @@ def filter_dup_itr_v3(cur_copies_out_contigs, TIR_len_dict):
     if len(seq) >= 30_000:
         return {}
     return {"%s-tir_%d-tsd_%s" % (query, TIR_len_dict.get(best_name, 0), tsd): seq}
+
+
+def _run_itrsearch(TRsearch_dir, input_path, work_dir):
+    """The reference's run_itrsearch (module/Util.py:216-224): the external ``itrsearch -i 0.7 -l 7`` of the HiTE tools
+    directory (closed binary, not part of this repository) on a FASTA of 80 bp end pairs -> (<input>.itr, <input>.log)."""
+    import os
+    import subprocess
+    os.makedirs(work_dir, exist_ok=True)
+    log = input_path + ".log"
+    with open(log, "w") as f:
+        subprocess.run([os.path.join(TRsearch_dir, "itrsearch"), "-i", "0.7", "-l", "7", input_path], cwd=work_dir, stdout=f,
+                       stderr=subprocess.DEVNULL)
+    return input_path + ".itr", log
+
+
+def _itr_headers(path):
+    """Header lines of an itrsearch output (read_fasta_v1 semantics, module/Util.py:1694: the whole line is the name; a
+    record without sequence is dropped)."""
+    import os
+    names = []
+    if os.path.exists(path):
+        name, has_seq = "", False
+        for line in open(path):
+            if line.startswith(">"):
+                if name and has_seq:
+                    names.append(name)
+                name, has_seq = line.strip()[1:], False
+            elif line.strip():
+                has_seq = True
+        if name and has_seq:
+            names.append(name)
+    return names
+
+
+def tsd_variant_groups(longest_repeats_flanked_path, tir_tsd_dir, flanking_len, threads, TRsearch_dir, plant, ctx=None,
+                       partition=20_000):
+    """Everything of ``multi_process_tsd_v1`` up to the per-candidate selection -> (candidate names in file order,
+    {candidate: {variant name: sequence}}, {variant name: TIR length}).  A candidate's dict lists the variants itrsearch
+    reported first, then its short-TIR variants, like the reference's dict (:6600-6609)."""
+    import os
+    import shutil
+    from concurrent.futures import ThreadPoolExecutor
+    from .fasta import read_fasta, store_fasta
+    if os.path.exists(tir_tsd_dir):
+        shutil.rmtree(tir_tsd_dir, ignore_errors=True)
+    os.makedirs(tir_tsd_dir, exist_ok=True)
+    names, contigs = read_fasta(longest_repeats_flanked_path)
+    all_contigs, short_contigs = search_confident_tir_batch({n: contigs[n] for n in names}, int(flanking_len), int(plant), ctx=ctx)
+    rest = {n: s for n, s in all_contigs.items() if n not in short_contigs}
+
+    def parts(d, tag):
+        items = list(d.items())
+        out = []
+        for k in range(0, len(items), partition):
+            path = os.path.join(tir_tsd_dir, "%d%s.fa" % (k // partition, tag))
+            store_fasta({n: s[:40] + s[-40:] for n, s in items[k:k + partition]}, path)     # :6556-6560, :6569-6573
+            out.append(path)
+        return out
+    jobs = parts(short_contigs, "_s") + parts(rest, "")
+    with ThreadPoolExecutor(max(1, int(threads))) as ex:
+        outs = list(ex.map(lambda p: _run_itrsearch(TRsearch_dir, p, tir_tsd_dir), jobs))
+    tir_len, with_tir = {}, set()
+    for (itr_path, _), job in zip(outs, jobs):
+        for header in _itr_headers(itr_path):
+            name = header.split(" ")[0]
+            tir_len[name] = int(header.split("Length itr=")[1])                             # :6586-6593
+            if not job.endswith("_s.fa"):
+                with_tir.add(name)
+    groups = {}
+    for name, seq in rest.items():                                                          # :6603-6605
+        if name in with_tir:
+            groups.setdefault(name.split("-C_")[0], {})[name] = seq
+    for name, seq in short_contigs.items():                                                 # :6606 update(short_itr_contigs)
+        groups.setdefault(name.split("-C_")[0], {})[name] = seq
+    shutil.rmtree(tir_tsd_dir, ignore_errors=True)
+    return names, groups, tir_len
+
+
+def multi_process_tsd_v1(longest_repeats_flanked_path, tir_tsd_path, tir_tsd_dir, flanking_len, threads, TRsearch_dir, plant,
+                         ctx=None):
+    """reference module/Util.py:6630-6655 (what judge_TIR_transposons.py:76 calls) with ``search_confident_tir_batch_v1``
+    (:6533-6628) inside: per flanked candidate the TSD-bounded variants (``hb_tsd_candidates``, ONE launch for the whole file
+    instead of a process pool over 10 kB partitions), the 40 + 40 bp end pairs of the variants through the external
+    ``itrsearch`` (``threads`` parallel partitions; short-TIR classes and the rest separately, as the reference does), the
+    TIR length of every variant from its output, and per candidate the variant closest to the raw boundaries
+    (``filter_dup_itr_v3``) -> ``tir_tsd_path`` FASTA, records in candidate order.  Among variants of equal distance the
+    reference's choice follows Python's set order (it changes with the hash seed of the run); here it is (start, end, k)."""
+    from .fasta import store_fasta
+    names, groups, tir_len = tsd_variant_groups(longest_repeats_flanked_path, tir_tsd_dir, flanking_len, threads, TRsearch_dir,
+                                                plant, ctx=ctx)
+    result = {}
+    for q in names:
+        if q in groups:
+            result.update(filter_dup_itr_v3(groups[q], tir_len))
+    store_fasta(result, tir_tsd_path)

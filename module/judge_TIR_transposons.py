@@ -8,4 +8,5 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from _hite_b200_patch import run_stage  # noqa: E402
 
 if __name__ == "__main__":
-    run_stage("judge_TIR_transposons.py")
+    # besides the boundary-adjustment loop, the stage's TSD / TIR pre-filter (multi_process_tsd_v1, judge_TIR_transposons.py:76)
+    run_stage("judge_TIR_transposons.py", extra=(("multi_process_tsd_v1", "hite_b200.tir_prefilter"),))

@@ -240,6 +240,10 @@ def test_drop_in_stage_scripts_patch_the_reference_namespace(monkeypatch, tmp_pa
         patch.run_stage("judge_Non_LTR_transposons.py", extra=(("get_candidate_non_ltr_parallel", "hite_b200.nonltr_prefilter"),))
         import hite_b200.nonltr_prefilter as hn
         assert U.get_candidate_non_ltr_parallel is hn.get_candidate_non_ltr_parallel
+        saved["multi_process_tsd_v1"] = U.multi_process_tsd_v1
+        patch.run_stage("judge_TIR_transposons.py", extra=(("multi_process_tsd_v1", "hite_b200.tir_prefilter"),))
+        import hite_b200.tir_prefilter as ht
+        assert U.multi_process_tsd_v1 is ht.multi_process_tsd_v1
         patch.run_stage("judge_LTR_transposons.py", patch_names=("mask_genome_with_TE",), source="hite_b200.masking")
         import hite_b200.masking as hm
         assert U.mask_genome_with_TE is hm.mask_genome_with_TE
