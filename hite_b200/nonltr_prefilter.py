@@ -17,10 +17,9 @@ _COMP = {"A": "T", "T": "A", "C": "G", "G": "C"}
 
 
 def _ctx():
-    global _CTX
-    if _CTX is None:
-        _CTX = _lib.Context(0)
-    return _CTX
+    """The stage process's context (shared with hite_b200.boundary: one context per process per GPU, HITE_GPU_DEVICES honoured)."""
+    from . import boundary
+    return boundary.get_context()
 
 
 def _reverse_sequence(s):                                     # getReverseSequence, module/Util.py:1635

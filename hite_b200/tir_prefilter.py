@@ -13,10 +13,9 @@ _CTX = None
 
 
 def _ctx():
-    global _CTX
-    if _CTX is None:
-        _CTX = _lib.Context(0)
-    return _CTX
+    """The stage process's context (shared with hite_b200.boundary: one context per process per GPU, HITE_GPU_DEVICES honoured)."""
+    from . import boundary
+    return boundary.get_context()
 
 
 def _records_to_dict(query_name, seq, recs, n):
