@@ -261,6 +261,7 @@ def test_stage_process_shards_candidates_over_gpus(monkeypatch, tmp_path):
     import threading
     from hite_b200 import boundary, fasta
     made, calls = [], []
+    sync = {"barrier": None}
 
     class FakeCtx:
         def __init__(self, device):
@@ -275,6 +276,8 @@ def test_stage_process_shards_candidates_over_gpus(monkeypatch, tmp_path):
             assert self.genome is not None
 
         def adjust(self, seqs, te_type, plant, result_type, flank=50):
+            if sync["barrier"] is not None:
+                sync["barrier"].wait(timeout=20)          # every GPU's call is in flight at the same time: one thread each
             calls.append((self.device, threading.get_ident(), list(seqs)))
             return [dict(is_te=len(s) % 3 != 0, info="", cons=s[2:-2], copy_num=7 + len(s) % 5) for s in seqs]
 
@@ -291,6 +294,7 @@ def test_stage_process_shards_candidates_over_gpus(monkeypatch, tmp_path):
     for devs in ("0", "0,1,2", "3,1"):
         monkeypatch.setenv("HITE_GPU_DEVICES", devs)
         made.clear(); calls.clear()
+        sync["barrier"] = threading.Barrier(len(devs.split(",")))
         monkeypatch.setattr(boundary, "_CTX", {})
         monkeypatch.setattr(boundary, "_GENOME", {})
         assert boundary.stage_devices() == [int(x) for x in devs.split(",")]
@@ -307,6 +311,8 @@ def test_stage_process_shards_candidates_over_gpus(monkeypatch, tmp_path):
     assert outs["0"] == outs["0,1,2"] == outs["3,1"]
     monkeypatch.setenv("WORLD_SIZE", "4"); monkeypatch.setenv("LOCAL_RANK", "1"); monkeypatch.setenv("HITE_GPU_DEVICES", "4,5,6,7")
     assert boundary.stage_devices() == [5]                                       # under torchrun a rank owns one GPU
+
+    sync["barrier"] = None
 
     class Boom(FakeCtx):
         def adjust(self, *a, **k):
