@@ -110,3 +110,45 @@ def test_reference_coarse_stage_equals_mirror_on_the_same_hsps(tmp_path, monkeyp
     U.flanking_seq(out_ref, out_ref + ".flanked", ref, 50)
     coarse.flanking_seq(out_ref, out_mine + ".flanked", ref, 50)
     assert open(out_ref + ".flanked").read() == open(out_mine + ".flanked").read()
+
+
+def test_mirror_reads_the_reference_chunkers_output(tmp_path, monkeypatch):
+    """split_genome_chunks.py (reference, run unmodified in-process) -> genome.cut{i}.fa -> hite_b200.coarse._chunk_to_chromosomes:
+    every chunk's records come back at their real coordinates (what is not in the chunk stays N), upper-cased, in file order --
+    the input contract of determine_repeat_boundary_v5 (row a1)."""
+    import runpy
+    import sys
+    from hite_b200 import coarse
+    ref_import.load_util()                                       # puts the reference's Util (third-party imports stubbed) in sys.modules
+    rng = np.random.default_rng(12)
+    B = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    genome = {"chrA": B[rng.integers(0, 9, 730_123)].tobytes().decode(), "chrB": B[rng.integers(0, 9, 250_000)].tobytes().decode(),
+              "scaffold_7 some description": B[rng.integers(0, 9, 99_999)].tobytes().decode()}
+    gpath = str(tmp_path / "genome.fa")
+    with open(gpath, "w") as f:
+        for n, s in genome.items():
+            f.write(">%s\n" % n)
+            for o in range(0, len(s), 80):
+                f.write(s[o:o + 80] + "\n")
+    out = tmp_path / "chunks"
+    out.mkdir()
+    script = os.path.join(ref_import.REF_ROOT, "module", "split_genome_chunks.py")
+    monkeypatch.setattr(sys, "argv", [script, "-g", gpath, "--tmp_output_dir", str(out), "--chrom_seg_length", "100000", "--chunk_size", "0.3"])
+    runpy.run_path(script, run_name="__main__")
+    cuts = sorted(p for p in os.listdir(out) if p.startswith("genome.cut"))
+    assert len(cuts) >= 3                                        # 0.3 MiB chunks: the genome spans several
+    seen = {}
+    for c in cuts:
+        names, chroms = coarse._chunk_to_chromosomes(str(out / c))
+        for n, arr in zip(names, chroms):
+            full = genome[[k for k in genome if k.split(" ")[0] == n][0]].upper()
+            s = arr.tobytes().decode()
+            assert len(s) <= len(full)
+            for i in range(0, len(s), 100_000):                  # a segment is either the real bases or not part of this chunk
+                piece = s[i:i + 100_000]
+                assert piece == full[i:i + 100_000] or set(piece) == {"N"}, (c, n, i)
+                if piece == full[i:i + 100_000] and set(piece) != {"N"}:
+                    assert (n, i) not in seen, "a segment appears in two chunks"
+                    seen[(n, i)] = c
+    total = sum((len(s) + 99_999) // 100_000 for s in genome.values())
+    assert len(seen) == total                                    # every segment is in exactly one chunk
