@@ -152,3 +152,62 @@ def test_mirror_reads_the_reference_chunkers_output(tmp_path, monkeypatch):
                     seen[(n, i)] = c
     total = sum((len(s) + 99_999) // 100_000 for s in genome.values())
     assert len(seen) == total                                    # every segment is in exactly one chunk
+
+
+def test_drop_in_script_runs_the_reference_stage_with_main_py_arguments(tmp_path, monkeypatch):
+    """module/coarse_boundary.py of this repo exactly as main.py invokes it (main.py:520-530): the reference's own stage script
+    runs -- its argparse, temp directory, logging, copy-back -- with determine_repeat_boundary_v5 rebound to the mirror (context
+    stood in, HSPs and chaining as above).  longest_repeats_{i}.fa and .flanked.fa appear in --tmp_output_dir."""
+    import sys
+    from hite_b200 import _lib, coarse, fasta
+    ref_import.load_util()
+    wl = synth.make_workload(genome_bp=2_400_000, n_contigs=2, n_families=12, cands_per_family=1, copies=(5, 10),
+                             length=(200, 1200), seed=63)
+    ref = str(tmp_path / "genome.fa")
+    wl.write_fasta(ref, str(tmp_path / "cand.fa"))
+    lens = [len(c) for c in wl.contig_seqs]
+    G = O.Genome(wl.contig_seqs)
+    hsps, segs, iv = G.coarse_boundary(lens, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64)
+    G.close()
+    cut = str(tmp_path / "genome.cut0.fa")
+    with open(cut, "w") as f:
+        for c, o in segs:
+            f.write(">%s$%d\n%s\n" % (wl.contig_names[c], o, wl.contig_seqs[c][o:o + 1_000_000].tobytes().decode()))
+
+    class OracleBackedCtx:
+        device = 0
+
+        def load_genome(self, chroms):
+            pass
+
+        def build_index(self, k, w):
+            return dict(kernel_ms=0.0)
+
+        def coarse_boundary(self, seg_len, skip_gap, max_len, occ_cap, threads):
+            out = np.zeros(len(iv), dtype=_lib.INTERVAL_DTYPE)
+            out["chr"] = [c for c, _, _ in iv]; out["start"] = [a for _, a, _ in iv]; out["end"] = [b for _, _, b in iv]
+            return out
+    monkeypatch.setattr(coarse, "get_context", lambda device=None: OracleBackedCtx())
+    monkeypatch.setenv("HITE_HOME", ref_import.REF_ROOT)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "module"))
+    import _hite_b200_patch as patch
+    outdir, work = tmp_path / "out", tmp_path / "work"
+    outdir.mkdir(); work.mkdir()
+    prev_te = str(tmp_path / "prev_TE.fa")
+    open(prev_te, "w").close()
+    monkeypatch.setattr(sys, "argv", ["coarse_boundary.py", "-g", cut, "--tmp_output_dir", str(outdir), "--prev_TE", prev_te,
+                                      "--fixed_extend_base_threshold", "2000", "--max_repeat_len", "30000", "--thread", "4",
+                                      "--flanking_len", "50", "--tandem_region_cutoff", "0.5", "--ref_index", "0", "-r", ref,
+                                      "--recover", "0", "--debug", "0", "-w", str(work)])
+    import Util
+    saved = Util.determine_repeat_boundary_v5
+    try:
+        patch.run_stage("coarse_boundary.py", patch_names=("determine_repeat_boundary_v5",), source="hite_b200.coarse")
+    finally:
+        Util.determine_repeat_boundary_v5 = saved
+    names, contigs = fasta.read_fasta(str(outdir / "longest_repeats_0.fa"))
+    assert sorted(names) == sorted({"%s:%d-%d" % (wl.contig_names[c], a, b) for c, a, b in iv}) and len(names) > 50
+    fnames, fcontigs = fasta.read_fasta(str(outdir / "longest_repeats_0.flanked.fa"))
+    assert len(fnames) == len(names) and all(len(s) >= 180 for s in fcontigs.values())
+    assert os.path.exists(str(outdir / "HiTE_coarse.log")) and not os.listdir(str(work))

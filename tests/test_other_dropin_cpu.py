@@ -88,3 +88,57 @@ def test_run_other_detection_consumes_the_mirror(tmp_path, monkeypatch):
                 any(abs(len(got[n]) - (b - a + 1)) <= 4 and got[n] in genome[names[c]][a - 9:b + 8] for c, a, b in spans)]
         assert hits, (name, [len(got[n]) for n in got_names if n.split("#")[1] == cls])
     assert all(len(s) >= 80 for s in got.values())                           # min_TE_len filter (:78-81)
+
+
+def test_drop_in_script_runs_the_reference_other_stage_with_main_py_arguments(tmp_path, monkeypatch):
+    """module/judge_Other_transposons.py of this repo as main.py invokes it (main.py:455-461): the reference's own stage script
+    (argparse, temp directory, logging, copy-back) with multi_process_align_and_get_copies rebound to the mirror."""
+    from hite_b200 import _lib, boundary, fasta, other
+    ref_import.load_util()
+    lib_names, lib = fasta.read_fasta(os.path.join(ref_import.REF_ROOT, "library", "non_LTR.lib"))
+    rng = np.random.default_rng(9)
+    chosen = [n for n in lib_names if 400 <= len(lib[n]) <= 2000 and set(lib[n]) <= set("ACGT")][::211][:5]
+    contig = bytearray(_B[rng.integers(0, 4, 200_000)].tobytes())
+    pos = 3_000
+    for name in chosen:
+        s = lib[name]
+        contig[pos:pos + len(s)] = s.encode()
+        pos += len(s) + 2_000
+    gpath = str(tmp_path / "genome.fa")
+    fasta.store_fasta({"chr_0": bytes(contig).decode()}, gpath)
+    G = O.Genome([bytes(contig)])
+
+    class OracleBackedCtx:
+        device = 0
+        contig_names = ["chr_0"]
+
+        def query_hsps(self, seqs, occ_cap=512, max_loci=128):
+            rows = [(qi, h["contig"], h["qs"], h["qe"], h["ss"], h["se"], h["n_match"], h["aln_len"], h["score"], h["rank"])
+                    for qi, q in enumerate(seqs) for h in G.query_hsps(q, occ_cap, max_loci)]
+            return np.array(rows, dtype=_lib.QHSP_DTYPE) if rows else np.zeros(0, dtype=_lib.QHSP_DTYPE)
+
+        def timing(self):
+            return dict(kernel_ms=0.0, k_ms=[0.0] * 8)
+    ctx = OracleBackedCtx()
+    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "ensure_genome", lambda c, ref, k=15, w=10, _parsed=None: c)
+    monkeypatch.setenv("HITE_HOME", ref_import.REF_ROOT)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "module"))
+    import _hite_b200_patch as patch
+    outdir, work = tmp_path / "out", tmp_path / "work"
+    outdir.mkdir(); work.mkdir()
+    monkeypatch.setattr(sys, "argv", ["judge_Other_transposons.py", "-r", gpath, "-t", "4", "--tmp_output_dir", str(outdir),
+                                      "--recover", "0", "--min_TE_len", "80", "-w", str(work)])
+    import Util
+    saved = Util.multi_process_align_and_get_copies
+    try:
+        patch.run_stage("judge_Other_transposons.py", patch_names=("multi_process_align_and_get_copies",), source="hite_b200.other")
+    finally:
+        Util.multi_process_align_and_get_copies = saved
+        G.close()
+    names, got = fasta.read_fasta(str(outdir / "confident_other.fa"))
+    assert len(names) >= len(chosen) and all(n.startswith("Homology_Non_LTR_") for n in names)
+    for name in chosen:
+        assert lib[name] in got.values(), name                     # the planted full-length copy, sliced from the genome
+    assert os.path.exists(str(outdir / "HiTE_other.log"))
