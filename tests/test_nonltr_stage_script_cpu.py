@@ -1,0 +1,100 @@
+"""The de novo non-LTR module as main.py runs it, end to end on the CPU through THIS repository's drop-in script:
+module/judge_Non_LTR_transposons.py -> the reference's own stage code (argparse, candidate generation call, cd-hit-est calls,
+the boundary-adjustment round, the LINE-domain rescue, length filter, rename_fasta, lib_add_prefix, update_prev_TE, copy-back)
+with get_candidate_non_ltr_parallel and flank_region_align_v5 rebound to the mirrors.  The GPU context is stood in by the
+oracle, `cd-hit-est` by a copying stand-in, the blastx domain search (get_domain_info) finds nothing.  A functional check of the
+whole stage boundary: planted poly-A elements with target-site duplications come out as confident_non_ltr_{i}.fa records.
+Needs the reference checkout (skipped on the GPU box)."""
+import os
+import stat
+import sys
+
+import numpy as np
+import pytest
+
+from hite_b200 import synth
+from oracle import oracle as O
+from oracle import ref_import
+from test_tir_stage_script_cpu import FAKE_CDHIT
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference checkout not mounted")
+
+
+def test_nonltr_stage_script_end_to_end(tmp_path, monkeypatch):
+    from hite_b200 import _lib, boundary, fasta
+    ref_import.load_util()
+    wl = synth.make_workload(genome_bp=1_200_000, n_contigs=2, n_families=10, cands_per_family=2, copies=(8, 20),
+                             length=(250, 1400), seed=93, kind="non_ltr")
+    ref = str(tmp_path / "genome.fa")
+    wl.write_fasta(ref, str(tmp_path / "cand_unused.fa"))
+    _, ref_contigs = fasta.read_fasta(ref)
+    flanked = {}
+    for name in wl.cand_names:
+        c, span = name.split(":")
+        a, b = (int(x) for x in span.split("-"))
+        if a - 50 >= 0 and b + 50 <= len(ref_contigs[c]):
+            flanked["%s:%d-%d" % (c, a - 50, b + 50)] = ref_contigs[c][a - 50:b + 50]
+    fpath = str(tmp_path / "longest_repeats_0.flanked.fa")
+    fasta.store_fasta(flanked, fpath)
+    G = O.Genome(wl.contig_seqs)
+
+    class OracleBackedCtx:
+        device = 0
+
+        def nonltr_candidates(self, seqs, flanking_len=50):
+            out = np.zeros(len(seqs), dtype=_lib.POLYA_DTYPE)
+            for i, s in enumerate(seqs):
+                for k, v in O.search_polyA_TSD(s, flanking_len)[3].items():
+                    out[i][k] = v
+            return out
+
+        def timing(self):
+            return dict(kernel_ms=0.0)
+
+        def adjust(self, seqs, te, plant, result_type, flank=50):
+            assert te == "non_ltr"
+            res = []
+            for s in seqs:
+                cps, rows = G.candidate_msa(s.encode())
+                res.append(O.judge_with_trunc_gate(s, cps, rows, judge=lambda c, r: O.judge_v9(c, r)) if rows
+                           else dict(is_te=False, info="", cons="", copy_num=0))
+            return res
+    ctx = OracleBackedCtx()
+    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "ensure_genome", lambda c, r, k=15, w=10, _parsed=None: c)
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    p = bindir / "cd-hit-est"
+    p.write_text(FAKE_CDHIT % sys.executable)
+    p.chmod(p.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(bindir) + os.pathsep + os.environ["PATH"])
+    monkeypatch.setenv("HITE_HOME", ref_import.REF_ROOT)
+    monkeypatch.setenv("HITE_GPU_DEVICES", "0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "module"))
+    import _hite_b200_patch as patch
+    outdir, work = tmp_path / "out", tmp_path / "work"
+    outdir.mkdir(); work.mkdir()
+    prev_te, low = str(tmp_path / "prev_TE.fa"), str(tmp_path / "all_low_copy_non_ltr.fa")
+    open(prev_te, "w").close()
+    monkeypatch.setattr(sys, "argv", ["judge_Non_LTR_transposons.py", "--seqs", fpath, "-t", "4", "--tmp_output_dir", str(outdir),
+                                      "--recover", "0", "--plant", "1", "--debug", "0", "--flanking_len", "50", "--ref_index", "0",
+                                      "--is_denovo_nonltr", "1", "-r", ref, "--split_ref_dir", str(tmp_path / "ref_chr"),
+                                      "--prev_TE", prev_te, "--all_low_copy_non_ltr", low, "--min_TE_len", "80", "-w", str(work)])
+    import Util
+    names_patched = ("flank_region_align_v5", "run_find_members_v8", "is_TE_from_align_file", "get_candidate_non_ltr_parallel", "get_domain_info")
+    saved = {n: getattr(Util, n) for n in names_patched}
+    Util.get_domain_info = lambda cons, lib, output_table, threads, temp_dir: open(output_table, "w").write("#\n#\n")   # blastx: nothing found
+    try:
+        patch.run_stage("judge_Non_LTR_transposons.py", extra=(("get_candidate_non_ltr_parallel", "hite_b200.nonltr_prefilter"),))
+    finally:
+        for n, f in saved.items():
+            setattr(Util, n, f)
+        G.close()
+    names, got = fasta.read_fasta(str(outdir / "confident_non_ltr_0.fa"))
+    assert len(names) >= 5 and all("Non-LTR_0_" in n for n in names)              # rename_fasta + lib_add_prefix
+    truth = {t["consensus"].decode() for t in wl.truth}
+    close = sum(1 for s in got.values() if any(s in t or t in s or s[:200] == t[:200] for t in truth))
+    assert close >= 0.6 * len(names), (close, len(names))
+    assert open(prev_te).read().count(">") == len(names)                          # update_prev_TE
+    print("non-LTR stage: %d flanked candidates -> %d confident records, %d matching a planted element" % (len(flanked), len(names), close))
