@@ -436,3 +436,41 @@ def test_coarse_masking_leaves_border_crossing_copies(monkeypatch):
     assert f.masked == [(0, 5000, 6000), (0, 1_999_000, 2_000_000)] and fresh == 2000     # the copy across 1 000 000 stays
     iv, fresh = masking.mask_context(f, ["te1"], {"te1": "A" * 1000})
     assert len(f.masked) == 3
+
+
+def test_smoke_next_rows_block_dry_run():
+    """__graft_entry__._smoke_next_rows (the part of smoke() that exercises the section-8f kernels on the GPU box) run on the CPU
+    against a stand-in context backed by the oracle: catches a typo in the checker code before the box does."""
+    import numpy as np
+    import __graft_entry__ as entry
+    from hite_b200 import _lib, synth
+    from oracle import oracle as O
+    wl = synth.make_workload(genome_bp=400_000, n_contigs=2, n_families=4, cands_per_family=2, copies=(6, 10),
+                             length=(200, 1200), seed=7)
+    G = O.Genome(wl.contig_seqs)
+
+    class OracleBackedCtx:
+        def query_hsps(self, seqs, occ_cap=512, max_loci=128):
+            rows = [(qi, h["contig"], h["qs"], h["qe"], h["ss"], h["se"], h["n_match"], h["aln_len"], h["score"], h["rank"])
+                    for qi, q in enumerate(seqs) for h in G.query_hsps(q)]
+            return np.array(rows, dtype=_lib.QHSP_DTYPE)
+
+        def tsd_candidates(self, seqs, raw_starts, raw_ends, d, plant):
+            out = np.zeros((len(seqs), 100), dtype=_lib.TSD_DTYPE)
+            cnt = np.zeros(len(seqs), dtype=np.uint32)
+            for i, (s, a, b) in enumerate(zip(seqs, raw_starts, raw_ends)):
+                r = O.search_confident_tir_v4(s, a, b, d, plant)
+                cnt[i] = len(r)
+                for j, x in enumerate(r):
+                    for f in ("k", "start", "end", "dist", "idx", "short_class"):
+                        out[i][j][f] = x[f]
+            return out, cnt
+
+        def nonltr_candidates(self, seqs, flanking_len=50):
+            out = np.zeros(len(seqs), dtype=_lib.POLYA_DTYPE)
+            for i, s in enumerate(seqs):
+                for k, v in O.search_polyA_TSD(s, flanking_len)[3].items():
+                    out[i][k] = v
+            return out
+    entry._smoke_next_rows(OracleBackedCtx(), G, wl)
+    G.close()
