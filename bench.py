@@ -28,7 +28,7 @@ import numpy as np  # noqa: E402
 
 
 def workload_for(world, small=False):
-    from hite_b200 import synth
+    from workloads import synth
     if small:
         return synth.make_workload(genome_bp=4_000_000 * world, n_contigs=2, n_families=40 * world, cands_per_family=10,
                                    copies=(10, 40), seed=1), "synthetic 4 Mbp x N, 400 TIR candidates per GPU (--small)"
@@ -340,7 +340,7 @@ def main():
         if world == 1 and not args.small:
             # the metric is reported per TE type.  Helitron / non-LTR candidates take the same
             # copy search + MSA and their own judges (judge_boundary_v6 / v9); 30 Mbp genome, 3000 candidates each.
-            from hite_b200 import synth
+            from workloads import synth
             per_type = {"tir": float(n_total * args.steps / dev_max)}
             for kind in ("helitron", "non_ltr"):
                 wk = synth.make_workload(genome_bp=30_000_000, n_contigs=3, n_families=300, cands_per_family=10, copies=(10, 40),

@@ -188,6 +188,7 @@ def load():
     lib.hb_vote_matrices.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp,
                                      C.c_uint64]
     lib.hb_genome_load.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.hb_genome_contig_rank.argtypes = [vp, vp, C.c_uint32]
     lib.hb_index_build.argtypes = [vp, C.c_int, C.c_int]
     lib.hb_genome_info.argtypes = [vp, u64p, u64p, vp, C.c_uint32]
     lib.hb_adjust.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(HbParams), vp, u64p]
@@ -195,6 +196,7 @@ def load():
     lib.hb_last_cons_device.argtypes = [vp, C.POINTER(vp), u64p]
     lib.hb_last_copies.argtypes = [vp, vp, C.c_uint64, u64p]
     lib.hb_debug_index.argtypes = [vp, vp, C.c_uint64]
+    lib.hb_debug_scan_total.argtypes = [vp, C.c_uint64, C.c_uint32, u64p, C.POINTER(C.c_uint32)]
     lib.hb_last_msa.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
     lib.hb_fmea_chain.argtypes = [vp, vp, C.c_uint32, vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
     lib.hb_query_copies.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, vp,
@@ -218,6 +220,15 @@ def load():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def contig_name_rank(contig_names):
+    """rank[c] = position of contig c among the names sorted by (name + ':') bytewise: the order of the member names
+    ``contig:start-end(strand)`` that tools/ready_for_MSA.sh's ``sort -nk 2 -r`` falls back on (C / POSIX locale)."""
+    order = sorted(range(len(contig_names)), key=lambda i: (contig_names[i] + ":").encode())
+    rank = np.zeros(len(contig_names), dtype=np.int32)
+    rank[order] = np.arange(len(contig_names), dtype=np.int32)
+    return rank
 
 
 def _calls_to_dicts(calls, cons_b):
@@ -306,8 +317,10 @@ class Context:
         return _calls_to_dicts(calls, cons.tobytes())
 
     # ------------------------------------------------------------------------------------
-    def load_genome(self, contig_seqs):
-        """Kernel (i) part 1.  ``contig_seqs``: list of bytes / uint8 arrays (ASCII, any case)."""
+    def load_genome(self, contig_seqs, contig_names=None):
+        """Kernel (i) part 1.  ``contig_seqs``: list of bytes / uint8 arrays (ASCII, any case).  ``contig_names``: their
+        FASTA names -- the "100 longest members" rule breaks length ties by member name (tools/ready_for_MSA.sh:63), so the
+        library needs the names' bytewise order (``hb_genome_contig_rank``); without names the contig index is used."""
         seqs = [np.frombuffer(x, dtype=np.uint8) if isinstance(x, (bytes, bytearray)) else
                 (np.frombuffer(x.encode("ascii"), dtype=np.uint8) if isinstance(x, str) else np.asarray(x, dtype=np.uint8))
                 for x in contig_seqs]
@@ -316,7 +329,14 @@ class Context:
         flat = np.concatenate(seqs) if len(seqs) > 1 else np.ascontiguousarray(seqs[0])
         self._check(self._lib.hb_genome_load(self._h, _ptr(flat), _ptr(off), len(seqs)), "hb_genome_load")
         self.contig_lens = [len(x) for x in seqs]
-        return self.timing()
+        tm = self.timing()
+        if contig_names is not None:
+            if len(contig_names) != len(seqs):
+                raise ValueError("contig_names and contig_seqs differ in length")
+            self.contig_names = list(contig_names)
+            rank = contig_name_rank(contig_names)
+            self._check(self._lib.hb_genome_contig_rank(self._h, _ptr(rank), len(rank)), "hb_genome_contig_rank")
+        return tm
 
     def build_index(self, k=15, w=10):
         self._check(self._lib.hb_index_build(self._h, int(k), int(w)), "hb_index_build")
@@ -328,13 +348,18 @@ class Context:
         self._check(self._lib.hb_genome_info(self._h, C.byref(tot), C.byref(nmm), _ptr(goff), len(goff)), "hb_genome_info")
         return dict(total_padded=tot.value, n_minimizers=nmm.value, contig_goff=goff)
 
+    def debug_scan_total(self, n, value):
+        tot, last = C.c_uint64(0), C.c_uint32(0)
+        self._check(self._lib.hb_debug_scan_total(self._h, int(n), int(value), C.byref(tot), C.byref(last)), "hb_debug_scan_total")
+        return tot.value, last.value
+
     def debug_index(self):
         n = self.genome_info()["n_minimizers"]
         keys = np.zeros(max(1, n), dtype=np.uint64)
         self._check(self._lib.hb_debug_index(self._h, _ptr(keys), len(keys)), "hb_debug_index")
         return keys[:n]
 
-    def adjust_raw(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=128, flank=50,
+    def adjust_raw(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=300, flank=50,
                    max_rows=100, tb_budget_bytes=0, trunc_gate=True, overlap=None):
         """One ``flank_region_align_v5``-equivalent round (kernels ii + iii) over the candidates.
         Returns ``(calls, cons)``: a structured array (CALL_DTYPE, one record per candidate) and the
@@ -434,7 +459,7 @@ class Context:
         self._check(self._lib.hb_genome_export(self._h, int(contig), _ptr(out), len(out)), "hb_genome_export")
         return out.tobytes()
 
-    def query_hsps(self, query_seqs, occ_cap=512, max_loci=128):
+    def query_hsps(self, query_seqs, occ_cap=512, max_loci=300):
         """Library-vs-genome local alignments (``hb_query_hsps``; replaces the blastn of reference module/Util.py:7213-7225)
         -> QHSP_DTYPE records ordered by (query, locus rank)."""
         if isinstance(query_seqs, tuple):

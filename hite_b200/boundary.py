@@ -68,8 +68,7 @@ def ensure_genome(ctx, reference, k=15, w=10, _parsed=None):
     key = (os.path.abspath(reference), st.st_mtime_ns, st.st_size, k, w)
     if _GENOME.get(ctx.device) != key:
         names, contigs = _parsed if _parsed is not None else read_fasta(reference)
-        ctx.contig_names = names
-        ctx.load_genome([contigs[n].encode("ascii") for n in names])
+        ctx.load_genome([contigs[n].encode("ascii") for n in names], names)
         ctx.build_index(k, w)
         _GENOME[ctx.device] = key
     return ctx
@@ -97,9 +96,17 @@ def adjust_on_devices(seqs, reference, TE_type, plant, result_type, flanking_len
     def work(dev, mine):
         try:
             ctx = ensure_genome(get_context(dev), reference, _parsed=parsed)
-            for b in range(0, len(mine), 65536):
-                chunk = mine[b:b + 65536]
-                res = ctx.adjust([seqs[i] for i in chunk], TE_type, int(plant), result_type, flank=int(flanking_len))
+            todo = [mine[b:b + 65536] for b in range(0, len(mine), 65536)]
+            while todo:
+                chunk = todo.pop(0)
+                try:
+                    res = ctx.adjust([seqs[i] for i in chunk], TE_type, int(plant), result_type, flank=int(flanking_len))
+                except _lib.HiteB200Error as e:
+                    # HB_ENOMEM (-4: too many seed hits / MSA columns for one call, or the device is full): halve and retry
+                    if "(-4)" not in str(e) or len(chunk) < 2:
+                        raise
+                    todo[:0] = [chunk[:len(chunk) // 2], chunk[len(chunk) // 2:]]
+                    continue
                 for i, r in zip(chunk, res):
                     results[i] = r
         except Exception as e:                               # surfaced in the caller's thread: no silent partial result

@@ -108,12 +108,37 @@ qhsp_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAln* __
     if (lane == 0) out[p] = r;
 }
 
+// Bytewise order of the decimal strings of two positive numbers, the shorter string being smaller when it is a
+// prefix of the longer one (in a member name the number is followed by '-' or '(', both below every digit).
+__device__ __forceinline__ int dec_lex_cmp(int64_t a, int64_t b) {
+    if (a == b) return 0;
+    int da = 1, db = 1;
+    for (int64_t t = a; t >= 10; t /= 10) ++da;
+    for (int64_t t = b; t >= 10; t /= 10) ++db;
+    int64_t pa = a, pb = b;                               // leading min(da, db) digits of each
+    for (int t = da; t > db; --t) pa /= 10;
+    for (int t = db; t > da; --t) pb /= 10;
+    if (pa != pb) return pa < pb ? -1 : 1;
+    return da < db ? -1 : 1;
+}
+// is copy y's member name `contig:start1-end1(strand)` bytewise larger than copy x's ?  (tools/ready_for_MSA.sh:63)
+__device__ __forceinline__ bool name_greater(const int32_t* __restrict__ crank, const HbAln& y, uint32_t rel_y, const HbAln& x,
+                                             uint32_t rel_x) {
+    const int ry = crank[y.contig], rx = crank[x.contig];
+    if (ry != rx) return ry > rx;
+    int c = dec_lex_cmp(y.start1, x.start1);
+    if (c) return c > 0;
+    c = dec_lex_cmp(y.end1, x.end1);
+    if (c) return c > 0;
+    return rel_y > rel_x;                                 // '-' (0x2D) > '+' (0x2B)
+}
+
 // S8 dedup + S9 "max_rows longest": warp per candidate
 constexpr int SEL_MAX = 512;
 __global__ void __launch_bounds__(128)
 copy_select_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, uint32_t n_cand,
-                   int max_rows, int trunc_gate, HbAln* __restrict__ alns, uint32_t* __restrict__ n_rows,
-                   uint32_t* __restrict__ n_trows) {
+                   int max_rows, int trunc_gate, const int32_t* __restrict__ crank, HbAln* __restrict__ alns,
+                   uint32_t* __restrict__ n_rows, uint32_t* __restrict__ n_trows) {
     __shared__ uint8_t s_keep[4][SEL_MAX];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = blockIdx.x * 4 + wid;
@@ -141,12 +166,16 @@ copy_select_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict
     if (nk > max_rows) {
         for (int x = lane; x < n; x += 32) {
             if (!keep[x]) continue;
-            const int lx = alns[p0 + x].ext_len;
+            // the 100 longest, length ties to the bytewise larger member name (sort -nk 2 -r, tools/ready_for_MSA.sh:63)
+            const HbAln ax = alns[p0 + x];
+            const uint32_t relx = pairs[p0 + x].rel;
+            const int lx = ax.ext_len;
             int longer = 0;
             for (int y = 0; y < n; ++y) {
                 if (y == x || !keep[y]) continue;
                 const int ly = alns[p0 + y].ext_len;
-                longer += (ly > lx || (ly == lx && y < x)) ? 1 : 0;
+                if (ly > lx) ++longer;
+                else if (ly == lx && name_greater(crank, alns[p0 + y], pairs[p0 + y].rel, ax, relx)) ++longer;
             }
             if (longer >= max_rows) keep[x] = 2;
         }
@@ -323,9 +352,10 @@ cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const 
     return cudaGetLastError();
 }
 cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, int max_rows,
-                                  int trunc_gate, HbAln* alns, uint32_t* n_rows, uint32_t* n_trows, cudaStream_t s) {
+                                  int trunc_gate, const int32_t* crank, HbAln* alns, uint32_t* n_rows, uint32_t* n_trows,
+                                  cudaStream_t s) {
     if (n_cand == 0) return cudaSuccess;
-    copy_select_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, max_rows, trunc_gate, alns, n_rows,
+    copy_select_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, max_rows, trunc_gate, crank, alns, n_rows,
                                                         n_trows);
     return cudaGetLastError();
 }

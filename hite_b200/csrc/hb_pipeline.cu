@@ -137,6 +137,12 @@ extern "C" int hb_genome_load(hb_ctx* ctx, const uint8_t* ascii, const uint64_t*
     ENSURE("g.glen", sizeof(uint64_t) * (n_contig + 1));
     ENSURE("g.seq2", L.tot / 4 + 64);
     ENSURE("g.nmask", L.tot / 8 + 64);
+    ENSURE("g.crank", sizeof(int32_t) * (n_contig + 1));
+    {   // name order of the contigs for the S9 tie rule: the contig index until hb_genome_contig_rank says otherwise
+        std::vector<int32_t> ident(n_contig);
+        for (uint32_t c = 0; c < n_contig; ++c) ident[c] = (int32_t)c;
+        HB_CUDA_OK(cudaMemcpy(ctx->buf("g.crank").p, ident.data(), sizeof(int32_t) * n_contig, cudaMemcpyHostToDevice));
+    }
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("g.ascii").p, ascii, ascii_bytes, cudaMemcpyHostToDevice, s));
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("g.src_off").p, contig_off, sizeof(uint64_t) * (n_contig + 1), cudaMemcpyHostToDevice, s));
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("g.goff").p, L.goff.data(), sizeof(uint64_t) * n_contig, cudaMemcpyHostToDevice, s));
@@ -154,6 +160,22 @@ extern "C" int hb_genome_load(hb_ctx* ctx, const uint8_t* ascii, const uint64_t*
     ctx->timing.h2d_bytes = ascii_bytes;
     ctx->timing.launches = 1;
     ctx->have_genome = true;
+    return HB_OK;
+}
+
+extern "C" int hb_genome_contig_rank(hb_ctx* ctx, const int32_t* rank, uint32_t n_contig) {
+    if (!ctx || !rank) return hb_fail_msg(ctx, HB_EINVAL, "hb_genome_contig_rank: null argument");
+    if (!ctx->have_genome) return hb_fail_msg(ctx, HB_ESTATE, "hb_genome_contig_rank: call hb_genome_load first");
+    if (n_contig != ctx->g_ncontig) return hb_fail_msg(ctx, HB_EINVAL, "hb_genome_contig_rank: n_contig differs from the loaded genome");
+    std::vector<uint8_t> seen(n_contig, 0);
+    for (uint32_t c = 0; c < n_contig; ++c) {
+        if (rank[c] < 0 || (uint32_t)rank[c] >= n_contig || seen[(size_t)rank[c]])
+            return hb_fail_msg(ctx, HB_EINVAL, "hb_genome_contig_rank: rank must be a permutation of 0..n_contig-1");
+        seen[(size_t)rank[c]] = 1;
+    }
+    cudaSetDevice(ctx->device);
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("g.crank").p, rank, sizeof(int32_t) * n_contig, cudaMemcpyHostToDevice, ctx->stream));
+    HB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return HB_OK;
 }
 
@@ -222,6 +244,31 @@ extern "C" int hb_genome_info(hb_ctx* ctx, uint64_t* total_padded, uint64_t* n_m
     if (total_padded) *total_padded = ctx->g_tot;
     if (n_minimizers) *n_minimizers = ctx->have_index ? ctx->g_nmm : 0;
     if (contig_goff) for (uint32_t c = 0; c < ctx->g_ncontig && c < cap; ++c) contig_goff[c] = ctx->g_goff[c];
+    return HB_OK;
+}
+
+namespace {
+__global__ void fill_u32_kernel(uint32_t* __restrict__ a, uint64_t n, uint32_t v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+}  // namespace
+
+// Test hook: exclusive scan of n copies of `value`; *total must be the exact 64-bit n * value even where the 32-bit
+// offsets have wrapped (every size guard of hb_adjust / hb_coarse_boundary relies on that), *last = the last offset.
+extern "C" int hb_debug_scan_total(hb_ctx* ctx, uint64_t n, uint32_t value, uint64_t* total, uint32_t* last) {
+    if (!ctx || !total || n == 0 || n > (1ull << 28)) return hb_fail_msg(ctx, HB_EINVAL, "hb_debug_scan_total: bad argument");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ENSURE("d.in", sizeof(uint32_t) * n); ENSURE("d.out", sizeof(uint32_t) * n);
+    ENSURE("d.tmp", sizeof(uint32_t) * hb_scan_tmp_words(n)); ENSURE("d.total", sizeof(uint64_t));
+    fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctx->buf("d.in").as<uint32_t>(), n, value);
+    HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("d.in").as<uint32_t>(), ctx->buf("d.out").as<uint32_t>(), n,
+                                     ctx->buf("d.tmp").as<uint32_t>(), ctx->buf("d.total").as<uint64_t>(), s));
+    HB_CUDA_OK(cudaMemcpyAsync(total, ctx->buf("d.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (last) HB_CUDA_OK(cudaMemcpyAsync(last, ctx->buf("d.out").as<uint32_t>() + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    ctx->buf("d.in").release(); ctx->buf("d.out").release();
     return HB_OK;
 }
 
@@ -452,7 +499,7 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
     HB_CUDA_OK(hb_copy_filter_launch(LB("p.pairs").as<HbLocus>(), n_pairs, d_clen, ctx->buf("g.goff").as<uint64_t>(),
                                      ctx->buf("g.glen").as<uint64_t>(), ctx->g_ncontig, tot, flank, LB("p.alns").as<HbAln>(), s));
     HB_CUDA_OK(hb_copy_select_launch(LB("p.pairs").as<HbLocus>(), LB("s.pair_off").as<uint32_t>(), n_cand,
-                                     prm->max_rows, trunc_gate, LB("p.alns").as<HbAln>(),
+                                     prm->max_rows, trunc_gate, ctx->buf("g.crank").as<int32_t>(), LB("p.alns").as<HbAln>(),
                                      LB("m.n_rows").as<uint32_t>(), LB("m.n_trows").as<uint32_t>(), s));
     HB_CUDA_OK(hb_ins_max_launch(LB("p.pairs").as<HbLocus>(), n_pairs, LB("p.alns").as<HbAln>(),
                                  LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(), d_coff,

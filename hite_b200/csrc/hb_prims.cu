@@ -48,18 +48,22 @@ scan_tile_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 
-// single CTA: exclusive scan of the tile sums in place, grand total to *total
+// single CTA: exclusive scan of the tile sums in place, grand total to *total.  The offsets are 32-bit (callers index
+// buffers of < 2^32 elements with them) and wrap silently beyond that, so the grand total is accumulated separately in
+// 64 bits: a caller compares it with its limit BEFORE it sizes or fills anything from the offsets.
 __global__ void __launch_bounds__(1024)
 scan_middle(uint32_t* __restrict__ tile_sums, size_t n_tiles, uint64_t* __restrict__ total) {
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_carry;
+    __shared__ unsigned long long s_total;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) { s_carry = 0; s_total = 0; }
     __syncthreads();
-    uint64_t grand = 0;
+    unsigned long long mine = 0;
     for (size_t b = 0; b < n_tiles; b += 1024) {
         size_t i = b + threadIdx.x;
         uint32_t v = i < n_tiles ? tile_sums[i] : 0, x = v;
+        mine += v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(HB_FULL, x, o);
@@ -83,9 +87,12 @@ scan_middle(uint32_t* __restrict__ tile_sums, size_t n_tiles, uint64_t* __restri
         __syncthreads();
         if (threadIdx.x == 1023) { s_carry = excl + v; }
         __syncthreads();
-        grand = s_carry;
     }
-    if (threadIdx.x == 0 && total) *total = grand;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(HB_FULL, mine, o);
+    if (lane == 0 && mine) atomicAdd(&s_total, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && total) *total = s_total;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)

@@ -38,7 +38,7 @@ def _tiles(seq):
     return [(o, seq[o:o + MAX_QUERY]) for o in range(0, len(seq), MAX_QUERY)]
 
 
-def query_hsp_records(ctx, names, contigs, occ_cap=512, max_loci=128):
+def query_hsp_records(ctx, names, contigs, occ_cap=512, max_loci=300):
     """All HSPs of the library against the genome resident in ``ctx`` as one REC_DTYPE array (query = index into
     ``names``, subj = contig index; 1-based inclusive spans, ss > se = minus strand, ident = 100 * matches / columns
     rounded to 3 decimals like outfmt 6).  Self hits (query name == subject name) are dropped (module/Util.py:7045)."""
@@ -81,7 +81,7 @@ def query_hsp_records(ctx, names, contigs, occ_cap=512, max_loci=128):
     return rec
 
 
-def query_hsps(ctx, names, contigs, occ_cap=512, max_loci=128):
+def query_hsps(ctx, names, contigs, occ_cap=512, max_loci=300):
     """{query_name: {subject_name: [(q_start, q_end, s_start, s_end, identity), ...]}} -- the ``query_records`` dict of
     get_copies_v1 (module/Util.py:7033-7055), HSPs of a query in (locus rank) order."""
     rec = query_hsp_records(ctx, names, contigs, occ_cap, max_loci)

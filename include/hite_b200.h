@@ -105,6 +105,16 @@ int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_ascii, const u
 int hb_genome_load(hb_ctx* ctx, const uint8_t* ascii, const uint64_t* contig_off, uint32_t n_contig);
 
 /*
+ * hb_genome_contig_rank -- the order of the contig NAMES, which the "100 longest members" rule needs: the reference
+ * subsets a member file of more than 100 copies with `sh tools/ready_for_MSA.sh <file> 100 100` (module/Util.py:10409-10412),
+ * whose `sort -nk 2 -r` on the samtools .fai lines (tools/ready_for_MSA.sh:63) breaks a length tie by a reversed whole-line
+ * comparison, i.e. by the member name `contig:start-end(strand)` bytewise descending.  rank[c] = position of contig c when the
+ * contigs are sorted by (name + ':') bytewise ascending.  Optional: after hb_genome_load the rank is the contig index
+ * (correct whenever the FASTA lists its contigs in that order).  Call it after hb_genome_load, before hb_adjust.
+ */
+int hb_genome_contig_rank(hb_ctx* ctx, const int32_t* rank, uint32_t n_contig);
+
+/*
  * hb_index_build -- kernel (i), part 2: (k,w)-minimizer sketch of both strands, hand-written LSD
  * radix sort with shared-memory binning, 22-bit bucket table.  Replaces `minimap2 -I 20G -d ref.mmi`
  * (module/Util.py:7938-7947).  8 <= k <= 15, 1 <= w <= 16; HiTE-equivalent default k=15, w=10.
@@ -112,6 +122,9 @@ int hb_genome_load(hb_ctx* ctx, const uint8_t* ascii, const uint64_t* contig_off
  */
 int hb_index_build(hb_ctx* ctx, int k, int w);
 int hb_genome_info(hb_ctx* ctx, uint64_t* total_padded, uint64_t* n_minimizers, uint64_t* contig_goff, uint32_t cap);
+/* Test hook: device exclusive scan of n copies of `value`: *total = exact 64-bit sum (the size guards of hb_adjust and
+ * hb_coarse_boundary compare it with their limits before anything is sized from the 32-bit offsets), *last = last offset. */
+int hb_debug_scan_total(hb_ctx* ctx, uint64_t n, uint32_t value, uint64_t* total, uint32_t* last);
 
 typedef struct {
     int32_t occ_cap;      /* occurrences used per minimizer (first occ_cap in position order); 512 */

@@ -34,7 +34,7 @@ struct hbo_genome {
     uint64_t *goff;    /* n_contig global offsets */
     uint64_t *glen;
     int32_t *crank;    /* rank of every contig by (name + ':') bytewise, or NULL: see hbo_genome_set_tie_rule */
-    int tie_rule;      /* S9 tie rule: 0 = earlier-ranked copy (what the kernels do today), 1 = ready_for_MSA.sh's */
+    int tie_rule;      /* S9 tie rule: 1 = ready_for_MSA.sh's (default, what the kernels do), 0 = earlier-ranked copy */
 };
 
 static inline uint8_t code_of(uint8_t c) {
@@ -44,6 +44,7 @@ static inline uint8_t code_of(uint8_t c) {
 hbo_genome *hbo_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_t n) {
     hbo_genome *g = (hbo_genome *)calloc(1, sizeof(*g));
     g->n_contig = n;
+    g->tie_rule = 1;
     g->goff = (uint64_t *)malloc(sizeof(uint64_t) * (n + 1));
     g->glen = (uint64_t *)malloc(sizeof(uint64_t) * (n + 1));
     uint64_t p = PAD;
@@ -57,8 +58,7 @@ hbo_genome *hbo_genome_create(const uint8_t *ascii, const uint64_t *off, uint32_
 }
 void hbo_genome_free(hbo_genome *g) { if (g) { free(g->code); free(g->goff); free(g->glen); free(g->crank); free(g); } }
 
-/* S9 tie rule of the reference's tools/ready_for_MSA.sh, kept next to the current one until the kernels follow (DESIGN.md
-   section 9, item 1): `sort -nk 2 -r` on the .fai lines breaks a length tie by a reversed whole-line comparison, i.e. the member
+/* S9 tie rule of the reference's tools/ready_for_MSA.sh (the default; copy_select_kernel follows it): `sort -nk 2 -r` on the .fai lines breaks a length tie by a reversed whole-line comparison, i.e. the member
    whose name "contig:start1-end1(strand)" is LARGER bytewise is the "longer" one (C / POSIX locale; pinned by running the real
    script, tests/test_flank_loop_dropin_cpu.py).  contig_rank[c] = rank of contig c by (name + ':') bytewise ascending. */
 void hbo_genome_set_tie_rule(hbo_genome *g, int tie_rule, const int32_t *contig_rank) {

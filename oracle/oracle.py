@@ -301,8 +301,9 @@ class Genome:
         L.hbo_sort_u64(self.index.ctypes.data, n)
 
     def set_tie_rule(self, tie_rule, contig_names=None):
-        """S9 tie rule: 0 = earlier-ranked copy (the kernels' rule today), 1 = the reference's ready_for_MSA.sh rule (larger
-        member name wins a length tie).  ``contig_names`` give the name order the rule needs."""
+        """S9 tie rule: 1 (default) = the reference's ready_for_MSA.sh rule (larger member name wins a length tie; what
+        copy_select_kernel does), 0 = earlier-ranked copy.  ``contig_names`` give the name order the rule needs (without
+        them: the contig index, as in the library before hb_genome_contig_rank)."""
         import numpy as np
         self._L.hbo_genome_set_tie_rule.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         rank = None
@@ -323,7 +324,7 @@ class Genome:
         except Exception:
             pass
 
-    def candidate_msa(self, cand, occ_cap=512, max_loci=128, flank=50, max_rows=100):
+    def candidate_msa(self, cand, occ_cap=512, max_loci=300, flank=50, max_rows=100):
         """-> (copies[list of dict], rows[list of str]) for one candidate (S3..S10)."""
         import numpy as np
         L = self._L
@@ -347,7 +348,7 @@ class Genome:
         rows = [raw[r * Cn.value:(r + 1) * Cn.value].decode() for r in range(R.value)]
         return cps, rows
 
-    def query_hsps(self, query, occ_cap=512, max_loci=128):
+    def query_hsps(self, query, occ_cap=512, max_loci=300):
         """Library-vs-genome HSPs of one query -> list of dicts (rank, contig, qs, qe, ss, se, n_match, aln_len, score)."""
         L = self._L
         qb = query if isinstance(query, (bytes, bytearray)) else query.encode()
@@ -358,7 +359,7 @@ class Genome:
                              out, max_loci + 1)
         return [{f: getattr(out[i], f) for f, _ in HboQhsp._fields_} for i in range(n)]
 
-    def run_batch(self, cand_seqs, threads, occ_cap=512, max_loci=128, flank=50, max_rows=100, plant=1):
+    def run_batch(self, cand_seqs, threads, occ_cap=512, max_loci=300, flank=50, max_rows=100, plant=1):
         """Whole per-candidate path (copy search + MSA + clean + judge) on ``threads`` host threads.
         -> int32 array [n, 4] = (is_te, info, copy_num, cons_len)."""
         import numpy as np

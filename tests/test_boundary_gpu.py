@@ -5,7 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from hite_b200 import boundary, fasta, synth
+from hite_b200 import boundary, fasta
+from workloads import synth
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle as O
 from oracle import ref_import
 

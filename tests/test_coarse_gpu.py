@@ -3,7 +3,7 @@ plain-C restatement (oracle/hbo_hsp.c + hbo_fmea.c); planted copies must be foun
 import numpy as np
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu

@@ -8,7 +8,7 @@ import types
 
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle as O
 from oracle import ref_import
 

@@ -17,7 +17,7 @@ import sys
 
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle as O
 from oracle import ref_import
 

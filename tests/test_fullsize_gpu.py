@@ -3,7 +3,7 @@ properties of the path + bit-exact spot checks against the C port."""
 import numpy as np
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu

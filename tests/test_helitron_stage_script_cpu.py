@@ -10,7 +10,7 @@ import sys
 
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle as O
 from oracle import ref_import
 from test_tir_stage_script_cpu import FAKE_CDHIT

@@ -269,7 +269,7 @@ def test_stage_process_shards_candidates_over_gpus(monkeypatch, tmp_path):
             self.genome = None
             made.append(device)
 
-        def load_genome(self, contigs):
+        def load_genome(self, contigs, names=None):
             self.genome = [bytes(c) for c in contigs]
 
         def build_index(self, k, w):
@@ -325,6 +325,21 @@ def test_stage_process_shards_candidates_over_gpus(monkeypatch, tmp_path):
     with pytest.raises(RuntimeError):                                            # a failing GPU fails the stage loudly
         boundary.adjust_on_devices(list(seqs.values()), str(ref), "tir", 1, "cons", 50)
 
+    # HB_ENOMEM (too many seed hits / MSA columns for one call): the batch is halved and retried, same results in the same order
+    sizes = []
+
+    class Tight(FakeCtx):
+        def adjust(self, sq, *a, **k):
+            sizes.append(len(sq))
+            if len(sq) > 4:
+                raise boundary._lib.HiteB200Error("hb_adjust failed (-4): hb_adjust: too many seed hits in one call; pass fewer candidates")
+            return FakeCtx.adjust(self, sq, *a, **k)
+    monkeypatch.setenv("HITE_GPU_DEVICES", "0")
+    monkeypatch.setattr(boundary._lib, "Context", Tight)
+    monkeypatch.setattr(boundary, "_CTX", {}); monkeypatch.setattr(boundary, "_GENOME", {})
+    got = boundary.adjust_on_devices(list(seqs.values()), str(ref), "tir", 1, "cons", 50)
+    assert got == outs["0"][0] and max(sizes) == 23 and sizes.count(23) == 1 and all(n <= 4 for n in sizes if n not in (23, 11, 12, 5, 6))
+
 
 def test_other_and_masking_host_logic_with_fake_context():
     """hite_b200.other / hite_b200.masking above the C-ABI: record arrays -> reference dict shapes, self hits dropped
@@ -378,7 +393,8 @@ def test_product_fmea_shares_state_inside_a_blast_file():
     follow it (reference split_and_store_sequences module/Util.py:4987, chr_pos_candidates :4155).  Product host code
     (hb_fmea_chain_files) == oracle on a genome with 600 kbp tails; the per-record form differs there, as it must."""
     import numpy as np
-    from hite_b200 import _lib, synth
+    from hite_b200 import _lib
+    from workloads import synth
     from oracle import oracle as O
     wl = synth.make_workload(genome_bp=3_200_000, n_contigs=2, n_families=25, cands_per_family=1, copies=(5, 14),
                              length=(200, 1500), seed=31)
@@ -443,7 +459,8 @@ def test_smoke_next_rows_block_dry_run():
     against a stand-in context backed by the oracle: catches a typo in the checker code before the box does."""
     import numpy as np
     import __graft_entry__ as entry
-    from hite_b200 import _lib, synth
+    from hite_b200 import _lib
+    from workloads import synth
     from oracle import oracle as O
     wl = synth.make_workload(genome_bp=400_000, n_contigs=2, n_families=4, cands_per_family=2, copies=(6, 10),
                              length=(200, 1200), seed=7)

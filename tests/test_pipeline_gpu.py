@@ -4,7 +4,7 @@ and final boundary calls must be bit-identical; planted elements must be recover
 import numpy as np
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -116,3 +116,52 @@ def test_stress_shapes_bit_exact(ctx):
                 assert res[ci][k] == exp[k], (ci, k)
     assert n_big >= 1                       # the 100-longest rule was exercised
     assert sum(r["is_te"] for r in res[len(wl.cand_seqs):len(wl.cand_seqs) + len(wl2.cand_seqs)]) >= 1      # long elements come through
+
+
+def test_100_longest_tie_rule_follows_member_names(ctx):
+    """Families with 130-180 kept copies of EQUAL length (no indels): every member ties at the 100-record cut, so the subset
+    is decided by tools/ready_for_MSA.sh's last-resort order -- member names `contig:start-end(strand)` bytewise descending
+    (reference module/Util.py:10409-10412; pinned on the real script in tests/test_flank_loop_dropin_cpu.py).  Twelve contigs
+    named chr1..chr12 make the name order differ from the contig index ('chr10:' < 'chr1:').  GPU rows == oracle rows under
+    that rule, and != the rows the earlier-ranked rule would have kept."""
+    wl = synth.make_workload(genome_bp=6_000_000, n_contigs=12, n_families=4, cands_per_family=2, copies=(130, 180),
+                             length=(150, 600), seed=78, indel=0.0)
+    G = oracle.Genome(wl.contig_seqs)
+    G.set_tie_rule(1, wl.contig_names)
+    ctx.load_genome(wl.contig_seqs, wl.contig_names)
+    ctx.build_index(15, 10)
+    res = ctx.adjust(wl.cand_seqs, "tir", 1)
+    copies = ctx.last_copies()
+    n_cut = n_differs = 0
+    for ci, seq in enumerate(wl.cand_seqs):
+        cps, rows = G.candidate_msa(seq)
+        mine = copies[copies["cand"] == ci]
+        assert [int(a["keep"]) for a in mine] == [int(b["keep"]) for b in cps], ci
+        assert ctx.last_msa(ci) == rows, ci
+        if len(rows) == 100:
+            n_cut += 1
+            G.set_tie_rule(0)
+            n_differs += G.candidate_msa(seq)[1] != rows
+            G.set_tie_rule(1, wl.contig_names)
+        exp = oracle.judge_with_trunc_gate(seq.decode(), cps, rows)
+        for k in ("is_te", "info", "cons", "copy_num"):
+            assert res[ci][k] == exp[k], (ci, k)
+    assert n_cut >= 4 and n_differs >= 2
+    # without names the library falls back to the contig index: still the oracle's rule under the same convention
+    G.set_tie_rule(1)
+    ctx.load_genome(wl.contig_seqs)
+    ctx.build_index(15, 10)
+    ctx.adjust(wl.cand_seqs[:2], "tir", 1)
+    for ci, seq in enumerate(wl.cand_seqs[:2]):
+        assert ctx.last_msa(ci) == G.candidate_msa(seq)[1]
+
+
+def test_scan_total_is_exact_beyond_32_bits(ctx):
+    """The size guards of hb_adjust (seed hits < 2^31) and hb_coarse_boundary (seed pairs < 2^32) read the grand total of a
+    device scan whose offsets are 32-bit: the total must stay exact where the offsets wrap."""
+    n, v = 1 << 20, 9000                      # 9.4e9 > 2^33
+    total, last = ctx.debug_scan_total(n, v)
+    assert total == n * v
+    assert last == ((n - 1) * v) % (1 << 32)
+    total, last = ctx.debug_scan_total(5000, 7)
+    assert (total, last) == (35000, 4999 * 7)

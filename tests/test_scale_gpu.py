@@ -5,7 +5,7 @@ run at this size (its index build alone takes minutes); bit-exactness is covered
 import numpy as np
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 
 pytestmark = pytest.mark.gpu
 

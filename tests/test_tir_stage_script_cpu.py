@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle as O
 from oracle import ref_import
 from test_tir_stage_dropin_cpu import FAKE_ITRSEARCH

@@ -3,7 +3,7 @@ search + star MSA + truncated-member gate) vs the C port, bit-exact, plus plante
 import numpy as np
 import pytest
 
-from hite_b200 import synth
+from workloads import synth
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu

@@ -6,7 +6,8 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hite_b200
-from hite_b200 import synth, other, masking
+from hite_b200 import other, masking
+from workloads import synth
 
 mbp = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3

@@ -1,7 +1,7 @@
 import sys, time
 sys.path.insert(0,'/root/repo')
 import hite_b200
-from hite_b200 import synth
+from workloads import synth
 wl = synth.make_workload(genome_bp=100_000_000, n_contigs=10, n_families=1000, cands_per_family=10, copies=(10,40), seed=1)
 ctx = hite_b200.Context(0)
 ctx.load_genome(wl.contig_seqs); ctx.build_index()

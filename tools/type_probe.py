@@ -4,7 +4,7 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hite_b200
-from hite_b200 import synth
+from workloads import synth
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "helitron"
 wk = synth.make_workload(genome_bp=30_000_000, n_contigs=3, n_families=300, cands_per_family=10, copies=(10, 40),
