@@ -10,13 +10,18 @@ but the copy search (minimap2), the MSA (mafft) and the pure-Python column votin
 one ``hb_adjust`` call into libhite_b200.so (sm_100a kernels).  There is no CPU fallback: without
 the built extension or without a GPU these functions raise ``HiteB200Error``.
 
-What is NOT reproduced (out of scope; documented in DESIGN.md): the low-copy
-rescue of module/Util.py:8197-8281 needs ``trf``, the closed ELF ``itrsearch`` and ``blastx`` -- low-copy
-elements are all appended to ``all_low_copy`` exactly as the reference does for the ones it cannot
-rescue (module/Util.py:8284-8287).
+The low-copy rescue of module/Util.py:8195-8281 (``trf`` mask, then ``remove_no_tirs`` + TIRPeps domains for TIR, or the
+Helitron / non-LTR protein-domain check) is NOT rewritten here: ``_reference_rescue`` runs the reference's OWN statements
+for it -- cut out of the reference's ``flank_region_align_v5`` by position in its syntax tree and executed in the
+reference's ``Util`` namespace -- whenever the reference is importable and the tools those statements call (``trf``,
+``tools/itrsearch``, ``blastx`` / ``makeblastdb``) exist on the host.  Otherwise it says so loudly and every low-copy
+element goes to ``all_low_copy``, which is what the reference does with the ones it could not rescue (:8284-8287).
 """
+import ast
 import os
 import re
+import shutil
+import sys
 import threading
 import time
 
@@ -144,6 +149,98 @@ def _post_filter(names, seqs, results, TE_type):
     return true_tes, low_copy
 
 
+def _reference_util():
+    """The reference's own ``Util`` module: already imported when this runs inside a HiTE stage (module/_hite_b200_patch.py),
+    else importable from ``$HITE_HOME/module``; None when there is no HiTE checkout."""
+    U = sys.modules.get("Util")
+    if U is not None and hasattr(U, "remove_no_tirs") and hasattr(U, "get_domain_info"):
+        return U
+    home = os.environ.get("HITE_HOME")
+    if home and os.path.exists(os.path.join(home, "module", "Util.py")):
+        for d in (home, os.path.join(home, "module")):
+            if d not in sys.path:
+                sys.path.insert(0, d)
+        import importlib
+        try:
+            return importlib.import_module("Util")
+        except Exception:
+            return None
+    return None
+
+
+_RESCUE_CODE = {}
+
+
+def _rescue_code(U):
+    """The statements of the reference's ``flank_region_align_v5`` between ``store_fasta(low_copy_contigs, low_copy_path)`` and
+    ``store_fasta(true_tes, real_TEs)`` (module/Util.py:8195-8281), compiled from the reference's source file as they are."""
+    path = U.__file__
+    if path in _RESCUE_CODE:
+        return _RESCUE_CODE[path]
+    code = None
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                   # the reference has invalid escape sequences in string literals
+            tree = ast.parse(open(path, encoding="utf-8").read(), filename=path)
+        fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "flank_region_align_v5"][0]
+
+        def is_store(n, a, b):
+            return (isinstance(n, ast.Expr) and isinstance(n.value, ast.Call) and getattr(n.value.func, "id", "") == "store_fasta"
+                    and [getattr(x, "id", None) for x in n.value.args] == [a, b])
+        i0 = [i for i, n in enumerate(fn.body) if is_store(n, "low_copy_contigs", "low_copy_path")][0]
+        i1 = [i for i, n in enumerate(fn.body) if is_store(n, "true_tes", "real_TEs")][0]
+        if i1 > i0 + 1:
+            code = compile(ast.Module(body=fn.body[i0 + 1:i1], type_ignores=[]), path, "exec")
+    except Exception:
+        code = None
+    _RESCUE_CODE[path] = code
+    return code
+
+
+def _rescue_tools_missing(U, TE_type):
+    need = ["trf", "blastx", "makeblastdb"]
+    missing = [t for t in need if shutil.which(t) is None]
+    if TE_type == "tir" and not os.path.exists(os.path.join(U.cur_dir, "tools", "itrsearch")):
+        missing.append("tools/itrsearch")
+    return missing
+
+
+def _reference_rescue(low_copy, true_tes, TE_type, temp_dir, threads, plant, log):
+    """Low-copy rescue by the reference's own code (module/Util.py:8195-8281): names it promotes are added to ``true_tes``.
+    Returns the set of rescued names (empty, with a loud message, when the reference or its tools are not there)."""
+    def say(msg):
+        if log is not None:
+            getattr(log.logger, "warning", log.logger.info)(msg)
+        else:
+            sys.stderr.write(msg + "\n")
+    if not low_copy:
+        return set()
+    U = _reference_util()
+    if U is None:
+        say("hite_b200: low-copy rescue SKIPPED for %d %s element(s): the HiTE checkout is not importable (set HITE_HOME); "
+            "they go to the all_low_copy file" % (len(low_copy), TE_type))
+        return set()
+    missing = _rescue_tools_missing(U, TE_type)
+    if missing:
+        say("hite_b200: low-copy rescue SKIPPED for %d %s element(s): %s not found on this host; they go to the all_low_copy file"
+            % (len(low_copy), TE_type, ", ".join(missing)))
+        return set()
+    code = _rescue_code(U)
+    if code is None:
+        say("hite_b200: low-copy rescue SKIPPED: the rescue statements were not found in %s (another HiTE version?)" % U.__file__)
+        return set()
+    low_copy_dir = temp_dir + "/low_copy_itr"                                      # :8155-8158
+    os.makedirs(low_copy_dir, exist_ok=True)
+    low_copy_path = low_copy_dir + "/low_copy_elements.fa"
+    U.store_fasta(low_copy, low_copy_path)                                         # :8194
+    before = set(true_tes)
+    env = dict(low_copy_contigs=low_copy, low_copy_path=low_copy_path, low_copy_dir=low_copy_dir, temp_dir=temp_dir,
+               TE_type=TE_type, plant=plant, threads=threads, true_tes=true_tes, true_te_names=set(true_tes))
+    exec(code, U.__dict__, env)
+    return set(true_tes) - before
+
+
 def flank_region_align_v5(candidate_sequence_path, real_TEs, flanking_len, reference, split_ref_dir, TE_type,
                           tmp_output_dir, threads, ref_index, log, subset_script_path, plant, debug, iter_num,
                           all_low_copy, result_type="cons"):
@@ -161,10 +258,15 @@ def flank_region_align_v5(candidate_sequence_path, real_TEs, flanking_len, refer
         for i, r in zip(ok, res):
             results[i] = r
     true_tes, low_copy = _post_filter(names, seqs, results, TE_type)
+    temp_dir = tmp_output_dir + "/" + TE_type + "_copies_" + str(ref_index) + "_" + str(iter_num)      # :8037
+    rescued = _reference_rescue(low_copy, true_tes, TE_type, temp_dir, threads, plant, log)           # :8195-8281
     store_fasta(true_tes, real_TEs)                                                # :8282
     with open(all_low_copy, "a") as f_save:                                        # :8284-8287
         for te_name, seq in low_copy.items():
-            f_save.write(">" + te_name + "\n" + seq + "\n")
+            if te_name not in rescued and te_name not in true_tes:
+                f_save.write(">" + te_name + "\n" + seq + "\n")
+    if debug != 1 and os.path.isdir(temp_dir):                                     # :8295-8296
+        shutil.rmtree(temp_dir, ignore_errors=True)
     if debug:
         nb = sum(1 for r in results if r["info"] == "nb")
         fl1 = sum(1 for r in results if r["info"] == "fl1")

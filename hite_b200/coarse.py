@@ -6,21 +6,46 @@
   library; ``generate_final_result`` (:4783-4796) slices the intervals out of the reference genome.
   The known-TE masking of :4654 (``mask_genome_with_TE``) runs on the chunk already resident in HBM
   (``hite_b200.masking.mask_context``: ``prev_TE`` vs chunk HSPs, full-length chaining, N-fill kernel, index rebuild).
-  NOT reproduced (external ``trf``): the tandem-repeat filter of :4650-4651 -- the chunk is taken as given.
+  The tandem-repeat filter of :4650-4651 is the reference's own ``filter_tandem_repeats`` (:4672-4697, ``trf`` per 100 kbp
+  file under its process pool), called as it is when the HiTE checkout is importable and ``trf`` is on ``$PATH``; otherwise
+  the stage says so loudly and takes the chunk unfiltered.
 * ``flanking_seq``  reference module/Util.py:4614-4634 -- same signature and clamping rules.
 """
 import os
+import shutil
+import sys
 
 import numpy as np
 
-from .boundary import _GENOME, get_context
+from .boundary import _GENOME, _reference_util, get_context
 from .fasta import file_exist, read_fasta, store_fasta
 
 
-def _chunk_to_chromosomes(repeats_path):
+def _filter_tandem_repeats(repeats_path, tmp_output_dir, ref_index, threads):
+    """module/Util.py:4650-4651 by the reference's own code: returns the path of ``filter_tandem_{ref_index}.fa`` (the chunk
+    with its tandem repeats N-masked by ``trf``), or ``repeats_path`` itself -- with a loud message -- when that cannot run."""
+    U = _reference_util()
+    why = None
+    if U is None or not hasattr(U, "filter_tandem_repeats"):
+        why = "the HiTE checkout is not importable (set HITE_HOME)"
+    elif shutil.which("trf") is None:
+        why = "trf not found on this host"
+    if why:
+        sys.stderr.write("hite_b200: tandem-repeat filter (trf) SKIPPED for %s: %s; the chunk is searched unfiltered\n"
+                         % (os.path.basename(repeats_path), why))
+        return repeats_path
+    repeat_names, repeat_contigs = U.read_fasta(repeats_path)
+    U.filter_tandem_repeats(repeat_names, repeat_contigs, tmp_output_dir, ref_index, max(1, int(threads)))
+    return os.path.join(tmp_output_dir, "filter_tandem_%s.fa" % ref_index)
+
+
+def _chunk_to_chromosomes(repeats_path, name_order=None):
     """genome.cut{i}.fa holds records ``chr$start`` (split_genome_chunks.py:47-52).  Rebuild per-chromosome
-    arrays (pieces missing from this chunk stay 'N') so segments sit at their real coordinates."""
+    arrays (pieces missing from this chunk stay 'N') so segments sit at their real coordinates.  ``name_order``: record
+    order to follow instead of the file's (the trf-filtered file is written in process-pool completion order)."""
     names, contigs = read_fasta(repeats_path)
+    if name_order is not None:
+        names = [n for n in name_order if n in contigs] + [n for n in names if n not in set(name_order)]
     pieces = {}
     order = []
     for n in names:
@@ -48,7 +73,8 @@ def determine_repeat_boundary_v5(repeats_path, longest_repeats_path, prev_TE, fi
                                  chrom_seg_length=1_000_000, occ_cap=64):
     if not os.path.exists(tmp_output_dir):
         os.makedirs(tmp_output_dir)
-    chr_names, chroms = _chunk_to_chromosomes(repeats_path)
+    filtered = _filter_tandem_repeats(repeats_path, tmp_output_dir, ref_index, threads)          # :4650-4651
+    chr_names, chroms = _chunk_to_chromosomes(filtered, read_fasta(repeats_path)[0] if filtered != repeats_path else None)
     ctx = get_context()
     _GENOME.pop(ctx.device, None)                 # this context now holds the chunk, not the reference
     ctx.load_genome(chroms)

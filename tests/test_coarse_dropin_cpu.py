@@ -211,3 +211,74 @@ def test_drop_in_script_runs_the_reference_stage_with_main_py_arguments(tmp_path
     fnames, fcontigs = fasta.read_fasta(str(outdir / "longest_repeats_0.flanked.fa"))
     assert len(fnames) == len(names) and all(len(s) >= 180 for s in fcontigs.values())
     assert os.path.exists(str(outdir / "HiTE_coarse.log")) and not os.listdir(str(work))
+
+
+FAKE_TRF_MASK = r'''#!%s
+# stand-in for `trf <file> 2 7 7 80 10 50 500 -f -d -m -h`: N-masks every (AC)n run of >= 60 bp, writes <file>...mask in the cwd
+import os, re, sys
+src = sys.argv[1]
+with open(os.path.basename(src) + ".2.7.7.80.10.50.500.mask", "w") as out:
+    for line in open(src):
+        out.write(line if line.startswith(">") else re.sub(r"(?:AC){30,}", lambda m: "N" * len(m.group(0)), line))
+'''
+
+
+def test_tandem_repeat_filter_is_the_references_own_code(tmp_path, monkeypatch, capfd):
+    """determine_repeat_boundary_v5 (mirror) hands the chunk to the reference's own filter_tandem_repeats (module/Util.py:4650-4651,
+    :4672-4697: 100 kbp files, `trf` under a process pool, merged in completion order) when trf is on $PATH, and loads the
+    N-masked result at the records' real coordinates; without trf it says so and loads the chunk as given."""
+    import stat
+    import sys
+    from hite_b200 import coarse, fasta
+    U = ref_import.load_util()
+    rng = np.random.default_rng(4)
+    B = np.frombuffer(b"ACGT", dtype=np.uint8)
+    chroms = {"chrA": B[rng.integers(0, 4, 450_000)].copy(), "chrB": B[rng.integers(0, 4, 230_000)].copy()}
+    planted = [("chrA", 120_000, 400), ("chrA", 330_500, 90), ("chrB", 10_000, 1000)]
+    for c, a, n in planted:
+        chroms[c][a:a + n] = np.frombuffer(b"AC" * (n // 2), dtype=np.uint8)
+    ref = str(tmp_path / "genome.fa")
+    fasta.store_fasta({c: s.tobytes().decode() for c, s in chroms.items()}, ref)
+    cut = str(tmp_path / "genome.cut0.fa")
+    with open(cut, "w") as f:
+        for c, s in chroms.items():
+            for o in range(0, len(s), 100_000):
+                f.write(">%s$%d\n%s\n" % (c, o, s[o:o + 100_000].tobytes().decode()))
+    loaded = []
+
+    class Ctx:
+        device = 0
+
+        def load_genome(self, ch):
+            loaded.append([bytes(x) for x in ch])
+
+        def build_index(self, k, w):
+            return dict(kernel_ms=0.0)
+
+        def coarse_boundary(self, **kw):
+            return np.zeros(0, dtype=coarse_lib.INTERVAL_DTYPE)
+    from hite_b200 import _lib as coarse_lib
+    monkeypatch.setattr(coarse, "get_context", lambda device=None: Ctx())
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    p = bindir / "trf"
+    p.write_text(FAKE_TRF_MASK % sys.executable)
+    p.chmod(p.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(bindir) + os.pathsep + os.environ["PATH"])
+    coarse.determine_repeat_boundary_v5(cut, str(tmp_path / "lr.fa"), None, 2000, 30000, str(tmp_path / "w1"), 3, 0, ref, 0,
+                                        chrom_seg_length=100_000)
+    got = dict(zip(["chrA", "chrB"], loaded[-1]))
+    for c, s in chroms.items():
+        exp = bytearray(s.tobytes())
+        for cc, a, n in planted:
+            if cc == c:
+                exp[a:a + n] = b"N" * n
+        assert got[c] == bytes(exp), c
+    assert os.path.exists(str(tmp_path / "w1" / "filter_tandem_0.fa"))          # the reference's own intermediate file
+    # no trf: loud message, unfiltered chunk
+    monkeypatch.setenv("PATH", os.pathsep.join(x for x in os.environ["PATH"].split(os.pathsep) if x != str(bindir)))
+    capfd.readouterr()
+    coarse.determine_repeat_boundary_v5(cut, str(tmp_path / "lr2.fa"), None, 2000, 30000, str(tmp_path / "w2"), 3, 0, ref, 0,
+                                        chrom_seg_length=100_000)
+    assert "SKIPPED" in capfd.readouterr().err
+    assert dict(zip(["chrA", "chrB"], loaded[-1])) == {c: s.tobytes() for c, s in chroms.items()}

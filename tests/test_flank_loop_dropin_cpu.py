@@ -277,3 +277,120 @@ def test_reference_loop_with_more_than_100_copies_under_the_scripts_tie_rule(tmp
         return sorted(zip(lines[0::2], lines[1::2]))
     assert records(out_mine) == records(out_ref) and records(low_mine) == records(low_ref)
     assert len(records(out_ref)) >= 3
+
+
+FAKE_TRF = r'''#!%s
+# stand-in for `trf <file> 2 7 7 80 10 50 500 -f -d -m -h`: no tandem repeats found, the .mask file is the input
+import shutil, sys, os
+src = sys.argv[1]
+shutil.copy(src, os.path.basename(src) + ".2.7.7.80.10.50.500.mask")
+'''
+
+FAKE_BLASTX = r'''#!%s
+# stand-in for `blastx -db <protein fasta> ... -query <fa> -outfmt 6`: one full-length protein hit for every query whose
+# name is listed in $HB_FAKE_DOMAIN_NAMES, nothing for the others
+import os, sys
+a = sys.argv
+db, query = a[a.index("-db") + 1], a[a.index("-query") + 1]
+pname, plen = None, 0
+for line in open(db):
+    if line.startswith(">"):
+        if pname is not None:
+            break
+        pname = line[1:].split()[0]
+    else:
+        plen += len(line.strip())
+want = set(os.environ.get("HB_FAKE_DOMAIN_NAMES", "").split(","))
+for line in open(query):
+    if line.startswith(">") and line[1:].strip() in want:
+        q = line[1:].strip()
+        print("\t".join(str(x) for x in (q, pname, 100.0, plen, 0, 0, 1, 3 * plen, 1, plen, 1e-50, 500)))
+'''
+
+
+def test_low_copy_rescue_is_the_references_own_code(tmp_path, monkeypatch):
+    """Low-copy elements (copy_num <= 5) through the rescue of module/Util.py:8195-8281 -- trf mask, remove_no_tirs (short-TIR
+    rules + itrsearch), TIRPeps domain recall -- on both sides: the reference's unmodified flank_region_align_v5, and the
+    mirror, which executes the reference's own rescue statements (hite_b200.boundary._reference_rescue) when the tools exist.
+    Stand-in trf / itrsearch / blastx; both sides must promote the same elements to the confident set and leave the same
+    remainder in the all_low_copy file, and elements must actually be rescued by TIR structure and by domain."""
+    from hite_b200 import boundary, fasta
+    U = ref_import.load_util()
+    wl = synth.make_workload(genome_bp=1_500_000, n_contigs=2, n_families=30, cands_per_family=1, copies=(3, 9),
+                             length=(150, 900), seed=31, sub=(0.0, 0.01), indel=0.0)
+    ref, cand = str(tmp_path / "genome.fa"), str(tmp_path / "cand.fa")
+    wl.write_fasta(ref, cand)
+    names, contigs = fasta.read_fasta(cand)
+    G = O.Genome(wl.contig_seqs)
+    all_copies, db, verdicts = {}, {}, {}
+    for name in names:
+        seq = contigs[name]
+        cps, rows = G.candidate_msa(seq.encode())
+        kept = [c for c in cps if c["keep"]]
+        if rows:
+            all_copies[name] = [(wl.contig_names[c["contig"]], c["start1"], c["end1"], c["end1"] - c["start1"] + 1,
+                                 "-" if c["rel"] else "+") for c in kept]
+            fname = re.sub(r'[<>:"/\\|?*]', "-", name)
+            db[fname + ".blast.bed.fa"] = rows
+            t = O.truncated_rows(cps, rows)
+            if t:
+                db[fname + ".trunc.blast.bed.fa"] = t
+            verdicts[seq] = O.judge_with_trunc_gate(seq, cps, rows, judge=lambda c, r: O.judge_v5(c, r, 1), plant=1)
+        else:
+            verdicts[seq] = dict(is_te=False, info="", cons="", copy_num=0)
+    G.close()
+    low = [n for n in names if verdicts[contigs[n]]["is_te"] and verdicts[contigs[n]]["copy_num"] <= 5]
+    assert len(low) >= 6
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    from test_tir_stage_dropin_cpu import FAKE_ITRSEARCH
+    for tool, body in (("mafft", FAKE_MAFFT), ("trf", FAKE_TRF), ("blastx", FAKE_BLASTX), ("makeblastdb", "#!%s\n"),
+                       ("itrsearch", FAKE_ITRSEARCH)):
+        p = bindir / tool
+        p.write_text(body % sys.executable)
+        p.chmod(p.stat().st_mode | stat.S_IEXEC)
+    dbpath = str(tmp_path / "msa_db.json")
+    json.dump(db, open(dbpath, "w"))
+    monkeypatch.setenv("PATH", str(bindir) + os.pathsep + os.environ["PATH"])
+    monkeypatch.setenv("HB_FAKE_MAFFT_DB", dbpath)
+    monkeypatch.setenv("HB_FAKE_DOMAIN_NAMES", ",".join(low[-2:]))            # two low-copy elements carry an intact domain
+    monkeypatch.setattr(U, "get_full_length_copies_minimap2", lambda q, r, t, m, th: dict(all_copies))
+    real_itr = U.run_itrsearch
+    monkeypatch.setattr(U, "run_itrsearch", lambda d, inp, inp_dir: real_itr(str(bindir), inp, inp_dir))   # $HITE_HOME/tools is read-only here
+    out_ref, low_ref = str(tmp_path / "ref_real.fa"), str(tmp_path / "ref_low.fa")
+    U.flank_region_align_v5(cand, out_ref, 50, ref, None, "tir", str(tmp_path / "refwork"), 4, 0, _Log, "", 1, 0, 0, low_ref, "cons")
+
+    class OracleBackedCtx:
+        device = 0
+
+        def adjust(self, seqs, te, plant, result_type, flank=50):
+            return [dict(verdicts[s]) for s in seqs]
+    ctx = OracleBackedCtx()
+    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "ensure_genome", lambda c, r, k=15, w=10, _parsed=None: c)
+    monkeypatch.setenv("HITE_GPU_DEVICES", "0")
+    assert boundary._rescue_tools_missing(U, "tir") == []
+    out_mine, low_mine = str(tmp_path / "mine_real.fa"), str(tmp_path / "mine_low.fa")
+    boundary.flank_region_align_v5(cand, out_mine, 50, ref, None, "tir", str(tmp_path / "minework"), 4, 0, _Log, "", 1, 0, 0, low_mine, "cons")
+
+    def records(p):
+        lines = open(p).read().splitlines() if os.path.exists(p) else []
+        return sorted(zip(lines[0::2], lines[1::2]))
+    assert records(out_mine) == records(out_ref) and records(low_mine) == records(low_ref)
+    confident = {n[1:] for n, _ in records(out_ref)}
+    rescued = [n for n in low if n in confident]
+    assert len(rescued) >= 3 and set(low[-2:]) <= confident                   # by TIR structure, and the two by domain
+    assert 1 <= len(records(low_ref)) <= len(low) - len(rescued)              # ('TG..CA' elements are dropped before the split)
+    print("low-copy rescue: %d low-copy elements, %d rescued (reference == mirror), %d left in all_low_copy"
+          % (len(low), len(rescued), len(records(low_ref))))
+    # without the tools the mirror says so and rescues nothing
+    monkeypatch.setenv("PATH", os.pathsep.join(p for p in os.environ["PATH"].split(os.pathsep) if p != str(bindir)))
+    msgs = []
+
+    class Log2:
+        class logger:
+            info = staticmethod(lambda m: None)
+            warning = staticmethod(msgs.append)
+    out2, low2 = str(tmp_path / "mine2_real.fa"), str(tmp_path / "mine2_low.fa")
+    boundary.flank_region_align_v5(cand, out2, 50, ref, None, "tir", str(tmp_path / "minework2"), 4, 0, Log2, "", 1, 0, 0, low2, "cons")
+    assert len(records(low2)) == len(records(low_ref)) + len(rescued) and any("SKIPPED" in m and "trf" in m for m in msgs)
