@@ -202,6 +202,8 @@ def load():
     lib.hb_query_copies.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, vp,
                                     C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_coarse_boundary.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
+    lib.hb_coarse_boundary_part.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
+    lib.hb_last_intervals.argtypes = [vp, vp, C.c_uint64, u64p]
     lib.hb_last_hsps.argtypes = [vp, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_full_length_copies.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_fmea_chain_files.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
@@ -427,22 +429,19 @@ class Context:
         return [raw[r * Cn.value:(r + 1) * Cn.value].decode() for r in range(R.value)]
 
     # ------------------------------------------------------------------------------------
-    def coarse_boundary(self, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=8):
+    def coarse_boundary(self, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=8, part=0, n_parts=1):
         """The all-vs-all + FMEA step of ``determine_repeat_boundary_v5`` (reference module/Util.py:4657-4663) on
-        the loaded genome -> INTERVAL_DTYPE array ('chr:start-end', 0-based half open)."""
-        # generous one-shot buffer: an interval needs at least one HSP, so #HSPs bounds the count; retry if short
-        cap = 1 << 16
-        while True:
-            out = np.zeros(cap, dtype=INTERVAL_DTYPE)
-            n = C.c_uint64(0)
-            rc = self._lib.hb_coarse_boundary(self._h, int(seg_len), int(skip_gap), int(max_len), int(occ_cap), int(threads),
-                                              _ptr(out), cap, C.byref(n))
-            if rc == 0:
-                return out[:n.value]
-            if n.value > cap:
-                cap = int(n.value)
-                continue
-            self._check(rc, "hb_coarse_boundary")
+        the loaded genome -> INTERVAL_DTYPE array ('chr:start-end', 0-based half open).  ``part`` / ``n_parts``: this
+        process's share of a stage sharded over several GPUs (``hb_coarse_boundary_part``): the parts' results
+        concatenated in part order are the unsharded result."""
+        n = C.c_uint64(0)
+        self._check(self._lib.hb_coarse_boundary_part(self._h, int(seg_len), int(skip_gap), int(max_len), int(occ_cap), int(threads),
+                                                      int(part), int(n_parts), None, 0, C.byref(n)), "hb_coarse_boundary")
+        tm = self.timing()
+        out = np.zeros(max(1, n.value), dtype=INTERVAL_DTYPE)
+        self._check(self._lib.hb_last_intervals(self._h, _ptr(out), len(out), C.byref(n)), "hb_last_intervals")
+        self._coarse_timing = tm
+        return out[:n.value]
 
     def mask_genome(self, contig, start, end):
         """N-fill [start, end) (0-based) of the resident packed genome (``hb_genome_mask``; reference module/Util.py:6414-6420)

@@ -26,12 +26,15 @@ __device__ __forceinline__ int seg_of(const uint64_t* __restrict__ seg_goff, int
 }
 
 // one thread per minimizer (position order)
+// [qpos_lo, qpos_hi): the query positions this call (one part of a sharded self-join) owns; the others pair with nothing
 __global__ void pair_count_kernel(const uint64_t* __restrict__ mm, uint32_t n_mm, const uint64_t* __restrict__ idx,
-                                  const uint32_t* __restrict__ bucket, int occ_cap, uint32_t* __restrict__ lo_out,
-                                  uint32_t* __restrict__ cnt_out) {
+                                  const uint32_t* __restrict__ bucket, int occ_cap, uint64_t qpos_lo, uint64_t qpos_hi,
+                                  uint32_t* __restrict__ lo_out, uint32_t* __restrict__ cnt_out) {
     const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= n_mm) return;
     const uint64_t e = mm[qi];
+    const uint64_t qpos = (e >> 1) & 0xFFFFFFFFull;
+    if (qpos < qpos_lo || qpos >= qpos_hi) { lo_out[qi] = 0; cnt_out[qi] = 0; return; }
     const uint32_t h = (uint32_t)(e >> 33);
     const uint32_t bk = h >> (30 - HB_COARSE_BUCKET_BITS);
     const uint64_t l = lower_bound_u64(idx, bucket[bk], bucket[bk + 1], (uint64_t)h << 33);
@@ -142,9 +145,9 @@ __global__ void hsp_compact_kernel(const HbHspRec* __restrict__ recs, const uint
 }  // namespace
 
 cudaError_t hb_pair_count_launch(const uint64_t* mm, uint32_t n_mm, const uint64_t* idx, const uint32_t* bucket,
-                                 int occ_cap, uint32_t* lo, uint32_t* cnt, cudaStream_t s) {
+                                 int occ_cap, uint64_t qpos_lo, uint64_t qpos_hi, uint32_t* lo, uint32_t* cnt, cudaStream_t s) {
     if (n_mm == 0) return cudaSuccess;
-    pair_count_kernel<<<(n_mm + 255) / 256, 256, 0, s>>>(mm, n_mm, idx, bucket, occ_cap, lo, cnt);
+    pair_count_kernel<<<(n_mm + 255) / 256, 256, 0, s>>>(mm, n_mm, idx, bucket, occ_cap, qpos_lo, qpos_hi, lo, cnt);
     return cudaGetLastError();
 }
 cudaError_t hb_pair_fill_launch(const uint64_t* mm, uint32_t n_mm, const uint64_t* idx, uint64_t n_idx, uint64_t tot, int k, int occ_cap,

@@ -8,7 +8,7 @@
 struct HbHspRec { int32_t qseg, subj, qs, qe, ss, se, pad; };
 
 cudaError_t hb_pair_count_launch(const uint64_t* mm, uint32_t n_mm, const uint64_t* idx, const uint32_t* bucket,
-                                 int occ_cap, uint32_t* lo, uint32_t* cnt, cudaStream_t s);
+                                 int occ_cap, uint64_t qpos_lo, uint64_t qpos_hi, uint32_t* lo, uint32_t* cnt, cudaStream_t s);
 cudaError_t hb_pair_fill_launch(const uint64_t* mm, uint32_t n_mm, const uint64_t* idx, uint64_t n_idx, uint64_t tot, int k, int occ_cap,
                                 const uint32_t* lo, const uint32_t* cnt, const uint32_t* off, uint64_t* keys,
                                 cudaStream_t s);

@@ -93,6 +93,7 @@ struct hb_ctx {
     std::vector<hb_hsp> last_hsps;            // last hb_coarse_boundary: HSPs grouped by query segment
     std::vector<uint64_t> last_hsp_off;
     std::vector<hb_segment> last_segs;
+    std::vector<hb_interval> last_intervals;  // last hb_coarse_boundary(_part): its result, for hb_last_intervals
     std::vector<uint32_t> last_rows, last_cols;
     std::vector<hb_qhsp> last_qhsps;          // last hb_query_hsps, ordered by (query, rank)
 };

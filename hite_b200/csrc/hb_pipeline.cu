@@ -1057,9 +1057,10 @@ extern "C" int hb_genome_export(hb_ctx* ctx, uint32_t contig, uint8_t* out_ascii
     return HB_OK;
 }
 
-extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
-                                  hb_interval* out, uint64_t cap, uint64_t* n_out) {
+extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
+                                       uint32_t part, uint32_t n_parts, hb_interval* out, uint64_t cap, uint64_t* n_out) {
     if (!ctx || !n_out) return HB_EINVAL;
+    if (n_parts == 0 || part >= n_parts) return hb_fail_msg(ctx, HB_EINVAL, "hb_coarse_boundary_part: need part < n_parts");
     if (!ctx->have_index) return hb_fail_msg(ctx, HB_ESTATE, "hb_coarse_boundary: call hb_genome_load + hb_index_build first");
     if (seg_len < 1000 || occ_cap < 1 || occ_cap > 4096) return hb_fail_msg(ctx, HB_EINVAL, "hb_coarse_boundary: parameter out of range");
     if (ctx->g_nmm >= (1ull << 29)) return hb_fail_msg(ctx, HB_EINVAL, "hb_coarse_boundary: more than 2^29 minimizers");
@@ -1078,6 +1079,31 @@ extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, in
         }
     const int n_seg = (int)segs.size();
     const uint32_t n_mm = (uint32_t)ctx->g_nmm;
+    // BLAST result files of the reference: split_and_store_sequences packs the segment records into a file until it holds
+    // >= 1 000 000 bases (module/Util.py:4737, :4987-5012), so a contig's short tail shares a file -- and FMEA's
+    // de-duplication state -- with the records that follow it.  A file is the unit a part (rank) owns.
+    std::vector<uint32_t> file_of_seg((size_t)n_seg);
+    uint32_t n_files = 0;
+    {
+        uint32_t f = 0;
+        uint64_t count = 0;
+        for (int g = 0; g < n_seg; ++g) {
+            file_of_seg[(size_t)g] = f;
+            count += std::min<uint64_t>((uint64_t)seg_len, ctx->g_glen[(size_t)segs[(size_t)g].chr] - (uint64_t)segs[(size_t)g].start);
+            if (count >= 1000000ull) { ++f; count = 0; }
+        }
+        n_files = n_seg ? file_of_seg[(size_t)n_seg - 1] + 1 : 0;
+    }
+    // this part's query segments: the files [n_files * part / n_parts, n_files * (part + 1) / n_parts), a contiguous
+    // range of the padded coordinate space
+    const uint32_t f_lo = (uint32_t)((uint64_t)n_files * part / n_parts), f_hi = (uint32_t)((uint64_t)n_files * (part + 1) / n_parts);
+    int g_lo = n_seg, g_hi = n_seg;
+    for (int g = 0; g < n_seg; ++g) {
+        if (file_of_seg[(size_t)g] >= f_lo && g_lo == n_seg) g_lo = g;
+        if (file_of_seg[(size_t)g] >= f_hi) { g_hi = g; break; }
+    }
+    const uint64_t qpos_lo = g_lo < n_seg ? seg_goff[(size_t)g_lo] : ctx->g_tot;
+    const uint64_t qpos_hi = g_hi < n_seg ? seg_goff[(size_t)g_hi] : ctx->g_tot;
     ENSURE("h.seg_goff", sizeof(uint64_t) * (n_seg + 1));
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("h.seg_goff").p, seg_goff.data(), sizeof(uint64_t) * n_seg, cudaMemcpyHostToDevice, s));
     ENSURE("h.lo", sizeof(uint32_t) * (n_mm + 1)); ENSURE("h.cnt", sizeof(uint32_t) * (n_mm + 1)); ENSURE("h.off", sizeof(uint32_t) * (n_mm + 1));
@@ -1085,7 +1111,7 @@ extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, in
     ENSURE("h.total", sizeof(uint64_t));
     HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
     HB_CUDA_OK(hb_pair_count_launch(ctx->buf("g.mm_pos").as<uint64_t>(), n_mm, ctx->buf("g.idx_a").as<uint64_t>(),
-                                    ctx->buf("g.bucket").as<uint32_t>(), occ_cap, ctx->buf("h.lo").as<uint32_t>(),
+                                    ctx->buf("g.bucket").as<uint32_t>(), occ_cap, qpos_lo, qpos_hi, ctx->buf("h.lo").as<uint32_t>(),
                                     ctx->buf("h.cnt").as<uint32_t>(), s));
     HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("h.cnt").as<uint32_t>(), ctx->buf("h.off").as<uint32_t>(), n_mm,
                                      ctx->buf("h.scan_tmp").as<uint32_t>(), ctx->buf("h.total").as<uint64_t>(), s));
@@ -1155,29 +1181,31 @@ extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, in
     ctx->last_segs = segs;
     auto t0 = std::chrono::steady_clock::now();
     std::vector<hb_interval> res;
-    // BLAST result files of the reference: split_and_store_sequences packs the segment records into a file until it holds
-    // >= 1 000 000 bases (module/Util.py:4737, :4987-5012), so a contig's short tail shares a file -- and FMEA's
-    // de-duplication state -- with the records that follow it
-    std::vector<uint32_t> file_of_seg((size_t)n_seg);
-    {
-        uint32_t f = 0;
-        uint64_t count = 0;
-        for (int g = 0; g < n_seg; ++g) {
-            file_of_seg[(size_t)g] = f;
-            count += std::min<uint64_t>((uint64_t)seg_len, ctx->g_glen[(size_t)segs[(size_t)g].chr] - (uint64_t)segs[(size_t)g].start);
-            if (count >= 1000000ull) { ++f; count = 0; }
-        }
-    }
     hb_fmea_run(ctx->last_hsps.data(), ctx->last_hsp_off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, res,
                 file_of_seg.data());
     tm.k_ms[3] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     tm.k_ms[6] = (float)h_recs.size();
     tm.k_ms[7] = (float)((double)n_pairs * 1e-6);
     tm.launches = launches;
+    ctx->last_intervals = res;                       // kept: hb_last_intervals fetches them without a second run
     *n_out = res.size();
     if (!out) return HB_OK;
-    if (cap < res.size()) return hb_fail_msg(ctx, HB_EINVAL, "hb_coarse_boundary: output buffer too small");
+    if (cap < res.size()) return hb_fail_msg(ctx, HB_EINVAL, "hb_coarse_boundary: output buffer too small (fetch with hb_last_intervals)");
     if (!res.empty()) memcpy(out, res.data(), sizeof(hb_interval) * res.size());
+    return HB_OK;
+}
+
+extern "C" int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
+                                  hb_interval* out, uint64_t cap, uint64_t* n_out) {
+    return hb_coarse_boundary_part(ctx, seg_len, skip_gap, max_len, occ_cap, threads, 0, 1, out, cap, n_out);
+}
+
+extern "C" int hb_last_intervals(hb_ctx* ctx, hb_interval* out, uint64_t cap, uint64_t* n) {
+    if (!ctx || !n) return HB_EINVAL;
+    *n = ctx->last_intervals.size();
+    if (!out) return HB_OK;
+    if (cap < ctx->last_intervals.size()) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_intervals: buffer too small");
+    if (!ctx->last_intervals.empty()) memcpy(out, ctx->last_intervals.data(), sizeof(hb_interval) * ctx->last_intervals.size());
     return HB_OK;
 }
 

@@ -128,7 +128,7 @@ int hb_debug_scan_total(hb_ctx* ctx, uint64_t n, uint32_t value, uint64_t* total
 
 typedef struct {
     int32_t occ_cap;      /* occurrences used per minimizer (first occ_cap in position order); 512 */
-    int32_t max_loci;     /* loci aligned per candidate (minimap2 -N 300 analogue, module/Util.py:7955); 128 */
+    int32_t max_loci;     /* loci aligned per candidate (minimap2 -N 300, module/Util.py:7955); 300 */
     int32_t flank;        /* flanking_len, module/Util.py:8103-8105; 50 */
     int32_t max_rows;     /* "100 longest" of ready_for_MSA.sh, module/Util.py:10409-10412; 100 */
     int32_t te_type;      /* HB_TE_* */
@@ -268,6 +268,17 @@ int hb_genome_export(hb_ctx* ctx, uint32_t contig, uint8_t* out_ascii, uint64_t 
  */
 int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
                        hb_interval* out, uint64_t cap, uint64_t* n_out);
+/*
+ * hb_coarse_boundary_part -- one part of the same stage sharded over n_parts processes / GPUs (the reference
+ * fans the n^2 segment pairs out over a process pool, module/Util.py:4746-4748).  Every part holds the whole genome + index
+ * and owns a contiguous block of the query-segment FILES (the unit FMEA de-duplicates in): the files
+ * [F * part / n_parts, F * (part + 1) / n_parts).  Only the minimizers of those segments are paired (against the whole index) and
+ * chained; the parts' interval lists concatenated in part order are exactly hb_coarse_boundary's list.  out = NULL (or a
+ * short buffer) still runs the stage and keeps the result in the context: fetch it with hb_last_intervals, no second run.
+ */
+int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
+                            uint32_t part, uint32_t n_parts, hb_interval* out, uint64_t cap, uint64_t* n_out);
+int hb_last_intervals(hb_ctx* ctx, hb_interval* out, uint64_t cap, uint64_t* n);
 /* the HSPs of the last hb_coarse_boundary, grouped by query segment (q_off has n_seg+1 entries) */
 int hb_last_hsps(hb_ctx* ctx, hb_hsp* out, uint64_t cap, uint64_t* n, uint64_t* q_off, hb_segment* segs,
                  uint32_t seg_cap, uint32_t* n_seg);

@@ -1,50 +1,54 @@
-"""The driver's bench contract on the committed bench lines of this round (profiles/r1_i_*.json, produced by bench.py on a
-B200): every key the contract names is present and consistent.  CPU only -- guards the JSON shape, not the numbers."""
+"""bench.py's CPU-runnable behaviour: the reference arm really runs (plain-C port on a bounded sample of the named workload)
+and prints the contract's line; the roofline's algorithmic bytes are SURVEY 8(d)-(ii)'s formula; the multi-GPU sharding of
+the C4 configuration (chunk -> rank, then rebalance) is a balanced partition."""
 import json
 import os
+import subprocess
+import sys
+
+import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _line(name):
-    with open(os.path.join(ROOT, "profiles", name)) as f:
-        return json.loads(f.read().strip().splitlines()[-1])
-
-
-def test_own_arm_line_has_the_contract_keys():
+def test_reference_arm_runs_and_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--small", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
     baseline = json.load(open(os.path.join(ROOT, "BASELINE.json")))
-    for name, n in (("r1_i_bench_n1.json", 1), ("r1_i_bench_n2.json", 2)):
-        d = _line(name)
-        assert d["metric"] in baseline["metric"] and d["unit"] == "candidates/s"
-        assert d["n_gpus"] == n and d["steps"] >= 1 and d["warmup"] >= 3
-        assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
-        assert d["dtype"] == "int32" and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
-        assert "l2" in d["config"]                                   # how L2 is defeated between timed iterations
-        assert abs(d["value"] - d["config"]["candidates"] / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
-        e = d["e2e"]
-        assert e["unit"] == d["unit"] and 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
-        assert d["gpu_launches"] > 0
-        c = d["clocks"]
-        assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-        r = d["roofline"]
-        assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-        assert "traffic" in r and r["kernel"]
-        assert set(d["stages_ms"]) == {"sketch_cands", "seed_sort_cluster", "extend", "copy_rules_msa", "clean_judge", "compact"}
-    d = _line("r1_i_bench_n1.json")
+    assert d["impl"] == "reference" and d["metric"] in baseline["metric"] and d["unit"] == "candidates/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["unit"] == d["unit"] and cb["sample"]
-    assert d["roofline"]["traffic"] and d["roofline"]["traffic"] > 0
-    for k in ("per_type_candidates_per_s", "coarse_boundary", "tir_prefilter", "nonltr_prefilter", "known_te_masking", "homology_copy_search"):
-        assert k in d, k
-    assert set(d["per_type_candidates_per_s"]) >= {"tir", "helitron", "non_ltr"}
-
-
-def test_reference_arm_line_has_the_contract_keys():
-    d = _line("r1_i_bench_reference_arm.json")
-    own = _line("r1_i_bench_n1.json")
-    assert d["impl"] == "reference" and d["metric"] == own["metric"] and d["unit"] == own["unit"]
-    assert d["higher_is_better"] is True and d["config"]["workload"] == own["config"]["workload"]
-    cb = d["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "NOT the reference's Python" in cb["sample"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_algorithmic_bytes_follow_survey_8d():
+    sys.path.insert(0, ROOT)
+    import bench
+    L, flank, w = 1000, 50, 10
+    exp = (L + (L + 2 * flank)) * 3 / 8 + 8 * (2 * L / (w + 1)) + 16 + -(-(L + 100) // 4)
+    assert abs(float(bench.algo_bytes_pair(L)) - exp) < 1e-9
+    assert 2400 < exp < 2600                                   # SURVEY: "L = 1 kbp => ~2.5 kB / pair"
+    v = bench.algo_bytes_pair(np.array([200, 3000]))
+    assert v.shape == (2,) and v[1] > v[0]
+
+
+def test_chunk_sharding_is_a_balanced_partition():
+    sys.path.insert(0, ROOT)
+    from hite_b200 import dist as hd
+    rng = np.random.default_rng(3)
+    n = 4000
+    lengths = [int(x) for x in rng.integers(100, 3000, n)]
+    chunk = [int(x) for x in rng.choice(4, n, p=[0.55, 0.25, 0.15, 0.05])]
+    for world in (1, 2, 4, 8):
+        parts = [hd.shard_by_chunk(chunk, lengths, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        loads = [sum(lengths[i] for i in p) for p in parts]
+        assert max(loads) <= 1.01 * sum(loads) / world
+        # candidates stay on their chunk's rank unless the rebalance moved them: the lightest chunk's rank only receives
+        if world == 4:
+            assert {chunk[i] for i in parts[3]} >= {3}

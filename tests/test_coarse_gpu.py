@@ -47,6 +47,29 @@ def test_coarse_boundary_bit_exact_and_finds_planted_copies(ctx):
     assert sum(fam_hit.values()) >= 0.8 * len(fam_hit), fam_hit
 
 
+def test_sharded_coarse_boundary_parts_concatenate_to_the_whole(ctx):
+    """hb_coarse_boundary_part: the query-segment files dealt in contiguous blocks to 1, 2, 3, 5 parts; every part pairs its
+    minimizers against the whole index and chains its own files.  Parts concatenated in part order == the unsharded list
+    (which is the oracle's), also when there are more parts than files."""
+    wl = synth.make_workload(genome_bp=5_200_000, n_contigs=3, n_families=14, cands_per_family=1, copies=(6, 14),
+                             length=(300, 1500), seed=33, sub=(0.0, 0.04), indel=0.003)
+    ctx.load_genome(wl.contig_seqs, wl.contig_names)
+    ctx.build_index(15, 10)
+    whole = ctx.coarse_boundary(seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=4)
+    G = oracle.Genome(wl.contig_seqs)
+    _, _, exp_iv = G.coarse_boundary([len(c) for c in wl.contig_seqs], seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64)
+    key = lambda iv: [(int(o["chr"]), int(o["start"]), int(o["end"])) for o in iv]
+    assert key(whole) == exp_iv and len(exp_iv) > 50
+    for n_parts in (2, 3, 5, 9):
+        got, sizes = [], []
+        for p in range(n_parts):
+            part = ctx.coarse_boundary(seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=4, part=p, n_parts=n_parts)
+            sizes.append(len(part))
+            got += key(part)
+        assert got == exp_iv, n_parts
+        assert n_parts > 5 or min(sizes) > 0
+
+
 def test_determine_repeat_boundary_v5_fasta_contract(ctx, tmp_path):
     """cut-chunk FASTA in -> longest_repeats FASTA + .flanked.fa out, same names/sequence rules as the
     reference (Util.py:4354-4363, 4614-4634, 4783-4796)."""

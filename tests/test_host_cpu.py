@@ -116,6 +116,28 @@ exp = []
 for r in range(world):
     exp += [(names[i], seqs[i].lower()) for i in hd.shard_indices(len(seqs), r, world, [len(s) for s in seqs]) if len(seqs[i]) %% 8 != 0]
 assert got == exp, (got, exp)
+# the fused exchange bench.py and the stages use: one fixed-capacity all_gather_into_tensor, sizes in the header
+import numpy as np, torch
+shards = [hd.shard_indices(len(seqs), r, world, [len(s) for s in seqs]) for r in range(world)]
+g = hd.RecordGather([len(s) for s in shards], [sum(len(seqs[i]) for i in s) for s in shards], "cpu")
+for step in range(3):
+    keep = [i for i in shards[rank] if (i + step) %% 3 != 0]
+    cons = "".join(seqs[i].lower() for i in keep).encode()
+    g.start(np.array(keep, dtype=np.int32), np.array([len(seqs[i]) for i in keep], dtype=np.int32),
+            torch.frombuffer(bytearray(cons), dtype=torch.uint8) if cons else None)
+    got = g.finish()
+    if rank == 0:
+        idx, ln, body = got
+        exp_keep = [i for r in range(world) for i in shards[r] if (i + step) %% 3 != 0]
+        assert idx.tolist() == exp_keep and ln.tolist() == [len(seqs[i]) for i in exp_keep]
+        assert body.tobytes().decode() == "".join(seqs[i].lower() for i in exp_keep)
+    else:
+        assert got is None
+try:
+    g.start(np.arange(99, dtype=np.int32), np.ones(99, dtype=np.int32), None)
+    raise SystemExit("capacity overflow not detected")
+except RuntimeError:
+    pass
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
