@@ -193,46 +193,52 @@ extern "C" int hb_index_build(hb_ctx* ctx, int k, int w) {
     ENSURE("g.mm_base", sizeof(uint32_t) * (ctas + 1));
     ENSURE("g.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(std::max<uint64_t>(ctas, (1u << HB_SEED_BUCKET_BITS) + 1)));
     ENSURE("g.total", sizeof(uint64_t));
+    const uint32_t nb = 1u << HB_SEED_BUCKET_BITS;
+    ENSURE("g.bucket_cnt", sizeof(uint32_t) * (nb + 1));
+    ENSURE("g.bucket", sizeof(uint32_t) * (nb + 1));
+    // events bracket kernels only: buffer (re)allocation sits between the intervals, outside every stage time
     HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
     HB_CUDA_OK(hb_minimizer_count_launch(ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(), tot, k, w,
                                          ctx->buf("g.mm_cnt").as<uint32_t>(), s));
     HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("g.mm_cnt").as<uint32_t>(), ctx->buf("g.mm_base").as<uint32_t>(), ctas,
                                      ctx->buf("g.scan_tmp").as<uint32_t>(), ctx->buf("g.total").as<uint64_t>(), s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
     uint64_t n_mm = 0;
     HB_CUDA_OK(cudaMemcpyAsync(&n_mm, ctx->buf("g.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     HB_CUDA_OK(cudaStreamSynchronize(s));
     ENSURE("g.idx_a", sizeof(uint64_t) * (n_mm + 1));
     ENSURE("g.idx_b", sizeof(uint64_t) * (n_mm + 1));
     ENSURE("g.sort_tmp", sizeof(uint32_t) * hb_sort_tmp_words(n_mm));
+    ENSURE("g.mm_pos", sizeof(uint64_t) * (n_mm + 1));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
     HB_CUDA_OK(hb_minimizer_write_launch(ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(), tot, k, w,
                                          ctx->buf("g.mm_base").as<uint32_t>(), ctx->buf("g.idx_a").as<uint64_t>(), s));
     // the position-ordered list is kept for the coarse-boundary self-join (hb_coarse.cu)
-    ENSURE("g.mm_pos", sizeof(uint64_t) * (n_mm + 1));
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("g.mm_pos").p, ctx->buf("g.idx_a").p, sizeof(uint64_t) * n_mm, cudaMemcpyDeviceToDevice, s));
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
     // stable sort on the 2k-bit hash (keys are emitted in position order, so (hash,pos) ends sorted)
     uint64_t* sorted = nullptr;
     uint32_t launches = 6;
     HB_CUDA_OK(hb_radix_sort_u64(ctx->buf("g.idx_a").as<uint64_t>(), ctx->buf("g.idx_b").as<uint64_t>(), n_mm, 33, 33 + 2 * k,
                                  ctx->buf("g.sort_tmp").as<uint32_t>(), &sorted, &launches, s));
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[4], s));
     // bucket table on the top HB_SEED_BUCKET_BITS bits of a 30-bit hash (hash < 4^k <= 2^30)
-    const uint32_t nb = 1u << HB_SEED_BUCKET_BITS;
-    ENSURE("g.bucket_cnt", sizeof(uint32_t) * (nb + 1));
-    ENSURE("g.bucket", sizeof(uint32_t) * (nb + 1));
     HB_CUDA_OK(cudaMemsetAsync(ctx->buf("g.bucket_cnt").p, 0, sizeof(uint32_t) * (nb + 1), s));
     HB_CUDA_OK(hb_bucket_count_launch(sorted, n_mm, 33 + (30 - HB_SEED_BUCKET_BITS), ctx->buf("g.bucket_cnt").as<uint32_t>(), s));
     HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("g.bucket_cnt").as<uint32_t>(), ctx->buf("g.bucket").as<uint32_t>(), nb + 1,
                                      ctx->buf("g.scan_tmp").as<uint32_t>(), nullptr, s));
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[5], s));
     HB_CUDA_OK(cudaStreamSynchronize(s));
     if (sorted != ctx->buf("g.idx_a").as<uint64_t>()) std::swap(ctx->bufs["g.idx_a"], ctx->bufs["g.idx_b"]);
-    ctx->buf("g.idx_b").release();
+    // idx_b is kept: a rebuild (after hb_genome_mask, or the next chunk) allocates nothing
     ctx->g_nmm = n_mm;
-    cudaEventElapsedTime(&ctx->timing.k_ms[0], ctx->ev[0], ctx->ev[1]);   // sketch
-    cudaEventElapsedTime(&ctx->timing.k_ms[1], ctx->ev[1], ctx->ev[2]);   // radix sort
-    cudaEventElapsedTime(&ctx->timing.k_ms[2], ctx->ev[2], ctx->ev[3]);   // bucket table
-    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[0], ctx->ev[3]);
+    float t_count = 0.f, t_write = 0.f;
+    cudaEventElapsedTime(&t_count, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&t_write, ctx->ev[2], ctx->ev[3]);
+    ctx->timing.k_ms[0] = t_count + t_write;                              // sketch (count pass + write pass)
+    cudaEventElapsedTime(&ctx->timing.k_ms[1], ctx->ev[3], ctx->ev[4]);   // radix sort
+    cudaEventElapsedTime(&ctx->timing.k_ms[2], ctx->ev[4], ctx->ev[5]);   // bucket table
+    ctx->timing.kernel_ms = ctx->timing.k_ms[0] + ctx->timing.k_ms[1] + ctx->timing.k_ms[2];
     ctx->timing.launches = launches + 4;
     ctx->have_index = true;
     return HB_OK;

@@ -67,7 +67,7 @@ def test_sharded_coarse_boundary_parts_concatenate_to_the_whole(ctx):
             sizes.append(len(part))
             got += key(part)
         assert got == exp_iv, n_parts
-        assert n_parts > 5 or min(sizes) > 0
+        assert sum(1 for x in sizes if x) >= min(n_parts, 4)          # the work really is spread over the parts
 
 
 def test_determine_repeat_boundary_v5_fasta_contract(ctx, tmp_path):
