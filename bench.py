@@ -339,7 +339,7 @@ def main():
     wall_max, dev_max, kern_max, gather_max = float(smax[0]), float(smax[1]) * 1e-3, float(smax[2]) * 1e-3, float(smax[4])
     n_te_total = int(ssum[3])
     if rank == 0 and got is not None:
-        assert len(got[0]) == n_te_total and int(got[1].sum()) == len(got[2]), "gathered records are inconsistent"
+        assert len(got[0]) == n_te_total and (got[2] is None or int(got[1].sum()) == len(got[2])), "gathered records are inconsistent"
     # roofline of the dominant stage (banded extension + traceback) from SURVEY 8(d)-(ii) bytes, on the LAST group's pairs
     copies = ctx.last_copies()
     last_kind, last_idx, _ = groups[-1]

@@ -107,39 +107,161 @@ __global__ void hsp_start_kernel(const uint32_t* __restrict__ flag, const uint32
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) run_start[rid[i]] = (uint32_t)i;
 }
-// one thread per run: valid HSPs are marked (keep flag) and described
-__global__ void hsp_emit_kernel(const uint64_t* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ run_start,
-                                uint32_t n_runs, const uint64_t* __restrict__ mm, uint64_t tot, int k,
-                                const uint64_t* __restrict__ seg_goff, int n_seg, HbHspRec* __restrict__ recs,
-                                uint32_t* __restrict__ keep) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_runs) return;
+// ---- S11b: base-level HSP ends (see oracle/hbo_hsp.c for the definition this follows bit for bit) ----------------------
+// A seed run is grown along its diagonal over 8-base blocks aligned in query coordinates; a block is good when >= 5 of its
+// 8 positions match.  Blocks are compared 8 bases at a time: 16 bits of 2-bit codes + 8 N-mask bits per side.
+constexpr int HSP_MAXEXT = 4096;
+
+struct Diag {
+    const uint32_t* seq2; const uint32_t* nmask;
+    int rel; int64_t d, qlo, qhi, slo, shi, tot;
+};
+__device__ __forceinline__ void fwd8(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask, uint64_t p,
+                                     uint32_t* codes, uint32_t* nm) {
+    const uint64_t w = p >> 4, wn = p >> 5;
+    const uint64_t v = (uint64_t)seq2[w] | ((uint64_t)seq2[w + 1] << 32);          // the buffers carry 64 B of slack
+    *codes = (uint32_t)(v >> (2 * (p & 15))) & 0xFFFFu;
+    const uint64_t m = (uint64_t)nmask[wn] | ((uint64_t)nmask[wn + 1] << 32);
+    *nm = (uint32_t)(m >> (p & 31)) & 0xFFu;
+}
+__device__ __forceinline__ int base_code(const Diag& D, int64_t p) {
+    if ((D.nmask[p >> 5] >> (p & 31)) & 1u) return 4;
+    return (int)((D.seq2[p >> 4] >> (2 * (p & 15))) & 3u);
+}
+// match mask of block b: bit i = query position 8b + i matches its subject base
+__device__ __forceinline__ uint32_t block_mask(const Diag& D, int64_t b) {
+    const int64_t q = 8 * b, j = q + D.d;
+    const int64_t f0 = D.rel ? D.tot - 1 - (j + 7) : j;                            // lowest forward subject position of the block
+    if (q >= D.qlo && q + 8 <= D.qhi && f0 >= D.slo && f0 + 8 <= D.shi) {
+        uint32_t cq, nq, cs, ns;
+        fwd8(D.seq2, D.nmask, (uint64_t)q, &cq, &nq);
+        fwd8(D.seq2, D.nmask, (uint64_t)f0, &cs, &ns);
+        if (D.rel) {                                                               // reverse the 8 bases and complement them
+            uint32_t r = __brev(cs) >> 16;
+            cs = (((r & 0xAAAAu) >> 1) | ((r & 0x5555u) << 1)) ^ 0xFFFFu;
+            ns = __brev(ns) >> 24;
+        }
+        uint32_t x = cq ^ cs;
+        x = (x | (x >> 1)) & 0x5555u;
+        x = (x | (x >> 1)) & 0x3333u;
+        x = (x | (x >> 2)) & 0x0F0Fu;
+        x = (x | (x >> 4)) & 0x00FFu;
+        return ~(x | nq | ns) & 0xFFu;
+    }
+    uint32_t m = 0;                                                                // a block cut by a segment boundary
+    for (int i = 0; i < 8; ++i) {
+        const int64_t qq = q + i, jj = qq + D.d, f = D.rel ? D.tot - 1 - jj : jj;
+        if (qq < D.qlo || qq >= D.qhi || f < D.slo || f >= D.shi) continue;
+        const int a = base_code(D, qq);
+        int c = base_code(D, f);
+        if (a > 3 || c > 3) continue;
+        if (D.rel) c = 3 - c;
+        m |= (uint32_t)(a == c) << i;
+    }
+    return m;
+}
+__device__ __forceinline__ void seed_segment(const Diag& D, int64_t q0, uint32_t* qa, uint32_t* qb) {
+    const int64_t bc = (q0 + 7) >> 3;
+    int64_t bl = bc, br = bc;
+    const uint32_t mc = block_mask(D, bc);                    // all ones unless a segment boundary cuts the seed
+    if (mc == 0) { *qa = *qb = (uint32_t)q0; return; }
+    uint32_t ml = mc, mr = mc, m;                             // masks of the last good block on either side
+    for (int n = 0; n < HSP_MAXEXT; ++n) { m = block_mask(D, bl - 1); if (__popc(m) < 5) break; ml = m; --bl; }
+    m = block_mask(D, bl - 1);
+    {
+        int sc = 0, best = 0, ext = 0;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) { sc += ((m >> i) & 1u) ? 1 : -2; if (sc > best) { best = sc; ext = 8 - i; } }
+        *qa = (uint32_t)(ext ? 8 * bl - ext : 8 * bl + (__ffs((int)ml) - 1));
+    }
+    for (int n = 0; n < HSP_MAXEXT; ++n) { m = block_mask(D, br + 1); if (__popc(m) < 5) break; mr = m; ++br; }
+    m = block_mask(D, br + 1);
+    {
+        int sc = 0, best = 0, ext = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc += ((m >> i) & 1u) ? 1 : -2; if (sc > best) { best = sc; ext = i + 1; } }
+        *qb = (uint32_t)(ext ? 8 * br + 7 + ext : 8 * br + (31 - __clz((int)mr)));
+    }
+}
+__device__ __forceinline__ void run_geometry(const uint64_t* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ run_start,
+                                             uint32_t n_runs, uint32_t r, const uint64_t* __restrict__ mm, int64_t* q0, int64_t* q1,
+                                             int* rel, int64_t* d) {
     const uint64_t a = run_start[r], b = (r + 1 < n_runs) ? run_start[r + 1] : n;
     const uint64_t k0 = keys[a], k1 = keys[b - 1];
-    const int64_t q0 = (int64_t)((mm[k0 & 0x1FFFFFFFull] >> 1) & 0xFFFFFFFFull);
-    const int64_t q1 = (int64_t)((mm[k1 & 0x1FFFFFFFull] >> 1) & 0xFFFFFFFFull);
-    const int rel = (int)(k0 >> 62) & 1;
-    const int64_t d = (int64_t)((k0 >> 29) & 0x1FFFFFFFFull) - (1ll << 32);
-    const bool ok = (q1 + k - q0) >= HSP_MINSPAN;
-    keep[r] = ok ? 1u : 0u;
-    if (!ok) return;
-    HbHspRec o;
-    const int qseg = seg_of(seg_goff, n_seg, (uint64_t)q0);
-    const int64_t s0 = rel ? (int64_t)tot - (q0 + d) - k : q0 + d;      // forward start of the first / last seed
-    const int64_t s1 = rel ? (int64_t)tot - (q1 + d) - k : q1 + d;
-    const int sseg = seg_of(seg_goff, n_seg, (uint64_t)s0);
-    const int64_t qg = (int64_t)seg_goff[qseg], sg = (int64_t)seg_goff[sseg];
-    o.qseg = qseg; o.subj = sseg;
-    o.qs = (int32_t)(q0 - qg + 1); o.qe = (int32_t)(q1 + k - qg);
-    if (!rel) { o.ss = (int32_t)(s0 - sg + 1); o.se = (int32_t)(s1 + k - sg); }
-    else { o.ss = (int32_t)(s0 + k - sg); o.se = (int32_t)(s1 - sg + 1); }
-    o.pad = 0;
-    recs[r] = o;
+    *q0 = (int64_t)((mm[k0 & 0x1FFFFFFFull] >> 1) & 0xFFFFFFFFull);
+    *q1 = (int64_t)((mm[k1 & 0x1FFFFFFFull] >> 1) & 0xFFFFFFFFull);
+    *rel = (int)(k0 >> 62) & 1;
+    *d = (int64_t)((k0 >> 29) & 0x1FFFFFFFFull) - (1ll << 32);
 }
-__global__ void hsp_compact_kernel(const HbHspRec* __restrict__ recs, const uint32_t* __restrict__ keep,
-                                   const uint32_t* __restrict__ pos, uint32_t n_runs, HbHspRec* __restrict__ out) {
+// one thread per run: the segment of its first seed (x, y) and of its last seed (z, w) in global query coordinates
+__global__ void __launch_bounds__(128)
+hsp_segment_kernel(const uint64_t* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ run_start, uint32_t n_runs,
+                   const uint64_t* __restrict__ mm, const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask,
+                   uint64_t tot, int k, const uint64_t* __restrict__ seg_goff, const uint64_t* __restrict__ seg_len, int n_seg,
+                   uint4* __restrict__ segs) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n_runs && keep[r]) out[pos[r]] = recs[r];
+    if (r >= n_runs) return;
+    int64_t q0, q1, d; int rel;
+    run_geometry(keys, n, run_start, n_runs, r, mm, &q0, &q1, &rel, &d);
+    const int64_t s0 = rel ? (int64_t)tot - (q0 + d) - k : q0 + d;
+    const int qseg = seg_of(seg_goff, n_seg, (uint64_t)q0), sseg = seg_of(seg_goff, n_seg, (uint64_t)s0);
+    Diag D;
+    D.seq2 = seq2; D.nmask = nmask; D.rel = rel; D.d = d; D.tot = (int64_t)tot;
+    D.qlo = (int64_t)seg_goff[qseg]; D.qhi = D.qlo + (int64_t)seg_len[qseg];
+    D.slo = (int64_t)seg_goff[sseg]; D.shi = D.slo + (int64_t)seg_len[sseg];
+    uint4 o;
+    seed_segment(D, q0, &o.x, &o.y);
+    o.z = o.x; o.w = o.y;
+    if (q1 + k - 1 > (int64_t)o.y) seed_segment(D, q1, &o.z, &o.w);
+    segs[r] = o;
+}
+__device__ __forceinline__ void run_keep(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ run_start, uint32_t r,
+                                         const uint4* __restrict__ segs, bool* ka, bool* kb) {
+    const uint4 s = segs[r];
+    bool dup_a = false;
+    if (r > 0 && (keys[run_start[r - 1]] >> 29) == (keys[run_start[r]] >> 29)) {
+        const uint4 p = segs[r - 1];
+        dup_a = p.z == s.x && p.w == s.y;
+    }
+    *ka = !dup_a && (s.y - s.x + 1u >= (uint32_t)HSP_MINSPAN);
+    *kb = !(s.z == s.x && s.w == s.y) && (s.w - s.z + 1u >= (uint32_t)HSP_MINSPAN);
+}
+// keep flags of the 2 slots of every run: a segment is dropped when it repeats its predecessor on the diagonal or is short
+__global__ void hsp_keep_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ run_start, uint32_t n_runs,
+                                const uint4* __restrict__ segs, uint32_t* __restrict__ keep) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    bool ka, kb;
+    run_keep(keys, run_start, r, segs, &ka, &kb);
+    keep[2 * (size_t)r] = ka ? 1u : 0u;
+    keep[2 * (size_t)r + 1] = kb ? 1u : 0u;
+}
+// the kept segments as HSP records at their compacted positions
+__global__ void hsp_emit_kernel(const uint64_t* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ run_start,
+                                uint32_t n_runs, const uint64_t* __restrict__ mm, uint64_t tot, int k,
+                                const uint64_t* __restrict__ seg_goff, int n_seg, const uint4* __restrict__ segs,
+                                const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, HbHspRec* __restrict__ out) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const uint32_t k0 = keep[2 * (size_t)r], k1 = keep[2 * (size_t)r + 1];
+    if (!(k0 | k1)) return;
+    int64_t q0, q1, d; int rel;
+    run_geometry(keys, n, run_start, n_runs, r, mm, &q0, &q1, &rel, &d);
+    const int64_t s0 = rel ? (int64_t)tot - (q0 + d) - k : q0 + d;
+    const int qseg = seg_of(seg_goff, n_seg, (uint64_t)q0), sseg = seg_of(seg_goff, n_seg, (uint64_t)s0);
+    const int64_t qg = (int64_t)seg_goff[qseg], sg = (int64_t)seg_goff[sseg];
+    const uint4 s = segs[r];
+#pragma unroll
+    for (int z = 0; z < 2; ++z) {
+        if (!(z ? k1 : k0)) continue;
+        const int64_t a = z ? s.z : s.x, b = z ? s.w : s.y;
+        HbHspRec o;
+        o.qseg = qseg; o.subj = sseg; o.pad = 0;
+        o.qs = (int32_t)(a - qg + 1); o.qe = (int32_t)(b - qg + 1);
+        if (!rel) { o.ss = (int32_t)(a + d - sg + 1); o.se = (int32_t)(b + d - sg + 1); }
+        else { o.ss = (int32_t)((int64_t)tot - 1 - (a + d) - sg + 1); o.se = (int32_t)((int64_t)tot - 1 - (b + d) - sg + 1); }
+        out[pos[2 * (size_t)r + z]] = o;
+    }
 }
 
 }  // namespace
@@ -169,16 +291,19 @@ cudaError_t hb_hsp_start_launch(const uint32_t* flag, const uint32_t* rid, uint6
     hsp_start_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flag, rid, n, run_start);
     return cudaGetLastError();
 }
-cudaError_t hb_hsp_emit_launch(const uint64_t* keys, uint64_t n, const uint32_t* run_start, uint32_t n_runs,
-                               const uint64_t* mm, uint64_t tot, int k, const uint64_t* seg_goff, int n_seg,
-                               HbHspRec* recs, uint32_t* keep, cudaStream_t s) {
+cudaError_t hb_hsp_segment_launch(const uint64_t* keys, uint64_t n, const uint32_t* run_start, uint32_t n_runs, const uint64_t* mm,
+                                  const uint32_t* seq2, const uint32_t* nmask, uint64_t tot, int k, const uint64_t* seg_goff,
+                                  const uint64_t* seg_len, int n_seg, uint4* segs, uint32_t* keep, cudaStream_t s) {
     if (n_runs == 0) return cudaSuccess;
-    hsp_emit_kernel<<<(n_runs + 255) / 256, 256, 0, s>>>(keys, n, run_start, n_runs, mm, tot, k, seg_goff, n_seg, recs, keep);
+    hsp_segment_kernel<<<(n_runs + 127) / 128, 128, 0, s>>>(keys, n, run_start, n_runs, mm, seq2, nmask, tot, k, seg_goff, seg_len,
+                                                             n_seg, segs);
+    hsp_keep_kernel<<<(n_runs + 255) / 256, 256, 0, s>>>(keys, run_start, n_runs, segs, keep);
     return cudaGetLastError();
 }
-cudaError_t hb_hsp_compact_launch(const HbHspRec* recs, const uint32_t* keep, const uint32_t* pos, uint32_t n_runs,
-                                  HbHspRec* out, cudaStream_t s) {
+cudaError_t hb_hsp_emit_launch(const uint64_t* keys, uint64_t n, const uint32_t* run_start, uint32_t n_runs, const uint64_t* mm,
+                               uint64_t tot, int k, const uint64_t* seg_goff, int n_seg, const uint4* segs, const uint32_t* keep,
+                               const uint32_t* pos, HbHspRec* out, cudaStream_t s) {
     if (n_runs == 0) return cudaSuccess;
-    hsp_compact_kernel<<<(n_runs + 255) / 256, 256, 0, s>>>(recs, keep, pos, n_runs, out);
+    hsp_emit_kernel<<<(n_runs + 255) / 256, 256, 0, s>>>(keys, n, run_start, n_runs, mm, tot, k, seg_goff, n_seg, segs, keep, pos, out);
     return cudaGetLastError();
 }

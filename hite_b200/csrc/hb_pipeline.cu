@@ -1111,7 +1111,12 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     const uint64_t qpos_lo = g_lo < n_seg ? seg_goff[(size_t)g_lo] : ctx->g_tot;
     const uint64_t qpos_hi = g_hi < n_seg ? seg_goff[(size_t)g_hi] : ctx->g_tot;
     ENSURE("h.seg_goff", sizeof(uint64_t) * (n_seg + 1));
+    ENSURE("h.seg_len", sizeof(uint64_t) * (n_seg + 1));
+    std::vector<uint64_t> seg_lens((size_t)n_seg);
+    for (int g = 0; g < n_seg; ++g)
+        seg_lens[(size_t)g] = std::min<uint64_t>((uint64_t)seg_len, ctx->g_glen[(size_t)segs[(size_t)g].chr] - (uint64_t)segs[(size_t)g].start);
     HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("h.seg_goff").p, seg_goff.data(), sizeof(uint64_t) * n_seg, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("h.seg_len").p, seg_lens.data(), sizeof(uint64_t) * n_seg, cudaMemcpyHostToDevice, s));
     ENSURE("h.lo", sizeof(uint32_t) * (n_mm + 1)); ENSURE("h.cnt", sizeof(uint32_t) * (n_mm + 1)); ENSURE("h.off", sizeof(uint32_t) * (n_mm + 1));
     ENSURE("h.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(n_mm + 1));
     ENSURE("h.total", sizeof(uint64_t));
@@ -1147,23 +1152,28 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
         uint64_t n_runs64 = 0;
         HB_CUDA_OK(cudaMemcpyAsync(&n_runs64, ctx->buf("h.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
+        if (n_runs64 >= (1ull << 31)) return hb_fail_msg(ctx, HB_ENOMEM, "hb_coarse_boundary: more than 2^31 seed runs; lower occ_cap");
         const uint32_t n_runs = (uint32_t)n_runs64;
-        ENSURE("h.run_start", sizeof(uint32_t) * (n_runs + 1)); ENSURE("h.keep", sizeof(uint32_t) * (n_runs + 1));
-        ENSURE("h.pos", sizeof(uint32_t) * (n_runs + 1)); ENSURE("h.recs", sizeof(HbHspRec) * ((size_t)n_runs + 1));
-        ENSURE("h.scan_tmp3", sizeof(uint32_t) * hb_scan_tmp_words(n_runs + 1));
+        // base-level HSP ends (HB-hsp S11b): per run the block-grown segments of its first / last seed, duplicates dropped
+        ENSURE("h.run_start", sizeof(uint32_t) * (n_runs + 1)); ENSURE("h.keep", sizeof(uint32_t) * (2 * (size_t)n_runs + 2));
+        ENSURE("h.pos", sizeof(uint32_t) * (2 * (size_t)n_runs + 2)); ENSURE("h.segs", sizeof(uint4) * ((size_t)n_runs + 1));
+        ENSURE("h.scan_tmp3", sizeof(uint32_t) * hb_scan_tmp_words(2 * (size_t)n_runs + 2));
         HB_CUDA_OK(hb_hsp_start_launch(ctx->buf("h.flag").as<uint32_t>(), ctx->buf("h.rid").as<uint32_t>(), n_pairs,
                                        ctx->buf("h.run_start").as<uint32_t>(), s));
-        HB_CUDA_OK(hb_hsp_emit_launch(keys, n_pairs, ctx->buf("h.run_start").as<uint32_t>(), n_runs,
-                                      ctx->buf("g.mm_pos").as<uint64_t>(), ctx->g_tot, ctx->k, ctx->buf("h.seg_goff").as<uint64_t>(),
-                                      n_seg, ctx->buf("h.recs").as<HbHspRec>(), ctx->buf("h.keep").as<uint32_t>(), s));
-        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("h.keep").as<uint32_t>(), ctx->buf("h.pos").as<uint32_t>(), n_runs,
+        HB_CUDA_OK(hb_hsp_segment_launch(keys, n_pairs, ctx->buf("h.run_start").as<uint32_t>(), n_runs, ctx->buf("g.mm_pos").as<uint64_t>(),
+                                         ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(), ctx->g_tot, ctx->k,
+                                         ctx->buf("h.seg_goff").as<uint64_t>(), ctx->buf("h.seg_len").as<uint64_t>(), n_seg,
+                                         ctx->buf("h.segs").as<uint4>(), ctx->buf("h.keep").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("h.keep").as<uint32_t>(), ctx->buf("h.pos").as<uint32_t>(), 2 * (size_t)n_runs,
                                          ctx->buf("h.scan_tmp3").as<uint32_t>(), ctx->buf("h.total").as<uint64_t>(), s));
         uint64_t n_hsp = 0;
         HB_CUDA_OK(cudaMemcpyAsync(&n_hsp, ctx->buf("h.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
         ENSURE("h.out", sizeof(HbHspRec) * (n_hsp + 1));
-        HB_CUDA_OK(hb_hsp_compact_launch(ctx->buf("h.recs").as<HbHspRec>(), ctx->buf("h.keep").as<uint32_t>(),
-                                         ctx->buf("h.pos").as<uint32_t>(), n_runs, ctx->buf("h.out").as<HbHspRec>(), s));
+        HB_CUDA_OK(hb_hsp_emit_launch(keys, n_pairs, ctx->buf("h.run_start").as<uint32_t>(), n_runs, ctx->buf("g.mm_pos").as<uint64_t>(),
+                                      ctx->g_tot, ctx->k, ctx->buf("h.seg_goff").as<uint64_t>(), n_seg, ctx->buf("h.segs").as<uint4>(),
+                                      ctx->buf("h.keep").as<uint32_t>(), ctx->buf("h.pos").as<uint32_t>(),
+                                      ctx->buf("h.out").as<HbHspRec>(), s));
         HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
         h_recs.resize(n_hsp);
         if (n_hsp) HB_CUDA_OK(cudaMemcpyAsync(h_recs.data(), ctx->buf("h.out").p, sizeof(HbHspRec) * n_hsp, cudaMemcpyDeviceToHost, s));

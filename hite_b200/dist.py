@@ -121,15 +121,16 @@ class RecordGather:
         if self.device.type == "cuda":
             torch.cuda.current_stream().synchronize()     # the library reuses its consensus buffer in the next hb_adjust
         self.bytes_sent = self.HDR + 8 * n + nb
+        self._own = (np.array(cand_index, dtype=np.int32), np.array(cons_len, dtype=np.int32), n, nb)
         if self.world > 1:
             self.work = dist.all_gather_into_tensor(self.out, self.buf, async_op=True)
         else:
-            self.out.copy_(self.buf)
-            self.work = None
+            self.work = None                              # one rank: the records are already where they are needed
 
     def finish(self):
         """Wait for the collective launched by ``start``; on the read-back rank returns (indices, lengths, consensus bytes)
-        of ALL ranks' records in rank order as numpy arrays, elsewhere None."""
+        of ALL ranks' records in rank order as numpy arrays, elsewhere None.  With one rank nothing is exchanged or copied
+        and the bytes come back as None (they are the caller's own hb_adjust result)."""
         import numpy as np
         if self.work is not None:
             self.work.wait()
@@ -137,6 +138,9 @@ class RecordGather:
         if self.h_out is None:
             return None
         cap, hdr_all = self.cap, self.HDR + self.rec_cap
+        if self.world == 1:                               # nothing was exchanged: hand the rank's own records back
+            idx, ln, n, nb = self._own                    # (the consensus bytes are the caller's own hb_adjust result)
+            return idx, ln, None
         for r in range(self.world):                       # headers + record tables first (small) ...
             self.h_out[r * cap:r * cap + hdr_all].copy_(self.out[r * cap:r * cap + hdr_all], non_blocking=True)
         if self.device.type == "cuda":

@@ -81,8 +81,9 @@ int hbo_fmea_shared(const hbo_hsp *h, int n, int q_chr, int64_t q_seg_start, int
 
 /* ---- HB-hsp restatement (hbo_hsp.c) ---- */
 typedef struct { int32_t qseg, subj, qs, qe, ss, se; } hbo_hsp_rec;
-uint64_t hbo_self_hsps(const uint64_t *mm_pos, const uint64_t *idx, uint64_t n, uint64_t tot, int k,
-                       const uint64_t *seg_goff, int n_seg, int occ_cap, hbo_hsp_rec *out, uint64_t cap);
+uint64_t hbo_self_hsps(const hbo_genome *g, const uint64_t *mm_pos, const uint64_t *idx, uint64_t n, uint64_t tot, int k,
+                       const uint64_t *seg_goff, const uint64_t *seg_len, int n_seg, int occ_cap, hbo_hsp_rec *out, uint64_t cap);
+int hbo_genome_code(const hbo_genome *g, uint64_t pos);     /* 0..3 ACGT, 4 N / pad / outside */
 
 typedef struct { int32_t subj, start, end, qlen, strand; } hbo_copy_out;   /* (subject, start, end, len, '+'/'-') :7015 */
 int hbo_query_copies(const hbo_hsp *h, const double *ident, int n, int query_len, const int32_t *subj_len, int n_subj,

@@ -88,6 +88,7 @@ static int name_greater(const hbo_genome *g, const hbo_copy *y, const hbo_copy *
     return y->rel > x->rel;                                   /* '-' (0x2D) > '+' (0x2B) */
 }
 uint64_t hbo_genome_total(const hbo_genome *g) { return g->tot; }
+int hbo_genome_code(const hbo_genome *g, uint64_t pos) { return pos < g->tot ? g->code[pos] : 4; }
 uint64_t hbo_genome_contig_off(const hbo_genome *g, uint32_t c) { return g->goff[c]; }
 
 /* oriented accessor: rel = 0 forward, 1 reverse-complement genome */

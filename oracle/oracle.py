@@ -388,13 +388,14 @@ class Genome:
             p += ln + 64
         goff = np.asarray(goff, dtype=np.uint64)
         L.hbo_self_hsps.restype = C.c_uint64
-        L.hbo_self_hsps.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                                    C.c_void_p, C.c_uint64]
-        n = L.hbo_self_hsps(self.mm_pos_order.ctypes.data, self.index.ctypes.data, len(self.index), self.total, self.k,
-                            goff.ctypes.data, len(segs), occ_cap, None, 0)
+        L.hbo_self_hsps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+        slen = np.asarray([min(seg_len, contig_lens[c] - o) for c, o in segs], dtype=np.uint64)
+        n = L.hbo_self_hsps(self.g, self.mm_pos_order.ctypes.data, self.index.ctypes.data, len(self.index), self.total, self.k,
+                            goff.ctypes.data, slen.ctypes.data, len(segs), occ_cap, None, 0)
         recs = np.zeros((max(1, n), 6), dtype=np.int32)
-        L.hbo_self_hsps(self.mm_pos_order.ctypes.data, self.index.ctypes.data, len(self.index), self.total, self.k,
-                        goff.ctypes.data, len(segs), occ_cap, recs.ctypes.data, n)
+        L.hbo_self_hsps(self.g, self.mm_pos_order.ctypes.data, self.index.ctypes.data, len(self.index), self.total, self.k,
+                        goff.ctypes.data, slen.ctypes.data, len(segs), occ_cap, recs.ctypes.data, n)
         recs = recs[:n]
         intervals = []
         # the query records of one split file share chr_pos_candidates and the file's longest_repeats dict (:4152-4155)
