@@ -133,6 +133,132 @@ __device__ __forceinline__ bool name_greater(const int32_t* __restrict__ crank, 
     return rel_y > rel_x;                                 // '-' (0x2D) > '+' (0x2B)
 }
 
+// S8b: chains of local alignments (definition and rationale: oracle/hbo_align.c::chain_pieces, which this follows bit for
+// bit).  A copy with an indel longer than the band, or a drifting diagonal, comes back from S7 as several colinear partial
+// alignments; minimap2 reports ONE alignment with a long I / D operation there (module/Util.py:7952-7961) and the copy rules
+// of :8007-8022 judge the whole span.  Warp per candidate: the leftmost unused partial piece starts a chain and repeatedly
+// takes the best compatible piece to its right; the chain is merged into the edit record of its best-ranked piece.
+constexpr int CH_MINADD = 20, CH_MAXGAP = 1000, CH_MAXTRIM = 64, CH_MAXN = 512, CH_MAXPIECES = 32;
+__global__ void __launch_bounds__(128)
+chain_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, uint32_t n_cand,
+             const uint32_t* __restrict__ clen, const uint32_t* __restrict__ qrec_unit_off, uint32_t* __restrict__ qrec,
+             HbAln* __restrict__ alns) {
+    __shared__ uint8_t s_used[4][CH_MAXN];
+    __shared__ int s_piece[4][CH_MAXPIECES], s_cut[4][CH_MAXPIECES];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t c = blockIdx.x * 4 + wid;
+    if (c >= n_cand) return;
+    const uint32_t p0 = pair_off[c];
+    const int n = min((int)(pair_off[c + 1] - p0), CH_MAXN);
+    const int L = (int)clen[c];
+    uint8_t* used = s_used[wid];
+    int* piece = s_piece[wid];
+    int* cuts = s_cut[wid];
+    int n_partial = 0;
+    for (int x = lane; x < n; x += 32) {
+        const HbAln a = alns[p0 + x];
+        const bool u = a.score <= 0 || (double)(a.i_e - a.i_s + 1) / (double)L >= 0.95;        // not a partial piece
+        used[x] = u ? 1 : 0;
+        n_partial += u ? 0 : 1;
+    }
+    if (__ballot_sync(HB_FULL, n_partial > 0) == 0u) return;
+    __syncwarp();
+    auto qr_of = [&](int x) -> uint32_t* { return qrec + ((size_t)qrec_unit_off[p0 + x] << 5); };
+    auto tpos = [&](int x, int qpos) -> int64_t {
+        return pairs[p0 + x].j0 + qpos + (int64_t)(qr_of(x)[qpos] & 0xFFFFu) - 32768;
+    };
+    for (;;) {
+        // the leftmost unused partial piece, best rank on ties
+        uint32_t key = 0xFFFFFFFFu;
+        for (int x = lane; x < n; x += 32)
+            if (!used[x]) key = min(key, ((uint32_t)alns[p0 + x].i_s << 16) | (uint32_t)x);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) key = min(key, __shfl_xor_sync(HB_FULL, key, o));
+        if (key == 0xFFFFFFFFu) break;
+        const int lead = (int)(key & 0xFFFFu);
+        __syncwarp();
+        if (lane == 0) { used[lead] = 1; piece[0] = lead; }
+        __syncwarp();
+        int np = 1;
+        while (np < CH_MAXPIECES) {
+            const int A = piece[np - 1];
+            const HbAln aA = alns[p0 + A];
+            const uint32_t relA = pairs[p0 + A].rel;
+            unsigned long long best = ~0ull;                  // (|gq - gt| << 12 | y) << 16 | cut
+            for (int y = lane; y < n; y += 32) {
+                if (used[y] || pairs[p0 + y].rel != relA) continue;
+                const HbAln aY = alns[p0 + y];
+                if (!(aY.i_s > aA.i_s && aY.i_e >= aA.i_e + CH_MINADD && aY.j_e > aA.j_e)) continue;
+                int cut = aA.i_e < aY.i_s - 1 ? aA.i_e : aY.i_s - 1;
+                for (int t = 0; t < CH_MAXTRIM && cut >= aA.i_s && tpos(A, cut) >= aY.j_s; ++t) --cut;
+                if (cut < aA.i_s) continue;
+                const int64_t tA = tpos(A, cut);
+                if (!(aY.j_s > tA)) continue;
+                const int64_t gq = aY.i_s - 1 - cut, gt = aY.j_s - tA - 1;
+                if (gq > CH_MAXGAP || gt > CH_MAXGAP) continue;
+                const unsigned long long k2 = ((((unsigned long long)(gq > gt ? gq - gt : gt - gq) << 12) | (unsigned long long)y) << 16) |
+                                              (unsigned long long)cut;
+                best = k2 < best ? k2 : best;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(HB_FULL, best, o); best = t < best ? t : best; }
+            if (best == ~0ull) break;
+            const int by = (int)((best >> 16) & 0xFFFu), bcut = (int)(best & 0xFFFFu);
+            __syncwarp();
+            if (lane == 0) { cuts[np - 1] = bcut; used[by] = 1; piece[np] = by; }
+            __syncwarp();
+            ++np;
+        }
+        if (np == 1) continue;
+        int h = piece[0];
+        for (int t = 1; t < np; ++t) h = min(h, piece[t]);                 // best rank = smallest locus index
+        const int64_t j0h = pairs[p0 + h].j0;
+        uint32_t* qh = qr_of(h);
+        int score = 0;
+        for (int t = 0; t < np; ++t) {
+            const int x = piece[t];
+            const HbAln ax = alns[p0 + x];
+            const int from = ax.i_s, to = (t + 1 < np) ? cuts[t] : ax.i_e;
+            score += ax.score;
+            int64_t tA = 0;
+            if (t + 1 < np) tA = tpos(x, to);                              // read before the junction is rewritten
+            __syncwarp();
+            if (x != h) {
+                const uint32_t* qx = qr_of(x);
+                const uint32_t delta = (uint32_t)(int32_t)(pairs[p0 + x].j0 - j0h);
+                for (int p = from + lane; p <= to; p += 32) {
+                    const uint32_t v = qx[p];
+                    qh[p] = (v & 0xFFFF0000u) | ((v + delta) & 0xFFFFu);
+                }
+            }
+            __syncwarp();
+            if (t + 1 < np) {
+                const HbAln ay = alns[p0 + piece[t + 1]];
+                const int64_t gt = ay.j_s - tA - 1;
+                if (lane == 0) qh[to] = (qh[to] & ~(255u << 16)) | ((uint32_t)(gt > 255 ? 255 : gt) << 16);
+                for (int p = to + 1 + lane; p < ay.i_s; p += 32)
+                    qh[p] = ((uint32_t)(tA - j0h - p + 32768) & 0xFFFFu) | (1u << 24) | (1u << 25);
+            }
+            __syncwarp();
+        }
+        const HbAln first = alns[p0 + piece[0]], last = alns[p0 + piece[np - 1]];
+        __syncwarp();
+        if (lane == 0) {
+            for (int t = 0; t < np; ++t) {
+                const int x = piece[t];
+                if (x == h) continue;
+                HbAln z = alns[p0 + x];
+                z.score = 0; z.i_s = -1; z.i_e = -1; z.j_s = 0; z.j_e = 0;
+                alns[p0 + x] = z;
+            }
+            HbAln m = alns[p0 + h];
+            m.score = score; m.i_s = first.i_s; m.i_e = last.i_e; m.j_s = first.j_s; m.j_e = last.j_e;
+            alns[p0 + h] = m;
+        }
+        __syncwarp();
+    }
+}
+
 // S8 dedup + S9 "max_rows longest": warp per candidate
 constexpr int SEL_MAX = 512;
 __global__ void __launch_bounds__(128)
@@ -349,6 +475,12 @@ cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const 
                                   cudaStream_t s) {
     if (n_pairs == 0) return cudaSuccess;
     copy_filter_kernel<<<(n_pairs + 255) / 256, 256, 0, s>>>(pairs, n_pairs, clen, goff, glen, n_contig, tot, flank, alns);
+    return cudaGetLastError();
+}
+cudaError_t hb_chain_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, const uint32_t* clen,
+                            const uint32_t* qrec_unit_off, uint32_t* qrec, HbAln* alns, cudaStream_t s) {
+    if (n_cand == 0) return cudaSuccess;
+    chain_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, clen, qrec_unit_off, qrec, alns);
     return cudaGetLastError();
 }
 cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, int max_rows,

@@ -6,6 +6,9 @@
 cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const uint32_t* clen, const uint64_t* goff,
                                   const uint64_t* glen, uint32_t n_contig, uint64_t tot, int flank, HbAln* alns,
                                   cudaStream_t s);
+// S8b: colinear partial alignments of one copy merged into the edit record of their best-ranked piece
+cudaError_t hb_chain_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, const uint32_t* clen,
+                            const uint32_t* qrec_unit_off, uint32_t* qrec, HbAln* alns, cudaStream_t s);
 cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, int max_rows,
                                   int trunc_gate, const int32_t* crank, HbAln* alns, uint32_t* n_rows, uint32_t* n_trows,
                                   cudaStream_t s);

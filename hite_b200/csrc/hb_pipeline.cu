@@ -367,19 +367,30 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
                                      47 + cand_bits, LB("s.sort_tmp").as<uint32_t>(), &d_hits, &launches, s));
         // ---- S5: clusters -----------------------------------------------------------------------
         ENSURE_L("s.flag", sizeof(uint32_t) * n_hits); ENSURE_L("s.cid", sizeof(uint32_t) * n_hits);
+        ENSURE_L("s.flag2", sizeof(uint32_t) * n_hits);
         ENSURE_L("s.scan_tmp2", sizeof(uint32_t) * hb_scan_tmp_words(n_hits));
+        ENSURE_L("s.cl_start", sizeof(uint32_t) * (n_hits + 1));
         HB_CUDA_OK(hb_cluster_flag_launch(d_hits, n_hits, LB("s.flag").as<uint32_t>(), s));
         HB_CUDA_OK(hb_exclusive_scan_u32(LB("s.flag").as<uint32_t>(), LB("s.cid").as<uint32_t>(), n_hits,
                                          LB("s.scan_tmp2").as<uint32_t>(), LB("s.total").as<uint64_t>(), s));
         uint64_t ncl64 = 0;
         HB_CUDA_OK(cudaMemcpyAsync(&ncl64, LB("s.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        HB_CUDA_OK(cudaStreamSynchronize(s));
-        n_cl = (uint32_t)ncl64;
-        ENSURE_L("s.cl_start", sizeof(uint32_t) * (n_cl + 1));
-        ENSURE_L("s.cand_first", sizeof(uint32_t) * (n_cand + 1));
-        ENSURE_L("s.loci", sizeof(HbLocus) * (size_t)n_cand * max_loci);
         HB_CUDA_OK(hb_cluster_start_launch(LB("s.flag").as<uint32_t>(), LB("s.cid").as<uint32_t>(), n_hits,
                                            LB("s.cl_start").as<uint32_t>(), s));
+        HB_CUDA_OK(cudaStreamSynchronize(s));
+        // S5b: clusters wider than the band are cut into pieces (second flag pass + rescan)
+        HB_CUDA_OK(hb_cluster_split_launch(d_hits, n_hits, LB("s.flag").as<uint32_t>(), LB("s.cid").as<uint32_t>(),
+                                           LB("s.cl_start").as<uint32_t>(), (uint32_t)ncl64, LB("s.flag2").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(LB("s.flag2").as<uint32_t>(), LB("s.cid").as<uint32_t>(), n_hits,
+                                         LB("s.scan_tmp2").as<uint32_t>(), LB("s.total").as<uint64_t>(), s));
+        HB_CUDA_OK(cudaMemcpyAsync(&ncl64, LB("s.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(hb_cluster_start_launch(LB("s.flag2").as<uint32_t>(), LB("s.cid").as<uint32_t>(), n_hits,
+                                           LB("s.cl_start").as<uint32_t>(), s));
+        HB_CUDA_OK(cudaStreamSynchronize(s));
+        n_cl = (uint32_t)ncl64;
+        launches += 6;
+        ENSURE_L("s.cand_first", sizeof(uint32_t) * (n_cand + 1));
+        ENSURE_L("s.loci", sizeof(HbLocus) * (size_t)n_cand * max_loci);
         HB_CUDA_OK(hb_rank_select_launch(d_hits, n_hits, LB("s.cl_start").as<uint32_t>(), n_cl,
                                          LB("s.cand_first").as<uint32_t>(), n_cand, max_loci,
                                          LB("s.loci").as<HbLocus>(), LB("s.n_loci").as<uint32_t>(), s));
@@ -502,6 +513,9 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
     ENSURE_L("m.ins", sizeof(uint32_t) * (cand_off[n_cand] + 1));
     HB_CUDA_OK(cudaMemsetAsync(LB("m.ins").p, 0, sizeof(uint32_t) * (cand_off[n_cand] + 1), s));
     HB_CUDA_OK(cudaMemsetAsync(LB("m.n_rows").p, 0, sizeof(uint32_t) * (n_cand + 1), s));
+    if (n_pairs > 0)
+        HB_CUDA_OK(hb_chain_launch(LB("p.pairs").as<HbLocus>(), LB("s.pair_off").as<uint32_t>(), n_cand, d_clen,
+                                   LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(), LB("p.alns").as<HbAln>(), s));
     HB_CUDA_OK(hb_copy_filter_launch(LB("p.pairs").as<HbLocus>(), n_pairs, d_clen, ctx->buf("g.goff").as<uint64_t>(),
                                      ctx->buf("g.glen").as<uint64_t>(), ctx->g_ncontig, tot, flank, LB("p.alns").as<HbAln>(), s));
     HB_CUDA_OK(hb_copy_select_launch(LB("p.pairs").as<HbLocus>(), LB("s.pair_off").as<uint32_t>(), n_cand,

@@ -94,6 +94,26 @@ __global__ void cluster_start_kernel(const uint32_t* __restrict__ flag, const ui
     if (i >= n) return;
     if (flag[i]) cl_start[cid[i]] = (uint32_t)i;
 }
+// S5b: a cluster wider than the band (a copy whose diagonal drifts) is cut into pieces of HB_SPLIT_SPREAD + 1 diagonals
+// counted from its first diagonal; each piece gets its own band and the pieces are chained after the alignment (S8b).
+// cid = exclusive scan of flag, so the cluster of hit i is cid[i] - (flag[i] ? 0 : 1).
+__global__ void cluster_split_kernel(const uint64_t* __restrict__ hits, uint64_t n, const uint32_t* __restrict__ flag,
+                                     const uint32_t* __restrict__ cid, const uint32_t* __restrict__ cl_start, uint32_t n_cl,
+                                     uint32_t* __restrict__ flag2) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t f = flag[i];
+    if (!f) {
+        const uint32_t c = cid[i] - 1u;
+        const uint64_t a = cl_start[c], b = (c + 1 < n_cl) ? cl_start[c + 1] : n;
+        const int64_t d0 = (int64_t)((hits[a] >> 13) & 0x1FFFFFFFFull), dl = (int64_t)((hits[b - 1] >> 13) & 0x1FFFFFFFFull);
+        if (dl - d0 > HB_SPLIT_SPREAD) {
+            const int64_t di = (int64_t)((hits[i] >> 13) & 0x1FFFFFFFFull), dp = (int64_t)((hits[i - 1] >> 13) & 0x1FFFFFFFFull);
+            f = ((di - d0) / (HB_SPLIT_SPREAD + 1) != (dp - d0) / (HB_SPLIT_SPREAD + 1)) ? 1u : 0u;
+        }
+    }
+    flag2[i] = f;
+}
 // per-candidate first cluster: clusters are ordered by candidate
 __global__ void cand_first_cluster_kernel(const uint64_t* __restrict__ hits, const uint32_t* __restrict__ cl_start,
                                           uint32_t n_cl, uint32_t n_cand, uint32_t* __restrict__ cand_first) {
@@ -254,6 +274,12 @@ cudaError_t hb_seed_fill_launch(const uint64_t* cm, uint32_t n_cm, const uint64_
 cudaError_t hb_cluster_flag_launch(const uint64_t* hits, uint64_t n, uint32_t* flag, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     cluster_flag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hits, n, flag);
+    return cudaGetLastError();
+}
+cudaError_t hb_cluster_split_launch(const uint64_t* hits, uint64_t n, const uint32_t* flag, const uint32_t* cid,
+                                    const uint32_t* cl_start, uint32_t n_cl, uint32_t* flag2, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    cluster_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hits, n, flag, cid, cl_start, n_cl, flag2);
     return cudaGetLastError();
 }
 cudaError_t hb_cluster_start_launch(const uint32_t* flag, const uint32_t* cid, uint64_t n, uint32_t* cl_start,

@@ -7,6 +7,7 @@
 #define HB_DIAG_OFF 65536
 #define HB_DGAP 16
 #define HB_MIN_SEEDS 3
+#define HB_SPLIT_SPREAD 47
 
 struct HbLocus {          // one ranked locus of a candidate (HB-align S6)
     uint32_t cand, rel, nseeds, rank;
@@ -30,6 +31,8 @@ cudaError_t hb_seed_fill_launch(const uint64_t* cm, uint32_t n_cm, const uint64_
                                 const uint32_t* m_lo, const uint32_t* m_cnt, const uint32_t* m_off, uint64_t* hits,
                                 cudaStream_t s);
 cudaError_t hb_cluster_flag_launch(const uint64_t* hits, uint64_t n, uint32_t* flag, cudaStream_t s);
+cudaError_t hb_cluster_split_launch(const uint64_t* hits, uint64_t n, const uint32_t* flag, const uint32_t* cid,
+                                    const uint32_t* cl_start, uint32_t n_cl, uint32_t* flag2, cudaStream_t s);
 cudaError_t hb_cluster_start_launch(const uint32_t* flag, const uint32_t* cid, uint64_t n, uint32_t* cl_start,
                                     cudaStream_t s);
 cudaError_t hb_rank_select_launch(const uint64_t* hits, uint64_t n_hits, const uint32_t* cl_start, uint32_t n_cl,

@@ -264,6 +264,7 @@ int hbo_align_pair(const hbo_genome *g, const uint8_t *q /*codes*/, int L, int r
 #define DIAG_OFF 65536
 #define DGAP 16
 #define MIN_SEEDS 3
+#define SPLIT_SPREAD 47
 
 static uint64_t lower_bound_h(const uint64_t *idx, uint64_t n, uint32_t h) {
     uint64_t lo = 0, hi = n;
@@ -332,7 +333,27 @@ uint64_t hbo_find_loci(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx,
             if (d - dl > DGAP) break;
             dl = d; ++j;
         }
-        if (j - i >= MIN_SEEDS) { cl[ncl].cand = c; cl[ncl].rel = rel; cl[ncl].n = (uint32_t)(j - i); cl[ncl].dmin = d0; cl[ncl].dmax = dl; ++ncl; }
+        if (dl - d0 <= SPLIT_SPREAD) {
+            if (j - i >= MIN_SEEDS) { cl[ncl].cand = c; cl[ncl].rel = rel; cl[ncl].n = (uint32_t)(j - i); cl[ncl].dmin = d0; cl[ncl].dmax = dl; ++ncl; }
+        } else {
+            /* S5b: a run wider than the band (a copy whose diagonal drifts: net insertions / deletions) is cut into pieces of
+               SPLIT_SPREAD + 1 diagonals counted from its first diagonal; each piece is aligned in its own band and the
+               pieces are chained afterwards (S8b) */
+            uint64_t a = i;
+            while (a < j) {
+                const int64_t da = (int64_t)((hits[a] >> 13) & 0x1FFFFFFFFull);
+                const int64_t bucket = (da - d0) / (SPLIT_SPREAD + 1);
+                uint64_t b = a + 1;
+                int64_t db = da;
+                while (b < j) {
+                    const int64_t d = (int64_t)((hits[b] >> 13) & 0x1FFFFFFFFull);
+                    if ((d - d0) / (SPLIT_SPREAD + 1) != bucket) break;
+                    db = d; ++b;
+                }
+                if (b - a >= MIN_SEEDS) { cl[ncl].cand = c; cl[ncl].rel = rel; cl[ncl].n = (uint32_t)(b - a); cl[ncl].dmin = da; cl[ncl].dmax = db; ++ncl; }
+                a = b;
+            }
+        }
         i = j;
     }
     uint64_t nout = 0;
@@ -373,6 +394,99 @@ static int contig_of(const hbo_genome *g, int64_t fs, int64_t fe) {
     return -1;
 }
 
+/* S8b: chains of local alignments.  A copy that differs from the candidate by an indel longer than the band, or whose
+   diagonal drifts out of it, comes back from S7 as several partial alignments ("pieces") that are colinear in the candidate
+   and in the genome -- what minimap2 reports as ONE alignment with a long I / D operation (its chaining bandwidth is 500,
+   `-r`; the copy rules of Util.py:8007-8022 then judge the whole span).  Pieces of one strand are chained left to right:
+   the leftmost unused partial piece (query coverage < 0.95) starts a chain and repeatedly takes the piece B that
+     starts after the chain's last piece A started, ends >= CH_MINADD query bases after A's end, ends later in the
+     genome, and whose junction  cut = min(A.i_e, B.i_s - 1), lowered (by at most CH_MAXTRIM) while A's genome column there is
+     not left of B.j_s,  cut >= A.i_s,  tA = genome column of A at query position cut,
+     B.j_s > tA,  query gap  gq = B.i_s - 1 - cut <= CH_MAXGAP,  genome gap  gt = B.j_s - tA - 1 <= CH_MAXGAP
+   minimises (|gq - gt|, rank).  The chain lives in the slot of its best-ranked piece (j0 of that piece): A's records beyond
+   cut are dropped, the gq skipped query bases become "query base without target" records, the gt skipped genome bases
+   become target-only bases after position cut (shown up to 255), B's records follow.  Absorbed pieces are cleared. */
+#define CH_MINADD 20
+#define CH_MAXGAP 1000
+#define CH_MAXTRIM 64
+#define CH_MAXPIECES 32
+static int64_t piece_tpos(const hbo_locus *loci, const uint32_t *qrecs, int L, int x, int qpos) {
+    return loci[x].j0 + qpos + (int64_t)(qrecs[(size_t)x * L + qpos] & 0xFFFFu) - 32768;
+}
+static void chain_pieces(int nl, const hbo_locus *loci, hbo_copy *cps, uint32_t *qrecs, int L) {
+    uint8_t *used = (uint8_t *)calloc((size_t)nl + 1, 1);
+    int *piece = (int *)malloc(sizeof(int) * ((size_t)nl + 1));
+    int *cuts = (int *)malloc(sizeof(int) * ((size_t)nl + 1));
+    uint32_t *tmp = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)L + 1));
+    for (int x = 0; x < nl; ++x)
+        if (cps[x].score <= 0 || (double)(cps[x].i_e - cps[x].i_s + 1) / (double)L >= 0.95) used[x] = 1;   /* not a partial piece */
+    for (;;) {
+        int lead = -1;                                   /* leftmost unused partial piece, best rank on ties */
+        for (int x = 0; x < nl; ++x)
+            if (!used[x] && (lead < 0 || cps[x].i_s < cps[lead].i_s)) lead = x;
+        if (lead < 0) break;
+        used[lead] = 1;
+        int np = 0;
+        piece[np++] = lead;
+        while (np < CH_MAXPIECES) {
+            const int A = piece[np - 1];
+            int best = -1, best_cut = 0;
+            int64_t best_key = 0;
+            for (int y = 0; y < nl; ++y) {
+                if (used[y] || cps[y].rel != cps[A].rel) continue;
+                if (!(cps[y].i_s > cps[A].i_s && cps[y].i_e >= cps[A].i_e + CH_MINADD && cps[y].j_e > cps[A].j_e)) continue;
+                int cut = cps[A].i_e < cps[y].i_s - 1 ? cps[A].i_e : cps[y].i_s - 1;
+                /* the two local alignments may share a few genome bases around the junction: A gives them up */
+                for (int n = 0; n < CH_MAXTRIM && cut >= cps[A].i_s && piece_tpos(loci, qrecs, L, A, cut) >= cps[y].j_s; ++n) --cut;
+                if (cut < cps[A].i_s) continue;
+                const int64_t tA = piece_tpos(loci, qrecs, L, A, cut);
+                if (!(cps[y].j_s > tA)) continue;
+                const int64_t gq = cps[y].i_s - 1 - cut, gt = cps[y].j_s - tA - 1;
+                if (gq > CH_MAXGAP || gt > CH_MAXGAP) continue;
+                const int64_t key = ((gq > gt ? gq - gt : gt - gq) << 12) | (int64_t)y;
+                if (best < 0 || key < best_key) { best = y; best_key = key; best_cut = cut; }
+            }
+            if (best < 0) break;
+            cuts[np - 1] = best_cut;
+            used[best] = 1;
+            piece[np++] = best;
+        }
+        if (np == 1) continue;
+        int h = piece[0];
+        for (int t = 1; t < np; ++t) if (piece[t] < h) h = piece[t];     /* best rank = smallest locus index */
+        const int first = piece[0], last = piece[np - 1];
+        const int cs = cps[first].i_s, ce = cps[last].i_e;
+        const int64_t js = cps[first].j_s, je = cps[last].j_e;
+        int32_t score = 0;
+        for (int t = 0; t < np; ++t) {
+            const int x = piece[t];
+            const int from = cps[x].i_s, to = (t + 1 < np) ? cuts[t] : cps[x].i_e;
+            const int64_t delta = loci[x].j0 - loci[h].j0;
+            for (int p = from; p <= to; ++p) {
+                const uint32_t v = qrecs[(size_t)x * L + p];
+                tmp[p] = (v & 0xFFFF0000u) | (uint32_t)((int64_t)(v & 0xFFFFu) + delta);
+            }
+            score += cps[x].score;
+            if (t + 1 < np) {
+                const int y = piece[t + 1];
+                const int64_t tA = piece_tpos(loci, qrecs, L, x, to);
+                const int64_t gt = cps[y].j_s - tA - 1;
+                tmp[to] = (tmp[to] & ~(255u << 16)) | ((uint32_t)(gt > 255 ? 255 : gt) << 16);
+                for (int p = to + 1; p < cps[y].i_s; ++p)
+                    tmp[p] = (uint32_t)(tA - loci[h].j0 - p + 32768) | (1u << 24) | (1u << 25);
+            }
+        }
+        for (int p = 0; p < L; ++p) qrecs[(size_t)h * L + p] = (p >= cs && p <= ce) ? tmp[p] : 0;
+        for (int t = 0; t < np; ++t) {
+            const int x = piece[t];
+            if (x == h) continue;
+            cps[x].score = 0; cps[x].i_s = -1; cps[x].i_e = -1; cps[x].j_s = 0; cps[x].j_e = 0;
+        }
+        cps[h].score = score; cps[h].i_s = cs; cps[h].i_e = ce; cps[h].j_s = js; cps[h].j_e = je;
+    }
+    free(used); free(piece); free(cuts); free(tmp);
+}
+
 int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int k, int w,
                       const uint8_t *cand_ascii, int L, int occ_cap, int max_loci, int flank, int max_rows,
                       hbo_copy *copies, int *n_copies, uint8_t *matrix, uint64_t matrix_cap, int *R_out, int *C_out) {
@@ -391,6 +505,12 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
         hbo_align_pair(g, q, L, (int)loci[x].rel, loci[x].j0,
                        (loci[x].dmax - loci[x].dmin <= HB_NARROW_SPREAD) ? 16 : 32, &a, qrecs + (size_t)x * L);
         cp->score = a.score; cp->i_s = a.i_s; cp->i_e = a.i_e; cp->j_s = a.j_s; cp->j_e = a.j_e;
+    }
+    if (!getenv("HBO_NO_CHAIN")) chain_pieces(nl, loci, copies, qrecs, L);   /* S8b (the switch is a debugging aid) */
+    for (int x = 0; x < nl; ++x) {
+        hbo_copy *cp = &copies[x];
+        hbo_aln a;
+        a.score = cp->score; a.i_s = cp->i_s; a.i_e = cp->i_e; a.j_s = cp->j_s; a.j_e = cp->j_e;
         if (a.score <= 0) continue;
         const int aligned = a.i_e - a.i_s + 1;                         /* query_alignment_length (M+I) */
         const int64_t tlen = a.j_e - a.j_s + 1;                        /* sum(M+D)                      */

@@ -165,3 +165,44 @@ def test_scan_total_is_exact_beyond_32_bits(ctx):
     assert last == ((n - 1) * v) % (1 << 32)
     total, last = ctx.debug_scan_total(5000, 7)
     assert (total, last) == (35000, 4999 * 7)
+
+
+def test_chained_pieces_bit_exact(ctx):
+    """HB-align S5b / S8b: copies that differ from the candidate by a block indel longer than the band (20 - 300 bp) or whose
+    diagonal drifts (LTR-sized, 3 % indels) come back from the banded extension as several colinear pieces; they are chained
+    into one copy (what minimap2 reports as one alignment with a long I / D).  GPU == C port on every copy record, MSA row
+    and call; chains really occur and recover copies the single pieces would not."""
+    import os
+    wl = synth.make_mixed_workload(3_000_000, 2, 60, copies=("uniform", 8, 20), cands_per_family=6, seed=11,
+                                   lengths={"tir": (400, 2500)}, sub=(0.03, 0.03), indel=(0.002, 0.002), block=(1, 20, 120))
+    wl2 = synth.make_mixed_workload(3_000_000, 1, 12, mix=(("ltr", 1.0),), copies=("uniform", 6, 10), cands_per_family=4, seed=12,
+                                    sub=(0.02, 0.02), indel=(0.03, 0.03))
+    contigs = list(wl.contig_seqs) + list(wl2.contig_seqs)
+    names = list(wl.contig_names) + ["ltr1"]
+    cands = list(wl.cand_seqs) + list(wl2.cand_seqs)
+    G = oracle.Genome(contigs)
+    G.set_tie_rule(1, names)
+    ctx.load_genome(contigs, names)
+    ctx.build_index(15, 10)
+    res = ctx.adjust(cands, "tir", 1)
+    copies = ctx.last_copies()
+    n_kept = 0
+    for ci, seq in enumerate(cands):
+        cps, rows = G.candidate_msa(seq)
+        mine = copies[copies["cand"] == ci]
+        assert len(mine) == len(cps), ci
+        for a, b in zip(mine, cps):
+            for k in ("rank", "rel", "score", "i_s", "i_e", "j_s", "j_e", "keep"):
+                assert int(a[k]) == int(b[k]), (ci, k, int(a[k]), int(b[k]))
+        assert ctx.last_msa(ci) == rows, ci
+        n_kept += len(rows)
+        if rows:
+            exp = oracle.judge_with_trunc_gate(seq.decode(), cps, rows)
+            for k in ("is_te", "info", "cons", "copy_num"):
+                assert res[ci][k] == exp[k], (ci, k)
+    os.environ["HBO_NO_CHAIN"] = "1"                       # the port without S8b: fewer copies survive the coverage rules
+    try:
+        n_unchained = sum(len(G.candidate_msa(seq)[1]) for seq in cands)
+    finally:
+        del os.environ["HBO_NO_CHAIN"]
+    assert n_kept >= n_unchained + 30, (n_kept, n_unchained)

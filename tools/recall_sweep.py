@@ -5,7 +5,9 @@ and the genome through hb_coarse_boundary.  Reported per setting:
 
   cand_te      fraction of candidates judged a TE
   ends_ok      fraction whose emitted consensus starts and ends like the planted family consensus (<= 2 mismatches in 20 bp)
-  copy_recall  of the planted INTACT copies of a candidate's family, the fraction among the kept copies (>= 90 % reciprocal overlap)
+  copy_recall  of the planted INTACT copies of a candidate's family that the reference's own coverage rule admits (a copy
+               more than 1 / 0.95 times as long as the candidate fails (M+I)/(M+D) >= 0.95, module/Util.py:8013-8022, whatever the
+               aligner), the fraction among the kept copies (>= 90 % reciprocal overlap)
   coarse_fam   fraction of families with a coarse interval within 40 bp of a planted copy at both ends
 
 Writes a markdown table (stdout and --out).  Runs on the GPU box: python tools/recall_sweep.py --out gpurun_out/recall.md"""
@@ -62,6 +64,8 @@ def run_setting(ctx, name, **kw):
             for m in mine:
                 spans.setdefault(int(m["contig"]), []).append((int(m["start1"]) - 1, int(m["end1"])))
             for (c, a, b) in by_fam[t["family"]]:
+                if (b - a) * 0.95 > len(wl.cand_seqs[i]):
+                    continue
                 cr_den += 1
                 for (x, y) in spans.get(c, []):
                     ov = min(b, y) - max(a, x)
