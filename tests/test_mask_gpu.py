@@ -131,10 +131,12 @@ def test_coarse_stage_masks_known_TEs(tmp_path, monkeypatch):
             if c == names[t["contig"]] and min(b, t["end1"]) - max(a, t["start1"] - 1) > 0.5 * (t["end1"] - t["start1"]):
                 return True
         return False
+    # FMEA keeps a repeated segment once per result file (module/Util.py:4328-4390), not once per copy: count families
     full = [t for t in truth if t["kind"] == "full"]
-    known_hit0 = sum(covered(n0, t) for t in full if t["query"] < 6)
-    known_hit1 = sum(covered(n1, t) for t in full if t["query"] < 6)
-    novel_hit0 = sum(covered(n0, t) for t in full if t["query"] >= 6)
-    novel_hit1 = sum(covered(n1, t) for t in full if t["query"] >= 6)
-    assert known_hit0 >= 8 and known_hit1 == 0, (known_hit0, known_hit1)
-    assert novel_hit1 >= novel_hit0 - 1 and novel_hit1 > 10, (novel_hit0, novel_hit1)
+
+    def families(recs, lo, hi):
+        return {t["query"] for t in full if lo <= t["query"] < hi and covered(recs, t)}
+    known0, known1 = families(n0, 0, 6), families(n1, 0, 6)
+    novel0, novel1 = families(n0, 6, 12), families(n1, 6, 12)
+    assert len(known0) >= 5 and len(known1) == 0, (known0, known1)
+    assert len(novel1) >= len(novel0) - 1 and len(novel1) >= 3, (novel0, novel1)
