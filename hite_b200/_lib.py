@@ -48,6 +48,7 @@ QHSP_DTYPE = np.dtype([("query", "<u4"), ("contig", "<i4"), ("qs", "<i4"), ("qe"
                        ("n_match", "<i4"), ("aln_len", "<i4"), ("score", "<i4"), ("rank", "<i4")])
 assert QHSP_DTYPE.itemsize == 40
 POLYA_DTYPE = np.dtype([(f, "<i4") for f in ("found", "direct", "end_5", "end_3", "tsd_k", "seq_start", "seq_end")])
+ITR_DTYPE = np.dtype([(f, "<i4") for f in ("found", "len5", "len3", "score", "n_match", "n_mismatch", "n_gap")])
 TSD_DTYPE = np.dtype([("k", "<i4"), ("start", "<i4"), ("end", "<i4"), ("dist", "<i4"), ("idx", "<i4"), ("short_class", "<i4")])
 HSP_DTYPE = np.dtype([("subj", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("ss", "<i4"), ("se", "<i4")])
 SEG_DTYPE = np.dtype([("chr", "<i4"), ("pad", "<i4"), ("start", "<i8")])
@@ -215,6 +216,7 @@ def load():
     lib.hb_query_hsps.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(HbParams), u64p]
     lib.hb_last_query_hsps.argtypes = [vp, vp, C.c_uint64, u64p]
     lib.hb_nonltr_candidates.argtypes = [vp, C.c_uint32, vp, vp, C.c_int32, vp]
+    lib.hb_itr_search.argtypes = [vp, C.c_uint32, vp, vp, C.c_double, C.c_int32, C.c_int32, vp]
     lib.hb_tsd_candidates.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp]
     _LIB = lib
     return lib
@@ -487,6 +489,20 @@ class Context:
         flat = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
         self._check(self._lib.hb_nonltr_candidates(self._h, len(cb), _ptr(flat), _ptr(off), int(flanking_len), _ptr(out)),
                     "hb_nonltr_candidates")
+        return out
+
+    def itr_search(self, seqs, min_identity=0.7, min_len=7, max_window=500):
+        """``hb_itr_search``: HB-itr, the stand-in for the closed ``tools/itrsearch -i 0.7 -l 7`` (reference
+        module/Util.py:216-224) -> ITR_DTYPE [n] (found, len5, len3, score, n_match, n_mismatch, n_gap)."""
+        cb = [c if isinstance(c, (bytes, bytearray)) else c.encode("ascii") for c in seqs]
+        out = np.zeros(len(cb), dtype=ITR_DTYPE)
+        if not cb:
+            return out
+        off = np.zeros(len(cb) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(c) for c in cb])
+        flat = np.frombuffer(b"".join(cb) + b"\0", dtype=np.uint8)
+        self._check(self._lib.hb_itr_search(self._h, len(cb), _ptr(flat), _ptr(off), float(min_identity), int(min_len),
+                                            int(max_window), _ptr(out)), "hb_itr_search")
         return out
 
     def tsd_candidates(self, seqs, raw_starts, raw_ends, tsd_search_distance, plant):

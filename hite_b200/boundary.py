@@ -201,7 +201,8 @@ def _rescue_code(U):
 def _rescue_tools_missing(U, TE_type):
     need = ["trf", "blastx", "makeblastdb"]
     missing = [t for t in need if shutil.which(t) is None]
-    if TE_type == "tir" and not os.path.exists(os.path.join(U.cur_dir, "tools", "itrsearch")):
+    rebound = getattr(getattr(U, "run_itrsearch", None), "__module__", "").startswith("hite_b200")   # HB-itr stands in
+    if TE_type == "tir" and not rebound and not os.path.exists(os.path.join(U.cur_dir, "tools", "itrsearch")):
         missing.append("tools/itrsearch")
     return missing
 

@@ -167,6 +167,50 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
 // ------------------------------------------------------------------------------------------------
 // TSD-bounded variant generation (hb_tsd.cu)
 #include "hb_tsd.cuh"
+#include "hb_itr.cuh"
+extern "C" int hb_itr_search(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off, double min_identity,
+                             int32_t min_len, int32_t max_window, hb_itr_rec* out) {
+    if (!ctx || !seq_ascii || !seq_off || !out) return hb_fail_msg(ctx, HB_EINVAL, "hb_itr_search: null argument");
+    if (max_window < 1 || max_window > 1000 || min_len < 1) return hb_fail_msg(ctx, HB_EINVAL, "hb_itr_search: need 1 <= max_window <= 1000, min_len >= 1");
+    if (n == 0) return HB_OK;
+    std::vector<uint64_t> off(n + 1), soff(n + 1);
+    soff[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = seq_off[i + 1] - seq_off[i];
+        if (len >= (1u << 20)) return hb_fail_msg(ctx, HB_EINVAL, "hb_itr_search: record " + std::to_string(i) + " is 2^20 bytes or longer");
+        soff[i + 1] = soff[i] + 3 * (std::min<uint64_t>((uint64_t)max_window, len / 2) + 1);
+    }
+    for (uint32_t i = 0; i <= n; ++i) off[i] = seq_off[i] - seq_off[0];
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    const uint64_t bytes = seq_off[n] - seq_off[0];
+    HB_CUDA_OK(ctx->buf("i.seq").ensure(bytes + 16));
+    HB_CUDA_OK(ctx->buf("i.off").ensure(sizeof(uint64_t) * (n + 1)));
+    HB_CUDA_OK(ctx->buf("i.soff").ensure(sizeof(uint64_t) * (n + 1)));
+    HB_CUDA_OK(ctx->buf("i.scratch").ensure(sizeof(long long) * (soff[n] + 1)));
+    HB_CUDA_OK(ctx->buf("i.out").ensure(sizeof(hb_itr_rec) * (size_t)n));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("i.seq").p, seq_ascii + seq_off[0], bytes, cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("i.off").p, off.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaMemcpyAsync(ctx->buf("i.soff").p, soff.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    HB_CUDA_OK(hb_itr_launch(ctx->buf("i.seq").as<uint8_t>(), ctx->buf("i.off").as<uint64_t>(), n, min_identity, min_len, max_window,
+                             ctx->buf("i.scratch").as<long long>(), ctx->buf("i.soff").as<uint64_t>(), ctx->buf("i.out").as<hb_itr_rec>(), s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    HB_CUDA_OK(cudaMemcpyAsync(out, ctx->buf("i.out").p, sizeof(hb_itr_rec) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->timing.k_ms[0] = ctx->timing.kernel_ms;
+    ctx->timing.h2d_bytes = bytes + 16ull * (n + 1);
+    ctx->timing.d2h_bytes = sizeof(hb_itr_rec) * (uint64_t)n;
+    ctx->timing.launches = 1;
+    return HB_OK;
+}
+
 extern "C" int hb_tsd_candidates(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off,
                                  const int32_t* raw_start1, const int32_t* raw_end1, int32_t d, int32_t plant,
                                  hb_tsd_rec* out, uint32_t* n_out) {

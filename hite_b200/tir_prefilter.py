@@ -93,7 +93,49 @@ def filter_dup_itr_v3(cur_copies_out_contigs, TIR_len_dict):
     return {"%s-tir_%d-tsd_%s" % (query, TIR_len_dict.get(best_name, 0), tsd): seq}
 
 
+def run_itrsearch(TRsearch_dir, input, input_dir, ctx=None):
+    """Same signature, file names and output format as the reference's run_itrsearch (module/Util.py:216-224, which runs the
+    closed binary ``<TRsearch_dir>/itrsearch -i 0.7 -l 7 <input>``): writes ``<input>.itr`` -- one record per input record with
+    a terminal inverted repeat, header ``><name> ITR(1,a)..(L,b) Length itr=<a-1>``, sequence in 60-column lines -- and
+    ``<input>.log``; returns both paths.  The search itself is HB-itr on the GPU (``hb_itr_search``; parity with the binary is
+    unpinned, see hite_b200/csrc/hb_itr.cu).  ``HITE_B200_ITRSEARCH=binary`` runs the reference's binary instead."""
+    import os
+    os.makedirs(input_dir, exist_ok=True)
+    if os.environ.get("HITE_B200_ITRSEARCH", "").lower() == "binary":
+        return _run_itrsearch_binary(TRsearch_dir, input, input_dir)
+    names, seqs = [], []
+    if os.path.exists(input):
+        name = None
+        for line in open(input):                              # read_fasta_v1 semantics: the whole header line is the name
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                name = line[1:]
+                names.append(name); seqs.append([])
+            elif name is not None and line.strip():
+                seqs[-1].append(line.strip())
+    seqs = ["".join(x) for x in seqs]
+    keep = [i for i, s in enumerate(seqs) if s]
+    recs = (ctx or _ctx()).itr_search([seqs[i].upper() for i in keep]) if keep else []
+    with open(input + ".itr", "w") as out, open(input + ".log", "w") as log:
+        for k, i in enumerate(keep):
+            r, s, nm = recs[k], seqs[i], names[i].split()[0] if names[i].split() else names[i]
+            log.write("load sequence #%d %s\tlength=%d\n" % (k + 1, nm, len(s)))
+            if not int(r["found"]):
+                log.write("\n no alignment!\n\n")
+                continue
+            a, b = int(r["len5"]), len(s) - int(r["len3"]) + 1
+            log.write("\t(1,%d)..(%d,%d) Length itr=%d\n\tLength TE=%d\n\t\t==> saved !\n" % (a, b, len(s), a, len(s)))
+            out.write(">%s ITR(1,%d)..(%d,%d) Length itr=%d\n" % (nm, a, len(s), b, a - 1))
+            for o in range(0, len(s), 60):
+                out.write(s[o:o + 60] + "\n")
+    return input + ".itr", input + ".log"
+
+
 def _run_itrsearch(TRsearch_dir, input_path, work_dir):
+    return run_itrsearch(TRsearch_dir, input_path, work_dir)
+
+
+def _run_itrsearch_binary(TRsearch_dir, input_path, work_dir):
     """The reference's run_itrsearch (module/Util.py:216-224): the external ``itrsearch -i 0.7 -l 7`` of the HiTE tools
     directory (closed binary, not part of this repository) on a FASTA of 80 bp end pairs -> (<input>.itr, <input>.log)."""
     import os

@@ -313,6 +313,21 @@ typedef struct { int32_t found, direct, end_5, end_3, tsd_k, seq_start, seq_end;
 int hb_nonltr_candidates(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off, int32_t flanking_len,
                          hb_polya_rec* out);
 
+/*
+ * hb_itr_search -- HB-itr, the terminal-inverted-repeat matcher that stands in for the closed binary `tools/itrsearch`
+ * (run as `itrsearch -i 0.7 -l 7`, module/Util.py:216-224; callers search_confident_tir_batch_v1 :6563 / :6575 and
+ * remove_no_tirs :13907).  Per record: the 5' end against the reverse complement of the 3' end, both anchored at the
+ * record's ends, window min(max_window, len / 2) (the binary: 500), match +10, mismatch -16, gap of n bases -(32 + 32 n),
+ * optimum over all end cells; found = score - p > 0 (p = 64 / 32 / 0 for len5 == / > / < len3, the binary's "Quality" as
+ * fitted to its outputs) and m / (m + x) >= min_identity and len5 >= min_len.
+ * len5 / len3 = bases of the 5' / 3' arm (the binary's header reads `ITR(1,len5)..(L,L-len3+1) Length itr=len5-1`).
+ * The binary's own search is a heuristic below this optimum in places: parity unpinned; measured agreement in
+ * tests/golden/itrsearch.json.gz.  Records of < 2^20 bytes; any case; N never matches.
+ */
+typedef struct { int32_t found, len5, len3, score, n_match, n_mismatch, n_gap; } hb_itr_rec;
+int hb_itr_search(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off, double min_identity, int32_t min_len,
+                  int32_t max_window, hb_itr_rec* out);
+
 /* parity/debug getters: the sorted minimizer index (hash<<33 | pos<<1 | strand) and the raw
  * (pre-clean) MSA of one candidate of the last hb_adjust as ASCII */
 int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap);

@@ -11,6 +11,7 @@ reference's ``Util`` namespace with the B200 implementations:
     Util.is_TE_from_align_file   -> hite_b200.boundary.is_TE_from_align_file
     Util.determine_repeat_boundary_v5 -> hite_b200.coarse.determine_repeat_boundary_v5   (coarse_boundary.py)
     Util.multi_process_tsd_v1        -> hite_b200.tir_prefilter.multi_process_tsd_v1     (judge_TIR_transposons.py)
+    Util.run_itrsearch               -> hite_b200.tir_prefilter.run_itrsearch            (judge_TIR_transposons.py; HB-itr)
     Util.get_candidate_non_ltr_parallel -> hite_b200.nonltr_prefilter.*                  (judge_Non_LTR_transposons.py)
     Util.multi_process_align_and_get_copies -> hite_b200.other.*                         (judge_Other_transposons.py)
     Util.mask_genome_with_TE         -> hite_b200.masking.mask_genome_with_TE            (judge_LTR_transposons.py)

@@ -117,4 +117,8 @@ int hbo_search_polyA_TSD(const char *seq, int n, int flanking_len, hbo_polya_rec
 }
 #endif
 
+
+/* ---- HB-itr (hbo_tsd.c): checker of hb_itr_search; out[7] = found, len5, len3, score, n_match, n_mismatch, n_gap ---- */
+void hbo_itr_search(const char *s, int len, double min_ident, int min_len, int max_w, int32_t *out);
+
 #endif

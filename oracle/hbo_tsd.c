@@ -240,3 +240,60 @@ int hbo_search_polyA_TSD(const char *seq, int n, int flanking_len, hbo_polya_rec
     if (out->seq_end < out->seq_start) out->seq_end = out->seq_start;
     return found;
 }
+
+/* ---- HB-itr: checker of hb_itr_search (hite_b200/csrc/hb_itr.cu) -------------------------------------------------------
+   The reference runs the closed binary `tools/itrsearch -i 0.7 -l 7` (module/Util.py:216-224); its behaviour was probed as
+   a black box (tests/golden/make_golden_itr.py keeps what it returned): 5' end against the reverse complement of the 3' end,
+   anchored at the record's ends, window min(max_w, len / 2), match +10, mismatch -16, gap of n bases -(32 + 32 n), best end
+   cell; kept when score - p > 0 (p = 64 for arms of equal length, 32 for a longer 5' arm, 0 for a shorter one: the binary's
+   "Quality", fitted to its outputs), m / (m + x) >= min_ident and the 5' arm >= min_len.  This is the exact optimum
+   of that scoring, written the slow obvious way: three full tables of (score, m, x, g) tuples, compared as the kernel's
+   packed keys compare (score, then m, then x, then g), best cell = first maximum in row-major order.  PARITY UNPINNED with
+   respect to the binary (its own search is heuristic and not always optimal); agreement is measured in the golden file. */
+typedef struct { int ok; int sc, m, x, g; } itr_cell;
+static int itr_gt(const itr_cell *a, const itr_cell *b) {          /* a > b as packed keys; unreachable = smallest */
+    if (!a->ok) return 0;
+    if (!b->ok) return 1;
+    if (a->sc != b->sc) return a->sc > b->sc;
+    if (a->m != b->m) return a->m > b->m;
+    if (a->x != b->x) return a->x > b->x;
+    return a->g > b->g;
+}
+static itr_cell itr_max(itr_cell a, itr_cell b) { return itr_gt(&b, &a) ? b : a; }
+static itr_cell itr_add(itr_cell a, int dsc, int dm, int dx, int dg) {
+    if (a.ok) { a.sc += dsc; a.m += dm; a.x += dx; a.g += dg; }
+    return a;
+}
+static int itr_code(char c) {
+    switch (c & 0xDF) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 4; }
+}
+/* out[7] = found, len5, len3, score, n_match, n_mismatch, n_gap */
+void hbo_itr_search(const char *s, int len, double min_ident, int min_len, int max_w, int32_t *out) {
+    const int w = len / 2 < max_w ? len / 2 : max_w;
+    const size_t W = (size_t)w + 1;
+    itr_cell *D = (itr_cell *)calloc(W * W, sizeof(itr_cell)), *E = (itr_cell *)calloc(W * W, sizeof(itr_cell)),
+             *F = (itr_cell *)calloc(W * W, sizeof(itr_cell));
+    D[0].ok = 1;
+    itr_cell best = D[0];
+    int bi = 0, bj = 0;
+    for (int i = 0; i <= w; ++i)
+        for (int j = 0; j <= w; ++j) {
+            if (i == 0 && j == 0) continue;
+            const size_t c = (size_t)i * W + (size_t)j;
+            if (j > 0) E[c] = itr_max(itr_add(itr_max(D[c - 1], F[c - 1]), -64, 0, 0, 1), itr_add(E[c - 1], -32, 0, 0, 1));
+            if (i > 0) F[c] = itr_max(itr_add(itr_max(D[c - W], E[c - W]), -64, 0, 0, 1), itr_add(F[c - W], -32, 0, 0, 1));
+            if (i > 0 && j > 0) {
+                const int ca = itr_code(s[i - 1]), cb = itr_code(s[len - j]);
+                const int m = ca < 4 && cb < 4 && ca == 3 - cb;
+                D[c] = itr_add(itr_max(itr_max(D[c - W - 1], E[c - W - 1]), F[c - W - 1]), m ? 10 : -16, m, !m, 0);
+            }
+            if (i > 0 && j > 0) {                                   /* row 0 / column 0 never beat the origin */
+                const itr_cell cm = itr_max(itr_max(D[c], E[c]), F[c]);
+                if (itr_gt(&cm, &best)) { best = cm; bi = i; bj = j; }
+            }
+        }
+    out[1] = bi; out[2] = bj; out[3] = best.sc; out[4] = best.m; out[5] = best.x; out[6] = best.g;
+    out[0] = (best.sc - (bi == bj ? 64 : (bi > bj ? 32 : 0)) > 0) && (best.m + best.x > 0) &&
+             ((double)best.m / (double)(best.m + best.x) >= min_ident) && bi >= min_len;
+    free(D); free(E); free(F);
+}

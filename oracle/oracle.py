@@ -421,3 +421,15 @@ class Genome:
         if state is not None:
             state.close()
         return recs, segs, intervals
+
+
+def itr_search(seq, min_ident=0.7, min_len=7, max_w=500):
+    """HB-itr (hbo_tsd.c::hbo_itr_search) -> dict(found, len5, len3, score, n_match, n_mismatch, n_gap)."""
+    import numpy as np
+    L = lib()
+    L.hbo_itr_search.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    L.hbo_itr_search.restype = None
+    b = seq.encode() if isinstance(seq, str) else bytes(seq)
+    out = np.zeros(7, dtype=np.int32)
+    L.hbo_itr_search(b, len(b), float(min_ident), int(min_len), int(max_w), out.ctypes.data)
+    return dict(zip(("found", "len5", "len3", "score", "n_match", "n_mismatch", "n_gap"), (int(x) for x in out)))

@@ -41,8 +41,9 @@ out.close()
 '''
 
 
-def test_tir_stage_prefilter_equals_the_reference_up_to_its_own_tie_order(tmp_path):
+def test_tir_stage_prefilter_equals_the_reference_up_to_its_own_tie_order(tmp_path, monkeypatch):
     from hite_b200 import _lib, tir_prefilter as TP
+    monkeypatch.setenv("HITE_B200_ITRSEARCH", "binary")         # both sides run the same (stand-in) itrsearch binary here
     U = ref_import.load_util()
     rng = np.random.default_rng(3)
     comp = str.maketrans("ACGT", "TGCA")

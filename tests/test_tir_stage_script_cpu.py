@@ -59,6 +59,13 @@ def test_tir_stage_script_end_to_end(tmp_path, monkeypatch):
                         out[i][j][f] = x[f]
             return out, cnt
 
+        def itr_search(self, seqs, min_identity=0.7, min_len=7, max_window=500):     # HB-itr, from its CPU restatement
+            out = np.zeros(len(seqs), dtype=_lib.ITR_DTYPE)
+            for i, s in enumerate(seqs):
+                for f, v in O.itr_search(s, min_identity, min_len, max_window).items():
+                    out[i][f] = v
+            return out
+
         def adjust(self, seqs, te, plant, result_type, flank=50):
             res = []
             for s in seqs:
@@ -75,8 +82,7 @@ def test_tir_stage_script_end_to_end(tmp_path, monkeypatch):
         p = bindir / tool
         p.write_text(body % sys.executable)
         p.chmod(p.stat().st_mode | stat.S_IEXEC)
-    real_run = tir_prefilter._run_itrsearch
-    monkeypatch.setattr(tir_prefilter, "_run_itrsearch", lambda d, path, work: real_run(str(bindir), path, work))   # $HITE_HOME/tools is read-only here
+    monkeypatch.setattr(tir_prefilter, "_ctx", lambda: ctx)      # run_itrsearch (HB-itr) asks for the stage's context
     monkeypatch.setenv("PATH", str(bindir) + os.pathsep + os.environ["PATH"])
     monkeypatch.setenv("HITE_HOME", ref_import.REF_ROOT)
     monkeypatch.setenv("HITE_GPU_DEVICES", "0")
@@ -92,9 +98,11 @@ def test_tir_stage_script_end_to_end(tmp_path, monkeypatch):
                                       "--recover", "0", "--debug", "0", "-r", ref, "--split_ref_dir", str(tmp_path / "ref_chr"),
                                       "--prev_TE", prev_te, "--all_low_copy_tir", low, "--min_TE_len", "80", "-w", str(work)])
     import Util
-    saved = {n: getattr(Util, n) for n in ("flank_region_align_v5", "run_find_members_v8", "is_TE_from_align_file", "multi_process_tsd_v1")}
+    saved = {n: getattr(Util, n) for n in ("flank_region_align_v5", "run_find_members_v8", "is_TE_from_align_file", "multi_process_tsd_v1",
+                                            "run_itrsearch")}
     try:
-        patch.run_stage("judge_TIR_transposons.py", extra=(("multi_process_tsd_v1", "hite_b200.tir_prefilter"),))
+        patch.run_stage("judge_TIR_transposons.py", extra=(("multi_process_tsd_v1", "hite_b200.tir_prefilter"),
+                                                           ("run_itrsearch", "hite_b200.tir_prefilter")))
     finally:
         for n, f in saved.items():
             setattr(Util, n, f)
