@@ -34,7 +34,7 @@ assert CALL_DTYPE.itemsize == C.sizeof(HbCall)
 class HbParams(C.Structure):
     _fields_ = [("occ_cap", C.c_int32), ("max_loci", C.c_int32), ("flank", C.c_int32), ("max_rows", C.c_int32),
                 ("te_type", C.c_int32), ("plant", C.c_int32), ("result_type", C.c_int32), ("trunc_gate", C.c_int32),
-                ("tb_budget_bytes", C.c_uint64), ("overlap", C.c_int32), ("reserved", C.c_int32)]
+                ("tb_budget_bytes", C.c_uint64), ("overlap", C.c_int32), ("flags", C.c_int32)]
 
 
 COPY_DTYPE = np.dtype([("cand", "<u4"), ("rank", "<i4"), ("rel", "<i4"), ("nseeds", "<i4"), ("score", "<i4"),
@@ -199,6 +199,7 @@ def load():
     lib.hb_debug_index.argtypes = [vp, vp, C.c_uint64]
     lib.hb_debug_scan_total.argtypes = [vp, C.c_uint64, C.c_uint32, u64p, C.POINTER(C.c_uint32)]
     lib.hb_last_msa.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
+    lib.hb_last_msa_trunc.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
     lib.hb_fmea_chain.argtypes = [vp, vp, C.c_uint32, vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
     lib.hb_query_copies.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, vp,
                                     C.c_uint32, C.POINTER(C.c_uint32)]
@@ -364,7 +365,7 @@ class Context:
         return keys[:n]
 
     def adjust_raw(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=300, flank=50,
-                   max_rows=100, tb_budget_bytes=0, trunc_gate=True, overlap=None):
+                   max_rows=100, tb_budget_bytes=0, trunc_gate=True, overlap=None, rows_first=False, no_judge=False):
         """One ``flank_region_align_v5``-equivalent round (kernels ii + iii) over the candidates.
         Returns ``(calls, cons)``: a structured array (CALL_DTYPE, one record per candidate) and the
         consensus bytes; candidate i's consensus is ``cons[calls['cons_off'][i] : +calls['cons_len'][i]]``.
@@ -385,7 +386,7 @@ class Context:
             return calls, np.zeros(0, dtype=np.uint8)
         prm = HbParams(occ_cap, max_loci, flank, max_rows, TE_TYPES[te_type], int(plant),
                        1 if result_type == "cons" else 0, 1 if trunc_gate else 0, int(tb_budget_bytes),
-                       int(overlap) if overlap is not None else 0, 0)
+                       int(overlap) if overlap is not None else 0, (1 if rows_first else 0) | (2 if no_judge else 0))
         nbytes = C.c_uint64(0)
         self._check(self._lib.hb_adjust(self._h, n, _ptr(flat), _ptr(off), C.byref(prm), _ptr(calls), C.byref(nbytes)),
                     "hb_adjust")
@@ -420,13 +421,15 @@ class Context:
         self._check(self._lib.hb_last_copies(self._h, _ptr(arr), len(arr), C.byref(n)), "hb_last_copies")
         return arr[:n.value]
 
-    def last_msa(self, cand):
+    def last_msa(self, cand, trunc=False):
+        """Rows of candidate ``cand``'s star MSA from the last adjust (``trunc``: its truncated-member matrix)."""
+        fn = self._lib.hb_last_msa_trunc if trunc else self._lib.hb_last_msa
         R, Cn = C.c_int32(0), C.c_int32(0)
-        self._check(self._lib.hb_last_msa(self._h, cand, None, 0, C.byref(R), C.byref(Cn)), "hb_last_msa")
+        self._check(fn(self._h, cand, None, 0, C.byref(R), C.byref(Cn)), "hb_last_msa")
         if R.value == 0:
             return []
         buf = np.zeros(R.value * Cn.value, dtype=np.uint8)
-        self._check(self._lib.hb_last_msa(self._h, cand, _ptr(buf), len(buf), C.byref(R), C.byref(Cn)), "hb_last_msa")
+        self._check(fn(self._h, cand, _ptr(buf), len(buf), C.byref(R), C.byref(Cn)), "hb_last_msa")
         raw = buf.tobytes()
         return [raw[r * Cn.value:(r + 1) * Cn.value].decode() for r in range(R.value)]
 

@@ -56,8 +56,8 @@ struct HbLane {
     uint64_t cons_bytes = 0;
     uint32_t n_pairs = 0;
     uint64_t ext_steps = 0;
-    std::vector<uint64_t> mat_off;
-    std::vector<uint32_t> rows, cols;
+    std::vector<uint64_t> mat_off, tmat_off;
+    std::vector<uint32_t> rows, cols, trows;
 };
 
 struct hb_ctx {
@@ -89,7 +89,8 @@ struct hb_ctx {
     HbHostBuf h_cons;              // pinned copy of the dense consensus bytes of the last hb_adjust
     uint64_t last_cons_bytes = 0;
     uint32_t last_ncand = 0, last_npairs = 0;
-    std::vector<uint64_t> last_mat_off;
+    std::vector<uint64_t> last_mat_off, last_tmat_off;
+    std::vector<uint32_t> last_trows;
     std::vector<hb_hsp> last_hsps;            // last hb_coarse_boundary: HSPs grouped by query segment
     std::vector<uint64_t> last_hsp_off;
     std::vector<hb_segment> last_segs;

@@ -263,7 +263,7 @@ chain_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pai
 constexpr int SEL_MAX = 512;
 __global__ void __launch_bounds__(128)
 copy_select_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, uint32_t n_cand,
-                   int max_rows, int trunc_gate, const int32_t* __restrict__ crank, HbAln* __restrict__ alns,
+                   int max_rows, int trunc_gate, int rows_first, const int32_t* __restrict__ crank, HbAln* __restrict__ alns,
                    uint32_t* __restrict__ n_rows, uint32_t* __restrict__ n_trows) {
     __shared__ uint8_t s_keep[4][SEL_MAX];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,7 +289,17 @@ copy_select_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict
     for (int x = lane; x < n; x += 32) nk += keep[x];
 #pragma unroll
     for (int o = 16; o; o >>= 1) nk += __shfl_xor_sync(HB_FULL, nk, o);
-    if (nk > max_rows) {
+    if (nk > max_rows && rows_first) {                    // FiLTR's extract_copies: the first max_rows members of the file
+        for (int x = lane; x < n; x += 32) {
+            if (!keep[x]) continue;
+            int before = 0;
+            for (int y = 0; y < x; ++y) before += keep[y] ? 1 : 0;
+            if (before >= max_rows) keep[x] = 2;
+        }
+        __syncwarp();
+        for (int x = lane; x < n; x += 32) if (keep[x] == 2) keep[x] = 0;
+        __syncwarp();
+    } else if (nk > max_rows) {
         for (int x = lane; x < n; x += 32) {
             if (!keep[x]) continue;
             // the 100 longest, length ties to the bytewise larger member name (sort -nk 2 -r, tools/ready_for_MSA.sh:63)
@@ -484,11 +494,11 @@ cudaError_t hb_chain_launch(const HbLocus* pairs, const uint32_t* pair_off, uint
     return cudaGetLastError();
 }
 cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, int max_rows,
-                                  int trunc_gate, const int32_t* crank, HbAln* alns, uint32_t* n_rows, uint32_t* n_trows,
-                                  cudaStream_t s) {
+                                  int trunc_gate, int rows_first, const int32_t* crank, HbAln* alns, uint32_t* n_rows,
+                                  uint32_t* n_trows, cudaStream_t s) {
     if (n_cand == 0) return cudaSuccess;
-    copy_select_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, max_rows, trunc_gate, crank, alns, n_rows,
-                                                        n_trows);
+    copy_select_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, max_rows, trunc_gate, rows_first, crank, alns,
+                                                        n_rows, n_trows);
     return cudaGetLastError();
 }
 cudaError_t hb_ins_max_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,

@@ -10,8 +10,8 @@ cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const 
 cudaError_t hb_chain_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, const uint32_t* clen,
                             const uint32_t* qrec_unit_off, uint32_t* qrec, HbAln* alns, cudaStream_t s);
 cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off, uint32_t n_cand, int max_rows,
-                                  int trunc_gate, const int32_t* crank, HbAln* alns, uint32_t* n_rows, uint32_t* n_trows,
-                                  cudaStream_t s);
+                                  int trunc_gate, int rows_first, const int32_t* crank, HbAln* alns, uint32_t* n_rows,
+                                  uint32_t* n_trows, cudaStream_t s);
 cudaError_t hb_ins_max_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* alns, const uint32_t* qrec_unit_off,
                               const uint32_t* qrec, const uint64_t* coff, uint32_t* ins, cudaStream_t s);
 cudaError_t hb_layout_launch(const uint64_t* coff, const uint32_t* clen, uint32_t n_cand, int flank, uint32_t* ins,

@@ -519,7 +519,8 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
     HB_CUDA_OK(hb_copy_filter_launch(LB("p.pairs").as<HbLocus>(), n_pairs, d_clen, ctx->buf("g.goff").as<uint64_t>(),
                                      ctx->buf("g.glen").as<uint64_t>(), ctx->g_ncontig, tot, flank, LB("p.alns").as<HbAln>(), s));
     HB_CUDA_OK(hb_copy_select_launch(LB("p.pairs").as<HbLocus>(), LB("s.pair_off").as<uint32_t>(), n_cand,
-                                     prm->max_rows, trunc_gate, ctx->buf("g.crank").as<int32_t>(), LB("p.alns").as<HbAln>(),
+                                     prm->max_rows, trunc_gate, (prm->flags & HB_PRM_ROWS_FIRST) ? 1 : 0,
+                                     ctx->buf("g.crank").as<int32_t>(), LB("p.alns").as<HbAln>(),
                                      LB("m.n_rows").as<uint32_t>(), LB("m.n_trows").as<uint32_t>(), s));
     HB_CUDA_OK(hb_ins_max_launch(LB("p.pairs").as<HbLocus>(), n_pairs, LB("p.alns").as<HbAln>(),
                                  LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(), d_coff,
@@ -604,6 +605,32 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
     }
     HB_CUDA_OK(cudaEventRecord(ln.ev[4], s));
     mark("copy rules + msa");
+    ln.tmat_off = h_tmat_off; ln.trows = h_trows;
+    if (prm->flags & HB_PRM_NO_JUDGE) {
+        // the FiLTR fork of the loop stops at the alignment (bin/FiLTR-main/src/Util.py:1315-1339): the matrices stay on the
+        // device for hb_last_msa / hb_last_msa_trunc, the copy records for hb_last_copies
+        HB_CUDA_OK(cudaStreamSynchronize(s));
+        for (uint32_t c = 0; c < n_cand; ++c) {
+            hb_call& o = calls[c];
+            memset(&o, 0, sizeof(o));
+            o.align_start = o.align_end = o.homo_start = o.homo_end = -1;
+            o.copy_num = (int32_t)h_rows[c];
+            o.flags = h_rows[c] ? 0 : HB_FLAG_NO_COPIES;
+        }
+        if (cons_bytes) *cons_bytes = 0;
+        ln.cons_bytes = 0;
+        ln.n_pairs = n_pairs; ln.ext_steps = ext_steps;
+        ln.mat_off = h_mat_off; ln.rows = h_rows; ln.cols = h_cols;
+        cudaEventElapsedTime(&tm.k_ms[0], ln.ev[0], ln.ev[1]);
+        cudaEventElapsedTime(&tm.k_ms[1], ln.ev[1], ln.ev[2]);
+        cudaEventElapsedTime(&tm.k_ms[2], ln.ev[2], ln.ev[3]);
+        cudaEventElapsedTime(&tm.k_ms[3], ln.ev[3], ln.ev[4]);
+        cudaEventElapsedTime(&tm.kernel_ms, ln.ev[0], ln.ev[4]);
+        tm.launches = launches;
+        tm.k_ms[6] = (float)n_pairs;
+        tm.k_ms[7] = (float)((double)ext_steps * 1e-6);
+        return HB_OK;
+    }
 
     // ---- kernel (iii): clean + judge ---------------------------------------------------------------
     std::vector<HbVoteCall> h_calls(n_tasks);
@@ -724,6 +751,7 @@ extern "C" int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii
         ctx->cons_parts.push_back({(const uint8_t*)ctx->part_cons[0].p, nb});
         ctx->last_ncand = n_cand; ctx->last_npairs = ln.n_pairs;
         ctx->last_mat_off = ln.mat_off; ctx->last_rows = ln.rows; ctx->last_cols = ln.cols;
+        ctx->last_tmat_off = ln.tmat_off; ctx->last_trows = ln.trows;
         if (cons_bytes) *cons_bytes = nb;
         return HB_OK;
     }
@@ -891,6 +919,21 @@ extern "C" int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t*
         o.contig = al[i].contig; o.j0 = pr[i].j0; o.j_s = al[i].j_s; o.j_e = al[i].j_e;
         o.start1 = al[i].start1; o.end1 = al[i].end1; o.ext_len = al[i].ext_len; o.trow = al[i].trow;
     }
+    return HB_OK;
+}
+
+extern "C" int hb_last_msa_trunc(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii, uint64_t cap, int32_t* R, int32_t* C) {
+    if (!ctx || !R || !C) return HB_EINVAL;
+    if (ctx->last_overlapped) return hb_fail_msg(ctx, HB_ESTATE, "hb_last_msa_trunc: needs a serial hb_adjust (hb_params.overlap < 2)");
+    if (cand >= ctx->last_ncand || cand >= ctx->last_trows.size()) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_msa_trunc: candidate out of range");
+    *R = ctx->last_rows[cand] ? (int32_t)ctx->last_trows[cand] : 0; *C = (int32_t)ctx->last_cols[cand];
+    const uint64_t bytes = (uint64_t)*R * (uint64_t)*C;
+    if (!out_ascii || bytes == 0) return HB_OK;
+    if (cap < bytes) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_msa_trunc: buffer too small");
+    cudaSetDevice(ctx->device);
+    HB_CUDA_OK(cudaMemcpyAsync(out_ascii, ctx->buf("m.mat").as<uint8_t>() + ctx->last_tmat_off[cand], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < bytes; ++i) out_ascii[i] = (uint8_t)hb_ascii_of_sym(out_ascii[i]);
     return HB_OK;
 }
 

@@ -89,6 +89,11 @@ int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_ascii, const u
                      const uint64_t* cand_off, int te_type, int plant, int result_type,
                      hb_call* calls, uint8_t* cons_out, uint64_t cons_cap);
 
+/* hb_params.flags: the FiLTR fork of the loop (bin/FiLTR-main/src/Util.py:956-1043, :1315-1339) keeps the FIRST 100 members of a
+ * file (extract_copies :1306) instead of the 100 longest and stops at the alignment -- its own get_both_ends_frame reads it */
+#define HB_PRM_ROWS_FIRST 1 /* S9: the first max_rows kept copies in rank order, not the longest */
+#define HB_PRM_NO_JUDGE 2   /* stop after the star MSA: hb_last_copies / hb_last_msa / hb_last_msa_trunc hold the result */
+
 /* hb_call.flags */
 #define HB_FLAG_NO_COPIES 1 /* no full-length copy survived: the reference writes no member file for such a
                                query (module/Util.py:8125-8137) and it silently drops out of the result */
@@ -138,7 +143,7 @@ typedef struct {
     uint64_t tb_budget_bytes; /* HBM budget of the traceback stream, 0 = 16 GiB */
     int32_t overlap;      /* 0 / 1 = one batch on the context's stream; N >= 2 = N sub-batches (contiguous candidate
                            * ranges) software-pipelined over two CUDA streams: same results, stages overlap */
-    int32_t reserved;
+    int32_t flags;        /* HB_PRM_* bits, 0 for the boundary-adjustment path */
 } hb_params;
 
 /* One candidate x locus pair: what get_copies_minimap2 (module/Util.py:7977-8030) returns per SAM
@@ -332,6 +337,9 @@ int hb_itr_search(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint6
  * (pre-clean) MSA of one candidate of the last hb_adjust as ASCII */
 int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap);
 int hb_last_msa(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii, uint64_t cap, int32_t* R, int32_t* C);
+/* the truncated-member matrix of the candidate (rows = kept copies longer than 1000 bp, cells outside each row's first and
+ * last 500 bases blanked; module/Util.py:8116-8124): what the reference aligns first when copies are long.  R = 0 if none. */
+int hb_last_msa_trunc(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii, uint64_t cap, int32_t* R, int32_t* C);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,8 @@ reference's ``Util`` namespace with the B200 implementations:
     Util.get_candidate_non_ltr_parallel -> hite_b200.nonltr_prefilter.*                  (judge_Non_LTR_transposons.py)
     Util.multi_process_align_and_get_copies -> hite_b200.other.*                         (judge_Other_transposons.py)
     Util.mask_genome_with_TE         -> hite_b200.masking.mask_genome_with_TE            (judge_LTR_transposons.py)
+    Util.run_FiLTR                   -> hite_b200.filtr.run_FiLTR  (judge_LTR_transposons.py; FiLTR's own Util gets
+                                        generate_both_ends_frame_from_seq_minimap2 rebound through module/filtr_hook)
 
 Everything else on the stage (TSD pre-filter, cd-hit-est, renaming, prev_TE bookkeeping) stays the
 reference's code.  ``HITE_HOME`` must point at the HiTE checkout.  There is no CPU fallback: if the

@@ -34,7 +34,8 @@ struct hbo_genome {
     uint64_t *goff;    /* n_contig global offsets */
     uint64_t *glen;
     int32_t *crank;    /* rank of every contig by (name + ':') bytewise, or NULL: see hbo_genome_set_tie_rule */
-    int tie_rule;      /* S9 tie rule: 1 = ready_for_MSA.sh's (default, what the kernels do), 0 = earlier-ranked copy */
+    int tie_rule;      /* S9: 1 = 100 longest, ties by ready_for_MSA.sh's name order (default), 0 = ties to the earlier-ranked copy,
+                          2 = the FIRST max_rows copies (FiLTR's extract_copies, HB_PRM_ROWS_FIRST) */
 };
 
 static inline uint8_t code_of(uint8_t c) {
@@ -538,6 +539,7 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
             int longer = 0;
             for (int y = 0; y < nl; ++y) {
                 if (y == x || !copies[y].keep) continue;
+                if (g->tie_rule == 2) { longer += y < x; continue; }      /* FiLTR's extract_copies: the first max_rows of the file */
                 const int first = g->tie_rule ? name_greater(g, &copies[y], &copies[x]) : (y < x);
                 if (copies[y].ext_len > copies[x].ext_len || (copies[y].ext_len == copies[x].ext_len && first)) ++longer;
             }

@@ -206,3 +206,30 @@ def test_chained_pieces_bit_exact(ctx):
     finally:
         del os.environ["HBO_NO_CHAIN"]
     assert n_kept >= n_unchained + 30, (n_kept, n_unchained)
+
+
+def test_filtr_mode_first_100_rows_no_judge_and_truncated_matrix(ctx):
+    """HB_PRM_ROWS_FIRST | HB_PRM_NO_JUDGE (the FiLTR fork of the loop, bin/FiLTR-main/src/Util.py:956-1043, :1306, :1315-1339):
+    flank 100, the FIRST 100 kept copies, no judge; full and truncated-member matrices == the C port's."""
+    wl = synth.make_workload(genome_bp=3_000_000, n_contigs=2, n_families=3, cands_per_family=2, copies=(120, 150),
+                             length=(300, 700), seed=41, indel=0.002)
+    wl2 = synth.make_workload(genome_bp=1_500_000, n_contigs=1, n_families=3, cands_per_family=2, copies=(6, 12),
+                              length=(1500, 4000), seed=42, indel=0.003, sub=(0.0, 0.04))
+    contigs = list(wl.contig_seqs) + list(wl2.contig_seqs)
+    cands = list(wl.cand_seqs) + list(wl2.cand_seqs)
+    G = oracle.Genome(contigs)
+    G.set_tie_rule(2)
+    ctx.load_genome(contigs)
+    ctx.build_index(15, 10)
+    calls, cons = ctx.adjust_raw(cands, "tir", 1, flank=100, rows_first=True, no_judge=True)
+    assert len(cons) == 0
+    n_cut = n_trunc = 0
+    for ci, seq in enumerate(cands):
+        cps, rows = G.candidate_msa(seq, flank=100)
+        assert ctx.last_msa(ci) == rows, ci
+        assert int(calls["copy_num"][ci]) == len(rows)
+        t = oracle.truncated_rows(cps, rows)
+        assert ctx.last_msa(ci, trunc=True) == t, ci
+        n_cut += len(rows) == 100
+        n_trunc += len(t) > 0
+    assert n_cut >= 3 and n_trunc >= 3
