@@ -56,6 +56,9 @@ struct HbLane {
     uint64_t cons_bytes = 0;
     uint32_t n_pairs = 0;
     uint64_t ext_steps = 0;
+    bool raw_valid = false, raw_has_trunc = false;   // raw matrices of the last batch: materialised on demand (hb_last_msa)
+    uint64_t raw_bytes = 0;
+    int raw_flank = 50;
     std::vector<uint64_t> mat_off, tmat_off;
     std::vector<uint32_t> rows, cols, trows;
 };

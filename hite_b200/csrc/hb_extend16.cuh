@@ -22,7 +22,7 @@ namespace hb16 {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int HB16_MAX_L = HB_EXTEND16_MAX_L;       // 2 * L + 4 + 6 < 32768
-constexpr int NARROW_SPREAD = 8;         // HB-align S7
+constexpr int NARROW_SPREAD = 12;        // HB-align S7 (5 %-trimmed diagonal spread of the cluster, band centred on its median)
 
 // ---- packed signed-16x2 primitives (device: one SASS instruction each; host: plain C) ------------
 #ifndef __CUDA_ARCH__

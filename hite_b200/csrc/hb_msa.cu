@@ -478,6 +478,120 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
     }
 }
 
+// S10d + sparse-column removal fused (msa_write_kernel followed by hb_vote.cu::hb_clean_kernel, without the raw matrix ever
+// reaching HBM): one CTA per judge task (a candidate's full matrix, or its truncated-member matrix).  The matrix is produced
+// 128 columns at a time in shared memory -- a warp per row derives the row's symbols from the column map and the pair's
+// edit records exactly like msa_write_kernel -- then every column of the tile is counted, kept or dropped by the
+// reference's rule (remove_sparse_col_in_align_file, module/Util.py:10379-10391: first and last column always kept, a
+// column goes when gaps > rows / 2) and the kept columns are appended to the clean matrix (row stride C, symbol codes).
+constexpr int MC_TILE = 128, MC_THREADS = 256, MC_MAXROWS = 104;
+__global__ void __launch_bounds__(MC_THREADS)
+msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restrict__ task_cand, uint32_t n_full,
+                 const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, const HbAln* __restrict__ alns,
+                 const uint32_t* __restrict__ qrec_unit_off, const uint32_t* __restrict__ qrec,
+                 const uint32_t* __restrict__ col_off, const uint32_t* __restrict__ colq, const uint32_t* __restrict__ gseq2,
+                 const uint32_t* __restrict__ gnmask, uint64_t tot, int flank, uint8_t* __restrict__ clean,
+                 HbVoteCall* __restrict__ calls) {
+    __shared__ __align__(16) uint8_t s_tile[MC_MAXROWS][MC_TILE];
+    __shared__ uint32_t s_pair[MC_MAXROWS];
+    __shared__ int s_warp[MC_TILE / 32];
+    __shared__ int s_base;
+    const uint32_t ti = blockIdx.x;
+    const HbVoteTask t = tasks[ti];
+    const int trunc = ti >= n_full ? 1 : 0;
+    const uint32_t c = task_cand[ti];
+    const int R = t.R, C = t.C;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t p0 = pair_off[c], p1 = pair_off[c + 1];
+    for (uint32_t p = p0 + tid; p < p1; p += MC_THREADS) {
+        const int r = trunc ? alns[p].trow : alns[p].row;
+        if (r >= 0 && r < MC_MAXROWS) s_pair[r] = p;
+    }
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const uint32_t* cq = colq + col_off[c];
+    uint8_t* out = clean + t.clean_off;
+    const uint32_t totm1 = (uint32_t)(tot - 1);
+    for (int c0 = 0; c0 < C; c0 += MC_TILE) {
+        // ---- the tile's symbols: warp per row, 4 columns per lane ----
+        for (int r = wid; r < R; r += MC_THREADS / 32) {
+            const uint32_t p = s_pair[r];
+            const HbAln a = alns[p];
+            const HbLocus pr = pairs[p];
+            const int rel = (int)pr.rel;
+            const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
+            const uint32_t j0 = (uint32_t)pr.j0, js = (uint32_t)a.j_s, je = (uint32_t)a.j_e;
+            const int i_s = a.i_s, i_e = a.i_e;
+            const uint32_t ext_lo = js - (uint32_t)flank, ext_len = je - js + 2u * (uint32_t)flank + 1u;
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = c0 + 4 * lane + k;
+                uint32_t sym = HB_SYM_GAP;
+                if (col < C) {
+                    const uint32_t e = cq[col];
+                    const int q = (int)(e >> 8) - flank;
+                    const uint32_t slot = e & 255u;
+                    uint32_t j = 0;
+                    bool have = true;
+                    if (q >= i_s && q <= i_e) {
+                        const uint32_t v = qr[q];
+                        if (slot == 0 ? ((v >> 24) & 1u) != 0 : slot > ((v >> 16) & 255u)) have = false;
+                        j = j0 + (uint32_t)q + (v & 0xFFFFu) - 32768u + slot;
+                    } else {
+                        if (slot != 0) have = false;
+                        else if (q < i_s) { if (q < i_s - flank) have = false; j = js - (uint32_t)(i_s - q); }
+                        else { if (q > i_e + flank) have = false; j = je + (uint32_t)(q - i_e); }
+                    }
+                    if (have && trunc) {
+                        const uint32_t d = j - ext_lo;
+                        if (d >= 500u && ext_len - 1u - d >= 500u) have = false;
+                    }
+                    if (have) {
+                        const uint32_t pos = rel ? totm1 - j : j;
+                        if ((gnmask[pos >> 5] >> (pos & 31u)) & 1u) sym = HB_SYM_N;
+                        else {
+                            const uint32_t b2 = (gseq2[pos >> 4] >> (2u * (pos & 15u))) & 3u;
+                            sym = rel ? 3u - b2 : b2;
+                        }
+                    }
+                }
+                w |= sym << (8 * k);
+            }
+            *reinterpret_cast<uint32_t*>(&s_tile[r][4 * lane]) = w;
+        }
+        __syncthreads();
+        // ---- sparse columns: thread per column of the tile ----
+        int keep = 0, pos = 0;
+        if (tid < MC_TILE) {
+            const int col = c0 + tid;
+            if (col < C) {
+                int gaps = 0;
+                for (int r = 0; r < R; ++r) gaps += s_tile[r][tid] == HB_SYM_GAP;
+                keep = (col == 0) || (col == C - 1) || !(2 * gaps > R);
+            }
+            const uint32_t bal = __ballot_sync(HB_FULL, keep);
+            if (lane == 0) s_warp[wid] = __popc(bal);
+            pos = __popc(bal & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        const int base = s_base;
+        if (tid < MC_TILE) {
+            int before = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < MC_TILE / 32; ++w2) before += (w2 < wid) ? s_warp[w2] : 0;
+            if (keep) {
+                const int at = base + before + pos;
+                for (int r = 0; r < R; ++r) out[(size_t)r * C + at] = s_tile[r][tid];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { int tot_keep = 0; for (int w2 = 0; w2 < MC_TILE / 32; ++w2) tot_keep += s_warp[w2]; s_base = base + tot_keep; }
+        __syncthreads();
+    }
+    if (tid == 0) calls[ti].clean_cols = s_base;
+}
+
 }  // namespace
 
 cudaError_t hb_copy_filter_launch(const HbLocus* pairs, uint32_t n_pairs, const uint32_t* clen, const uint64_t* goff,
@@ -542,5 +656,14 @@ cudaError_t hb_qhsp_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* 
     const uint64_t threads = (uint64_t)n_pairs * 32;
     qhsp_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(pairs, n_pairs, alns, qrec_unit_off, qrec, cseq2, cnmask, cgoff,
                                                                   gseq2, gnmask, goff, glen, n_contig, tot, out);
+    return cudaGetLastError();
+}
+cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* task_cand, uint32_t n_tasks, uint32_t n_full,
+                                const HbLocus* pairs, const uint32_t* pair_off, const HbAln* alns, const uint32_t* qrec_unit_off,
+                                const uint32_t* qrec, const uint32_t* col_off, const uint32_t* colq, const uint32_t* gseq2,
+                                const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* clean, HbVoteCall* calls, cudaStream_t s) {
+    if (n_tasks == 0) return cudaSuccess;
+    msa_clean_kernel<<<n_tasks, MC_THREADS, 0, s>>>(tasks, task_cand, n_full, pairs, pair_off, alns, qrec_unit_off, qrec, col_off,
+                                                    colq, gseq2, gnmask, tot, flank, clean, calls);
     return cudaGetLastError();
 }

@@ -583,8 +583,6 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
     ENSURE_L("m.tmat_off", sizeof(uint64_t) * (n_cand + 1));
     HB_CUDA_OK(cudaMemcpyAsync(LB("m.mat_off").p, h_mat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
     HB_CUDA_OK(cudaMemcpyAsync(LB("m.tmat_off").p, h_tmat_off.data(), sizeof(uint64_t) * (n_cand + 1), cudaMemcpyHostToDevice, s));
-    ENSURE_L("m.mat", mat_total + 4);
-    // every byte of every row is written by msa_write_kernel (gaps included): no pre-fill
     {
         uint64_t all_cols = 0;
         for (uint32_t c = 0; c < n_cand; ++c) all_cols += h_cols[c];
@@ -594,15 +592,9 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
                                     LB("m.col_off").as<uint32_t>(), LB("m.colq").as<uint32_t>(), s));
         ++launches;
     }
-    for (int trunc = 0; trunc <= (n_tasks > n_full ? 1 : 0); ++trunc) {
-        HB_CUDA_OK(hb_msa_write_launch(LB("p.pairs").as<HbLocus>(), n_pairs, LB("p.alns").as<HbAln>(),
-                                       LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(),
-                                       LB("m.n_cols").as<uint32_t>(), LB("m.col_off").as<uint32_t>(),
-                                       LB("m.colq").as<uint32_t>(),
-                                       LB(trunc ? "m.tmat_off" : "m.mat_off").as<uint64_t>(), ctx->buf("g.seq2").as<uint32_t>(),
-                                       ctx->buf("g.nmask").as<uint32_t>(), tot, flank, trunc, LB("m.mat").as<uint8_t>(), s));
-        ++launches;
-    }
+    // the raw matrices are not written on the path: msa_clean_kernel below goes from the edit records straight to the clean
+    // matrices.  hb_last_msa / hb_last_msa_trunc (parity getters, the FiLTR mode) materialise them on demand.
+    ln.raw_valid = false; ln.raw_bytes = mat_total; ln.raw_flank = flank; ln.raw_has_trunc = n_tasks > n_full;
     HB_CUDA_OK(cudaEventRecord(ln.ev[4], s));
     mark("copy rules + msa");
     ln.tmat_off = h_tmat_off; ln.trows = h_trows;
@@ -648,9 +640,17 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
         ENSURE_L("v.dense", col_total + 2ull * n_tasks + 1);
         ENSURE_L("v.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(n_tasks + 1));
         ENSURE_L("v.total", sizeof(uint64_t));
+        ENSURE_L("v.task_cand", sizeof(uint32_t) * n_tasks);
         HB_CUDA_OK(cudaMemcpyAsync(LB("v.tasks").p, tasks.data(), sizeof(HbVoteTask) * n_tasks, cudaMemcpyHostToDevice, s));
+        HB_CUDA_OK(cudaMemcpyAsync(LB("v.task_cand").p, task_cand.data(), sizeof(uint32_t) * n_tasks, cudaMemcpyHostToDevice, s));
         HB_CUDA_OK(cudaMemsetAsync(LB("v.calls").p, 0, sizeof(HbVoteCall) * n_tasks, s));
-        HB_CUDA_OK(hb_vote_launch(LB("v.tasks").as<HbVoteTask>(), (int)n_tasks, LB("m.mat").as<uint8_t>(),
+        HB_CUDA_OK(hb_msa_clean_launch(LB("v.tasks").as<HbVoteTask>(), LB("v.task_cand").as<uint32_t>(), n_tasks, n_full,
+                                       LB("p.pairs").as<HbLocus>(), LB("s.pair_off").as<uint32_t>(), LB("p.alns").as<HbAln>(),
+                                       LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(), LB("m.col_off").as<uint32_t>(),
+                                       LB("m.colq").as<uint32_t>(), ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(),
+                                       tot, flank, LB("v.clean").as<uint8_t>(), LB("v.calls").as<HbVoteCall>(), s));
+        ++launches;
+        HB_CUDA_OK(hb_vote_launch(LB("v.tasks").as<HbVoteTask>(), (int)n_tasks, nullptr,
                                   LB("v.clean").as<uint8_t>(), LB("v.planes").as<uint32_t>(), LB("v.matches").p,
                                   LB("v.anchors").as<int>(), LB("c.ascii").as<uint8_t>(),
                                   LB("v.cons").as<uint8_t>(), LB("v.calls").as<HbVoteCall>(), prm->te_type,
@@ -922,6 +922,25 @@ extern "C" int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t*
     return HB_OK;
 }
 
+// Raw (pre-clean) matrices of the last serial hb_adjust, written on demand from the buffers it left on the device.
+static int materialise_raw(hb_ctx* ctx) {
+    HbLane& ln = ctx->lane[0];
+    if (ln.raw_valid) return HB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ln.stream;
+    HB_CUDA_OK(ctx->buf("m.mat").ensure(ln.raw_bytes + 4));
+    for (int trunc = 0; trunc <= (ln.raw_has_trunc ? 1 : 0); ++trunc)
+        HB_CUDA_OK(hb_msa_write_launch(ctx->buf("p.pairs").as<HbLocus>(), ln.n_pairs, ctx->buf("p.alns").as<HbAln>(),
+                                       ctx->buf("p.qr_off").as<uint32_t>(), ctx->buf("p.qrec").as<uint32_t>(),
+                                       ctx->buf("m.n_cols").as<uint32_t>(), ctx->buf("m.col_off").as<uint32_t>(),
+                                       ctx->buf("m.colq").as<uint32_t>(),
+                                       ctx->buf(trunc ? "m.tmat_off" : "m.mat_off").as<uint64_t>(), ctx->buf("g.seq2").as<uint32_t>(),
+                                       ctx->buf("g.nmask").as<uint32_t>(), ctx->g_tot, ln.raw_flank, trunc, ctx->buf("m.mat").as<uint8_t>(), s));
+    HB_CUDA_OK(cudaStreamSynchronize(s));
+    ln.raw_valid = true;
+    return HB_OK;
+}
+
 extern "C" int hb_last_msa_trunc(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii, uint64_t cap, int32_t* R, int32_t* C) {
     if (!ctx || !R || !C) return HB_EINVAL;
     if (ctx->last_overlapped) return hb_fail_msg(ctx, HB_ESTATE, "hb_last_msa_trunc: needs a serial hb_adjust (hb_params.overlap < 2)");
@@ -930,6 +949,7 @@ extern "C" int hb_last_msa_trunc(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii,
     const uint64_t bytes = (uint64_t)*R * (uint64_t)*C;
     if (!out_ascii || bytes == 0) return HB_OK;
     if (cap < bytes) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_msa_trunc: buffer too small");
+    { const int rc = materialise_raw(ctx); if (rc != HB_OK) return rc; }
     cudaSetDevice(ctx->device);
     HB_CUDA_OK(cudaMemcpyAsync(out_ascii, ctx->buf("m.mat").as<uint8_t>() + ctx->last_tmat_off[cand], bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -945,6 +965,7 @@ extern "C" int hb_last_msa(hb_ctx* ctx, uint32_t cand, uint8_t* out_ascii, uint6
     const uint64_t bytes = (uint64_t)*R * (uint64_t)*C;
     if (!out_ascii || bytes == 0) return HB_OK;
     if (cap < bytes) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_msa: buffer too small");
+    { const int rc = materialise_raw(ctx); if (rc != HB_OK) return rc; }
     cudaSetDevice(ctx->device);
     HB_CUDA_OK(cudaMemcpyAsync(out_ascii, ctx->buf("m.mat").as<uint8_t>() + ctx->last_mat_off[cand], bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HB_CUDA_OK(cudaStreamSynchronize(ctx->stream));

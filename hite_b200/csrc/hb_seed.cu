@@ -128,6 +128,16 @@ __global__ void cand_first_cluster_kernel(const uint64_t* __restrict__ hits, con
     (void)n_cand;
 }
 
+// S5c: the band of a locus is centred on the MEDIAN diagonal of its cluster's hits (sorted by diagonal: hits a .. b-1) and
+// sized by their 5 %-trimmed spread, so a stray hit within HB_DGAP of the chain neither drags the band off the copy nor
+// widens it (dmin / dmax of the locus are the trimmed bounds; the extension kernels pick their band from dmax - dmin)
+__device__ __forceinline__ void locus_band(const uint64_t* __restrict__ hits, uint64_t a, uint64_t b, HbLocus* L) {
+    const uint64_t n = b - a, t = n / 20;
+    L->dmin = (int64_t)((hits[a + t] >> 13) & 0x1FFFFFFFFull);
+    L->dmax = (int64_t)((hits[b - 1 - t] >> 13) & 0x1FFFFFFFFull);
+    L->j0 = (int64_t)((hits[a + n / 2] >> 13) & 0x1FFFFFFFFull) - HB_DIAG_OFF;
+}
+
 constexpr uint32_t RANK_SMEM_KEYS = 768;     // valid clusters per candidate ranked in shared memory (12 B each, 4 warps)
 
 // S5/S6: rank the clusters of a candidate (n desc, rel asc, dmin asc), keep the best max_loci.
@@ -192,12 +202,10 @@ rank_select_kernel(const uint64_t* __restrict__ hits, uint64_t n_hits, const uin
                 if (rank < (uint32_t)max_loci) {
                     const uint32_t x = kcl[v];
                     const uint64_t e = (x + 1 < n_cl) ? cl_start[x + 1] : n_hits;
-                    const int64_t dmin = (int64_t)(kx & 0x1FFFFFFFFull);
-                    const int64_t dmax = (int64_t)((hits[e - 1] >> 13) & 0x1FFFFFFFFull);
                     HbLocus L;
                     L.cand = c; L.rel = (uint32_t)((kx >> 33) & 1ull); L.nseeds = 0xFFFFFFFFu - (uint32_t)(kx >> 34);
-                    L.rank = rank; L.dmin = dmin; L.dmax = dmax;
-                    L.j0 = ((dmin + dmax) >> 1) - HB_DIAG_OFF;
+                    L.rank = rank;
+                    locus_band(hits, cl_start[x], e, &L);
                     loci[(size_t)c * max_loci + rank] = L;
                 }
             }
@@ -227,10 +235,9 @@ rank_select_kernel(const uint64_t* __restrict__ hits, uint64_t n_hits, const uin
                 }
                 if (rank < (uint32_t)max_loci) {
                     const uint64_t e = (x + 1 < n_cl) ? cl_start[x + 1] : n_hits;
-                    const int64_t dmax = (int64_t)((hits[e - 1] >> 13) & 0x1FFFFFFFFull);
                     HbLocus L;
-                    L.cand = c; L.rel = relx; L.nseeds = nx; L.rank = rank; L.dmin = dminx; L.dmax = dmax;
-                    L.j0 = ((dminx + dmax) >> 1) - HB_DIAG_OFF;
+                    L.cand = c; L.rel = relx; L.nseeds = nx; L.rank = rank;
+                    locus_band(hits, cl_start[x], e, &L);
                     loci[(size_t)c * max_loci + rank] = L;
                 }
             }

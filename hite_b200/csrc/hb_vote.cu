@@ -1491,7 +1491,8 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
                                       uint8_t* d_cons, HbVoteCall* d_calls, int te_type, int avg_rows, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     static_assert(ROW_WARPS == WARPS_PER_CTA, "the NW = 1 tail kernel shares the one-warp-per-candidate grid");
-    hb_clean_kernel<<<n, CLEAN_THREADS, 0, stream>>>(d_tasks, d_raw, d_clean, d_calls);
+    // d_raw == nullptr: the clean matrices (and calls[].clean_cols) were already produced by hb_msa.cu::msa_clean_kernel
+    if (d_raw) hb_clean_kernel<<<n, CLEAN_THREADS, 0, stream>>>(d_tasks, d_raw, d_clean, d_calls);
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (te_type == 0) {
         hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);

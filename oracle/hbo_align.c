@@ -169,7 +169,7 @@ void hbo_sort_u64(uint64_t *keys, uint64_t n) { qsort(keys, n, sizeof(uint64_t),
    Outside the band / outside the genome: H = 0, E = F = -6.                                       */
 /* band half-width: 16 when the seed cluster's diagonal spread is <= HB_NARROW_SPREAD (o in [-16,15]),
    else 32 (o in [-32,31])  -- HB-align S7 */
-#define HB_NARROW_SPREAD 8
+#define HB_NARROW_SPREAD 12
 #define SC_MATCH 2
 #define SC_MIS (-4)
 #define SC_GAPO 4
@@ -273,12 +273,21 @@ static uint64_t lower_bound_h(const uint64_t *idx, uint64_t n, uint32_t h) {
     return lo;
 }
 
-typedef struct { uint32_t cand, rel, n; int64_t dmin, dmax; } cluster_t;
+typedef struct { uint32_t cand, rel, n; int64_t dmin, dmax; int64_t tlo, thi, med; } cluster_t;   /* tlo / thi / med: S5c */
 
 static int better_cluster(const cluster_t *a, const cluster_t *b) {   /* a ranks before b */
     if (a->n != b->n) return a->n > b->n;
     if (a->rel != b->rel) return a->rel < b->rel;
     return a->dmin < b->dmin;
+}
+
+/* S5c: the band of a cluster is centred on the MEDIAN diagonal of its hits and sized by their 5 %-trimmed spread (hits a..b-1,
+   sorted by diagonal): a stray hit within DGAP of the chain no longer drags the band off the copy or widens it */
+static void cluster_trim(const uint64_t *hits, uint64_t a, uint64_t b, cluster_t *c) {
+    const uint64_t n = b - a, t = n / 20;
+    c->tlo = (int64_t)((hits[a + t] >> 13) & 0x1FFFFFFFFull);
+    c->thi = (int64_t)((hits[b - 1 - t] >> 13) & 0x1FFFFFFFFull);
+    c->med = (int64_t)((hits[a + n / 2] >> 13) & 0x1FFFFFFFFull);
 }
 
 /* Returns number of loci written (<= cap).  cands: codes (0..4), cand i at coff[i]..coff[i+1]. */
@@ -335,7 +344,7 @@ uint64_t hbo_find_loci(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx,
             dl = d; ++j;
         }
         if (dl - d0 <= SPLIT_SPREAD) {
-            if (j - i >= MIN_SEEDS) { cl[ncl].cand = c; cl[ncl].rel = rel; cl[ncl].n = (uint32_t)(j - i); cl[ncl].dmin = d0; cl[ncl].dmax = dl; ++ncl; }
+            if (j - i >= MIN_SEEDS) { cl[ncl].cand = c; cl[ncl].rel = rel; cl[ncl].n = (uint32_t)(j - i); cl[ncl].dmin = d0; cl[ncl].dmax = dl; cluster_trim(hits, i, j, &cl[ncl]); ++ncl; }
         } else {
             /* S5b: a run wider than the band (a copy whose diagonal drifts: net insertions / deletions) is cut into pieces of
                SPLIT_SPREAD + 1 diagonals counted from its first diagonal; each piece is aligned in its own band and the
@@ -351,7 +360,7 @@ uint64_t hbo_find_loci(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx,
                     if ((d - d0) / (SPLIT_SPREAD + 1) != bucket) break;
                     db = d; ++b;
                 }
-                if (b - a >= MIN_SEEDS) { cl[ncl].cand = c; cl[ncl].rel = rel; cl[ncl].n = (uint32_t)(b - a); cl[ncl].dmin = da; cl[ncl].dmax = db; ++ncl; }
+                if (b - a >= MIN_SEEDS) { cl[ncl].cand = c; cl[ncl].rel = rel; cl[ncl].n = (uint32_t)(b - a); cl[ncl].dmin = da; cl[ncl].dmax = db; cluster_trim(hits, a, b, &cl[ncl]); ++ncl; }
                 a = b;
             }
         }
@@ -375,8 +384,9 @@ uint64_t hbo_find_loci(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx,
             if (rank < cnt && nout + rank < cap) {
                 hbo_locus *L = &out[nout + rank];
                 L->cand = cl[x].cand; L->rel = cl[x].rel; L->nseeds = cl[x].n; L->rank = (uint32_t)rank;
-                L->dmin = cl[x].dmin; L->dmax = dmax;
-                L->j0 = ((cl[x].dmin + dmax) >> 1) - DIAG_OFF;
+                (void)dmax;
+                L->dmin = cl[x].tlo; L->dmax = cl[x].thi;
+                L->j0 = cl[x].med - DIAG_OFF;
             }
         }
         nout += cnt;
@@ -507,6 +517,7 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
                        (loci[x].dmax - loci[x].dmin <= HB_NARROW_SPREAD) ? 16 : 32, &a, qrecs + (size_t)x * L);
         cp->score = a.score; cp->i_s = a.i_s; cp->i_e = a.i_e; cp->j_s = a.j_s; cp->j_e = a.j_e;
     }
+    if (getenv("HBO_DEBUG_SPREAD")) for (int x = 0; x < nl; ++x) fprintf(stderr, "SPREAD %lld %u\n", (long long)(loci[x].dmax - loci[x].dmin), loci[x].nseeds);
     if (!getenv("HBO_NO_CHAIN")) chain_pieces(nl, loci, copies, qrecs, L);   /* S8b (the switch is a debugging aid) */
     for (int x = 0; x < nl; ++x) {
         hbo_copy *cp = &copies[x];
