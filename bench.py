@@ -249,7 +249,7 @@ def main():
     tc = time.perf_counter()
     iv = ctx.coarse_boundary(seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=max(1, cores // world),
                              part=rank, n_parts=world)
-    tmc = ctx.timing()
+    tmc = ctx.coarse_timing()
     cs = torch.tensor([(tmc["kernel_ms"] + tmc["k_ms"][3]) * 1e-3, time.perf_counter() - tc, float(len(iv)),
                        tmc["kernel_ms"], tmc["k_ms"][3], tmc["k_ms"][6], tmc["k_ms"][7]], device="cuda", dtype=torch.float64)
     cmax, csum = cs.clone(), cs.clone()
@@ -281,23 +281,23 @@ def main():
     gather = hbdist.RecordGather([len(s) for s in shards], [sum(lens_all[i] for i in s) for s in shards], "cuda")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     state = {"pending": False}
+    chunk = {"n": 1 << 16}                  # candidates per hb_adjust call; halved when a call reports HB_ENOMEM (too many seed hits)
 
     def step():
         """one round over this rank's shard + the exchange -> (kernel ms, stage ms, h2d, d2h, launches, n_te)"""
         k_ms, stage, h2d, d2h, launches, n_te = 0.0, np.zeros(8), 0, 0, 0, 0
         idx_all, len_all, parts = [], [], []
         for kind, idx, host_cands in groups:
-            calls, cons = ctx.adjust_raw(host_cands, kind, 1)
-            tm = ctx.timing()
-            k_ms += tm["kernel_ms"]; stage += np.array(tm["k_ms"])
-            h2d += tm["h2d_bytes"]; d2h += tm["d2h_bytes"]; launches += tm["launches"]
-            te = calls["is_te"] != 0
-            n_te += int(te.sum())
-            idx_all.append(idx[te]); len_all.append(calls["cons_len"][te])
-            dev = ctx.last_cons_device()
-            if dev is not None:
-                t = torch.as_tensor(dev, device="cuda")
-                parts.append(t if len(groups) == 1 else t.clone())
+            for calls, cons, sub_idx, dev in adjust_chunked(ctx, kind, idx, host_cands, chunk, len(groups) == 1):
+                state["last"] = (kind, sub_idx)
+                tm = ctx.timing()
+                k_ms += tm["kernel_ms"]; stage += np.array(tm["k_ms"])
+                h2d += tm["h2d_bytes"]; d2h += tm["d2h_bytes"]; launches += tm["launches"]
+                te = calls["is_te"] != 0
+                n_te += int(te.sum())
+                idx_all.append(sub_idx[te]); len_all.append(calls["cons_len"][te])
+                if dev is not None:
+                    parts.append(dev)
         if state["pending"]:
             gather.finish()                               # last step's collective: it overlapped this step's kernels
         ev[0].record()
@@ -342,7 +342,7 @@ def main():
         assert len(got[0]) == n_te_total and (got[2] is None or int(got[1].sum()) == len(got[2])), "gathered records are inconsistent"
     # roofline of the dominant stage (banded extension + traceback) from SURVEY 8(d)-(ii) bytes, on the LAST group's pairs
     copies = ctx.last_copies()
-    last_kind, last_idx, _ = groups[-1]
+    last_kind, last_idx = state["last"]
     lens = np.array([lens_all[i] for i in last_idx])
     pair_L = lens[copies["cand"]]
     algo_bytes = float(np.sum(algo_bytes_pair(pair_L)))
@@ -429,6 +429,35 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def adjust_chunked(ctx, kind, idx, host_cands, chunk, alias_ok):
+    """hb_adjust over a group in sub-batches of at most chunk["n"] candidates (one call when it fits); a call refused with
+    HB_ENOMEM (more than 2^31 seed hits: high-copy families at Gbp scale) halves the sub-batch size for the rest of the run.
+    Yields (calls, cons, candidate indices, consensus bytes on the device -- cloned unless it is the only sub-batch)."""
+    import torch
+    import hite_b200
+    flat, offs = host_cands
+    n = len(offs) - 1
+    lo = 0
+    while lo < n:
+        hi = min(n, lo + chunk["n"])
+        sub = (flat[int(offs[lo]):int(offs[hi]) + 1], offs[lo:hi + 1] - offs[lo]) if (lo, hi) != (0, n) else host_cands
+        try:
+            calls, cons = ctx.adjust_raw(sub, kind, 1)
+        except hite_b200.HiteB200Error as e:
+            if "(-4)" not in str(e) or chunk["n"] <= 64:
+                raise
+            chunk["n"] //= 2
+            continue
+        dev = ctx.last_cons_device()
+        t = None
+        if dev is not None:
+            t = torch.as_tensor(dev, device="cuda")
+            if (lo, hi) != (0, n) or not alias_ok:
+                t = t.clone()
+        yield calls, cons, idx[lo:hi], t
+        lo = hi
 
 
 def extras(line, ctx, wl, my_cands, cores):

@@ -284,6 +284,10 @@ class Context:
         if rc != 0:
             raise HiteB200Error("%s failed (%d): %s" % (what, rc, (self._lib.hb_last_error(self._h) or b"").decode()))
 
+    def coarse_timing(self):
+        """timing of the last ``coarse_boundary`` call, summed over its passes"""
+        return self._coarse_timing
+
     def timing(self):
         t = HbTiming()
         self._lib.hb_get_timing(self._h, C.byref(t))
@@ -438,15 +442,35 @@ class Context:
         """The all-vs-all + FMEA step of ``determine_repeat_boundary_v5`` (reference module/Util.py:4657-4663) on
         the loaded genome -> INTERVAL_DTYPE array ('chr:start-end', 0-based half open).  ``part`` / ``n_parts``: this
         process's share of a stage sharded over several GPUs (``hb_coarse_boundary_part``): the parts' results
-        concatenated in part order are the unsharded result."""
-        n = C.c_uint64(0)
-        self._check(self._lib.hb_coarse_boundary_part(self._h, int(seg_len), int(skip_gap), int(max_len), int(occ_cap), int(threads),
-                                                      int(part), int(n_parts), None, 0, C.byref(n)), "hb_coarse_boundary")
-        tm = self.timing()
-        out = np.zeros(max(1, n.value), dtype=INTERVAL_DTYPE)
-        self._check(self._lib.hb_last_intervals(self._h, _ptr(out), len(out), C.byref(n)), "hb_last_intervals")
-        self._coarse_timing = tm
-        return out[:n.value]
+        concatenated in part order are the unsharded result.  A share whose seed pairs do not fit one pass (HB_ENOMEM:
+        more than 2^32 pairs, repeat-rich Gbp genomes) is run as 2, 4, ... consecutive sub-parts; ``timing()`` afterwards
+        is the sum over the passes."""
+        split = 1
+        while True:
+            outs, tm_sum = [], None
+            try:
+                for sub in range(split):
+                    n = C.c_uint64(0)
+                    self._check(self._lib.hb_coarse_boundary_part(self._h, int(seg_len), int(skip_gap), int(max_len), int(occ_cap),
+                                                                  int(threads), int(part) * split + sub, int(n_parts) * split, None, 0,
+                                                                  C.byref(n)), "hb_coarse_boundary")
+                    tm = self.timing()
+                    out = np.zeros(max(1, n.value), dtype=INTERVAL_DTYPE)
+                    self._check(self._lib.hb_last_intervals(self._h, _ptr(out), len(out), C.byref(n)), "hb_last_intervals")
+                    outs.append(out[:n.value])
+                    if tm_sum is None:
+                        tm_sum = tm
+                    else:
+                        tm_sum["kernel_ms"] += tm["kernel_ms"]
+                        tm_sum["k_ms"] = [a + b for a, b in zip(tm_sum["k_ms"], tm["k_ms"])]
+                        tm_sum["launches"] += tm["launches"]
+                        tm_sum["d2h_bytes"] += tm["d2h_bytes"]
+                self._coarse_timing = tm_sum
+                return np.concatenate(outs) if len(outs) > 1 else outs[0]
+            except HiteB200Error as e:
+                if "(-4)" not in str(e) or split >= 1024:
+                    raise
+                split *= 2
 
     def mask_genome(self, contig, start, end):
         """N-fill [start, end) (0-based) of the resident packed genome (``hb_genome_mask``; reference module/Util.py:6414-6420)

@@ -58,12 +58,16 @@ def stage_devices():
 _LOCK = threading.Lock()
 
 
-def get_context(device=None):
+def get_context(device=None, role="reference"):
+    """One context per process, GPU and role.  ``reference``: holds the stage's reference genome + index (loaded once, see
+    ensure_genome).  ``members``: a second, small context for sequence sets that come and go -- the member file of one
+    candidate (is_TE_from_align_file), the sequence set of a clustering run -- so that they never evict the reference."""
     d = _device() if device is None else device
+    key = d if role == "reference" else (d, role)
     with _LOCK:
-        if d not in _CTX:
-            _CTX[d] = _lib.Context(d)
-        return _CTX[d]
+        if key not in _CTX:
+            _CTX[key] = _lib.Context(d)
+        return _CTX[key]
 
 
 def ensure_genome(ctx, reference, k=15, w=10, _parsed=None):
@@ -307,15 +311,14 @@ def is_TE_from_align_file(cur_align_file, query_name, cur_seq, temp_dir, subset_
     member_names, member_contigs = read_fasta(cur_align_file)
     if not member_names:
         return (None, None, "", 0, cur_align_file)
-    ctx = get_context()
+    ctx = get_context(role="members")
     if _is_aligned(member_contigs):
         rows = [member_contigs[n] for n in member_names]
         r = ctx.vote_matrices([cur_seq], [rows], TE_type, int(plant), result_type)[0]
     else:
         if len(member_names) > 100:                                              # :10409-10412, 100 longest
             member_names = subset_100_longest(member_names, member_contigs)
-        _GENOME.pop(ctx.device, None)
-        ctx.load_genome([member_contigs[n].encode("ascii") for n in member_names])
+        ctx.load_genome([member_contigs[n].encode("ascii") for n in member_names], member_names)
         ctx.build_index(15, 10)
         # the truncated-member gate is run_find_members_v8's job (it owns the two files), not this call's
         r = ctx.adjust([cur_seq], TE_type, int(plant), result_type, flank=50, trunc_gate=False)[0]

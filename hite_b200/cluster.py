@@ -91,8 +91,7 @@ def cd_hit_est(input_path, output_path, c=0.8, aS=0.95, aL=0.95, A=80, g=1, ctx=
                             ("n_match", "<i4"), ("aln_len", "<i4"), ("score", "<i4"), ("rank", "<i4")])
     if len(usable) > 1:
         if ctx is None:
-            ctx = boundary.get_context()
-            boundary._GENOME.pop(ctx.device, None)               # the context now holds the sequence set, not the reference
+            ctx = boundary.get_context(role="members")           # never evicts the stage's reference genome
         seqs = [recs[i][1].encode("ascii") for i in usable]
         ctx.load_genome(seqs)
         ctx.build_index(15, 10)

@@ -101,6 +101,7 @@ constexpr int MM_PER_THREAD = 8;
 constexpr int MM_TILE = MM_THREADS * MM_PER_THREAD;     // positions owned by a CTA
 constexpr int MM_HALO = 16;                             // >= w-1 on both sides
 constexpr uint32_t INVALID_H = 0xFFFFFFFFu;
+constexpr int MM_WORDS = (MM_TILE + 2 * MM_HALO + 16 + 15) / 16;   // seq2 words holding the tile + halo + k - 1 bases
 
 __device__ __forceinline__ uint32_t hash_kmer(uint64_t key, int k) {   // sketch.c hash64, masked
     const uint64_t mask = (1ULL << (2 * k)) - 1;
@@ -112,6 +113,19 @@ __device__ __forceinline__ uint32_t hash_kmer(uint64_t key, int k) {   // sketch
     key = key ^ key >> 28;
     key = (key + (key << 31)) & mask;
     return (uint32_t)key;
+}
+
+// the same mix on 32-bit registers: every step keeps only the low 2k <= 30 bits, which +, << and ~ determine from the low
+// bits of their inputs, and the right shifts act on values already masked to 2k bits
+__device__ __forceinline__ uint32_t hash_kmer32(uint32_t key, uint32_t mask) {
+    key = (~key + (key << 21)) & mask;
+    key = key ^ key >> 24;
+    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = key ^ key >> 14;
+    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = key ^ key >> 28;
+    key = (key + (key << 31)) & mask;
+    return key;
 }
 
 __device__ __forceinline__ int base_at(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ nmask,
@@ -134,32 +148,55 @@ minimizer_kernel(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__
     const int64_t tile0 = (int64_t)blockIdx.x * MM_TILE;
     const int64_t ext0 = tile0 - MM_HALO;
     const int ext_n = MM_TILE + 2 * MM_HALO;
-    // hashes of the k-mers starting at ext0 + x
-    for (int x0 = tid * 9; x0 < ext_n; x0 += MM_THREADS * 9) {
-        // each thread rolls over 9 consecutive positions
-        uint64_t f = 0, r = 0;
-        int bad = 0;   // number of N among the current k bases (counted via last-N distance)
-        const int64_t p0 = ext0 + x0;
-        int last_n = -1000;
-        for (int t = 0; t < k - 1; ++t) {
-            const int c = base_at(seq2, nmask, tot, p0 + t);
-            if (c > 3) last_n = t;
-            f = (f << 2) | (uint64_t)(c & 3);
-            r = (r >> 2) | ((uint64_t)(3 - (c & 3)) << (2 * (k - 1)));
+    // The packed words of the tile (+ halo + k - 1 bases) are staged once in shared memory; every hash is then cut out of a
+    // 64-bit window of the 2-bit stream held in registers: no per-base loads.  The stream has base t of a k-mer at bits 2t,
+    // which IS the reverse-complement k-mer once complemented; the forward k-mer is the same slice with its 2-bit groups
+    // reversed (brev + swap inside the pairs).  tile0 and MM_HALO are multiples of 16, so ext0 is word aligned.
+    __shared__ uint32_t s_seq[MM_WORDS + 2];
+    __shared__ uint32_t s_nm[MM_WORDS / 2 + 2];
+    {
+        const int64_t w0 = ext0 >> 4;                                  // first seq2 word (ext0 may be -16: word -1)
+        const int64_t n_words = (int64_t)((tot + 15) >> 4), n_nwords = (int64_t)((tot + 31) >> 5);
+        for (int x = tid; x < MM_WORDS + 2; x += MM_THREADS) {
+            const int64_t wi = w0 + x;
+            s_seq[x] = (wi >= 0 && wi < n_words) ? seq2[wi] : 0u;
         }
-        (void)bad;
-        const uint64_t mask = (1ULL << (2 * k)) - 1;
-        for (int j = 0; j < 9 && x0 + j < ext_n; ++j) {
-            const int t = k - 1 + j;
-            const int c = base_at(seq2, nmask, tot, p0 + t);
-            if (c > 3) last_n = t;
-            f = ((f << 2) | (uint64_t)(c & 3)) & mask;
-            r = (r >> 2) | ((uint64_t)(3 - (c & 3)) << (2 * (k - 1)));
-            const bool has_n = last_n >= j;              // an N inside positions j..j+k-1
+        const int64_t nw0 = ext0 >> 5;                                 // floor, also for -16
+        for (int x = tid; x < MM_WORDS / 2 + 2; x += MM_THREADS) {
+            const int64_t wi = nw0 + x;
+            uint32_t m = (wi >= 0 && wi < n_nwords) ? nmask[wi] : 0xFFFFFFFFu;
+            // positions at or beyond tot inside the last word count as N
+            if (wi >= 0 && wi < n_nwords && (uint64_t)(wi + 1) * 32 > tot) m |= ~0u << (tot & 31);
+            s_nm[x] = m;
+        }
+    }
+    __syncthreads();
+    const uint32_t kmask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const uint32_t nmask_k = (1u << k) - 1u;
+    const int nm_shift0 = (int)(ext0 - ((ext0 >> 5) << 5));            // 0 or 16: offset of ext0 inside its nmask word
+    for (int x0 = tid * 9; x0 < ext_n; x0 += MM_THREADS * 9) {
+        // 9 consecutive positions need 9 + k - 1 <= 24 bases = 48 bits from bit offset 2 * (x0 & 15) of word x0 >> 4
+        const int wq = x0 >> 4, off = 2 * (x0 & 15);
+        const uint64_t lo = (uint64_t)s_seq[wq] | ((uint64_t)s_seq[wq + 1] << 32);
+        const uint64_t hi = (uint64_t)s_seq[wq + 2];
+        const uint64_t stream = off ? ((lo >> off) | (hi << (64 - off))) : lo;
+        const int nb = x0 + nm_shift0;                                 // bit index into the staged N-mask stream
+        const uint64_t nlo = (uint64_t)s_nm[nb >> 5] | ((uint64_t)s_nm[(nb >> 5) + 1] << 32);
+        const uint32_t nbits = (uint32_t)(nlo >> (nb & 31));           // >= 32 - 0 ... at least 32 valid bits: 24 needed
+        const int64_t p0 = ext0 + x0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            if (x0 + j >= ext_n) break;
+            const uint32_t slice = (uint32_t)(stream >> (2 * j)) & kmask;
+            const uint32_t r = ~slice & kmask;
+            uint32_t y = __brev(slice);
+            y = ((y & 0xAAAAAAAAu) >> 1) | ((y & 0x55555555u) << 1);
+            const uint32_t f = y >> (32 - 2 * k);
+            const bool has_n = ((nbits >> j) & nmask_k) != 0u;
             uint32_t h = INVALID_H; uint8_t st = 0;
             if (!has_n && f != r && p0 + j >= 0 && (uint64_t)(p0 + j) + (uint64_t)k <= tot) {
                 st = r < f;
-                h = hash_kmer(r < f ? r : f, k);
+                h = hash_kmer32(r < f ? r : f, kmask);
             }
             s_h[x0 + j] = h; s_st[x0 + j] = st; s_sel[x0 + j] = 0;
         }

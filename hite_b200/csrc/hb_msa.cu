@@ -479,46 +479,55 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
 }
 
 // S10d + sparse-column removal fused (msa_write_kernel followed by hb_vote.cu::hb_clean_kernel, without the raw matrix ever
-// reaching HBM): one CTA per judge task (a candidate's full matrix, or its truncated-member matrix).  The matrix is produced
-// 128 columns at a time in shared memory -- a warp per row derives the row's symbols from the column map and the pair's
-// edit records exactly like msa_write_kernel -- then every column of the tile is counted, kept or dropped by the
-// reference's rule (remove_sparse_col_in_align_file, module/Util.py:10379-10391: first and last column always kept, a
-// column goes when gaps > rows / 2) and the kept columns are appended to the clean matrix (row stride C, symbol codes).
+// reaching HBM): one CTA per candidate, producing the clean matrix of its full judge task AND of its truncated-member task
+// (rows = its copies longer than 1000 bp, cells outside each row's first / last 500 bases blanked) from ONE computation of
+// the symbols.  The matrix is built 128 columns at a time in shared memory -- the tile's column map is staged once, a warp
+// per row derives the row's symbols from it and the pair's edit records exactly like msa_write_kernel, bit 7 of a cell
+// marks "blank in the truncated matrix" -- then every column of the tile is counted twice (all rows; truncated rows), kept or
+// dropped by the reference's rule (remove_sparse_col_in_align_file, module/Util.py:10379-10391: first and last column always
+// kept, a column goes when gaps > rows / 2) and the kept columns are appended to the two clean matrices (row stride C).
 constexpr int MC_TILE = 128, MC_THREADS = 256, MC_MAXROWS = 104;
 __global__ void __launch_bounds__(MC_THREADS)
-msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restrict__ task_cand, uint32_t n_full,
+msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restrict__ task_cand, const int32_t* __restrict__ trunc_of_full,
                  const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, const HbAln* __restrict__ alns,
                  const uint32_t* __restrict__ qrec_unit_off, const uint32_t* __restrict__ qrec,
                  const uint32_t* __restrict__ col_off, const uint32_t* __restrict__ colq, const uint32_t* __restrict__ gseq2,
                  const uint32_t* __restrict__ gnmask, uint64_t tot, int flank, uint8_t* __restrict__ clean,
                  HbVoteCall* __restrict__ calls) {
     __shared__ __align__(16) uint8_t s_tile[MC_MAXROWS][MC_TILE];
+    __shared__ uint32_t s_cq[MC_TILE];
     __shared__ uint32_t s_pair[MC_MAXROWS];
-    __shared__ int s_warp[MC_TILE / 32];
-    __shared__ int s_base;
-    const uint32_t ti = blockIdx.x;
+    __shared__ short s_trow[MC_MAXROWS];
+    __shared__ int s_warp[2][MC_TILE / 32];
+    __shared__ int s_base[2];
+    const uint32_t ti = blockIdx.x;                       // full task
+    const int tt = trunc_of_full[ti];                     // its truncated-member task, or -1
     const HbVoteTask t = tasks[ti];
-    const int trunc = ti >= n_full ? 1 : 0;
     const uint32_t c = task_cand[ti];
     const int R = t.R, C = t.C;
+    const int RT = tt >= 0 ? tasks[tt].R : 0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t p0 = pair_off[c], p1 = pair_off[c + 1];
     for (uint32_t p = p0 + tid; p < p1; p += MC_THREADS) {
-        const int r = trunc ? alns[p].trow : alns[p].row;
-        if (r >= 0 && r < MC_MAXROWS) s_pair[r] = p;
+        const HbAln a = alns[p];
+        if (a.row >= 0 && a.row < MC_MAXROWS) { s_pair[a.row] = p; s_trow[a.row] = (short)a.trow; }
     }
-    if (tid == 0) s_base = 0;
+    if (tid < 2) s_base[tid] = 0;
     __syncthreads();
     const uint32_t* cq = colq + col_off[c];
     uint8_t* out = clean + t.clean_off;
+    uint8_t* tout = tt >= 0 ? clean + tasks[tt].clean_off : nullptr;
     const uint32_t totm1 = (uint32_t)(tot - 1);
     for (int c0 = 0; c0 < C; c0 += MC_TILE) {
+        if (tid < MC_TILE) s_cq[tid] = c0 + tid < C ? cq[c0 + tid] : 0u;
+        __syncthreads();
         // ---- the tile's symbols: warp per row, 4 columns per lane ----
         for (int r = wid; r < R; r += MC_THREADS / 32) {
             const uint32_t p = s_pair[r];
             const HbAln a = alns[p];
             const HbLocus pr = pairs[p];
             const int rel = (int)pr.rel;
+            const bool in_trunc = s_trow[r] >= 0;
             const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
             const uint32_t j0 = (uint32_t)pr.j0, js = (uint32_t)a.j_s, je = (uint32_t)a.j_e;
             const int i_s = a.i_s, i_e = a.i_e;
@@ -529,7 +538,7 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
                 const int col = c0 + 4 * lane + k;
                 uint32_t sym = HB_SYM_GAP;
                 if (col < C) {
-                    const uint32_t e = cq[col];
+                    const uint32_t e = s_cq[4 * lane + k];
                     const int q = (int)(e >> 8) - flank;
                     const uint32_t slot = e & 255u;
                     uint32_t j = 0;
@@ -543,16 +552,16 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
                         else if (q < i_s) { if (q < i_s - flank) have = false; j = js - (uint32_t)(i_s - q); }
                         else { if (q > i_e + flank) have = false; j = je + (uint32_t)(q - i_e); }
                     }
-                    if (have && trunc) {
-                        const uint32_t d = j - ext_lo;
-                        if (d >= 500u && ext_len - 1u - d >= 500u) have = false;
-                    }
                     if (have) {
                         const uint32_t pos = rel ? totm1 - j : j;
                         if ((gnmask[pos >> 5] >> (pos & 31u)) & 1u) sym = HB_SYM_N;
                         else {
                             const uint32_t b2 = (gseq2[pos >> 4] >> (2u * (pos & 15u))) & 3u;
                             sym = rel ? 3u - b2 : b2;
+                        }
+                        if (in_trunc) {                                        // blank in the truncated-member matrix ?
+                            const uint32_t d = j - ext_lo;
+                            if (d >= 500u && ext_len - 1u - d >= 500u) sym |= 0x80u;
                         }
                     }
                 }
@@ -561,35 +570,54 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
             *reinterpret_cast<uint32_t*>(&s_tile[r][4 * lane]) = w;
         }
         __syncthreads();
-        // ---- sparse columns: thread per column of the tile ----
-        int keep = 0, pos = 0;
+        // ---- sparse columns of both matrices: thread per column of the tile ----
+        int keep = 0, pos = 0, tkeep = 0, tpos = 0;
         if (tid < MC_TILE) {
             const int col = c0 + tid;
             if (col < C) {
-                int gaps = 0;
-                for (int r = 0; r < R; ++r) gaps += s_tile[r][tid] == HB_SYM_GAP;
+                int gaps = 0, tgaps = 0;
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t b = s_tile[r][tid];
+                    gaps += (b & 0x7Fu) == HB_SYM_GAP;
+                    tgaps += (s_trow[r] >= 0) && (b == HB_SYM_GAP || (b & 0x80u));
+                }
                 keep = (col == 0) || (col == C - 1) || !(2 * gaps > R);
+                tkeep = RT > 0 && ((col == 0) || (col == C - 1) || !(2 * tgaps > RT));
             }
-            const uint32_t bal = __ballot_sync(HB_FULL, keep);
-            if (lane == 0) s_warp[wid] = __popc(bal);
+            const uint32_t bal = __ballot_sync(HB_FULL, keep), tbal = __ballot_sync(HB_FULL, tkeep);
+            if (lane == 0) { s_warp[0][wid] = __popc(bal); s_warp[1][wid] = __popc(tbal); }
             pos = __popc(bal & ((1u << lane) - 1u));
+            tpos = __popc(tbal & ((1u << lane) - 1u));
         }
         __syncthreads();
-        const int base = s_base;
+        const int base = s_base[0], tbase = s_base[1];
         if (tid < MC_TILE) {
-            int before = 0;
+            int before = 0, tbefore = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < MC_TILE / 32; ++w2) before += (w2 < wid) ? s_warp[w2] : 0;
+            for (int w2 = 0; w2 < MC_TILE / 32; ++w2) { before += (w2 < wid) ? s_warp[0][w2] : 0; tbefore += (w2 < wid) ? s_warp[1][w2] : 0; }
             if (keep) {
                 const int at = base + before + pos;
-                for (int r = 0; r < R; ++r) out[(size_t)r * C + at] = s_tile[r][tid];
+                for (int r = 0; r < R; ++r) out[(size_t)r * C + at] = s_tile[r][tid] & 0x7Fu;
+            }
+            if (tkeep) {
+                const int at = tbase + tbefore + tpos;
+                for (int r = 0; r < R; ++r) {
+                    const int tr = s_trow[r];
+                    if (tr < 0) continue;
+                    const uint32_t b = s_tile[r][tid];
+                    tout[(size_t)tr * C + at] = (b & 0x80u) ? (uint8_t)HB_SYM_GAP : (uint8_t)b;
+                }
             }
         }
         __syncthreads();
-        if (tid == 0) { int tot_keep = 0; for (int w2 = 0; w2 < MC_TILE / 32; ++w2) tot_keep += s_warp[w2]; s_base = base + tot_keep; }
+        if (tid == 0) {
+            int k0 = 0, k1 = 0;
+            for (int w2 = 0; w2 < MC_TILE / 32; ++w2) { k0 += s_warp[0][w2]; k1 += s_warp[1][w2]; }
+            s_base[0] = base + k0; s_base[1] = tbase + k1;
+        }
         __syncthreads();
     }
-    if (tid == 0) calls[ti].clean_cols = s_base;
+    if (tid == 0) { calls[ti].clean_cols = s_base[0]; if (tt >= 0) calls[tt].clean_cols = s_base[1]; }
 }
 
 }  // namespace
@@ -658,12 +686,12 @@ cudaError_t hb_qhsp_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* 
                                                                   gseq2, gnmask, goff, glen, n_contig, tot, out);
     return cudaGetLastError();
 }
-cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* task_cand, uint32_t n_tasks, uint32_t n_full,
+cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* task_cand, const int32_t* trunc_of_full, uint32_t n_full,
                                 const HbLocus* pairs, const uint32_t* pair_off, const HbAln* alns, const uint32_t* qrec_unit_off,
                                 const uint32_t* qrec, const uint32_t* col_off, const uint32_t* colq, const uint32_t* gseq2,
                                 const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* clean, HbVoteCall* calls, cudaStream_t s) {
-    if (n_tasks == 0) return cudaSuccess;
-    msa_clean_kernel<<<n_tasks, MC_THREADS, 0, s>>>(tasks, task_cand, n_full, pairs, pair_off, alns, qrec_unit_off, qrec, col_off,
-                                                    colq, gseq2, gnmask, tot, flank, clean, calls);
+    if (n_full == 0) return cudaSuccess;
+    msa_clean_kernel<<<n_full, MC_THREADS, 0, s>>>(tasks, task_cand, trunc_of_full, pairs, pair_off, alns, qrec_unit_off, qrec, col_off,
+                                                   colq, gseq2, gnmask, tot, flank, clean, calls);
     return cudaGetLastError();
 }

@@ -30,9 +30,10 @@ cudaError_t hb_qhsp_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* 
                            const uint32_t* qrec, const uint32_t* cseq2, const uint32_t* cnmask, const uint64_t* cgoff,
                            const uint32_t* gseq2, const uint32_t* gnmask, const uint64_t* goff, const uint64_t* glen,
                            uint32_t n_contig, uint64_t tot, hb_qhsp* out, cudaStream_t s);
-// star MSA + sparse-column removal fused: the clean matrices of all judge tasks (tasks >= n_full: truncated-member
-// matrices) straight from the edit records; calls[t].clean_cols is set.  The raw matrix is never written.
-cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* task_cand, uint32_t n_tasks, uint32_t n_full,
+// star MSA + sparse-column removal fused: the clean matrices of all judge tasks straight from the edit records, a CTA per
+// full task also producing its truncated-member task trunc_of_full[t] (-1: none); calls[].clean_cols is set for both.
+// The raw matrix is never written.
+cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* task_cand, const int32_t* trunc_of_full, uint32_t n_full,
                                 const HbLocus* pairs, const uint32_t* pair_off, const HbAln* alns, const uint32_t* qrec_unit_off,
                                 const uint32_t* qrec, const uint32_t* col_off, const uint32_t* colq, const uint32_t* gseq2,
                                 const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* clean, HbVoteCall* calls, cudaStream_t s);

@@ -641,10 +641,14 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
         ENSURE_L("v.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(n_tasks + 1));
         ENSURE_L("v.total", sizeof(uint64_t));
         ENSURE_L("v.task_cand", sizeof(uint32_t) * n_tasks);
+        ENSURE_L("v.f2t", sizeof(int32_t) * (n_full + 1));
+        std::vector<int32_t> trunc_of_full(n_full, -1);
+        for (uint32_t k = 0; k < trunc_to_full.size(); ++k) trunc_of_full[trunc_to_full[k]] = (int32_t)(n_full + k);
+        HB_CUDA_OK(cudaMemcpyAsync(LB("v.f2t").p, trunc_of_full.data(), sizeof(int32_t) * n_full, cudaMemcpyHostToDevice, s));
         HB_CUDA_OK(cudaMemcpyAsync(LB("v.tasks").p, tasks.data(), sizeof(HbVoteTask) * n_tasks, cudaMemcpyHostToDevice, s));
         HB_CUDA_OK(cudaMemcpyAsync(LB("v.task_cand").p, task_cand.data(), sizeof(uint32_t) * n_tasks, cudaMemcpyHostToDevice, s));
         HB_CUDA_OK(cudaMemsetAsync(LB("v.calls").p, 0, sizeof(HbVoteCall) * n_tasks, s));
-        HB_CUDA_OK(hb_msa_clean_launch(LB("v.tasks").as<HbVoteTask>(), LB("v.task_cand").as<uint32_t>(), n_tasks, n_full,
+        HB_CUDA_OK(hb_msa_clean_launch(LB("v.tasks").as<HbVoteTask>(), LB("v.task_cand").as<uint32_t>(), LB("v.f2t").as<int32_t>(), n_full,
                                        LB("p.pairs").as<HbLocus>(), LB("s.pair_off").as<uint32_t>(), LB("p.alns").as<HbAln>(),
                                        LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(), LB("m.col_off").as<uint32_t>(),
                                        LB("m.colq").as<uint32_t>(), ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(),

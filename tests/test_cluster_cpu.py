@@ -101,7 +101,7 @@ def test_command_line_of_the_reference(tmp_path, monkeypatch):
         for n, s in recs:
             f.write(">%s\n%s\n" % (n, s))
     ctx = OracleBackedCtx()
-    monkeypatch.setattr(cluster.boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(cluster.boundary, "get_context", lambda device=None, role="reference": ctx)
     rc = cluster.main("-aS 0.95 -aL 0.95 -c 0.8 -G 0 -g 1 -A 80 -i %s -o %s -T 0 -M 0" % (inp, out)).__int__() if False else \
         cluster.main(("-aS 0.95 -aL 0.95 -c 0.8 -G 0 -g 1 -A 80 -i %s -o %s -T 0 -M 0" % (inp, out)).split())
     assert rc == 0 and os.path.getsize(out) > 0 and os.path.exists(out + ".clstr")

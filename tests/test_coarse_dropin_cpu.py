@@ -97,7 +97,7 @@ def test_reference_coarse_stage_equals_mirror_on_the_same_hsps(tmp_path, monkeyp
             assert [(int(o["chr"]), int(o["start"]), int(o["end"])) for o in out] == iv
             return out
 
-    monkeypatch.setattr(coarse, "get_context", lambda device=None: OracleBackedCtx())
+    monkeypatch.setattr(coarse, "get_context", lambda device=None, role="reference": OracleBackedCtx())
     out_mine = str(tmp_path / "mine_longest_repeats_0.fa")
     coarse.determine_repeat_boundary_v5(cut, out_mine, None, skip_gap, 30000, str(tmp_path / "minework"), 4, 0, ref, 0)
 
@@ -187,7 +187,7 @@ def test_drop_in_script_runs_the_reference_stage_with_main_py_arguments(tmp_path
             out = np.zeros(len(iv), dtype=_lib.INTERVAL_DTYPE)
             out["chr"] = [c for c, _, _ in iv]; out["start"] = [a for _, a, _ in iv]; out["end"] = [b for _, _, b in iv]
             return out
-    monkeypatch.setattr(coarse, "get_context", lambda device=None: OracleBackedCtx())
+    monkeypatch.setattr(coarse, "get_context", lambda device=None, role="reference": OracleBackedCtx())
     monkeypatch.setenv("HITE_HOME", ref_import.REF_ROOT)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     monkeypatch.syspath_prepend(os.path.join(root, "module"))
@@ -258,7 +258,7 @@ def test_tandem_repeat_filter_is_the_references_own_code(tmp_path, monkeypatch, 
         def coarse_boundary(self, **kw):
             return np.zeros(0, dtype=coarse_lib.INTERVAL_DTYPE)
     from hite_b200 import _lib as coarse_lib
-    monkeypatch.setattr(coarse, "get_context", lambda device=None: Ctx())
+    monkeypatch.setattr(coarse, "get_context", lambda device=None, role="reference": Ctx())
     bindir = tmp_path / "bin"
     bindir.mkdir()
     p = bindir / "trf"

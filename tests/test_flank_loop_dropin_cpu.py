@@ -116,7 +116,7 @@ def test_reference_loop_equals_mirror_on_the_same_copies_and_msa(tmp_path, monke
 
     globals_plant = plant
     ctx = OracleBackedCtx()
-    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "get_context", lambda device=None, role="reference": ctx)
     monkeypatch.setattr(boundary, "ensure_genome", lambda c, r, k=15, w=10, _parsed=None: c)
     monkeypatch.setenv("HITE_GPU_DEVICES", "0")
     out_mine, low_mine = str(tmp_path / "mine_real.fa"), str(tmp_path / "mine_low.fa")
@@ -266,7 +266,7 @@ def test_reference_loop_with_more_than_100_copies_under_the_scripts_tie_rule(tmp
         def adjust(self, seqs, te, plant, result_type, flank=50):
             return [dict(verdicts[s]) for s in seqs]
     ctx = OracleBackedCtx()
-    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "get_context", lambda device=None, role="reference": ctx)
     monkeypatch.setattr(boundary, "ensure_genome", lambda c, r, k=15, w=10, _parsed=None: c)
     monkeypatch.setenv("HITE_GPU_DEVICES", "0")
     out_mine, low_mine = str(tmp_path / "mine_real.fa"), str(tmp_path / "mine_low.fa")
@@ -366,7 +366,7 @@ def test_low_copy_rescue_is_the_references_own_code(tmp_path, monkeypatch):
         def adjust(self, seqs, te, plant, result_type, flank=50):
             return [dict(verdicts[s]) for s in seqs]
     ctx = OracleBackedCtx()
-    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "get_context", lambda device=None, role="reference": ctx)
     monkeypatch.setattr(boundary, "ensure_genome", lambda c, r, k=15, w=10, _parsed=None: c)
     monkeypatch.setenv("HITE_GPU_DEVICES", "0")
     assert boundary._rescue_tools_missing(U, "tir") == []

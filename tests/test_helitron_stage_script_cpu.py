@@ -48,7 +48,7 @@ def test_helitron_stage_script_end_to_end(tmp_path, monkeypatch):
                            else dict(is_te=False, info="", cons="", copy_num=0))
             return res
     ctx = OracleBackedCtx()
-    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "get_context", lambda device=None, role="reference": ctx)
     monkeypatch.setattr(boundary, "ensure_genome", lambda c, r, k=15, w=10, _parsed=None: c)
     bindir = tmp_path / "bin"
     bindir.mkdir()

@@ -35,7 +35,7 @@ def test_itr_search_bit_exact_vs_oracle(ctx):
 
 def test_run_itrsearch_writes_the_references_files(ctx, tmp_path, monkeypatch):
     from hite_b200 import boundary, tir_prefilter as TP
-    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "get_context", lambda device=None, role="reference": ctx)
     comp = str.maketrans("ACGT", "TGCA")
     tir = "GTAGCCAGAAGGCTGCAACTC"
     recs = {"withTIR-C_0-tsd_TA-distance_0": tir + "ACGTTGCAAGGTCCAT" * 5 + tir.translate(comp)[::-1],

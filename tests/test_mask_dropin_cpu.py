@@ -51,7 +51,7 @@ def test_mirror_masked_genome_equals_reference_on_the_same_records(tmp_path, mon
             return dict(kernel_ms=0.0)
 
     ctx = OracleBackedCtx()
-    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "get_context", lambda device=None, role="reference": ctx)
     monkeypatch.setattr(boundary, "ensure_genome", lambda c, ref, k=15, w=10, _parsed=None: c)
     monkeypatch.setattr(boundary, "_GENOME", {})
     out = masking.mask_genome_with_TE(lpath, gpath, str(tmp_path), 4, 0, debug=0)

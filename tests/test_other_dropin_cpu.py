@@ -59,7 +59,7 @@ def test_run_other_detection_consumes_the_mirror(tmp_path, monkeypatch):
             return dict(kernel_ms=0.0, k_ms=[0.0] * 8)
 
     ctx = OracleBackedCtx()
-    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "get_context", lambda device=None, role="reference": ctx)
     monkeypatch.setattr(boundary, "ensure_genome", lambda c, ref, k=15, w=10, _parsed=None: c)
     # wire it the way module/_hite_b200_patch.run_stage does, then import the reference's stage module
     monkeypatch.setattr(U, "multi_process_align_and_get_copies", other.multi_process_align_and_get_copies)
@@ -120,7 +120,7 @@ def test_drop_in_script_runs_the_reference_other_stage_with_main_py_arguments(tm
         def timing(self):
             return dict(kernel_ms=0.0, k_ms=[0.0] * 8)
     ctx = OracleBackedCtx()
-    monkeypatch.setattr(boundary, "get_context", lambda device=None: ctx)
+    monkeypatch.setattr(boundary, "get_context", lambda device=None, role="reference": ctx)
     monkeypatch.setattr(boundary, "ensure_genome", lambda c, ref, k=15, w=10, _parsed=None: c)
     monkeypatch.setenv("HITE_HOME", ref_import.REF_ROOT)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
