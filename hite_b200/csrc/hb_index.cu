@@ -15,35 +15,87 @@
 namespace {
 
 // ---- S1: pack ---------------------------------------------------------------------------------
-// one thread per aligned 32-base group of the global coordinate space; the 64-base pads guarantee a
-// group intersects at most one contig.
-__global__ void pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ src_off,
-                            const uint64_t* __restrict__ goff, const uint64_t* __restrict__ glen, uint32_t n_contig,
-                            uint64_t tot, uint32_t* __restrict__ seq2, uint32_t* __restrict__ nmask) {
-    const uint64_t grp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t g0 = grp * 32;
-    if (g0 >= tot) return;
-    // last contig with goff <= g0 + 31
-    int lo = 0, hi = (int)n_contig;   // first contig with goff > g0+31
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (goff[mid] <= g0 + 31) lo = mid + 1; else hi = mid; }
-    const int c = lo - 1;
-    uint32_t w0 = 0, w1 = 0, nm = 0xffffffffu;
-    if (c >= 0) {
-        const uint64_t cs = goff[c], ce = cs + glen[c];
-        const uint8_t* src = ascii + src_off[c];
+// One thread per 16 bases = one seq2 word; a lane pair shares one N-mask word.  The 64-base pads guarantee that a word
+// intersects at most one contig.  A word that lies wholly inside its contig takes the fast path: its 16 ASCII bytes come
+// from TWO aligned 16-byte loads (LDG.128; the source of a contig is not 16-byte aligned with the packed space, so the
+// bytes are re-aligned with funnel shifts) and are classified four at a time in 32-bit registers: upper-casing by & 0xDF,
+// code = ((c >> 1) & 3) ^ (((c >> 1) & 3) >> 1) maps A C G T -> 0 1 2 3, validity by four byte-wise compares, and the
+// 4 x 2 code bits / 4 validity bits of a register are gathered by one multiply each.  Words cut by a contig boundary (two
+// per contig) and words in the pads take the byte path.
+__device__ __forceinline__ void pack4(uint32_t w, uint32_t* code8, uint32_t* valid4) {
+    const uint32_t u = w & 0xDFDFDFDFu;
+    const uint32_t x = (u >> 1) & 0x03030303u;
+    const uint32_t c = x ^ ((x >> 1) & 0x01010101u);
+    *code8 = (c * 0x01041040u) >> 24;                     // b0 | b1 << 2 | b2 << 4 | b3 << 6
+    const uint32_t v = (__vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u)) &
+                       0x01010101u;
+    *valid4 = ((v * 0x01020408u) >> 24) & 0xFu;           // bit i = byte i is one of A C G T (either case)
+}
+__device__ __forceinline__ uint4 ldg128(const uint4* p) {      // one LDG.E.128 (the compiler otherwise splits it into two 64-bit loads)
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ goff,
+            const uint64_t* __restrict__ glen, uint32_t n_contig, uint64_t tot, uint32_t* __restrict__ seq2,
+            uint32_t* __restrict__ nmask) {
+    const uint64_t wq = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // seq2 word
+    const uint64_t g0 = wq * 16;
+    uint32_t word = 0, nm16 = 0xFFFFu;
+    if (g0 < tot) {
+        int lo = 0, hi = (int)n_contig;                   // last contig with goff <= g0 + 15
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (goff[mid] <= g0 + 15) lo = mid + 1; else hi = mid; }
+        const int c = lo - 1;
+        if (c >= 0) {
+            const uint64_t cs = goff[c], ce = cs + glen[c];
+            const uint8_t* src = ascii + src_off[c];
+            if (g0 >= cs && g0 + 16 <= ce) {
+                const uint8_t* p = src + (g0 - cs);
+                const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+                const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+                const uint4 v0 = ldg128(q);
+                const int sh = (int)(a & 15);
+                uint32_t w0 = v0.x, w1 = v0.y, w2 = v0.z, w3 = v0.w;
+                if (sh) {                                 // bytes sh .. sh + 15 of the 32 loaded (the upload buffer has 16 B of slack)
+                    const uint4 v1 = ldg128(q + 1);
+                    const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    const int qw = sh >> 2, bs = 8 * (sh & 3);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        uint32_t lo32 = 0, hi32 = 0;
+#pragma unroll
+                        for (int z = 0; z < 4; ++z) { if (qw == z) { lo32 = r[z + t]; hi32 = r[z + t + 1]; } }
+                        const uint32_t o = __funnelshift_r(lo32, hi32, bs);
+                        if (t == 0) w0 = o; else if (t == 1) w1 = o; else if (t == 2) w2 = o; else w3 = o;
+                    }
+                }
+                uint32_t c0, c1, c2, c3, k0, k1, k2, k3;
+                pack4(w0, &c0, &k0); pack4(w1, &c1, &k1); pack4(w2, &c2, &k2); pack4(w3, &c3, &k3);
+                const uint32_t valid = k0 | (k1 << 4) | (k2 << 8) | (k3 << 12);
+                // codes of invalid bytes are cleared like the byte path leaves them (0)
+                uint32_t spread = valid;                  // 16 validity bits -> 2 bits each
+                spread = (spread | (spread << 8)) & 0x00FF00FFu;
+                spread = (spread | (spread << 4)) & 0x0F0F0F0Fu;
+                spread = (spread | (spread << 2)) & 0x33333333u;
+                spread = (spread | (spread << 1)) & 0x55555555u;
+                word = (c0 | (c1 << 8) | (c2 << 16) | (c3 << 24)) & (spread | (spread << 1));
+                nm16 = ~valid & 0xFFFFu;
+            } else {
 #pragma unroll 4
-        for (int b = 0; b < 32; ++b) {
-            const uint64_t p = g0 + b;
-            if (p >= cs && p < ce) {
-                const int s = hb_sym_of_ascii(src[p - cs]);
-                if (s < 4) {
-                    nm &= ~(1u << b);
-                    if (b < 16) w0 |= (uint32_t)s << (2 * b); else w1 |= (uint32_t)s << (2 * (b - 16));
+                for (int b = 0; b < 16; ++b) {
+                    const uint64_t p = g0 + b;
+                    if (p >= cs && p < ce) {
+                        const int sy = hb_sym_of_ascii(src[p - cs]);
+                        if (sy < 4) { nm16 &= ~(1u << b); word |= (uint32_t)sy << (2 * b); }
+                    }
                 }
             }
         }
+        seq2[wq] = word;
     }
-    seq2[grp * 2] = w0; seq2[grp * 2 + 1] = w1; nmask[grp] = nm;
+    const uint32_t other = __shfl_xor_sync(HB_FULL, nm16, 1);
+    if (!(threadIdx.x & 1) && g0 < tot) nmask[wq >> 1] = nm16 | (other << 16);
 }
 
 // ---- known-TE masking: N-fill of [start, end) intervals (mask_genome_intactTE, module/Util.py:6414-6420) -------------
@@ -255,9 +307,9 @@ __global__ void bucket_count_kernel(const uint64_t* __restrict__ idx, uint64_t n
 cudaError_t hb_pack_launch(const uint8_t* d_ascii, const uint64_t* d_src_off, const uint64_t* d_goff,
                            const uint64_t* d_glen, uint32_t n_contig, uint64_t tot, uint32_t* d_seq2,
                            uint32_t* d_nmask, cudaStream_t s) {
-    const uint64_t groups = tot / 32;
-    pack_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, s>>>(d_ascii, d_src_off, d_goff, d_glen, n_contig, tot,
-                                                                  d_seq2, d_nmask);
+    const uint64_t words = tot / 16;                      // tot is a multiple of 64
+    pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(d_ascii, d_src_off, d_goff, d_glen, n_contig, tot,
+                                                                 d_seq2, d_nmask);
     return cudaGetLastError();
 }
 
