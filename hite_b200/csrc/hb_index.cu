@@ -297,9 +297,15 @@ minimizer_kernel(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__
 }
 
 // ---- bucket table over the sorted index ----------------------------------------------------------
-__global__ void bucket_count_kernel(const uint64_t* __restrict__ idx, uint64_t n, int shift, uint32_t* __restrict__ cnt) {
+// bucket[b] = first index entry whose hash prefix is >= b.  The index is sorted, so entry i opens every bucket in
+// (prefix(i-1), prefix(i)]: one pass, each table entry written exactly once, no atomics (the counting version spent
+// 22 ms of a 2.3 Gbp build on atomic increments of hot buckets).  Thread n closes the table up to bucket nb.
+__global__ void bucket_bounds_kernel(const uint64_t* __restrict__ idx, uint64_t n, int shift, uint32_t nb, uint32_t* __restrict__ bucket) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[(uint32_t)(idx[i] >> shift)], 1u);
+    if (i > n) return;
+    const int64_t prev = i > 0 ? (int64_t)(idx[i - 1] >> shift) : -1;
+    const int64_t cur = i < n ? (int64_t)(idx[i] >> shift) : (int64_t)nb;
+    for (int64_t b = prev + 1; b <= cur; ++b) bucket[b] = (uint32_t)i;
 }
 
 }  // namespace
@@ -327,9 +333,8 @@ cudaError_t hb_minimizer_write_launch(const uint32_t* d_seq2, const uint32_t* d_
                                                                          d_cta_base, d_out);
     return cudaGetLastError();
 }
-cudaError_t hb_bucket_count_launch(const uint64_t* d_idx, uint64_t n, int shift, uint32_t* d_cnt, cudaStream_t s) {
-    if (n == 0) return cudaSuccess;
-    bucket_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_idx, n, shift, d_cnt);
+cudaError_t hb_bucket_bounds_launch(const uint64_t* d_idx, uint64_t n, int shift, uint32_t nb, uint32_t* d_bucket, cudaStream_t s) {
+    bucket_bounds_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(d_idx, n, shift, nb, d_bucket);
     return cudaGetLastError();
 }
 cudaError_t hb_mask_fill_launch(const int32_t* d_contig, const int64_t* d_start, const int64_t* d_end, uint32_t n,

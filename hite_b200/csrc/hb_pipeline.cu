@@ -194,7 +194,6 @@ extern "C" int hb_index_build(hb_ctx* ctx, int k, int w) {
     ENSURE("g.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(std::max<uint64_t>(ctas, (1u << HB_SEED_BUCKET_BITS) + 1)));
     ENSURE("g.total", sizeof(uint64_t));
     const uint32_t nb = 1u << HB_SEED_BUCKET_BITS;
-    ENSURE("g.bucket_cnt", sizeof(uint32_t) * (nb + 1));
     ENSURE("g.bucket", sizeof(uint32_t) * (nb + 1));
     // events bracket kernels only: buffer (re)allocation sits between the intervals, outside every stage time
     HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
@@ -223,10 +222,7 @@ extern "C" int hb_index_build(hb_ctx* ctx, int k, int w) {
                                  ctx->buf("g.sort_tmp").as<uint32_t>(), &sorted, &launches, s));
     HB_CUDA_OK(cudaEventRecord(ctx->ev[4], s));
     // bucket table on the top HB_SEED_BUCKET_BITS bits of a 30-bit hash (hash < 4^k <= 2^30)
-    HB_CUDA_OK(cudaMemsetAsync(ctx->buf("g.bucket_cnt").p, 0, sizeof(uint32_t) * (nb + 1), s));
-    HB_CUDA_OK(hb_bucket_count_launch(sorted, n_mm, 33 + (30 - HB_SEED_BUCKET_BITS), ctx->buf("g.bucket_cnt").as<uint32_t>(), s));
-    HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("g.bucket_cnt").as<uint32_t>(), ctx->buf("g.bucket").as<uint32_t>(), nb + 1,
-                                     ctx->buf("g.scan_tmp").as<uint32_t>(), nullptr, s));
+    HB_CUDA_OK(hb_bucket_bounds_launch(sorted, n_mm, 33 + (30 - HB_SEED_BUCKET_BITS), nb, ctx->buf("g.bucket").as<uint32_t>(), s));
     HB_CUDA_OK(cudaEventRecord(ctx->ev[5], s));
     HB_CUDA_OK(cudaStreamSynchronize(s));
     if (sorted != ctx->buf("g.idx_a").as<uint64_t>()) std::swap(ctx->bufs["g.idx_a"], ctx->bufs["g.idx_b"]);

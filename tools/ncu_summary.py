@@ -64,5 +64,39 @@ def full(path, out, cmd):
             f.write("\n")
 
 
+def table(path, out, cmd, peak=6540.5):
+    """One row per captured launch from `ncu -i x.ncu-rep --page raw --csv` output (a .csv, made on the GPU box so the .ncu-rep
+    need not travel): duration, DRAM bytes, achieved DRAM GB/s and its fraction of the MEASURED HBM peak, pipe / issue / occupancy."""
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tm = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3}
+
+    def g(r, k):
+        try:
+            i = hdr.index(k)
+            return float(r[i].replace(",", "")), units[i]
+        except Exception:
+            return float("nan"), ""
+    with open(out, "w") as f:
+        f.write("# ncu --set full --clock-control none, one row per captured launch\n\ncommand: `%s`\n\n" % cmd)
+        f.write("achieved = (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration.sum; peak = %.1f GB/s (MEASURED_PEAKS.json hbm_gbs)\n\n" % peak)
+        f.write("| kernel | ms | DRAM read MB | DRAM write MB | achieved GB/s | of measured HBM | DRAM % | SM % | ALU pipe % | issue % | warps active % | regs | grid |\n")
+        f.write("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+            t, u = g(r, "gpu__time_duration.sum"); t *= tm.get(u, 1)
+            rd, u1 = g(r, "dram__bytes_read.sum"); rd *= mult.get(u1, 1)
+            wr, u2 = g(r, "dram__bytes_write.sum"); wr *= mult.get(u2, 1)
+            gbs = (rd + wr) / 1e9 / (t * 1e-3) if t else 0.0
+            f.write("| %s | %.3f | %.1f | %.1f | %.0f | %.3f | %.1f | %.1f | %.1f | %.1f | %.1f | %d | %d |\n" % (
+                name, t, rd / 1e6, wr / 1e6, gbs, gbs / peak, g(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")[0],
+                g(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed")[0],
+                g(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")[0],
+                g(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")[0],
+                g(r, "sm__warps_active.avg.pct_of_peak_sustained_active")[0], g(r, "launch__registers_per_thread")[0],
+                g(r, "launch__grid_size")[0]))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    {"launches": launches, "full": full, "table": table}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
