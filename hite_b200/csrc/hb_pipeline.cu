@@ -1181,13 +1181,6 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     // this part's query segments: the files [n_files * part / n_parts, n_files * (part + 1) / n_parts), a contiguous
     // range of the padded coordinate space
     const uint32_t f_lo = (uint32_t)((uint64_t)n_files * part / n_parts), f_hi = (uint32_t)((uint64_t)n_files * (part + 1) / n_parts);
-    int g_lo = n_seg, g_hi = n_seg;
-    for (int g = 0; g < n_seg; ++g) {
-        if (file_of_seg[(size_t)g] >= f_lo && g_lo == n_seg) g_lo = g;
-        if (file_of_seg[(size_t)g] >= f_hi) { g_hi = g; break; }
-    }
-    const uint64_t qpos_lo = g_lo < n_seg ? seg_goff[(size_t)g_lo] : ctx->g_tot;
-    const uint64_t qpos_hi = g_hi < n_seg ? seg_goff[(size_t)g_hi] : ctx->g_tot;
     ENSURE("h.seg_goff", sizeof(uint64_t) * (n_seg + 1));
     ENSURE("h.seg_len", sizeof(uint64_t) * (n_seg + 1));
     std::vector<uint64_t> seg_lens((size_t)n_seg);
@@ -1198,19 +1191,31 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     ENSURE("h.lo", sizeof(uint32_t) * (n_mm + 1)); ENSURE("h.cnt", sizeof(uint32_t) * (n_mm + 1)); ENSURE("h.off", sizeof(uint32_t) * (n_mm + 1));
     ENSURE("h.scan_tmp", sizeof(uint32_t) * hb_scan_tmp_words(n_mm + 1));
     ENSURE("h.total", sizeof(uint64_t));
-    HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
-    HB_CUDA_OK(hb_pair_count_launch(ctx->buf("g.mm_pos").as<uint64_t>(), n_mm, ctx->buf("g.idx_a").as<uint64_t>(),
-                                    ctx->buf("g.bucket").as<uint32_t>(), occ_cap, qpos_lo, qpos_hi, ctx->buf("h.lo").as<uint32_t>(),
-                                    ctx->buf("h.cnt").as<uint32_t>(), s));
-    HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("h.cnt").as<uint32_t>(), ctx->buf("h.off").as<uint32_t>(), n_mm,
-                                     ctx->buf("h.scan_tmp").as<uint32_t>(), ctx->buf("h.total").as<uint64_t>(), s));
-    uint64_t n_pairs = 0;
-    HB_CUDA_OK(cudaMemcpyAsync(&n_pairs, ctx->buf("h.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    HB_CUDA_OK(cudaStreamSynchronize(s));
-    launches += 4;
-    if (n_pairs >= (1ull << 32)) return hb_fail_msg(ctx, HB_ENOMEM, "hb_coarse_boundary: more than 2^32 seed pairs; lower occ_cap");
-    std::vector<HbHspRec> h_recs;
-    if (n_pairs > 0) {
+    uint64_t n_pairs_total = 0;
+    // ---- GPU half of one block of files [fb_lo, fb_hi): seed pairs -> sort -> runs -> base-level HSPs, read back ----
+    auto gpu_block = [&](uint32_t fb_lo, uint32_t fb_hi, std::vector<HbHspRec>& h_recs) -> int {
+        int g_lo = n_seg, g_hi = n_seg;
+        for (int g = 0; g < n_seg; ++g) {
+            if (file_of_seg[(size_t)g] >= fb_lo && g_lo == n_seg) g_lo = g;
+            if (file_of_seg[(size_t)g] >= fb_hi) { g_hi = g; break; }
+        }
+        const uint64_t qpos_lo = g_lo < n_seg ? seg_goff[(size_t)g_lo] : ctx->g_tot;
+        const uint64_t qpos_hi = g_hi < n_seg ? seg_goff[(size_t)g_hi] : ctx->g_tot;
+        h_recs.clear();
+        if (qpos_hi <= qpos_lo) return HB_OK;
+        HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+        HB_CUDA_OK(hb_pair_count_launch(ctx->buf("g.mm_pos").as<uint64_t>(), n_mm, ctx->buf("g.idx_a").as<uint64_t>(),
+                                        ctx->buf("g.bucket").as<uint32_t>(), occ_cap, qpos_lo, qpos_hi, ctx->buf("h.lo").as<uint32_t>(),
+                                        ctx->buf("h.cnt").as<uint32_t>(), s));
+        HB_CUDA_OK(hb_exclusive_scan_u32(ctx->buf("h.cnt").as<uint32_t>(), ctx->buf("h.off").as<uint32_t>(), n_mm,
+                                         ctx->buf("h.scan_tmp").as<uint32_t>(), ctx->buf("h.total").as<uint64_t>(), s));
+        uint64_t n_pairs = 0;
+        HB_CUDA_OK(cudaMemcpyAsync(&n_pairs, ctx->buf("h.total").p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(cudaStreamSynchronize(s));
+        launches += 4;
+        if (n_pairs >= (1ull << 32)) return hb_fail_msg(ctx, HB_ENOMEM, "hb_coarse_boundary: more than 2^32 seed pairs; lower occ_cap");
+        n_pairs_total += n_pairs;
+        if (n_pairs == 0) return HB_OK;
         ENSURE("h.keys_a", sizeof(uint64_t) * n_pairs); ENSURE("h.keys_b", sizeof(uint64_t) * n_pairs);
         ENSURE("h.sort_tmp", sizeof(uint32_t) * hb_sort_tmp_words(n_pairs));
         HB_CUDA_OK(hb_pair_fill_launch(ctx->buf("g.mm_pos").as<uint64_t>(), n_mm, ctx->buf("g.idx_a").as<uint64_t>(), ctx->g_nmm,
@@ -1257,29 +1262,68 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
         if (n_hsp) HB_CUDA_OK(cudaMemcpyAsync(h_recs.data(), ctx->buf("h.out").p, sizeof(HbHspRec) * n_hsp, cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
         launches += 12;
-        tm.d2h_bytes = sizeof(HbHspRec) * n_hsp;
-        cudaEventElapsedTime(&tm.k_ms[0], ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&tm.k_ms[1], ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&tm.k_ms[2], ctx->ev[2], ctx->ev[3]);
-        cudaEventElapsedTime(&tm.kernel_ms, ctx->ev[0], ctx->ev[3]);
+        tm.d2h_bytes += sizeof(HbHspRec) * n_hsp;
+        float a = 0.f, b = 0.f, c = 0.f;
+        cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+        tm.k_ms[0] += a; tm.k_ms[1] += b; tm.k_ms[2] += c; tm.kernel_ms += a + b + c;
+        return HB_OK;
+    };
+    // ---- host half of one block: HSPs grouped by query segment (stable: the "file order" of a query is the sorted-key
+    // order), FMEA over the block's files on `threads` host threads ----
+    struct Block { std::vector<hb_hsp> hsps; std::vector<uint64_t> off; std::vector<hb_interval> res; double fmea_ms = 0.0; };
+    auto group_block = [&](const std::vector<HbHspRec>& h_recs, Block& B) {
+        B.off.assign((size_t)n_seg + 1, 0);
+        for (const HbHspRec& r : h_recs) B.off[(size_t)r.qseg + 1]++;
+        for (int g = 0; g < n_seg; ++g) B.off[(size_t)g + 1] += B.off[(size_t)g];
+        B.hsps.resize(h_recs.size());
+        std::vector<uint64_t> cur(B.off.begin(), B.off.end() - 1);
+        for (const HbHspRec& r : h_recs) B.hsps[cur[(size_t)r.qseg]++] = hb_hsp{r.subj, r.qs, r.qe, r.ss, r.se};
+    };
+    auto fmea_block = [&](Block& B) {
+        auto t0 = std::chrono::steady_clock::now();
+        hb_fmea_run(B.hsps.data(), B.off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, B.res, file_of_seg.data());
+        B.fmea_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    // The part's files in up to 4 blocks, software-pipelined: while the host threads chain block b (FMEA is the longer
+    // half), the GPU already produces the HSPs of block b + 1.  A block is made of whole files, so its chaining is independent.
+    auto t_all = std::chrono::steady_clock::now();
+    const uint32_t nf = f_hi - f_lo;
+    const uint32_t n_blocks = nf >= 8 ? 4u : 1u;
+    std::vector<Block> blocks(n_blocks);
+    std::vector<HbHspRec> h_recs;
+    std::thread worker;
+    int rc_gpu = HB_OK;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        const uint32_t fb_lo = f_lo + (uint32_t)((uint64_t)nf * b / n_blocks), fb_hi = f_lo + (uint32_t)((uint64_t)nf * (b + 1) / n_blocks);
+        rc_gpu = gpu_block(fb_lo, fb_hi, h_recs);
+        if (rc_gpu != HB_OK) break;
+        group_block(h_recs, blocks[b]);
+        if (worker.joinable()) worker.join();
+        worker = std::thread(fmea_block, std::ref(blocks[b]));
     }
-    // group by query segment, stable (the "file order" of each query is the sorted-key order)
+    if (worker.joinable()) worker.join();
+    if (rc_gpu != HB_OK) return rc_gpu;
+    // the getters see the whole part: HSPs grouped by query segment, intervals in block (= query-segment) order
     ctx->last_hsp_off.assign((size_t)n_seg + 1, 0);
-    for (const HbHspRec& r : h_recs) ctx->last_hsp_off[(size_t)r.qseg + 1]++;
-    for (int g = 0; g < n_seg; ++g) ctx->last_hsp_off[g + 1] += ctx->last_hsp_off[g];
-    ctx->last_hsps.resize(h_recs.size());
+    size_t n_all = 0;
+    for (const Block& B : blocks) { n_all += B.hsps.size(); for (int g = 0; g <= n_seg; ++g) ctx->last_hsp_off[(size_t)g] += B.off[(size_t)g]; }
+    ctx->last_hsps.resize(n_all);
     {
         std::vector<uint64_t> cur(ctx->last_hsp_off.begin(), ctx->last_hsp_off.end() - 1);
-        for (const HbHspRec& r : h_recs) ctx->last_hsps[cur[r.qseg]++] = hb_hsp{r.subj, r.qs, r.qe, r.ss, r.se};
+        for (const Block& B : blocks)
+            for (int g = 0; g < n_seg; ++g)
+                for (uint64_t i = B.off[(size_t)g]; i < B.off[(size_t)g + 1]; ++i) ctx->last_hsps[cur[(size_t)g]++] = B.hsps[i];
     }
     ctx->last_segs = segs;
-    auto t0 = std::chrono::steady_clock::now();
     std::vector<hb_interval> res;
-    hb_fmea_run(ctx->last_hsps.data(), ctx->last_hsp_off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, res,
-                file_of_seg.data());
-    tm.k_ms[3] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    tm.k_ms[6] = (float)h_recs.size();
-    tm.k_ms[7] = (float)((double)n_pairs * 1e-6);
+    double fmea_ms = 0.0;
+    for (const Block& B : blocks) { res.insert(res.end(), B.res.begin(), B.res.end()); fmea_ms += B.fmea_ms; }
+    tm.k_ms[3] = (float)fmea_ms;                                                    // host FMEA, summed over the blocks
+    tm.k_ms[4] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_all).count();   // wall of the pipelined stage
+    tm.k_ms[6] = (float)n_all;
+    tm.k_ms[7] = (float)((double)n_pairs_total * 1e-6);
     tm.launches = launches;
     ctx->last_intervals = res;                       // kept: hb_last_intervals fetches them without a second run
     *n_out = res.size();

@@ -210,40 +210,63 @@ rank_select_kernel(const uint64_t* __restrict__ hits, uint64_t n_hits, const uin
                 }
             }
         } else {
-        // more valid clusters than the shared-memory buffer holds: rank against global memory
-        nvalid = 0;
-        for (uint32_t x0 = first; x0 < end; x0 += 32) {
-            const uint32_t x = x0 + lane;
-            bool valid = false;
-            uint32_t nx = 0, relx = 0; int64_t dminx = 0;
-            if (x < end) {
-                nx = cl_n(x);
-                valid = nx >= HB_MIN_SEEDS;
-                const uint64_t k0 = hits[cl_start[x]];
-                relx = (uint32_t)((k0 >> 46) & 1); dminx = (int64_t)((k0 >> 13) & 0x1FFFFFFFFull);
+            // More valid clusters than the shared-memory buffer holds (families with thousands of copies): only the best
+            // max_loci matter, so first find the seed-count threshold T with  #{n > T} < max_loci <= #{n >= T}  by bisection
+            // (each probe is one strided pass over the clusters), then collect every cluster with n > T and, in array
+            // order -- which is (strand, first diagonal) order, the tie-break of the ranking -- the first clusters with
+            // n == T that still fit.  The <= max_loci collected keys are ranked in shared memory like the small case:
+            // the result equals the full O(n^2) ranking.
+            auto count_ge = [&](uint32_t T) -> uint32_t {
+                uint32_t cnt = 0;
+                for (uint32_t x = first + lane; x < end; x += 32) cnt += cl_n(x) >= T ? 1u : 0u;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(HB_FULL, cnt, o);
+                return cnt;
+            };
+            uint32_t lo = HB_MIN_SEEDS, hi = 1u << 20;                  // invariant: count_ge(lo) >= max_loci > count_ge(hi)
+            while (hi - lo > 1) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if (count_ge(mid) >= (uint32_t)max_loci) lo = mid; else hi = mid;
             }
-            uint32_t rank = 0;
-            if (valid) {
-                for (uint32_t y = first; y < end; ++y) {
-                    if (y == x) continue;
-                    const uint32_t ny = cl_n(y);
-                    if (ny < HB_MIN_SEEDS) continue;
-                    const uint64_t k1 = hits[cl_start[y]];
-                    const uint32_t rely = (uint32_t)((k1 >> 46) & 1); const int64_t dminy = (int64_t)((k1 >> 13) & 0x1FFFFFFFFull);
-                    const bool better = (ny != nx) ? (ny > nx) : ((rely != relx) ? (rely < relx) : (dminy < dminx));
-                    rank += better ? 1u : 0u;
+            const uint32_t T = lo;
+            const uint32_t n_gt = count_ge(T + 1);
+            const uint32_t need_eq = (uint32_t)max_loci - n_gt;
+            uint32_t m = 0, taken_eq = 0;
+            for (uint32_t x0 = first; x0 < end; x0 += 32) {
+                const uint32_t x = x0 + lane;
+                uint32_t nx = 0;
+                uint64_t key = 0;
+                if (x < end) {
+                    nx = cl_n(x);
+                    const uint64_t k0 = hits[cl_start[x]];
+                    key = ((uint64_t)(0xFFFFFFFFu - nx) << 34) | (((k0 >> 46) & 1ull) << 33) | ((k0 >> 13) & 0x1FFFFFFFFull);
                 }
-                if (rank < (uint32_t)max_loci) {
-                    const uint64_t e = (x + 1 < n_cl) ? cl_start[x + 1] : n_hits;
-                    HbLocus L;
-                    L.cand = c; L.rel = relx; L.nseeds = nx; L.rank = rank;
-                    locus_band(hits, cl_start[x], e, &L);
-                    loci[(size_t)c * max_loci + rank] = L;
-                }
+                const bool gt = x < end && nx > T, eq = x < end && nx == T;
+                const uint32_t bal_eq = __ballot_sync(HB_FULL, eq);
+                const bool take_eq = eq && (taken_eq + __popc(bal_eq & ((1u << lane) - 1u)) < need_eq);
+                const bool take = gt || take_eq;
+                const uint32_t bal = __ballot_sync(HB_FULL, take);
+                const uint32_t pos = m + __popc(bal & ((1u << lane) - 1u));
+                if (take) { keys[pos] = key; kcl[pos] = x; }
+                m += __popc(bal);
+                taken_eq += __popc(bal_eq);
             }
-            nvalid += __popc(__ballot_sync(HB_FULL, valid));
+            __syncwarp();
+            for (uint32_t v0 = 0; v0 < m; v0 += 32) {
+                const uint32_t v = v0 + lane;
+                if (v >= m) continue;
+                const uint64_t kx = keys[v];
+                uint32_t rank = 0;
+                for (uint32_t y = 0; y < m; ++y) rank += keys[y] < kx ? 1u : 0u;
+                const uint32_t x = kcl[v];
+                const uint64_t e = (x + 1 < n_cl) ? cl_start[x + 1] : n_hits;
+                HbLocus L;
+                L.cand = c; L.rel = (uint32_t)((kx >> 33) & 1ull); L.nseeds = 0xFFFFFFFFu - (uint32_t)(kx >> 34);
+                L.rank = rank;
+                locus_band(hits, cl_start[x], e, &L);
+                loci[(size_t)c * max_loci + rank] = L;
+            }
         }
-    }
         }
     if (lane == 0) n_loci[c] = min(nvalid, (uint32_t)max_loci);
 }

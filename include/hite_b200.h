@@ -269,7 +269,8 @@ int hb_genome_export(hb_ctx* ctx, uint32_t contig, uint8_t* out_ascii, uint64_t 
  * runs of 1 Mbp segments) as one self-join of the minimizer index on the GPU (seed pairs -> radix sort ->
  * exact-diagonal runs = HSPs), followed by hb_fmea_chain.  Uses the genome + index of the context; segments
  * are seg_len-long pieces of each contig (chrom_seg_length, main.py:41).  Two-call like hb_fmea_chain.
- * Timing: k_ms[0] pair count+fill, [1] sort, [2] HSP extraction, [3] host FMEA (wall), [6] #HSPs, [7] million seed pairs.
+ * Timing: k_ms[0] pair count+fill, [1] sort, [2] HSP extraction, [3] host FMEA (summed over its blocks), [4] wall of the
+ * whole stage (the GPU half of block b + 1 runs while the host chains block b), [6] #HSPs, [7] million seed pairs.
  */
 int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
                        hb_interval* out, uint64_t cap, uint64_t* n_out);
