@@ -196,6 +196,7 @@ def load():
     lib.hb_last_cons.argtypes = [vp, vp, C.c_uint64]
     lib.hb_last_cons_device.argtypes = [vp, C.POINTER(vp), u64p]
     lib.hb_last_copies.argtypes = [vp, vp, C.c_uint64, u64p]
+    lib.hb_last_pair_counts.argtypes = [vp, vp, C.c_uint32]
     lib.hb_debug_index.argtypes = [vp, vp, C.c_uint64]
     lib.hb_debug_scan_total.argtypes = [vp, C.c_uint64, C.c_uint32, u64p, C.POINTER(C.c_uint32)]
     lib.hb_last_msa.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
@@ -417,6 +418,12 @@ class Context:
             __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "|u1", "data": (int(p.value), False),
                                         "version": 2}
         return _Dev()
+
+    def last_pair_counts(self, n_cand):
+        """loci aligned per candidate in the last adjust (``hb_last_pair_counts``): x length = the cost of a candidate"""
+        out = np.zeros(max(1, int(n_cand)), dtype=np.uint32)
+        self._check(self._lib.hb_last_pair_counts(self._h, _ptr(out), len(out)), "hb_last_pair_counts")
+        return out[:int(n_cand)]
 
     def last_copies(self):
         n = C.c_uint64(0)

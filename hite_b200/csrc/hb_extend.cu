@@ -81,8 +81,7 @@ extend_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair
     pr.cand = 0; pr.rel = 0; pr.j0 = 0; pr.dmin = 0; pr.dmax = 0; pr.nseeds = 0; pr.rank = 0;
     if (active) {
         pr = pairs[p];
-        const bool narrow = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD;
-        active = ((HB == 16) ? narrow : !narrow) && (int)clen[pr.cand] > hb16::HB16_MAX_L;
+        active = (int)clen[pr.cand] > hb16::HB16_MAX_L && hb16::half_band(pr.dmax - pr.dmin, (int)clen[pr.cand]) == HB;
     }
     if (!__ballot_sync(HB_FULL, active)) return;
     const int L = active ? (int)clen[pr.cand] : 0;
@@ -230,24 +229,28 @@ extend16_kernel(const uint32_t* __restrict__ order, const uint64_t* __restrict__
                             tb_unit_off, tb_unit_base, tbuf, alns, s_rq + wid * PPW * WIN, s_rt + wid * PPW * WIN);
 }
 
-// class of every pair of [pair_lo, pair_hi): flag arrays for the two order lists
+// class of every pair of [pair_lo, pair_hi): flag arrays for the three order lists (tight / narrow / wide band)
 __global__ void order_flag_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi,
-                                  const uint32_t* __restrict__ clen, uint32_t* __restrict__ flag_n,
+                                  const uint32_t* __restrict__ clen, uint32_t* __restrict__ flag_t, uint32_t* __restrict__ flag_n,
                                   uint32_t* __restrict__ flag_w) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair_lo + t >= pair_hi) return;
     const HbLocus pr = pairs[pair_lo + t];
-    const bool fits = (int)clen[pr.cand] <= hb16::HB16_MAX_L;
-    const bool narrow = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD;
-    flag_n[t] = (fits && narrow) ? 1u : 0u;
-    flag_w[t] = (fits && !narrow) ? 1u : 0u;
+    const int L = (int)clen[pr.cand];
+    const bool fits = L <= hb16::HB16_MAX_L;
+    const int hb = hb16::half_band(pr.dmax - pr.dmin, L);
+    flag_t[t] = (fits && hb == 8) ? 1u : 0u;
+    flag_n[t] = (fits && hb == 16) ? 1u : 0u;
+    flag_w[t] = (fits && hb == 32) ? 1u : 0u;
 }
-__global__ void order_scatter_kernel(uint32_t pair_lo, uint32_t n, const uint32_t* __restrict__ flag_n,
-                                     const uint32_t* __restrict__ flag_w, const uint32_t* __restrict__ off_n,
-                                     const uint32_t* __restrict__ off_w, uint32_t* __restrict__ order_n,
-                                     uint32_t* __restrict__ order_w) {
+__global__ void order_scatter_kernel(uint32_t pair_lo, uint32_t n, const uint32_t* __restrict__ flag_t,
+                                     const uint32_t* __restrict__ flag_n, const uint32_t* __restrict__ flag_w,
+                                     const uint32_t* __restrict__ off_t, const uint32_t* __restrict__ off_n,
+                                     const uint32_t* __restrict__ off_w, uint32_t* __restrict__ order_t,
+                                     uint32_t* __restrict__ order_n, uint32_t* __restrict__ order_w) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    if (flag_t[t]) order_t[off_t[t]] = pair_lo + t;
     if (flag_n[t]) order_n[off_n[t]] = pair_lo + t;
     if (flag_w[t]) order_w[off_w[t]] = pair_lo + t;
 }
@@ -255,12 +258,12 @@ __global__ void order_scatter_kernel(uint32_t pair_lo, uint32_t n, const uint32_
 // Traceback: ONE THREAD per pair (the walk is inherently serial; 32 independent walks per warp keep
 // the issue slots full where a warp-per-pair walk leaves 31 lanes idle).
 __global__ void __launch_bounds__(128)
-traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi,
+traceback_kernel(const HbLocus* __restrict__ pairs, uint32_t pair_lo, uint32_t pair_hi, const uint32_t* __restrict__ clen,
                  const uint32_t* __restrict__ tb_unit_off, uint32_t tb_unit_base, const uint32_t* __restrict__ tbuf,
                  const uint32_t* __restrict__ qrec_unit_off, uint32_t* __restrict__ qrec, HbAln* __restrict__ alns) {
     const uint32_t p = pair_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= pair_hi) return;
-    hb16::traceback_pair(p, pairs, tb_unit_off, tb_unit_base, tbuf, qrec_unit_off, qrec, alns);
+    hb16::traceback_pair(p, pairs, clen, tb_unit_off, tb_unit_base, tbuf, qrec_unit_off, qrec, alns);
 }
 
 // sizes: tb units (512 B = 64 steps x 16 lanes x 4 bit) and qrec units (32 words) per pair
@@ -270,8 +273,8 @@ __global__ void pair_sizes_kernel(const HbLocus* __restrict__ pairs, uint32_t n_
     if (p >= n_pairs) return;
     const HbLocus pr = pairs[p];
     const uint32_t L = clen[pr.cand];
-    const uint32_t hb = (pr.dmax - pr.dmin) <= HB_NARROW_SPREAD ? 16u : 32u;
-    tb_units[p] = ((2 * L + 2 * hb - 2 + 63) >> 6) * (hb / 16);      // 128-word units
+    const uint32_t hb = (uint32_t)hb16::half_band(pr.dmax - pr.dmin, (int)L);
+    tb_units[p] = (((2 * L + 2 * hb - 2 + 63) >> 6) * hb + 15) / 16;  // 128-word units: a super-step is hb x 8 words
     qrec_units[p] = (L + 31) >> 5;
 }
 
@@ -285,8 +288,8 @@ cudaError_t hb_pair_sizes_launch(const HbLocus* pairs, uint32_t n_pairs, const u
 }
 
 size_t hb_extend_order_words(uint32_t n_pairs) {
-    // flag_n, flag_w, off_n, off_w, order_n, order_w (n each), two totals (4 words), scan scratch
-    return 6 * ((size_t)n_pairs + 2) + 4 + hb_scan_tmp_words((size_t)n_pairs + 1);
+    // flag_t/n/w, off_t/n/w, order_t/n/w (n each), three totals (8 words), scan scratch
+    return 9 * ((size_t)n_pairs + 2) + 8 + hb_scan_tmp_words((size_t)n_pairs + 1);
 }
 
 cudaError_t hb_extend_launch(const HbLocus* pairs, uint32_t pair_lo, uint32_t pair_hi, const uint32_t* gseq2,
@@ -297,22 +300,27 @@ cudaError_t hb_extend_launch(const HbLocus* pairs, uint32_t pair_lo, uint32_t pa
     if (pair_hi <= pair_lo) return cudaSuccess;
     const uint32_t n = pair_hi - pair_lo;
     const size_t st = (size_t)n + 2;
-    uint32_t *flag_n = order_ws, *flag_w = flag_n + st, *off_n = flag_w + st, *off_w = off_n + st,
-             *order_n = off_w + st, *order_w = order_n + st;
-    uint64_t* totals = reinterpret_cast<uint64_t*>(order_w + st);        // 6 * st words: 8 B aligned
-    uint32_t* scan_tmp = reinterpret_cast<uint32_t*>(totals + 2);
-    // ---- order lists: narrow / wide pairs whose candidate fits the 16-bit kernel ------------------
-    order_flag_kernel<<<(n + 255) / 256, 256, 0, s>>>(pairs, pair_lo, pair_hi, clen, flag_n, flag_w);
-    cudaError_t e = hb_exclusive_scan_u32(flag_n, off_n, n, scan_tmp, totals, s);
+    uint32_t *flag_t = order_ws, *flag_n = flag_t + st, *flag_w = flag_n + st, *off_t = flag_w + st, *off_n = off_t + st,
+             *off_w = off_n + st, *order_t = off_w + st, *order_n = order_t + st, *order_w = order_n + st;
+    uint64_t* totals = reinterpret_cast<uint64_t*>(order_ws + ((9 * st + 1) & ~(size_t)1));     // 8 B aligned
+    uint32_t* scan_tmp = reinterpret_cast<uint32_t*>(totals + 3);
+    // ---- order lists: tight / narrow / wide pairs whose candidate fits the 16-bit kernel ----------
+    order_flag_kernel<<<(n + 255) / 256, 256, 0, s>>>(pairs, pair_lo, pair_hi, clen, flag_t, flag_n, flag_w);
+    cudaError_t e = hb_exclusive_scan_u32(flag_t, off_t, n, scan_tmp, totals + 2, s);
+    if (e != cudaSuccess) return e;
+    e = hb_exclusive_scan_u32(flag_n, off_n, n, scan_tmp, totals, s);
     if (e != cudaSuccess) return e;
     e = hb_exclusive_scan_u32(flag_w, off_w, n, scan_tmp, totals + 1, s);
     if (e != cudaSuccess) return e;
-    order_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pair_lo, n, flag_n, flag_w, off_n, off_w, order_n, order_w);
+    order_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pair_lo, n, flag_t, flag_n, flag_w, off_t, off_n, off_w, order_t, order_n, order_w);
     // ---- 16-bit kernels: grids sized for "all pairs in this class", surplus blocks exit at once ----
     extend16_kernel<32><<<(n + 2 * EXT_WARPS - 1) / (2 * EXT_WARPS), EXT_WARPS * 32, 0, s>>>(
         order_w, totals + 1, pairs, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
     extend16_kernel<16><<<(n + 4 * EXT_WARPS - 1) / (4 * EXT_WARPS), EXT_WARPS * 32, 0, s>>>(
         order_n, totals, pairs, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
+    extend16_kernel<8><<<(n + 8 * EXT_WARPS - 1) / (8 * EXT_WARPS), EXT_WARPS * 32, 0, s>>>(
+        order_t, totals + 2, pairs, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
+    *launches += 4;
     *launches += 10;
     if (any_long) {
         // 32-bit kernels: one pair per warp (wide band) / two pairs per warp (narrow); each skips the
@@ -323,7 +331,7 @@ cudaError_t hb_extend_launch(const HbLocus* pairs, uint32_t pair_lo, uint32_t pa
             pairs, pair_lo, pair_hi, gseq2, gnmask, tot, cseq2, cnmask, cgoff, clen, tb_unit_off, tb_unit_base, tbuf, alns);
         *launches += 2;
     }
-    traceback_kernel<<<(n + 127) / 128, 128, 0, s>>>(pairs, pair_lo, pair_hi, tb_unit_off, tb_unit_base, tbuf,
+    traceback_kernel<<<(n + 127) / 128, 128, 0, s>>>(pairs, pair_lo, pair_hi, clen, tb_unit_off, tb_unit_base, tbuf,
                                                       qrec_unit_off, qrec, alns);
     *launches += 1;
     return cudaGetLastError();

@@ -23,6 +23,12 @@ namespace hb16 {
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int HB16_MAX_L = HB_EXTEND16_MAX_L;       // 2 * L + 4 + 6 < 32768
 constexpr int NARROW_SPREAD = 12;        // HB-align S7 (5 %-trimmed diagonal spread of the cluster, band centred on its median)
+constexpr int TIGHT_SPREAD = 3;          // ... and 16 diagonals are enough when the hits sit within 3 diagonals
+// half band (lanes per pair) of a locus: 8 / 16 / 32; candidates beyond the 16-bit kernel only have the 16 / 32 kernels
+HB_HD int half_band(int64_t spread, int L) {
+    if (spread > NARROW_SPREAD) return 32;
+    return (spread <= TIGHT_SPREAD && L <= HB16_MAX_L) ? 8 : 16;
+}
 
 // ---- packed signed-16x2 primitives (device: one SASS instruction each; host: plain C) ------------
 #ifndef __CUDA_ARCH__
@@ -365,7 +371,8 @@ HB_HD int hb_clz32(uint32_t x) {
     return x ? __builtin_clz(x) : 32;
 #endif
 }
-HB_HD void traceback_pair(uint32_t p, const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ tb_unit_off,
+HB_HD void traceback_pair(uint32_t p, const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ clen,
+                          const uint32_t* __restrict__ tb_unit_off,
                           uint32_t tb_unit_base, const uint32_t* __restrict__ tbuf,
                           const uint32_t* __restrict__ qrec_unit_off, uint32_t* __restrict__ qrec,
                           HbAln* __restrict__ alns) {
@@ -373,7 +380,7 @@ HB_HD void traceback_pair(uint32_t p, const HbLocus* __restrict__ pairs, const u
     if (a.score <= 0) return;
     const HbLocus pr = pairs[p];
     const int64_t j0 = pr.j0;
-    const int HB = (pr.dmax - pr.dmin) <= NARROW_SPREAD ? 16 : 32;
+    const int HB = half_band(pr.dmax - pr.dmin, (int)clen[pr.cand]);
     const uint32_t* tb = tbuf + ((size_t)(tb_unit_off[p] - tb_unit_base) << 7);
     uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
     int i = a.i_e, o = (int)(a.j_e - j0) - a.i_e, pending_d = 0;

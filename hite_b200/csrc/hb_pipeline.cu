@@ -899,6 +899,17 @@ extern "C" int hb_last_cons_device(hb_ctx* ctx, const void** dptr, uint64_t* nby
     return HB_OK;
 }
 
+extern "C" int hb_last_pair_counts(hb_ctx* ctx, uint32_t* out, uint32_t cap) {
+    if (!ctx || !out) return HB_EINVAL;
+    if (ctx->last_overlapped) return hb_fail_msg(ctx, HB_ESTATE, "hb_last_pair_counts: needs a serial hb_adjust (hb_params.overlap < 2)");
+    if (cap < ctx->last_ncand) return hb_fail_msg(ctx, HB_EINVAL, "hb_last_pair_counts: buffer too small");
+    if (ctx->last_ncand == 0) return HB_OK;
+    cudaSetDevice(ctx->device);
+    HB_CUDA_OK(cudaMemcpyAsync(out, ctx->buf("s.n_loci").p, sizeof(uint32_t) * ctx->last_ncand, cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
 extern "C" int hb_last_copies(hb_ctx* ctx, hb_copy* out, uint64_t cap, uint64_t* n) {
     if (!ctx || !n) return HB_EINVAL;
     *n = ctx->last_npairs;

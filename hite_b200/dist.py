@@ -43,6 +43,23 @@ def allgather_records(records, device=None):
     return merged
 
 
+def shard_by_cost(costs, rank, world):
+    """Longest-processing-time deal on measured costs (e.g. loci x length of a first round: a stage runs the same candidates
+    through several rounds, judge_TIR_transposons.py:29-38, and a candidate of a 5 000-copy family costs 60 x one of a 5-copy
+    family of the same length): heaviest first, each to the currently least loaded rank.  Deterministic and identical on
+    every rank; returns this rank's indices in ascending order."""
+    import heapq
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    heap = [(0, r) for r in range(world)]
+    mine = []
+    for i in order:
+        ld, r = heapq.heappop(heap)
+        if r == rank:
+            mine.append(i)
+        heapq.heappush(heap, (ld + costs[i], r))
+    return sorted(mine)
+
+
 def shard_by_chunk(chunk_of, lengths, rank, world):
     """SURVEY 8(e) partitioning for a multi-chunk genome (reference main.nf:627-648: one process per chunk): chunk c goes to
     rank c % world, then the candidates are rebalanced -- every rank above the mean base count puts its shortest candidates
@@ -127,9 +144,10 @@ class RecordGather:
         else:
             self.work = None                              # one rank: the records are already where they are needed
 
-    def finish(self):
+    def finish(self, concat=True):
         """Wait for the collective launched by ``start``; on the read-back rank returns (indices, lengths, consensus bytes)
-        of ALL ranks' records in rank order as numpy arrays, elsewhere None.  With one rank nothing is exchanged or copied
+        of ALL ranks' records in rank order as numpy arrays (``concat=False``: per-rank lists of zero-copy views into the
+        pinned staging buffer, valid until the next ``finish``), elsewhere None.  With one rank nothing is exchanged or copied
         and the bytes come back as None (they are the caller's own hb_adjust result)."""
         import numpy as np
         if self.work is not None:
@@ -140,7 +158,7 @@ class RecordGather:
         cap, hdr_all = self.cap, self.HDR + self.rec_cap
         if self.world == 1:                               # nothing was exchanged: hand the rank's own records back
             idx, ln, n, nb = self._own                    # (the consensus bytes are the caller's own hb_adjust result)
-            return idx, ln, None
+            return (idx, ln, None) if concat else ([idx], [ln], None)
         for r in range(self.world):                       # headers + record tables first (small) ...
             self.h_out[r * cap:r * cap + hdr_all].copy_(self.out[r * cap:r * cap + hdr_all], non_blocking=True)
         if self.device.type == "cuda":
@@ -158,9 +176,11 @@ class RecordGather:
         for r in range(self.world):
             n, nb = int(sizes[r][0]), int(sizes[r][1])
             rec = ho[r * cap + 16:r * cap + 16 + 8 * n].view(np.int32).reshape(n, 2)
-            idx.append(rec[:, 0].copy()); ln.append(rec[:, 1].copy())
+            idx.append(rec[:, 0]); ln.append(rec[:, 1])
             a = r * cap + hdr_all
-            cons.append(ho[a:a + nb].copy())
+            cons.append(ho[a:a + nb])                       # views into the pinned staging buffer: valid until the next finish()
+        if not concat:
+            return idx, ln, cons
         return np.concatenate(idx), np.concatenate(ln), np.concatenate(cons)
 
 

@@ -334,6 +334,10 @@ typedef struct { int32_t found, len5, len3, score, n_match, n_mismatch, n_gap; }
 int hb_itr_search(hb_ctx* ctx, uint32_t n, const uint8_t* seq_ascii, const uint64_t* seq_off, double min_identity, int32_t min_len,
                   int32_t max_window, hb_itr_rec* out);
 
+/* loci aligned per candidate in the last hb_adjust (<= max_loci each): the cost proxy (x candidate length) a multi-GPU caller
+ * rebalances the next round's shards with -- the stages run the same candidates through several rounds (judge_TIR_transposons.py:29-38) */
+int hb_last_pair_counts(hb_ctx* ctx, uint32_t* out, uint32_t cap);
+
 /* parity/debug getters: the sorted minimizer index (hash<<33 | pos<<1 | strand) and the raw
  * (pre-clean) MSA of one candidate of the last hb_adjust as ASCII */
 int hb_debug_index(hb_ctx* ctx, uint64_t* keys_out, uint64_t cap);

@@ -170,6 +170,14 @@ void hbo_sort_u64(uint64_t *keys, uint64_t n) { qsort(keys, n, sizeof(uint64_t),
 /* band half-width: 16 when the seed cluster's diagonal spread is <= HB_NARROW_SPREAD (o in [-16,15]),
    else 32 (o in [-32,31])  -- HB-align S7 */
 #define HB_NARROW_SPREAD 12
+#define HB_TIGHT_SPREAD 3
+#define HB16_MAX_L 16000
+/* half band of a locus (HB-align S7): 8 (o in [-8,7]) when the cluster's trimmed diagonal spread is <= HB_TIGHT_SPREAD and the
+   candidate fits the 16-bit kernel, 16 when it is <= HB_NARROW_SPREAD, else 32 */
+static int half_band_of(int64_t spread, int L) {
+    if (spread > HB_NARROW_SPREAD) return 32;
+    return (spread <= HB_TIGHT_SPREAD && L <= HB16_MAX_L) ? 8 : 16;
+}
 #define SC_MATCH 2
 #define SC_MIS (-4)
 #define SC_GAPO 4
@@ -514,7 +522,7 @@ int hbo_candidate_msa(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, 
         memset(cp, 0, sizeof(*cp));
         cp->rank = x; cp->rel = (int32_t)loci[x].rel; cp->contig = -1;
         hbo_align_pair(g, q, L, (int)loci[x].rel, loci[x].j0,
-                       (loci[x].dmax - loci[x].dmin <= HB_NARROW_SPREAD) ? 16 : 32, &a, qrecs + (size_t)x * L);
+                       half_band_of(loci[x].dmax - loci[x].dmin, L), &a, qrecs + (size_t)x * L);
         cp->score = a.score; cp->i_s = a.i_s; cp->i_e = a.i_e; cp->j_s = a.j_s; cp->j_e = a.j_e;
     }
     if (getenv("HBO_DEBUG_SPREAD")) for (int x = 0; x < nl; ++x) fprintf(stderr, "SPREAD %lld %u\n", (long long)(loci[x].dmax - loci[x].dmin), loci[x].nseeds);
@@ -623,7 +631,7 @@ int hbo_query_hsps(const hbo_genome *g, const uint64_t *idx, uint64_t n_idx, int
     for (int x = 0; x < nl && n < cap; ++x) {
         hbo_aln a;
         const int rel = (int)loci[x].rel;
-        hbo_align_pair(g, q, L, rel, loci[x].j0, (loci[x].dmax - loci[x].dmin <= HB_NARROW_SPREAD) ? 16 : 32, &a, qr);
+        hbo_align_pair(g, q, L, rel, loci[x].j0, half_band_of(loci[x].dmax - loci[x].dmin, L), &a, qr);
         if (a.score <= 0) continue;
         const int64_t fs = rel ? (int64_t)g->tot - 1 - a.j_e : a.j_s;
         const int64_t fe = rel ? (int64_t)g->tot - 1 - a.j_s : a.j_e;

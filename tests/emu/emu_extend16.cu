@@ -103,7 +103,7 @@ void run_class(const std::vector<uint32_t>& order, const HbLocus* pairs, const u
 }  // namespace
 
 // genome_codes: tot entries 0..4 (the oracle's padded layout); cand_codes: concatenated candidates.
-// pairs: cand, rel, j0, narrow per pair.  Outputs per pair: score, i_s, i_e, j_s, j_e and qrec rows
+// pairs: cand, rel, j0, band class (0 wide = 64 diagonals, 1 narrow = 32, 2 tight = 16) per pair.  Outputs per pair: score, i_s, i_e, j_s, j_e and qrec rows
 // (qrec_off[p] .. + L words, zero outside the alignment).
 extern "C" int emu_extend16(const uint8_t* genome_codes, uint64_t tot, const uint8_t* cand_codes, const uint64_t* cand_off,
                             uint32_t n_cand, const uint32_t* p_cand, const uint32_t* p_rel, const int64_t* p_j0,
@@ -123,19 +123,19 @@ extern "C" int emu_extend16(const uint8_t* genome_codes, uint64_t tot, const uin
     pack_codes(cc.data(), ctot, cseq2, cnmask);
 
     std::vector<HbLocus> pairs(n_pairs);
-    std::vector<uint32_t> tb_off(n_pairs + 1), qr_off(n_pairs + 1), order_n, order_w;
+    std::vector<uint32_t> tb_off(n_pairs + 1), qr_off(n_pairs + 1), order_t, order_n, order_w;
     uint32_t tbu = 0, qru = 0;
     for (uint32_t i = 0; i < n_pairs; ++i) {
         HbLocus& pr = pairs[i];
         pr.cand = p_cand[i]; pr.rel = p_rel[i]; pr.nseeds = 3; pr.rank = i; pr.j0 = p_j0[i];
-        pr.dmin = 0; pr.dmax = p_narrow[i] ? 0 : 100;
+        pr.dmin = 0; pr.dmax = p_narrow[i] == 2 ? 0 : p_narrow[i] == 1 ? hb16::NARROW_SPREAD : 100;   // band class: 0 wide, 1 narrow, 2 tight
         const uint32_t L = clen[pr.cand];
         if ((int)L > hb16::HB16_MAX_L) return -1;
-        const uint32_t hb = p_narrow[i] ? 16u : 32u;
+        const uint32_t hb = (uint32_t)hb16::half_band(pr.dmax - pr.dmin, (int)L);
         tb_off[i] = tbu; qr_off[i] = qru;
-        tbu += ((2 * L + 2 * hb - 2 + 63) >> 6) * (hb / 16);
+        tbu += (((2 * L + 2 * hb - 2 + 63) >> 6) * hb + 15) / 16;
         qru += (L + 31) >> 5;
-        (p_narrow[i] ? order_n : order_w).push_back(i);
+        (hb == 8 ? order_t : hb == 16 ? order_n : order_w).push_back(i);
     }
     std::vector<uint32_t> tbuf(((size_t)tbu + 1) << 7, 0xDEADBEEFu);       // poison: unwritten sectors must never be read
     std::vector<uint32_t> qrec(((size_t)qru + 1) << 5, 0u);
@@ -145,8 +145,10 @@ extern "C" int emu_extend16(const uint8_t* genome_codes, uint64_t tot, const uin
                   clen.data(), tb_off.data(), tbuf.data(), alns.data());
     run_class<16>(order_n, pairs.data(), gseq2.data(), gnmask.data(), tot, cseq2.data(), cnmask.data(), cgoff.data(),
                   clen.data(), tb_off.data(), tbuf.data(), alns.data());
+    run_class<8>(order_t, pairs.data(), gseq2.data(), gnmask.data(), tot, cseq2.data(), cnmask.data(), cgoff.data(),
+                 clen.data(), tb_off.data(), tbuf.data(), alns.data());
     for (uint32_t i = 0; i < n_pairs; ++i)
-        hb16::traceback_pair(i, pairs.data(), tb_off.data(), 0u, tbuf.data(), qr_off.data(), qrec.data(), alns.data());
+        hb16::traceback_pair(i, pairs.data(), clen.data(), tb_off.data(), 0u, tbuf.data(), qr_off.data(), qrec.data(), alns.data());
     for (uint32_t i = 0; i < n_pairs; ++i) {
         out_score[i] = alns[i].score; out_is[i] = alns[i].i_s; out_ie[i] = alns[i].i_e;
         out_js[i] = alns[i].j_s; out_je[i] = alns[i].j_e;

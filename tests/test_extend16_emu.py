@@ -108,14 +108,15 @@ def _run(seed, n_fam, lens, sub, indel, n_runs=0, edge=False, skew=6, pin=None):
     for (f, strand, pos, clen) in plan:
         gpos = 64 + pos
         j0 = gpos if strand == 0 else tot - (gpos + clen)
-        narrow = int(rng.integers(0, 2))
+        narrow = int(rng.integers(0, 3))                     # band class: 0 wide (half band 32), 1 narrow (16), 2 tight (8)
+        hb = (32, 16, 8)[narrow]
         # seeds put the band roughly, not exactly, on the copy; a large skew runs the path along the band edge
-        j0 += int(rng.integers(-skew, skew + 1)) * (1 if narrow or skew <= 6 else 2)
-        if pin is not None:                                  # put the copy on a chosen diagonal o = pin (x2 for the wide band)
-            j0 = (gpos if strand == 0 else tot - (gpos + clen)) - pin * (1 if narrow else 2)
+        j0 += int(rng.integers(-skew, skew + 1)) * hb // 16 if skew > 6 else int(rng.integers(-skew, skew + 1)) * min(hb, 16) // 16
+        if pin is not None:                                  # put the copy on a chosen diagonal o = pin (scaled to the band)
+            j0 = (gpos if strand == 0 else tot - (gpos + clen)) - (pin * hb) // 16
         p_cand.append(f); p_rel.append(strand); p_j0.append(j0); p_narrow.append(narrow)
     if edge:                                                 # windows hanging over both genome ends, and a pure-noise pair
-        p_cand += [0, 0, 1]; p_rel += [0, 1, 0]; p_j0 += [-40, tot - 30, 500]; p_narrow += [1, 0, 1]
+        p_cand += [0, 0, 1, 0, 1]; p_rel += [0, 1, 0, 0, 1]; p_j0 += [-40, tot - 30, 500, -20, tot - 12]; p_narrow += [1, 0, 1, 2, 2]
     n = len(p_cand)
     p_cand = np.array(p_cand, dtype=np.uint32); p_rel = np.array(p_rel, dtype=np.uint32)
     p_j0 = np.array(p_j0, dtype=np.int64); p_narrow = np.array(p_narrow, dtype=np.uint32)
@@ -134,7 +135,7 @@ def _run(seed, n_fam, lens, sub, indel, n_runs=0, edge=False, skew=6, pin=None):
         a = _Aln()
         oq = np.zeros(L, dtype=np.uint32)
         lib.hbo_align_pair(C.c_void_p(g), P(ccodes[p_cand[i]]), C.c_int(L), C.c_int(int(p_rel[i])), C.c_int64(int(p_j0[i])),
-                           C.c_int(16 if p_narrow[i] else 32), C.byref(a), P(oq))
+                           C.c_int((32, 16, 8)[int(p_narrow[i])]), C.byref(a), P(oq))
         assert score[i] == a.score, (seed, i)
         if a.score > 0:
             n_pos += 1

@@ -88,6 +88,13 @@ def test_shard_indices_deterministic_partition():
     assert sorted(sum(parts, [])) == list(range(len(lens)))
     assert parts == [hd.shard_indices(len(lens), r, 3, lens) for r in range(3)]
     assert hd.shard_indices(5, 1, 2) == [1, 3]
+    # cost deal (heaviest first, to the least loaded rank): a partition, deterministic, and balanced within one item
+    cost = [900, 20, 30, 880, 10, 15, 870, 5, 300, 310, 290, 1]
+    parts = [hd.shard_by_cost(cost, r, 3) for r in range(3)]
+    assert sorted(sum(parts, [])) == list(range(len(cost))) and parts == [hd.shard_by_cost(cost, r, 3) for r in range(3)]
+    loads = [sum(cost[i] for i in p_) for p_ in parts]
+    assert max(loads) - min(loads) <= 30, loads
+    assert hd.shard_by_cost([], 0, 2) == [] and hd.shard_by_cost([7], 1, 2) == []
 
 
 GLOO_WORKER = r"""
@@ -133,6 +140,13 @@ for step in range(3):
         assert body.tobytes().decode() == "".join(seqs[i].lower() for i in exp_keep)
     else:
         assert got is None
+    if step == 2:                                                     # zero-copy read-back: per-rank views, same content
+        g.start(np.array(keep, dtype=np.int32), np.array([len(seqs[i]) for i in keep], dtype=np.int32),
+                torch.frombuffer(bytearray(cons), dtype=torch.uint8) if cons else None)
+        got = g.finish(concat=False)
+        if rank == 0:
+            assert len(got[0]) == world and np.concatenate(got[0]).tolist() == exp_keep
+            assert b"".join(c.tobytes() for c in got[2]).decode() == "".join(seqs[i].lower() for i in exp_keep)
 try:
     g.start(np.arange(99, dtype=np.int32), np.ones(99, dtype=np.int32), None)
     raise SystemExit("capacity overflow not detected")
