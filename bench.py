@@ -375,6 +375,16 @@ def main():
         dist.all_reduce(ssum, op=dist.ReduceOp.SUM)
     wall_max, dev_max, kern_max, gather_max = float(smax[0]), float(smax[1]) * 1e-3, float(smax[2]) * 1e-3, float(smax[4])
     n_te_total = int(ssum[3])
+    # per-rank view (diagnostic): device ms / step, its stages, wall ms / step and the rank's SM clock at the end of the timed region
+    try:
+        my_mhz = float(torch.cuda.clock_rate())
+    except Exception:
+        my_mhz = 0.0
+    mine_v = torch.tensor([float(np.sum(dev_ms)) / args.steps] + [float(x) / args.steps for x in stage[:6]] + [wall * 1e3 / args.steps, my_mhz],
+                          device="cuda", dtype=torch.float64)
+    per_rank = [mine_v.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine_v)
     if rank == 0 and got is not None:
         assert sum(len(a) for a in got[0]) == n_te_total and \
             (got[2] is None or sum(int(a.sum()) for a in got[1]) == sum(len(c) for c in got[2])), "gathered records are inconsistent"
@@ -434,6 +444,11 @@ def main():
                 ("sketch_cands", "seed_sort_cluster", "extend", "copy_rules_msa", "clean_judge", "compact"), stage[:6])},
             "collective_ms_per_step": gather_max / args.steps,
             "kernel_only_ms_per_step": kern_max / args.steps * 1e3,
+            "per_rank": {"kernel_ms": [round(float(v[0]), 2) for v in per_rank],
+                         "extend_ms": [round(float(v[3]), 2) for v in per_rank],
+                         "clean_judge_ms": [round(float(v[5]), 2) for v in per_rank],
+                         "wall_ms": [round(float(v[7]), 2) for v in per_rank],
+                         "sm_mhz": [int(v[8]) for v in per_rank]},
             "setup": {"genome_load_ms": t_load["kernel_ms"] + t_load["h2d_ms"], "index_build_ms": t_idx["kernel_ms"],
                       "index_stages_ms": [round(float(x), 3) for x in t_idx["k_ms"][:3]],
                       "index_Mbp_per_s": wl.genome_bp / 1e6 / max(1e-9, t_idx["kernel_ms"] * 1e-3), "setup_wall_s": setup_s,

@@ -487,20 +487,71 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
 // dropped by the reference's rule (remove_sparse_col_in_align_file, module/Util.py:10379-10391: first and last column always
 // kept, a column goes when gaps > rows / 2) and the kept columns are appended to the two clean matrices (row stride C).
 constexpr int MC_TILE = 128, MC_THREADS = 256, MC_MAXROWS = 104;
-__global__ void __launch_bounds__(MC_THREADS)
-msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restrict__ task_cand, const int32_t* __restrict__ trunc_of_full,
+
+// per-row constants of a candidate's kept copies, staged once per CTA (struct of arrays in shared memory)
+struct McRows {
+    uint32_t qoff[MC_MAXROWS], j0[MC_MAXROWS], js[MC_MAXROWS], je[MC_MAXROWS];
+    int i_s[MC_MAXROWS], i_e[MC_MAXROWS];
+    short trow[MC_MAXROWS];
+    uint8_t rel[MC_MAXROWS];
+};
+
+// four adjacent cells of one row, branch-free so that the 4 edit-record loads and then the 8 genome loads are in flight together
+__device__ __forceinline__ uint32_t mc_row_word(const McRows& rw, int r, const uint32_t* __restrict__ s_cq4, int col0, int C,
+                                                const uint32_t* __restrict__ qrec, const uint32_t* __restrict__ gseq2,
+                                                const uint32_t* __restrict__ gnmask, uint32_t totm1, int flank) {
+    const uint32_t* qr = qrec + ((size_t)rw.qoff[r] << 5);
+    const uint32_t j0 = rw.j0[r], js = rw.js[r], je = rw.je[r];
+    const int i_s = rw.i_s[r], i_e = rw.i_e[r];
+    const bool rel = rw.rel[r] != 0, in_trunc = rw.trow[r] >= 0;
+    const uint32_t ext_lo = js - (uint32_t)flank, ext_len = je - js + 2u * (uint32_t)flank + 1u;
+    uint32_t v[4];
+    int q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        q[k] = (int)(s_cq4[k] >> 8) - flank;
+        v[k] = qr[min(max(q[k], i_s), i_e)];
+    }
+    uint32_t j[4], nm[4], sq[4];
+    bool have[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t slot = s_cq4[k] & 255u;
+        const bool inside = q[k] >= i_s && q[k] <= i_e, left = q[k] < i_s;
+        const bool have_in = slot == 0 ? ((v[k] >> 24) & 1u) == 0 : slot <= ((v[k] >> 16) & 255u);
+        const bool have_out = slot == 0 && (left ? q[k] >= i_s - flank : q[k] <= i_e + flank);
+        const uint32_t j_in = j0 + (uint32_t)q[k] + (v[k] & 0xFFFFu) - 32768u + slot;
+        const uint32_t j_out = left ? js - (uint32_t)(i_s - q[k]) : je + (uint32_t)(q[k] - i_e);
+        have[k] = (col0 + k < C) && (inside ? have_in : have_out);
+        j[k] = inside ? j_in : j_out;
+        const uint32_t pos = min(rel ? totm1 - j[k] : j[k], totm1);       // a cell without a base reads a harmless word
+        nm[k] = (gnmask[pos >> 5] >> (pos & 31u)) & 1u;
+        sq[k] = (gseq2[pos >> 4] >> (2u * (pos & 15u))) & 3u;
+    }
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t sym = nm[k] ? (uint32_t)HB_SYM_N : (rel ? 3u - sq[k] : sq[k]);
+        const uint32_t d = j[k] - ext_lo;                                   // blank in the truncated-member matrix ?
+        if (in_trunc && d >= 500u && ext_len - 1u - d >= 500u) sym |= 0x80u;
+        w |= (have[k] ? sym : (uint32_t)HB_SYM_GAP) << (8 * k);
+    }
+    return w;
+}
+
+__global__ void __launch_bounds__(MC_THREADS, 4)
+msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restrict__ order, const uint32_t* __restrict__ task_cand,
+                 const int32_t* __restrict__ trunc_of_full,
                  const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, const HbAln* __restrict__ alns,
                  const uint32_t* __restrict__ qrec_unit_off, const uint32_t* __restrict__ qrec,
                  const uint32_t* __restrict__ col_off, const uint32_t* __restrict__ colq, const uint32_t* __restrict__ gseq2,
                  const uint32_t* __restrict__ gnmask, uint64_t tot, int flank, uint8_t* __restrict__ clean,
-                 HbVoteCall* __restrict__ calls) {
+                 uint32_t* __restrict__ planes, HbVoteCall* __restrict__ calls) {
     __shared__ __align__(16) uint8_t s_tile[MC_MAXROWS][MC_TILE];
-    __shared__ uint32_t s_cq[MC_TILE];
-    __shared__ uint32_t s_pair[MC_MAXROWS];
-    __shared__ short s_trow[MC_MAXROWS];
+    __shared__ __align__(16) uint32_t s_cq[MC_TILE];
+    __shared__ McRows rw;
     __shared__ int s_warp[2][MC_TILE / 32];
-    __shared__ int s_base[2];
-    const uint32_t ti = blockIdx.x;                       // full task
+    const uint32_t ti = order[blockIdx.x];                // full task; the largest matrices are started first
     const int tt = trunc_of_full[ti];                     // its truncated-member task, or -1
     const HbVoteTask t = tasks[ti];
     const uint32_t c = task_cand[ti];
@@ -510,114 +561,91 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
     const uint32_t p0 = pair_off[c], p1 = pair_off[c + 1];
     for (uint32_t p = p0 + tid; p < p1; p += MC_THREADS) {
         const HbAln a = alns[p];
-        if (a.row >= 0 && a.row < MC_MAXROWS) { s_pair[a.row] = p; s_trow[a.row] = (short)a.trow; }
+        if (a.row >= 0 && a.row < MC_MAXROWS) {
+            const HbLocus pr = pairs[p];
+            const int r = a.row;
+            rw.qoff[r] = qrec_unit_off[p]; rw.j0[r] = (uint32_t)pr.j0; rw.js[r] = (uint32_t)a.j_s; rw.je[r] = (uint32_t)a.j_e;
+            rw.i_s[r] = a.i_s; rw.i_e[r] = a.i_e; rw.trow[r] = (short)a.trow; rw.rel[r] = (uint8_t)pr.rel;
+        }
     }
-    if (tid < 2) s_base[tid] = 0;
     __syncthreads();
     const uint32_t* cq = colq + col_off[c];
-    uint8_t* out = clean + t.clean_off;
-    uint8_t* tout = tt >= 0 ? clean + tasks[tt].clean_off : nullptr;
     const uint32_t totm1 = (uint32_t)(tot - 1);
+    // column phase: threads 0..127 own the full matrix, 128..255 the truncated-member matrix
+    const int half = tid >> 7, ct = tid & (MC_TILE - 1), hw = wid & 3;
+    uint8_t* out = half == 0 ? clean + t.clean_off : (tt >= 0 ? clean + tasks[tt].clean_off : nullptr);
+    const int RH = half == 0 ? R : RT;
+    // six bit-planes of every kept column over ALL rows of my matrix (row k = bit k & 31 of word k >> 5): what the judges
+    // vote on (hb_vote.cu::Planes; they mask the rows they keep), built here while the column is in shared memory
+    uint32_t* pw = planes == nullptr ? nullptr : planes + (half == 0 ? t.plane_off : (tt >= 0 ? tasks[tt].plane_off : 0));
+    int base = 0;                                         // kept columns of my matrix so far
     for (int c0 = 0; c0 < C; c0 += MC_TILE) {
         if (tid < MC_TILE) s_cq[tid] = c0 + tid < C ? cq[c0 + tid] : 0u;
         __syncthreads();
-        // ---- the tile's symbols: warp per row, 4 columns per lane ----
-        for (int r = wid; r < R; r += MC_THREADS / 32) {
-            const uint32_t p = s_pair[r];
-            const HbAln a = alns[p];
-            const HbLocus pr = pairs[p];
-            const int rel = (int)pr.rel;
-            const bool in_trunc = s_trow[r] >= 0;
-            const uint32_t* qr = qrec + ((size_t)qrec_unit_off[p] << 5);
-            const uint32_t j0 = (uint32_t)pr.j0, js = (uint32_t)a.j_s, je = (uint32_t)a.j_e;
-            const int i_s = a.i_s, i_e = a.i_e;
-            const uint32_t ext_lo = js - (uint32_t)flank, ext_len = je - js + 2u * (uint32_t)flank + 1u;
-            uint32_t w = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int col = c0 + 4 * lane + k;
-                uint32_t sym = HB_SYM_GAP;
-                if (col < C) {
-                    const uint32_t e = s_cq[4 * lane + k];
-                    const int q = (int)(e >> 8) - flank;
-                    const uint32_t slot = e & 255u;
-                    uint32_t j = 0;
-                    bool have = true;
-                    if (q >= i_s && q <= i_e) {
-                        const uint32_t v = qr[q];
-                        if (slot == 0 ? ((v >> 24) & 1u) != 0 : slot > ((v >> 16) & 255u)) have = false;
-                        j = j0 + (uint32_t)q + (v & 0xFFFFu) - 32768u + slot;
-                    } else {
-                        if (slot != 0) have = false;
-                        else if (q < i_s) { if (q < i_s - flank) have = false; j = js - (uint32_t)(i_s - q); }
-                        else { if (q > i_e + flank) have = false; j = je + (uint32_t)(q - i_e); }
-                    }
-                    if (have) {
-                        const uint32_t pos = rel ? totm1 - j : j;
-                        if ((gnmask[pos >> 5] >> (pos & 31u)) & 1u) sym = HB_SYM_N;
-                        else {
-                            const uint32_t b2 = (gseq2[pos >> 4] >> (2u * (pos & 15u))) & 3u;
-                            sym = rel ? 3u - b2 : b2;
-                        }
-                        if (in_trunc) {                                        // blank in the truncated-member matrix ?
-                            const uint32_t d = j - ext_lo;
-                            if (d >= 500u && ext_len - 1u - d >= 500u) sym |= 0x80u;
-                        }
-                    }
-                }
-                w |= sym << (8 * k);
-            }
-            *reinterpret_cast<uint32_t*>(&s_tile[r][4 * lane]) = w;
+        // ---- the tile's symbols: warp per row (two rows in flight), 4 columns per lane ----
+        uint32_t e4[4];
+        *reinterpret_cast<uint4*>(e4) = *reinterpret_cast<const uint4*>(&s_cq[4 * lane]);
+        for (int r = wid; r < R; r += 2 * (MC_THREADS / 32)) {
+            const int r2 = r + MC_THREADS / 32;
+            const uint32_t wa = mc_row_word(rw, r, e4, c0 + 4 * lane, C, qrec, gseq2, gnmask, totm1, flank);
+            const uint32_t wb = mc_row_word(rw, min(r2, R - 1), e4, c0 + 4 * lane, C, qrec, gseq2, gnmask, totm1, flank);
+            *reinterpret_cast<uint32_t*>(&s_tile[r][4 * lane]) = wa;
+            if (r2 < R) *reinterpret_cast<uint32_t*>(&s_tile[r2][4 * lane]) = wb;
         }
         __syncthreads();
-        // ---- sparse columns of both matrices: thread per column of the tile ----
-        int keep = 0, pos = 0, tkeep = 0, tpos = 0;
-        if (tid < MC_TILE) {
-            const int col = c0 + tid;
-            if (col < C) {
-                int gaps = 0, tgaps = 0;
+        // ---- sparse columns (remove_sparse_col_in_align_file): thread per column and matrix ----
+        const int col = c0 + ct;
+        int keep = 0;
+        if (RH > 0 && col < C) {
+            int gaps = 0;
+            if (half == 0) {
+                for (int r = 0; r < R; ++r) gaps += (s_tile[r][ct] & 0x7Fu) == HB_SYM_GAP;
+            } else {
                 for (int r = 0; r < R; ++r) {
-                    const uint32_t b = s_tile[r][tid];
-                    gaps += (b & 0x7Fu) == HB_SYM_GAP;
-                    tgaps += (s_trow[r] >= 0) && (b == HB_SYM_GAP || (b & 0x80u));
+                    const uint32_t b = s_tile[r][ct];
+                    gaps += (rw.trow[r] >= 0) && (b == HB_SYM_GAP || (b & 0x80u));
                 }
-                keep = (col == 0) || (col == C - 1) || !(2 * gaps > R);
-                tkeep = RT > 0 && ((col == 0) || (col == C - 1) || !(2 * tgaps > RT));
             }
-            const uint32_t bal = __ballot_sync(HB_FULL, keep), tbal = __ballot_sync(HB_FULL, tkeep);
-            if (lane == 0) { s_warp[0][wid] = __popc(bal); s_warp[1][wid] = __popc(tbal); }
-            pos = __popc(bal & ((1u << lane) - 1u));
-            tpos = __popc(tbal & ((1u << lane) - 1u));
+            keep = (col == 0) || (col == C - 1) || !(2 * gaps > RH);
         }
+        const uint32_t bal = __ballot_sync(HB_FULL, keep);
+        if (lane == 0) s_warp[half][hw] = __popc(bal);
         __syncthreads();
-        const int base = s_base[0], tbase = s_base[1];
-        if (tid < MC_TILE) {
-            int before = 0, tbefore = 0;
+        int before = 0, total = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < MC_TILE / 32; ++w2) { before += (w2 < wid) ? s_warp[0][w2] : 0; tbefore += (w2 < wid) ? s_warp[1][w2] : 0; }
-            if (keep) {
-                const int at = base + before + pos;
-                for (int r = 0; r < R; ++r) out[(size_t)r * C + at] = s_tile[r][tid] & 0x7Fu;
-            }
-            if (tkeep) {
-                const int at = tbase + tbefore + tpos;
-                for (int r = 0; r < R; ++r) {
-                    const int tr = s_trow[r];
-                    if (tr < 0) continue;
-                    const uint32_t b = s_tile[r][tid];
-                    tout[(size_t)tr * C + at] = (b & 0x80u) ? (uint8_t)HB_SYM_GAP : (uint8_t)b;
+        for (int w2 = 0; w2 < MC_TILE / 32; ++w2) { const int n = s_warp[half][w2]; before += (w2 < hw) ? n : 0; total += n; }
+        if (keep) {
+            const int at = base + before + __popc(bal & ((1u << lane) - 1u));
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+            int k = 0;                                    // rows of my matrix written so far (trow / row are dealt in row order)
+            for (int r = 0; r < R; ++r) {
+                uint32_t b = s_tile[r][ct];
+                if (half == 0) b &= 0x7Fu;
+                else {
+                    if (rw.trow[r] < 0) continue;
+                    if (b & 0x80u) b = HB_SYM_GAP;
+                }
+                out[(size_t)k * C + at] = (uint8_t)b;
+                const uint32_t bit = 1u << (k & 31);
+                a0 |= b == 0 ? bit : 0u; a1 |= b == 1 ? bit : 0u; a2 |= b == 2 ? bit : 0u;
+                a3 |= b == 3 ? bit : 0u; a4 |= b == 4 ? bit : 0u; a5 |= b == 5 ? bit : 0u;
+                ++k;
+                if ((k & 31) == 0 || k == RH) {
+                    if (pw != nullptr) {
+                        const int wd = (k - 1) >> 5;
+                        pw[(size_t)(0 * 4 + wd) * C + at] = a0; pw[(size_t)(1 * 4 + wd) * C + at] = a1;
+                        pw[(size_t)(2 * 4 + wd) * C + at] = a2; pw[(size_t)(3 * 4 + wd) * C + at] = a3;
+                        pw[(size_t)(4 * 4 + wd) * C + at] = a4; pw[(size_t)(5 * 4 + wd) * C + at] = a5;
+                    }
+                    a0 = a1 = a2 = a3 = a4 = a5 = 0;
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            int k0 = 0, k1 = 0;
-            for (int w2 = 0; w2 < MC_TILE / 32; ++w2) { k0 += s_warp[0][w2]; k1 += s_warp[1][w2]; }
-            s_base[0] = base + k0; s_base[1] = tbase + k1;
-        }
-        __syncthreads();
+        base += total;
+        // no barrier here: s_cq is only read before the tile's second barrier, s_tile is rewritten after the next tile's first
+        // barrier and s_warp after its second
     }
-    if (tid == 0) { calls[ti].clean_cols = s_base[0]; if (tt >= 0) calls[tt].clean_cols = s_base[1]; }
+    if (ct == 0) { if (half == 0) calls[ti].clean_cols = base; else if (tt >= 0) calls[tt].clean_cols = base; }
 }
 
 }  // namespace
@@ -686,12 +714,14 @@ cudaError_t hb_qhsp_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* 
                                                                   gseq2, gnmask, goff, glen, n_contig, tot, out);
     return cudaGetLastError();
 }
-cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* task_cand, const int32_t* trunc_of_full, uint32_t n_full,
+cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* order, const uint32_t* task_cand, const int32_t* trunc_of_full,
+                                uint32_t n_full,
                                 const HbLocus* pairs, const uint32_t* pair_off, const HbAln* alns, const uint32_t* qrec_unit_off,
                                 const uint32_t* qrec, const uint32_t* col_off, const uint32_t* colq, const uint32_t* gseq2,
-                                const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* clean, HbVoteCall* calls, cudaStream_t s) {
+                                const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* clean, uint32_t* planes, HbVoteCall* calls,
+                                cudaStream_t s) {
     if (n_full == 0) return cudaSuccess;
-    msa_clean_kernel<<<n_full, MC_THREADS, 0, s>>>(tasks, task_cand, trunc_of_full, pairs, pair_off, alns, qrec_unit_off, qrec, col_off,
-                                                   colq, gseq2, gnmask, tot, flank, clean, calls);
+    msa_clean_kernel<<<n_full, MC_THREADS, 0, s>>>(tasks, order, task_cand, trunc_of_full, pairs, pair_off, alns, qrec_unit_off, qrec, col_off,
+                                                   colq, gseq2, gnmask, tot, flank, clean, planes, calls);
     return cudaGetLastError();
 }

@@ -32,8 +32,11 @@ cudaError_t hb_qhsp_launch(const HbLocus* pairs, uint32_t n_pairs, const HbAln* 
                            uint32_t n_contig, uint64_t tot, hb_qhsp* out, cudaStream_t s);
 // star MSA + sparse-column removal fused: the clean matrices of all judge tasks straight from the edit records, a CTA per
 // full task also producing its truncated-member task trunc_of_full[t] (-1: none); calls[].clean_cols is set for both.
-// The raw matrix is never written.
-cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* task_cand, const int32_t* trunc_of_full, uint32_t n_full,
+// The raw matrix is never written.  planes != nullptr: the six bit-planes of every kept column over all rows of each matrix
+// are written too (plane_off of the task; hb_vote_launch is then told they are prebuilt).
+cudaError_t hb_msa_clean_launch(const HbVoteTask* tasks, const uint32_t* order /* n_full task ids, CTA b takes order[b] */,
+                                const uint32_t* task_cand, const int32_t* trunc_of_full, uint32_t n_full,
                                 const HbLocus* pairs, const uint32_t* pair_off, const HbAln* alns, const uint32_t* qrec_unit_off,
                                 const uint32_t* qrec, const uint32_t* col_off, const uint32_t* colq, const uint32_t* gseq2,
-                                const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* clean, HbVoteCall* calls, cudaStream_t s);
+                                const uint32_t* gnmask, uint64_t tot, int flank, uint8_t* clean, uint32_t* planes, HbVoteCall* calls,
+                                cudaStream_t s);

@@ -641,14 +641,24 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
         std::vector<int32_t> trunc_of_full(n_full, -1);
         for (uint32_t k = 0; k < trunc_to_full.size(); ++k) trunc_of_full[trunc_to_full[k]] = (int32_t)(n_full + k);
         HB_CUDA_OK(cudaMemcpyAsync(LB("v.f2t").p, trunc_of_full.data(), sizeof(int32_t) * n_full, cudaMemcpyHostToDevice, s));
+        // CTA per candidate: start the largest matrices first so that a long one is never the last to be scheduled
+        ENSURE_L("v.order", sizeof(uint32_t) * (n_full + 1));
+        std::vector<uint32_t> order(n_full);
+        for (uint32_t k = 0; k < n_full; ++k) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return (uint64_t)tasks[a].R * (uint64_t)tasks[a].C > (uint64_t)tasks[b].R * (uint64_t)tasks[b].C; });
+        HB_CUDA_OK(cudaMemcpyAsync(LB("v.order").p, order.data(), sizeof(uint32_t) * n_full, cudaMemcpyHostToDevice, s));
         HB_CUDA_OK(cudaMemcpyAsync(LB("v.tasks").p, tasks.data(), sizeof(HbVoteTask) * n_tasks, cudaMemcpyHostToDevice, s));
         HB_CUDA_OK(cudaMemcpyAsync(LB("v.task_cand").p, task_cand.data(), sizeof(uint32_t) * n_tasks, cudaMemcpyHostToDevice, s));
         HB_CUDA_OK(cudaMemsetAsync(LB("v.calls").p, 0, sizeof(HbVoteCall) * n_tasks, s));
-        HB_CUDA_OK(hb_msa_clean_launch(LB("v.tasks").as<HbVoteTask>(), LB("v.task_cand").as<uint32_t>(), LB("v.f2t").as<int32_t>(), n_full,
+        HB_CUDA_OK(hb_msa_clean_launch(LB("v.tasks").as<HbVoteTask>(), LB("v.order").as<uint32_t>(), LB("v.task_cand").as<uint32_t>(),
+                                       LB("v.f2t").as<int32_t>(), n_full,
                                        LB("p.pairs").as<HbLocus>(), LB("s.pair_off").as<uint32_t>(), LB("p.alns").as<HbAln>(),
                                        LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(), LB("m.col_off").as<uint32_t>(),
                                        LB("m.colq").as<uint32_t>(), ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(),
-                                       tot, flank, LB("v.clean").as<uint8_t>(), LB("v.calls").as<HbVoteCall>(), s));
+                                       tot, flank, LB("v.clean").as<uint8_t>(),
+                                       prm->te_type == 1 ? nullptr : LB("v.planes").as<uint32_t>(),   // (the Helitron judge builds its own)
+                                       LB("v.calls").as<HbVoteCall>(), s));
         ++launches;
         HB_CUDA_OK(hb_vote_launch(LB("v.tasks").as<HbVoteTask>(), (int)n_tasks, nullptr,
                                   LB("v.clean").as<uint8_t>(), LB("v.planes").as<uint32_t>(), LB("v.matches").p,

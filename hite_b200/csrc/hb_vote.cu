@@ -300,9 +300,11 @@ struct Planes {
     int stride;          // C
     int nw;              // words in use
     int row_num;
-    uint32_t rowmask[4];
+    uint32_t rowmask[4]; // the rows that take part: planes built by build_planes hold exactly the kept rows in list order (a prefix
+                         // mask); planes prebuilt over ALL matrix rows (hb_msa.cu::msa_clean_kernel) are masked down to the kept
+                         // rows -- counts and first-seen order (ascending row) are the same either way
     __device__ __forceinline__ uint32_t w(int sym, int word, int col) const {
-        return p[(size_t)(sym * 4 + word) * stride + col];
+        return p[(size_t)(sym * 4 + word) * stride + col] & rowmask[word];
     }
     __device__ __forceinline__ int count(int sym, int col) const {
         int c = 0;
@@ -695,7 +697,7 @@ __device__ __noinline__ bool front_anchors(const HbVoteTask& t, HbVoteCall& call
 // phase b: full-length member filter (:9196-9225) + bit-planes of the kept rows.  false: verdict 'fl1'.
 __device__ __noinline__ bool front_members(const HbVoteTask& t, HbVoteCall& call, const uint8_t* __restrict__ m,
                                            uint32_t* __restrict__ planes, int as, int ae, int fl1_copy_num_is_rows,
-                                           unsigned short* rows, int lane, Front& F) {
+                                           unsigned short* rows, int lane, Front& F, int prebuilt) {
     const int R = t.R, C = t.C, Cc = F.Cc;
     int e_lo, e_hi;
     py_slice(Cc, (long long)ae - 10, (ae + 10 < Cc) ? ae + 10 : Cc, &e_lo, &e_hi);
@@ -706,7 +708,17 @@ __device__ __noinline__ bool front_members(const HbVoteTask& t, HbVoteCall& call
         return false;
     }
     call.copy_num = row_num;
-    build_planes(F.P, planes + t.plane_off, m, C, Cc, rows, row_num, lane);
+    if (!prebuilt) { build_planes(F.P, planes + t.plane_off, m, C, Cc, rows, row_num, lane); return true; }
+    Planes& P = F.P;
+    P.p = planes + t.plane_off; P.stride = C; P.nw = (R + 31) >> 5; P.row_num = row_num;
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+        uint32_t mk = 0;
+        for (int k = lane; k < row_num; k += 32) mk |= (rows[k] >> 5) == wd ? 1u << (rows[k] & 31) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mk |= __shfl_xor_sync(HB_FULL, mk, o);
+        P.rowmask[wd] = mk;
+    }
     return true;
 }
 // phase c: outermost valid columns (:9269-9294) + homology boundaries (:9297-9308).
@@ -745,7 +757,7 @@ __device__ bool judge_front_v3(const HbVoteTask& t, HbVoteCall& call, const uint
                                int* vc, unsigned short* rows, int* cnt, int lane, Front& F) {
     int as, ae;
     if (!front_anchors(t, call, m, matches, cands, cnt, lane, F, &as, &ae)) return false;
-    if (!front_members(t, call, m, planes, as, ae, fl1_copy_num_is_rows, rows, lane, F)) return false;
+    if (!front_members(t, call, m, planes, as, ae, fl1_copy_num_is_rows, rows, lane, F, 0)) return false;
     return front_boundaries(call, as, ae, thr_many, vc, lane, F);
 }
 
@@ -819,7 +831,7 @@ hb_judge_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 hb_judge_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
                   uint32_t* __restrict__ planes, Match* __restrict__ matches, HbVoteCall* __restrict__ calls,
-                  int fl1_copy_num_is_rows) {
+                  int fl1_copy_num_is_rows, int prebuilt) {
     __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * WARPS_PER_CTA + wid;
@@ -831,7 +843,7 @@ hb_judge_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
     unsigned short* rows = s_rows[wid];
     Front F;
     F.Cc = st->Cc;
-    const bool go = front_members(t, call, clean + t.clean_off, planes, st->as, st->ae, fl1_copy_num_is_rows, rows, lane, F);
+    const bool go = front_members(t, call, clean + t.clean_off, planes, st->as, st->ae, fl1_copy_num_is_rows, rows, lane, F, prebuilt);
     for (int k = lane; k < F.row_num; k += 32) st->rows[k] = rows[k];
     if (lane == 0) {
         st->go = go ? 1 : 0; st->row_num = F.row_num;
@@ -1494,9 +1506,10 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
     // d_raw == nullptr: the clean matrices (and calls[].clean_cols) were already produced by hb_msa.cu::msa_clean_kernel
     if (d_raw) hb_clean_kernel<<<n, CLEAN_THREADS, 0, stream>>>(d_tasks, d_raw, d_clean, d_calls);
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int prebuilt = d_raw == nullptr;               // ... and so were the bit-planes over all rows (TIR / non-LTR judges)
     if (te_type == 0) {
         hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);
-        hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 0);
+        hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 0, prebuilt);
         hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls, 0.7);
         hb_judge_d_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
                                                                    d_calls);
@@ -1508,7 +1521,7 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
                                                                       d_calls);
     } else if (te_type == 2) {
         hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);
-        hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 1);
+        hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 1, prebuilt);
         hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls, 0.8);
         if (avg_rows > 48)
             hb_judge_v9_tail_kernel<ROW_WARPS><<<n, ROW_WARPS * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches,
