@@ -259,85 +259,91 @@ chain_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pai
     }
 }
 
-// S8 dedup + S9 "max_rows longest": warp per candidate
-constexpr int SEL_MAX = 512;
-__global__ void __launch_bounds__(128)
+// S8 dedup + S9 "max_rows longest": CTA per candidate, the compared fields staged in shared memory (both steps compare every
+// copy with every other one: as a warp per candidate reading the records from global memory, a 300-locus candidate took
+// milliseconds and set the kernel's duration on high-copy genomes)
+constexpr int SEL_MAX = 512, SEL_THREADS = 128;
+__global__ void __launch_bounds__(SEL_THREADS)
 copy_select_kernel(const HbLocus* __restrict__ pairs, const uint32_t* __restrict__ pair_off, uint32_t n_cand,
                    int max_rows, int trunc_gate, int rows_first, const int32_t* __restrict__ crank, HbAln* __restrict__ alns,
                    uint32_t* __restrict__ n_rows, uint32_t* __restrict__ n_trows) {
-    __shared__ uint8_t s_keep[4][SEL_MAX];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t c = blockIdx.x * 4 + wid;
-    if (c >= n_cand) return;
+    __shared__ long long s_js[SEL_MAX], s_je[SEL_MAX];
+    __shared__ int s_len[SEL_MAX];
+    __shared__ uint8_t s_rel[SEL_MAX], s_raw[SEL_MAX], s_keep[SEL_MAX];
+    __shared__ int s_nk;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t c = blockIdx.x;
     const uint32_t p0 = pair_off[c], p1 = pair_off[c + 1];
     const int n = min((int)(p1 - p0), SEL_MAX);
-    uint8_t* keep = s_keep[wid];
-    for (int x = lane; x < n; x += 32) {
+    uint8_t* keep = s_keep;
+    for (int x = tid; x < n; x += SEL_THREADS) {
         const HbAln a = alns[p0 + x];
-        int k = a.keep;
+        s_js[x] = a.j_s; s_je[x] = a.j_e; s_len[x] = a.ext_len; s_raw[x] = a.keep ? 1 : 0; s_rel[x] = (uint8_t)pairs[p0 + x].rel;
+    }
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int x = tid; x < n; x += SEL_THREADS) {
+        int k = s_raw[x];
         if (k) {
-            const uint32_t rel = pairs[p0 + x].rel;
-            for (int y = 0; y < x; ++y) {
-                const HbAln b = alns[p0 + y];
-                if (b.keep && pairs[p0 + y].rel == rel && b.j_s == a.j_s && b.j_e == a.j_e) { k = 0; break; }
-            }
+            const uint8_t rel = s_rel[x];
+            const long long js = s_js[x], je = s_je[x];
+            for (int y = 0; y < x; ++y)
+                if (s_raw[y] && s_rel[y] == rel && s_js[y] == js && s_je[y] == je) { k = 0; break; }
         }
         keep[x] = (uint8_t)k;
+        mine += k;
     }
-    __syncwarp();
-    int nk = 0;
-    for (int x = lane; x < n; x += 32) nk += keep[x];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) nk += __shfl_xor_sync(HB_FULL, nk, o);
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(HB_FULL, mine, o);
+    if (lane == 0 && mine) atomicAdd(&s_nk, mine);
+    __syncthreads();
+    const int nk = s_nk;
     if (nk > max_rows && rows_first) {                    // FiLTR's extract_copies: the first max_rows members of the file
-        for (int x = lane; x < n; x += 32) {
+        for (int x = tid; x < n; x += SEL_THREADS) {
             if (!keep[x]) continue;
             int before = 0;
             for (int y = 0; y < x; ++y) before += keep[y] ? 1 : 0;
             if (before >= max_rows) keep[x] = 2;
         }
-        __syncwarp();
-        for (int x = lane; x < n; x += 32) if (keep[x] == 2) keep[x] = 0;
-        __syncwarp();
     } else if (nk > max_rows) {
-        for (int x = lane; x < n; x += 32) {
+        for (int x = tid; x < n; x += SEL_THREADS) {
             if (!keep[x]) continue;
             // the 100 longest, length ties to the bytewise larger member name (sort -nk 2 -r, tools/ready_for_MSA.sh:63)
-            const HbAln ax = alns[p0 + x];
-            const uint32_t relx = pairs[p0 + x].rel;
-            const int lx = ax.ext_len;
+            const int lx = s_len[x];
             int longer = 0;
             for (int y = 0; y < n; ++y) {
                 if (y == x || !keep[y]) continue;
-                const int ly = alns[p0 + y].ext_len;
+                const int ly = s_len[y];
                 if (ly > lx) ++longer;
-                else if (ly == lx && name_greater(crank, alns[p0 + y], pairs[p0 + y].rel, ax, relx)) ++longer;
+                else if (ly == lx && name_greater(crank, alns[p0 + y], s_rel[y], alns[p0 + x], s_rel[x])) ++longer;
             }
             if (longer >= max_rows) keep[x] = 2;
         }
-        __syncwarp();
-        for (int x = lane; x < n; x += 32) if (keep[x] == 2) keep[x] = 0;
-        __syncwarp();
     }
+    __syncthreads();
+    for (int x = tid; x < n; x += SEL_THREADS) if (keep[x] == 2) keep[x] = 0;
+    __syncthreads();
     // rows of the full MSA, and of the truncated-member pass (Util.py:8116-8124, :10442-10446): the kept
     // copies whose extended length exceeds 1000 bp, reduced to their first 500 + last 500 bases
-    int rows = 0, trows = 0;
-    for (int x0 = 0; x0 < n; x0 += 32) {
-        const int x = x0 + lane;
-        const bool k = x < n && keep[x];
-        const bool lg = trunc_gate && k && alns[p0 + x].ext_len > 1000;
-        const uint32_t bal = __ballot_sync(HB_FULL, k), balt = __ballot_sync(HB_FULL, lg);
-        if (x < n) {
-            alns[p0 + x].keep = k ? 1 : 0;
-            alns[p0 + x].row = k ? rows + __popc(bal & ((1u << lane) - 1u)) : -1;
-            alns[p0 + x].trow = lg ? trows + __popc(balt & ((1u << lane) - 1u)) : -1;
+    if (tid < 32) {
+        int rows = 0, trows = 0;
+        for (int x0 = 0; x0 < n; x0 += 32) {
+            const int x = x0 + lane;
+            const bool k = x < n && keep[x];
+            const bool lg = trunc_gate && k && s_len[x < n ? x : 0] > 1000;
+            const uint32_t bal = __ballot_sync(HB_FULL, k), balt = __ballot_sync(HB_FULL, lg);
+            if (x < n) {
+                alns[p0 + x].keep = k ? 1 : 0;
+                alns[p0 + x].row = k ? rows + __popc(bal & ((1u << lane) - 1u)) : -1;
+                alns[p0 + x].trow = lg ? trows + __popc(balt & ((1u << lane) - 1u)) : -1;
+            }
+            rows += __popc(bal);
+            trows += __popc(balt);
         }
-        rows += __popc(bal);
-        trows += __popc(balt);
+        if (lane == 0) { n_trows[c] = (uint32_t)trows; n_rows[c] = (uint32_t)rows; }
     }
-    if (lane == 0) n_trows[c] = (uint32_t)trows;
-    for (uint32_t x = p0 + n + lane; x < p1; x += 32) { alns[x].keep = 0; alns[x].row = -1; alns[x].trow = -1; }
-    if (lane == 0) n_rows[c] = (uint32_t)rows;
+    for (uint32_t x = p0 + n + tid; x < p1; x += SEL_THREADS) { alns[x].keep = 0; alns[x].row = -1; alns[x].trow = -1; }
 }
 
 // S10a: insertion-column widths, warp per kept pair
@@ -478,15 +484,18 @@ msa_write_kernel(const HbLocus* __restrict__ pairs, uint32_t n_pairs, const HbAl
     }
 }
 
-// S10d + sparse-column removal fused (msa_write_kernel followed by hb_vote.cu::hb_clean_kernel, without the raw matrix ever
-// reaching HBM): one CTA per candidate, producing the clean matrix of its full judge task AND of its truncated-member task
-// (rows = its copies longer than 1000 bp, cells outside each row's first / last 500 bases blanked) from ONE computation of
-// the symbols.  The matrix is built 128 columns at a time in shared memory -- the tile's column map is staged once, a warp
-// per row derives the row's symbols from it and the pair's edit records exactly like msa_write_kernel, bit 7 of a cell
-// marks "blank in the truncated matrix" -- then every column of the tile is counted twice (all rows; truncated rows), kept or
-// dropped by the reference's rule (remove_sparse_col_in_align_file, module/Util.py:10379-10391: first and last column always
-// kept, a column goes when gaps > rows / 2) and the kept columns are appended to the two clean matrices (row stride C).
-constexpr int MC_TILE = 128, MC_THREADS = 256, MC_MAXROWS = 104;
+// S10d + sparse-column removal + bit-planes fused (msa_write_kernel, hb_vote.cu::hb_clean_kernel and build_planes without the
+// raw matrix ever reaching HBM): one CTA per candidate, producing the clean matrix of its full judge task AND of its
+// truncated-member task (rows = its copies longer than 1000 bp, cells outside each row's first / last 500 bases blanked)
+// from ONE computation of the symbols.  The matrices are built 128 columns at a time in shared memory, COLUMN-major (a
+// column's rows are consecutive bytes, 27 words per column so that a warp's columns fall into distinct banks): a warp per
+// row derives the row's symbols from the staged column map and the pair's edit records exactly like msa_write_kernel and
+// drops them into the full tile at its row and into the truncated tile at its truncated row.  Then a thread per column and
+// matrix works on four rows per 32-bit word: gaps are counted by a zero-byte test, the column is kept or dropped by the
+// reference's rule (remove_sparse_col_in_align_file, module/Util.py:10379-10391: first and last column always kept, a column
+// goes when gaps > rows / 2), kept columns are appended to the clean matrix (row stride C) and their six bit-planes (what the
+// judges vote on) are derived from three code-bit planes gathered with one multiply per word.
+constexpr int MC_TILE = 128, MC_THREADS = 256, MC_MAXROWS = 104, MC_PITCH = 108;
 
 // per-row constants of a candidate's kept copies, staged once per CTA (struct of arrays in shared memory)
 struct McRows {
@@ -496,8 +505,9 @@ struct McRows {
     uint8_t rel[MC_MAXROWS];
 };
 
-// four adjacent cells of one row, branch-free so that the 4 edit-record loads and then the 8 genome loads are in flight together
-__device__ __forceinline__ uint32_t mc_row_word(const McRows& rw, int r, const uint32_t* __restrict__ s_cq4, int col0, int C,
+// four cells of one row (columns col0 + 32 k), branch-free so that the 4 edit-record loads and then the 8 genome loads are in
+// flight together; byte k = symbol, bit 7 = blank in the truncated-member matrix
+__device__ __forceinline__ uint32_t mc_row_word(const McRows& rw, int r, const uint32_t (&e)[4], int col0, int C,
                                                 const uint32_t* __restrict__ qrec, const uint32_t* __restrict__ gseq2,
                                                 const uint32_t* __restrict__ gnmask, uint32_t totm1, int flank) {
     const uint32_t* qr = qrec + ((size_t)rw.qoff[r] << 5);
@@ -509,20 +519,20 @@ __device__ __forceinline__ uint32_t mc_row_word(const McRows& rw, int r, const u
     int q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        q[k] = (int)(s_cq4[k] >> 8) - flank;
+        q[k] = (int)(e[k] >> 8) - flank;
         v[k] = qr[min(max(q[k], i_s), i_e)];
     }
     uint32_t j[4], nm[4], sq[4];
     bool have[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t slot = s_cq4[k] & 255u;
+        const uint32_t slot = e[k] & 255u;
         const bool inside = q[k] >= i_s && q[k] <= i_e, left = q[k] < i_s;
         const bool have_in = slot == 0 ? ((v[k] >> 24) & 1u) == 0 : slot <= ((v[k] >> 16) & 255u);
         const bool have_out = slot == 0 && (left ? q[k] >= i_s - flank : q[k] <= i_e + flank);
         const uint32_t j_in = j0 + (uint32_t)q[k] + (v[k] & 0xFFFFu) - 32768u + slot;
         const uint32_t j_out = left ? js - (uint32_t)(i_s - q[k]) : je + (uint32_t)(q[k] - i_e);
-        have[k] = (col0 + k < C) && (inside ? have_in : have_out);
+        have[k] = (col0 + 32 * k < C) && (inside ? have_in : have_out);
         j[k] = inside ? j_in : j_out;
         const uint32_t pos = min(rel ? totm1 - j[k] : j[k], totm1);       // a cell without a base reads a harmless word
         nm[k] = (gnmask[pos >> 5] >> (pos & 31u)) & 1u;
@@ -547,10 +557,11 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
                  const uint32_t* __restrict__ col_off, const uint32_t* __restrict__ colq, const uint32_t* __restrict__ gseq2,
                  const uint32_t* __restrict__ gnmask, uint64_t tot, int flank, uint8_t* __restrict__ clean,
                  uint32_t* __restrict__ planes, HbVoteCall* __restrict__ calls) {
-    __shared__ __align__(16) uint8_t s_tile[MC_MAXROWS][MC_TILE];
-    __shared__ __align__(16) uint32_t s_cq[MC_TILE];
+    __shared__ __align__(16) uint8_t s_tile[2][MC_TILE][MC_PITCH];     // [full | truncated][column][row]
+    __shared__ uint32_t s_cq[MC_TILE];
     __shared__ McRows rw;
     __shared__ int s_warp[2][MC_TILE / 32];
+    static_assert(HB_SYM_GAP == 5 && MC_PITCH % 4 == 0 && (MC_PITCH / 4) % 2 == 1 && MC_PITCH >= MC_MAXROWS, "tile layout");
     const uint32_t ti = order[blockIdx.x];                // full task; the largest matrices are started first
     const int tt = trunc_of_full[ti];                     // its truncated-member task, or -1
     const HbVoteTask t = tasks[ti];
@@ -568,6 +579,8 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
             rw.i_s[r] = a.i_s; rw.i_e[r] = a.i_e; rw.trow[r] = (short)a.trow; rw.rel[r] = (uint8_t)pr.rel;
         }
     }
+    // rows R.. (RT..) of a tile column are never written: zero = "not a gap", and they stay outside the planes' valid bits
+    for (int i = tid; i < 2 * MC_TILE * MC_PITCH / 4; i += MC_THREADS) reinterpret_cast<uint32_t*>(&s_tile[0][0][0])[i] = 0u;
     __syncthreads();
     const uint32_t* cq = colq + col_off[c];
     const uint32_t totm1 = (uint32_t)(tot - 1);
@@ -575,36 +588,42 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
     const int half = tid >> 7, ct = tid & (MC_TILE - 1), hw = wid & 3;
     uint8_t* out = half == 0 ? clean + t.clean_off : (tt >= 0 ? clean + tasks[tt].clean_off : nullptr);
     const int RH = half == 0 ? R : RT;
+    const int G = (RH + 3) >> 2;                          // 4-row words of my column
+    const uint32_t* colw = reinterpret_cast<const uint32_t*>(&s_tile[half][ct][0]);
     // six bit-planes of every kept column over ALL rows of my matrix (row k = bit k & 31 of word k >> 5): what the judges
-    // vote on (hb_vote.cu::Planes; they mask the rows they keep), built here while the column is in shared memory
+    // vote on (hb_vote.cu::Planes; they mask the rows they keep)
     uint32_t* pw = planes == nullptr ? nullptr : planes + (half == 0 ? t.plane_off : (tt >= 0 ? tasks[tt].plane_off : 0));
     int base = 0;                                         // kept columns of my matrix so far
     for (int c0 = 0; c0 < C; c0 += MC_TILE) {
         if (tid < MC_TILE) s_cq[tid] = c0 + tid < C ? cq[c0 + tid] : 0u;
         __syncthreads();
-        // ---- the tile's symbols: warp per row (two rows in flight), 4 columns per lane ----
+        // ---- the tile's symbols: warp per row (two rows in flight), columns lane + 32 k ----
         uint32_t e4[4];
-        *reinterpret_cast<uint4*>(e4) = *reinterpret_cast<const uint4*>(&s_cq[4 * lane]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e4[k] = s_cq[lane + 32 * k];
         for (int r = wid; r < R; r += 2 * (MC_THREADS / 32)) {
-            const int r2 = r + MC_THREADS / 32;
-            const uint32_t wa = mc_row_word(rw, r, e4, c0 + 4 * lane, C, qrec, gseq2, gnmask, totm1, flank);
-            const uint32_t wb = mc_row_word(rw, min(r2, R - 1), e4, c0 + 4 * lane, C, qrec, gseq2, gnmask, totm1, flank);
-            *reinterpret_cast<uint32_t*>(&s_tile[r][4 * lane]) = wa;
-            if (r2 < R) *reinterpret_cast<uint32_t*>(&s_tile[r2][4 * lane]) = wb;
+            const int r2 = min(r + MC_THREADS / 32, R - 1);              // (r2 == r: computed twice, stored twice: harmless)
+            const uint32_t wa = mc_row_word(rw, r, e4, c0 + lane, C, qrec, gseq2, gnmask, totm1, flank);
+            const uint32_t wb = mc_row_word(rw, r2, e4, c0 + lane, C, qrec, gseq2, gnmask, totm1, flank);
+            const int ta = rw.trow[r], tb = rw.trow[r2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t ba = (wa >> (8 * k)) & 255u, bb = (wb >> (8 * k)) & 255u;
+                s_tile[0][lane + 32 * k][r] = (uint8_t)(ba & 0x7Fu);
+                s_tile[0][lane + 32 * k][r2] = (uint8_t)(bb & 0x7Fu);
+                if (ta >= 0) s_tile[1][lane + 32 * k][ta] = (ba & 0x80u) ? (uint8_t)HB_SYM_GAP : (uint8_t)ba;
+                if (tb >= 0) s_tile[1][lane + 32 * k][tb] = (bb & 0x80u) ? (uint8_t)HB_SYM_GAP : (uint8_t)bb;
+            }
         }
         __syncthreads();
-        // ---- sparse columns (remove_sparse_col_in_align_file): thread per column and matrix ----
+        // ---- sparse columns (remove_sparse_col_in_align_file): thread per column and matrix, four rows per word ----
         const int col = c0 + ct;
         int keep = 0;
         if (RH > 0 && col < C) {
             int gaps = 0;
-            if (half == 0) {
-                for (int r = 0; r < R; ++r) gaps += (s_tile[r][ct] & 0x7Fu) == HB_SYM_GAP;
-            } else {
-                for (int r = 0; r < R; ++r) {
-                    const uint32_t b = s_tile[r][ct];
-                    gaps += (rw.trow[r] >= 0) && (b == HB_SYM_GAP || (b & 0x80u));
-                }
+            for (int g = 0; g < G; ++g) {
+                const uint32_t x = colw[g] ^ 0x05050505u;                 // symbols are < 0x80: exact zero-byte test
+                gaps += __popc(~((x + 0x7F7F7F7Fu) | x) & 0x80808080u);
             }
             keep = (col == 0) || (col == C - 1) || !(2 * gaps > RH);
         }
@@ -616,34 +635,40 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
         for (int w2 = 0; w2 < MC_TILE / 32; ++w2) { const int n = s_warp[half][w2]; before += (w2 < hw) ? n : 0; total += n; }
         if (keep) {
             const int at = base + before + __popc(bal & ((1u << lane) - 1u));
-            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-            int k = 0;                                    // rows of my matrix written so far (trow / row are dealt in row order)
-            for (int r = 0; r < R; ++r) {
-                uint32_t b = s_tile[r][ct];
-                if (half == 0) b &= 0x7Fu;
-                else {
-                    if (rw.trow[r] < 0) continue;
-                    if (b & 0x80u) b = HB_SYM_GAP;
+            uint8_t* op = out + at;
+            uint32_t b0 = 0, b1 = 0, b2 = 0;              // code-bit planes of the current 32 rows
+            for (int g = 0; g < G; ++g) {
+                const uint32_t w = colw[g];
+                const int r = 4 * g;
+                if (r + 3 < RH) {
+                    op[0] = (uint8_t)w; op[(size_t)C] = (uint8_t)(w >> 8); op[2 * (size_t)C] = (uint8_t)(w >> 16);
+                    op[3 * (size_t)C] = (uint8_t)(w >> 24);
+                } else {
+                    op[0] = (uint8_t)w;
+                    if (r + 1 < RH) op[(size_t)C] = (uint8_t)(w >> 8);
+                    if (r + 2 < RH) op[2 * (size_t)C] = (uint8_t)(w >> 16);
                 }
-                out[(size_t)k * C + at] = (uint8_t)b;
-                const uint32_t bit = 1u << (k & 31);
-                a0 |= b == 0 ? bit : 0u; a1 |= b == 1 ? bit : 0u; a2 |= b == 2 ? bit : 0u;
-                a3 |= b == 3 ? bit : 0u; a4 |= b == 4 ? bit : 0u; a5 |= b == 5 ? bit : 0u;
-                ++k;
-                if ((k & 31) == 0 || k == RH) {
-                    if (pw != nullptr) {
-                        const int wd = (k - 1) >> 5;
-                        pw[(size_t)(0 * 4 + wd) * C + at] = a0; pw[(size_t)(1 * 4 + wd) * C + at] = a1;
-                        pw[(size_t)(2 * 4 + wd) * C + at] = a2; pw[(size_t)(3 * 4 + wd) * C + at] = a3;
-                        pw[(size_t)(4 * 4 + wd) * C + at] = a4; pw[(size_t)(5 * 4 + wd) * C + at] = a5;
+                op += 4 * (size_t)C;
+                if (pw != nullptr) {
+                    // bits 0 / 8 / 16 / 24 -> one nibble: x * 0x01020408 puts them at bits 24..27 without carries
+                    const int sh = 4 * (g & 7);
+                    b0 |= (((w & 0x01010101u) * 0x01020408u) >> 24) << sh;
+                    b1 |= ((((w >> 1) & 0x01010101u) * 0x01020408u) >> 24) << sh;
+                    b2 |= ((((w >> 2) & 0x01010101u) * 0x01020408u) >> 24) << sh;
+                    if ((g & 7) == 7 || g == G - 1) {
+                        const int wd = g >> 3, left = RH - 32 * wd;
+                        const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : (1u << left) - 1u;
+                        const size_t o = (size_t)wd * C + at, pl = 4 * (size_t)C;
+                        pw[o] = ~b2 & ~b1 & ~b0 & valid; pw[o + pl] = ~b2 & ~b1 & b0; pw[o + 2 * pl] = ~b2 & b1 & ~b0;
+                        pw[o + 3 * pl] = ~b2 & b1 & b0; pw[o + 4 * pl] = b2 & ~b1 & ~b0; pw[o + 5 * pl] = b2 & ~b1 & b0;
+                        b0 = b1 = b2 = 0;
                     }
-                    a0 = a1 = a2 = a3 = a4 = a5 = 0;
                 }
             }
         }
         base += total;
-        // no barrier here: s_cq is only read before the tile's second barrier, s_tile is rewritten after the next tile's first
-        // barrier and s_warp after its second
+        // no barrier here: s_cq is only read before the tile's second barrier, the tiles are rewritten after the next tile's
+        // first barrier and s_warp after its second
     }
     if (ct == 0) { if (half == 0) calls[ti].clean_cols = base; else if (tt >= 0) calls[tt].clean_cols = base; }
 }
@@ -667,7 +692,7 @@ cudaError_t hb_copy_select_launch(const HbLocus* pairs, const uint32_t* pair_off
                                   int trunc_gate, int rows_first, const int32_t* crank, HbAln* alns, uint32_t* n_rows,
                                   uint32_t* n_trows, cudaStream_t s) {
     if (n_cand == 0) return cudaSuccess;
-    copy_select_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(pairs, pair_off, n_cand, max_rows, trunc_gate, rows_first, crank, alns,
+    copy_select_kernel<<<n_cand, SEL_THREADS, 0, s>>>(pairs, pair_off, n_cand, max_rows, trunc_gate, rows_first, crank, alns,
                                                         n_rows, n_trows);
     return cudaGetLastError();
 }

@@ -532,6 +532,30 @@ __device__ __noinline__ bool row_anchor(const uint8_t* __restrict__ row, int Cc,
     return true;
 }
 
+// Does the row hold at least one end with distance <= 2 for BOTH patterns -- i.e. would row_anchor succeed?  Same lane chunks
+// and the same 40-symbol warm-up as anchor_scan_row, but no match lists, no start search and the pattern masks in registers:
+// used to look for the first anchored row of a matrix with many warps at once (hb_judge_a2_kernel).
+__device__ __noinline__ bool row_has_anchors(const uint8_t* __restrict__ row, int Cc, const Pattern& P1, const Pattern& P2, int lane) {
+    const int chunk = (Cc + 31) >> 5;
+    const int lo = min(Cc, lane * chunk), hi = min(Cc, lo + chunk);
+    const uint32_t a0 = P1.peq[0], a1 = P1.peq[1], a2 = P1.peq[2], a3 = P1.peq[3], a4 = P1.peq[4];
+    const uint32_t b0 = P2.peq[0], b1 = P2.peq[1], b2 = P2.peq[2], b3 = P2.peq[3], b4 = P2.peq[4];
+    const uint32_t top1 = 1u << (P1.m - 1), top2 = 1u << (P2.m - 1);
+    Myers M1, M2; M1.init(P1.m); M2.init(P2.m);
+    int c0 = lo, need = 40;
+    while (c0 > 0 && need > 0) { --c0; need -= (row[c0] != HB_SYM_GAP); }
+    bool f1 = false, f2 = false;
+    for (int c = c0; c < hi; ++c) {
+        const int s = row[c];
+        if (s == HB_SYM_GAP) continue;
+        const uint32_t e1 = s == 0 ? a0 : s == 1 ? a1 : s == 2 ? a2 : s == 3 ? a3 : a4;
+        const uint32_t e2 = s == 0 ? b0 : s == 1 ? b1 : s == 2 ? b2 : s == 3 ? b3 : b4;
+        M1.step(e1, top1); M2.step(e2, top2);
+        if (c >= lo) { f1 |= M1.score <= 2; f2 |= M2.score <= 2; }
+    }
+    return __any_sync(HB_FULL, f1) && __any_sync(HB_FULL, f2);
+}
+
 // six bit-planes of the listed rows (row k of the list = bit k&31 of word k>>5)
 __device__ __noinline__ void build_planes(Planes& P, uint32_t* __restrict__ pw, const uint8_t* __restrict__ m, int C, int Cc,
                              const unsigned short* rows, int row_num, int lane) {
@@ -671,7 +695,8 @@ struct Front {
 // phase a: call defaults + anchors (:9151-9187).  false: `call` holds the verdict ('nb').
 __device__ __noinline__ bool front_anchors(const HbVoteTask& t, HbVoteCall& call, const uint8_t* __restrict__ m,
                                            Match* __restrict__ matches, const uint8_t* __restrict__ cands, int* cnt,
-                                           int lane, Front& F, int* as_out, int* ae_out) {
+                                           int lane, Front& F, int* as_out, int* ae_out, int max_rows = 1 << 30,
+                                           bool* rows_left = nullptr) {
     const int R = t.R, C = t.C, Cc = call.clean_cols;
     F.Cc = Cc;
     call.is_te = 0; call.info = 0; call.copy_num = 0; call.align_start = -1; call.align_end = -1;
@@ -686,8 +711,10 @@ __device__ __noinline__ bool front_anchors(const HbVoteTask& t, HbVoteCall& call
         pattern_init(P1, cand, alen);
         pattern_init(P2, cand + (t.cand_len - alen), alen);
         Match* ml = matches + t.match_off;
-        for (int r = 0; r < R; ++r)
-            if (row_anchor(m + (size_t)r * C, Cc, C + 2, P1, P2, ml, cnt, lane, &as, &ae)) break;
+        bool found = false;
+        const int rend = min(R, max_rows);
+        for (int r = 0; r < rend && !found; ++r) found = row_anchor(m + (size_t)r * C, Cc, C + 2, P1, P2, ml, cnt, lane, &as, &ae);
+        if (rows_left != nullptr) *rows_left = !found && rend < R;     // the caller has the other rows searched (hb_judge_a2_kernel)
     }
     call.align_start = as; call.align_end = ae;
     *as_out = as; *ae_out = ae;
@@ -808,9 +835,15 @@ __device__ __forceinline__ void front_load(Front& F, const JState* st, uint32_t*
     for (int k = 0; k < 4; ++k) F.P.rowmask[k] = st->rowmask[k];
 }
 
+// Phase a tries the first A_FIRST_ROWS rows itself (one warp per task: nearly every element anchors in its first row); a
+// matrix whose first rows hold no anchor pair is queued (work[0] = count, work[1..] = tasks) and its remaining rows are
+// searched by hb_judge_a2_kernel with A2_WARPS warps at once -- as one warp, such a matrix cost R row scans and set the
+// kernel's duration (ncu launch lists of a C5 shard: 7 ms for 1 300 candidates).
+constexpr int A_FIRST_ROWS = 2, A2_WARPS = 8;
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 hb_judge_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
-                  Match* __restrict__ matches, const uint8_t* __restrict__ cands, HbVoteCall* __restrict__ calls) {
+                  Match* __restrict__ matches, const uint8_t* __restrict__ cands, HbVoteCall* __restrict__ calls,
+                  int* __restrict__ work) {
     __shared__ int s_cnt[WARPS_PER_CTA][2];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * WARPS_PER_CTA + wid;
@@ -819,12 +852,55 @@ hb_judge_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
     HbVoteCall call = calls[ti];          // clean_cols written by kernel A
     Front F;
     int as, ae;
-    const bool go = front_anchors(t, call, clean + t.clean_off, matches, cands, s_cnt[wid], lane, F, &as, &ae);
+    bool rows_left = false;
+    const bool go = front_anchors(t, call, clean + t.clean_off, matches, cands, s_cnt[wid], lane, F, &as, &ae, A_FIRST_ROWS, &rows_left);
     __syncwarp();                          // the match scratch is dead from here on; the state sits behind it
     if (lane == 0) {
         JState* st = jstate_of(matches, t);
         st->go = go ? 1 : 0; st->as = as; st->ae = ae; st->Cc = F.Cc;
         calls[ti] = call;
+        if (rows_left) work[1 + atomicAdd(&work[0], 1)] = ti;
+    }
+}
+
+// rows A_FIRST_ROWS.. of the queued matrices: the warps of a CTA test rows round-robin (row_has_anchors), the smallest
+// anchored row wins -- the row the sequential loop would have stopped at (:9151-9181) -- and warp 0 anchors on it.
+__global__ void __launch_bounds__(A2_WARPS * 32)
+hb_judge_a2_kernel(const HbVoteTask* __restrict__ tasks, const int* __restrict__ work, const uint8_t* __restrict__ clean,
+                   Match* __restrict__ matches, const uint8_t* __restrict__ cands, HbVoteCall* __restrict__ calls) {
+    __shared__ int s_first;
+    __shared__ int s_cnt[2];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = work[0];
+    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int ti = work[1 + wi];
+        const HbVoteTask t = tasks[ti];
+        const int R = t.R, C = t.C, Cc = calls[ti].clean_cols;
+        const uint8_t* m = clean + t.clean_off;
+        if (threadIdx.x == 0) s_first = R;
+        __syncthreads();
+        const int alen = min(20, t.cand_len);
+        Pattern P1, P2;
+        pattern_init(P1, cands + t.cand_off, alen);
+        pattern_init(P2, cands + t.cand_off + (t.cand_len - alen), alen);
+        for (int r = A_FIRST_ROWS + wid; r < R; r += A2_WARPS) {
+            if (r > *(volatile int*)&s_first) break;
+            if (row_has_anchors(m + (size_t)r * C, Cc, P1, P2, lane)) { if (lane == 0) atomicMin(&s_first, r); break; }
+        }
+        __syncthreads();
+        const int fr = s_first;
+        if (wid == 0 && fr < R) {
+            int as = -1, ae = -1;
+            row_anchor(m + (size_t)fr * C, Cc, C + 2, P1, P2, matches + t.match_off, s_cnt, lane, &as, &ae);
+            __syncwarp();
+            if (lane == 0) {
+                JState* st = jstate_of(matches, t);
+                st->as = as; st->ae = ae;
+                calls[ti].align_start = as; calls[ti].align_end = ae;
+                if (as >= 0 && ae >= 0) { calls[ti].info = 0; st->go = 1; }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -1508,7 +1584,9 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int prebuilt = d_raw == nullptr;               // ... and so were the bit-planes over all rows (TIR / non-LTR judges)
     if (te_type == 0) {
-        hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);
+        cudaMemsetAsync(d_anchors, 0, sizeof(int), stream);                    // (the anchor scratch of the Helitron judge: its work queue here)
+        hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls, d_anchors);
+        hb_judge_a2_kernel<<<min(n, 148 * 4), A2_WARPS * 32, 0, stream>>>(d_tasks, d_anchors, d_clean, (Match*)d_matches, d_cands, d_calls);
         hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 0, prebuilt);
         hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls, 0.7);
         hb_judge_d_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
@@ -1520,7 +1598,9 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
         hb_judge_v6_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
                                                                       d_calls);
     } else if (te_type == 2) {
-        hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls);
+        cudaMemsetAsync(d_anchors, 0, sizeof(int), stream);                    // (the anchor scratch of the Helitron judge: its work queue here)
+        hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls, d_anchors);
+        hb_judge_a2_kernel<<<min(n, 148 * 4), A2_WARPS * 32, 0, stream>>>(d_tasks, d_anchors, d_clean, (Match*)d_matches, d_cands, d_calls);
         hb_judge_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, 1, prebuilt);
         hb_judge_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_planes, (Match*)d_matches, d_calls, 0.8);
         if (avg_rows > 48)
