@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the per-type / adjacent-row measurements of the N = 1 line")
     ap.add_argument("--rebalance", default="on", choices=["on", "off"],
                     help="N > 1: re-deal the shards on the per-candidate cost measured by the first warm-up round")
+    ap.add_argument("--gather-thread", default="on", choices=["on", "off"],
+                    help="N > 1: finish the all-gather (and rank 0's read-back) on a helper thread while the next round runs")
     ap.add_argument("--coarse", default=None, choices=["on", "off"],
                     help="time the coarse-boundary stage too (default: on, except C5 -- at ~85 %% repeat content the all-vs-all has "
                          "> 10^10 seed pairs before the known-TE masking the reference applies first)")
@@ -298,12 +300,15 @@ def main():
     cost = np.zeros(n_total, dtype=np.int64)              # filled by the first warm-up round when the shards get rebalanced
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     state = {"pending": False}
+    threaded = args.gather_thread == "on" and world > 1
+    host_t = np.zeros(3)                                  # host wall inside: hb_adjust calls | gather.finish | gather.start
     chunk = {"n": 1 << 16}                  # candidates per hb_adjust call; halved when a call reports HB_ENOMEM (too many seed hits)
 
     def step():
         """one round over this rank's shard + the exchange -> (kernel ms, stage ms, h2d, d2h, launches, n_te)"""
         k_ms, stage, h2d, d2h, launches, n_te = 0.0, np.zeros(8), 0, 0, 0, 0
         idx_all, len_all, parts = [], [], []
+        tw0 = time.perf_counter()
         for kind, idx, host_cands in groups:
             for calls, cons, sub_idx, dev in adjust_chunked(ctx, kind, idx, host_cands, chunk, len(groups) == 1):
                 state["last"] = (kind, sub_idx)
@@ -317,13 +322,18 @@ def main():
                 idx_all.append(sub_idx[te]); len_all.append(calls["cons_len"][te])
                 if dev is not None:
                     parts.append(dev)
-        if state["pending"]:
-            gather.finish()                               # last step's collective: it overlapped this step's kernels
+        tw1 = time.perf_counter()
+        if state["pending"]:                              # last step's collective: it overlapped this step's kernels
+            gather.result() if threaded else gather.finish(concat=False)
+        tw2 = time.perf_counter()
         ev[0].record()
         body = None if not parts else (parts[0] if len(parts) == 1 else torch.cat(parts))
         gather.start(np.concatenate(idx_all), np.concatenate(len_all), body)
         ev[1].record()
+        if threaded:
+            gather.finish_async()                         # wait + rank 0's read-back on a helper thread, joined one step later
         state["pending"] = True
+        host_t[:] += (tw1 - tw0, tw2 - tw1, time.perf_counter() - tw2)
         return k_ms, stage, h2d, d2h, launches, n_te
 
     # N > 1: the first warm-up round runs on the length-balanced deal and measures what each candidate costs (loci aligned x
@@ -335,7 +345,8 @@ def main():
         step()
         if state["collect_cost"]:
             state["collect_cost"] = False
-            gather.finish(); state["pending"] = False
+            gather.result() if threaded else gather.finish()
+            state["pending"] = False
             ct = torch.as_tensor(cost, device="cuda")
             dist.all_reduce(ct, op=dist.ReduceOp.SUM)
             cl = ct.cpu().numpy().tolist()
@@ -345,12 +356,13 @@ def main():
             gather = hbdist.RecordGather([len(s) for s in shards], [sum(lens_all[i] for i in s) for s in shards], "cuda")
             rebalanced = True
     if state["pending"]:
-        gather.finish()
+        gather.result() if threaded else gather.finish()
     state["pending"] = False
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
+    host_t[:] = 0
     dev_ms, g_ms, stage = [], [], np.zeros(8)
     h2d = d2h = launches = 0
     n_te_local = 0
@@ -360,7 +372,8 @@ def main():
         torch.cuda.current_stream().synchronize()
         dev_ms.append(k_ms); g_ms.append(ev[0].elapsed_time(ev[1])); stage += st
     tg = time.perf_counter()
-    got = gather.finish(concat=False); state["pending"] = False   # the last step's collective + rank 0's read-back (views, no copy)
+    got = gather.result() if threaded else gather.finish(concat=False)    # the last step's collective + rank 0's read-back (views)
+    state["pending"] = False
     flush_ms = (time.perf_counter() - tg) * 1e3
     barrier()
     wall = time.perf_counter() - t0
@@ -380,8 +393,8 @@ def main():
         my_mhz = float(torch.cuda.clock_rate())
     except Exception:
         my_mhz = 0.0
-    mine_v = torch.tensor([float(np.sum(dev_ms)) / args.steps] + [float(x) / args.steps for x in stage[:6]] + [wall * 1e3 / args.steps, my_mhz],
-                          device="cuda", dtype=torch.float64)
+    mine_v = torch.tensor([float(np.sum(dev_ms)) / args.steps] + [float(x) / args.steps for x in stage[:6]] + [wall * 1e3 / args.steps, my_mhz] +
+                          [float(x) * 1e3 / args.steps for x in host_t], device="cuda", dtype=torch.float64)
     per_rank = [mine_v.clone() for _ in range(world)]
     if world > 1:
         dist.all_gather(per_rank, mine_v)
@@ -448,7 +461,10 @@ def main():
                          "extend_ms": [round(float(v[3]), 2) for v in per_rank],
                          "clean_judge_ms": [round(float(v[5]), 2) for v in per_rank],
                          "wall_ms": [round(float(v[7]), 2) for v in per_rank],
-                         "sm_mhz": [int(v[8]) for v in per_rank]},
+                         "sm_mhz": [int(v[8]) for v in per_rank],
+                         "host_adjust_ms": [round(float(v[9]), 2) for v in per_rank],
+                         "host_gather_finish_ms": [round(float(v[10]), 2) for v in per_rank],
+                         "host_gather_start_ms": [round(float(v[11]), 2) for v in per_rank]},
             "setup": {"genome_load_ms": t_load["kernel_ms"] + t_load["h2d_ms"], "index_build_ms": t_idx["kernel_ms"],
                       "index_stages_ms": [round(float(x), 3) for x in t_idx["k_ms"][:3]],
                       "index_Mbp_per_s": wl.genome_bp / 1e6 / max(1e-9, t_idx["kernel_ms"] * 1e-3), "setup_wall_s": setup_s,

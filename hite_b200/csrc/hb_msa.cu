@@ -602,17 +602,25 @@ msa_clean_kernel(const HbVoteTask* __restrict__ tasks, const uint32_t* __restric
 #pragma unroll
         for (int k = 0; k < 4; ++k) e4[k] = s_cq[lane + 32 * k];
         for (int r = wid; r < R; r += 2 * (MC_THREADS / 32)) {
-            const int r2 = min(r + MC_THREADS / 32, R - 1);              // (r2 == r: computed twice, stored twice: harmless)
+            const int r2 = r + MC_THREADS / 32;
+            const bool two = r2 < R;                                     // (warp-uniform)
             const uint32_t wa = mc_row_word(rw, r, e4, c0 + lane, C, qrec, gseq2, gnmask, totm1, flank);
-            const uint32_t wb = mc_row_word(rw, r2, e4, c0 + lane, C, qrec, gseq2, gnmask, totm1, flank);
-            const int ta = rw.trow[r], tb = rw.trow[r2];
+            const int ta = rw.trow[r];
+            if (two) {
+                const uint32_t wb = mc_row_word(rw, r2, e4, c0 + lane, C, qrec, gseq2, gnmask, totm1, flank);
+                const int tb = rw.trow[r2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t bb = (wb >> (8 * k)) & 255u;
+                    s_tile[0][lane + 32 * k][r2] = (uint8_t)(bb & 0x7Fu);
+                    if (tb >= 0) s_tile[1][lane + 32 * k][tb] = (bb & 0x80u) ? (uint8_t)HB_SYM_GAP : (uint8_t)bb;
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t ba = (wa >> (8 * k)) & 255u, bb = (wb >> (8 * k)) & 255u;
+                const uint32_t ba = (wa >> (8 * k)) & 255u;
                 s_tile[0][lane + 32 * k][r] = (uint8_t)(ba & 0x7Fu);
-                s_tile[0][lane + 32 * k][r2] = (uint8_t)(bb & 0x7Fu);
                 if (ta >= 0) s_tile[1][lane + 32 * k][ta] = (ba & 0x80u) ? (uint8_t)HB_SYM_GAP : (uint8_t)ba;
-                if (tb >= 0) s_tile[1][lane + 32 * k][tb] = (bb & 0x80u) ? (uint8_t)HB_SYM_GAP : (uint8_t)bb;
             }
         }
         __syncthreads();

@@ -105,6 +105,8 @@ class RecordGather:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())     # (a helper thread has no current device of its own)
         self.nmax = max(shard_sizes) if shard_sizes else 0
         self.rec_cap = 8 * self.nmax
         body = max(int(b * 1.25) + 64 * n for n, b in zip(shard_sizes, shard_bases)) if shard_sizes else 0
@@ -143,6 +145,35 @@ class RecordGather:
             self.work = dist.all_gather_into_tensor(self.out, self.buf, async_op=True)
         else:
             self.work = None                              # one rank: the records are already where they are needed
+
+    def finish_async(self, concat=False):
+        """``finish`` on a helper thread, so that the read-back rank's host keeps launching the next round while the collective
+        completes and its payload crosses PCIe; ``result()`` joins.  Nothing may call ``start`` before ``result``."""
+        import threading
+        box = {}
+
+        def run():
+            try:
+                if self.device.type == "cuda":
+                    torch.cuda.set_device(self.device)
+                    if getattr(self, "_side", None) is None:
+                        self._side = torch.cuda.Stream(device=self.device)
+                    with torch.cuda.stream(self._side):   # the wait and the copies stay off the streams the next round uses
+                        box["v"] = self.finish(concat)
+                else:
+                    box["v"] = self.finish(concat)
+            except BaseException as e:                    # surfaced by result()
+                box["e"] = e
+        self._thread = (threading.Thread(target=run, daemon=True), box)
+        self._thread[0].start()
+
+    def result(self):
+        th, box = self._thread
+        th.join()
+        self._thread = None
+        if "e" in box:
+            raise box["e"]
+        return box["v"]
 
     def finish(self, concat=True):
         """Wait for the collective launched by ``start``; on the read-back rank returns (indices, lengths, consensus bytes)

@@ -68,3 +68,30 @@ def test_c2_full_size_properties(ctx):
         if rows:
             exp = oracle.judge_with_trunc_gate(wl.cand_seqs[i].decode(), cps, rows)
             assert (bool(calls["is_te"][i]), seqs[i] if exp["is_te"] else "") == (exp["is_te"], exp["cons"] if exp["is_te"] else ""), i
+
+
+def test_c2_at_spec_verdicts_match_the_port_on_a_sample(ctx):
+    """BASELINE configs[1] at SURVEY section 8(d) spec (copies U[6,100], 0-10 % divergence, indels <= 2 %, families of more
+    than 100 copies included): every 25th candidate (400) goes through the C port with all host threads and through
+    hb_adjust -- is_te, info, copy_num and the consensus length agree on every one (the check bench.py repeats per run)."""
+    import os
+    from oracle import oracle as O
+    wl = synth.config_c2()
+    assert len(wl.cand_seqs) == 10_000 and 99_000_000 <= wl.genome_bp <= 101_000_000
+    ctx.load_genome(wl.contig_seqs, wl.contig_names)
+    ctx.build_index(15, 10)
+    sample = list(range(0, 10_000, 25))
+    G = O.Genome(wl.contig_seqs)
+    G.set_tie_rule(1, wl.contig_names)
+    assert np.array_equal(ctx.debug_index(), G.index)
+    verd = G.run_batch([wl.cand_seqs[i] for i in sample], os.cpu_count() or 1)
+    calls, _ = ctx.adjust_raw([wl.cand_seqs[i] for i in sample], "tir", 1, trunc_gate=False)
+    mine = np.stack([calls["is_te"], calls["info"], calls["copy_num"], calls["cons_len"]], axis=1).astype(np.int32)
+    bad = np.nonzero(~(mine == verd).all(axis=1))[0]
+    assert len(bad) == 0, (len(bad), [(sample[b], mine[b].tolist(), verd[b].tolist()) for b in bad[:5]])
+    assert int(calls["is_te"].sum()) >= 0.8 * len(sample)
+    # the same candidates inside the full batch: a verdict does not depend on what else is in the call
+    full, _ = ctx.adjust_raw(wl.cand_seqs, "tir", 1, trunc_gate=False)
+    for k in ("is_te", "info", "copy_num", "cons_len"):
+        assert np.array_equal(full[k][sample], calls[k]), k
+    G.close()

@@ -143,7 +143,8 @@ for step in range(3):
     if step == 2:                                                     # zero-copy read-back: per-rank views, same content
         g.start(np.array(keep, dtype=np.int32), np.array([len(seqs[i]) for i in keep], dtype=np.int32),
                 torch.frombuffer(bytearray(cons), dtype=torch.uint8) if cons else None)
-        got = g.finish(concat=False)
+        g.finish_async()                                              # same, finished on the helper thread
+        got = g.result()
         if rank == 0:
             assert len(got[0]) == world and np.concatenate(got[0]).tolist() == exp_keep
             assert b"".join(c.tobytes() for c in got[2]).decode() == "".join(seqs[i].lower() for i in exp_keep)
