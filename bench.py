@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the per-type / adjacent-row measurements of the N = 1 line")
     ap.add_argument("--rebalance", default="on", choices=["on", "off"],
                     help="N > 1: re-deal the shards on the per-candidate cost measured by the first warm-up round")
-    ap.add_argument("--gather-thread", default="on", choices=["on", "off"],
+    ap.add_argument("--gather-thread", default="off", choices=["on", "off"],
                     help="N > 1: finish the all-gather (and rank 0's read-back) on a helper thread while the next round runs")
     ap.add_argument("--coarse", default=None, choices=["on", "off"],
                     help="time the coarse-boundary stage too (default: on, except C5 -- at ~85 %% repeat content the all-vs-all has "
