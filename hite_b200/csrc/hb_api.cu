@@ -4,6 +4,7 @@
 
 extern "C" size_t hb_vote_match_entry_size();
 extern "C" size_t hb_vote_state_entries();
+extern "C" size_t hb_vote_match_entries(int C);
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
                                       uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
                                       uint8_t* d_cons, HbVoteCall* d_calls, int te_type, int avg_rows, cudaStream_t stream);
@@ -122,7 +123,7 @@ extern "C" int hb_vote_matrices(hb_ctx* ctx, uint32_t n, const uint8_t* rows_asc
         t.te_type = te_type; t.plant = plant; t.result_type = result_type; t.raw_is_ascii = 1;
         raw_total = mat_off[i] + (uint64_t)R[i] * C[i] > raw_total ? mat_off[i] + (uint64_t)R[i] * C[i] : raw_total;
         col_total += (uint64_t)C[i];
-        match_total += 2ull * ((uint64_t)C[i] + 2) + hb_vote_state_entries();
+        match_total += hb_vote_match_entries(C[i]);
         row_total += (uint64_t)R[i];
     }
     const uint64_t cons_total = col_total + 2ull * n;

@@ -20,6 +20,7 @@
 
 extern "C" size_t hb_vote_match_entry_size();
 extern "C" size_t hb_vote_state_entries();
+extern "C" size_t hb_vote_match_entries(int C);
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
                                       uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
                                       uint8_t* d_cons, HbVoteCall* d_calls, int te_type, int avg_rows, cudaStream_t stream);
@@ -552,7 +553,7 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
         t.te_type = prm->te_type; t.plant = prm->plant; t.result_type = prm->result_type; t.raw_is_ascii = 0;
         tasks.push_back(t); task_cand.push_back(c);
         col_total += h_cols[c];
-        match_total += 2ull * ((uint64_t)h_cols[c] + 2) + hb_vote_state_entries();
+        match_total += hb_vote_match_entries((int)h_cols[c]);
         row_total += rows;
     };
     for (uint32_t c = 0; c < n_cand; ++c) {
@@ -657,7 +658,7 @@ static int adjust_batch(hb_ctx* ctx, HbLane& ln, HbHostBuf& h_cons, uint32_t n_c
                                        LB("p.qr_off").as<uint32_t>(), LB("p.qrec").as<uint32_t>(), LB("m.col_off").as<uint32_t>(),
                                        LB("m.colq").as<uint32_t>(), ctx->buf("g.seq2").as<uint32_t>(), ctx->buf("g.nmask").as<uint32_t>(),
                                        tot, flank, LB("v.clean").as<uint8_t>(),
-                                       prm->te_type == 1 ? nullptr : LB("v.planes").as<uint32_t>(),   // (the Helitron judge builds its own)
+                                       LB("v.planes").as<uint32_t>(),
                                        LB("v.calls").as<HbVoteCall>(), s));
         ++launches;
         HB_CUDA_OK(hb_vote_launch(LB("v.tasks").as<HbVoteTask>(), (int)n_tasks, nullptr,

@@ -584,6 +584,21 @@ __device__ __noinline__ void build_planes(Planes& P, uint32_t* __restrict__ pw, 
     __syncwarp();
 }
 
+// planes prebuilt over ALL rows of the matrix (hb_msa.cu::msa_clean_kernel): keeping a row list = masking the other rows
+__device__ __noinline__ void planes_select(Planes& P, const uint32_t* __restrict__ pw, int C, int R, const unsigned short* rows,
+                                           int row_num, int lane) {
+    P.p = pw; P.stride = C; P.nw = (R + 31) >> 5; P.row_num = row_num;
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+        uint32_t mk = 0;
+        for (int k = lane; k < row_num; k += 32) mk |= (rows[k] >> 5) == wd ? 1u << (rows[k] & 31) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mk |= __shfl_xor_sync(HB_FULL, mk, o);
+        P.rowmask[wd] = mk;
+    }
+    __syncwarp();
+}
+
 // rows (in order) that have a non-gap symbol in [lo1,hi1) and in [lo2,hi2); at most MAX_KEPT
 // ("len(...) > 100: break", Util.py:9201 / :10017)
 __device__ __noinline__ int select_rows(const uint8_t* __restrict__ m, int R, int C, int lo1, int hi1, int lo2, int hi2,
@@ -735,17 +750,8 @@ __device__ __noinline__ bool front_members(const HbVoteTask& t, HbVoteCall& call
         return false;
     }
     call.copy_num = row_num;
-    if (!prebuilt) { build_planes(F.P, planes + t.plane_off, m, C, Cc, rows, row_num, lane); return true; }
-    Planes& P = F.P;
-    P.p = planes + t.plane_off; P.stride = C; P.nw = (R + 31) >> 5; P.row_num = row_num;
-#pragma unroll
-    for (int wd = 0; wd < 4; ++wd) {
-        uint32_t mk = 0;
-        for (int k = lane; k < row_num; k += 32) mk |= (rows[k] >> 5) == wd ? 1u << (rows[k] & 31) : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mk |= __shfl_xor_sync(HB_FULL, mk, o);
-        P.rowmask[wd] = mk;
-    }
+    if (!prebuilt) build_planes(F.P, planes + t.plane_off, m, C, Cc, rows, row_num, lane);
+    else planes_select(F.P, planes + t.plane_off, C, R, rows, row_num, lane);
     return true;
 }
 // phase c: outermost valid columns (:9269-9294) + homology boundaries (:9297-9308).
@@ -822,11 +828,14 @@ struct JState {
 struct JState6 {        // Helitron judge (judge_boundary_v6)
     int go, as, ae, hs, he, Cc;
 };
+// a task's match scratch: MATCH_LISTS lists of C + 2 entries (two per warp that scans rows: hb_judge_v6_a_kernel runs four), then
+// the judge's phase state
+constexpr int MATCH_LISTS = 8;
 __device__ __forceinline__ JState6* jstate6_of(Match* matches, const HbVoteTask& t) {
-    return reinterpret_cast<JState6*>(matches + t.match_off + 2 * ((size_t)t.C + 2));
+    return reinterpret_cast<JState6*>(matches + t.match_off + MATCH_LISTS * ((size_t)t.C + 2));
 }
 __device__ __forceinline__ JState* jstate_of(Match* matches, const HbVoteTask& t) {
-    return reinterpret_cast<JState*>(matches + t.match_off + 2 * ((size_t)t.C + 2));
+    return reinterpret_cast<JState*>(matches + t.match_off + MATCH_LISTS * ((size_t)t.C + 2));
 }
 __device__ __forceinline__ void front_load(Front& F, const JState* st, uint32_t* planes, const HbVoteTask& t) {
     F.Cc = st->Cc; F.row_num = st->row_num; F.hs = st->hs; F.he = st->he; F.vl = st->vl; F.vr = st->vr;
@@ -1051,8 +1060,8 @@ hb_judge_d_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8
 // kernel B': judge_boundary_v6 (Helitron, Util.py:9821-10159).  Phase a anchors EVERY row (two 20-mers by Myers over the
 // whole row), ~R times the work of the TIR judge's phase a: one CTA of ROW_WARPS warps per candidate, rows dealt round-robin
 // to the warps (one warp per candidate left the GPU a third full at 3 000 candidates and serialised <= 100 row scans).
-// Warp 0 scans into the task's match scratch, warps 1.. into the task's bit-plane area, which phase b only builds later
-// (96 C bytes >= (ROW_WARPS - 1) * 2 (C + 2) * 12 for every MSA width).  Per-row anchors land at an[r] / an[R + r] (-1 =
+// Every warp scans into its own pair of match lists of the task's match scratch (MATCH_LISTS; the bit-plane area is already
+// filled when the matrices come from hb_msa.cu::msa_clean_kernel).  Per-row anchors land at an[r] / an[R + r] (-1 =
 // none) and are compacted in row order by warp 0: the mode's tie-break is "first inserted" (:9722-9730).
 constexpr int ROW_WARPS = 4;
 __global__ void __launch_bounds__(ROW_WARPS * 32)
@@ -1080,9 +1089,9 @@ hb_judge_v6_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
         Pattern P1, P2;
         pattern_init(P1, cand, alen);
         pattern_init(P2, cand + (t.cand_len - alen), alen);
-        Match* ml = wid == 0 ? matches + t.match_off
-                             : reinterpret_cast<Match*>(planes + t.plane_off) + (size_t)(wid - 1) * 2 * ((size_t)C + 2);
-        const int nw = C >= 6 ? ROW_WARPS : 1;     // narrower matrices: the plane area cannot hold the extra scratch
+        static_assert(MATCH_LISTS >= 2 * ROW_WARPS, "one pair of match lists per scanning warp");
+        Match* ml = matches + t.match_off + (size_t)wid * 2 * ((size_t)C + 2);
+        const int nw = ROW_WARPS;
         for (int r = wid; r < R && wid < nw; r += nw) {
             int a = -1, b = -1;
             const bool hit = row_anchor(m + (size_t)r * C, Cc, C + 2, P1, P2, ml, s_cnt[wid], lane, &a, &b);
@@ -1135,7 +1144,7 @@ hb_judge_v6_a_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
 // phase B: start / end member sets, then the end and the start boundary (search_boundary_homo_v4)
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 hb_judge_v6_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
-                     uint32_t* __restrict__ planes, Match* __restrict__ matches, HbVoteCall* __restrict__ calls) {
+                     uint32_t* __restrict__ planes, Match* __restrict__ matches, HbVoteCall* __restrict__ calls, int prebuilt) {
     __shared__ int s_vc[WARPS_PER_CTA][128];
     __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
     __shared__ unsigned short s_rows2[WARPS_PER_CTA][104];
@@ -1183,7 +1192,7 @@ hb_judge_v6_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
     uint32_t* pw = planes + t.plane_off;
     int he = -1, hs = -1;
     {   // end first (:9972-9979)
-        build_planes(P, pw, m, C, Cc, rows2, ne, lane);
+        if (prebuilt) planes_select(P, pw, C, R, rows2, ne, lane); else build_planes(P, pw, m, C, Cc, rows2, ne, lane);
         const double thr = ne <= 2 ? 0.95 : (ne <= 5 ? 0.9 : 0.7);
         const double ithr = ne <= 2 ? 0.9 : (ne <= 5 ? 0.85 : 0.65);
         const double othr = ne <= 2 ? 0.95 : (ne <= 5 ? 0.9 : 0.7);
@@ -1192,7 +1201,7 @@ hb_judge_v6_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
         call.homo_end = he;
     }
     {   // then start (:9991-10008)
-        build_planes(P, pw, m, C, Cc, rows, ns, lane);
+        if (prebuilt) planes_select(P, pw, C, R, rows, ns, lane); else build_planes(P, pw, m, C, Cc, rows, ns, lane);
         const double thr = ns <= 2 ? 0.95 : (ns <= 5 ? 0.9 : 0.7);
         const double ithr = ns <= 2 ? 0.9 : (ns <= 5 ? 0.85 : 0.65);
         const double othr = ns <= 2 ? 0.95 : (ns <= 5 ? 0.9 : 0.7);
@@ -1206,7 +1215,7 @@ hb_judge_v6_b_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 hb_judge_v6_c_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ clean,
                      uint32_t* __restrict__ planes, Match* __restrict__ matches, uint8_t* __restrict__ cons_buf,
-                     HbVoteCall* __restrict__ calls) {
+                     HbVoteCall* __restrict__ calls, int prebuilt) {
     __shared__ unsigned short s_rows[WARPS_PER_CTA][104];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * WARPS_PER_CTA + wid;
@@ -1230,7 +1239,7 @@ hb_judge_v6_c_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const ui
     }
     if (row_num <= 0) { if (lane == 0) calls[ti] = call; return; }
     call.copy_num = row_num;
-    build_planes(P, pw, m, C, Cc, rows, row_num, lane);
+    if (prebuilt) planes_select(P, pw, C, R, rows, row_num, lane); else build_planes(P, pw, m, C, Cc, rows, row_num, lane);
     // ---- 4. consensus with 'N' for weak columns (:10078-10095) and +-1 bp extension (:10097-10130)
     uint8_t* cons = cons_buf + t.cons_off;
     const int half = row_num / 2;
@@ -1571,8 +1580,10 @@ hb_judge_v9_tail_kernel(const HbVoteTask* __restrict__ tasks, int n_tasks, const
 // ------------------------------------------------------------------------------------------
 // host launchers (called from hb_api.cu)
 extern "C" size_t hb_vote_match_entry_size() { return sizeof(Match); }
-// extra Match entries per task (after its 2 * (C + 2) match slots) that hold the judge's phase state
+// extra Match entries per task (after its MATCH_LISTS * (C + 2) match slots) that hold the judge's phase state
 extern "C" size_t hb_vote_state_entries() { return (sizeof(JState) + sizeof(Match) - 1) / sizeof(Match); }
+// Match entries of one task with C columns: its match lists + the state
+extern "C" size_t hb_vote_match_entries(int C) { return (size_t)MATCH_LISTS * ((size_t)C + 2) + hb_vote_state_entries(); }
 
 extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const uint8_t* d_raw, uint8_t* d_clean,
                                       uint32_t* d_planes, void* d_matches, int* d_anchors, const uint8_t* d_cands,
@@ -1582,7 +1593,7 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
     // d_raw == nullptr: the clean matrices (and calls[].clean_cols) were already produced by hb_msa.cu::msa_clean_kernel
     if (d_raw) hb_clean_kernel<<<n, CLEAN_THREADS, 0, stream>>>(d_tasks, d_raw, d_clean, d_calls);
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int prebuilt = d_raw == nullptr;               // ... and so were the bit-planes over all rows (TIR / non-LTR judges)
+    const int prebuilt = d_raw == nullptr;               // ... and so were the bit-planes over all rows
     if (te_type == 0) {
         cudaMemsetAsync(d_anchors, 0, sizeof(int), stream);                    // (the anchor scratch of the Helitron judge: its work queue here)
         hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls, d_anchors);
@@ -1594,9 +1605,9 @@ extern "C" cudaError_t hb_vote_launch(const HbVoteTask* d_tasks, int n, const ui
     } else if (te_type == 1) {
         hb_judge_v6_a_kernel<<<n, ROW_WARPS * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_anchors, d_cands,
                                                                d_calls);
-        hb_judge_v6_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls);
+        hb_judge_v6_b_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_calls, prebuilt);
         hb_judge_v6_c_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, d_planes, (Match*)d_matches, d_cons,
-                                                                      d_calls);
+                                                                      d_calls, prebuilt);
     } else if (te_type == 2) {
         cudaMemsetAsync(d_anchors, 0, sizeof(int), stream);                    // (the anchor scratch of the Helitron judge: its work queue here)
         hb_judge_a_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(d_tasks, n, d_clean, (Match*)d_matches, d_cands, d_calls, d_anchors);
