@@ -73,6 +73,7 @@ extern "C" void hb_destroy(hb_ctx* ctx) {
     for (auto& kv : ctx->bufs) kv.second.release();
     ctx->h_stage.release();
     ctx->h_cons.release();
+    ctx->h_hsp_pin[0].release(); ctx->h_hsp_pin[1].release();
     for (auto& pc : ctx->part_cons) pc.release();
     for (auto& ln : ctx->lane) {
         cudaStreamSynchronize(ln.stream);

@@ -96,6 +96,8 @@ struct hb_ctx {
     std::vector<uint32_t> last_trows;
     std::vector<hb_hsp> last_hsps;            // last hb_coarse_boundary: HSPs grouped by query segment
     std::vector<uint64_t> last_hsp_off;
+    std::vector<std::pair<std::vector<hb_hsp>, std::vector<uint64_t>>> last_hsp_blocks;   // ... per pipelined block, until asked for
+    HbHostBuf h_hsp_pin[2];                   // pinned read-back buffers of the coarse stage's HSP records (double-buffered)
     std::vector<hb_segment> last_segs;
     std::vector<hb_interval> last_intervals;  // last hb_coarse_boundary(_part): its result, for hb_last_intervals
     std::vector<uint32_t> last_rows, last_cols;

@@ -1215,7 +1215,7 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     ENSURE("h.total", sizeof(uint64_t));
     uint64_t n_pairs_total = 0;
     // ---- GPU half of one block of files [fb_lo, fb_hi): seed pairs -> sort -> runs -> base-level HSPs, read back ----
-    auto gpu_block = [&](uint32_t fb_lo, uint32_t fb_hi, std::vector<HbHspRec>& h_recs) -> int {
+    auto gpu_block = [&](uint32_t fb_lo, uint32_t fb_hi, HbHostBuf& pin, uint64_t& n_recs) -> int {
         int g_lo = n_seg, g_hi = n_seg;
         for (int g = 0; g < n_seg; ++g) {
             if (file_of_seg[(size_t)g] >= fb_lo && g_lo == n_seg) g_lo = g;
@@ -1223,7 +1223,7 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
         }
         const uint64_t qpos_lo = g_lo < n_seg ? seg_goff[(size_t)g_lo] : ctx->g_tot;
         const uint64_t qpos_hi = g_hi < n_seg ? seg_goff[(size_t)g_hi] : ctx->g_tot;
-        h_recs.clear();
+        n_recs = 0;
         if (qpos_hi <= qpos_lo) return HB_OK;
         HB_CUDA_OK(cudaEventRecord(ctx->ev[0], s));
         HB_CUDA_OK(hb_pair_count_launch(ctx->buf("g.mm_pos").as<uint64_t>(), n_mm, ctx->buf("g.idx_a").as<uint64_t>(),
@@ -1280,9 +1280,10 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
                                       ctx->buf("h.keep").as<uint32_t>(), ctx->buf("h.pos").as<uint32_t>(),
                                       ctx->buf("h.out").as<HbHspRec>(), s));
         HB_CUDA_OK(cudaEventRecord(ctx->ev[3], s));
-        h_recs.resize(n_hsp);
-        if (n_hsp) HB_CUDA_OK(cudaMemcpyAsync(h_recs.data(), ctx->buf("h.out").p, sizeof(HbHspRec) * n_hsp, cudaMemcpyDeviceToHost, s));
+        HB_CUDA_OK(pin.ensure(sizeof(HbHspRec) * (n_hsp + 1)));                        // pinned: the read-back runs at PCIe speed
+        if (n_hsp) HB_CUDA_OK(cudaMemcpyAsync(pin.p, ctx->buf("h.out").p, sizeof(HbHspRec) * n_hsp, cudaMemcpyDeviceToHost, s));
         HB_CUDA_OK(cudaStreamSynchronize(s));
+        n_recs = n_hsp;
         launches += 12;
         tm.d2h_bytes += sizeof(HbHspRec) * n_hsp;
         float a = 0.f, b = 0.f, c = 0.f;
@@ -1295,49 +1296,63 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     // ---- host half of one block: HSPs grouped by query segment (stable: the "file order" of a query is the sorted-key
     // order), FMEA over the block's files on `threads` host threads ----
     struct Block { std::vector<hb_hsp> hsps; std::vector<uint64_t> off; std::vector<hb_interval> res; double fmea_ms = 0.0; };
-    auto group_block = [&](const std::vector<HbHspRec>& h_recs, Block& B) {
+    // stable counting sort by query segment on up to 8 host threads (thread t owns a contiguous slice of the records)
+    auto group_block = [&](const HbHspRec* recs, uint64_t n, Block& B) {
+        const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)std::max(1, threads), 8ull, n / 65536 + 1}));
+        std::vector<std::vector<uint64_t>> cnt((size_t)T, std::vector<uint64_t>((size_t)n_seg + 1, 0));
+        auto slice = [&](int t) { return std::make_pair(n * (uint64_t)t / (uint64_t)T, n * (uint64_t)(t + 1) / (uint64_t)T); };
+        auto par = [&](auto fn) {
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; ++t) th.emplace_back(fn, t);
+            fn(0);
+            for (auto& x : th) x.join();
+        };
+        par([&](int t) { auto [a, b] = slice(t); for (uint64_t i = a; i < b; ++i) cnt[(size_t)t][(size_t)recs[i].qseg]++; });
         B.off.assign((size_t)n_seg + 1, 0);
-        for (const HbHspRec& r : h_recs) B.off[(size_t)r.qseg + 1]++;
-        for (int g = 0; g < n_seg; ++g) B.off[(size_t)g + 1] += B.off[(size_t)g];
-        B.hsps.resize(h_recs.size());
-        std::vector<uint64_t> cur(B.off.begin(), B.off.end() - 1);
-        for (const HbHspRec& r : h_recs) B.hsps[cur[(size_t)r.qseg]++] = hb_hsp{r.subj, r.qs, r.qe, r.ss, r.se};
+        uint64_t run = 0;
+        for (int g = 0; g < n_seg; ++g) {
+            B.off[(size_t)g] = run;
+            for (int t = 0; t < T; ++t) { const uint64_t c = cnt[(size_t)t][(size_t)g]; cnt[(size_t)t][(size_t)g] = run; run += c; }
+        }
+        B.off[(size_t)n_seg] = run;
+        B.hsps.resize(n);
+        par([&](int t) {
+            auto [a, b] = slice(t);
+            std::vector<uint64_t>& cur = cnt[(size_t)t];
+            for (uint64_t i = a; i < b; ++i) { const HbHspRec& r = recs[i]; B.hsps[cur[(size_t)r.qseg]++] = hb_hsp{r.subj, r.qs, r.qe, r.ss, r.se}; }
+        });
     };
-    auto fmea_block = [&](Block& B) {
+    auto host_block = [&](const HbHspRec* recs, uint64_t n, Block& B) {
+        group_block(recs, n, B);
         auto t0 = std::chrono::steady_clock::now();
         hb_fmea_run(B.hsps.data(), B.off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, B.res, file_of_seg.data());
         B.fmea_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
-    // The part's files in up to 4 blocks, software-pipelined: while the host threads chain block b (FMEA is the longer
-    // half), the GPU already produces the HSPs of block b + 1.  A block is made of whole files, so its chaining is independent.
+    // The part's files in up to 4 blocks, software-pipelined: while the host threads group and chain block b (FMEA is the
+    // longer half), the GPU already produces the HSPs of block b + 1 into the other pinned read-back buffer.  A block is made of
+    // whole files, so its chaining is independent.
     auto t_all = std::chrono::steady_clock::now();
     const uint32_t nf = f_hi - f_lo;
     const uint32_t n_blocks = nf >= 8 ? 4u : 1u;
     std::vector<Block> blocks(n_blocks);
-    std::vector<HbHspRec> h_recs;
     std::thread worker;
     int rc_gpu = HB_OK;
     for (uint32_t b = 0; b < n_blocks; ++b) {
         const uint32_t fb_lo = f_lo + (uint32_t)((uint64_t)nf * b / n_blocks), fb_hi = f_lo + (uint32_t)((uint64_t)nf * (b + 1) / n_blocks);
-        rc_gpu = gpu_block(fb_lo, fb_hi, h_recs);
+        HbHostBuf& pin = ctx->h_hsp_pin[b & 1];           // block b - 2's worker was joined before block b - 1's was started
+        uint64_t n_recs = 0;
+        rc_gpu = gpu_block(fb_lo, fb_hi, pin, n_recs);
         if (rc_gpu != HB_OK) break;
-        group_block(h_recs, blocks[b]);
         if (worker.joinable()) worker.join();
-        worker = std::thread(fmea_block, std::ref(blocks[b]));
+        worker = std::thread(host_block, pin.as<HbHspRec>(), n_recs, std::ref(blocks[b]));
     }
     if (worker.joinable()) worker.join();
     if (rc_gpu != HB_OK) return rc_gpu;
-    // the getters see the whole part: HSPs grouped by query segment, intervals in block (= query-segment) order
-    ctx->last_hsp_off.assign((size_t)n_seg + 1, 0);
+    // hb_last_hsps (a parity / debug getter) assembles the part's HSPs from the blocks on demand
     size_t n_all = 0;
-    for (const Block& B : blocks) { n_all += B.hsps.size(); for (int g = 0; g <= n_seg; ++g) ctx->last_hsp_off[(size_t)g] += B.off[(size_t)g]; }
-    ctx->last_hsps.resize(n_all);
-    {
-        std::vector<uint64_t> cur(ctx->last_hsp_off.begin(), ctx->last_hsp_off.end() - 1);
-        for (const Block& B : blocks)
-            for (int g = 0; g < n_seg; ++g)
-                for (uint64_t i = B.off[(size_t)g]; i < B.off[(size_t)g + 1]; ++i) ctx->last_hsps[cur[(size_t)g]++] = B.hsps[i];
-    }
+    ctx->last_hsp_blocks.clear();
+    for (Block& B : blocks) { n_all += B.hsps.size(); ctx->last_hsp_blocks.emplace_back(std::move(B.hsps), std::move(B.off)); }
+    ctx->last_hsps.clear(); ctx->last_hsp_off.clear();
     ctx->last_segs = segs;
     std::vector<hb_interval> res;
     double fmea_ms = 0.0;
@@ -1372,6 +1387,18 @@ extern "C" int hb_last_intervals(hb_ctx* ctx, hb_interval* out, uint64_t cap, ui
 extern "C" int hb_last_hsps(hb_ctx* ctx, hb_hsp* out, uint64_t cap, uint64_t* n, uint64_t* q_off, hb_segment* segs,
                             uint32_t seg_cap, uint32_t* n_seg) {
     if (!ctx || !n || !n_seg) return HB_EINVAL;
+    if (ctx->last_hsp_off.empty() && !ctx->last_hsp_blocks.empty()) {              // grouped by query segment, blocks in order
+        const size_t ns = ctx->last_segs.size();
+        ctx->last_hsp_off.assign(ns + 1, 0);
+        size_t n_all = 0;
+        for (const auto& B : ctx->last_hsp_blocks) { n_all += B.first.size(); for (size_t g = 0; g <= ns; ++g) ctx->last_hsp_off[g] += B.second[g]; }
+        ctx->last_hsps.resize(n_all);
+        std::vector<uint64_t> cur(ctx->last_hsp_off.begin(), ctx->last_hsp_off.end() - 1);
+        for (const auto& B : ctx->last_hsp_blocks)
+            for (size_t g = 0; g < ns; ++g)
+                for (uint64_t i = B.second[g]; i < B.second[g + 1]; ++i) ctx->last_hsps[cur[g]++] = B.first[i];
+        ctx->last_hsp_blocks.clear();
+    }
     *n = ctx->last_hsps.size();
     *n_seg = (uint32_t)ctx->last_segs.size();
     if (!out) return HB_OK;
