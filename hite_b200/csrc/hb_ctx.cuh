@@ -96,7 +96,8 @@ struct hb_ctx {
     std::vector<uint32_t> last_trows;
     std::vector<hb_hsp> last_hsps;            // last hb_coarse_boundary: HSPs grouped by query segment
     std::vector<uint64_t> last_hsp_off;
-    std::vector<std::pair<std::vector<hb_hsp>, std::vector<uint64_t>>> last_hsp_blocks;   // ... per pipelined block, until asked for
+    std::vector<std::pair<uint64_t, std::vector<uint64_t>>> last_hsp_blocks;   // ... per pipelined block (count, offsets), until asked for
+    std::vector<std::vector<hb_hsp>> hsp_store;   // the blocks' grouped HSPs (grow-only, reused by every coarse call)
     HbHostBuf h_hsp_pin[2];                   // pinned read-back buffers of the coarse stage's HSP records (double-buffered)
     std::vector<hb_segment> last_segs;
     std::vector<hb_interval> last_intervals;  // last hb_coarse_boundary(_part): its result, for hb_last_intervals

@@ -1295,7 +1295,9 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     };
     // ---- host half of one block: HSPs grouped by query segment (stable: the "file order" of a query is the sorted-key
     // order), FMEA over the block's files on `threads` host threads ----
-    struct Block { std::vector<hb_hsp> hsps; std::vector<uint64_t> off; std::vector<hb_interval> res; double fmea_ms = 0.0; };
+    // (the grouped HSPs live in the context and only ever grow: a fresh 100 MB vector per block costs more in page faults
+    // than the chaining itself)
+    struct Block { std::vector<hb_hsp>* hsps = nullptr; uint64_t n = 0; std::vector<uint64_t> off; std::vector<hb_interval> res; double fmea_ms = 0.0; };
     // stable counting sort by query segment on up to 8 host threads (thread t owns a contiguous slice of the records)
     auto group_block = [&](const HbHspRec* recs, uint64_t n, Block& B) {
         const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)std::max(1, threads), 8ull, n / 65536 + 1}));
@@ -1315,17 +1317,19 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
             for (int t = 0; t < T; ++t) { const uint64_t c = cnt[(size_t)t][(size_t)g]; cnt[(size_t)t][(size_t)g] = run; run += c; }
         }
         B.off[(size_t)n_seg] = run;
-        B.hsps.resize(n);
+        if (B.hsps->size() < n) B.hsps->resize(n + n / 8);
+        B.n = n;
+        hb_hsp* dst = B.hsps->data();
         par([&](int t) {
             auto [a, b] = slice(t);
             std::vector<uint64_t>& cur = cnt[(size_t)t];
-            for (uint64_t i = a; i < b; ++i) { const HbHspRec& r = recs[i]; B.hsps[cur[(size_t)r.qseg]++] = hb_hsp{r.subj, r.qs, r.qe, r.ss, r.se}; }
+            for (uint64_t i = a; i < b; ++i) { const HbHspRec& r = recs[i]; dst[cur[(size_t)r.qseg]++] = hb_hsp{r.subj, r.qs, r.qe, r.ss, r.se}; }
         });
     };
     auto host_block = [&](const HbHspRec* recs, uint64_t n, Block& B) {
         group_block(recs, n, B);
         auto t0 = std::chrono::steady_clock::now();
-        hb_fmea_run(B.hsps.data(), B.off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, B.res, file_of_seg.data());
+        hb_fmea_run(B.hsps->data(), B.off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, B.res, file_of_seg.data());
         B.fmea_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
     // The part's files in up to 4 blocks, software-pipelined: while the host threads group and chain block b (FMEA is the
@@ -1335,6 +1339,8 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     const uint32_t nf = f_hi - f_lo;
     const uint32_t n_blocks = nf >= 8 ? 4u : 1u;
     std::vector<Block> blocks(n_blocks);
+    if (ctx->hsp_store.size() < n_blocks) ctx->hsp_store.resize(n_blocks);
+    for (uint32_t b = 0; b < n_blocks; ++b) blocks[b].hsps = &ctx->hsp_store[b];
     std::thread worker;
     int rc_gpu = HB_OK;
     for (uint32_t b = 0; b < n_blocks; ++b) {
@@ -1351,7 +1357,7 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     // hb_last_hsps (a parity / debug getter) assembles the part's HSPs from the blocks on demand
     size_t n_all = 0;
     ctx->last_hsp_blocks.clear();
-    for (Block& B : blocks) { n_all += B.hsps.size(); ctx->last_hsp_blocks.emplace_back(std::move(B.hsps), std::move(B.off)); }
+    for (Block& B : blocks) { n_all += B.n; ctx->last_hsp_blocks.emplace_back(B.n, std::move(B.off)); }
     ctx->last_hsps.clear(); ctx->last_hsp_off.clear();
     ctx->last_segs = segs;
     std::vector<hb_interval> res;
@@ -1391,12 +1397,15 @@ extern "C" int hb_last_hsps(hb_ctx* ctx, hb_hsp* out, uint64_t cap, uint64_t* n,
         const size_t ns = ctx->last_segs.size();
         ctx->last_hsp_off.assign(ns + 1, 0);
         size_t n_all = 0;
-        for (const auto& B : ctx->last_hsp_blocks) { n_all += B.first.size(); for (size_t g = 0; g <= ns; ++g) ctx->last_hsp_off[g] += B.second[g]; }
+        for (const auto& B : ctx->last_hsp_blocks) { n_all += B.first; for (size_t g = 0; g <= ns; ++g) ctx->last_hsp_off[g] += B.second[g]; }
         ctx->last_hsps.resize(n_all);
         std::vector<uint64_t> cur(ctx->last_hsp_off.begin(), ctx->last_hsp_off.end() - 1);
-        for (const auto& B : ctx->last_hsp_blocks)
+        for (size_t b = 0; b < ctx->last_hsp_blocks.size(); ++b) {
+            const auto& B = ctx->last_hsp_blocks[b];
+            const hb_hsp* src = ctx->hsp_store[b].data();
             for (size_t g = 0; g < ns; ++g)
-                for (uint64_t i = B.second[g]; i < B.second[g + 1]; ++i) ctx->last_hsps[cur[g]++] = B.first[i];
+                for (uint64_t i = B.second[g]; i < B.second[g + 1]; ++i) ctx->last_hsps[cur[g]++] = src[i];
+        }
         ctx->last_hsp_blocks.clear();
     }
     *n = ctx->last_hsps.size();
