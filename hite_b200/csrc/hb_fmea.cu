@@ -33,23 +33,46 @@ struct Pt { int32_t chr, da, db, used; };     // one stored point per interval o
 // Per-worker scratch, reused across work items: repeated large malloc/free from many threads serialises on
 // the kernel's address-space lock (mmap/munmap), which made the pool anti-scale.
 struct Scratch {
-    std::vector<Frag> fw, rv, cl;
+    std::vector<Frag> sorted, cl, ctmp;
+    std::vector<uint64_t> keys, tmp;
     std::vector<char> used;
     std::vector<Chain> chains;
     std::vector<Pt> table;
 };
 
-void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Chain>& out, std::vector<char>& used) {
+// `c` is sorted in place; `keys` / `tmp` are scratch
+void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Chain>& out, std::vector<char>& used,
+                   std::vector<uint64_t>& keys, std::vector<Frag>& tmp) {
     if (c.size() == 1) { out.push_back(Chain{c[0].qs, c[0].qe, c[0].ss, c[0].se, subj}); return; }   // the common case
-    for (size_t i = 0; i < c.size(); ++i) c[i].ord = (int32_t)i;
-    std::sort(c.begin(), c.end(), [](const Frag& a, const Frag& b) {          // == stable sort on (qs, qe)
-        return a.qs != b.qs ? a.qs < b.qs : (a.qe != b.qe ? a.qe < b.qe : a.ord < b.ord);
-    });
+    {   // stable sort on (qs, qe) (:4231): one packed key per fragment when the coordinates fit, as in sort_strand
+        const size_t m = c.size();
+        bool fits = m < (1u << 22);
+        keys.resize(m);
+        for (size_t i = 0; fits && i < m; ++i) {
+            const uint32_t qs = (uint32_t)c[i].qs, qe = (uint32_t)c[i].qe;
+            if ((qs | qe) >> 21) fits = false;
+            keys[i] = (uint64_t)qs << 43 | (uint64_t)qe << 22 | (uint64_t)i;
+        }
+        if (fits) {
+            std::sort(keys.begin(), keys.end());
+            tmp.assign(c.begin(), c.end());
+            for (size_t i = 0; i < m; ++i) c[i] = tmp[keys[i] & 0x3FFFFFu];
+        } else {
+            for (size_t i = 0; i < m; ++i) c[i].ord = (int32_t)i;
+            std::sort(c.begin(), c.end(), [](const Frag& a, const Frag& b) {
+                return a.qs != b.qs ? a.qs < b.qs : (a.qe != b.qe ? a.qe < b.qe : a.ord < b.ord);
+            });
+        }
+    }
     const size_t n = c.size();
     used.assign(n, 0);
-    auto mark = [&](size_t i) {       // visited_frag is keyed by the HSP tuple: identical lines fall together
-        for (size_t t = 0; t < n; ++t)
-            if (c[t].qs == c[i].qs && c[t].qe == c[i].qe && c[t].ss == c[i].ss && c[t].se == c[i].se) used[t] = 1;
+    // visited_frag is keyed by the HSP tuple: identical lines fall together.  After the sort they can only sit in the run of
+    // equal (qs, qe) around i, so that run is all there is to look at.
+    auto mark = [&](size_t i) {
+        const int32_t qs = c[i].qs, qe = c[i].qe, ss = c[i].ss, se = c[i].se;
+        used[i] = 1;
+        for (size_t t = i; t-- > 0 && c[t].qs == qs && c[t].qe == qe;) if (c[t].ss == ss && c[t].se == se) used[t] = 1;
+        for (size_t t = i + 1; t < n && c[t].qs == qs && c[t].qe == qe; ++t) if (c[t].ss == ss && c[t].se == se) used[t] = 1;
     };
     for (size_t i = 0; i < n; ++i) {
         if (used[i]) continue;
@@ -76,45 +99,114 @@ void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Cha
     }
 }
 
-// chains of one (query, subject) pair: forward clusters, then reverse clusters (module/Util.py:4162-4319)
-void chain_subject(const std::vector<Frag>& frags, int skip_gap, int subj, std::vector<Chain>& chains, Scratch& S) {
-    std::vector<Frag>&fw = S.fw, &rv = S.rv, &cl = S.cl;
-    fw.clear(); rv.clear();
-    for (const Frag& f : frags) { Frag g = f; std::vector<Frag>& dst = (f.ss > f.se ? rv : fw); g.ord = (int32_t)dst.size(); dst.push_back(g); }   // :4168-4172
-    std::sort(fw.begin(), fw.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : (a.se != b.se ? a.se < b.se : a.ord < b.ord); });
-    std::sort(rv.begin(), rv.end(), [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : (a.se != b.se ? a.se > b.se : a.ord < b.ord); });
+// Stable LSD radix sort of packed 64-bit keys on the bit range [lo, hi): 11-bit digits, counting passes; a digit on which
+// all keys agree costs one histogram pass and no scatter.
+void radix_sort_keys(std::vector<uint64_t>& keys, std::vector<uint64_t>& tmp, int lo, int hi) {
+    const size_t n = keys.size();
+    tmp.resize(n);
+    uint64_t* a = keys.data();
+    uint64_t* b = tmp.data();
+    uint32_t hist[2048];
+    for (int sh = lo; sh < hi; sh += 11) {
+        const int bits = std::min(11, hi - sh);
+        const uint32_t mask = (1u << bits) - 1u;
+        for (uint32_t d = 0; d <= mask; ++d) hist[d] = 0;
+        for (size_t i = 0; i < n; ++i) hist[(a[i] >> sh) & mask]++;
+        if (hist[(a[0] >> sh) & mask] == n) continue;
+        uint32_t run = 0;
+        for (uint32_t d = 0; d <= mask; ++d) { const uint32_t c = hist[d]; hist[d] = run; run += c; }
+        for (size_t i = 0; i < n; ++i) b[hist[(a[i] >> sh) & mask]++] = a[i];
+        std::swap(a, b);
+    }
+    if (a != keys.data()) keys.swap(tmp);
+}
+
+// Stable sort of one strand's fragments along the subject (module/Util.py:4174-4176): forward ascending on (ss, se), reverse
+// descending.  Coordinates are 1-based positions inside a segment; when they (and the count) fit 21 / 21 / 22 bits the order
+// is the order of one packed 64-bit key per fragment (position in file order in the low bits keeps it stable), otherwise a
+// comparison sort on the records.  `out` only ever grows (no value-initialisation per call); the strand is out[0 .. n).
+void sort_strand(const Frag* f, size_t n, bool reverse, std::vector<Frag>& out, std::vector<uint64_t>& keys, std::vector<uint64_t>& tmp) {
+    if (out.size() < n) out.resize(n + n / 4);
+    if (n == 0) return;
+    if (n == 1) { out[0] = f[0]; return; }
+    bool fits = n < (1u << 22);
+    if (fits) {
+        keys.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t ss = (uint32_t)f[i].ss, se = (uint32_t)f[i].se;
+            if ((ss | se) >> 21) { fits = false; break; }
+            const uint64_t a = reverse ? 0x1FFFFFu - ss : ss, b = reverse ? 0x1FFFFFu - se : se;
+            keys[i] = a << 43 | b << 22 | (uint64_t)i;
+        }
+    }
+    if (fits) {
+        if (n < 192) std::sort(keys.begin(), keys.end());
+        else radix_sort_keys(keys, tmp, 22, 64);                    // stable: the file position in the low bits stays ordered
+        for (size_t i = 0; i < n; ++i) out[i] = f[keys[i] & 0x3FFFFFu];
+        return;
+    }
+    for (size_t i = 0; i < n; ++i) { out[i] = f[i]; out[i].ord = (int32_t)i; }
+    if (!reverse)
+        std::sort(out.begin(), out.begin() + (ptrdiff_t)n, [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : (a.se != b.se ? a.se < b.se : a.ord < b.ord); });
+    else
+        std::sort(out.begin(), out.begin() + (ptrdiff_t)n, [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : (a.se != b.se ? a.se > b.se : a.ord < b.ord); });
+}
+
+// chains of one (query, subject) pair: forward clusters, then reverse clusters (module/Util.py:4162-4319).
+// `fw` / `rv`: the pair's HSPs of either strand in file order (:4168-4172).
+void chain_subject(const Frag* fw, size_t n_fw, const Frag* rv, size_t n_rv, int skip_gap, int subj, std::vector<Chain>& chains,
+                   Scratch& S) {
+    std::vector<Frag>& cl = S.cl;
     for (int pass = 0; pass < 2; ++pass) {                                            // :4178-4227
-        const std::vector<Frag>& p = pass ? rv : fw;
+        const size_t np = pass ? n_rv : n_fw;
+        sort_strand(pass ? rv : fw, np, pass != 0, S.sorted, S.keys, S.tmp);
+        const Frag* p = S.sorted.data();
         cl.clear();
-        for (size_t k = 0; k < p.size(); ++k) {
+        for (size_t k = 0; k < np; ++k) {
             bool closed = false;
             if (k > 0)
                 for (size_t e = cl.size(); e-- > 0;) {
                     const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
                     if (gap < skip_gap && p[k].qe > cl[e].qe) { closed = true; break; }
                 }
-            if (k > 0 && !closed) { chain_cluster(cl, skip_gap, subj, chains, S.used); cl.clear(); }
+            if (k > 0 && !closed) { chain_cluster(cl, skip_gap, subj, chains, S.used, S.keys, S.ctmp); cl.clear(); }
             cl.push_back(p[k]);
         }
-        if (!cl.empty()) chain_cluster(cl, skip_gap, subj, chains, S.used);
+        if (!cl.empty()) chain_cluster(cl, skip_gap, subj, chains, S.used, S.keys, S.ctmp);
     }
 }
 
-// per query segment: subjects in order of first appearance (Python dict order, module/Util.py:4140-4147)
+// per query segment: subjects in order of first appearance (Python dict order, module/Util.py:4140-4147); the HSPs of the
+// query in ONE array, bucketed by (subject slot, strand) with the file order kept inside a bucket (a counting sort: two
+// passes over the query's HSPs, no per-subject vectors)
 struct QueryWork {
     std::vector<int32_t> order;                  // subject ids in first-appearance order
-    std::vector<std::vector<Frag>> per;          // HSPs of each subject, file order
+    std::vector<uint32_t> start;                 // bucket 2 * slot (forward) / 2 * slot + 1 (reverse) = frags[start[b] .. start[b + 1])
+    std::vector<Frag> frags;
     std::vector<std::vector<Chain>> chains;      // filled by the (query, subject) work items
 };
 
-void group_query(const hb_hsp* h, size_t n, int32_t q_index, QueryWork& w) {
-    std::vector<int32_t> slot;
+void group_query(const hb_hsp* h, size_t n, int32_t q_index, QueryWork& w, uint32_t n_subj) {
+    std::vector<int32_t> slot((size_t)n_subj, -1);
+    std::vector<uint32_t>& start = w.start;
+    start.clear();
+    auto skip = [&](const hb_hsp& x) { return x.subj == q_index && x.qs == x.ss && x.qe == x.se; };            // :4138
     for (size_t i = 0; i < n; ++i) {
         const hb_hsp& x = h[i];
-        if (x.subj == q_index && x.qs == x.ss && x.qe == x.se) continue;            // :4138
+        if (skip(x)) continue;
         if ((size_t)x.subj >= slot.size()) slot.resize((size_t)x.subj + 1, -1);
-        if (slot[x.subj] < 0) { slot[x.subj] = (int32_t)w.order.size(); w.order.push_back(x.subj); w.per.emplace_back(); }
-        w.per[slot[x.subj]].push_back(Frag{x.qs, x.qe, x.ss, x.se, 0});
+        if (slot[x.subj] < 0) { slot[x.subj] = (int32_t)w.order.size(); w.order.push_back(x.subj); start.push_back(0); start.push_back(0); }
+        start[2 * (size_t)slot[x.subj] + (x.ss > x.se ? 1 : 0)]++;
+    }
+    uint32_t run = 0;
+    for (uint32_t& c : start) { const uint32_t k = c; c = run; run += k; }
+    start.push_back(run);
+    w.frags.resize(run);
+    std::vector<uint32_t> cur(start.begin(), start.end() - 1);
+    for (size_t i = 0; i < n; ++i) {
+        const hb_hsp& x = h[i];
+        if (skip(x)) continue;
+        w.frags[cur[2 * (size_t)slot[x.subj] + (x.ss > x.se ? 1 : 0)]++] = Frag{x.qs, x.qe, x.ss, x.se, 0};
     }
     w.chains.resize(w.order.size());
 }
@@ -163,7 +255,18 @@ void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const
     };
     struct Iv { int64_t a, b; };
     std::vector<Iv> names;
-    for (const Chain& ch : chains) {
+    const size_t n_ch = chains.size();
+    for (size_t ci = 0; ci < n_ch; ++ci) {
+        if (ci + 8 < n_ch) {                          // the table is L2-sized and the probes are random: fetch ahead
+            const Chain& nx = chains[ci + 8];
+            const hb_segment& ns = segs[nx.subj];
+            const int32_t nsd = (int32_t)((ns.start + (nx.ss - 1)) / 10), nqd = (int32_t)((q.start + (nx.qs - 1)) / 10);
+            for (int x = -1; x <= 1; ++x) {
+                __builtin_prefetch(&table[slot_of(ns.chr, nsd + x)]);
+                __builtin_prefetch(&table[slot_of(q.chr, nqd + x)]);
+            }
+        }
+        const Chain& ch = chains[ci];
         const hb_segment& s = segs[ch.subj];
         const int64_t sa = s.start + (ch.ss - 1), sb = s.start + ch.se;
         const int64_t qa = q.start + (ch.qs - 1), qb = q.start + ch.qe;
@@ -240,7 +343,7 @@ int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const 
     };
     run_pool(n_seg, [&](size_t g, Scratch&) {
         const uint64_t a = q_off[g], b = q_off[g + 1];
-        if (b > a) group_query(hsp + a, (size_t)(b - a), (int32_t)g, work[g]);
+        if (b > a) group_query(hsp + a, (size_t)(b - a), (int32_t)g, work[g], n_seg);
     });
     lap("group");
     std::vector<std::pair<uint32_t, uint32_t>> items;          // (query, subject slot)
@@ -249,7 +352,9 @@ int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const 
     run_pool(items.size(), [&](size_t i, Scratch& S) {
         QueryWork& w = work[items[i].first];
         const uint32_t k = items[i].second;
-        chain_subject(w.per[k], skip_gap, w.order[k], w.chains[k], S);
+        const Frag* f = w.frags.data();
+        const uint32_t a = w.start[2 * k], m = w.start[2 * k + 1], b = w.start[2 * k + 2];
+        chain_subject(f + a, m - a, f + m, b - m, skip_gap, w.order[k], w.chains[k], S);
     });
     lap("chain");
     // de-duplication per BLAST result FILE: the query records of one file share the rounded-position table and the file's
