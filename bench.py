@@ -182,6 +182,8 @@ def main():
                     help="N > 1: re-deal the shards on the per-candidate cost measured by the first warm-up round")
     ap.add_argument("--gather-thread", default="off", choices=["on", "off"],
                     help="N > 1: finish the all-gather (and rank 0's read-back) on a helper thread while the next round runs")
+    ap.add_argument("--strong-leg", default="on", choices=["on", "off"],
+                    help="default C2 run: also measure the strong-scaling leg (C4, fixed genome) and report it under strong_scaling")
     ap.add_argument("--coarse", default=None, choices=["on", "off"],
                     help="time the coarse-boundary stage too (default: on, except C5 -- at ~85 %% repeat content the all-vs-all has "
                          "> 10^10 seed pairs before the known-TE masking the reference applies first)")
@@ -230,13 +232,38 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = gpu_arm(args, args.config, scaling, args.steps, args.warmup, rank, world, local, cores, headline=True)
+    # second leg of the default run: STRONG scaling on a fixed genome (C4: 400 Mbp, 50 000 candidates dealt over the N GPUs by
+    # chunk then rebalanced) next to the weak-scaling headline, so every N of a scaling sweep carries both curves
+    if args.strong_leg == "on" and args.config == "C2" and not args.small:
+        s_line = gpu_arm(args, "C4", "strong", min(args.steps, 5), min(args.warmup, 3), rank, world, local, cores, headline=False)
+        if rank == 0:
+            line["strong_scaling"] = {k: s_line[k] for k in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "e2e",
+                                                             "stages_ms", "collective_ms_per_step", "kernel_only_ms_per_step", "per_rank",
+                                                             "calls", "gpu_launches")}
+            line["strong_scaling"]["config"] = {k: s_line["config"][k] for k in ("workload", "name", "genome_bp", "candidates", "parallelism")}
+            line["strong_scaling"]["index_build_ms"] = s_line["setup"]["index_build_ms"]
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def gpu_arm(args, config, scaling, n_steps, n_warmup, rank, world, local, cores, headline):
+    """One measured leg on the GPUs: workload `config`, `n_warmup` untimed + `n_steps` timed rounds.  -> the JSON line (rank 0;
+    None elsewhere).  `headline`: also the coarse stage, the per-type / adjacent-row extras and the CPU baseline."""
+    import torch
+    import torch.distributed as dist
+    import hite_b200
+    from hite_b200 import dist as hbdist
     t_gen = time.perf_counter()
-    wl, wname = workload_for(args.config, scaling, world, args.small)
+    wl, wname = workload_for(config, scaling, world, args.small)
     t_gen = time.perf_counter() - t_gen
     n_total = len(wl.cand_seqs)
     lens_all = [len(c) for c in wl.cand_seqs]
     # SURVEY 8(e): chunk -> rank, then rebalance by candidate (chunk = 100 Mbp of the concatenated contigs; one chunk: plain deal)
-    if args.config == "C4" and world > 1:
+    if config == "C4" and world > 1:
         clen = wl.genome_bp // len(wl.contig_seqs)
         chunk_of = [(t["contig"] * clen + t["start"]) // 100_000_000 for t in wl.truth]
         shards = [hbdist.shard_by_chunk(chunk_of, lens_all, r, world) for r in range(world)]
@@ -254,7 +281,7 @@ def main():
 
     # coarse-boundary stage on the same genome (module/coarse_boundary.py): all-vs-all self-join + FMEA, the query-segment
     # files dealt in contiguous blocks to the ranks (every rank holds the whole index); max over ranks.
-    do_coarse = (args.coarse or ("off" if args.config == "C5" else "on")) == "on"
+    do_coarse = headline and (args.coarse or ("off" if config == "C5" else "on")) == "on"
     coarse = None
     if do_coarse:
         ctx.coarse_boundary(seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=max(1, cores // world),
@@ -265,13 +292,14 @@ def main():
         tmc = ctx.coarse_timing()
         # k_ms[4] = wall of the stage inside the library: GPU blocks software-pipelined with the host FMEA of the previous block
         cs = torch.tensor([tmc["k_ms"][4] * 1e-3, time.perf_counter() - tc, float(len(iv)),
-                           tmc["kernel_ms"], tmc["k_ms"][3], tmc["k_ms"][6], tmc["k_ms"][7]], device="cuda", dtype=torch.float64)
+                           tmc["kernel_ms"], tmc["k_ms"][3], tmc["k_ms"][6], tmc["k_ms"][7], tmc["k_ms"][5]], device="cuda", dtype=torch.float64)
         cmax, csum = cs.clone(), cs.clone()
         if world > 1:
             dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(csum, op=dist.ReduceOp.SUM)
         coarse = {"intervals": int(csum[2]), "hsps": int(csum[5]), "seed_pairs_M": float(csum[6]),
-                  "gpu_ms_max_rank": float(cmax[3]), "fmea_host_ms_max_rank": float(cmax[4]), "stage_ms_max_rank": float(cmax[0]) * 1e3,
+                  "gpu_ms_max_rank": float(cmax[3]), "fmea_host_ms_max_rank": float(cmax[4]),
+                  "fmea_task_ms_per_thread_max_rank": float(cmax[7]), "stage_ms_max_rank": float(cmax[0]) * 1e3,
                   "wall_s_max_rank": float(cmax[1]),
                   "Mbp_per_s": wl.genome_bp / 1e6 / max(1e-9, float(cmax[0])),
                   "sharding": "query-segment file blocks over %d rank(s), whole index on every rank" % world}
@@ -293,8 +321,11 @@ def main():
             flat = np.frombuffer(b"".join(cands) + b"\0", dtype=np.uint8)
             offs = np.zeros(len(cands) + 1, dtype=np.uint64)
             offs[1:] = np.cumsum([len(c) for c in cands])
+            ctx.pin_host(flat)                            # the round's candidate file is handed to hb_adjust every step
+            pinned.append(flat)
             out.append((kind, np.asarray(idx, dtype=np.int32), (flat, offs)))
         return out
+    pinned = []
     groups = make_groups(my)
     gather = hbdist.RecordGather([len(s) for s in shards], [sum(lens_all[i] for i in s) for s in shards], "cuda")
     cost = np.zeros(n_total, dtype=np.int64)              # filled by the first warm-up round when the shards get rebalanced
@@ -340,7 +371,7 @@ def main():
     # length); the shards are then re-dealt heaviest-first on that cost -- what a stage does between its rounds, which run the
     # same candidates again (judge_TIR_transposons.py:29-38).  The timed rounds all run on the re-dealt shards.
     rebalanced = False
-    for w in range(args.warmup):
+    for w in range(n_warmup):
         state["collect_cost"] = world > 1 and w == 0 and args.rebalance == "on"
         step()
         if state["collect_cost"]:
@@ -367,7 +398,7 @@ def main():
     h2d = d2h = launches = 0
     n_te_local = 0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         k_ms, st, h2d, d2h, launches, n_te_local = step()
         torch.cuda.current_stream().synchronize()
         dev_ms.append(k_ms); g_ms.append(ev[0].elapsed_time(ev[1])); stage += st
@@ -393,8 +424,8 @@ def main():
         my_mhz = float(torch.cuda.clock_rate())
     except Exception:
         my_mhz = 0.0
-    mine_v = torch.tensor([float(np.sum(dev_ms)) / args.steps] + [float(x) / args.steps for x in stage[:6]] + [wall * 1e3 / args.steps, my_mhz] +
-                          [float(x) * 1e3 / args.steps for x in host_t], device="cuda", dtype=torch.float64)
+    mine_v = torch.tensor([float(np.sum(dev_ms)) / n_steps] + [float(x) / n_steps for x in stage[:6]] + [wall * 1e3 / n_steps, my_mhz] +
+                          [float(x) * 1e3 / n_steps for x in host_t], device="cuda", dtype=torch.float64)
     per_rank = [mine_v.clone() for _ in range(world)]
     if world > 1:
         dist.all_gather(per_rank, mine_v)
@@ -409,6 +440,7 @@ def main():
     algo_bytes = float(np.sum(algo_bytes_pair(pair_L)))
     last_tm = ctx.timing()
     ext_s_last = last_tm["k_ms"][2] * 1e-3
+    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -419,7 +451,7 @@ def main():
         traffic, alu_pct, tsrc = None, None, None     # dram bytes / ALU-pipe utilisation of the dominant stage: one `ncu --set full` capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-            if not args.small and world == 1 and args.config == "C2":
+            if not args.small and world == 1 and config == "C2":
                 traffic = tj["extend_stage"]["dram_bytes_per_step"]
                 alu_pct = tj["extend_stage"].get("alu_pipe_pct_of_peak")
                 tsrc = tj["extend_stage"].get("source")
@@ -428,21 +460,21 @@ def main():
         achieved = algo_bytes / ext_s_last / 1e9 if ext_s_last > 0 else 0.0
         dp_cells = float(last_tm["k_ms"][7]) * 1e6 * 32
         line = {
-            "metric": "candidate TEs boundary-adjusted/sec", "value": n_total * args.steps / dev_max, "unit": "candidates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_max / args.steps * 1e3,
+            "metric": "candidate TEs boundary-adjusted/sec", "value": n_total * n_steps / dev_max, "unit": "candidates/s",
+            "n_gpus": world, "steps": n_steps, "warmup": n_warmup, "ms_per_step": dev_max / n_steps * 1e3,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": wname, "name": args.config, "genome_bp": wl.genome_bp, "candidates": n_total, "k": K_MM, "w": W_MM,
+            "config": {"workload": wname, "name": config, "genome_bp": wl.genome_bp, "candidates": n_total, "k": K_MM, "w": W_MM,
                        "max_loci": 300, "band": "32 / 64 diagonals", "judges": kinds,
                        "mean_candidate_bp": float(np.mean(lens_all)), "repeat_bp": getattr(wl, "repeat_bp", None),
                        "l2": "inputs larger than L2 (packed genome+index %.0f MB, traceback stream %.1f GB/step)"
-                       % ((info["total_padded"] * 0.375 + info["n_minimizers"] * 8) / 1e6, float(stage[7] / args.steps) * 1e6 * 16 / 1e9),
+                       % ((info["total_padded"] * 0.375 + info["n_minimizers"] * 8) / 1e6, float(stage[7] / n_steps) * 1e6 * 16 / 1e9),
                        "parallelism": "candidates sharded over %d GPU(s)%s, genome+index replicated, 1 fused NCCL all-gather/step "
-                                      "(inside ms_per_step)%s" % (world, " by chunk then rebalanced" if args.config == "C4" and world > 1 else "",
+                                      "(inside ms_per_step)%s" % (world, " by chunk then rebalanced" if config == "C4" and world > 1 else "",
                                                                  "; shards re-dealt on measured cost (loci x length) after the first warm-up round"
                                                                  if rebalanced else "")},
-            "e2e": {"value": n_total * args.steps / wall_max, "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
+            "e2e": {"value": n_total * n_steps / wall_max, "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h) + (int(gather.bytes_sent) if world > 1 else 0)},
-            "gpu_launches": int(launches) * args.steps,
+            "gpu_launches": int(launches) * n_steps,
             "clocks": clocks,
             "roofline": {"kernel": "extend16_kernel + traceback_kernel (banded SW, two pairs per lane; hb_extend16.cuh)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -453,10 +485,10 @@ def main():
                                  "bytes/pair per SURVEY 8(d)-(ii) = (2L+2*flank)*3/8 + 8*(2L/(w+1)) + 16 + ceil((L+100)/4)"
                                  % (dp_cells / ext_s_last / 1e9 if ext_s_last else 0, "%.1f" % alu_pct if alu_pct else "n/a"),
                          "kernel_ms": ext_s_last * 1e3, "pairs": int(len(copies)), "judge_group": last_kind},
-            "stages_ms": {k: float(v / args.steps) for k, v in zip(
+            "stages_ms": {k: float(v / n_steps) for k, v in zip(
                 ("sketch_cands", "seed_sort_cluster", "extend", "copy_rules_msa", "clean_judge", "compact"), stage[:6])},
-            "collective_ms_per_step": gather_max / args.steps,
-            "kernel_only_ms_per_step": kern_max / args.steps * 1e3,
+            "collective_ms_per_step": gather_max / n_steps,
+            "kernel_only_ms_per_step": kern_max / n_steps * 1e3,
             "per_rank": {"kernel_ms": [round(float(v[0]), 2) for v in per_rank],
                          "extend_ms": [round(float(v[3]), 2) for v in per_rank],
                          "clean_judge_ms": [round(float(v[5]), 2) for v in per_rank],
@@ -475,9 +507,9 @@ def main():
             "coarse_boundary": coarse,
             "mbp_per_s": coarse["Mbp_per_s"] if coarse else None,
         }
-        if world == 1 and not args.small and not args.no_extras and args.config == "C2":
+        if headline and world == 1 and not args.small and not args.no_extras and config == "C2":
             extras(line, ctx, wl, [wl.cand_seqs[i] for i in my], cores)
-        if not args.no_cpu_baseline and world == 1:
+        if headline and not args.no_cpu_baseline and world == 1:
             per = min(len(my), max(256, 32 * cores))
             dt, verd, _ = cpu_reference_run(wl, [my[i] for i in range(per)], cores)
             line["cpu_baseline"] = {"value": per / dt, "unit": "candidates/s", "cores": cores, "kind": "port",
@@ -495,11 +527,10 @@ def main():
                 same = int((mine == verd[tir]).all(axis=1).sum())
                 line["cpu_baseline"]["parity"] = {"candidates": len(tir), "identical_verdicts": same,
                                                   "fields": "is_te, info, copy_num, cons_len (full pass, no truncated-member gate)"}
-        print(json.dumps(line))
+    for a in pinned:
+        ctx.unpin_host(a)
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return line if rank == 0 else None
 
 
 def adjust_chunked(ctx, kind, idx, host_cands, chunk, alias_ok):
@@ -515,7 +546,7 @@ def adjust_chunked(ctx, kind, idx, host_cands, chunk, alias_ok):
         hi = min(n, lo + chunk["n"])
         sub = (flat[int(offs[lo]):int(offs[hi]) + 1], offs[lo:hi + 1] - offs[lo]) if (lo, hi) != (0, n) else host_cands
         try:
-            calls, cons = ctx.adjust_raw(sub, kind, 1)
+            calls, cons = ctx.adjust_raw(sub, kind, 1, cons_view=True)
         except hite_b200.HiteB200Error as e:
             if "(-4)" not in str(e) or chunk["n"] <= 64:
                 raise

@@ -201,6 +201,9 @@ def load():
     lib.hb_debug_scan_total.argtypes = [vp, C.c_uint64, C.c_uint32, u64p, C.POINTER(C.c_uint32)]
     lib.hb_last_msa.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
     lib.hb_last_msa_trunc.argtypes = [vp, C.c_uint32, vp, C.c_uint64, i32p, i32p]
+    lib.hb_last_cons_view.argtypes = [vp, C.POINTER(C.c_void_p), u64p]
+    lib.hb_host_register.argtypes = [vp, C.c_uint64]
+    lib.hb_host_unregister.argtypes = [vp]
     lib.hb_fmea_chain.argtypes = [vp, vp, C.c_uint32, vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
     lib.hb_query_copies.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, vp,
                                     C.c_uint32, C.POINTER(C.c_uint32)]
@@ -369,14 +372,26 @@ class Context:
         self._check(self._lib.hb_debug_index(self._h, _ptr(keys), len(keys)), "hb_debug_index")
         return keys[:n]
 
+    def pin_host(self, arr):
+        """Page-lock a caller-owned numpy buffer that is passed to ``adjust_raw`` repeatedly (``hb_host_register``): the
+        host->device copy then runs as one DMA.  Returns False when the range cannot be locked (the buffer stays usable);
+        call ``unpin_host`` before the array is freed."""
+        return self._lib.hb_host_register(_ptr(arr), arr.nbytes) == 0
+
+    def unpin_host(self, arr):
+        return self._lib.hb_host_unregister(_ptr(arr)) == 0
+
     def adjust_raw(self, cand_seqs, te_type="tir", plant=1, result_type="cons", occ_cap=512, max_loci=300, flank=50,
-                   max_rows=100, tb_budget_bytes=0, trunc_gate=True, overlap=None, rows_first=False, no_judge=False):
+                   max_rows=100, tb_budget_bytes=0, trunc_gate=True, overlap=None, rows_first=False, no_judge=False,
+                   cons_view=False):
         """One ``flank_region_align_v5``-equivalent round (kernels ii + iii) over the candidates.
         Returns ``(calls, cons)``: a structured array (CALL_DTYPE, one record per candidate) and the
         consensus bytes; candidate i's consensus is ``cons[calls['cons_off'][i] : +calls['cons_len'][i]]``.
         ``overlap`` >= 2: that many candidate sub-batches software-pipelined over two CUDA streams (same bytes
         back; measured on B200 it does not beat the serial batch -- every stage already fills the SMs, see
-        tools/overlap_sweep.py -- so the default is one serial batch, which ``last_copies`` / ``last_msa`` need)."""
+        tools/overlap_sweep.py -- so the default is one serial batch, which ``last_copies`` / ``last_msa`` need).
+        ``cons_view``: the consensus bytes come back as a read-only view of the library's page-locked result buffer
+        (``hb_last_cons_view``: no second pass over them), valid until the next call on this context."""
         if isinstance(cand_seqs, tuple):                      # pre-flattened (uint8 array, uint64 offsets)
             flat, off = cand_seqs
             n = len(off) - 1
@@ -395,9 +410,17 @@ class Context:
         nbytes = C.c_uint64(0)
         self._check(self._lib.hb_adjust(self._h, n, _ptr(flat), _ptr(off), C.byref(prm), _ptr(calls), C.byref(nbytes)),
                     "hb_adjust")
+        self.last_calls = calls
+        if cons_view:
+            p, nb = C.c_void_p(), C.c_uint64(0)
+            self._check(self._lib.hb_last_cons_view(self._h, C.byref(p), C.byref(nb)), "hb_last_cons_view")
+            if not nb.value:
+                return calls, np.zeros(0, dtype=np.uint8)
+            view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(int(nb.value),))
+            view.flags.writeable = False
+            return calls, view
         cons = np.empty(max(1, nbytes.value), dtype=np.uint8)
         self._check(self._lib.hb_last_cons(self._h, _ptr(cons), len(cons)), "hb_last_cons")
-        self.last_calls = calls
         return calls, cons[:nbytes.value]
 
     def adjust(self, cand_seqs, *a, **kw):

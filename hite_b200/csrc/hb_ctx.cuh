@@ -81,6 +81,7 @@ struct hb_ctx {
     HbLane lane[3];
     std::vector<HbHostBuf> part_cons;                                  // pinned consensus bytes per sub-batch
     std::vector<std::pair<const uint8_t*, uint64_t>> cons_parts;       // last hb_adjust: parts in candidate order
+    std::vector<uint8_t> cons_stitched;                                // hb_last_cons_view of an overlapped run
     bool last_overlapped = false;  // the hb_last_copies / hb_last_msa getters need a serial hb_adjust
     // genome state (HB-align S1/S2)
     bool have_genome = false, have_index = false;

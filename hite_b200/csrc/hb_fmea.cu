@@ -16,6 +16,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <unordered_set>
 #include <vector>
@@ -184,6 +188,7 @@ struct QueryWork {
     std::vector<uint32_t> start;                 // bucket 2 * slot (forward) / 2 * slot + 1 (reverse) = frags[start[b] .. start[b + 1])
     std::vector<Frag> frags;
     std::vector<std::vector<Chain>> chains;      // filled by the (query, subject) work items
+    void swap_storage(QueryWork& o) { order.swap(o.order); start.swap(o.start); frags.swap(o.frags); chains.swap(o.chains); }
 };
 
 void group_query(const hb_hsp* h, size_t n, int32_t q_index, QueryWork& w, uint32_t n_subj) {
@@ -313,60 +318,73 @@ void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const
 
 }  // namespace
 
-// HSPs must be grouped by query segment: query segment g owns hsp[q_off[g] .. q_off[g+1]).
-// Three phases over a thread pool: group per query, chain per (query, subject) pair (the bulk of the work,
-// 10^4 independent items for a 100-segment chunk), order-dependent de-duplication per query.
-int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
-                int max_len, int threads, std::vector<hb_interval>& result, const uint32_t* file_of_seg) {
-    std::vector<QueryWork> work(n_seg);
-    std::vector<std::vector<hb_interval>> per(n_seg);
-    const int nt = std::max(1, threads);
-    std::vector<Scratch> scratch((size_t)nt);
-    auto run_pool = [&](size_t n_items, const std::function<void(size_t, Scratch&)>& fn) {
-        std::atomic<size_t> next{0};
-        std::atomic<int> workers{0};
-        std::atomic<long> busy_us{0};
-        auto loop = [&](int tid) { int did = 0; auto b0 = std::chrono::steady_clock::now(); for (;;) { const size_t i = next.fetch_add(1); if (i >= n_items) break; fn(i, scratch[(size_t)tid]); ++did; } if (did) workers++; busy_us += (long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - b0).count(); };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < (int)std::min<size_t>((size_t)nt, n_items); ++t) pool.emplace_back(loop, t);
-        loop(0);
-        for (auto& th : pool) th.join();
-        if (getenv("HB_DEBUG_TIMING")) fprintf(stderr, "[hb_fmea] pool: %zu items, nt=%d, spawned=%zu, workers that got items=%d, sum busy %.1f ms\n", n_items, nt, pool.size(), workers.load(), busy_us.load() * 1e-3);
-    };
-    const bool dbg = getenv("HB_DEBUG_TIMING") != nullptr;
-    auto t0 = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
-        if (!dbg) return;
-        auto t = std::chrono::steady_clock::now();
-        fprintf(stderr, "[hb_fmea] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t0).count());
-        t0 = t;
-    };
-    run_pool(n_seg, [&](size_t g, Scratch&) {
-        const uint64_t a = q_off[g], b = q_off[g + 1];
-        if (b > a) group_query(hsp + a, (size_t)(b - a), (int32_t)g, work[g], n_seg);
-    });
-    lap("group");
-    std::vector<std::pair<uint32_t, uint32_t>> items;          // (query, subject slot)
-    for (uint32_t g = 0; g < n_seg; ++g)
-        for (uint32_t k = 0; k < work[g].order.size(); ++k) items.emplace_back(g, k);
-    run_pool(items.size(), [&](size_t i, Scratch& S) {
-        QueryWork& w = work[items[i].first];
-        const uint32_t k = items[i].second;
-        const Frag* f = w.frags.data();
-        const uint32_t a = w.start[2 * k], m = w.start[2 * k + 1], b = w.start[2 * k + 2];
-        chain_subject(f + a, m - a, f + m, b - m, skip_gap, w.order[k], w.chains[k], S);
-    });
-    lap("chain");
-    // de-duplication per BLAST result FILE: the query records of one file share the rounded-position table and the file's
-    // name dict, in record order (file_of_seg: non-decreasing file id per segment; NULL = one record per file)
-    std::vector<std::pair<uint32_t, uint32_t>> files;           // [first, last) segment of every file
-    for (uint32_t g = 0; g < n_seg;) {
-        uint32_t e = g + 1;
-        while (file_of_seg && e < n_seg && file_of_seg[e] == file_of_seg[g]) ++e;
-        files.emplace_back(g, e);
-        g = e;
+// ------------------------------------------------------------------------------------------------
+// The chaining as a task graph on one pool of host threads (no phase barriers):
+//   G(q)    group the HSPs of query segment q by (subject, strand)          -> releases the C(q, k) of its subjects
+//   C(q, k) chain one (query, subject) pair (the bulk of the work, ~10^4 items for a 100-segment chunk)
+//   D(f)    order-dependent de-duplication of BLAST result file f, once every C of the file's queries is done
+// Blocks of whole files are submitted as the GPU delivers them (hb_coarse_boundary) and are chained while the GPU produces the
+// next ones; a file's D runs while the C items of later files still keep the other threads busy.
+struct HbFmeaPool {
+    struct Task { uint8_t type; uint32_t a, b; };       // 0 = G(a), 1 = C(a, slot b), 2 = D(file a)
+    uint32_t n_seg = 0;
+    const hb_segment* segs = nullptr;
+    int skip_gap = 0, max_len = 0;
+    std::vector<QueryWork> work;
+    std::vector<std::vector<hb_interval>> per;
+    std::vector<const hb_hsp*> q_hsp;                    // HSP slice of every query segment (set by submit)
+    std::vector<uint64_t> q_n;
+    std::vector<std::pair<uint32_t, uint32_t>> files;    // [first, last) segment of every file
+    std::vector<uint32_t> file_of;                       // file index of every segment
+    std::unique_ptr<std::atomic<int64_t>[]> pending;     // per file: G / C tasks not finished yet
+    std::deque<Task> queue;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t inflight = 0;                               // tasks pushed and not finished (under mu)
+    bool closing = false;
+    std::vector<std::thread> threads;
+    std::vector<Scratch> scratch;
+    std::atomic<int64_t> busy_us{0};
+    std::chrono::steady_clock::time_point t_first{}, t_last{};
+    bool any = false;
+
+    void push_locked(const Task& t, bool front) {
+        if (front) queue.push_front(t); else queue.push_back(t);
+        ++inflight;
     }
-    run_pool(files.size(), [&](size_t f, Scratch& S) {
+    void run_task(const Task& t, Scratch& S) {
+        if (t.type == 0) {
+            const uint32_t g = t.a;
+            group_query(q_hsp[g], (size_t)q_n[g], (int32_t)g, work[g], n_seg);
+            const uint32_t n_items = (uint32_t)work[g].order.size();
+            std::atomic<int64_t>& pend = pending[file_of[g]];
+            pend.fetch_add((int64_t)n_items);
+            if (n_items) {
+                std::lock_guard<std::mutex> lk(mu);
+                for (uint32_t k = 0; k < n_items; ++k) push_locked(Task{1, g, k}, false);
+            }
+            if (n_items > 1) cv.notify_all(); else if (n_items) cv.notify_one();
+            release(file_of[g]);
+        } else if (t.type == 1) {
+            QueryWork& w = work[t.a];
+            const uint32_t k = t.b;
+            const Frag* f = w.frags.data();
+            const uint32_t a = w.start[2 * k], m = w.start[2 * k + 1], b = w.start[2 * k + 2];
+            chain_subject(f + a, m - a, f + m, b - m, skip_gap, w.order[k], w.chains[k], S);
+            release(file_of[t.a]);
+        } else {
+            dedup_file(t.a, S);
+        }
+    }
+    void release(uint32_t f) {
+        if (pending[f].fetch_sub(1) == 1) {              // the file's last G / C: its de-duplication can run (long task: front)
+            { std::lock_guard<std::mutex> lk(mu); push_locked(Task{2, f, 0}, true); }
+            cv.notify_one();
+        }
+    }
+    // de-duplication per BLAST result FILE: the query records of one file share the rounded-position table and the file's
+    // name dict, in record order
+    void dedup_file(uint32_t f, Scratch& S) {
         const uint32_t g0 = files[f].first, g1 = files[f].second;
         size_t file_chains = 0;
         for (uint32_t g = g0; g < g1; ++g) for (const auto& c : work[g].chains) file_chains += c.size();
@@ -384,11 +402,96 @@ int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const 
                     return false;
                 }), mine.end());
             }
+            QueryWork().swap_storage(work[g]);           // the query's fragments and chains are not needed any more
         }
-    });
-    lap("dedup");
+    }
+    void worker(int tid) {
+        Scratch& S = scratch[(size_t)tid];
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !queue.empty() || (closing && inflight == 0); });
+                if (queue.empty()) return;
+                t = queue.front();
+                queue.pop_front();
+            }
+            const auto b0 = std::chrono::steady_clock::now();
+            run_task(t, S);
+            busy_us += (int64_t)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - b0).count();
+            bool done = false;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                done = (--inflight == 0);
+                if (done) t_last = std::chrono::steady_clock::now();
+            }
+            if (done) cv.notify_all();                   // finish() and the idle workers re-check
+        }
+    }
+};
+
+HbFmeaPool* hb_fmea_pool_start(uint32_t n_seg, const hb_segment* segs, const uint32_t* file_of_seg, int skip_gap, int max_len,
+                               int threads) {
+    HbFmeaPool* P = new HbFmeaPool();
+    P->n_seg = n_seg; P->segs = segs; P->skip_gap = skip_gap; P->max_len = max_len;
+    P->work.resize(n_seg); P->per.resize(n_seg); P->q_hsp.assign(n_seg, nullptr); P->q_n.assign(n_seg, 0);
+    P->file_of.resize(n_seg);
+    for (uint32_t g = 0; g < n_seg;) {                   // file_of_seg: non-decreasing file id per segment; NULL = one record per file
+        uint32_t e = g + 1;
+        while (file_of_seg && e < n_seg && file_of_seg[e] == file_of_seg[g]) ++e;
+        for (uint32_t x = g; x < e; ++x) P->file_of[x] = (uint32_t)P->files.size();
+        P->files.emplace_back(g, e);
+        g = e;
+    }
+    P->pending.reset(new std::atomic<int64_t>[P->files.size() + 1]);
+    for (size_t f = 0; f <= P->files.size(); ++f) P->pending[f].store(0);
+    const int nt = std::max(1, threads);
+    P->scratch.resize((size_t)nt);
+    for (int t = 0; t < nt; ++t) P->threads.emplace_back(&HbFmeaPool::worker, P, t);
+    return P;
+}
+
+// One block: the HSPs of the query segments that have any, grouped by query segment (segment g owns hsp[q_off[g] ..
+// q_off[g+1])).  The arrays stay the caller's and must live until hb_fmea_pool_finish; a block holds whole files and a query
+// segment's HSPs come in one block.
+void hb_fmea_pool_submit(HbFmeaPool* P, const hb_hsp* hsp, const uint64_t* q_off) {
+    std::vector<uint32_t> mine;
+    for (uint32_t g = 0; g < P->n_seg; ++g)
+        if (q_off[g + 1] > q_off[g]) { P->q_hsp[g] = hsp + q_off[g]; P->q_n[g] = q_off[g + 1] - q_off[g]; mine.push_back(g); }
+    if (mine.empty()) return;
+    for (uint32_t g : mine) P->pending[P->file_of[g]].fetch_add(1);      // every G holds its file open until its C items are queued
+    {
+        std::lock_guard<std::mutex> lk(P->mu);
+        if (!P->any) { P->any = true; P->t_first = std::chrono::steady_clock::now(); }
+        for (uint32_t g : mine) P->push_locked(HbFmeaPool::Task{0, g, 0}, false);
+    }
+    P->cv.notify_all();
+}
+
+// Waits for every task, joins the pool and frees it.  span_ms: first submit -> last task done; busy_ms: task time summed over
+// the threads.
+void hb_fmea_pool_finish(HbFmeaPool* P, std::vector<hb_interval>& result, double* span_ms, double* busy_ms) {
+    {
+        std::lock_guard<std::mutex> lk(P->mu);
+        P->closing = true;
+    }
+    P->cv.notify_all();
+    for (auto& th : P->threads) th.join();
     result.clear();
-    for (uint32_t g = 0; g < n_seg; ++g) result.insert(result.end(), per[g].begin(), per[g].end());
+    for (uint32_t g = 0; g < P->n_seg; ++g) result.insert(result.end(), P->per[g].begin(), P->per[g].end());
+    if (span_ms) *span_ms = P->any ? std::chrono::duration<double, std::milli>(P->t_last - P->t_first).count() : 0.0;
+    if (busy_ms) *busy_ms = (double)P->busy_us.load() * 1e-3;
+    delete P;
+}
+
+// HSPs must be grouped by query segment: query segment g owns hsp[q_off[g] .. q_off[g+1]).
+int hb_fmea_run(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs, int skip_gap,
+                int max_len, int threads, std::vector<hb_interval>& result, const uint32_t* file_of_seg) {
+    HbFmeaPool* P = hb_fmea_pool_start(n_seg, segs, file_of_seg, skip_gap, max_len, threads);
+    hb_fmea_pool_submit(P, hsp, q_off);
+    double span = 0.0, busy = 0.0;
+    hb_fmea_pool_finish(P, result, &span, &busy);
+    if (getenv("HB_DEBUG_TIMING")) fprintf(stderr, "[hb_fmea] %d threads: span %.3f ms, busy %.1f ms summed\n", std::max(1, threads), span, busy);
     return 0;
 }
 

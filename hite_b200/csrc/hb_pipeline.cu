@@ -890,6 +890,36 @@ extern "C" int hb_last_cons(hb_ctx* ctx, uint8_t* out, uint64_t cap) {
     return HB_OK;
 }
 
+extern "C" int hb_last_cons_view(hb_ctx* ctx, const uint8_t** ptr, uint64_t* nbytes) {
+    if (!ctx || !ptr || !nbytes) return HB_EINVAL;
+    *nbytes = ctx->last_cons_bytes;
+    *ptr = nullptr;
+    if (!ctx->last_cons_bytes) return HB_OK;
+    const std::pair<const uint8_t*, uint64_t>* only = nullptr;
+    int n_parts = 0;
+    for (const auto& part : ctx->cons_parts) if (part.second) { only = &part; ++n_parts; }
+    if (n_parts == 1 && only->second == ctx->last_cons_bytes) { *ptr = only->first; return HB_OK; }
+    ctx->cons_stitched.resize(ctx->last_cons_bytes);              // an overlapped run leaves one piece per sub-batch
+    uint64_t at = 0;
+    for (const auto& part : ctx->cons_parts) { if (part.second) memcpy(ctx->cons_stitched.data() + at, part.first, part.second); at += part.second; }
+    *ptr = ctx->cons_stitched.data();
+    return HB_OK;
+}
+
+extern "C" int hb_host_register(void* ptr, uint64_t nbytes) {
+    if (!ptr || !nbytes) return HB_EINVAL;
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)nbytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return HB_ECUDA; }
+    return HB_OK;
+}
+
+extern "C" int hb_host_unregister(void* ptr) {
+    if (!ptr) return HB_EINVAL;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return HB_ECUDA; }
+    return HB_OK;
+}
+
 extern "C" int hb_last_cons_device(hb_ctx* ctx, const void** dptr, uint64_t* nbytes) {
     if (!ctx || !dptr || !nbytes) return HB_EINVAL;
     *nbytes = ctx->last_cons_bytes;
@@ -1297,7 +1327,7 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     // order), FMEA over the block's files on `threads` host threads ----
     // (the grouped HSPs live in the context and only ever grow: a fresh 100 MB vector per block costs more in page faults
     // than the chaining itself)
-    struct Block { std::vector<hb_hsp>* hsps = nullptr; uint64_t n = 0; std::vector<uint64_t> off; std::vector<hb_interval> res; double fmea_ms = 0.0; };
+    struct Block { std::vector<hb_hsp>* hsps = nullptr; uint64_t n = 0; std::vector<uint64_t> off; };
     // stable counting sort by query segment on up to 8 host threads (thread t owns a contiguous slice of the records)
     auto group_block = [&](const HbHspRec* recs, uint64_t n, Block& B) {
         const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)std::max(1, threads), 8ull, n / 65536 + 1}));
@@ -1326,18 +1356,24 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
             for (uint64_t i = a; i < b; ++i) { const HbHspRec& r = recs[i]; dst[cur[(size_t)r.qseg]++] = hb_hsp{r.subj, r.qs, r.qe, r.ss, r.se}; }
         });
     };
+    // FMEA runs as a task graph on one pool of `threads` host threads for the whole part (hb_fmea.cu): a block is grouped and
+    // handed over as soon as its read-back is there, its chaining overlaps the GPU half of the following blocks and the
+    // order-dependent per-file de-duplication of earlier files overlaps the chaining of later ones.
+    auto t_all = std::chrono::steady_clock::now();
+    HbFmeaPool* pool = hb_fmea_pool_start((uint32_t)n_seg, segs.data(), file_of_seg.data(), skip_gap, max_len, threads);
     auto host_block = [&](const HbHspRec* recs, uint64_t n, Block& B) {
         group_block(recs, n, B);
-        auto t0 = std::chrono::steady_clock::now();
-        hb_fmea_run(B.hsps->data(), B.off.data(), (uint32_t)n_seg, segs.data(), skip_gap, max_len, threads, B.res, file_of_seg.data());
-        B.fmea_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        hb_fmea_pool_submit(pool, B.hsps->data(), B.off.data());
     };
-    // The part's files in up to 4 blocks, software-pipelined: while the host threads group and chain block b (FMEA is the
+    // The part's files in up to 8 blocks, software-pipelined: while the host threads group and chain block b (FMEA is the
     // longer half), the GPU already produces the HSPs of block b + 1 into the other pinned read-back buffer.  A block is made of
     // whole files, so its chaining is independent.
-    auto t_all = std::chrono::steady_clock::now();
     const uint32_t nf = f_hi - f_lo;
-    const uint32_t n_blocks = nf >= 8 ? 4u : 1u;
+    uint32_t n_blocks = nf >= 16 ? 8u : nf >= 8 ? 4u : 1u;
+    if (const char* e = getenv("HB_COARSE_BLOCKS")) {       // test hook: force the block count (the result does not depend on it)
+        const long v = atol(e);
+        if (v >= 1) n_blocks = (uint32_t)std::min<long>(v, std::max<uint32_t>(1u, nf));
+    }
     std::vector<Block> blocks(n_blocks);
     if (ctx->hsp_store.size() < n_blocks) ctx->hsp_store.resize(n_blocks);
     for (uint32_t b = 0; b < n_blocks; ++b) blocks[b].hsps = &ctx->hsp_store[b];
@@ -1353,6 +1389,9 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
         worker = std::thread(host_block, pin.as<HbHspRec>(), n_recs, std::ref(blocks[b]));
     }
     if (worker.joinable()) worker.join();
+    std::vector<hb_interval> res;
+    double fmea_span_ms = 0.0, fmea_busy_ms = 0.0;
+    hb_fmea_pool_finish(pool, res, &fmea_span_ms, &fmea_busy_ms);
     if (rc_gpu != HB_OK) return rc_gpu;
     // hb_last_hsps (a parity / debug getter) assembles the part's HSPs from the blocks on demand
     size_t n_all = 0;
@@ -1360,10 +1399,8 @@ extern "C" int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_ga
     for (Block& B : blocks) { n_all += B.n; ctx->last_hsp_blocks.emplace_back(B.n, std::move(B.off)); }
     ctx->last_hsps.clear(); ctx->last_hsp_off.clear();
     ctx->last_segs = segs;
-    std::vector<hb_interval> res;
-    double fmea_ms = 0.0;
-    for (const Block& B : blocks) { res.insert(res.end(), B.res.begin(), B.res.end()); fmea_ms += B.fmea_ms; }
-    tm.k_ms[3] = (float)fmea_ms;                                                    // host FMEA, summed over the blocks
+    tm.k_ms[3] = (float)fmea_span_ms;                                               // host FMEA: first block handed over -> last task done
+    tm.k_ms[5] = (float)(fmea_busy_ms / std::max(1, threads));                      // ... and its task time per host thread
     tm.k_ms[4] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_all).count();   // wall of the pipelined stage
     tm.k_ms[6] = (float)n_all;
     tm.k_ms[7] = (float)((double)n_pairs_total * 1e-6);

@@ -174,6 +174,16 @@ typedef struct {
 int hb_adjust(hb_ctx* ctx, uint32_t n_cand, const uint8_t* cand_ascii, const uint64_t* cand_off,
               const hb_params* prm, hb_call* calls, uint64_t* cons_bytes);
 int hb_last_cons(hb_ctx* ctx, uint8_t* out, uint64_t cap);
+/* the same bytes without a copy: *ptr points into the context's page-locked result buffer (what the device wrote by DMA),
+ * valid until the next call on this context.  The reference hands the consensus on as Python strings in memory
+ * (module/Util.py:10434-10437); a binding that wraps the view skips one pass over the bytes. */
+int hb_last_cons_view(hb_ctx* ctx, const uint8_t** ptr, uint64_t* nbytes);
+/* Page-lock (and release) a caller-owned host buffer that is handed to hb_adjust / hb_query_hsps / hb_tsd_candidates again
+ * and again, e.g. the flattened candidate file of a stage that runs several rounds over it (judge_TIR_transposons.py:29-38):
+ * the host->device copy then runs as one DMA at link speed instead of through the driver's staging buffer.  Optional --
+ * every entry point accepts pageable memory.  HB_ECUDA when the range cannot be locked (the buffer stays usable). */
+int hb_host_register(void* ptr, uint64_t nbytes);
+int hb_host_unregister(void* ptr);
 /* device-resident copy of the same bytes (valid until the next hb_adjust on this context): lets the
  * multi-GPU merge all-gather the records over NVLink without a host round trip */
 int hb_last_cons_device(hb_ctx* ctx, const void** dptr, uint64_t* nbytes);

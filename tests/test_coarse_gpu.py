@@ -47,7 +47,7 @@ def test_coarse_boundary_bit_exact_and_finds_planted_copies(ctx):
     assert sum(fam_hit.values()) >= 0.8 * len(fam_hit), fam_hit
 
 
-def test_sharded_coarse_boundary_parts_concatenate_to_the_whole(ctx):
+def test_sharded_coarse_boundary_parts_concatenate_to_the_whole(ctx, monkeypatch):
     """hb_coarse_boundary_part: the query-segment files dealt in contiguous blocks to 1, 2, 3, 5 parts; every part pairs its
     minimizers against the whole index and chains its own files.  Parts concatenated in part order == the unsharded list
     (which is the oracle's), also when there are more parts than files."""
@@ -68,6 +68,17 @@ def test_sharded_coarse_boundary_parts_concatenate_to_the_whole(ctx):
             got += key(part)
         assert got == exp_iv, n_parts
         assert sum(1 for x in sizes if x) >= min(n_parts, 4)          # the work really is spread over the parts
+    # the software pipeline inside one part (GPU block b + 1 while the host chains block b) never changes the result:
+    # blocks are whole files.  Real chunks get 4-8 blocks; the hook forces them on this small genome, HSP getter included.
+    ctx.coarse_boundary(seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=4)
+    whole_hsps, whole_off, _ = (np.array(x) for x in ctx.last_hsps())
+    for n_blocks in ("2", "3", "8"):
+        monkeypatch.setenv("HB_COARSE_BLOCKS", n_blocks)
+        blk = ctx.coarse_boundary(seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64, threads=4)
+        assert key(blk) == exp_iv, n_blocks
+        hs, off, _ = ctx.last_hsps()
+        assert np.array_equal(np.array(off), whole_off) and np.array_equal(np.array(hs), whole_hsps), n_blocks
+    monkeypatch.delenv("HB_COARSE_BLOCKS")
 
 
 def test_determine_repeat_boundary_v5_fasta_contract(ctx, tmp_path):

@@ -55,6 +55,27 @@ def test_copies_msa_and_calls_bit_exact(ctx, small):
     assert n_match >= 0.75 * len(wl.cand_seqs)      # planted truth recovered
 
 
+def test_pinned_input_and_result_view_return_the_same_bytes(ctx, small):
+    """hb_host_register + hb_last_cons_view (zero-copy ends of the public call) change nothing in the result, also for an
+    overlapped run whose consensus comes back in several pieces."""
+    wl, G = small
+    flat = np.frombuffer(b"".join(wl.cand_seqs) + b"\0", dtype=np.uint8).copy()
+    offs = np.zeros(len(wl.cand_seqs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(c) for c in wl.cand_seqs])
+    calls0, cons0 = ctx.adjust_raw((flat, offs), "tir", 1)
+    assert ctx.pin_host(flat)
+    try:
+        calls1, view = ctx.adjust_raw((flat, offs), "tir", 1, cons_view=True)
+        assert not view.flags.writeable
+        assert calls1.tobytes() == calls0.tobytes() and view.tobytes() == cons0.tobytes() and len(cons0) > 0
+    finally:
+        assert ctx.unpin_host(flat)
+    many = wl.cand_seqs * 8                                    # >= 64 candidates per part: the overlapped path really splits
+    c0, b0 = ctx.adjust_raw(many, "tir", 1, overlap=2)
+    c1, b1 = ctx.adjust_raw(many, "tir", 1, overlap=2, cons_view=True)
+    assert c1.tobytes() == c0.tobytes() and b1.tobytes() == b0.tobytes() and len(b0) > len(cons0)
+
+
 def test_edge_cases(ctx, small):
     wl, G = small
     rng = np.random.default_rng(5)
