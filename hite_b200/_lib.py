@@ -91,6 +91,22 @@ def fmea_chain_files(hsps, q_off, segs, file_of_seg, skip_gap, max_len, threads=
     return out[:n.value]
 
 
+def debug_fmea_blocks(hsps, q_off, segs, file_of_seg, skip_gap, max_len, threads, n_blocks):
+    """Test hook (``hb_debug_fmea_blocks``): the chaining fed in ``n_blocks`` submissions of whole files."""
+    lib = load()
+    hsps = np.ascontiguousarray(hsps, dtype=HSP_DTYPE)
+    q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+    segs = np.ascontiguousarray(segs, dtype=SEG_DTYPE)
+    fos = np.ascontiguousarray(file_of_seg, dtype=np.uint32)
+    out = np.zeros(len(hsps) + 1, dtype=INTERVAL_DTYPE)
+    n = C.c_uint64(0)
+    rc = lib.hb_debug_fmea_blocks(_ptr(hsps), _ptr(q_off), len(segs), _ptr(segs), _ptr(fos), int(skip_gap), int(max_len), int(threads),
+                                  int(n_blocks), _ptr(out), len(out), C.byref(n))
+    if rc != 0:
+        raise HiteB200Error("hb_debug_fmea_blocks failed (%d)" % rc)
+    return out[:n.value]
+
+
 QCOPY_DTYPE = np.dtype([("subj", "<i4"), ("start", "<i4"), ("end", "<i4"), ("qlen", "<i4"), ("strand", "<i4")])
 
 
@@ -213,6 +229,7 @@ def load():
     lib.hb_last_hsps.argtypes = [vp, vp, C.c_uint64, u64p, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_full_length_copies.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.hb_fmea_chain_files.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint64, u64p]
+    lib.hb_debug_fmea_blocks.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, C.c_uint64, u64p]
     lib.hb_full_length_copies_batch.argtypes = [vp, vp, C.c_uint32, vp, C.c_double, C.c_int, vp, vp, C.c_uint64, u64p]
     lib.hb_query_copies_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                           C.c_uint64, u64p]

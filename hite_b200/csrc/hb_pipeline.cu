@@ -1038,6 +1038,31 @@ extern "C" int hb_fmea_chain(const hb_hsp* hsp, const uint64_t* q_off, uint32_t 
     return HB_OK;
 }
 
+extern "C" int hb_debug_fmea_blocks(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs,
+                                    const uint32_t* file_of_seg, int skip_gap, int max_len, int threads, uint32_t n_blocks,
+                                    hb_interval* out, uint64_t cap, uint64_t* n_out) {
+    if (!q_off || !segs || !n_out || !file_of_seg || !n_blocks || (n_seg && q_off[n_seg] && !hsp)) return HB_EINVAL;
+    for (uint32_t g = 1; g < n_seg; ++g) if (file_of_seg[g] < file_of_seg[g - 1]) return HB_EINVAL;
+    std::vector<uint32_t> first_seg;                                   // first segment of every file (+ n_seg)
+    for (uint32_t g = 0; g < n_seg; ++g) if (g == 0 || file_of_seg[g] != file_of_seg[g - 1]) first_seg.push_back(g);
+    const uint32_t nf = (uint32_t)first_seg.size();
+    first_seg.push_back(n_seg);
+    HbFmeaPool* pool = hb_fmea_pool_start(n_seg, segs, file_of_seg, skip_gap, max_len, threads);
+    std::vector<std::vector<uint64_t>> offs(n_blocks, std::vector<uint64_t>((size_t)n_seg + 1));
+    for (uint32_t b = 0; b < n_blocks; ++b) {                          // block b: whole files, the other segments empty
+        const uint32_t g_lo = first_seg[(size_t)((uint64_t)nf * b / n_blocks)], g_hi = first_seg[(size_t)((uint64_t)nf * (b + 1) / n_blocks)];
+        for (uint32_t g = 0; g <= n_seg; ++g) offs[b][g] = q_off[std::min(std::max(g, g_lo), g_hi)];
+        hb_fmea_pool_submit(pool, hsp, offs[b].data());
+    }
+    std::vector<hb_interval> res;
+    hb_fmea_pool_finish(pool, res, nullptr, nullptr);
+    *n_out = res.size();
+    if (!out) return HB_OK;
+    if (cap < res.size()) return HB_EINVAL;
+    if (!res.empty()) memcpy(out, res.data(), sizeof(hb_interval) * res.size());
+    return HB_OK;
+}
+
 extern "C" int hb_fmea_chain_files(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs,
                                    const uint32_t* file_of_seg, int skip_gap, int max_len, int threads, hb_interval* out,
                                    uint64_t cap, uint64_t* n_out) {

@@ -235,6 +235,11 @@ int hb_fmea_chain(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, cons
 int hb_fmea_chain_files(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs,
                         const uint32_t* file_of_seg, int skip_gap, int max_len, int threads, hb_interval* out,
                         uint64_t cap, uint64_t* n_out);
+/* Test hook: hb_fmea_chain_files with the files handed to the chaining pool in n_blocks separate submissions, the way
+ * hb_coarse_boundary hands over the blocks of its GPU pipeline; the result must not depend on n_blocks or on `threads`. */
+int hb_debug_fmea_blocks(const hb_hsp* hsp, const uint64_t* q_off, uint32_t n_seg, const hb_segment* segs,
+                         const uint32_t* file_of_seg, int skip_gap, int max_len, int threads, uint32_t n_blocks,
+                         hb_interval* out, uint64_t cap, uint64_t* n_out);
 
 /*
  * hb_query_copies -- get_query_copies (module/Util.py:6828-7030; used by judge_Other_transposons.py:45 through

@@ -458,6 +458,40 @@ def test_product_fmea_shares_state_inside_a_blast_file():
     assert [tuple(x) for x in same.tolist()] == [tuple(x) for x in solo.tolist()]
 
 
+def test_product_fmea_task_graph_is_independent_of_blocks_and_threads():
+    """The chaining runs as a task graph (group query -> chain (query, subject) pairs -> de-duplicate file) on one pool of host
+    threads and is fed block by block by the coarse stage's GPU pipeline.  Whatever the number of submissions and of threads --
+    including more threads than files and more blocks than files -- the intervals are the oracle's (hbo_fmea.c driven per file),
+    on a genome with shared files (contig tails) and several files per block."""
+    import numpy as np
+    from hite_b200 import _lib
+    from workloads import synth
+    from oracle import oracle as O
+    wl = synth.make_workload(genome_bp=7_500_000, n_contigs=3, n_families=30, cands_per_family=1, copies=(5, 16),
+                             length=(200, 1500), seed=41)
+    lens = [len(c) for c in wl.contig_seqs]
+    G = O.Genome(wl.contig_seqs)
+    hsps, segs, iv = G.coarse_boundary(lens, seg_len=1_000_000, skip_gap=2000, max_len=30000, occ_cap=64)
+    G.close()
+    files = O.split_file_groups([min(1_000_000, lens[c] - o) for c, o in segs])
+    assert len(set(files)) < len(segs) and len(iv) > 100          # tails share files; there is something to chain
+    h = np.asarray(hsps)
+    h = h[np.argsort(h[:, 0], kind="stable")]
+    q_off = np.searchsorted(h[:, 0], np.arange(len(segs) + 1)).astype(np.uint64)
+    hs = np.zeros(len(h), dtype=_lib.HSP_DTYPE)
+    for k, f in enumerate(("subj", "qs", "qe", "ss", "se")):
+        hs[f] = h[:, k + 1]
+    sg = np.zeros(len(segs), dtype=_lib.SEG_DTYPE)
+    sg["chr"] = [s[0] for s in segs]; sg["start"] = [s[1] for s in segs]
+    for n_blocks, threads in ((1, 1), (1, 7), (2, 3), (3, 16), (len(set(files)), 5), (64, 2)):
+        for _ in range(3):                                         # scheduling differs from run to run; the result must not
+            out = _lib.debug_fmea_blocks(hs, q_off, sg, files, 2000, 30000, threads, n_blocks)
+            assert [(int(o["chr"]), int(o["start"]), int(o["end"])) for o in out] == iv, (n_blocks, threads)
+    # no HSPs at all: nothing to do, nothing hangs
+    none = _lib.debug_fmea_blocks(hs[:0], np.zeros(len(segs) + 1, dtype=np.uint64), sg, files, 2000, 30000, 4, 3)
+    assert len(none) == 0
+
+
 def test_coarse_masking_leaves_border_crossing_copies(monkeypatch):
     """masking.mask_context(record_len=...): a full-length copy lying across a 1 Mbp record border is not masked, as in the
     reference, where the two halves are partial hits on two subject records (module/Util.py:4654 on chr$start records)."""
