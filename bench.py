@@ -464,7 +464,7 @@ def gpu_arm(args, config, scaling, n_steps, n_warmup, rank, world, local, cores,
             "n_gpus": world, "steps": n_steps, "warmup": n_warmup, "ms_per_step": dev_max / n_steps * 1e3,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": wname, "name": config, "genome_bp": wl.genome_bp, "candidates": n_total, "k": K_MM, "w": W_MM,
-                       "max_loci": 300, "band": "32 / 64 diagonals", "judges": kinds,
+                       "max_loci": 300, "band": "16 / 32 / 64 diagonals by cluster spread", "judges": kinds,
                        "mean_candidate_bp": float(np.mean(lens_all)), "repeat_bp": getattr(wl, "repeat_bp", None),
                        "l2": "inputs larger than L2 (packed genome+index %.0f MB, traceback stream %.1f GB/step)"
                        % ((info["total_padded"] * 0.375 + info["n_minimizers"] * 8) / 1e6, float(stage[7] / n_steps) * 1e6 * 16 / 1e9),
@@ -479,6 +479,7 @@ def gpu_arm(args, config, scaling, n_steps, n_warmup, rank, world, local, cores,
             "roofline": {"kernel": "extend16_kernel + traceback_kernel (banded SW, two pairs per lane; hb_extend16.cuh)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "wasted": (traffic / algo_bytes) if traffic else None, "traffic_source": tsrc,
+                         "alu_pipe_frac": (alu_pct / 100.0) if alu_pct else None, "gcups": dp_cells / ext_s_last / 1e9 if ext_s_last else None,
                          "algorithmic_bytes": algo_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "note": "integer-ALU-bound DP, not HBM-bound: %.2f GCUPS, ALU pipe %s %% of peak (ncu, profiles/); algorithmic "
