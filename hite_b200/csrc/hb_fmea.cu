@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -28,7 +29,7 @@
 
 namespace {
 
-struct Frag { int32_t qs, qe, ss, se; int32_t ord; };      // ord: position before the current sort (stable order)
+struct Frag { int32_t qs, qe, ss, se; };
 
 struct Chain { int32_t qs, qe, ss, se, subj; };
 
@@ -37,35 +38,32 @@ struct Pt { int32_t chr, da, db, used; };     // one stored point per interval o
 // Per-worker scratch, reused across work items: repeated large malloc/free from many threads serialises on
 // the kernel's address-space lock (mmap/munmap), which made the pool anti-scale.
 struct Scratch {
-    std::vector<Frag> sorted, cl, ctmp;
+    std::vector<Frag> sorted, cl;
     std::vector<uint64_t> keys, tmp;
     std::vector<char> used;
     std::vector<Chain> chains;
     std::vector<Pt> table;
 };
 
-// `c` is sorted in place; `keys` / `tmp` are scratch
-void chain_cluster(std::vector<Frag>& c, int skip_gap, int subj, std::vector<Chain>& out, std::vector<char>& used,
-                   std::vector<uint64_t>& keys, std::vector<Frag>& tmp) {
-    if (c.size() == 1) { out.push_back(Chain{c[0].qs, c[0].qe, c[0].ss, c[0].se, subj}); return; }   // the common case
+// `src[0 .. m)`: one cluster, a contiguous run of the strand in subject order; its (qs, qe)-sorted copy is built in `c`
+void chain_cluster(const Frag* src, size_t m, int skip_gap, int subj, std::vector<Chain>& out, std::vector<char>& used,
+                   std::vector<uint64_t>& keys, std::vector<Frag>& c) {
+    if (m == 1) { out.push_back(Chain{src[0].qs, src[0].qe, src[0].ss, src[0].se, subj}); return; }   // the common case
     {   // stable sort on (qs, qe) (:4231): one packed key per fragment when the coordinates fit, as in sort_strand
-        const size_t m = c.size();
         bool fits = m < (1u << 22);
         keys.resize(m);
         for (size_t i = 0; fits && i < m; ++i) {
-            const uint32_t qs = (uint32_t)c[i].qs, qe = (uint32_t)c[i].qe;
+            const uint32_t qs = (uint32_t)src[i].qs, qe = (uint32_t)src[i].qe;
             if ((qs | qe) >> 21) fits = false;
             keys[i] = (uint64_t)qs << 43 | (uint64_t)qe << 22 | (uint64_t)i;
         }
+        c.resize(m);
         if (fits) {
             std::sort(keys.begin(), keys.end());
-            tmp.assign(c.begin(), c.end());
-            for (size_t i = 0; i < m; ++i) c[i] = tmp[keys[i] & 0x3FFFFFu];
+            for (size_t i = 0; i < m; ++i) c[i] = src[keys[i] & 0x3FFFFFu];
         } else {
-            for (size_t i = 0; i < m; ++i) c[i].ord = (int32_t)i;
-            std::sort(c.begin(), c.end(), [](const Frag& a, const Frag& b) {
-                return a.qs != b.qs ? a.qs < b.qs : (a.qe != b.qe ? a.qe < b.qe : a.ord < b.ord);
-            });
+            for (size_t i = 0; i < m; ++i) c[i] = src[i];
+            std::stable_sort(c.begin(), c.end(), [](const Frag& a, const Frag& b) { return a.qs != b.qs ? a.qs < b.qs : a.qe < b.qe; });
         }
     }
     const size_t n = c.size();
@@ -145,38 +143,45 @@ void sort_strand(const Frag* f, size_t n, bool reverse, std::vector<Frag>& out, 
     }
     if (fits) {
         if (n < 192) std::sort(keys.begin(), keys.end());
-        else radix_sort_keys(keys, tmp, 22, 64);                    // stable: the file position in the low bits stays ordered
+        else {
+            // two counting passes on the subject start alone (stable), then the few runs of equal starts ordered on (end, file
+            // position) by the rest of the key
+            radix_sort_keys(keys, tmp, 43, 64);
+            for (size_t a = 0; a < n;) {
+                size_t b = a + 1;
+                while (b < n && (keys[b] >> 43) == (keys[a] >> 43)) ++b;
+                if (b - a > 1) std::sort(keys.begin() + (ptrdiff_t)a, keys.begin() + (ptrdiff_t)b);
+                a = b;
+            }
+        }
         for (size_t i = 0; i < n; ++i) out[i] = f[keys[i] & 0x3FFFFFu];
         return;
     }
-    for (size_t i = 0; i < n; ++i) { out[i] = f[i]; out[i].ord = (int32_t)i; }
+    for (size_t i = 0; i < n; ++i) out[i] = f[i];
     if (!reverse)
-        std::sort(out.begin(), out.begin() + (ptrdiff_t)n, [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : (a.se != b.se ? a.se < b.se : a.ord < b.ord); });
+        std::stable_sort(out.begin(), out.begin() + (ptrdiff_t)n, [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss < b.ss : a.se < b.se; });
     else
-        std::sort(out.begin(), out.begin() + (ptrdiff_t)n, [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : (a.se != b.se ? a.se > b.se : a.ord < b.ord); });
+        std::stable_sort(out.begin(), out.begin() + (ptrdiff_t)n, [](const Frag& a, const Frag& b) { return a.ss != b.ss ? a.ss > b.ss : a.se > b.se; });
 }
 
 // chains of one (query, subject) pair: forward clusters, then reverse clusters (module/Util.py:4162-4319).
 // `fw` / `rv`: the pair's HSPs of either strand in file order (:4168-4172).
 void chain_subject(const Frag* fw, size_t n_fw, const Frag* rv, size_t n_rv, int skip_gap, int subj, std::vector<Chain>& chains,
                    Scratch& S) {
-    std::vector<Frag>& cl = S.cl;
     for (int pass = 0; pass < 2; ++pass) {                                            // :4178-4227
         const size_t np = pass ? n_rv : n_fw;
         sort_strand(pass ? rv : fw, np, pass != 0, S.sorted, S.keys, S.tmp);
         const Frag* p = S.sorted.data();
-        cl.clear();
-        for (size_t k = 0; k < np; ++k) {
+        size_t k0 = 0;                                   // the open cluster is the run p[k0 .. k)
+        for (size_t k = 1; k < np; ++k) {
             bool closed = false;
-            if (k > 0)
-                for (size_t e = cl.size(); e-- > 0;) {
-                    const int gap = pass ? (cl[e].se - p[k].ss) : (p[k].ss - cl[e].se);
-                    if (gap < skip_gap && p[k].qe > cl[e].qe) { closed = true; break; }
-                }
-            if (k > 0 && !closed) { chain_cluster(cl, skip_gap, subj, chains, S.used, S.keys, S.ctmp); cl.clear(); }
-            cl.push_back(p[k]);
+            for (size_t e = k; e-- > k0;) {
+                const int gap = pass ? (p[e].se - p[k].ss) : (p[k].ss - p[e].se);
+                if (gap < skip_gap && p[k].qe > p[e].qe) { closed = true; break; }
+            }
+            if (!closed) { chain_cluster(p + k0, k - k0, skip_gap, subj, chains, S.used, S.keys, S.cl); k0 = k; }
         }
-        if (!cl.empty()) chain_cluster(cl, skip_gap, subj, chains, S.used, S.keys, S.ctmp);
+        if (np) chain_cluster(p + k0, np - k0, skip_gap, subj, chains, S.used, S.keys, S.cl);
     }
 }
 
@@ -211,7 +216,7 @@ void group_query(const hb_hsp* h, size_t n, int32_t q_index, QueryWork& w, uint3
     for (size_t i = 0; i < n; ++i) {
         const hb_hsp& x = h[i];
         if (skip(x)) continue;
-        w.frags[cur[2 * (size_t)slot[x.subj] + (x.ss > x.se ? 1 : 0)]++] = Frag{x.qs, x.qe, x.ss, x.se, 0};
+        w.frags[cur[2 * (size_t)slot[x.subj] + (x.ss > x.se ? 1 : 0)]++] = Frag{x.qs, x.qe, x.ss, x.se};
     }
     w.chains.resize(w.order.size());
 }
@@ -285,11 +290,32 @@ void dedup_query(const QueryWork& w, const hb_segment& q, int32_t q_index, const
     // >= 95 % overlap merge, longest first (module/Util.py:4529-4549): interval i removes every later (not longer) interval j
     // with overlap / len_j >= 0.95.  Such a j starts inside [a_i - 0.05 len_j, b_i), so only the intervals whose start lies in
     // [a_i - 0.06 len_i - 1, b_i) are looked at (found in a start-sorted index) -- the predicate itself is unchanged.
-    std::stable_sort(names.begin(), names.end(), [](const Iv& x, const Iv& y) { return (x.b - x.a) > (y.b - y.a); });
+    // both orders through packed 64-bit keys (value, position) when the values fit -- they do: lengths are below max_len and the
+    // starts lie inside one query segment
     const size_t nn = names.size();
+    std::vector<uint64_t>& keys = S.keys;
+    int64_t a_min = INT64_MAX, a_max = INT64_MIN, len_max = 0;
+    for (const Iv& x : names) { a_min = std::min(a_min, x.a); a_max = std::max(a_max, x.a); len_max = std::max(len_max, x.b - x.a); }
+    const bool packed = nn > 1 && nn < (1u << 24) && len_max < (1ll << 39) && a_max - a_min < (1ll << 39);
+    if (packed) {
+        keys.resize(nn);
+        for (size_t i = 0; i < nn; ++i) keys[i] = (uint64_t)(len_max - (names[i].b - names[i].a)) << 24 | (uint64_t)i;
+        std::sort(keys.begin(), keys.end());                                    // longest first, ties in visiting order
+        std::vector<Iv> sorted(nn);
+        for (size_t i = 0; i < nn; ++i) sorted[i] = names[keys[i] & 0xFFFFFFu];
+        names.swap(sorted);
+    } else {
+        std::stable_sort(names.begin(), names.end(), [](const Iv& x, const Iv& y) { return (x.b - x.a) > (y.b - y.a); });
+    }
     std::vector<uint32_t> by_start(nn);
-    for (size_t i = 0; i < nn; ++i) by_start[i] = (uint32_t)i;
-    std::sort(by_start.begin(), by_start.end(), [&](uint32_t x, uint32_t y) { return names[x].a != names[y].a ? names[x].a < names[y].a : x < y; });
+    if (packed) {
+        for (size_t i = 0; i < nn; ++i) keys[i] = (uint64_t)(names[i].a - a_min) << 24 | (uint64_t)i;
+        std::sort(keys.begin(), keys.end());
+        for (size_t i = 0; i < nn; ++i) by_start[i] = (uint32_t)(keys[i] & 0xFFFFFFu);
+    } else {
+        for (size_t i = 0; i < nn; ++i) by_start[i] = (uint32_t)i;
+        std::sort(by_start.begin(), by_start.end(), [&](uint32_t x, uint32_t y) { return names[x].a != names[y].a ? names[x].a < names[y].a : x < y; });
+    }
     std::vector<char> keep(nn, 1);
     for (size_t i = 0; i < nn; ++i) {
         if (!keep[i]) continue;
