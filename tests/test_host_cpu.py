@@ -492,6 +492,35 @@ def test_product_fmea_task_graph_is_independent_of_blocks_and_threads():
     assert len(none) == 0
 
 
+def test_product_fmea_long_segments_take_the_comparison_sorts():
+    """The chaining orders fragments through packed 64-bit keys while segment coordinates fit 21 bits (the default 1 Mbp
+    segments do) and through comparison sorts beyond that.  `chrom_seg_length` is a user option (main.py:41): with 3 Mbp
+    segments most coordinates are past 2^21 and the result must still be the oracle's."""
+    import numpy as np
+    from hite_b200 import _lib
+    from workloads import synth
+    from oracle import oracle as O
+    wl = synth.make_workload(genome_bp=7_500_000, n_contigs=2, n_families=30, cands_per_family=1, copies=(5, 16),
+                             length=(200, 1500), seed=43)
+    lens = [len(c) for c in wl.contig_seqs]
+    G = O.Genome(wl.contig_seqs)
+    hsps, segs, iv = G.coarse_boundary(lens, seg_len=3_000_000, skip_gap=2000, max_len=30000, occ_cap=64)
+    G.close()
+    h = np.asarray(hsps)
+    assert (h[:, 2:] >= (1 << 21)).any() and len(iv) > 100          # coordinates past the packed-key range, work to do
+    files = O.split_file_groups([min(3_000_000, lens[c] - o) for c, o in segs])
+    h = h[np.argsort(h[:, 0], kind="stable")]
+    q_off = np.searchsorted(h[:, 0], np.arange(len(segs) + 1)).astype(np.uint64)
+    hs = np.zeros(len(h), dtype=_lib.HSP_DTYPE)
+    for k, f in enumerate(("subj", "qs", "qe", "ss", "se")):
+        hs[f] = h[:, k + 1]
+    sg = np.zeros(len(segs), dtype=_lib.SEG_DTYPE)
+    sg["chr"] = [s[0] for s in segs]; sg["start"] = [s[1] for s in segs]
+    for threads in (1, 5):
+        out = _lib.fmea_chain_files(hs, q_off, sg, files, 2000, 30000, threads=threads)
+        assert [(int(o["chr"]), int(o["start"]), int(o["end"])) for o in out] == iv
+
+
 def test_coarse_masking_leaves_border_crossing_copies(monkeypatch):
     """masking.mask_context(record_len=...): a full-length copy lying across a 1 Mbp record border is not masked, as in the
     reference, where the two halves are partial hits on two subject records (module/Util.py:4654 on chr$start records)."""
