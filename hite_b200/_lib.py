@@ -356,6 +356,11 @@ class Context:
                 for x in contig_seqs]
         off = np.zeros(len(seqs) + 1, dtype=np.uint64)
         off[1:] = np.cumsum([len(x) for x in seqs])
+        padded = int(off[-1]) + 64 * (len(seqs) + 2)
+        if padded >= (1 << 32):                               # checked before 4 GB are concatenated and shipped
+            raise HiteB200Error("hb_genome_load: %d bp in %d contigs do not fit the index's 32-bit positions (limit 2^32 bp including the "
+                                "64 N between contigs); run the stage per genome chunk (HiTE --chunk_size, default 400 MB) or on a subset "
+                                "of the contigs" % (int(off[-1]), len(seqs)))
         flat = np.concatenate(seqs) if len(seqs) > 1 else np.ascontiguousarray(seqs[0])
         self._check(self._lib.hb_genome_load(self._h, _ptr(flat), _ptr(off), len(seqs)), "hb_genome_load")
         self.contig_lens = [len(x) for x in seqs]

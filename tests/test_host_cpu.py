@@ -425,6 +425,28 @@ def test_other_and_masking_host_logic_with_fake_context():
     assert [c[:3] for c in other.copies_from_records(rec, ["big"], big, f.contig_names)["big"]] == [("chr1", 1, 70000)]
 
 
+def test_genomes_past_the_32_bit_position_space_are_refused_early():
+    """2^32 bp and more cannot be indexed (32-bit positions in the keys); the wrapper says so before it concatenates and
+    ships the bases -- no device, no library call involved."""
+    import numpy as np
+    import pytest as _pytest
+    import hite_b200
+    from hite_b200 import _lib
+
+    class Big:                                   # stands for a 1.5 Gbp contig without holding it
+        def __init__(self, n): self.n = n
+        def __len__(self): return self.n
+
+    ctx = object.__new__(_lib.Context)
+    real_asarray = np.asarray
+    try:
+        np.asarray = lambda x, dtype=None: x if isinstance(x, Big) else real_asarray(x, dtype=dtype)
+        with _pytest.raises(hite_b200.HiteB200Error, match="32-bit positions"):
+            _lib.Context.load_genome(ctx, [Big(1_500_000_000)] * 3)
+    finally:
+        np.asarray = real_asarray
+
+
 def test_product_fmea_shares_state_inside_a_blast_file():
     """A contig's short tail segment shares its BLAST result file -- and FMEA's de-duplication dicts -- with the records that
     follow it (reference split_and_store_sequences module/Util.py:4987, chr_pos_candidates :4155).  Product host code
