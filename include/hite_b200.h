@@ -296,6 +296,10 @@ int hb_coarse_boundary(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, 
  * [F * part / n_parts, F * (part + 1) / n_parts).  Only the minimizers of those segments are paired (against the whole index) and
  * chained; the parts' interval lists concatenated in part order are exactly hb_coarse_boundary's list.  out = NULL (or a
  * short buffer) still runs the stage and keeps the result in the context: fetch it with hb_last_intervals, no second run.
+ * Inside a part the files go through the GPU in up to 8 blocks, software-pipelined with the host chaining of the blocks already
+ * read back; the result does not depend on the block count (test hook: the environment variable HB_COARSE_BLOCKS forces it).
+ * Timing: k_ms[0] seed pairs, [1] sort, [2] runs + base-level HSPs, [3] host FMEA span (first block handed over -> last task
+ * done), [4] wall of the pipelined stage, [5] FMEA task time per host thread, [6] #HSPs, [7] million seed pairs.
  */
 int hb_coarse_boundary_part(hb_ctx* ctx, int64_t seg_len, int skip_gap, int max_len, int occ_cap, int threads,
                             uint32_t part, uint32_t n_parts, hb_interval* out, uint64_t cap, uint64_t* n_out);
